@@ -1,0 +1,99 @@
+// common.cuh — process-wide context, error plumbing and warp helpers of libbpk.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+#include "../../include/bpk.h"
+
+struct BpkCtx {
+    bool ready = false;
+    int device = -1;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaMemPool_t pool = nullptr;
+    int *d_flag = nullptr;          // device status word set by kernels (non-SPD, domain)
+    int *h_flag = nullptr;          // pinned mirror
+    double *scratch = nullptr;      // reduction partials
+    size_t scratch_bytes = 0;
+    void *l2buf = nullptr;          // > L2 sized buffer for bpk_flush_l2
+    size_t l2bytes = 0;
+    uint64_t launches = 0;
+    char err[512] = {0};
+};
+
+extern BpkCtx g_bpk;
+
+int bpk_set_error(int code, const char *fmt, ...);
+int bpk_check_flag(int what_if_set);    // sync + read d_flag, clear it
+double *bpk_scratch(size_t bytes);      // stream-ordered scratch (grown on demand)
+
+#define BPK_REQUIRE_INIT()                                                      \
+    do {                                                                        \
+        if (!g_bpk.ready)                                                       \
+            return bpk_set_error(BPK_ENOGPU, "bpk_init() has not succeeded: no CUDA device bound"); \
+    } while (0)
+
+#define BPK_CUDA(call)                                                          \
+    do {                                                                        \
+        cudaError_t e_ = (call);                                                \
+        if (e_ != cudaSuccess)                                                  \
+            return bpk_set_error(BPK_ECUDA, "%s failed: %s (%s:%d)", #call,     \
+                                 cudaGetErrorString(e_), __FILE__, __LINE__);   \
+    } while (0)
+
+// every kernel launch goes through this so bpk_launch_count() is honest
+#define BPK_LAUNCH(kernel, grid, block, smem, ...)                              \
+    do {                                                                        \
+        kernel<<<(grid), (block), (smem), g_bpk.stream>>>(__VA_ARGS__);         \
+        g_bpk.launches++;                                                       \
+        cudaError_t e_ = cudaPeekAtLastError();                                 \
+        if (e_ != cudaSuccess)                                                  \
+            return bpk_set_error(BPK_ECUDA, "launch of %s failed: %s (%s:%d)",  \
+                                 #kernel, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+#define BPK_FLAG_NOTSPD 1
+#define BPK_FLAG_DOMAIN 2
+
+// ---- device helpers -------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// psi(x), fp64, |err| ~ 1e-15 for x > 0 (recurrence up to x >= 10, then the
+// asymptotic series); reflection for x <= 0.  Matches scipy.special.psi to
+// ~1e-14 relative away from the root at 1.4616.
+__device__ __forceinline__ double bpk_digamma(double x) {
+    double r = 0.0;
+    if (x <= 0.0) {
+        if (x == floor(x)) return nan("");
+        // psi(1-x) - psi(x) = pi cot(pi x)
+        r = -M_PI / tan(M_PI * x);
+        x = 1.0 - x;
+    }
+    while (x < 10.0) { r -= 1.0 / x; x += 1.0; }
+    double xi = 1.0 / x, x2 = xi * xi;
+    // B2k/(2k): 1/12, -1/120, 1/252, -1/240, 1/132, -691/32760, 1/12
+    double s = x2 * (1.0 / 12.0 - x2 * (1.0 / 120.0 - x2 * (1.0 / 252.0 - x2 * (1.0 / 240.0
+               - x2 * (1.0 / 132.0 - x2 * (691.0 / 32760.0 - x2 * (1.0 / 12.0)))))));
+    return r + log(x) - 0.5 * xi - s;
+}
+__device__ __forceinline__ double bpk_mvdigamma(double a, int d) {
+    double s = 0.0;
+    for (int i = 0; i < d; ++i) s += bpk_digamma(a - 0.5 * i);
+    return s;
+}
+__device__ __forceinline__ double bpk_mvlgamma(double a, int d) {
+    // scipy.special.multigammaln: d(d-1)/4 log(pi) + sum_j lgamma(a - j/2)
+    double s = d * (d - 1) * 0.25 * 1.1447298858494001741434;
+    for (int j = 0; j < d; ++j) s += lgamma(a - 0.5 * j);
+    return s;
+}

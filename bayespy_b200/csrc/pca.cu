@@ -1,0 +1,382 @@
+// pca.cu — the fused one-pass sweep of the plated Gaussian factor model
+//   y[m,n] ~ N(w_m . x_n, 1/tau)      (Bayesian PCA)
+//
+// Reference path being replaced (per VB sweep, all Python/NumPy):
+//   X.update():   dot.py:581 einsum messages -> gaussian.py:672-706 moments
+//   C.update():   dot.py:581 again with the roles swapped (sum over n)
+//   tau.update(): dot.py:355,403 <f>,<f^2> over (M,N) -> gaussian.py:2361-2369
+//   bound:        expfamily.py:400-480 over (M,N) again
+// Here: ONE pass over Y per sweep.  For every column n
+//   x_n = A y_n + b                       (A = tau Cov_x <W>^T, K x M)
+// is written out, and the plate-summed sufficient statistics that every other
+// node of the model needs (the einsum reductions over n of dot.py:581 and
+// the <f>,<f^2> sums of dot.py:355,403) are accumulated on the fly:
+//   S_yx = sum_n y_n x_n^T (M x K),  S_xx = sum_n x_n x_n^T (K x K),  s_x = sum_n x_n.
+// Algorithmic traffic: M*8 B read + K*8 B written per column (640 B at 64x16).
+//
+// Mapping (sm_100a): persistent grid of one 256-thread CTA per SM; Y tiles of
+// 64 x T doubles stream through a cp.async ring in shared memory (padded pitch
+// T+4 -> conflict-free fragment reads); both GEMM-shaped contractions run on
+// the fp64 tensor pipe with mma.sync.m8n8k4.f64 (tcgen05 has no fp64 kind);
+// A lives in registers as 32 fragments for the whole kernel; each warp owns
+// NT columns of a tile and a private S_yx/S_xx accumulator set in registers;
+// partials are reduced warp->CTA in smem and CTA->grid by a second tiny
+// kernel in a fixed order (deterministic, no atomics).
+#include "common.cuh"
+
+#define PCA_MP 64      // padded M
+#define PCA_KP 16      // padded K
+#define PCA_WARPS 8
+#define PCA_LDX 20     // pitch of the per-warp X staging tile
+#define PCA_NSTAT (PCA_MP * PCA_KP + PCA_KP * PCA_KP + PCA_KP)
+
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async16(void *smem, const void *g, int src_bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(g), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *smem, const void *g, int src_bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(g), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+template <int NT, bool ALIGN16>
+__device__ __forceinline__ void pca_issue_tile(double *Ys, const double *__restrict__ Y, int64_t M, int64_t N,
+                                               int64_t n0) {
+    constexpr int T = PCA_WARPS * NT, LDY = T + 4;
+    if (ALIGN16) {
+        constexpr int CH = T / 2;   // 16-byte chunks per row
+        for (int e = threadIdx.x; e < (int)M * CH; e += PCA_WARPS * 32) {
+            int m = e / CH, c = e - m * CH;
+            int64_t n = n0 + 2 * c;
+            const double *src = Y + (int64_t)m * N + (n < N ? n : 0);
+            cp_async16(Ys + m * LDY + 2 * c, src, n < N ? 16 : 0);
+        }
+    } else {
+        for (int e = threadIdx.x; e < (int)M * T; e += PCA_WARPS * 32) {
+            int m = e / T, c = e - m * T;
+            int64_t n = n0 + c;
+            const double *src = Y + (int64_t)m * N + (n < N ? n : 0);
+            cp_async8(Ys + m * LDY + c, src, n < N ? 8 : 0);
+        }
+    }
+}
+
+template <int NT, int STAGES, bool ALIGN16, bool COMPUTE_X>
+__global__ void __launch_bounds__(PCA_WARPS * 32, 1)
+pca_xsweep_kernel(const double *__restrict__ Y, int64_t M, int64_t N, int K,
+                  const double *__restrict__ A, const double *__restrict__ bvec,
+                  double *__restrict__ X, double *__restrict__ partial, int64_t ntiles) {
+    constexpr int T = PCA_WARPS * NT, LDY = T + 4, CB = NT / 8, NS = NT / 4;
+    extern __shared__ __align__(16) double smem[];
+    double *Ysm = smem;                                            // [STAGES][64][LDY]
+    double *Xsm = smem + (size_t)STAGES * PCA_MP * LDY;            // [WARPS][NT][LDX]
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int gr = lane >> 2, tg = lane & 3;                       // mma groupID / threadID_in_group
+    double *Xs = Xsm + (size_t)w * NT * PCA_LDX;
+
+    // zero the whole ring once: padded rows m >= M stay zero for the kernel's lifetime
+    for (int e = threadIdx.x; e < STAGES * PCA_MP * LDY; e += PCA_WARPS * 32) Ysm[e] = 0.0;
+    __syncthreads();
+
+    // A fragments (row-major 8x4 blocks of the K x M matrix), zero padded
+    double afrag[2][16];
+    if (COMPUTE_X) {
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+            for (int ms = 0; ms < 16; ++ms) {
+                int k = kb * 8 + gr, m = ms * 4 + tg;
+                afrag[kb][ms] = (k < K && m < M) ? A[(int64_t)k * M + m] : 0.0;
+            }
+    }
+    double bk[2] = {0.0, 0.0};
+    if (COMPUTE_X && bvec) {
+        if (gr < K) bk[0] = bvec[gr];
+        if (8 + gr < K) bk[1] = bvec[8 + gr];
+    }
+
+    double syx[8][2][2];   // [mb][kb][j]
+    double sxx[3][2];      // blocks (0,0),(0,1),(1,1)
+    double sx = 0.0;       // lanes 0..15: sum_n x[n][lane]
+#pragma unroll
+    for (int mb = 0; mb < 8; ++mb)
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) syx[mb][kb][0] = syx[mb][kb][1] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) sxx[i][0] = sxx[i][1] = 0.0;
+
+    // prologue: STAGES-1 tiles in flight
+    const int64_t first = blockIdx.x, stride = gridDim.x;
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        int64_t t = first + (int64_t)s * stride;
+        if (t < ntiles) pca_issue_tile<NT, ALIGN16>(Ysm + (size_t)s * PCA_MP * LDY, Y, M, N, t * T);
+        cp_async_commit();
+    }
+
+    int it = 0;
+    for (int64_t tile = first; tile < ntiles; tile += stride, ++it) {
+        {   // keep the ring full
+            int64_t tn = tile + (int64_t)(STAGES - 1) * stride;
+            if (tn < ntiles)
+                pca_issue_tile<NT, ALIGN16>(Ysm + (size_t)((it + STAGES - 1) % STAGES) * PCA_MP * LDY, Y, M, N, tn * T);
+            cp_async_commit();
+        }
+        cp_async_wait<STAGES - 1>();
+        __syncthreads();
+        const double *Ys = Ysm + (size_t)(it % STAGES) * PCA_MP * LDY;
+        const int c0 = w * NT;                     // this warp's first column within the tile
+        const int64_t nbase = tile * T + c0;       // global column of Xs row 0
+
+        if (COMPUTE_X) {
+            double acc[2][CB][2];
+#pragma unroll
+            for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                for (int cb = 0; cb < CB; ++cb) acc[kb][cb][0] = acc[kb][cb][1] = bk[kb];
+#pragma unroll
+            for (int ms = 0; ms < 16; ++ms) {
+#pragma unroll
+                for (int cb = 0; cb < CB; ++cb) {
+                    double yb = Ys[(ms * 4 + tg) * LDY + c0 + cb * 8 + gr];
+                    dmma884(acc[0][cb][0], acc[0][cb][1], afrag[0][ms], yb);
+                    dmma884(acc[1][cb][0], acc[1][cb][1], afrag[1][ms], yb);
+                }
+            }
+            // stage x (zeroed beyond N so that padded columns add nothing to the statistics)
+#pragma unroll
+            for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                for (int cb = 0; cb < CB; ++cb)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        int nl = cb * 8 + 2 * tg + j;
+                        double v = (nbase + nl < N) ? acc[kb][cb][j] : 0.0;
+                        Xs[nl * PCA_LDX + kb * 8 + gr] = v;
+                    }
+            __syncwarp();
+            // coalesced store of the NT x K block
+            for (int e = lane; e < NT * K; e += 32) {
+                int nl = e / K, k = e - nl * K;
+                if (nbase + nl < N) X[(nbase + nl) * K + k] = Xs[nl * PCA_LDX + k];
+            }
+        } else {
+            for (int e = lane; e < NT * PCA_KP; e += 32) {
+                int nl = e >> 4, k = e & 15;
+                Xs[nl * PCA_LDX + k] = (nbase + nl < N && k < K) ? X[(nbase + nl) * K + k] : 0.0;
+            }
+            __syncwarp();
+        }
+
+        if (lane < PCA_KP) {
+#pragma unroll
+            for (int nl = 0; nl < NT; ++nl) sx += Xs[nl * PCA_LDX + lane];
+        }
+
+#pragma unroll
+        for (int ns = 0; ns < NS; ++ns) {
+            double xf0 = Xs[(ns * 4 + tg) * PCA_LDX + gr];
+            double xf1 = Xs[(ns * 4 + tg) * PCA_LDX + 8 + gr];
+#pragma unroll
+            for (int mb = 0; mb < 8; ++mb) {
+                double ya = Ys[(mb * 8 + gr) * LDY + c0 + ns * 4 + tg];
+                dmma884(syx[mb][0][0], syx[mb][0][1], ya, xf0);
+                dmma884(syx[mb][1][0], syx[mb][1][1], ya, xf1);
+            }
+            dmma884(sxx[0][0], sxx[0][1], xf0, xf0);
+            dmma884(sxx[1][0], sxx[1][1], xf0, xf1);
+            dmma884(sxx[2][0], sxx[2][1], xf1, xf1);
+        }
+        __syncthreads();   // everyone is done with this stage before it is refilled
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+
+    // ---- warp -> CTA reduction through smem (reuses the ring) ----
+    double *red = smem;    // [WARPS][NSTAT]
+    double *mine = red + (size_t)w * PCA_NSTAT;
+#pragma unroll
+    for (int mb = 0; mb < 8; ++mb)
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                mine[(mb * 8 + gr) * PCA_KP + kb * 8 + 2 * tg + j] = syx[mb][kb][j];
+    double *mxx = mine + PCA_MP * PCA_KP;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        mxx[gr * PCA_KP + 2 * tg + j] = sxx[0][j];
+        mxx[gr * PCA_KP + 8 + 2 * tg + j] = sxx[1][j];
+        mxx[(8 + 2 * tg + j) * PCA_KP + gr] = sxx[1][j];      // symmetric block
+        mxx[(8 + gr) * PCA_KP + 8 + 2 * tg + j] = sxx[2][j];
+    }
+    if (lane < PCA_KP) mine[PCA_MP * PCA_KP + PCA_KP * PCA_KP + lane] = sx;
+    __syncthreads();
+    double *pout = partial + (size_t)blockIdx.x * PCA_NSTAT;
+    for (int e = threadIdx.x; e < PCA_NSTAT; e += PCA_WARPS * 32) {
+        double s = 0.0;
+#pragma unroll
+        for (int ww = 0; ww < PCA_WARPS; ++ww) s += red[(size_t)ww * PCA_NSTAT + e];
+        pout[e] = s;
+    }
+}
+
+// grid-level reduction of the per-CTA partials into the caller's (unpadded) stats
+__global__ void pca_stats_final_kernel(const double *__restrict__ partial, int nblocks, int M, int K,
+                                       double *__restrict__ stats) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    int total = M * K + K * K + K;
+    if (e >= total) return;
+    int pe;
+    if (e < M * K) { int m = e / K, k = e - m * K; pe = m * PCA_KP + k; }
+    else if (e < M * K + K * K) { int r = e - M * K; int i = r / K, j = r - i * K; pe = PCA_MP * PCA_KP + i * PCA_KP + j; }
+    else { pe = PCA_MP * PCA_KP + PCA_KP * PCA_KP + (e - M * K - K * K); }
+    double s = 0.0;
+    for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * PCA_NSTAT + pe];
+    stats[e] += s;
+}
+
+template <int NT, int STAGES, bool COMPUTE_X>
+static int pca_launch(const double *Y, int64_t M, int64_t N, int K, const double *A, const double *b,
+                      double *X, double *stats) {
+    constexpr int T = PCA_WARPS * NT, LDY = T + 4;
+    size_t ring = (size_t)STAGES * PCA_MP * LDY * sizeof(double);
+    size_t xs = (size_t)PCA_WARPS * NT * PCA_LDX * sizeof(double);
+    size_t redb = (size_t)PCA_WARPS * PCA_NSTAT * sizeof(double);
+    size_t smem = ring + xs;
+    if (smem < redb) smem = redb;
+    int64_t ntiles = (N + T - 1) / T;
+    int grid = g_bpk.sm_count;
+    if (ntiles < grid) grid = (int)ntiles;
+    double *partial = bpk_scratch((size_t)grid * PCA_NSTAT * sizeof(double));
+    if (!partial) return bpk_set_error(BPK_ECUDA, "pca: scratch allocation failed");
+    bool al = (N % 2 == 0) && (((uintptr_t)Y & 15u) == 0);
+    if (al) {
+        auto kern = pca_xsweep_kernel<NT, STAGES, true, COMPUTE_X>;
+        BPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        BPK_LAUNCH(kern, grid, PCA_WARPS * 32, smem, Y, M, N, K, A, b, X, partial, ntiles);
+    } else {
+        auto kern = pca_xsweep_kernel<NT, STAGES, false, COMPUTE_X>;
+        BPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        BPK_LAUNCH(kern, grid, PCA_WARPS * 32, smem, Y, M, N, K, A, b, X, partial, ntiles);
+    }
+    int total = (int)(M * K + K * K + K);
+    BPK_LAUNCH(pca_stats_final_kernel, (total + 127) / 128, 128, 0, partial, grid, (int)M, K, stats);
+    return BPK_OK;
+}
+
+// ---- generic shapes (M > 64 or K > 16): plain kernels, not roofline-tuned -----------
+__global__ void pca_x_generic_kernel(const double *__restrict__ Y, int64_t M, int64_t N, int K,
+                                     const double *__restrict__ A, const double *__restrict__ b,
+                                     double *__restrict__ X) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; e < N * K; e += (int64_t)gridDim.x * blockDim.x) {
+        int64_t n = e / K;
+        int k = (int)(e - n * K);
+        double s = b ? b[k] : 0.0;
+        for (int64_t m = 0; m < M; ++m) s += A[(int64_t)k * M + m] * Y[m * N + n];
+        X[e] = s;
+    }
+}
+
+static int pca_stats_generic(const double *Y, int64_t M, int64_t N, int K, const double *X, double *stats) {
+    // S_yx[m,k] += sum_n Y[m,n] X[n,k] ; S_xx[i,j] += sum_n X[n,i] X[n,j] ; s_x[k] += sum_n X[n,k]
+    const void *in[2];
+    int dt[2] = {BPK_F64, BPK_F64};
+    {
+        int64_t shape[3] = {M, N, K};
+        int64_t is[6] = {N, 1, 0, 0, K, 1};
+        int64_t os[3] = {K, 0, 1};
+        in[0] = Y; in[1] = X;
+        int rc = bpk_sum_multiply(3, shape, 2, in, dt, is, stats, os, 1.0, 1);
+        if (rc) return rc;
+    }
+    {
+        int64_t shape[3] = {N, K, K};
+        int64_t is[6] = {K, 1, 0, K, 0, 1};
+        int64_t os[3] = {0, K, 1};
+        in[0] = X; in[1] = X;
+        int rc = bpk_sum_multiply(3, shape, 2, in, dt, is, stats + M * K, os, 1.0, 1);
+        if (rc) return rc;
+    }
+    {
+        int64_t shape[2] = {N, K};
+        int64_t is[2] = {K, 1};
+        int64_t os[2] = {0, 1};
+        in[0] = X;
+        int rc = bpk_sum_multiply(2, shape, 1, in, dt, is, stats + M * K + (int64_t)K * K, os, 1.0, 1);
+        if (rc) return rc;
+    }
+    return BPK_OK;
+}
+
+extern "C" int bpk_pca_xsweep(const double *Y, int64_t M, int64_t N, int K,
+                              const double *A, const double *b, double *X, double *stats) {
+    BPK_REQUIRE_INIT();
+    if (M < 1 || K < 1 || N < 0) return bpk_set_error(BPK_EINVAL, "bpk_pca_xsweep: bad shape");
+    if (N == 0) return BPK_OK;
+    if (M <= PCA_MP && K <= PCA_KP) return pca_launch<16, 2, true>(Y, M, N, K, A, b, X, stats);
+    int64_t blocks = (N * K + 255) / 256;
+    int64_t cap = (int64_t)g_bpk.sm_count * 32;
+    if (blocks > cap) blocks = cap;
+    BPK_LAUNCH(pca_x_generic_kernel, (unsigned)blocks, 256, 0, Y, M, N, K, A, b, X);
+    return pca_stats_generic(Y, M, N, K, X, stats);
+}
+
+extern "C" int bpk_pca_stats(const double *Y, int64_t M, int64_t N, int K, const double *X, double *stats) {
+    BPK_REQUIRE_INIT();
+    if (M < 1 || K < 1 || N < 0) return bpk_set_error(BPK_EINVAL, "bpk_pca_stats: bad shape");
+    if (N == 0) return BPK_OK;
+    if (M <= PCA_MP && K <= PCA_KP)
+        return pca_launch<16, 2, false>(Y, M, N, K, nullptr, nullptr, const_cast<double *>(X), stats);
+    return pca_stats_generic(Y, M, N, K, X, stats);
+}
+
+// ---- sum y^2 / count of observed entries (constant of the tau update) ---------------
+__global__ void __launch_bounds__(256) sumsq_kernel(const double *__restrict__ Y, const uint8_t *__restrict__ mask,
+                                                    int64_t count, double *__restrict__ partial) {
+    double s = 0.0, c = 0.0;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+        double y = Y[i];
+        if (!mask || mask[i]) { s += y * y; c += 1.0; }
+    }
+    __shared__ double rs[8], rc[8];
+    s = warp_sum(s); c = warp_sum(c);
+    int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { rs[w] = s; rc[w] = c; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int k = 0; k < 8; ++k) { a += rs[k]; b += rc[k]; }
+        partial[2 * blockIdx.x] = a;
+        partial[2 * blockIdx.x + 1] = b;
+    }
+}
+__global__ void sumsq_final_kernel(const double *__restrict__ partial, int nblocks, double *__restrict__ out2) {
+    if (threadIdx.x < 2) {
+        double s = 0.0;
+        for (int b = 0; b < nblocks; ++b) s += partial[2 * b + threadIdx.x];
+        out2[threadIdx.x] = s;
+    }
+}
+extern "C" int bpk_sumsq(const double *Y, const uint8_t *mask, int64_t count, double *out2) {
+    BPK_REQUIRE_INIT();
+    int64_t blocks = (count + 255) / 256;
+    int64_t cap = (int64_t)g_bpk.sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    double *partial = bpk_scratch((size_t)blocks * 2 * sizeof(double));
+    if (!partial) return bpk_set_error(BPK_ECUDA, "sumsq: scratch allocation failed");
+    BPK_LAUNCH(sumsq_kernel, (unsigned)blocks, 256, 0, Y, mask, count, partial);
+    BPK_LAUNCH(sumsq_final_kernel, 1, 32, 0, partial, (int)blocks, out2);
+    return BPK_OK;
+}

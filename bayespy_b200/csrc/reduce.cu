@@ -1,0 +1,237 @@
+// reduce.cu — bpk_sum_multiply: sum over chosen axes of the product of up to
+// four broadcast operands (the restricted einsum of bayespy/utils/misc.py:851
+// and the masked plate-sum of nodes/node.py:650).  Deterministic: fixed
+// reduction trees, no atomics.
+#include "common.cuh"
+#include <string.h>
+
+struct SmArgs {
+    int n_in, nk, ns;
+    int64_t n_kept, n_sum;
+    int64_t kshape[BPK_MAXD], sshape[BPK_MAXD];
+    int64_t kout[BPK_MAXD];
+    int64_t kin[BPK_MAXIN][BPK_MAXD], sin[BPK_MAXIN][BPK_MAXD];
+    const void *in[BPK_MAXIN];
+    int dtype[BPK_MAXIN];
+    double *out;
+    double scale;
+    int accumulate;
+    int nsplit;
+    int64_t chunk;
+    double *partial;
+};
+
+__device__ __forceinline__ double sm_load(const void *p, int dtype, int64_t off) {
+    return dtype == BPK_U8 ? (double)((const uint8_t *)p)[off] : ((const double *)p)[off];
+}
+
+__device__ __forceinline__ void sm_decode_kept(const SmArgs &A, int64_t o, int64_t &oo, int64_t base[BPK_MAXIN]) {
+    oo = 0;
+#pragma unroll
+    for (int k = 0; k < BPK_MAXIN; ++k) base[k] = 0;
+    int64_t rem = o;
+    for (int d = A.nk - 1; d >= 0; --d) {
+        int64_t q = rem / A.kshape[d];
+        int64_t r = rem - q * A.kshape[d];
+        rem = q;
+        oo += r * A.kout[d];
+#pragma unroll
+        for (int k = 0; k < BPK_MAXIN; ++k)
+            if (k < A.n_in) base[k] += r * A.kin[k][d];
+    }
+}
+
+__device__ __forceinline__ double sm_term(const SmArgs &A, int64_t s, const int64_t base[BPK_MAXIN]) {
+    int64_t off[BPK_MAXIN];
+#pragma unroll
+    for (int k = 0; k < BPK_MAXIN; ++k) off[k] = base[k];
+    int64_t rem = s;
+    for (int d = A.ns - 1; d >= 0; --d) {
+        int64_t q = rem / A.sshape[d];
+        int64_t r = rem - q * A.sshape[d];
+        rem = q;
+#pragma unroll
+        for (int k = 0; k < BPK_MAXIN; ++k)
+            if (k < A.n_in) off[k] += r * A.sin[k][d];
+    }
+    double p = sm_load(A.in[0], A.dtype[0], off[0]);
+#pragma unroll
+    for (int k = 1; k < BPK_MAXIN; ++k)
+        if (k < A.n_in) p *= sm_load(A.in[k], A.dtype[k], off[k]);
+    return p;
+}
+
+// A: one thread per kept element, serial loop over the summed space.
+__global__ void __launch_bounds__(256) sm_thread_kernel(SmArgs A) {
+    int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (; o < A.n_kept; o += step) {
+        int64_t oo, base[BPK_MAXIN];
+        sm_decode_kept(A, o, oo, base);
+        double acc = 0.0;
+        if (A.ns == 1) {   // common case: odometer-free inner loop
+            for (int64_t s = 0; s < A.n_sum; ++s) {
+                double p = sm_load(A.in[0], A.dtype[0], base[0] + s * A.sin[0][0]);
+#pragma unroll
+                for (int k = 1; k < BPK_MAXIN; ++k)
+                    if (k < A.n_in) p *= sm_load(A.in[k], A.dtype[k], base[k] + s * A.sin[k][0]);
+                acc += p;
+            }
+        } else {
+            for (int64_t s = 0; s < A.n_sum; ++s) acc += sm_term(A, s, base);
+        }
+        double v = A.scale * acc;
+        A.out[oo] = A.accumulate ? A.out[oo] + v : v;
+    }
+}
+
+// B: one block per (kept element, split); threads stride over the summed space.
+__global__ void __launch_bounds__(256) sm_block_kernel(SmArgs A) {
+    __shared__ double red[8];
+    int64_t b = blockIdx.x;
+    for (; b < A.n_kept * A.nsplit; b += gridDim.x) {
+        int64_t o = b / A.nsplit;
+        int sp = (int)(b - o * A.nsplit);
+        int64_t oo, base[BPK_MAXIN];
+        sm_decode_kept(A, o, oo, base);
+        int64_t s0 = sp * A.chunk;
+        int64_t s1 = s0 + A.chunk;
+        if (s1 > A.n_sum) s1 = A.n_sum;
+        double acc = 0.0;
+        for (int64_t s = s0 + threadIdx.x; s < s1; s += blockDim.x) acc += sm_term(A, s, base);
+        acc = warp_sum(acc);
+        int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        if (nw > 1) {
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0) red[w] = acc;
+            __syncthreads();
+            acc = 0.0;
+            if (threadIdx.x < nw) acc = red[threadIdx.x];
+            if (w == 0) acc = warp_sum(acc);
+        }
+        if (threadIdx.x == 0) {
+            if (A.nsplit == 1) {
+                double v = A.scale * acc;
+                A.out[oo] = A.accumulate ? A.out[oo] + v : v;
+            } else {
+                A.partial[b] = acc;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) sm_final_kernel(SmArgs A) {
+    int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (; o < A.n_kept; o += step) {
+        int64_t oo, base[BPK_MAXIN];
+        sm_decode_kept(A, o, oo, base);
+        double acc = 0.0;
+        for (int sp = 0; sp < A.nsplit; ++sp) acc += A.partial[o * A.nsplit + sp];
+        double v = A.scale * acc;
+        A.out[oo] = A.accumulate ? A.out[oo] + v : v;
+    }
+}
+
+extern "C" int bpk_sum_multiply(int nd, const int64_t *shape,
+                                int n_in, const void *const *in, const int *in_dtype,
+                                const int64_t *in_stride,
+                                double *out, const int64_t *out_stride,
+                                double scale, int accumulate) {
+    BPK_REQUIRE_INIT();
+    if (nd < 0 || nd > BPK_MAXD) return bpk_set_error(BPK_EINVAL, "bpk_sum_multiply: nd=%d exceeds %d", nd, BPK_MAXD);
+    if (n_in < 1 || n_in > BPK_MAXIN) return bpk_set_error(BPK_EINVAL, "bpk_sum_multiply: n_in=%d (max %d)", n_in, BPK_MAXIN);
+    SmArgs A;
+    memset(&A, 0, sizeof(A));
+    A.n_in = n_in; A.out = out; A.scale = scale; A.accumulate = accumulate;
+    for (int k = 0; k < n_in; ++k) { A.in[k] = in[k]; A.dtype[k] = in_dtype[k]; }
+    A.n_kept = 1; A.n_sum = 1;
+    bool empty = false;
+    for (int d = 0; d < nd; ++d) {
+        int64_t e = shape[d];
+        if (e < 0) return bpk_set_error(BPK_EINVAL, "bpk_sum_multiply: negative extent");
+        if (e == 0) empty = true;
+        if (e == 1) continue;                 // carries no index
+        if (out_stride[d] != 0) {             // kept axis
+            // merge with the previous kept axis when every array is contiguous across the pair
+            bool merge = A.nk > 0 && A.kout[A.nk - 1] == out_stride[d] * e;
+            for (int k = 0; merge && k < n_in; ++k)
+                merge = A.kin[k][A.nk - 1] == in_stride[k * nd + d] * e;
+            // only adjacent original axes may merge: guaranteed because axes are visited in order
+            if (merge && d > 0) {
+                int j = A.nk - 1;
+                A.kshape[j] *= e;
+                A.kout[j] = out_stride[d];
+                for (int k = 0; k < n_in; ++k) A.kin[k][j] = in_stride[k * nd + d];
+            } else {
+                int j = A.nk++;
+                A.kshape[j] = e;
+                A.kout[j] = out_stride[d];
+                for (int k = 0; k < n_in; ++k) A.kin[k][j] = in_stride[k * nd + d];
+            }
+            A.n_kept *= e;
+        } else {                              // summed axis
+            bool all_bcast = true;
+            for (int k = 0; k < n_in; ++k) all_bcast = all_bcast && in_stride[k * nd + d] == 0;
+            if (all_bcast) { A.scale *= (double)e; continue; }   // broadcasting multiplier (misc.py:761)
+            bool merge = A.ns > 0;
+            for (int k = 0; merge && k < n_in; ++k)
+                merge = A.sin[k][A.ns - 1] == in_stride[k * nd + d] * e;
+            if (merge) {
+                int j = A.ns - 1;
+                A.sshape[j] *= e;
+                for (int k = 0; k < n_in; ++k) A.sin[k][j] = in_stride[k * nd + d];
+            } else {
+                int j = A.ns++;
+                A.sshape[j] = e;
+                for (int k = 0; k < n_in; ++k) A.sin[k][j] = in_stride[k * nd + d];
+            }
+            A.n_sum *= e;
+        }
+    }
+    if (empty) {
+        // empty sum: the result is zero (or unchanged when accumulating) over the kept space;
+        // an empty kept space writes nothing.
+        return BPK_OK;
+    }
+    if (A.ns == 0) { A.ns = 1; A.sshape[0] = 1; }   // pure broadcast product
+
+    bool kept_contig = false;   // some operand is unit-stride along the innermost kept axis
+    if (A.nk > 0)
+        for (int k = 0; k < n_in; ++k) kept_contig = kept_contig || A.kin[k][A.nk - 1] == 1;
+    bool use_thread = A.n_sum <= 8 || (A.n_kept >= 32768 && (kept_contig || A.n_sum <= 64));
+    if (use_thread) {
+        int64_t blocks = (A.n_kept + 255) / 256;
+        int64_t cap = (int64_t)g_bpk.sm_count * 32;
+        if (blocks > cap) blocks = cap;
+        BPK_LAUNCH(sm_thread_kernel, (unsigned)blocks, 256, 0, A);
+        return BPK_OK;
+    }
+    // block-per-output path
+    int threads = A.n_sum >= 4096 ? 256 : (A.n_sum >= 512 ? 128 : 32);
+    int64_t target_blocks = (int64_t)g_bpk.sm_count * 16;
+    int nsplit = 1;
+    if (A.n_kept < target_blocks) {
+        int64_t want = target_blocks / A.n_kept;
+        int64_t maxsplit = A.n_sum / (threads * 8);   // keep >= 8 terms per thread
+        if (maxsplit < 1) maxsplit = 1;
+        nsplit = (int)(want < maxsplit ? want : maxsplit);
+        if (nsplit > 4096) nsplit = 4096;
+        if (nsplit < 1) nsplit = 1;
+    }
+    A.nsplit = nsplit;
+    A.chunk = (A.n_sum + nsplit - 1) / nsplit;
+    if (nsplit > 1) {
+        A.partial = bpk_scratch((size_t)A.n_kept * nsplit * sizeof(double));
+        if (!A.partial) return bpk_set_error(BPK_ECUDA, "bpk_sum_multiply: scratch allocation failed");
+    }
+    int64_t blocks = A.n_kept * nsplit;
+    int64_t cap = (int64_t)g_bpk.sm_count * 64;
+    if (blocks > cap) blocks = cap;
+    BPK_LAUNCH(sm_block_kernel, (unsigned)blocks, threads, 0, A);
+    if (nsplit > 1) {
+        int64_t fb = (A.n_kept + 255) / 256;
+        BPK_LAUNCH(sm_final_kernel, (unsigned)fb, 256, 0, A);
+    }
+    return BPK_OK;
+}

@@ -1,0 +1,93 @@
+"""Gamma node on device (replaces the array math of nodes/gamma.py:90-241).
+
+x ~ Gamma(a, b) with fixed shape ``a`` and a gamma-like (or fixed) rate ``b``.
+Natural parameters phi = [-<b>, a]; moments u = [<x>, <log x>];
+all of it is one fused kernel, ``bpk_gamma_moments``.
+"""
+import numpy as np
+
+from .. import _bpk
+from .. import darray as D
+from ..darray import DArray
+from .expfam import Distribution, ExponentialFamily
+from .gaussian import ensure_gamma
+from .node import Constant, Node
+
+
+def gamma_prior_constant(a):
+    """[a, lgamma(a)]  (GammaPriorMoments, gamma.py:33-59)."""
+    a = np.asarray(a, dtype=np.float64)
+    if np.any(a <= 0):
+        raise ValueError("Shape parameter must be positive")
+    ad = D.asarray(a)
+    return Constant("gamma_prior", [ad, D.gammaln(ad)], dims=((), ()), plates=a.shape, value=a)
+
+
+class GammaDistribution(Distribution):
+
+    def compute_message_to_parent(self, parent, index, u_self, u_a, u_b):
+        """gamma.py:96-113."""
+        if index == 0:
+            raise NotImplementedError("Message to the shape parameter of Gamma is not supported "
+                                      "(the reference needs a GammaShape node for it)")
+        elif index == 1:
+            return [D.mul(u_self[0], -1.0), u_a[0]]
+        raise ValueError("Index out of bounds")
+
+    def compute_phi_from_parents(self, u_a, u_b, mask=True):
+        """gamma.py:116-121."""
+        return [D.mul(u_b[0], -1.0), u_a[0]]
+
+    def compute_cgf_from_parents(self, u_a, u_b):
+        """a <log b> - lgamma(a)   (gamma.py:151-160)."""
+        return D.sub(D.mul(u_a[0], u_b[1]), u_a[1])
+
+    def compute_moments_and_cgf(self, phi, mask=True):
+        """gamma.py:124-148 as one kernel."""
+        be = _bpk.get()
+        P = tuple(np.broadcast_shapes(phi[0].shape, phi[1].shape))
+        n = int(np.prod(P, dtype=np.int64)) if P else 1
+
+        def prep(p):
+            cnt = p.size
+            if cnt != 1 and tuple(p.shape) != P and (1,) * (len(P) - p.ndim) + tuple(p.shape) != P:
+                p = p.broadcast_to(P)
+                cnt = n
+            return p.contiguous(), (1 if cnt == 1 else n)
+        p0, n0 = prep(phi[0])
+        p1, n1 = prep(phi[1])
+        u0, u1, g = DArray.empty(P), DArray.empty(P), DArray.empty(P)
+        be.gamma_moments(p0.ptr, n0, p1.ptr, n1, n, u0.ptr, u1.ptr, g.ptr, True)
+        return [u0, u1], g
+
+    def compute_fixed_moments_and_f(self, x, mask=True):
+        """gamma.py:163-173."""
+        x = np.asarray(x, dtype=np.float64)
+        if np.any(x < 0):
+            raise ValueError("Values must be positive")
+        xd = D.asarray(x)
+        logx = D.log(xd)
+        return [xd, logx], D.mul(logx, -1.0)
+
+    def random(self, *phi, plates=None):
+        return np.random.gamma(phi[1], -1 / phi[0], size=plates)
+
+
+class Gamma(ExponentialFamily):
+    """``Gamma(a, b, plates=None, name="")`` as in the reference (gamma.py:214-241)."""
+    moment_kind = "gamma"
+
+    def __init__(self, a, b, plates=None, name="", initialize=True):
+        if isinstance(a, Node):
+            if a.moment_kind != "gamma_prior":
+                raise ValueError("Shape parameter must be a fixed value or a gamma-prior node")
+        else:
+            a = gamma_prior_constant(a)
+        b = ensure_gamma(b)
+        super().__init__(a, b, dims=((), ()), distribution=GammaDistribution(), plates=plates, name=name,
+                         initialize=initialize)
+
+    def __str__(self):
+        a = self.phi[1].numpy()
+        b = -self.phi[0].numpy()
+        return "%s ~ Gamma(a, b)\n  a =\n%s\n  b =\n%s\n" % (self.name, a, b)

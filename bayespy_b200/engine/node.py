@@ -1,0 +1,270 @@
+"""Host-side node graph: plates, masks and message routing.
+
+This is bookkeeping only (shapes, who-is-whose-parent, boolean masks); every
+floating-point array is a :class:`bayespy_b200.darray.DArray` in HBM and every
+arithmetic step is a libbpk kernel.  It plays the role of the reference's
+``bayespy/inference/vmp/nodes/node.py`` (Node :223-857), ``deterministic.py``
+and ``constant.py`` but is organised differently: there are no Moments /
+converter classes — a node advertises a *moment kind* string and parents given
+as plain arrays become :class:`Constant` nodes of the kind the child expects.
+
+Moment kinds and their per-plate dims
+    "gaussian"     [<x>, <x x^T>]          dims (S, S+S)
+    "gamma"        [<a>, <log a>]          dims ((), ())
+    "gamma_prior"  [a, lgamma(a)]          dims ((), ())        (gamma.py:33-59)
+    "wishart"      [<L>, <log|L|>]         dims ((D,D), ())
+    "wishart_prior" [n, lgamma_D(n/2)]     dims ((), ())        (wishart.py:23-42)
+    "dirichlet"    [<log p>]               dims ((K,),)
+    "dirichlet_prior" [alpha, ...]         dims ((K,), ())      (dirichlet.py:25-62)
+    "categorical"  [<one-hot>]             dims ((K,),)
+"""
+import numpy as np
+
+from .. import darray as D
+from ..darray import DArray
+
+
+# --------------------------------------------------------------------------------------------
+# shape helpers (pure host integer work)
+# --------------------------------------------------------------------------------------------
+def broadcast_plates(*plates):
+    try:
+        return tuple(int(n) for n in np.broadcast_shapes(*[tuple(p) for p in plates]))
+    except ValueError:
+        raise ValueError("The plates of the parents do not broadcast: %s" % (plates,))
+
+
+def is_subshape(sub, full):
+    """True if ``sub`` broadcasts to ``full`` without enlarging it (right-aligned)."""
+    sub, full = tuple(sub), tuple(full)
+    if len(sub) > len(full):
+        return False
+    for a, b in zip(reversed(sub), reversed(full)):
+        if a != 1 and a != b:
+            return False
+    return True
+
+
+def mask_is_full(mask):
+    return mask is True or bool(np.all(mask))
+
+
+class Node:
+    """Base class: plates, parents/children, masks, message reduction."""
+
+    moment_kind = None
+    _id_counter = 0
+
+    def __init__(self, *parents, dims=None, plates=None, name="", notify_parents=True):
+        self.parents = list(parents)
+        self.dims = tuple(tuple(d) for d in dims)
+        self.name = name
+        self.children = []          # (child, index) in registration order
+        parent_plates = [self._plates_from_parent(i) for i in range(len(self.parents))]
+        if plates is None:
+            self.plates = broadcast_plates(*parent_plates) if parent_plates else ()
+        else:
+            plates = tuple(int(n) for n in plates)
+            for p in parent_plates:
+                if not is_subshape(p, plates):
+                    raise ValueError("The plates %s of the parents are not broadcastable to the given "
+                                     "plates %s." % (p, plates))
+            self.plates = plates
+        # which plates take part in inference at all (OR of the children's masks)
+        self.mask = np.array(False)
+        self._mask_dev = None
+        self._version = 0           # bumped whenever the moments change (message caches key on it)
+        if notify_parents:
+            for i, p in enumerate(self.parents):
+                p._add_child(self, i)
+
+    # ---- graph ------------------------------------------------------------------------------
+    def _add_child(self, child, index):
+        self.children.append((child, index))
+
+    def _remove_child(self, child, index):
+        self.children.remove((child, index))
+
+    def delete(self):
+        for i, p in enumerate(self.parents):
+            p._remove_child(self, i)
+        for c, _ in list(self.children):
+            c.delete()
+
+    def _ids(self):
+        """IDs of the stochastic factors this node depends on (independence check)."""
+        raise NotImplementedError
+
+    def _check_independent_parents(self):
+        ids = []
+        for p in self.parents:
+            ids += list(p._ids())
+        if len(ids) != len(set(ids)):
+            raise ValueError("Parent nodes are not independent")
+
+    # ---- plates -----------------------------------------------------------------------------
+    def _plates_from_parent(self, index):
+        """Plates of parent[index] as seen from this node."""
+        return tuple(self.parents[index].plates)
+
+    def _plates_to_parent(self, index):
+        """This node's plates as seen from parent[index]."""
+        return tuple(self.plates)
+
+    def get_shape(self, i):
+        return tuple(self.plates) + tuple(self.dims[i])
+
+    # ---- masks (host booleans; nodes.node.py:446-526) ------------------------------------------
+    def get_mask(self):
+        return self.mask
+
+    def _set_mask(self, mask):
+        self.mask = mask
+        self._mask_dev = None
+
+    def _weights_to_parent(self, index, mask):
+        """Map this node's plate mask to the plate space of parent[index]."""
+        return mask
+
+    def _mask_to_parent(self, index):
+        mask = np.asarray(self._weights_to_parent(index, self.mask)) != 0
+        tgt = tuple(self.parents[index].plates)
+        nd = mask.ndim
+        full = (1,) * (nd - len(tgt)) + tgt if nd >= len(tgt) else tgt[len(tgt) - nd:]
+        axes = tuple(i for i in range(nd) if full[i] == 1 and mask.shape[i] != 1)
+        if axes:
+            mask = np.any(mask, axis=axes, keepdims=True)
+        while mask.ndim > len(tgt):
+            mask = mask[0]
+        return mask
+
+    def _update_mask(self):
+        mask = np.array(False)
+        for child, index in self.children:
+            mask = np.logical_or(mask, child._mask_to_parent(index))
+        self._set_mask(mask)
+        if not is_subshape(np.shape(self.mask), self.plates):
+            raise ValueError("The mask of the node %s has updated incorrectly. The plates in the mask %s "
+                             "are not a subset of the plates of the node %s."
+                             % (self.name, np.shape(self.mask), self.plates))
+        for p in self.parents:
+            p._update_mask()
+
+    def mask_device(self, mask=None):
+        """u8 device copy of a host mask, or None when every plate is active."""
+        if mask is None:
+            if mask_is_full(self.mask):
+                return None
+            if self._mask_dev is None:
+                self._mask_dev = DArray.from_numpy(np.asarray(self.mask, dtype=bool), "u1")
+            return self._mask_dev
+        if mask_is_full(mask):
+            return None
+        return DArray.from_numpy(np.asarray(mask, dtype=bool), "u1")
+
+    # ---- messages -----------------------------------------------------------------------------
+    def get_moments(self):
+        raise NotImplementedError
+
+    def _message_and_mask_to_parent(self, index):
+        """Un-reduced message list (device) and the host mask that gates it."""
+        raise NotImplementedError
+
+    def message_to_parent(self, index):
+        """Message to parent[index], masked and summed to the parent's plates
+        (node.py:570-655).  Entries may be None (no contribution)."""
+        if index >= len(self.parents):
+            raise ValueError("Parent index larger than the number of parents")
+        m, mask = self._message_and_mask_to_parent(index)
+        parent = self.parents[index]
+        plates_self = self._plates_to_parent(index)
+        mdev = self.mask_device() if mask is self.mask else self.mask_device(mask)
+        out = []
+        for i, mi in enumerate(m):
+            if mi is None:
+                out.append(None)
+                continue
+            nd = len(parent.dims[i])
+            mi = D.asarray(mi)
+            dims = tuple(parent.dims[i])
+            from_shape = tuple(plates_self) + dims
+            to_shape = tuple(parent.plates) + dims
+            mk = mdev.add_trailing(nd) if mdev is not None else None
+            out.append(D.reduce_to_shape(mi, to_shape, mask=mk, from_shape=from_shape))
+        return out
+
+    def message_from_children(self):
+        """Sum of the children's messages, one entry per moment (None = no message)."""
+        msg = [None] * len(self.dims)
+        for child, index in self.children:
+            m = child.message_to_parent(index)
+            for i in range(len(self.dims)):
+                if m[i] is not None:
+                    msg[i] = m[i] if msg[i] is None else D.add(msg[i], m[i])
+        return msg
+
+    def moments_from_parents(self, exclude=None):
+        return [p.get_moments() if i != exclude else None for i, p in enumerate(self.parents)]
+
+    def lower_bound_contribution(self):
+        return 0.0
+
+
+# --------------------------------------------------------------------------------------------
+class Constant(Node):
+    """Fixed moments (nodes/constant.py).  ``u`` is a list of DArrays shaped plates+dims."""
+
+    def __init__(self, kind, u, dims, plates, name="const", value=None):
+        self.moment_kind = kind
+        self.u = list(u)
+        self.value = value
+        super().__init__(dims=dims, plates=plates, name=name)
+
+    def _ids(self):
+        return []
+
+    def get_moments(self):
+        return list(self.u)
+
+    def _update_mask(self):
+        pass
+
+
+# --------------------------------------------------------------------------------------------
+class Deterministic(Node):
+    """Node whose moments are a function of the parents' moments
+    (nodes/deterministic.py:16-153).  Sub-classes implement
+    ``_compute_moments(*u_parents)`` and
+    ``_compute_message_to_parent(index, m_children, *u_parents)``."""
+
+    def __init__(self, *parents, dims, plates=None, name=""):
+        super().__init__(*parents, dims=dims, plates=plates, name=name)
+        self._cache = None
+        self._check_independent_parents()
+
+    def _ids(self):
+        ids = []
+        for p in self.parents:
+            ids += list(p._ids())
+        return ids
+
+    def _parent_versions(self):
+        return tuple(getattr(p, "_version", 0) if not isinstance(p, Deterministic) else p._parent_versions()
+                     for p in self.parents)
+
+    def get_moments(self):
+        key = self._parent_versions()
+        if self._cache is None or self._cache[0] != key:
+            u = self._compute_moments(*[p.get_moments() for p in self.parents])
+            self._cache = (key, u)
+        return list(self._cache[1])
+
+    def _message_and_mask_to_parent(self, index):
+        u_parents = self.moments_from_parents(exclude=index)
+        m_children = self.message_from_children()
+        m = self._compute_message_to_parent(index, m_children, *u_parents)
+        mask = self._weights_to_parent(index, self.mask)
+        return m, mask
+
+    def lower_bound_contribution(self):
+        return 0.0

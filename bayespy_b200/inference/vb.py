@@ -1,0 +1,188 @@
+"""VB — the variational Bayes sweep scheduler (replaces ``VB.update``,
+``_end_iteration_step`` and ``loglikelihood_lowerbound`` of
+bayespy/inference/vmp/vmp.py:52-232, :682-764).
+
+Host side: node order, ``repeat`` / ``tol`` / ``verbose`` semantics, the
+iteration print format (vmp.py:725, doctests match on it), the lower-bound
+histories ``L``, ``l`` and ``cputime``.  Device side: every node update and
+every lower-bound term is enqueued on one CUDA stream; the only device->host
+traffic per sweep is the vector of per-node bound terms (a few doubles), which
+the convergence test needs (vmp.py:717-747).
+
+When the model contains a sub-graph a fused sweep kernel exists for (the
+plated Gaussian factor model of PCA, the Gaussian mixture), ``VB`` attaches the
+corresponding *plan* (``bayespy_b200.engine.plans``), which serves the same node
+updates from one pass over the data instead of one pass per message.
+"""
+import time
+import warnings
+
+import numpy as np
+
+from .. import darray as D
+from ..darray import DArray
+from ..engine.node import Node
+
+
+class VB:
+
+    def __init__(self, *nodes, tol=1e-5, autosave_filename=None, autosave_iterations=0,
+                 use_logging=False, user_data=None, callback=None, fused=True):
+        self.user_data = user_data
+        for ind, node in enumerate(nodes):
+            if not isinstance(node, Node):
+                raise ValueError("Argument number %d is not a node" % (ind + 1))
+        if use_logging:
+            import logging
+            self.print = logging.getLogger(__name__).info
+        else:
+            self.print = print
+        model = []
+        for n in nodes:
+            if n not in model:
+                model.append(n)
+        self.model = model
+        self.ignore_bound_checks = False
+        self.iter = 0
+        self.annealing_changed = False
+        self.converged = False
+        self.L = np.array(())
+        self.cputime = np.array(())
+        self.l = {node: np.array([]) for node in self.model}
+        self.autosave_iterations = autosave_iterations
+        self.autosave_filename = autosave_filename
+        names = [node.name for node in self.model]
+        if len(names) != len(self.model):
+            raise Exception("Use unique names for nodes.")
+        self.callback = callback
+        self.callback_output = None
+        self.tol = tol
+        self.plans = []
+        if fused:
+            from ..engine import plans
+            self.plans = plans.attach(self.model)
+
+    # ---- container protocol (vmp.py:358-400) ---------------------------------------------------
+    def __getitem__(self, name):
+        if isinstance(name, Node):
+            return name
+        for node in self.model:
+            if node.name == name:
+                return node
+        raise ValueError("Node %s not found" % (name,))
+
+    def set_callback(self, callback):
+        self.callback = callback
+
+    def has_converged(self, tol=None):
+        return self.converged
+
+    # ---- the sweep (vmp.py:132-172) ------------------------------------------------------------
+    def update(self, *nodes, repeat=1, plot=False, tol=None, verbose=True, tqdm=None):
+        if len(nodes) == 0:
+            nodes = self.model
+        if tqdm is not None:
+            tqdm = tqdm(total=repeat)
+        i = 0
+        while repeat is None or i < repeat:
+            t = time.time()
+            for node in nodes:
+                X = self[node]
+                if hasattr(X, "update") and callable(X.update):
+                    X.update()
+            cputime = time.time() - t
+            i += 1
+            if tqdm is not None:
+                tqdm.update()
+            if self._end_iteration_step(None, cputime, tol=tol, verbose=verbose):
+                return
+
+    # ---- lower bound (vmp.py:180-199) -----------------------------------------------------------
+    def _bound_terms(self):
+        """One D2H of len(model) doubles: every node's term is produced on device."""
+        terms = [node.lower_bound_contribution() for node in self.model]
+        vec = DArray.empty((len(terms),))
+        host_fill = {}
+        for i, t in enumerate(terms):
+            if isinstance(t, DArray):
+                D.copy_into(vec.slice_axis(0, i, i + 1), t.reshape((1,)))
+            else:
+                host_fill[i] = float(t)
+        out = vec.numpy()
+        for i, v in host_fill.items():
+            out[i] = v
+        return out
+
+    def compute_lowerbound(self, ignore_masked=True):
+        return float(np.sum(self._bound_terms()))
+
+    def compute_lowerbound_terms(self, *nodes):
+        vals = self._bound_terms()
+        d = dict(zip(self.model, vals))
+        if len(nodes) == 0:
+            return d
+        return {self[n]: d[self[n]] for n in nodes}
+
+    def loglikelihood_lowerbound(self):
+        vals = self._bound_terms()
+        for node, lp in zip(self.model, vals):
+            self.l[node][self.iter] = lp
+        return float(np.sum(vals))
+
+    def get_iteration_by_nodes(self):
+        return self.l
+
+    def _append_iterations(self, iters):
+        nans = np.full(iters, np.nan)
+        self.L = np.append(self.L, nans)
+        self.cputime = np.append(self.cputime, nans)
+        for node in self.l:
+            self.l[node] = np.append(self.l[node], nans)
+
+    def _end_iteration_step(self, method, cputime, tol=None, verbose=True, bound_cpu_time=True):
+        """vmp.py:693-764: callback, bound, print, decrease warning, convergence test."""
+        if self.iter >= len(self.L):
+            self._append_iterations(100)
+        if callable(self.callback):
+            z = self.callback()
+            if z is not None:
+                z = np.array(z)[..., np.newaxis]
+                if self.callback_output is None:
+                    self.callback_output = z
+                else:
+                    self.callback_output = np.concatenate((self.callback_output, z), axis=-1)
+        t = time.time()
+        L = self.loglikelihood_lowerbound()
+        if bound_cpu_time:
+            cputime += time.time() - t
+        self.cputime[self.iter] = cputime
+        self.L[self.iter] = L
+        if verbose:
+            if method:
+                self.print("Iteration %d (%s): loglike=%e (%.3f seconds)" % (self.iter + 1, method, L, cputime))
+            else:
+                self.print("Iteration %d: loglike=%e (%.3f seconds)" % (self.iter + 1, L, cputime))
+        self.converged = False
+        if not self.ignore_bound_checks and not self.annealing_changed and self.iter > 0:
+            if self.L[self.iter - 1] - L > 1e-6:
+                L_diff = (self.L[self.iter - 1] - L)
+                warnings.warn("Lower bound decreased %e! Bug somewhere or numerical inaccuracy?" % L_diff)
+            L0 = self.L[self.iter - 1]
+            L1 = self.L[self.iter]
+            if tol is None:
+                tol = self.tol
+            div = 0.5 * (abs(L0) + abs(L1))
+            if (L1 - L0) / div < tol:
+                if verbose:
+                    self.print("Converged at iteration %d." % (self.iter + 1))
+                self.converged = True
+        self.annealing_changed = False
+        self.iter += 1
+        return self.converged
+
+    def set_annealing(self, annealing):
+        """vmp.py:665-679."""
+        for node in self.model:
+            node.annealing = annealing
+        self.annealing_changed = True
+        self.converged = False

@@ -1,0 +1,204 @@
+/*
+ * bpk.h — C ABI of libbpk.so, the B200 (sm_100a) kernel library behind the
+ * BayesPy plate-batched VMP update path.
+ *
+ * Boundary.  The reference (pure Python) has no FFI; the seams
+ * this ABI replaces are, citing /root/reference paths:
+ *   seam 1  bayespy/utils/misc.py:851 sum_multiply, :935 sum_product,
+ *           :805 sum_multiply_to_plates            -> bpk_sum_multiply
+ *           bayespy/utils/linalg.py:31 chol, :66 chol_solve, :174 chol_inv,
+ *           :209 chol_logdet                       -> bpk_chol*
+ *   seam 2  the Distribution protocol methods
+ *           (bayespy/inference/vmp/nodes/expfamily.py:26-43) of
+ *           gaussian.py:672 (GaussianARD), gaussian.py:397 (Gaussian),
+ *           gamma.py:124, wishart.py:165, dirichlet.py:130,
+ *           multinomial.py:101, mixture.py:53    -> bpk_*_moments, bpk_mix_*
+ *           and dot.py:355,403,581 (SumMultiply)   -> bpk_sum_multiply / bpk_pca_*
+ *   seam 3  VB.update (bayespy/inference/vmp/vmp.py:132) -> fused sweeps
+ *           bpk_pca_* / bpk_gmm_* scheduled by bayespy_b200.inference.VB
+ *
+ * Conventions: plain C, no torch types.  All entry points return 0 on success
+ * or a BPK_E* code (text via bpk_last_error()).  All arrays are fp64 unless a
+ * dtype is given; "dev" pointers are device pointers returned by bpk_malloc.
+ * Everything is ordered on the library's single compute stream; only bpk_d2h,
+ * bpk_sync and the *_check variants block the host.  One process drives one
+ * GPU (one rank per GPU under torchrun); the caller owns every buffer.
+ */
+#ifndef BPK_H
+#define BPK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BPK_MAXD 8          /* max broadcast rank of the generic kernels     */
+#define BPK_MAXIN 4         /* max inputs of bpk_ewise / bpk_sum_multiply    */
+#define BPK_MAXDIM 64       /* max matrix dimension of the batched linalg    */
+
+/* status codes */
+#define BPK_OK 0
+#define BPK_ECUDA 1         /* CUDA runtime error                            */
+#define BPK_EINVAL 2        /* bad argument (-> ValueError)                  */
+#define BPK_ENOTSPD 3       /* "Matrix not positive definite" linalg.py:58   */
+#define BPK_EDOMAIN 4       /* non-positive natural parameter (gamma.py:142, dirichlet.py:147) */
+#define BPK_ENCCL 5
+#define BPK_ENOGPU 6
+
+/* dtypes of generic-kernel inputs */
+#define BPK_F64 0
+#define BPK_U8 1            /* bool masks                                    */
+
+/* ---- lifecycle / memory ------------------------------------------------ */
+int bpk_init(int device);
+int bpk_shutdown(void);
+const char *bpk_last_error(void);
+int bpk_device_info(int *sm_count, int *cc_major, int *cc_minor,
+                    uint64_t *hbm_total, uint64_t *hbm_free);
+int bpk_sync(void);
+uint64_t bpk_launch_count(void);      /* kernels launched since bpk_init    */
+int bpk_malloc(void **dev, uint64_t bytes);
+int bpk_free(void *dev);
+int bpk_h2d(void *dev, const void *host, uint64_t bytes);
+int bpk_d2h(void *host, const void *dev, uint64_t bytes);   /* blocks */
+int bpk_d2d(void *dst, const void *src, uint64_t bytes);
+int bpk_memset(void *dev, int byte, uint64_t bytes);
+int bpk_host_alloc(void **host, uint64_t bytes);            /* pinned */
+int bpk_host_free(void *host);
+/* CUDA-event timers on the compute stream (bench.py) */
+int bpk_timer_create(int *id);
+int bpk_timer_record(int id, int which /*0=start,1=stop*/);
+int bpk_timer_elapsed_ms(int id, double *ms);               /* blocks */
+int bpk_flush_l2(void);               /* overwrite a >L2-sized scratch buffer */
+
+/* ---- multi-GPU: one NCCL communicator per process -------- */
+int bpk_comm_unique_id(char id[128]);
+int bpk_comm_init(const char id[128], int nranks, int rank);
+int bpk_comm_size(int *nranks, int *rank);
+int bpk_allreduce_sum_f64(double *dev, uint64_t count);     /* in place, on the compute stream */
+int bpk_comm_destroy(void);
+
+/* ---- generic broadcast kernels (seam 1) -------------------------------- */
+/* Elementwise out[i] = op(in0[i], in1[i], in2[i]; alpha, beta) over an
+ * nd-dimensional index space `shape`.  Strides are in elements; 0 = broadcast.
+ * The output may be strided too (e.g. the diagonal of a KxK tile).          */
+enum {
+    BPK_OP_COPY = 0,    /* a                                   */
+    BPK_OP_ADD,         /* a + b                               */
+    BPK_OP_SUB,         /* a - b                               */
+    BPK_OP_MUL,         /* a * b                               */
+    BPK_OP_DIV,         /* a / b                               */
+    BPK_OP_AXPBY,       /* alpha*a + beta*b                    */
+    BPK_OP_AFFINE,      /* alpha*a + beta                      */
+    BPK_OP_FMA,         /* alpha*a*b + beta*c                  */
+    BPK_OP_WHERE,       /* a(mask) ? b : c                     */
+    BPK_OP_LOG,         /* log(a)                              */
+    BPK_OP_EXP,         /* exp(a)                              */
+    BPK_OP_RECIP,       /* alpha / a                           */
+    BPK_OP_SQUARE,      /* a*a                                 */
+    BPK_OP_SQRT,        /* sqrt(a)                             */
+    BPK_OP_LGAMMA,      /* lgamma(a)      scipy.special.gammaln */
+    BPK_OP_DIGAMMA,     /* psi(a)         scipy.special.psi     */
+    BPK_OP_MVLGAMMA,    /* multigammaln(a, d=(int)alpha)        */
+    BPK_OP_MVDIGAMMA,   /* sum_{i<d} psi(a - i/2), d=(int)alpha  misc.py:1146 */
+    BPK_OP_NONZERO,     /* a != 0 ? b : 0   (expfamily.py:463 "0 * -inf") */
+    BPK_OP_COUNT_
+};
+int bpk_ewise(int op, int nd, const int64_t *shape,
+              double *out, const int64_t *out_stride,
+              int n_in, const void *const *in, const int *in_dtype,
+              const int64_t *in_stride /* [n_in][nd] */,
+              double alpha, double beta);
+
+/* out[kept] = scale * sum_{summed} prod_i in_i[...]  (+ out if accumulate).
+ * Axes with out_stride==0 are summed.  This is misc.sum_multiply (misc.py:851,
+ * an np.einsum over broadcast operands) and the masked plate-sum of
+ * Node._message_to_parent (node.py:650).                                    */
+int bpk_sum_multiply(int nd, const int64_t *shape,
+                     int n_in, const void *const *in, const int *in_dtype,
+                     const int64_t *in_stride /* [n_in][nd] */,
+                     double *out, const int64_t *out_stride,
+                     double scale, int accumulate);
+
+/* ---- batched dense SPD linear algebra (linalg.py:31-223) --------------- */
+/* A,U: [batch][D][D] row-major.  U is upper-triangular with A = U^T U
+ * (scipy cho_factor(lower=False)); the strict lower triangle is written as 0
+ * (the reference leaves it undefined).  check!=0: block and return
+ * BPK_ENOTSPD if any matrix was not positive definite.                      */
+int bpk_chol(const double *A, double *U, int64_t batch, int D, int check);
+/* X = A^{-1} B for B: [batchB][D][nrhs]; batchU, batchB in {1, batch}.      */
+int bpk_chol_solve(const double *U, int64_t batchU, const double *B, int64_t batchB,
+                   double *X, int64_t batch, int D, int nrhs);
+int bpk_chol_inv(const double *U, double *Ainv, int64_t batch, int D);
+int bpk_chol_logdet(const double *U, double *out, int64_t batch, int D);
+
+/* ---- fused per-node moment kernels (seam 2) ---------------------------- */
+/* Gaussian / GaussianARD (gaussian.py:397-446, :672-706):
+ *   Lambda = -2 phi1,  Cov = Lambda^-1,  u0 = Cov phi0,
+ *   g = -1/2 u0.phi0 + 1/2 log|Lambda|.   phi0: [n0][K], phi1: [n1][K][K],
+ *   n0,n1 in {1,N}.  Outputs u0 [N][K], cov [n1][K][K] (second moment is
+ *   cov + u0 u0^T, materialised on demand by bpk_outer_add), g [N].
+ *   Outputs may be NULL to skip.                                            */
+int bpk_gaussian_moments(const double *phi0, int64_t n0, const double *phi1, int64_t n1,
+                         int64_t N, int K, double *u0, double *cov, double *g,
+                         double *logdet /* [n1] or NULL */, int check);
+/* u1[n] = cov[n or 0] + u0[n] u0[n]^T                                        */
+int bpk_outer_add(const double *u0, const double *cov, int64_t ncov,
+                  int64_t N, int K, double *u1);
+/* Gamma (gamma.py:124-148): a = phi1, b = -phi0: u0=a/b, u1=psi(a)-log b,
+ * g = a log b - lgamma(a).  n0,n1 in {1,n}.                                 */
+int bpk_gamma_moments(const double *phi0, int64_t n0, const double *phi1, int64_t n1,
+                      int64_t n, double *u0, double *u1, double *g, int check);
+/* Wishart (wishart.py:165-188): V=-phi0 [n][D][D], nu/2 = phi1 [n1]:
+ * u0 = phi1 V^-1, u1 = -log|V| + psi_D(phi1), g = phi1 log|V| - lgamma_D(phi1) */
+int bpk_wishart_moments(const double *phi0, const double *phi1, int64_t n1,
+                        int64_t n, int D, double *u0, double *u1, double *g, int check);
+/* Dirichlet (dirichlet.py:130-160): u = psi(phi) - psi(sum phi),
+ * g = lgamma(sum phi) - sum lgamma(phi); phi: [n][K]                         */
+int bpk_dirichlet_moments(const double *phi, int64_t n, int K,
+                          double *u, double *g, int check);
+/* Categorical/Multinomial(1) (multinomial.py:101-121, misc.py:1366-1401):
+ * u = softmax(phi) (renormalised), g = -logsumexp(phi); phi: [n][K]          */
+int bpk_softmax_moments(const double *phi, int64_t n, int K, double *u, double *g);
+/* one-hot encode integer labels (categorical.py:30-47); bit-exact           */
+int bpk_one_hot(const int64_t *labels, int64_t n, int K, double *u, int check);
+
+/* ---- fused sweep kernels (seam 3) -------------------------- */
+/* PCA / factor model  y[m,n] ~ N(w_m . x_n, 1/tau), fully observed.
+ * One pass over Y: x_n = A y_n + b for every column n (A: [K][M], b: [K]),
+ * writes X [N][K] and accumulates the sufficient statistics
+ *   stats = [ S_yx (M*K) | S_xx (K*K) | s_x (K) ]  (sum_n y_n x_n^T, x_n x_n^T, x_n)
+ * Y: [M][N] row-major (n fastest).  stats must be zeroed by the caller
+ * (or hold a partial to accumulate onto).  640 B/col at M=64, K=16.         */
+int bpk_pca_xsweep(const double *Y, int64_t M, int64_t N, int K,
+                   const double *A, const double *b, double *X, double *stats);
+/* statistics only, for an X that did not come from bpk_pca_xsweep           */
+int bpk_pca_stats(const double *Y, int64_t M, int64_t N, int K,
+                  const double *X, double *stats);
+/* masked variant: per-column precision.  mask: [M][N] u8.
+ * Lam_n = diag(alpha) + tau sum_m mask[m,n] WW[m];  phi0_n = tau sum_m mask y w_m + amu
+ * writes X [N][K], optional COV [N][K][K], g [N], and stats
+ *   [ S_yx (M*K) | S_xx (M*K*K, per row m incl. covariance) ]               */
+int bpk_pca_xsweep_masked(const double *Y, const uint8_t *mask, int64_t M, int64_t N, int K,
+                          const double *W /*[M][K]*/, const double *WW /*[M][K][K]*/,
+                          double tau, const double *alpha /*[K]*/, const double *amu /*[K]*/,
+                          double *X, double *COV /*nullable*/, double *g /*[N]*/,
+                          double *stats, int check);
+/* sum_{m,n} mask*y^2 and count (constants of the tau update)                */
+int bpk_sumsq(const double *Y, const uint8_t *mask /*nullable*/, int64_t count,
+              double *out2 /* [2]: sum y^2, #observed */);
+
+/* Gaussian mixture E-step + statistics in one pass over y [N][D]:
+ *   L[n,k] = c[k] + y_n.h[k] - 1/2 y_n^T Lam[k] y_n + logpi[k]
+ *   p[n,:] = softmax(L[n,:]);  writes P [N][K] (nullable), g [N] = -logsumexp
+ *   stats = [ sum_n p (K) | sum_n p y (K*D) | sum_n p y y^T (K*D*D) | sum_n logsumexp (1) ] */
+int bpk_gmm_sweep(const double *Y, int64_t N, int D, int K,
+                  const double *c, const double *h, const double *Lam, const double *logpi,
+                  double *P, double *g, double *stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BPK_H */

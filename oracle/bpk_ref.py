@@ -1,0 +1,412 @@
+"""TEST INFRASTRUCTURE — NumPy/SciPy restatement of every libbpk entry point.
+
+This is the per-kernel oracle: each method restates, on the CPU, the reference
+arithmetic that the CUDA kernel of the same name replaces (reference file:line
+cited per method, paths relative to /root/reference).  It is pinned against the
+reference itself by ``tests/golden/make_golden.py`` (run in the build container,
+where the reference imports) and the committed ``tests/golden/*.npz`` vectors.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline leg
+may import this module.  "Device pointers" are raw host addresses of buffers it
+allocates, so pointer arithmetic done by the host layer works unchanged.
+"""
+import ctypes
+
+import numpy as np
+import scipy.linalg
+import scipy.special as sp
+
+F64, U8 = 0, 1
+ENOTSPD, EDOMAIN = 3, 4
+
+
+class NotPositiveDefinite(Exception):
+    pass
+
+
+def _view(ptr, shape, strides_elems, dtype=np.float64):
+    """ndarray view of raw memory at ``ptr`` with element strides."""
+    shape = tuple(int(s) for s in shape)
+    itemsize = np.dtype(dtype).itemsize
+    if any(s == 0 for s in shape):
+        return np.empty(shape, dtype)
+    extent = 1 + sum((n - 1) * abs(int(st)) for n, st in zip(shape, strides_elems))
+    buf = (ctypes.c_byte * (extent * itemsize)).from_address(int(ptr))
+    base = np.frombuffer(buf, dtype=dtype)
+    return np.lib.stride_tricks.as_strided(base, shape, [int(st) * itemsize for st in strides_elems])
+
+
+def _dense(ptr, shape, dtype=np.float64):
+    shape = tuple(int(s) for s in shape)
+    st = []
+    acc = 1
+    for n in reversed(shape):
+        st.append(acc)
+        acc *= n
+    return _view(ptr, shape, list(reversed(st)), dtype)
+
+
+class RefBackend:
+    """Same method surface as bayespy_b200._bpk.CudaBackend."""
+
+    name = "oracle"
+
+    def __init__(self):
+        self._bufs = {}
+        self._launches = 0
+        self._timers = []
+        self.nranks, self.rank = 1, 0
+        self._allreduce_hook = None   # tests install a gloo all-reduce here
+
+    # ---- plumbing -------------------------------------------------------------
+    def sync(self):
+        pass
+
+    def launch_count(self):
+        return self._launches
+
+    def device_info(self):
+        return dict(sm_count=0, cc=(0, 0), hbm_total=0, hbm_free=0)
+
+    def malloc(self, nbytes):
+        a = np.zeros(max(int(nbytes), 8) + 64, dtype=np.uint8)
+        addr = a.ctypes.data
+        off = (-addr) % 64
+        p = addr + off
+        self._bufs[p] = a
+        a[:] = 0xFF   # poison: unwritten doubles read as NaN
+        return p
+
+    def free(self, ptr):
+        self._bufs.pop(ptr, None)
+
+    def h2d(self, dev, host_array):
+        a = np.ascontiguousarray(host_array)
+        ctypes.memmove(dev, a.ctypes.data, a.nbytes)
+
+    def d2h(self, host_array, dev):
+        ctypes.memmove(host_array.ctypes.data, dev, host_array.nbytes)
+
+    def d2d(self, dst, src, nbytes):
+        ctypes.memmove(dst, src, int(nbytes))
+
+    def memset(self, dev, byte, nbytes):
+        ctypes.memset(dev, int(byte), int(nbytes))
+
+    def timer_create(self):
+        self._timers.append([0.0, 0.0])
+        return len(self._timers) - 1
+
+    def timer_record(self, tid, which):
+        import time
+        self._timers[tid][which] = time.perf_counter()
+
+    def timer_elapsed_ms(self, tid):
+        return 1e3 * (self._timers[tid][1] - self._timers[tid][0])
+
+    def flush_l2(self):
+        pass
+
+    def comm_unique_id(self):
+        return b"\0" * 128
+
+    def comm_init(self, uid, nranks, rank):
+        self.nranks, self.rank = nranks, rank
+
+    def comm_size(self):
+        return self.nranks, self.rank
+
+    def allreduce_sum_f64(self, dev, count):
+        if self._allreduce_hook is not None:
+            v = _dense(dev, (count,))
+            v[...] = self._allreduce_hook(v.copy())
+
+    def comm_destroy(self):
+        self.nranks, self.rank = 1, 0
+
+    # ---- generic kernels --------------------------------------------------------
+    def ewise(self, op, shape, out, out_stride, ins, dtypes, in_strides, alpha=0.0, beta=0.0):
+        self._launches += 1
+        arrs = [_view(p, shape, st, np.uint8 if dt == U8 else np.float64).astype(np.float64)
+                for p, dt, st in zip(ins, dtypes, in_strides)]
+        a = arrs[0]
+        b = arrs[1] if len(arrs) > 1 else None
+        c = arrs[2] if len(arrs) > 2 else None
+        with np.errstate(all="ignore"):
+            if op == 0: r = a
+            elif op == 1: r = a + b
+            elif op == 2: r = a - b
+            elif op == 3: r = a * b
+            elif op == 4: r = a / b
+            elif op == 5: r = alpha * a + beta * b
+            elif op == 6: r = alpha * a + beta
+            elif op == 7: r = alpha * a * b + beta * c
+            elif op == 8: r = np.where(a != 0, b, c)
+            elif op == 9: r = np.log(a)
+            elif op == 10: r = np.exp(a)
+            elif op == 11: r = alpha / a
+            elif op == 12: r = a * a
+            elif op == 13: r = np.sqrt(a)
+            elif op == 14: r = sp.gammaln(a)                       # gamma.py:147
+            elif op == 15: r = sp.digamma(a)                       # gamma.py:145
+            elif op == 16: r = sp.multigammaln(a, int(alpha)) if np.ndim(a) == 0 else \
+                np.vectorize(lambda v: sp.multigammaln(v, int(alpha)))(a)   # wishart.py:187
+            elif op == 17: r = np.sum(sp.digamma(a[..., None] - 0.5 * np.arange(int(alpha))), axis=-1)  # misc.py:1146
+            elif op == 18: r = np.where(a != 0, b, 0.0)            # expfamily.py:463
+            else:
+                raise ValueError("bad op")
+        o = _view(out, shape, out_stride)
+        o[...] = r
+
+    def sum_multiply(self, shape, ins, dtypes, in_strides, out, out_stride, scale=1.0, accumulate=False):
+        """misc.py:851-933 (np.einsum over broadcast operands) / node.py:650."""
+        self._launches += 1
+        nd = len(shape)
+        arrs = [_view(p, shape, st, np.uint8 if dt == U8 else np.float64).astype(np.float64)
+                for p, dt, st in zip(ins, dtypes, in_strides)]
+        keys = list(range(nd))
+        kept = [d for d in keys if out_stride[d] != 0 or shape[d] == 1]
+        args = []
+        for a in arrs:
+            args += [a, keys]
+        r = np.einsum(*args, kept) if nd > 0 else np.prod([a for a in arrs])
+        kshape = [shape[d] for d in kept]
+        kstr = [out_stride[d] for d in kept]
+        o = _view(out, kshape, kstr)
+        if any(s == 0 for s in shape):
+            return
+        if accumulate:
+            o[...] = o + scale * r
+        else:
+            o[...] = scale * r
+
+    # ---- linalg (bayespy/utils/linalg.py) ----------------------------------------
+    def chol(self, A, U, batch, D, check=True):
+        """linalg.py:31-63: per-matrix scipy cho_factor (upper)."""
+        self._launches += 1
+        a = _dense(A, (batch, D, D))
+        u = _dense(U, (batch, D, D))
+        bad = False
+        for i in range(batch):
+            try:
+                f = scipy.linalg.cho_factor(a[i])[0]
+                u[i] = np.triu(f)
+            except (np.linalg.LinAlgError, ValueError):
+                u[i] = np.nan
+                bad = True
+        if bad and check:
+            raise NotPositiveDefinite("Matrix not positive definite")   # linalg.py:58-59
+
+    def chol_solve(self, U, batchU, B, batchB, X, batch, D, nrhs):
+        """linalg.py:66-171: per-matrix cho_solve."""
+        self._launches += 1
+        u = _dense(U, (batchU, D, D))
+        b = _dense(B, (batchB, D, nrhs))
+        x = _dense(X, (batch, D, nrhs))
+        for i in range(batch):
+            x[i] = scipy.linalg.cho_solve((u[0 if batchU == 1 else i], False), b[0 if batchB == 1 else i])
+
+    def chol_inv(self, U, Ainv, batch, D):
+        """linalg.py:174-207."""
+        self._launches += 1
+        u = _dense(U, (batch, D, D))
+        o = _dense(Ainv, (batch, D, D))
+        I = np.identity(D)
+        for i in range(batch):
+            o[i] = scipy.linalg.cho_solve((u[i], False), I)
+
+    def chol_logdet(self, U, out, batch, D):
+        """linalg.py:209-223."""
+        self._launches += 1
+        u = _dense(U, (batch, D, D))
+        _dense(out, (batch,))[...] = 2 * np.sum(np.log(np.einsum("...ii->...i", u)), axis=-1)
+
+    # ---- node kernels ----------------------------------------------------------------
+    def gaussian_moments(self, phi0, n0, phi1, n1, N, K, u0, cov, g, logdet, check=True):
+        """gaussian.py:672-706 / :397-446."""
+        self._launches += 1
+        p0 = _dense(phi0, (n0, K))
+        p1 = _dense(phi1, (n1, K, K))
+        covs = np.empty((n1, K, K))
+        lds = np.empty(n1)
+        I = np.identity(K)
+        bad = False
+        for i in range(n1):
+            try:
+                f = scipy.linalg.cho_factor(-2 * p1[i])
+                covs[i] = scipy.linalg.cho_solve(f, I)
+                lds[i] = 2 * np.sum(np.log(np.diag(f[0])))
+            except (np.linalg.LinAlgError, ValueError):
+                covs[i] = np.nan
+                lds[i] = np.nan
+                bad = True
+        if cov:
+            _dense(cov, (n1, K, K))[...] = covs
+        if logdet:
+            _dense(logdet, (n1,))[...] = lds
+        P0 = np.broadcast_to(p0, (N, K))
+        C = np.broadcast_to(covs, (N, K, K))
+        m = np.einsum("nij,nj->ni", C, P0)
+        if u0:
+            _dense(u0, (N, K))[...] = m
+        if g:
+            _dense(g, (N,))[...] = -0.5 * np.einsum("ni,ni->n", m, P0) + 0.5 * np.broadcast_to(lds, (N,))
+        if bad and check:
+            raise NotPositiveDefinite("Matrix not positive definite")
+
+    def outer_add(self, u0, cov, ncov, N, K, u1):
+        """gaussian.py:695: u1 = outer(u0,u0) + Cov."""
+        self._launches += 1
+        m = _dense(u0, (N, K))
+        r = m[:, :, None] * m[:, None, :]
+        if cov:
+            r = r + np.broadcast_to(_dense(cov, (ncov, K, K)), (N, K, K))
+        _dense(u1, (N, K, K))[...] = r
+
+    def gamma_moments(self, phi0, n0, phi1, n1, n, u0, u1, g, check=True):
+        """gamma.py:124-148."""
+        self._launches += 1
+        p0 = np.broadcast_to(_dense(phi0, (n0,)), (n,))
+        p1 = np.broadcast_to(_dense(phi1, (n1,)), (n,))
+        bad = bool(np.any(~(-p0 > 0)) or np.any(~(p1 > 0)))
+        with np.errstate(all="ignore"):
+            logb = np.log(-p0)
+            if u0: _dense(u0, (n,))[...] = p1 / (-p0)
+            if u1: _dense(u1, (n,))[...] = sp.digamma(p1) - logb
+            if g: _dense(g, (n,))[...] = p1 * logb - sp.gammaln(p1)
+        if bad and check:
+            raise ValueError("Natural parameters should be positive")
+
+    def wishart_moments(self, phi0, phi1, n1, n, D, u0, u1, g, check=True):
+        """wishart.py:165-188."""
+        self._launches += 1
+        p0 = _dense(phi0, (n, D, D))
+        p1 = np.broadcast_to(_dense(phi1, (n1,)), (n,))
+        I = np.identity(D)
+        bad = False
+        for i in range(n):
+            try:
+                f = scipy.linalg.cho_factor(-p0[i])
+                ld = 2 * np.sum(np.log(np.diag(f[0])))
+                inv = scipy.linalg.cho_solve(f, I)
+            except (np.linalg.LinAlgError, ValueError):
+                ld, inv, bad = np.nan, np.full((D, D), np.nan), True
+            if u0: _dense(u0, (n, D, D))[i] = p1[i] * inv
+            if u1: _dense(u1, (n,))[i] = -ld + np.sum(sp.digamma(p1[i] - 0.5 * np.arange(D)))
+            if g: _dense(g, (n,))[i] = p1[i] * ld - sp.multigammaln(p1[i], D)
+        if bad and check:
+            raise NotPositiveDefinite("Matrix not positive definite")
+
+    def dirichlet_moments(self, phi, n, K, u, g, check=True):
+        """dirichlet.py:130-160."""
+        self._launches += 1
+        p = _dense(phi, (n, K))
+        bad = bool(np.any(~(p > 0)))
+        with np.errstate(all="ignore"):
+            s = np.sum(p, axis=-1)
+            if u: _dense(u, (n, K))[...] = sp.psi(p) - sp.psi(s)[:, None]
+            if g: _dense(g, (n,))[...] = sp.gammaln(s) - np.sum(sp.gammaln(p), axis=-1)
+        if bad and check:
+            raise ValueError("Natural parameters should be positive")
+
+    def softmax_moments(self, phi, n, K, u, g):
+        """multinomial.py:101-121 with misc.py:1366-1401 (max-shift, second renormalisation)."""
+        self._launches += 1
+        p = _dense(phi, (n, K))
+        with np.errstate(all="ignore"):
+            m = np.amax(p, axis=-1, keepdims=True)
+            m = np.where(np.isfinite(m), m, 0.0)
+            lse = np.log(np.sum(np.exp(p - m), axis=-1, keepdims=True)) + m
+            q = np.exp(p - lse)
+            if u: _dense(u, (n, K))[...] = q / np.sum(q, axis=-1, keepdims=True)
+            if g: _dense(g, (n,))[...] = -lse[:, 0]
+
+    def one_hot(self, labels, n, K, u, check=True):
+        """categorical.py:30-47."""
+        self._launches += 1
+        l = _dense(labels, (n,), np.int64)
+        if check and (np.any(l < 0) or np.any(l >= K)):
+            raise ValueError("Invalid category index")
+        o = np.zeros((n, K))
+        ok = (l >= 0) & (l < K)
+        o[np.nonzero(ok)[0], l[ok]] = 1.0
+        _dense(u, (n, K))[...] = o
+
+    # ---- fused sweeps -----------------------------------------------------------------
+    def pca_xsweep(self, Y, M, N, K, A, b, X, stats):
+        """x_n = A y_n + b and the plate sums of dot.py:581 / :355,403 (see csrc/pca.cu)."""
+        self._launches += 1
+        y = _dense(Y, (M, N))
+        a = _dense(A, (K, M))
+        x = y.T @ a.T
+        if b:
+            x = x + _dense(b, (K,))
+        _dense(X, (N, K))[...] = x
+        self._pca_stats(y, x, M, N, K, stats)
+
+    def pca_stats(self, Y, M, N, K, X, stats):
+        self._launches += 1
+        self._pca_stats(_dense(Y, (M, N)), _dense(X, (N, K)), M, N, K, stats)
+
+    @staticmethod
+    def _pca_stats(y, x, M, N, K, stats):
+        s = _dense(stats, (M * K + K * K + K,))
+        s[:M * K] += (y @ x).ravel()
+        s[M * K:M * K + K * K] += (x.T @ x).ravel()
+        s[M * K + K * K:] += x.sum(axis=0)
+
+    def pca_xsweep_masked(self, Y, mask, M, N, K, W, WW, tau, alpha, amu, X, COV, g, stats, check=True):
+        """Per-column precision path (gaussian.py:672-706 with per-plate phi1; dot.py:581 with a mask)."""
+        self._launches += 1
+        y = _dense(Y, (M, N))
+        mk = _dense(mask, (M, N), np.uint8).astype(np.float64)
+        w = _dense(W, (M, K))
+        ww = _dense(WW, (M, K, K))
+        al = _dense(alpha, (K,))
+        am = _dense(amu, (K,)) if amu else np.zeros(K)
+        Lam = np.diag(al)[None] + tau * np.einsum("mn,mij->nij", mk, ww)
+        phi0 = tau * np.einsum("mn,mn,mk->nk", mk, y, w) + am
+        cov = np.linalg.inv(Lam)
+        x = np.einsum("nij,nj->ni", cov, phi0)
+        _dense(X, (N, K))[...] = x
+        if COV:
+            _dense(COV, (N, K, K))[...] = cov
+        if g:
+            _dense(g, (N,))[...] = -0.5 * np.einsum("ni,ni->n", x, phi0) + 0.5 * np.linalg.slogdet(Lam)[1]
+        xx = cov + x[:, :, None] * x[:, None, :]
+        s = _dense(stats, (M * K + M * K * K,))
+        s[:M * K] += np.einsum("mn,mn,nk->mk", mk, y, x).ravel()
+        s[M * K:] += np.einsum("mn,nij->mij", mk, xx).ravel()
+
+    def sumsq(self, Y, mask, count, out2):
+        self._launches += 1
+        y = _dense(Y, (count,))
+        o = _dense(out2, (2,))
+        if mask:
+            mk = _dense(mask, (count,), np.uint8) != 0
+            o[0] = np.sum(y[mk] ** 2)
+            o[1] = float(np.sum(mk))
+        else:
+            o[0] = np.sum(y ** 2)
+            o[1] = float(count)
+
+    def gmm_sweep(self, Y, N, D, K, c, h, Lam, logpi, P, g, stats):
+        """mixture.py:53-160 (index 0 and index>=1 messages) + multinomial.py:101-121, fused."""
+        self._launches += 1
+        y = _dense(Y, (N, D))
+        cc = _dense(c, (K,))
+        hh = _dense(h, (K, D))
+        LL = _dense(Lam, (K, D, D))
+        lp = _dense(logpi, (K,))
+        L = cc[None] + y @ hh.T - 0.5 * np.einsum("ni,kij,nj->nk", y, LL, y) + lp[None]
+        m = np.amax(L, axis=-1, keepdims=True)
+        lse = np.log(np.sum(np.exp(L - m), axis=-1, keepdims=True)) + m
+        q = np.exp(L - lse)
+        p = q / np.sum(q, axis=-1, keepdims=True)
+        if P: _dense(P, (N, K))[...] = p
+        if g: _dense(g, (N,))[...] = -lse[:, 0]
+        s = _dense(stats, (K + K * D + K * D * D + 1,))
+        s[:K] += p.sum(axis=0)
+        s[K:K + K * D] += (p.T @ y).ravel()
+        s[K + K * D:K + K * D + K * D * D] += np.einsum("nk,ni,nj->kij", p, y, y).ravel()
+        s[-1] += lse.sum()
