@@ -380,3 +380,165 @@ extern "C" int bpk_sumsq(const double *Y, const uint8_t *mask, int64_t count, do
     BPK_LAUNCH(sumsq_final_kernel, 1, 32, 0, partial, (int)blocks, out2);
     return BPK_OK;
 }
+
+// ---- masked variant (missing values): per-column precision -------------------------------
+// v0: one warp per column builds Lam_n = diag(alpha) + tau sum_m mask[m,n] <w_m w_m^T>
+// in shared memory, factors/inverts it with the warp-cooperative routines of linalg.cu,
+// and writes x_n, Cov_n, g_n.  The mask-weighted statistics are then two plate-sums over
+// n (bpk_sum_multiply).  TODO(next): fuse the statistics into the column kernel and move
+// the two M x K^2 contractions onto DMMA (they are GEMMs with the mask as one operand).
+#define MLD(D) ((D) | 1)
+__device__ __forceinline__ int m_warp_chol_upper(double *S, int D, int ld, int lane) {
+    int bad = 0;
+    for (int k = 0; k < D; ++k) {
+        double akk = S[k * ld + k];
+        if (!(akk > 0.0) || !isfinite(akk)) bad = 1;
+        double d = sqrt(akk), inv = 1.0 / d;
+        __syncwarp();
+        for (int j = k + lane; j < D; j += 32) S[k * ld + j] = (j == k) ? d : S[k * ld + j] * inv;
+        __syncwarp();
+        int m = D - k - 1;
+        for (int idx = lane; idx < m * m; idx += 32) {
+            int i = k + 1 + idx / m, j = k + 1 + idx % m;
+            if (j >= i) S[i * ld + j] -= S[k * ld + i] * S[k * ld + j];
+        }
+        __syncwarp();
+    }
+    return bad;
+}
+
+__global__ void pca_masked_cols_kernel(const double *__restrict__ Y, const uint8_t *__restrict__ mask,
+                                       int64_t M, int64_t N, int K,
+                                       const double *__restrict__ W, const double *__restrict__ WW,
+                                       double tau, const double *__restrict__ alpha, const double *__restrict__ amu,
+                                       double *__restrict__ X, double *__restrict__ COV, double *__restrict__ g,
+                                       int *flag) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int ld = MLD(K);
+    double *S = smem + (size_t)w * (2 * (size_t)K * ld + (size_t)K * 32 + K);
+    double *B = S + (size_t)K * ld;
+    double *C = B + (size_t)K * 32;
+    double *p0 = C + (size_t)K * ld;
+    for (int64_t n = (int64_t)blockIdx.x * nw + w; n < N; n += (int64_t)gridDim.x * nw) {
+        __syncwarp();
+        for (int e = lane; e < K * K; e += 32) {
+            int i = e / K, j = e - i * K;
+            double s = (i == j) ? alpha[i] : 0.0;
+            for (int64_t m = 0; m < M; ++m)
+                if (mask[m * N + n]) s += tau * WW[m * K * K + e];
+            S[i * ld + j] = s;
+        }
+        for (int k = lane; k < K; k += 32) {
+            double s = amu ? amu[k] : 0.0;
+            for (int64_t m = 0; m < M; ++m)
+                if (mask[m * N + n]) s += tau * Y[m * N + n] * W[m * K + k];
+            p0[k] = s;
+        }
+        __syncwarp();
+        int bad = m_warp_chol_upper(S, K, ld, lane);
+        if (bad && lane == 0) atomicOr(flag, BPK_FLAG_NOTSPD);
+        double ldt = 0.0;
+        for (int i = lane; i < K; i += 32) ldt += log(S[i * ld + i]);
+        ldt = 2.0 * warp_sum(ldt);
+        // inverse: lane-per-column solves against the identity
+        for (int c0 = 0; c0 < K; c0 += 32) {
+            int nc = K - c0 < 32 ? K - c0 : 32;
+            __syncwarp();
+            for (int e = lane; e < K * nc; e += 32) {
+                int i = e / nc, c = e % nc;
+                B[i * 32 + c] = (i == c0 + c) ? 1.0 : 0.0;
+            }
+            __syncwarp();
+            if (lane < nc) {
+                for (int i = 0; i < K; ++i) {
+                    double s = B[i * 32 + lane];
+                    for (int j = 0; j < i; ++j) s -= S[j * ld + i] * B[j * 32 + lane];
+                    B[i * 32 + lane] = s / S[i * ld + i];
+                }
+                for (int i = K - 1; i >= 0; --i) {
+                    double s = B[i * 32 + lane];
+                    for (int j = i + 1; j < K; ++j) s -= S[i * ld + j] * B[j * 32 + lane];
+                    B[i * 32 + lane] = s / S[i * ld + i];
+                }
+            }
+            __syncwarp();
+            for (int e = lane; e < K * nc; e += 32) {
+                int i = e / nc, c = e % nc;
+                C[i * ld + c0 + c] = B[i * 32 + c];
+            }
+        }
+        __syncwarp();
+        double dot = 0.0;
+        for (int i = lane; i < K; i += 32) {
+            double s = 0.0;
+            for (int j = 0; j < K; ++j) s += C[i * ld + j] * p0[j];
+            X[n * K + i] = s;
+            dot += s * p0[i];
+        }
+        dot = warp_sum(dot);
+        if (g && lane == 0) g[n] = -0.5 * dot + 0.5 * ldt;
+        if (COV)
+            for (int e = lane; e < K * K; e += 32) COV[n * K * K + e] = C[(e / K) * ld + (e % K)];
+    }
+}
+
+extern "C" int bpk_pca_xsweep_masked(const double *Y, const uint8_t *mask, int64_t M, int64_t N, int K,
+                                     const double *W, const double *WW, double tau,
+                                     const double *alpha, const double *amu,
+                                     double *X, double *COV, double *g, double *stats, int check) {
+    BPK_REQUIRE_INIT();
+    if (M < 1 || K < 1 || K > BPK_MAXDIM || N < 0) return bpk_set_error(BPK_EINVAL, "bpk_pca_xsweep_masked: bad shape");
+    if (N == 0) return BPK_OK;
+    const int ld = MLD(K);
+    size_t per = (2 * (size_t)K * ld + (size_t)K * 32 + K) * sizeof(double);
+    int nw = (int)((160u << 10) / per);
+    if (nw > 8) nw = 8;
+    if (nw < 1) nw = 1;
+    size_t smem = nw * per;
+    if (smem > (48u << 10))
+        BPK_CUDA(cudaFuncSetAttribute(pca_masked_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    double *cov = COV;
+    bool own_cov = false;
+    if (!cov) {
+        BPK_CUDA(cudaMallocAsync((void **)&cov, (size_t)N * K * K * sizeof(double), g_bpk.stream));
+        own_cov = true;
+    }
+    int64_t blocks = (N + nw - 1) / nw;
+    int64_t cap = (int64_t)g_bpk.sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    BPK_LAUNCH(pca_masked_cols_kernel, (unsigned)blocks, nw * 32, smem, Y, mask, M, N, K, W, WW, tau, alpha, amu,
+               X, cov, g, g_bpk.d_flag);
+    // statistics: S_yx[m,k] += sum_n mask y x ; S_xx[m,i,j] += sum_n mask (cov + x x^T)
+    int rc;
+    {
+        const void *in[3] = {mask, Y, X};
+        int dt[3] = {BPK_U8, BPK_F64, BPK_F64};
+        int64_t shape[3] = {M, N, K};
+        int64_t is[9] = {N, 1, 0, N, 1, 0, 0, K, 1};
+        int64_t os[3] = {K, 0, 1};
+        rc = bpk_sum_multiply(3, shape, 3, in, dt, is, stats, os, 1.0, 1);
+        if (rc) return rc;
+    }
+    {
+        const void *in[2] = {mask, cov};
+        int dt[2] = {BPK_U8, BPK_F64};
+        int64_t shape[3] = {M, N, (int64_t)K * K};
+        int64_t is[6] = {N, 1, 0, 0, (int64_t)K * K, 1};
+        int64_t os[3] = {(int64_t)K * K, 0, 1};
+        rc = bpk_sum_multiply(3, shape, 2, in, dt, is, stats + M * K, os, 1.0, 1);
+        if (rc) return rc;
+    }
+    {
+        const void *in[3] = {mask, X, X};
+        int dt[3] = {BPK_U8, BPK_F64, BPK_F64};
+        int64_t shape[4] = {M, N, K, K};
+        int64_t is[12] = {N, 1, 0, 0, 0, K, 1, 0, 0, K, 0, 1};
+        int64_t os[4] = {(int64_t)K * K, 0, K, 1};
+        rc = bpk_sum_multiply(4, shape, 3, in, dt, is, stats + M * K, os, 1.0, 1);
+        if (rc) return rc;
+    }
+    if (own_cov) BPK_CUDA(cudaFreeAsync(cov, g_bpk.stream));
+    if (check) return bpk_check_flag(BPK_ENOTSPD);
+    return BPK_OK;
+}

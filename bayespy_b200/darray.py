@@ -253,6 +253,8 @@ def asarray(x):
     """DArray (fp64) from a DArray / NumPy array / scalar."""
     if isinstance(x, DArray):
         return x
+    if hasattr(x, "materialize"):        # lazily produced device arrays (engine.plans, engine.gaussian)
+        return x.materialize()
     return DArray.from_numpy(np.asarray(x, dtype=np.float64), "f8")
 
 

@@ -229,7 +229,7 @@ class ExponentialFamily(Node):
             else:
                 lat = DArray.from_numpy(np.logical_not(self.observed), "u1").add_trailing(nd)
                 diff = D.axpby(1.0, phi_p[i], -T, D.where(lat, self.phi[i], D.asarray(0.0)))
-            ui = self.u[i]
+            ui = D.asarray(self.u[i])
             if self._guard_zero_times_inf:
                 diff = D.nonzero_select(ui, diff)
             nplate = max(ui.ndim, diff.ndim) - nd

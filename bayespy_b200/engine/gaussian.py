@@ -69,7 +69,7 @@ class FactoredSecondMoment:
 
 
 def dense(x):
-    return x.materialize() if isinstance(x, FactoredSecondMoment) else x
+    return x.materialize() if hasattr(x, "materialize") else x
 
 
 # --------------------------------------------------------------------------------------------
@@ -333,7 +333,9 @@ class GaussianARDDistribution(Distribution):
             # -1/2 (<x^2> - 2 <x><mu> + <mu^2>)
             t = D.fma(-2.0, x, mu, 1.0, x2)
             t = D.add(t, mu2)
-            return [D.mul(t, -0.5), D.asarray(0.5)]
+            # 0.5 * ones(shape): explicit over the variable axes like gaussian.py:633
+            half = DArray.full(self.shape, 0.5) if self.ndim else D.asarray(0.5)
+            return [D.mul(t, -0.5), half]
         raise ValueError("Invalid parent index")
 
     def compute_fixed_moments_and_f(self, x, mask=True):
@@ -341,11 +343,16 @@ class GaussianARDDistribution(Distribution):
         if self.ndim > 0 and x.shape[-self.ndim:] != self.shape:
             raise ValueError("Invalid shape")
         xd = D.asarray(x)
+        # the second moment of observed data is produced on first use only: the fused
+        # sweeps never read it, and at N=1e7 it would be another 5 GB of HBM writes
+        from .plans import LazyArray
         if self.ndim == 0:
-            xx = D.square(xd)
+            xx = LazyArray(xd.shape, lambda: D.square(xd))
         else:
             pl = x.shape[:x.ndim - self.ndim]
-            xx = D.mul(xd.add_trailing(self.ndim), xd.reshape(pl + (1,) * self.ndim + self.shape))
+            nd, shp = self.ndim, self.shape
+            xx = LazyArray(tuple(pl) + shp + shp,
+                           lambda: D.mul(xd.add_trailing(nd), xd.reshape(pl + (1,) * nd + shp)))
         return [xd, xx], -0.5 * self.K * LOG2PI
 
     def random(self, *phi, plates=None):

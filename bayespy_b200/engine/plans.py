@@ -1,5 +1,367 @@
-"""Fused sweep plans (filled in below)."""
+"""Fused sweep plans: sub-graphs that one pass over the data can serve.
+
+The reference recomputes every message on every request (node.py:657-688,
+deterministic.py:72-82), so a PCA sweep traverses the (M, N) data >= 6 times
+and materialises (N, K, K) second moments.  A *plan* recognises a sub-graph,
+and re-routes the handful of node methods whose cost scales with the plate
+count to fused kernels and to cached plate-summed sufficient statistics:
+
+FactorModelPlan   Y ~ GaussianARD(SumMultiply('k,k->', A, B), tau), observed,
+                  A plated (M,1), B plated (1,N)  (Bayesian PCA, pca.rst:40-66)
+
+    B.update()                     -> bpk_pca_xsweep: one pass over Y writes <b_n>
+                                      and accumulates S_yx, S_xx, s_x
+    F.message_to_parent(A)         -> from the statistics        (dot.py:581 sums over n)
+    Y.message_to_parent(tau)       -> from the statistics        (gaussian.py:2361-2369)
+    Y.lower_bound_contribution()   -> from the statistics        (expfamily.py:400-480)
+    B.lower_bound_contribution()   -> from the statistics
+
+The statistics are tagged with the version counter of the node they were
+computed from, so any update order the user chooses stays correct: a stale tag
+triggers ``bpk_pca_stats`` (one pass over Y and <B>) instead of reusing them.
+Whenever a precondition does not hold (missing values, annealing, plated tau,
+extra children ...) the plan steps aside and the generic path runs.
+"""
+import types
+
+import numpy as np
+
+from .. import _bpk
+from .. import darray as D
+from .. import parallel
+from ..darray import DArray
+from .dot import SumMultiply
+from .expfam import ExponentialFamily
+from .gamma import Gamma
+from .gaussian import GaussianARD, FactoredSecondMoment, dense, LOG2PI
+from .node import Constant, mask_is_full
+
+
+class LazyArray:
+    """Device array produced on first use (kept out of the sweep's HBM traffic)."""
+
+    def __init__(self, shape, fn):
+        self.shape = tuple(shape)
+        self._fn = fn
+        self._val = None
+
+    def materialize(self):
+        if self._val is None:
+            self._val = self._fn()
+            self._fn = None
+        return self._val
+
+    @property
+    def ndim(self):
+        return len(self.shape)
+
+    def numpy(self):
+        return self.materialize().numpy()
+
+    def __array__(self, dtype=None, copy=None):
+        return self.numpy()
+
+
+def _scalar_plates(node):
+    return all(n == 1 for n in node.plates)
+
+
+class FactorModelPlan:
+
+    def __init__(self, Y, F, row, col, i_row, i_col, tau):
+        self.Y, self.F, self.row, self.col, self.tau = Y, F, row, col, tau
+        self.i_row, self.i_col = i_row, i_col
+        self.M, self.N = Y.plates
+        self.K = row.dims[0][0]
+        # plate sharding: N is this rank's block; Ng the global column count
+        self.world = parallel.world()
+        self.Ng = int(round(float(np.sum(parallel.allgather_scalar(self.N))))) if self.world > 1 else self.N
+        self.kernel_timers = None     # bench.py: list of timer ids to record around the sweep kernel
+        self._timer_pos = 0
+        self._stats = None            # (col._version, DArray)
+        self._sumsq = None            # (Y._version, DArray[2])
+        self._e2 = None               # ((row._version, col._version), DArray scalar)
+        self._orig = {}
+        self.fused_calls = 0
+        self._install()
+
+    # ---- wiring ---------------------------------------------------------------------------------
+    def _install(self):
+        plan = self
+        o = self._orig
+        o["col.update"] = self.col.update
+        o["col.lb"] = self.col.lower_bound_contribution
+        o["F.msg"] = self.F.message_to_parent
+        o["Y.msg"] = self.Y.message_to_parent
+        o["Y.lb"] = self.Y.lower_bound_contribution
+
+        def col_update(node, annealing=1.0):
+            if annealing == 1.0 and plan.valid():
+                return plan.update_col()
+            return o["col.update"](annealing) if annealing != 1.0 else o["col.update"]()
+
+        def col_lb(node):
+            return plan.bound_col() if plan.valid() and plan._col_is_fused() else o["col.lb"]()
+
+        def F_msg(node, index):
+            if index == plan.i_row and plan.valid():
+                return plan.message_to_row()
+            return o["F.msg"](index)
+
+        def Y_msg(node, index):
+            if index == 1 and plan.valid():
+                return plan.message_to_tau()
+            return o["Y.msg"](index)
+
+        def Y_lb(node):
+            return plan.bound_Y() if plan.valid() else o["Y.lb"]()
+
+        self.col.update = types.MethodType(col_update, self.col)
+        self.col.lower_bound_contribution = types.MethodType(col_lb, self.col)
+        self.F.message_to_parent = types.MethodType(F_msg, self.F)
+        self.Y.message_to_parent = types.MethodType(Y_msg, self.Y)
+        self.Y.lower_bound_contribution = types.MethodType(Y_lb, self.Y)
+
+    def valid(self):
+        ok = self._valid()
+        if not ok and self.world > 1:
+            raise NotImplementedError("plate sharding is only supported on the fused path "
+                                      "(fully observed data, no annealing)")
+        return ok
+
+    def _valid(self):
+        Y, col, row = self.Y, self.col, self.row
+        if not (Y.observed is True or (isinstance(Y.observed, np.ndarray) and Y.observed.all())):
+            return False
+        if not mask_is_full(Y.mask):
+            return False
+        if any(n.annealing != 1.0 for n in (Y, col, row) if hasattr(n, "annealing")):
+            return False
+        if col.observed is not False or row.observed is not False:
+            return False
+        return True
+
+    def _col_is_fused(self):
+        return isinstance(self.col.u[1], FactoredSecondMoment) and \
+            all(n == 1 for n in self.col.u[1].cov.shape[:-2])
+
+    # ---- small shared quantities ---------------------------------------------------------------------
+    def _Yd(self):
+        return self.Y.u[0].contiguous()
+
+    def _tau_moments(self):
+        u = self.tau.get_moments()
+        return u[0].reshape(()), u[1].reshape(())
+
+    def _sum_second_moment(self, node, count):
+        """sum over the node's plates of <x x^T>  -> (K, K)."""
+        K = self.K
+        u1 = node.u[1]
+        if isinstance(u1, FactoredSecondMoment):
+            W = u1.u0.reshape((-1, K))
+            S = D.sum_product([W, W], [["m", "i"], ["m", "j"]], ["i", "j"])
+            cov = u1.cov.reshape((-1, K, K))
+            D.sum_product([cov], [["c", "i", "j"]], ["i", "j"], out=S, accumulate=True,
+                          scale=float(count) / cov.shape[0])
+            return S
+        u1 = D.asarray(u1).reshape((-1, K, K))
+        return D.sum_product([u1], [["m", "i", "j"]], ["i", "j"], scale=float(count) / u1.shape[0])
+
+    def _mean(self, node):
+        return node.u[0].reshape((-1, self.K))
+
+    def stats(self):
+        """[S_yx | S_xx | s_x] for the current posterior of the column factor."""
+        v = self.col._version
+        if self._stats is None or self._stats[0] != v:
+            M, N, K = self.M, self.N, self.K
+            st = DArray.zeros((M * K + K * K + K,))
+            X = self._mean(self.col)
+            if X.shape[0] != N:
+                X = self.col.u[0].broadcast_to((1, N, K)).reshape((N, K))
+            X = X.contiguous()
+            _bpk.get().pca_stats(self._Yd().ptr, M, N, K, X.ptr, st.ptr)
+            parallel.allreduce_sum(st)
+            self._stats = (v, st)
+        return self._split(self._stats[1])
+
+    def _split(self, st):
+        M, K = self.M, self.K
+        return (st.slice_axis(0, 0, M * K).reshape((M, K)),
+                st.slice_axis(0, M * K, M * K + K * K).reshape((K, K)),
+                st.slice_axis(0, M * K + K * K, M * K + K * K + K))
+
+    def _sum_xx(self):
+        """sum_n <x_n x_n^T> = sum_n Cov_n + S_xx."""
+        _, Sxx, _ = self.stats()
+        u1 = self.col.u[1]
+        if isinstance(u1, FactoredSecondMoment):
+            cov = u1.cov.reshape((-1, self.K, self.K))
+            if cov.shape[0] == 1:
+                return D.sum_product([cov], [["c", "i", "j"]], ["i", "j"], out=Sxx.copy(), accumulate=True,
+                                     scale=float(self.Ng))
+            if self.world > 1:
+                raise NotImplementedError("per-column covariances are not supported with plate sharding yet")
+            return D.sum_product([cov], [["c", "i", "j"]], ["i", "j"], out=Sxx.copy(), accumulate=True)
+        if self.world > 1:
+            raise NotImplementedError("dense second moments are not supported with plate sharding yet")
+        return self._sum_second_moment(self.col, self.N)
+
+    def _sumsq_y(self):
+        v = self.Y._version
+        if self._sumsq is None or self._sumsq[0] != v:
+            out = DArray.empty((2,))
+            _bpk.get().sumsq(self._Yd().ptr, 0, self.M * self.N, out.ptr)
+            parallel.allreduce_sum(out)
+            self._sumsq = (v, out)
+        return self._sumsq[1].slice_axis(0, 0, 1).reshape(())
+
+    def _E2(self):
+        """sum_mn <(y - f)^2> = sum y^2 - 2 <W>:S_yx + tr(sum_m<ww^T> sum_n<xx^T>)."""
+        key = (self.row._version, self.col._version)
+        if self._e2 is None or self._e2[0] != key:
+            Syx, _, _ = self.stats()
+            W = self._mean(self.row)
+            if W.shape[0] != self.M:
+                W = self.row.u[0].broadcast_to((self.M, 1, self.K)).reshape((self.M, self.K))
+            t1 = D.sum_product([W, Syx], [["m", "k"], ["m", "k"]], [])
+            t2 = D.sum_product([self._sum_second_moment(self.row, self.M), self._sum_xx()],
+                               [["i", "j"], ["i", "j"]], [])
+            e2 = D.add(D.axpby(1.0, self._sumsq_y(), -2.0, t1), t2)
+            self._e2 = (key, e2)
+        return self._e2[1]
+
+    # ---- fused node operations -----------------------------------------------------------------------
+    def update_col(self):
+        """col.update(): prior + messages + moments of the (1,N)-plated factor in one pass over Y."""
+        col, M, N, K = self.col, self.M, self.N, self.K
+        be = _bpk.get()
+        u_par = col.moments_from_parents()
+        phi_p = col._canonical_phi(col._distribution.compute_phi_from_parents(*u_par))
+        if not (all(n == 1 for n in phi_p[0].shape[:-1]) and all(n == 1 for n in phi_p[1].shape[:-2])):
+            return self._orig["col.update"]()          # prior differs per column: generic path
+        tau, _ = self._tau_moments()
+        SWW = self._sum_second_moment(self.row, M)
+        phi1 = D.fma(-0.5, tau, SWW, 1.0, phi_p[1])                        # (1,1,K,K)
+        phi0p = phi_p[0].reshape((1, K)).contiguous()
+        phi1c = phi1.reshape((1, K, K)).contiguous()
+        b = DArray.empty((K,))
+        cov = DArray.empty((1, 1, K, K))
+        logdet = DArray.empty(())
+        be.gaussian_moments(phi0p.ptr, 1, phi1c.ptr, 1, 1, K, b.ptr, cov.ptr, 0, logdet.ptr, True)
+        W = self._mean(self.row)
+        if W.shape[0] != M:
+            W = self.row.u[0].broadcast_to((M, 1, K)).reshape((M, K))
+        A = D.sum_product([tau, cov.reshape((K, K)), W], [[], ["k", "j"], ["m", "j"]], ["k", "m"])
+        X = DArray.empty((1, N, K))
+        st = DArray.zeros((M * K + K * K + K,))
+        Yd = self._Yd()
+        if self.kernel_timers is not None and self._timer_pos < len(self.kernel_timers):
+            tid = self.kernel_timers[self._timer_pos]
+            self._timer_pos += 1
+            be.timer_record(tid, 0)
+            be.pca_xsweep(Yd.ptr, M, N, K, A.ptr, b.ptr, X.ptr, st.ptr)
+            be.timer_record(tid, 1)
+        else:
+            be.pca_xsweep(Yd.ptr, M, N, K, A.ptr, b.ptr, X.ptr, st.ptr)
+        parallel.allreduce_sum(st)            # the one exchange step of the sweep
+        self.fused_calls += 1
+        # publish the new posterior; phi0 / g / <xx^T> stay virtual until somebody looks
+        Lam = D.mul(phi1.reshape((K, K)), -2.0)
+
+        def phi0_fn():
+            return D.sum_product([Lam, X], [["i", "j"], ["o", "n", "j"]], ["o", "n", "i"])
+
+        def g_fn():
+            q = D.sum_product([X, Lam, X], [["o", "n", "i"], ["i", "j"], ["o", "n", "j"]], ["o", "n"])
+            return D.axpby(-0.5, q, 0.5, logdet)
+        col.phi = [LazyArray((1, N, K), phi0_fn), phi1]
+        col.u = [X, FactoredSecondMoment(X, cov, (K,))]
+        col.g = LazyArray((1, N), g_fn)
+        col._version += 1
+        col._fused = dict(Lam=Lam, logdet=logdet, phi_p=phi_p, cov=cov)
+        self._stats = (col._version, st)
+
+    def message_to_row(self):
+        """F -> row factor:  m0[m] = tau S_yx[m],  m1 = -1/2 tau sum_n <x x^T>  (dot.py:581 summed over n)."""
+        tau, _ = self._tau_moments()
+        Syx, _, _ = self.stats()
+        M, K = self.M, self.K
+        m0 = D.mul(Syx, tau).reshape((M, 1, K))
+        m1 = D.mul(D.mul(self._sum_xx(), tau), -0.5).reshape((1, 1, K, K))
+        self.fused_calls += 1
+        return [m0, m1]
+
+    def message_to_tau(self):
+        """Y -> tau: [-1/2 sum <(y-f)^2>, 1/2 #obs] reduced to tau's plates (gaussian.py:2361-2369)."""
+        self.fused_calls += 1
+        shp = tuple(self.tau.plates)
+        m0 = D.mul(self._E2(), -0.5).reshape(shp)
+        m1 = D.asarray(0.5 * self.M * self.Ng).reshape(shp)
+        return [m0, m1]
+
+    def bound_Y(self):
+        """sum_mn <log N(y | f, 1/tau)> = -1/2 tau E2 + MN/2 (<log tau> - log 2pi)."""
+        tau, logtau = self._tau_moments()
+        MN = float(self.M) * float(self.Ng)
+        a = D.mul(D.mul(self._E2(), tau), -0.5)
+        return D.add(a, D.affine(logtau, 0.5 * MN, -0.5 * MN * LOG2PI))
+
+    def bound_col(self):
+        """E[log p(X)] - E[log q(X)] from the statistics (no pass over N)."""
+        col, N, K = self.col, self.Ng, self.K
+        fz = col._fused
+        u_par = col.moments_from_parents()
+        cgf = D.asarray(col._distribution.compute_cgf_from_parents(*u_par))     # per-plate, shared
+        _, Sxx, sx = self.stats()
+        Lam, logdet, phi_p, cov = fz["Lam"], fz["logdet"], fz["phi_p"], fz["cov"]
+        SXX = D.axpby(float(N), cov.reshape((K, K)), 1.0, Sxx)                  # sum_n <xx^T>
+        trLS = D.sum_product([Lam, Sxx], [["i", "j"], ["i", "j"]], [])           # sum_n x^T Lam x
+        # sum_n (phi0p - phi0q_n).x_n = phi0p.s_x - tr(Lam S_xx)
+        t0 = D.sub(D.sum_product([phi_p[0].reshape((K,)), sx], [["k"], ["k"]], []), trLS)
+        # sum_n (phi1p - phi1q):<xx^T>_n,  phi1q = -Lam/2
+        dphi1 = D.axpby(1.0, phi_p[1].reshape((K, K)), 0.5, Lam)
+        t1 = D.sum_product([dphi1, SXX], [["i", "j"], ["i", "j"]], [])
+        # -sum_n g_n = 1/2 tr(Lam S_xx) - N/2 logdet
+        mg = D.axpby(0.5, trLS, -0.5 * N, logdet)
+        ncgf = D.mul(D.reduce_to_shape(cgf, (), from_shape=col.plates), float(self.Ng) / float(self.N))
+        return D.add(D.add(D.add(t0, t1), mg), ncgf)
 
 
 def attach(model):
-    return []
+    """Find fusable sub-graphs among ``model`` and install their plans."""
+    plans = []
+    for Y in model:
+        if not isinstance(Y, GaussianARD) or len(Y.dims[0]) != 0 or len(Y.plates) != 2:
+            continue
+        if getattr(Y, "_plan", None) is not None:
+            plans.append(Y._plan)
+            continue
+        F, tau = Y.parents
+        if not isinstance(F, SumMultiply) or len(F.parents) != 2 or F.out_keys != []:
+            continue
+        if len(F.children) != 1 or Y.children:
+            continue
+        if not (isinstance(tau, (Gamma, Constant)) and _scalar_plates(tau)):
+            continue
+        A, B = F.parents
+        if not (isinstance(A, GaussianARD) and isinstance(B, GaussianARD)):
+            continue
+        if len(A.dims[0]) != 1 or A.dims[0] != B.dims[0] or F.in_keys[0] != F.in_keys[1]:
+            continue
+        if len(A.children) != 1 or len(B.children) != 1:
+            continue
+        M, N = Y.plates
+        pa, pb = tuple(A.plates), tuple(B.plates)
+        if pa == (M, 1) and pb == (1, N):
+            row, col, i_row, i_col = A, B, 0, 1
+        elif pb == (M, 1) and pa == (1, N):
+            row, col, i_row, i_col = B, A, 1, 0
+        else:
+            continue
+        if A.dims[0][0] > _bpk.MAXDIM:
+            continue
+        plan = FactorModelPlan(Y, F, row, col, i_row, i_col, tau)
+        Y._plan = plan
+        plans.append(plan)
+    return plans

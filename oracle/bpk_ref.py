@@ -93,6 +93,12 @@ class RefBackend:
     def memset(self, dev, byte, nbytes):
         ctypes.memset(dev, int(byte), int(nbytes))
 
+    def host_alloc(self, nbytes):
+        return self.malloc(nbytes)
+
+    def host_free(self, ptr):
+        self.free(ptr)
+
     def timer_create(self):
         self._timers.append([0.0, 0.0])
         return len(self._timers) - 1

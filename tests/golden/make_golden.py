@@ -1,0 +1,235 @@
+"""Generate the golden vectors in tests/golden/*.npz by running the UNMODIFIED
+reference (read-only at /root/reference) in the build container.
+
+    python tests/golden/make_golden.py
+
+The reference cannot travel to the GPU box, so its outputs are committed here
+as small fixtures; tests compare the oracle (CPU) and the CUDA path (GPU)
+against them.  ``h5py`` / ``truncnorm`` are stubbed (tests/golden/_stubs): both
+are imported by the reference at module import but never used on this path.
+"""
+import os
+import sys
+import warnings
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "_stubs"))
+sys.path.insert(0, "/root/reference")
+warnings.filterwarnings("ignore")
+
+import numpy as np                                            # noqa: E402
+import bayespy                                                # noqa: E402
+from bayespy.nodes import (GaussianARD, Gamma, SumMultiply, Gaussian, Wishart, Dirichlet,     # noqa: E402
+                           Categorical, Mixture)
+from bayespy.inference import VB                              # noqa: E402
+from bayespy.utils import misc, linalg, random                # noqa: E402
+
+assert bayespy.__file__.startswith("/root/reference"), bayespy.__file__
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+def node_state(prefix, node, out):
+    for i, u in enumerate(node.u):
+        out["%s_u%d" % (prefix, i)] = np.asarray(u)
+    for i, p in enumerate(node.phi):
+        out["%s_phi%d" % (prefix, i)] = np.asarray(p)
+    out["%s_g" % prefix] = np.asarray(node.g)
+
+
+def quickstart():
+    """doc/source/user_guide/quickstart.rst:8-118."""
+    np.random.seed(1)
+    data = np.random.normal(5, 10, size=(10,))
+    mu = GaussianARD(0, 1e-6)
+    tau = Gamma(1e-6, 1e-6)
+    y = GaussianARD(mu, tau, plates=(10,))
+    y.observe(data)
+    Q = VB(mu, tau, y)
+    Q.update(repeat=20, verbose=False)
+    out = dict(data=data, L=Q.L[:Q.iter], iters=Q.iter)
+    node_state("mu", mu, out)
+    node_state("tau", tau, out)
+    save("quickstart", **out)
+
+
+def pca(name, M, N, K, mask_p=None, iters=8):
+    """doc/source/examples/pca.rst:26-66 (no rotation), demos/pca.py:21-71."""
+    np.random.seed(1)
+    w = np.random.randn(M, 4)
+    x = np.random.randn(N, 4)
+    y = w @ x.T + 0.1 * np.random.randn(M, N)
+    X = GaussianARD(0, 1, plates=(1, N), shape=(K,))
+    alpha = Gamma(1e-5, 1e-5, plates=(K,))
+    C = GaussianARD(0, alpha, plates=(M, 1), shape=(K,))
+    F = SumMultiply('d,d->', X, C)
+    tau = Gamma(1e-5, 1e-5)
+    Y = GaussianARD(F, tau)
+    out = dict(y=y)
+    if mask_p is not None:
+        mask = random.mask(M, N, p=mask_p)
+        Y.observe(y, mask=mask)
+        out["mask"] = mask
+    else:
+        Y.observe(y)
+    C.initialize_from_random()
+    out["C_init"] = np.array(C.u[0], copy=True)
+    Q = VB(Y, X, C, alpha, tau)
+    Q.update(repeat=iters, verbose=False, tol=0)
+    out["L"] = Q.L[:Q.iter]
+    out["l_Y"], out["l_X"], out["l_C"] = Q.l[Y][:Q.iter], Q.l[X][:Q.iter], Q.l[C][:Q.iter]
+    out["l_alpha"], out["l_tau"] = Q.l[alpha][:Q.iter], Q.l[tau][:Q.iter]
+    for nm, node in (("X", X), ("C", C), ("alpha", alpha), ("tau", tau)):
+        node_state(nm, node, out)
+    # messages arriving at the stochastic parents (reference-format composite messages)
+    mC = C._message_from_children()
+    out["msgC0"], out["msgC1"] = mC[0], mC[1]
+    mt = tau._message_from_children()
+    out["msgtau0"], out["msgtau1"] = np.asarray(mt[0]), np.asarray(mt[1])
+    save(name, **out)
+
+
+def linalg_vectors():
+    """bayespy/utils/linalg.py:31-223 on random SPD stacks."""
+    rng = np.random.RandomState(7)
+    out = {}
+    for D in (1, 3, 8, 16, 33):
+        A = rng.randn(5, 2, D, D)
+        A = A @ np.swapaxes(A, -1, -2) + D * np.identity(D)
+        b = rng.randn(5, 2, D)
+        B = rng.randn(1, 2, D, 4)
+        U = linalg.chol(A)
+        out["A%d" % D], out["b%d" % D], out["B%d" % D] = A, b, B
+        out["U%d" % D] = np.triu(U)
+        out["solve%d" % D] = linalg.chol_solve(U, b)
+        out["solveM%d" % D] = linalg.chol_solve(U, B * np.ones((5, 1, 1, 1)), matrix=True)
+        out["inv%d" % D] = linalg.chol_inv(U)
+        out["logdet%d" % D] = linalg.chol_logdet(U)
+    save("linalg", **out)
+
+
+def summul_vectors():
+    """bayespy/utils/misc.py:805-945."""
+    rng = np.random.RandomState(11)
+    a = rng.randn(4, 1, 5)
+    b = rng.randn(3, 5)
+    c = rng.randn(5)
+    out = dict(a=a, b=b, c=c)
+    out["r0"] = misc.sum_multiply(a, b, c)
+    out["r1"] = misc.sum_multiply(a, b, c, axis=-1)
+    out["r2"] = misc.sum_multiply(a, b, c, axis=(0, 2), keepdims=True)
+    out["r3"] = misc.sum_multiply(a, b, axis=[1], sumaxis=False)
+    out["r4"] = misc.sum_product(a, b, c, axes_to_keep=[0, 2])
+    out["r5"] = misc.sum_product(a, b, axes_to_sum=[-2], keepdims=True)
+    out["p0"] = misc.sum_multiply_to_plates(a, b, to_plates=(3, 1), from_plates=(4, 3, 5))
+    out["p1"] = misc.sum_multiply_to_plates(a, b, to_plates=(1,), from_plates=(4, 3, 5))
+    out["p2"] = misc.sum_multiply_to_plates(c, to_plates=(), from_plates=(6, 5))
+    A = rng.randn(4, 3, 2, 2)
+    out["A"] = A
+    out["p3"] = misc.sum_multiply_to_plates(A, to_plates=(3,), from_plates=(4, 3), ndim=2)
+    save("summul", **out)
+
+
+def distribution_vectors():
+    """compute_moments_and_cgf of the scalar/simplex families on random phi."""
+    from bayespy.inference.vmp.nodes.gamma import GammaDistribution
+    from bayespy.inference.vmp.nodes.wishart import WishartDistribution
+    from bayespy.inference.vmp.nodes.dirichlet import DirichletDistribution
+    from bayespy.inference.vmp.nodes.categorical import CategoricalDistribution
+    from bayespy.inference.vmp.nodes.gaussian import GaussianARDDistribution
+    rng = np.random.RandomState(3)
+    out = {}
+    phi = [-rng.gamma(2.0, 1.0, size=(7, 3)), rng.gamma(3.0, 1.0, size=(7, 3)) + 0.01]
+    (u, g) = GammaDistribution().compute_moments_and_cgf(phi)
+    out.update(gam_phi0=phi[0], gam_phi1=phi[1], gam_u0=u[0], gam_u1=u[1], gam_g=g)
+    D = 4
+    V = rng.randn(6, D, D)
+    V = V @ np.swapaxes(V, -1, -2) + np.identity(D)
+    phi = [-0.5 * V, 0.5 * (D + rng.gamma(2.0, 2.0, size=(6,)))]
+    (u, g) = WishartDistribution().compute_moments_and_cgf(phi)
+    out.update(wis_phi0=phi[0], wis_phi1=phi[1], wis_u0=u[0], wis_u1=u[1], wis_g=g)
+    phi = [rng.gamma(1.0, 2.0, size=(5, 6)) + 1e-3]
+    (u, g) = DirichletDistribution().compute_moments_and_cgf(phi)
+    out.update(dir_phi0=phi[0], dir_u0=u[0], dir_g=g)
+    phi = [5 * rng.randn(9, 6)]
+    (u, g) = CategoricalDistribution(6).compute_moments_and_cgf(phi)
+    out.update(cat_phi0=phi[0], cat_u0=u[0], cat_g=g)
+    K = 5
+    L = rng.randn(8, K, K)
+    L = L @ np.swapaxes(L, -1, -2) + np.identity(K)
+    phi = [rng.randn(8, K), -0.5 * L]
+    (u, g) = GaussianARDDistribution((K,)).compute_moments_and_cgf(phi)
+    out.update(gau_phi0=phi[0], gau_phi1=phi[1], gau_u0=u[0], gau_u1=u[1], gau_g=g)
+    phi = [rng.randn(8, K), -0.5 * L[:1]]
+    (u, g) = GaussianARDDistribution((K,)).compute_moments_and_cgf(phi)
+    out.update(gaus_phi0=phi[0], gaus_phi1=phi[1], gaus_u0=u[0], gaus_u1=u[1], gaus_g=g)
+    save("distributions", **out)
+
+
+def gmm(name, N, D, K, iters=10):
+    """doc/source/examples/gmm.rst:71-98 on blobs (demos/stochastic_inference.py:49-54 pattern)."""
+    np.random.seed(1)
+    means = 5 * np.random.randn(K, D)
+    z = np.random.randint(0, K, size=N)
+    y = means[z] + np.random.randn(N, D)
+    alpha = Dirichlet(1e-5 * np.ones(K))
+    Z = Categorical(alpha, plates=(N,))
+    mu = Gaussian(np.zeros(D), 1e-5 * np.identity(D), plates=(K,))
+    Lambda = Wishart(D, 1e-5 * np.identity(D), plates=(K,))
+    Y = Mixture(Z, Gaussian, mu, Lambda)
+    Z.initialize_from_random()
+    out = dict(y=y, Z_init=np.array(Z.u[0], copy=True))
+    Y.observe(y)
+    Q = VB(Y, mu, Lambda, Z, alpha)
+    Q.update(repeat=iters, verbose=False, tol=0)
+    out["L"] = Q.L[:Q.iter]
+    for nm, node in (("Z", Z), ("mu", mu), ("Lambda", Lambda), ("alpha", alpha)):
+        node_state(nm, node, out)
+        out["l_" + nm] = Q.l[node][:Q.iter]
+    out["l_Y"] = Q.l[Y][:Q.iter]
+    save(name, **out)
+
+
+def gmm_doc():
+    """doc/source/examples/gmm.rst:8-118: literal doctest trajectory (-1.402345e+03 ... -8.888464e+02)."""
+    np.random.seed(1)
+    y0 = np.random.multivariate_normal([0, 0], [[2, 0], [0, 0.1]], size=50)
+    y1 = np.random.multivariate_normal([0, 0], [[0.1, 0], [0, 2]], size=50)
+    y2 = np.random.multivariate_normal([2, 2], [[2, -1.5], [-1.5, 2]], size=50)
+    y3 = np.random.multivariate_normal([-2, -2], [[0.5, 0], [0, 0.5]], size=50)
+    y = np.vstack([y0, y1, y2, y3])
+    N, D, K = 200, 2, 10
+    alpha = Dirichlet(1e-5 * np.ones(K), name='alpha')
+    Z = Categorical(alpha, plates=(N,), name='z')
+    mu = Gaussian(np.zeros(D), 1e-5 * np.identity(D), plates=(K,), name='mu')
+    Lambda = Wishart(D, 1e-5 * np.identity(D), plates=(K,), name='Lambda')
+    Y = Mixture(Z, Gaussian, mu, Lambda, name='Y')
+    Z.initialize_from_random()
+    Zi = np.array(Z.u[0], copy=True)
+    Q = VB(Y, mu, Lambda, Z, alpha)
+    Y.observe(y)
+    Q.update(repeat=1000, verbose=False)
+    save("gmm_doc", y=y, Z_init=Zi, L=Q.L[:Q.iter], iters=Q.iter)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["quickstart", "pca", "linalg", "summul", "dist", "gmm"]
+    if "quickstart" in which:
+        quickstart()
+    if "pca" in which:
+        pca("pca_small", 20, 100, 5)
+        pca("pca_64x16", 64, 96, 16, iters=5)
+        pca("pca_masked", 12, 40, 4, mask_p=0.8)
+    if "linalg" in which:
+        linalg_vectors()
+    if "summul" in which:
+        summul_vectors()
+    if "dist" in which:
+        distribution_vectors()
+    if "gmm" in which:
+        gmm("gmm_small", 300, 3, 5)
+        gmm_doc()

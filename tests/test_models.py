@@ -1,0 +1,148 @@
+"""Model-level parity against golden vectors produced by the unmodified reference
+(tests/golden/make_golden.py): posterior u / phi / g of every node and the per-sweep
+lower bound Q.L, rtol 1e-6 (north_star: 1e-5).  backend='oracle' checks the host-side
+graph logic on CPU; backend='cuda' (-m gpu) is the end-to-end parity test of the kernels."""
+import numpy as np
+import pytest
+
+from conftest import golden
+
+RTOL = 1e-6
+
+
+def close(a, b, rtol=RTOL, atol=1e-9):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol)
+
+
+def check_node(g, name, node, skip_g=False):
+    for i in range(len(node.u)):
+        close(node.u[i], g["%s_u%d" % (name, i)])
+        close(node.phi[i], g["%s_phi%d" % (name, i)])
+    if not skip_g:
+        close(node.g, g["%s_g" % name])
+
+
+def test_quickstart(backend, capsys):
+    """doc/source/user_guide/quickstart.rst:8-118 — loglike -6.020956e+01 ... converged at 4."""
+    from bayespy_b200.nodes import GaussianARD, Gamma
+    from bayespy_b200.inference import VB
+    g = golden("quickstart")
+    np.random.seed(1)
+    data = np.random.normal(5, 10, size=(10,))
+    assert np.array_equal(data, g["data"])
+    mu = GaussianARD(0, 1e-6)
+    tau = Gamma(1e-6, 1e-6)
+    y = GaussianARD(mu, tau, plates=(10,))
+    y.observe(data)
+    Q = VB(mu, tau, y)
+    Q.update(repeat=20)
+    out = capsys.readouterr().out
+    assert "Iteration 1: loglike=-6.020956e+01" in out
+    assert "Iteration 4: loglike=-5.820288e+01" in out
+    assert "Converged at iteration 4." in out
+    assert Q.iter == int(g["iters"])
+    close(Q.L[:Q.iter], g["L"], rtol=1e-9)
+    check_node(g, "mu", mu)
+    check_node(g, "tau", tau)
+
+
+def build_pca(g, M, N, K, fused, seeded_init=True):
+    from bayespy_b200.nodes import GaussianARD, Gamma, SumMultiply
+    from bayespy_b200.inference import VB
+    from bayespy_b200.utils import random
+    np.random.seed(1)
+    w = np.random.randn(M, 4)
+    x = np.random.randn(N, 4)
+    y = w @ x.T + 0.1 * np.random.randn(M, N)
+    assert np.array_equal(y, g["y"])
+    X = GaussianARD(0, 1, plates=(1, N), shape=(K,), name="X")
+    alpha = Gamma(1e-5, 1e-5, plates=(K,), name="alpha")
+    C = GaussianARD(0, alpha, plates=(M, 1), shape=(K,), name="C")
+    F = SumMultiply("d,d->", X, C)
+    tau = Gamma(1e-5, 1e-5, name="tau")
+    Y = GaussianARD(F, tau, name="Y")
+    if "mask" in g.files:
+        mask = random.mask(M, N, p=0.8)
+        assert np.array_equal(mask, g["mask"])
+        Y.observe(y, mask=mask)
+    else:
+        Y.observe(y)
+    if seeded_init:
+        C.initialize_from_random()          # host RNG parity with the reference stream
+        close(C.u[0], g["C_init"], rtol=1e-12)
+    else:
+        C.initialize_from_value(g["C_init"])
+    Q = VB(Y, X, C, alpha, tau, fused=fused)
+    return Q, dict(X=X, C=C, alpha=alpha, tau=tau, Y=Y, F=F)
+
+
+@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("name,M,N,K", [("pca_small", 20, 100, 5), ("pca_64x16", 64, 96, 16)])
+def test_pca(backend, name, M, N, K, fused):
+    g = golden(name)
+    Q, n = build_pca(g, M, N, K, fused)
+    iters = len(g["L"])
+    Q.update(repeat=iters, verbose=False, tol=0)
+    close(Q.L[:iters], g["L"], rtol=1e-8)
+    for nm in ("Y", "X", "C", "alpha", "tau"):
+        close(Q.l[n[nm]][:iters], g["l_" + nm], rtol=1e-7, atol=1e-7)
+    for nm in ("X", "C", "alpha", "tau"):
+        check_node(g, nm, n[nm])
+    if fused:
+        assert len(Q.plans) == 1 and Q.plans[0].fused_calls > 0
+    # composite messages arriving at the stochastic parents
+    mC = n["C"].message_from_children()
+    close(mC[0], g["msgC0"]); close(mC[1], g["msgC1"])
+    mt = n["tau"].message_from_children()
+    close(mt[0], g["msgtau0"]); close(mt[1], g["msgtau1"])
+
+
+def test_pca_masked_generic(backend):
+    """Missing values (random.mask, p=0.8): per-plate covariances, masks and broadcasting."""
+    g = golden("pca_masked")
+    Q, n = build_pca(g, 12, 40, 4, fused=False)
+    iters = len(g["L"])
+    Q.update(repeat=iters, verbose=False, tol=0)
+    close(Q.L[:iters], g["L"], rtol=1e-8)
+    for nm in ("X", "C", "alpha", "tau"):
+        check_node(g, nm, n[nm])
+
+
+def test_pca_update_order_independent_of_plan(backend):
+    """Arbitrary user update orders give the same answer with and without the fused plan
+    (stale statistics must be detected through the version tags)."""
+    g = golden("pca_small")
+    order = ("tau", "C", "X", "alpha", "C", "tau", "X")
+    res = []
+    for fused in (False, True):
+        Q, n = build_pca(g, 20, 100, 5, fused)
+        for _ in range(3):
+            Q.update(*order, verbose=False, tol=0)
+        res.append((Q.L[:3].copy(), np.asarray(n["X"].u[0]), np.asarray(n["C"].u[1])))
+    close(res[0][0], res[1][0], rtol=1e-9)
+    close(res[0][1], res[1][1], rtol=1e-8)
+    close(res[0][2], res[1][2], rtol=1e-8)
+
+
+def test_vb_api(backend, capsys):
+    """VB bookkeeping: duplicate removal, lookup by name, tol / converged, histories."""
+    from bayespy_b200.nodes import GaussianARD, Gamma
+    from bayespy_b200.inference import VB
+    np.random.seed(3)
+    mu = GaussianARD(0, 1e-3, name="mu")
+    tau = Gamma(1e-3, 1e-3, name="tau")
+    y = GaussianARD(mu, tau, plates=(50,), name="y")
+    y.observe(np.random.randn(50) + 2)
+    Q = VB(y, mu, tau, mu)
+    assert Q.model == [y, mu, tau]
+    assert Q["mu"] is mu
+    with pytest.raises(ValueError):
+        VB(y, 3)
+    Q.update(repeat=100, tol=1e-8, verbose=False)
+    assert Q.has_converged() and Q.iter < 100
+    assert len(Q.L) >= Q.iter and np.all(np.diff(Q.L[:Q.iter]) > -1e-6)
+    assert abs(Q.compute_lowerbound() - Q.L[Q.iter - 1]) < 1e-8 * abs(Q.L[Q.iter - 1])
+    terms = Q.compute_lowerbound_terms()
+    assert abs(sum(terms.values()) - Q.L[Q.iter - 1]) < 1e-8 * abs(Q.L[Q.iter - 1])
