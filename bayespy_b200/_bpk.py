@@ -79,6 +79,7 @@ PROTOTYPES = {
                                         _dp, _dp, _dp, _dp, C.c_int]),
     "bpk_sumsq": (C.c_int, [_dp, _vp, C.c_int64, _dp]),
     "bpk_gmm_sweep": (C.c_int, [_dp, C.c_int64, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
+    "bpk_gmm_stats": (C.c_int, [_dp, C.c_int64, C.c_int, C.c_int, _dp, _dp]),
 }
 
 
@@ -278,6 +279,10 @@ class CudaBackend:
 
     def gmm_sweep(self, Y, N, D, K, c, h, Lam, logpi, P, g, stats):
         self._chk(self.lib.bpk_gmm_sweep(Y, N, D, K, c, h, Lam, logpi, P, g, stats))
+
+
+    def gmm_stats(self, Y, N, D, K, P, stats):
+        self._chk(self.lib.bpk_gmm_stats(Y, N, D, K, P, stats))
 
 
 _backend = None

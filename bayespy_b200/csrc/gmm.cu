@@ -31,6 +31,7 @@ struct GmmArgs {
     int D, K;
     const double *c, *h, *Lam, *logpi;
     double *P, *g, *partial;
+    int given_p;        // 1: P is an input (statistics only), 0: E-step + statistics
     int nfeat;          // 1 + D + D*D
     int per_thread;     // ceil(K*nfeat / 128)
 };
@@ -47,9 +48,11 @@ __global__ void __launch_bounds__(GMM_ROWS, 1) gmm_sweep_kernel(GmmArgs a) {
     double *sZ = sP + GMM_ROWS * ldp;      // [ROWS][F]   features 1, y_i, y_i y_j
     __shared__ double red[GMM_ROWS / 32];
     const int t = threadIdx.x;
-    for (int e = t; e < K; e += GMM_ROWS) sc[e] = a.c[e] + a.logpi[e];
-    for (int e = t; e < K * D; e += GMM_ROWS) sh[e] = a.h[e];
-    for (int e = t; e < K * D * D; e += GMM_ROWS) sL[e] = a.Lam[e];
+    if (!a.given_p) {
+        for (int e = t; e < K; e += GMM_ROWS) sc[e] = a.c[e] + a.logpi[e];
+        for (int e = t; e < K * D; e += GMM_ROWS) sh[e] = a.h[e];
+        for (int e = t; e < K * D * D; e += GMM_ROWS) sL[e] = a.Lam[e];
+    }
     double acc[PT];
 #pragma unroll
     for (int i = 0; i < PT; ++i) acc[i] = 0.0;
@@ -76,6 +79,16 @@ __global__ void __launch_bounds__(GMM_ROWS, 1) gmm_sweep_kernel(GmmArgs a) {
         sZ[t * F] = live ? 1.0 : 0.0;
         for (int i = 0; i < D; ++i)
             for (int j = 0; j < D; ++j) sZ[t * F + 1 + D + i * D + j] = y[i] * y[j];
+        double lse = 0.0;
+        if (a.given_p) {
+            // responsibilities are an input: stage them (coalesced) and skip the E-step
+            __syncthreads();
+            const int64_t pbase = tile * GMM_ROWS * K;
+            int64_t plim = a.N * K - pbase;
+            if (plim > (int64_t)GMM_ROWS * K) plim = (int64_t)GMM_ROWS * K;
+            for (int e = t; e < GMM_ROWS * K; e += GMM_ROWS)
+                sP[(e / K) * ldp + (e % K)] = e < plim ? a.P[pbase + e] : 0.0;
+        } else {
         // log-evidence of each component (mixture.py:58-106)
         double m = -INFINITY;
         for (int k = 0; k < K; ++k) {
@@ -94,7 +107,7 @@ __global__ void __launch_bounds__(GMM_ROWS, 1) gmm_sweep_kernel(GmmArgs a) {
         double mm = isfinite(m) ? m : 0.0;
         double s = 0.0;
         for (int k = 0; k < K; ++k) s += exp(sP[t * ldp + k] - mm);
-        double lse = log(s) + mm;
+        lse = log(s) + mm;
         double s2 = 0.0;
         for (int k = 0; k < K; ++k) {
             double p = exp(sP[t * ldp + k] - lse);
@@ -105,13 +118,14 @@ __global__ void __launch_bounds__(GMM_ROWS, 1) gmm_sweep_kernel(GmmArgs a) {
             double p = live ? sP[t * ldp + k] / s2 : 0.0;
             sP[t * ldp + k] = p;
         }
-        if (live) {
+        }
+        if (live && !a.given_p) {
             lse_acc += lse;
             if (a.g) a.g[n] = -lse;
         }
         __syncthreads();
         // coalesced store of the responsibilities
-        if (a.P) {
+        if (a.P && !a.given_p) {
             const int64_t base = tile * GMM_ROWS * K;
             int64_t lim = a.N * K - base;
             if (lim > (int64_t)GMM_ROWS * K) lim = (int64_t)GMM_ROWS * K;
@@ -164,15 +178,32 @@ __global__ void gmm_final_kernel(const double *__restrict__ partial, int nblocks
     stats[e] += s;
 }
 
+static int gmm_run(const double *Y, int64_t N, int D, int K,
+                   const double *c, const double *h, const double *Lam, const double *logpi,
+                   double *P, double *g, double *stats, int given_p);
+
 extern "C" int bpk_gmm_sweep(const double *Y, int64_t N, int D, int K,
                              const double *c, const double *h, const double *Lam, const double *logpi,
                              double *P, double *g, double *stats) {
     BPK_REQUIRE_INIT();
+    return gmm_run(Y, N, D, K, c, h, Lam, logpi, P, g, stats, 0);
+}
+
+extern "C" int bpk_gmm_stats(const double *Y, int64_t N, int D, int K, const double *P, double *stats) {
+    BPK_REQUIRE_INIT();
+    if (!P) return bpk_set_error(BPK_EINVAL, "bpk_gmm_stats: P is required");
+    return gmm_run(Y, N, D, K, nullptr, nullptr, nullptr, nullptr, const_cast<double *>(P), nullptr, stats, 1);
+}
+
+static int gmm_run(const double *Y, int64_t N, int D, int K,
+                   const double *c, const double *h, const double *Lam, const double *logpi,
+                   double *P, double *g, double *stats, int given_p) {
     if (D < 1 || D > GMM_MAXD) return bpk_set_error(BPK_EINVAL, "bpk_gmm_sweep: D=%d outside [1,%d]", D, GMM_MAXD);
     if (K < 1 || K > GMM_MAXK) return bpk_set_error(BPK_EINVAL, "bpk_gmm_sweep: K=%d outside [1,%d]", K, GMM_MAXK);
     if (N <= 0) return BPK_OK;
     GmmArgs a;
     a.Y = Y; a.N = N; a.D = D; a.K = K; a.c = c; a.h = h; a.Lam = Lam; a.logpi = logpi; a.P = P; a.g = g;
+    a.given_p = given_p;
     a.nfeat = 1 + D + D * D;
     a.per_thread = (K * a.nfeat + GMM_ROWS - 1) / GMM_ROWS;
     size_t smem = ((size_t)K * (1 + D + D * D) + (size_t)GMM_ROWS * ((K | 1) + a.nfeat)) * sizeof(double);

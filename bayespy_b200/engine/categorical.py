@@ -1,0 +1,100 @@
+"""Categorical node on device (replaces nodes/categorical.py:87-201 and the softmax of
+nodes/multinomial.py:101-121 / misc.py:1366-1401).  One-hot encoding of integer labels is
+index work and is bit-exact (``bpk_one_hot``)."""
+import numpy as np
+
+from .. import _bpk
+from .. import darray as D
+from ..darray import DArray
+from .dirichlet import dirichlet_constant
+from .expfam import Distribution, ExponentialFamily
+from .node import Constant, Node
+
+
+def one_hot(x, K):
+    x = np.asarray(x)
+    if not np.issubdtype(x.dtype, np.integer):
+        if np.any(x != np.floor(x)):
+            raise ValueError("Values must be integers")
+        x = x.astype(np.int64)
+    if np.any(x < 0) or np.any(x >= K):
+        raise ValueError("Invalid category index")
+    lab = DArray.from_numpy(np.ascontiguousarray(x, dtype=np.int64).reshape(x.shape), "i8")
+    out = DArray.empty(tuple(x.shape) + (K,))
+    _bpk.get().one_hot(lab.ptr, int(x.size), K, out.ptr, True)
+    return out
+
+
+def categorical_constant(x, K):
+    x = np.asarray(x)
+    return Constant("categorical", [one_hot(x, K)], dims=((K,),), plates=x.shape, value=x)
+
+
+class CategoricalDistribution(Distribution):
+
+    def __init__(self, categories):
+        if not isinstance(categories, (int, np.integer)):
+            raise ValueError("Number of categories must be integer")
+        if categories < 0:
+            raise ValueError("Number of categoriess must be non-negative")
+        self.D = int(categories)
+
+    def compute_message_to_parent(self, parent, index, u, u_p):
+        if index == 0:
+            return [u[0]]
+        raise ValueError("Index out of bounds")
+
+    def compute_phi_from_parents(self, u_p, mask=True):
+        return [u_p[0]]
+
+    def compute_cgf_from_parents(self, u_p):
+        return D.asarray(0.0)
+
+    def compute_moments_and_cgf(self, phi, mask=True):
+        """softmax with the reference's max-shift and second renormalisation; g = -logsumexp."""
+        p = phi[0].contiguous()
+        K = p.shape[-1]
+        P = tuple(p.shape[:-1])
+        n = int(np.prod(P, dtype=np.int64)) if P else 1
+        u, g = DArray.empty(P + (K,)), DArray.empty(P)
+        _bpk.get().softmax_moments(p.ptr, n, K, u.ptr, g.ptr)
+        return [u], g
+
+    def compute_fixed_moments_and_f(self, x, mask=True):
+        return [one_hot(x, self.D)], 0.0
+
+    def random(self, *phi, plates=None):
+        """Host draw, same call pattern as categorical.py:117-124 + utils/random.py:247-288."""
+        logp = np.array(phi[0])
+        logp -= np.amax(logp, axis=-1, keepdims=True)
+        p = np.exp(logp)
+        size = tuple(plates) if plates is not None else p.shape[:-1]
+        p = p / np.sum(p, axis=-1, keepdims=True)
+        P = np.cumsum(p, axis=-1)
+        x = np.random.rand(*size)
+        P = P * np.ones(size + (p.shape[-1],))
+        if size == ():
+            return int(np.searchsorted(P, x))
+        z = np.zeros(size)
+        for ind in np.ndindex(*size):
+            z[ind] = np.searchsorted(P[ind], x[ind])
+        return z.astype(int)
+
+
+class Categorical(ExponentialFamily):
+    """``Categorical(p, plates=None, name="")`` (categorical.py:127-201)."""
+    moment_kind = "categorical"
+    _guard_zero_times_inf = True
+
+    def __init__(self, p, plates=None, name="", initialize=True):
+        if isinstance(p, Node):
+            if p.moment_kind != "dirichlet":
+                raise ValueError("Expected a Dirichlet-like node")
+        else:
+            p = dirichlet_constant(p)
+        K = p.dims[0][0]
+        super().__init__(p, dims=((K,),), distribution=CategoricalDistribution(K), plates=plates, name=name,
+                         initialize=initialize)
+
+    def __str__(self):
+        return "%s ~ Categorical(p)\n  p = \n%s\n" % (self.name, self.u[0].numpy())

@@ -1,0 +1,88 @@
+"""Dirichlet node on device (replaces the array math of nodes/dirichlet.py:107-389).
+phi = [alpha]; u = [<log p>] = psi(phi) - psi(sum phi); one kernel, ``bpk_dirichlet_moments``."""
+import numpy as np
+
+from .. import _bpk
+from .. import darray as D
+from ..darray import DArray
+from .expfam import Distribution, ExponentialFamily
+from .node import Constant, Node
+
+
+def concentration_constant(alpha):
+    """[alpha, lgamma(sum alpha) - sum lgamma(alpha)]  (ConcentrationMoments, dirichlet.py:25-62)."""
+    alpha = np.asarray(alpha, dtype=np.float64)
+    if alpha.ndim < 1:
+        raise ValueError("The prior sample sizes must be a vector")
+    if np.any(alpha < 0):
+        raise ValueError("The prior sample sizes must be non-negative")
+    ad = D.asarray(alpha)
+    K = alpha.shape[-1]
+    s = D.sum_product([ad], [list(range(ad.ndim))], list(range(ad.ndim - 1)))
+    lg = D.sum_product([D.gammaln(ad)], [list(range(ad.ndim))], list(range(ad.ndim - 1)))
+    z = D.sub(D.gammaln(s), lg)
+    return Constant("dirichlet_prior", [ad, z], dims=((K,), ()), plates=alpha.shape[:-1], value=alpha)
+
+
+def dirichlet_constant(p):
+    """[log p] of fixed probabilities (DirichletMoments.compute_fixed_moments)."""
+    p = np.asarray(p, dtype=np.float64)
+    if p.ndim < 1:
+        raise ValueError("Probabilities must be given as a vector")
+    if np.any(p < 0) or np.any(p > 1):
+        raise ValueError("Probabilities must be in range [0,1]")
+    if not np.allclose(np.sum(p, axis=-1), 1.0):
+        raise ValueError("Probabilities must sum to one")
+    p = p / np.sum(p, axis=-1, keepdims=True)
+    with np.errstate(divide="ignore"):
+        return Constant("dirichlet", [D.log(D.asarray(p))], dims=((p.shape[-1],),), plates=p.shape[:-1], value=p)
+
+
+class DirichletDistribution(Distribution):
+
+    def compute_message_to_parent(self, parent, index, u_self, u_alpha):
+        return [u_self[0], D.asarray(1.0)]
+
+    def compute_phi_from_parents(self, u_alpha, mask=True):
+        return [u_alpha[0]]
+
+    def compute_cgf_from_parents(self, u_alpha):
+        return u_alpha[1]
+
+    def compute_moments_and_cgf(self, phi, mask=True):
+        """dirichlet.py:130-160; raises ValueError("Natural parameters should be positive")."""
+        p = phi[0].contiguous()
+        K = p.shape[-1]
+        P = tuple(p.shape[:-1])
+        n = int(np.prod(P, dtype=np.int64)) if P else 1
+        u, g = DArray.empty(P + (K,)), DArray.empty(P)
+        _bpk.get().dirichlet_moments(p.ptr, n, K, u.ptr, g.ptr, True)
+        return [u], g
+
+    def compute_fixed_moments_and_f(self, p, mask=True):
+        c = dirichlet_constant(p)
+        logp = c.u[0]
+        f = D.sum_product([logp], [list(range(logp.ndim))], list(range(logp.ndim - 1)), scale=-1.0)
+        return [logp], f
+
+    def random(self, *phi, plates=None):
+        return np.random.dirichlet(phi[0], size=plates)
+
+
+class Dirichlet(ExponentialFamily):
+    """``Dirichlet(alpha, plates=None, name="")`` (dirichlet.py:333-389)."""
+    moment_kind = "dirichlet"
+    _guard_zero_times_inf = True
+
+    def __init__(self, alpha, plates=None, name="", initialize=True):
+        if isinstance(alpha, Node):
+            if alpha.moment_kind != "dirichlet_prior":
+                raise ValueError("Concentration must be a fixed array")
+        else:
+            alpha = concentration_constant(alpha)
+        K = alpha.dims[0][0]
+        super().__init__(alpha, dims=((K,),), distribution=DirichletDistribution(), plates=plates, name=name,
+                         initialize=initialize)
+
+    def __str__(self):
+        return "%s ~ Dirichlet(alpha)\n  alpha =\n%s" % (self.name, self.phi[0].numpy())

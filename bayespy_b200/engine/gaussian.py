@@ -433,3 +433,107 @@ class GaussianARD(_GaussianNode):
         outer = mu.reshape(mu.shape + (1,) * nd) * mu.reshape(mu.shape[:mu.ndim - nd] + (1,) * nd + mu.shape[mu.ndim - nd:])
         self._store([D.asarray(mu), D.asarray(Cov + outer)], None, np.logical_not(self.observed))
         self.g = D.asarray(np.nan)
+
+
+# --------------------------------------------------------------------------------------------
+# Gaussian (full precision matrix)
+# --------------------------------------------------------------------------------------------
+class GaussianDistribution(Distribution):
+    """x ~ N(mu, Lambda^-1), x in R^D (gaussian.py:293-573).  Parents: mu (Gaussian moments,
+    ndim 1) and Lambda (Wishart moments).  The reference routes both through
+    WrapToGaussianWishart (gaussian.py:2374-2527); the products with <Lambda> computed there
+    are computed here, so the messages reaching mu and Lambda are the same."""
+
+    def __init__(self, D_):
+        self.D = int(D_)
+        self.shape = (self.D,)
+        self.ndim = 1
+
+    def compute_phi_from_parents(self, u_mu, u_Lambda, mask=True):
+        """[<Lambda><mu>, -1/2 <Lambda>]  (gaussian.py:377-394 with :2438-2457)."""
+        Lam = u_Lambda[0]
+        mu = u_mu[0]
+        npl = max(Lam.ndim - 2, mu.ndim - 1)
+        pk = [("p", j) for j in range(npl, 0, -1)]
+        phi0 = D.sum_product([Lam, mu], [pk[npl - (Lam.ndim - 2):] + ["i", "j"], pk[npl - (mu.ndim - 1):] + ["j"]],
+                             pk + ["i"])
+        return [phi0, D.mul(Lam, -0.5)]
+
+    def compute_cgf_from_parents(self, u_mu, u_Lambda):
+        """-1/2 tr(<mu mu^T><Lambda>) + 1/2 <log|Lambda|>  (gaussian.py:449-463)."""
+        Lam, logdet = u_Lambda
+        mumu = dense(u_mu[1])
+        npl = max(Lam.ndim - 2, mumu.ndim - 2)
+        pk = [("p", j) for j in range(npl, 0, -1)]
+        t = D.sum_product([Lam, mumu], [pk[npl - (Lam.ndim - 2):] + ["i", "j"],
+                                        pk[npl - (mumu.ndim - 2):] + ["i", "j"]], pk)
+        return D.axpby(-0.5, t, 0.5, logdet)
+
+    def compute_moments_and_cgf(self, phi, mask=True):
+        """gaussian.py:397-446 (no truncation)."""
+        u0, cov, g, _ = gaussian_moments_device(phi[0], phi[1], self.D)
+        return [u0, FactoredSecondMoment(u0, cov, self.shape)], g
+
+    def compute_message_to_parent(self, parent, index, u, u_mu, u_Lambda):
+        """To mu: [<Lambda> x, -1/2 <Lambda>]; to Lambda: [-1/2 (xx^T - x mu^T - mu x^T + mu mu^T), 1/2]
+        (gaussian.py:341-375 with :2496-2522)."""
+        x = u[0]
+        if index == 0:
+            Lam = u_Lambda[0]
+            npl = max(Lam.ndim - 2, x.ndim - 1)
+            pk = [("p", j) for j in range(npl, 0, -1)]
+            m0 = D.sum_product([Lam, x], [pk[npl - (Lam.ndim - 2):] + ["i", "j"], pk[npl - (x.ndim - 1):] + ["j"]],
+                               pk + ["i"])
+            return [m0, D.mul(Lam, -0.5)]
+        elif index == 1:
+            xx = dense(u[1])
+            mu, mumu = u_mu[0], dense(u_mu[1])
+            xm = D.mul(x.add_trailing(1), mu.expand_dims(-2))          # x mu^T
+            mx = D.mul(mu.add_trailing(1), x.expand_dims(-2))          # mu x^T
+            t = D.add(D.sub(D.sub(xx, xm), mx), mumu)
+            return [D.mul(t, -0.5), D.asarray(0.5)]
+        raise ValueError("Index out of bounds")
+
+    def compute_fixed_moments_and_f(self, x, mask=True):
+        x = np.asarray(x, dtype=np.float64)
+        if x.ndim < 1 or x.shape[-1] != self.D:
+            raise ValueError("Invalid shape")
+        xd = D.asarray(x)
+        from .plans import LazyArray
+        xx = LazyArray(tuple(x.shape) + (self.D,), lambda: D.mul(xd.add_trailing(1), xd.expand_dims(-2)))
+        return [xd, xx], -0.5 * self.D * LOG2PI
+
+    def random(self, *phi, plates=None):
+        import scipy.linalg
+        N = self.D
+        plates = tuple(plates)
+        V = -2 * np.asarray(phi[1])
+        z = np.random.randn(*(plates + (N,)))
+        Vb = np.broadcast_to(V, plates + (N, N))
+        pb = np.broadcast_to(phi[0], plates + (N,))
+        x = np.empty(plates + (N,))
+        for idx in np.ndindex(*plates):
+            U = scipy.linalg.cho_factor(Vb[idx])[0]
+            mu = scipy.linalg.cho_solve((U, False), pb[idx])
+            x[idx] = mu + scipy.linalg.solve_triangular(U, z[idx], trans="N", lower=False)
+        return x
+
+
+class Gaussian(_GaussianNode):
+    """``Gaussian(mu, Lambda, plates=None, name="")`` (gaussian.py:1346-1417)."""
+
+    def __init__(self, mu, Lambda, plates=None, name="", initialize=True):
+        from .wishart import ensure_wishart
+        Lambda = ensure_wishart(Lambda)
+        Dm = Lambda.dims[0][-1]
+        if isinstance(mu, Node):
+            if mu.moment_kind != "gaussian" or tuple(mu.dims[0]) != (Dm,):
+                raise ValueError("Mean and precision have inconsistent shapes: {0} and {1}".format(
+                    mu.dims, Lambda.dims))
+        else:
+            mu = gaussian_constant(mu, 1)
+            if tuple(mu.dims[0]) != (Dm,):
+                raise ValueError("Mean and precision have inconsistent shapes: {0} and {1}".format(
+                    mu.dims, Lambda.dims))
+        super().__init__(mu, Lambda, dims=((Dm,), (Dm, Dm)), distribution=GaussianDistribution(Dm),
+                         plates=plates, name=name, initialize=initialize)

@@ -314,7 +314,12 @@ class FactorModelPlan:
         u_par = col.moments_from_parents()
         cgf = D.asarray(col._distribution.compute_cgf_from_parents(*u_par))     # per-plate, shared
         _, Sxx, sx = self.stats()
-        Lam, logdet, phi_p, cov = fz["Lam"], fz["logdet"], fz["phi_p"], fz["cov"]
+        Lam, logdet, cov = fz["Lam"], fz["logdet"], fz["cov"]
+        # the prior is evaluated NOW (its parents may have moved since q(X) was formed); q's own
+        # natural parameters are the ones stored by update_col
+        phi_p = col._canonical_phi(col._distribution.compute_phi_from_parents(*u_par))
+        if not (all(n == 1 for n in phi_p[0].shape[:-1]) and all(n == 1 for n in phi_p[1].shape[:-2])):
+            return self._orig["col.lb"]()
         SXX = D.axpby(float(N), cov.reshape((K, K)), 1.0, Sxx)                  # sum_n <xx^T>
         trLS = D.sum_product([Lam, Sxx], [["i", "j"], ["i", "j"]], [])           # sum_n x^T Lam x
         # sum_n (phi0p - phi0q_n).x_n = phi0p.s_x - tr(Lam S_xx)
@@ -326,6 +331,222 @@ class FactorModelPlan:
         mg = D.axpby(0.5, trLS, -0.5 * N, logdet)
         ncgf = D.mul(D.reduce_to_shape(cgf, (), from_shape=col.plates), float(self.Ng) / float(self.N))
         return D.add(D.add(D.add(t0, t1), mg), ncgf)
+
+
+class GaussianMixturePlan:
+    """Y = Mixture(Z, Gaussian, mu, Lambda) with Y fully observed (gmm.rst:71-98).
+
+    Z.update()                  -> bpk_gmm_sweep: one pass over y writes the responsibilities
+                                   and accumulates  R_k = sum_n p_nk, s1_k = sum_n p_nk y_n,
+                                   S2_k = sum_n p_nk y_n y_n^T  and  sum_n logsumexp_n
+    Y.message_to_parent(mu)     -> [<Lam_k> s1_k, -1/2 <Lam_k> R_k]                 (mixture.py:108-160)
+    Y.message_to_parent(Lambda) -> [-1/2 (S2 - s1 mu^T - mu s1^T + R <mu mu^T>), 1/2 R]
+    Z.message_to_parent(alpha)  -> [R]                                              (multinomial.py:83-90)
+    Y / Z lower bounds          -> from the statistics                              (expfamily.py:400-480)
+    """
+
+    def __init__(self, Y, Z, mu, Lam):
+        self.Y, self.Z, self.mu, self.Lam = Y, Z, mu, Lam
+        self.N = Y.plates[0]
+        self.D = mu.dims[0][0]
+        self.K = mu.plates[0]
+        self.world = parallel.world()
+        self.Ng = int(round(float(np.sum(parallel.allgather_scalar(self.N))))) if self.world > 1 else self.N
+        self._stats = None           # (Z._version, Y._version, DArray)
+        self._orig = {}
+        self.fused_calls = 0
+        self.kernel_timers = None
+        self._timer_pos = 0
+        self._install()
+
+    def _install(self):
+        plan, o = self, self._orig
+        o["Z.update"] = self.Z.update
+        o["Z.lb"] = self.Z.lower_bound_contribution
+        o["Z.msg"] = self.Z.message_to_parent
+        o["Y.msg"] = self.Y.message_to_parent
+        o["Y.lb"] = self.Y.lower_bound_contribution
+
+        def Z_update(node, annealing=1.0):
+            if annealing == 1.0 and plan.valid():
+                return plan.update_Z()
+            return o["Z.update"](annealing) if annealing != 1.0 else o["Z.update"]()
+
+        def Z_lb(node):
+            return plan.bound_Z() if plan.valid() and getattr(plan.Z, "_fused", None) is not None else o["Z.lb"]()
+
+        def Z_msg(node, index):
+            if index == 0 and plan.valid() and mask_is_full(plan.Z.mask):
+                return plan.message_to_alpha()
+            return o["Z.msg"](index)
+
+        def Y_msg(node, index):
+            if index in (1, 2) and plan.valid():
+                return plan.message_to_mu() if index == 1 else plan.message_to_Lambda()
+            return o["Y.msg"](index)
+
+        def Y_lb(node):
+            return plan.bound_Y() if plan.valid() else o["Y.lb"]()
+
+        self.Z.update = types.MethodType(Z_update, self.Z)
+        self.Z.lower_bound_contribution = types.MethodType(Z_lb, self.Z)
+        self.Z.message_to_parent = types.MethodType(Z_msg, self.Z)
+        self.Y.message_to_parent = types.MethodType(Y_msg, self.Y)
+        self.Y.lower_bound_contribution = types.MethodType(Y_lb, self.Y)
+
+    def valid(self):
+        Y, Z = self.Y, self.Z
+        ok = (Y.observed is True) and mask_is_full(Y.mask) and Z.observed is False \
+            and all(getattr(n, "annealing", 1.0) == 1.0 for n in (Y, Z, self.mu, self.Lam))
+        if not ok and self.world > 1:
+            raise NotImplementedError("plate sharding is only supported on the fused path")
+        return ok
+
+    # ---- cluster parameters as the kernel wants them --------------------------------------------
+    def _params(self):
+        """g_k (K), h_k = <Lam_k mu_k> (K,D), <Lam_k> (K,D,D) from the mixed Gaussian's protocol."""
+        raw = self.Y._distribution.raw
+        u_mu, u_L = self.mu.get_moments(), self.Lam.get_moments()
+        phi = raw.compute_phi_from_parents(u_mu, u_L)
+        g = D.asarray(raw.compute_cgf_from_parents(u_mu, u_L))
+        K, Dm = self.K, self.D
+        h = D.asarray(phi[0]).broadcast_to((K, Dm)).contiguous()
+        Lm = D.asarray(u_L[0]).broadcast_to((K, Dm, Dm)).contiguous()
+        return g.broadcast_to((K,)).contiguous(), h, Lm
+
+    def _Yd(self):
+        return self.Y.u[0].contiguous()
+
+    def stats(self):
+        key = (self.Z._version, self.Y._version)
+        if self._stats is None or self._stats[0] != key:
+            N, Dm, K = self.N, self.D, self.K
+            st = DArray.zeros((K + K * Dm + K * Dm * Dm + 1,))
+            P = self.Z.u[0].broadcast_to((N, K)).contiguous()
+            _bpk.get().gmm_stats(self._Yd().ptr, N, Dm, K, P.ptr, st.ptr)
+            parallel.allreduce_sum(st)
+            self._stats = (key, st)
+        return self._split(self._stats[1])
+
+    def _split(self, st):
+        K, Dm = self.K, self.D
+        a, b, c = K, K + K * Dm, K + K * Dm + K * Dm * Dm
+        return (st.slice_axis(0, 0, a), st.slice_axis(0, a, b).reshape((K, Dm)),
+                st.slice_axis(0, b, c).reshape((K, Dm, Dm)), st.slice_axis(0, c, c + 1).reshape(()))
+
+    # ---- fused operations --------------------------------------------------------------------------
+    def update_Z(self):
+        Z, N, Dm, K = self.Z, self.N, self.D, self.K
+        be = _bpk.get()
+        u_par = Z.moments_from_parents()
+        logpi = D.asarray(Z._distribution.compute_phi_from_parents(*u_par)[0])
+        if logpi.size != K:
+            return self._orig["Z.update"]()           # per-sample prior: generic path
+        logpi = logpi.reshape((K,)).contiguous()
+        g, h, Lm = self._params()
+        P = DArray.empty((N, K))
+        gz = DArray.empty((N,))
+        st = DArray.zeros((K + K * Dm + K * Dm * Dm + 1,))
+        Yd = self._Yd()
+        if self.kernel_timers is not None and self._timer_pos < len(self.kernel_timers):
+            tid = self.kernel_timers[self._timer_pos]
+            self._timer_pos += 1
+            be.timer_record(tid, 0)
+            be.gmm_sweep(Yd.ptr, N, Dm, K, g.ptr, h.ptr, Lm.ptr, logpi.ptr, P.ptr, gz.ptr, st.ptr)
+            be.timer_record(tid, 1)
+        else:
+            be.gmm_sweep(Yd.ptr, N, Dm, K, g.ptr, h.ptr, Lm.ptr, logpi.ptr, P.ptr, gz.ptr, st.ptr)
+        parallel.allreduce_sum(st)
+        self.fused_calls += 1
+        Y = self.Y
+
+        def phi_fn():
+            m = plan_self._orig["Y.msg"](0)[0]
+            return D.add(m, logpi)
+        plan_self = self
+        Z.phi = [LazyArray((N, K), phi_fn)]
+        Z.u = [P]
+        Z.g = gz
+        Z._version += 1
+        self._stats = ((Z._version, Y._version), st)
+        # sum_nk p_nk * (message from Y) with the parameters q(Z) was built from: needed by Z's bound
+        Z._fused = dict(logpi=logpi, T=self._T(params=(g, h, Lm)))
+
+    def message_to_alpha(self):
+        R, _, _, _ = self.stats()
+        self.fused_calls += 1
+        par = self.Z.parents[0]
+        return [R.reshape((1,) * len(par.plates) + (self.K,)) if len(par.plates) else R]
+
+    def message_to_mu(self):
+        R, s1, _, _ = self.stats()
+        Lm = D.asarray(self.Lam.get_moments()[0]).broadcast_to((self.K, self.D, self.D))
+        m0 = D.sum_product([Lm, s1], [["k", "i", "j"], ["k", "j"]], ["k", "i"])
+        m1 = D.mul(D.mul(Lm, R.reshape((self.K, 1, 1))), -0.5)
+        self.fused_calls += 1
+        return [m0, m1]
+
+    def message_to_Lambda(self):
+        R, s1, S2, _ = self.stats()
+        u_mu = self.mu.get_moments()
+        K, Dm = self.K, self.D
+        mu = D.asarray(u_mu[0]).broadcast_to((K, Dm))
+        mumu = D.asarray(u_mu[1]).broadcast_to((K, Dm, Dm))
+        sm = D.mul(s1.reshape((K, Dm, 1)), mu.reshape((K, 1, Dm)))            # s1 mu^T
+        ms = D.mul(mu.reshape((K, Dm, 1)), s1.reshape((K, 1, Dm)))            # mu s1^T
+        t = D.add(D.sub(D.sub(S2, sm), ms), D.mul(mumu, R.reshape((K, 1, 1))))
+        self.fused_calls += 1
+        return [D.mul(t, -0.5), D.mul(R, 0.5)]
+
+    def _T(self, params=None):
+        """sum_nk p_nk (g_k + h_k.y_n - 1/2 y_n^T Lam_k y_n) from the statistics."""
+        R, s1, S2, _ = self.stats()
+        g, h, Lm = params if params is not None else self._params()
+        a = D.sum_product([g, R], [["k"], ["k"]], [])
+        b = D.sum_product([h, s1], [["k", "i"], ["k", "i"]], [])
+        c = D.sum_product([Lm, S2], [["k", "i", "j"], ["k", "i", "j"]], [], scale=-0.5)
+        return D.add(D.add(a, b), c)
+
+    def bound_Y(self):
+        """E[log p(Y|Z,mu,Lambda)] = T - N D/2 log 2pi."""
+        return D.affine(self._T(), 1.0, -0.5 * self.D * LOG2PI * self.Ng)
+
+    def bound_Z(self):
+        """E[log p(Z|pi)] - E[log q(Z)] = sum_n logsumexp_n - T_q + sum_k (<log pi_k> - logpi_q,k) R_k,
+        where T_q and logpi_q are the message sum and prior q(Z) was built from (expfamily.py:400-480)."""
+        R, _, _, lse = self.stats()
+        fz = self.Z._fused
+        u_par = self.Z.moments_from_parents()
+        logpi = D.asarray(self.Z._distribution.compute_phi_from_parents(*u_par)[0]).reshape((self.K,))
+        dpi = D.sum_product([D.sub(logpi, fz["logpi"]), R], [["k"], ["k"]], [])
+        return D.add(D.sub(lse, fz["T"]), dpi)
+
+
+def _attach_gmm(model, plans):
+    from .mixture import Mixture
+    from .gaussian import Gaussian
+    from .wishart import Wishart
+    from .categorical import Categorical
+    for Y in model:
+        if not isinstance(Y, Mixture) or Y.mixed_class is not Gaussian or Y.cluster_plate != -1:
+            continue
+        if getattr(Y, "_plan", None) is not None:
+            plans.append(Y._plan)
+            continue
+        if len(Y.plates) != 1 or Y.children or len(Y.parents) != 3:
+            continue
+        Z, mu, Lam = Y.parents
+        if not (isinstance(Z, Categorical) and isinstance(mu, Gaussian) and isinstance(Lam, Wishart)):
+            continue
+        if tuple(Z.plates) != tuple(Y.plates) or len(mu.plates) != 1 or tuple(mu.plates) != tuple(Lam.plates):
+            continue
+        if len(Z.children) != 1 or len(mu.children) != 1 or len(Lam.children) != 1:
+            continue
+        if mu.dims[0][0] > 16 or mu.plates[0] > 128:
+            continue
+        plan = GaussianMixturePlan(Y, Z, mu, Lam)
+        Y._plan = plan
+        plans.append(plan)
 
 
 def attach(model):
@@ -364,4 +585,5 @@ def attach(model):
         plan = FactorModelPlan(Y, F, row, col, i_row, i_col, tau)
         Y._plan = plan
         plans.append(plan)
+    _attach_gmm(model, plans)
     return plans

@@ -4,3 +4,8 @@ from ..engine.expfam import ExponentialFamily                                 # 
 from ..engine.gaussian import GaussianARD                                     # noqa: F401
 from ..engine.gamma import Gamma                                              # noqa: F401
 from ..engine.dot import SumMultiply, Dot                                     # noqa: F401
+from ..engine.gaussian import Gaussian                                        # noqa: F401
+from ..engine.wishart import Wishart                                          # noqa: F401
+from ..engine.dirichlet import Dirichlet                                      # noqa: F401
+from ..engine.categorical import Categorical                                  # noqa: F401
+from ..engine.mixture import Mixture                                          # noqa: F401

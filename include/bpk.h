@@ -198,6 +198,10 @@ int bpk_gmm_sweep(const double *Y, int64_t N, int D, int K,
                   const double *c, const double *h, const double *Lam, const double *logpi,
                   double *P, double *g, double *stats);
 
+/* statistics only, for responsibilities P [N][K] that did not come from bpk_gmm_sweep
+ * (e.g. a random initialisation): stats[0..K+K*D+K*D*D) += sums, stats[last] unchanged.   */
+int bpk_gmm_stats(const double *Y, int64_t N, int D, int K, const double *P, double *stats);
+
 #ifdef __cplusplus
 }
 #endif

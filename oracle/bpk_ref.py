@@ -416,3 +416,13 @@ class RefBackend:
         s[K:K + K * D] += (p.T @ y).ravel()
         s[K + K * D:K + K * D + K * D * D] += np.einsum("nk,ni,nj->kij", p, y, y).ravel()
         s[-1] += lse.sum()
+
+    def gmm_stats(self, Y, N, D, K, P, stats):
+        """p-weighted plate sums of mixture.py:108-160 + node.py:650 for given responsibilities."""
+        self._launches += 1
+        y = _dense(Y, (N, D))
+        p = _dense(P, (N, K))
+        s = _dense(stats, (K + K * D + K * D * D + 1,))
+        s[:K] += p.sum(axis=0)
+        s[K:K + K * D] += (p.T @ y).ravel()
+        s[K + K * D:K + K * D + K * D * D] += np.einsum("nk,ni,nj->kij", p, y, y).ravel()

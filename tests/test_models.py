@@ -146,3 +146,73 @@ def test_vb_api(backend, capsys):
     assert abs(Q.compute_lowerbound() - Q.L[Q.iter - 1]) < 1e-8 * abs(Q.L[Q.iter - 1])
     terms = Q.compute_lowerbound_terms()
     assert abs(sum(terms.values()) - Q.L[Q.iter - 1]) < 1e-8 * abs(Q.L[Q.iter - 1])
+
+
+def build_gmm(g, N, D, K, fused, y=None):
+    from bayespy_b200.nodes import Gaussian, Wishart, Dirichlet, Categorical, Mixture
+    from bayespy_b200.inference import VB
+    if y is None:
+        np.random.seed(1)
+        means = 5 * np.random.randn(K, D)
+        z = np.random.randint(0, K, size=N)
+        y = means[z] + np.random.randn(N, D)
+    assert np.array_equal(y, g["y"])
+    alpha = Dirichlet(1e-5 * np.ones(K), name="alpha")
+    Z = Categorical(alpha, plates=(N,), name="Z")
+    mu = Gaussian(np.zeros(D), 1e-5 * np.identity(D), plates=(K,), name="mu")
+    Lambda = Wishart(D, 1e-5 * np.identity(D), plates=(K,), name="Lambda")
+    Y = Mixture(Z, Gaussian, mu, Lambda, name="Y")
+    Z.initialize_from_random()                       # host RNG parity (categorical one-hot: bit-exact)
+    assert np.array_equal(np.asarray(Z.u[0]), g["Z_init"])
+    return Y, Z, mu, Lambda, alpha, y
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_gmm_small(backend, fused):
+    """Mixture + Gaussian + Wishart + Dirichlet + Categorical (gmm.rst:71-98 on 5 blobs)."""
+    from bayespy_b200.inference import VB
+    g = golden("gmm_small")
+    Y, Z, mu, Lambda, alpha, y = build_gmm(g, 300, 3, 5, fused)
+    Y.observe(y)
+    Q = VB(Y, mu, Lambda, Z, alpha, fused=fused)
+    iters = len(g["L"])
+    Q.update(repeat=iters, verbose=False, tol=0)
+    close(Q.L[:iters], g["L"], rtol=1e-8)
+    for nm, node in (("Z", Z), ("mu", mu), ("Lambda", Lambda), ("alpha", alpha)):
+        check_node(g, nm, node)
+        close(Q.l[node][:iters], g["l_" + nm], rtol=1e-7, atol=1e-6)
+    close(Q.l[Y][:iters], g["l_Y"], rtol=1e-8)
+    if fused:
+        assert len(Q.plans) == 1 and Q.plans[0].fused_calls > 0
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_gmm_doc_example(backend, fused, capsys):
+    """doc/source/examples/gmm.rst:8-118: 'Iteration 1: loglike=-1.402345e+03' ...
+    'Iteration 61: loglike=-8.888464e+02', 'Converged at iteration 61.'"""
+    from bayespy_b200.nodes import Gaussian, Wishart, Dirichlet, Categorical, Mixture
+    from bayespy_b200.inference import VB
+    g = golden("gmm_doc")
+    np.random.seed(1)
+    y0 = np.random.multivariate_normal([0, 0], [[2, 0], [0, 0.1]], size=50)
+    y1 = np.random.multivariate_normal([0, 0], [[0.1, 0], [0, 2]], size=50)
+    y2 = np.random.multivariate_normal([2, 2], [[2, -1.5], [-1.5, 2]], size=50)
+    y3 = np.random.multivariate_normal([-2, -2], [[0.5, 0], [0, 0.5]], size=50)
+    y = np.vstack([y0, y1, y2, y3])
+    assert np.array_equal(y, g["y"])
+    N, D, K = 200, 2, 10
+    alpha = Dirichlet(1e-5 * np.ones(K), name="alpha")
+    Z = Categorical(alpha, plates=(N,), name="z")
+    mu = Gaussian(np.zeros(D), 1e-5 * np.identity(D), plates=(K,), name="mu")
+    Lambda = Wishart(D, 1e-5 * np.identity(D), plates=(K,), name="Lambda")
+    Y = Mixture(Z, Gaussian, mu, Lambda, name="Y")
+    Z.initialize_from_random()
+    assert np.array_equal(np.asarray(Z.u[0]), g["Z_init"])
+    Q = VB(Y, mu, Lambda, Z, alpha, fused=fused)
+    Y.observe(y)
+    Q.update(repeat=1000)
+    out = capsys.readouterr().out
+    assert "Iteration 1: loglike=-1.402345e+03" in out
+    assert "Iteration 61: loglike=-8.888464e+02" in out
+    assert "Converged at iteration 61." in out
+    close(Q.L[:Q.iter], g["L"], rtol=1e-7)

@@ -135,3 +135,19 @@ def test_gmm_sweep(backend, N, D, K):
     np.testing.assert_allclose(s[K + K * D:-1].reshape(K, D, D), np.einsum("nk,ni,nj->kij", p, y, y), rtol=1e-10,
                                atol=1e-10)
     np.testing.assert_allclose(s[-1], lse.sum(), rtol=1e-11)
+
+
+@pytest.mark.parametrize("N,D,K", [(300, 3, 5), (1000, 8, 64)])
+def test_gmm_stats(backend, N, D, K):
+    rng = np.random.RandomState(N)
+    y = rng.randn(N, D)
+    p = rng.dirichlet(np.ones(K), size=N)
+    Y, P = DArray.from_numpy(y), DArray.from_numpy(p)
+    st = DArray.zeros((K + K * D + K * D * D + 1,))
+    backend.gmm_stats(Y.ptr, N, D, K, P.ptr, st.ptr)
+    s = st.numpy()
+    np.testing.assert_allclose(s[:K], p.sum(0), rtol=1e-11)
+    np.testing.assert_allclose(s[K:K + K * D].reshape(K, D), p.T @ y, rtol=1e-10, atol=1e-11)
+    np.testing.assert_allclose(s[K + K * D:-1].reshape(K, D, D), np.einsum("nk,ni,nj->kij", p, y, y), rtol=1e-10,
+                               atol=1e-11)
+    assert s[-1] == 0.0
