@@ -56,6 +56,7 @@ PROTOTYPES = {
     "bpk_comm_init": (C.c_int, [C.c_char_p, C.c_int, C.c_int]),
     "bpk_comm_size": (C.c_int, [_ip, _ip]),
     "bpk_allreduce_sum_f64": (C.c_int, [_dp, C.c_uint64]),
+    "bpk_allreduce_sum_f64_oop": (C.c_int, [_dp, _dp, C.c_uint64]),
     "bpk_comm_destroy": (C.c_int, []),
     "bpk_ewise": (C.c_int, [C.c_int, C.c_int, _i64p, _dp, _i64p, C.c_int, C.POINTER(C.c_void_p), _ip, _i64p,
                             C.c_double, C.c_double]),
@@ -80,7 +81,16 @@ PROTOTYPES = {
     "bpk_sumsq": (C.c_int, [_dp, _vp, C.c_int64, _dp]),
     "bpk_gmm_sweep": (C.c_int, [_dp, C.c_int64, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
     "bpk_gmm_stats": (C.c_int, [_dp, C.c_int64, C.c_int, C.c_int, _dp, _dp]),
+    "bpk_pca_vb_layout": (C.c_int, [C.c_int, C.c_int, _i64p, _ip]),
+    "bpk_pca_vb_field_name": (C.c_char_p, [C.c_int]),
+    "bpk_pca_vb_run": (C.c_int, [_dp, C.c_int64, C.c_int64, C.c_int, _dp, _dp, _ip, C.c_int, C.c_int, C.c_int,
+                                 C.c_int, C.c_double, _dp, C.c_int, _vp]),
+    "bpk_pca_vb_set_timers": (C.c_int, [_ip, C.c_int]),
+    "bpk_pca_vb_timers_used": (C.c_int, []),
 }
+
+# opcodes of bpk_pca_vb_run (include/bpk.h)
+VBOP = dict(XSWEEP=1, STATS=2, SXXT=3, XPRE=4, ROW=5, ALPHA=6, TAU=7, BOUND=8)
 
 
 class BpkError(RuntimeError):
@@ -208,6 +218,9 @@ class CudaBackend:
     def allreduce_sum_f64(self, dev, count):
         self._chk(self.lib.bpk_allreduce_sum_f64(dev, int(count)))
 
+    def allreduce_sum_f64_oop(self, src, dst, count):
+        self._chk(self.lib.bpk_allreduce_sum_f64_oop(src, dst, int(count)))
+
     def comm_destroy(self):
         self._chk(self.lib.bpk_comm_destroy())
 
@@ -280,9 +293,30 @@ class CudaBackend:
     def gmm_sweep(self, Y, N, D, K, c, h, Lam, logpi, P, g, stats):
         self._chk(self.lib.bpk_gmm_sweep(Y, N, D, K, c, h, Lam, logpi, P, g, stats))
 
-
     def gmm_stats(self, Y, N, D, K, P, stats):
         self._chk(self.lib.bpk_gmm_stats(Y, N, D, K, P, stats))
+
+    # -- device-resident VB loop of the factor model
+    def pca_vb_layout(self, M, K):
+        """{field: (offset, size)} of the fp64 state vector, and its total length."""
+        n = C.c_int()
+        self._chk(self.lib.bpk_pca_vb_layout(M, K, None, C.byref(n)))
+        off = (C.c_int64 * (n.value + 1))()
+        self._chk(self.lib.bpk_pca_vb_layout(M, K, off, C.byref(n)))
+        names = [self.lib.bpk_pca_vb_field_name(i).decode() for i in range(n.value)]
+        return {nm: (off[i], off[i + 1] - off[i]) for i, nm in enumerate(names)}, off[n.value]
+
+    def pca_vb_run(self, Y, M, N, K, X, state, ops, niter, has_alpha, has_tau, tol, Lhist, cap, ctrl):
+        arr = (C.c_int * len(ops))(*ops)
+        self._chk(self.lib.bpk_pca_vb_run(Y, M, N, K, X, state, arr, len(ops), int(niter), int(has_alpha),
+                                          int(has_tau), float(tol), Lhist, int(cap), ctrl))
+
+    def pca_vb_set_timers(self, ids):
+        arr = (C.c_int * max(len(ids), 1))(*ids)
+        self._chk(self.lib.bpk_pca_vb_set_timers(arr, len(ids)))
+
+    def pca_vb_timers_used(self):
+        return int(self.lib.bpk_pca_vb_timers_used())
 
 
 _backend = None

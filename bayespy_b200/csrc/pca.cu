@@ -23,12 +23,11 @@
 // partials are reduced warp->CTA in smem and CTA->grid by a second tiny
 // kernel in a fixed order (deterministic, no atomics).
 #include "common.cuh"
+#include "pca_common.cuh"
+#include "spd.cuh"
 
-#define PCA_MP 64      // padded M
-#define PCA_KP 16      // padded K
 #define PCA_WARPS 8
 #define PCA_LDX 20     // pitch of the per-warp X staging tile
-#define PCA_NSTAT (PCA_MP * PCA_KP + PCA_KP * PCA_KP + PCA_KP)
 
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -73,8 +72,10 @@ template <int NT, int STAGES, bool ALIGN16, bool COMPUTE_X>
 __global__ void __launch_bounds__(PCA_WARPS * 32, 1)
 pca_xsweep_kernel(const double *__restrict__ Y, int64_t M, int64_t N, int K,
                   const double *__restrict__ A, const double *__restrict__ bvec,
-                  double *__restrict__ X, double *__restrict__ partial, int64_t ntiles) {
+                  double *__restrict__ X, double *__restrict__ partial, int64_t ntiles,
+                  const int *__restrict__ stop) {
     constexpr int T = PCA_WARPS * NT, LDY = T + 4, CB = NT / 8, NS = NT / 4;
+    if (stop && *stop) return;      // resident VB loop: converged, leave state frozen
     extern __shared__ __align__(16) double smem[];
     double *Ysm = smem;                                            // [STAGES][64][LDY]
     double *Xsm = smem + (size_t)STAGES * PCA_MP * LDY;            // [WARPS][NT][LDX]
@@ -245,8 +246,8 @@ __global__ void pca_stats_final_kernel(const double *__restrict__ partial, int n
 }
 
 template <int NT, int STAGES, bool COMPUTE_X>
-static int pca_launch(const double *Y, int64_t M, int64_t N, int K, const double *A, const double *b,
-                      double *X, double *stats) {
+static int pca_launch_partials(const double *Y, int64_t M, int64_t N, int K, const double *A, const double *b,
+                               double *X, const int *stop, double **partial_out, int *nparts_out) {
     constexpr int T = PCA_WARPS * NT, LDY = T + 4;
     size_t ring = (size_t)STAGES * PCA_MP * LDY * sizeof(double);
     size_t xs = (size_t)PCA_WARPS * NT * PCA_LDX * sizeof(double);
@@ -262,15 +263,33 @@ static int pca_launch(const double *Y, int64_t M, int64_t N, int K, const double
     if (al) {
         auto kern = pca_xsweep_kernel<NT, STAGES, true, COMPUTE_X>;
         BPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        BPK_LAUNCH(kern, grid, PCA_WARPS * 32, smem, Y, M, N, K, A, b, X, partial, ntiles);
+        BPK_LAUNCH(kern, grid, PCA_WARPS * 32, smem, Y, M, N, K, A, b, X, partial, ntiles, stop);
     } else {
         auto kern = pca_xsweep_kernel<NT, STAGES, false, COMPUTE_X>;
         BPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        BPK_LAUNCH(kern, grid, PCA_WARPS * 32, smem, Y, M, N, K, A, b, X, partial, ntiles);
+        BPK_LAUNCH(kern, grid, PCA_WARPS * 32, smem, Y, M, N, K, A, b, X, partial, ntiles, stop);
     }
+    *partial_out = partial;
+    *nparts_out = grid;
+    return BPK_OK;
+}
+
+template <int NT, int STAGES, bool COMPUTE_X>
+static int pca_launch(const double *Y, int64_t M, int64_t N, int K, const double *A, const double *b,
+                      double *X, double *stats) {
+    double *partial = nullptr;
+    int grid = 0;
+    int rc = pca_launch_partials<NT, STAGES, COMPUTE_X>(Y, M, N, K, A, b, X, nullptr, &partial, &grid);
+    if (rc) return rc;
     int total = (int)(M * K + K * K + K);
     BPK_LAUNCH(pca_stats_final_kernel, (total + 127) / 128, 128, 0, partial, grid, (int)M, K, stats);
     return BPK_OK;
+}
+
+// resident VB loop (pca_vb.cu): sweep only, per-CTA partials left in scratch
+int pca_xsweep_partials(const double *Y, int64_t M, int64_t N, int K, const double *A, const double *b,
+                        double *X, const int *stop, double **partial_out, int *nparts_out) {
+    return pca_launch_partials<16, 2, true>(Y, M, N, K, A, b, X, stop, partial_out, nparts_out);
 }
 
 // ---- generic shapes (M > 64 or K > 16): plain kernels, not roofline-tuned -----------
@@ -387,25 +406,8 @@ extern "C" int bpk_sumsq(const double *Y, const uint8_t *mask, int64_t count, do
 // and writes x_n, Cov_n, g_n.  The mask-weighted statistics are then two plate-sums over
 // n (bpk_sum_multiply).  TODO(next): fuse the statistics into the column kernel and move
 // the two M x K^2 contractions onto DMMA (they are GEMMs with the mask as one operand).
-#define MLD(D) ((D) | 1)
-__device__ __forceinline__ int m_warp_chol_upper(double *S, int D, int ld, int lane) {
-    int bad = 0;
-    for (int k = 0; k < D; ++k) {
-        double akk = S[k * ld + k];
-        if (!(akk > 0.0) || !isfinite(akk)) bad = 1;
-        double d = sqrt(akk), inv = 1.0 / d;
-        __syncwarp();
-        for (int j = k + lane; j < D; j += 32) S[k * ld + j] = (j == k) ? d : S[k * ld + j] * inv;
-        __syncwarp();
-        int m = D - k - 1;
-        for (int idx = lane; idx < m * m; idx += 32) {
-            int i = k + 1 + idx / m, j = k + 1 + idx % m;
-            if (j >= i) S[i * ld + j] -= S[k * ld + i] * S[k * ld + j];
-        }
-        __syncwarp();
-    }
-    return bad;
-}
+#define MLD(D) SPD_LD(D)
+#define m_warp_chol_upper spd_warp_chol_upper
 
 __global__ void pca_masked_cols_kernel(const double *__restrict__ Y, const uint8_t *__restrict__ mask,
                                        int64_t M, int64_t N, int K,

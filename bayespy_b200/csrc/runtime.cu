@@ -276,6 +276,17 @@ extern "C" int bpk_allreduce_sum_f64(double *dev, uint64_t count) {
     g_bpk.launches++;
     return BPK_OK;
 }
+extern "C" int bpk_allreduce_sum_f64_oop(const double *src, double *dst, uint64_t count) {
+    BPK_REQUIRE_INIT();
+    if (g_nranks == 1 && !g_comm) {
+        if (src != dst) BPK_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(double), cudaMemcpyDeviceToDevice, g_bpk.stream));
+        return BPK_OK;
+    }
+    if (!g_comm) return bpk_set_error(BPK_ENCCL, "bpk_comm_init has not been called");
+    BPK_NCCL(p_ncclAllReduce(src, dst, (size_t)count, 8, 0, g_comm, g_bpk.stream));
+    g_bpk.launches++;
+    return BPK_OK;
+}
 extern "C" int bpk_comm_destroy(void) {
     if (g_comm) {
         cudaStreamSynchronize(g_bpk.stream);

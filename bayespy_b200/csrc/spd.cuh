@@ -1,0 +1,69 @@
+// spd.cuh — warp-cooperative dense SPD routines on a K x K tile held in shared memory.
+// Used where ONE warp owns one small matrix (per-column precision of the masked factor
+// model, the shared K x K posteriors of the resident PCA sweep).  Same arithmetic as
+// linalg.py:31-223 (cho_factor(lower=False) -> U with A = U^T U; inverse by two
+// triangular solves against the identity; log-det = 2 sum log diag U).
+#pragma once
+#include "common.cuh"
+
+#define SPD_LD(D) ((D) | 1)      // odd pitch: conflict-free column walks
+
+// In-place upper Cholesky of the (row-major, pitch ld) tile S; the strict lower triangle is
+// left untouched.  Returns 1 in every lane if a pivot was not positive/finite.
+__device__ __forceinline__ int spd_warp_chol_upper(double *S, int D, int ld, int lane) {
+    int bad = 0;
+    for (int k = 0; k < D; ++k) {
+        double akk = S[k * ld + k];
+        if (!(akk > 0.0) || !isfinite(akk)) bad = 1;
+        double d = sqrt(akk), inv = 1.0 / d;
+        __syncwarp();
+        for (int j = k + lane; j < D; j += 32) S[k * ld + j] = (j == k) ? d : S[k * ld + j] * inv;
+        __syncwarp();
+        int m = D - k - 1;
+        for (int idx = lane; idx < m * m; idx += 32) {
+            int i = k + 1 + idx / m, j = k + 1 + idx % m;
+            if (j >= i) S[i * ld + j] -= S[k * ld + i] * S[k * ld + j];
+        }
+        __syncwarp();
+    }
+    return bad;
+}
+
+// 2 sum_i log U_ii, same value in every lane
+__device__ __forceinline__ double spd_warp_logdet(const double *S, int D, int ld, int lane) {
+    double s = 0.0;
+    for (int i = lane; i < D; i += 32) s += log(S[i * ld + i]);
+    return 2.0 * warp_sum(s);
+}
+
+// C = (U^T U)^-1 for the factor U in S.  B is a K x 32 scratch tile (lane-per-column solves
+// against the identity, 32 columns per pass).
+__device__ __forceinline__ void spd_warp_inverse(const double *S, double *B, double *C, int K, int ld, int lane) {
+    for (int c0 = 0; c0 < K; c0 += 32) {
+        int nc = K - c0 < 32 ? K - c0 : 32;
+        __syncwarp();
+        for (int e = lane; e < K * nc; e += 32) {
+            int i = e / nc, c = e % nc;
+            B[i * 32 + c] = (i == c0 + c) ? 1.0 : 0.0;
+        }
+        __syncwarp();
+        if (lane < nc) {
+            for (int i = 0; i < K; ++i) {
+                double s = B[i * 32 + lane];
+                for (int j = 0; j < i; ++j) s -= S[j * ld + i] * B[j * 32 + lane];
+                B[i * 32 + lane] = s / S[i * ld + i];
+            }
+            for (int i = K - 1; i >= 0; --i) {
+                double s = B[i * 32 + lane];
+                for (int j = i + 1; j < K; ++j) s -= S[i * ld + j] * B[j * 32 + lane];
+                B[i * 32 + lane] = s / S[i * ld + i];
+            }
+        }
+        __syncwarp();
+        for (int e = lane; e < K * nc; e += 32) {
+            int i = e / nc, c = e % nc;
+            C[i * ld + c0 + c] = B[i * 32 + c];
+        }
+    }
+    __syncwarp();
+}

@@ -333,6 +333,257 @@ class FactorModelPlan:
         return D.add(D.add(D.add(t0, t1), mg), ncgf)
 
 
+    # ---- device-resident VB loop (csrc/pca_vb.cu) ----------------------------------------------------
+    @staticmethod
+    def _const_vec(node, K):
+        """Value of a Constant parent as a length-K host vector, or None if it varies over plates."""
+        if not isinstance(node, Constant) or node.value is None:
+            return None
+        v = np.asarray(node.value, dtype=np.float64)
+        if v.size == 1:
+            return np.full(K, float(v.reshape(())))
+        if v.size == K and v.shape[-1] == K:
+            return v.reshape(K).copy()
+        return None
+
+    def _resident_hyper(self):
+        """Host constants of the model, or None when some prior is not a plain constant."""
+        K, col, row, tau = self.K, self.col, self.row, self.tau
+        h = dict(mux=self._const_vec(col.parents[0], K), ax=self._const_vec(col.parents[1], K),
+                 muc=self._const_vec(row.parents[0], K))
+        alpha = row.parents[1]
+        if isinstance(alpha, Gamma):
+            if tuple(alpha.plates) != (K,) or len(alpha.children) != 1 or alpha.observed is not False:
+                return None
+            h["a0"] = self._const_vec(alpha.parents[0], K)
+            h["b0"] = self._const_vec(alpha.parents[1], K)
+        else:
+            h["a0"] = h["b0"] = np.ones(K)
+            h["alpha_const"] = self._const_vec(alpha, K)
+            if h["alpha_const"] is None:
+                return None
+        if isinstance(tau, Gamma):
+            if len(tau.children) != 1 or tau.observed is not False:
+                return None
+            ta0, tb0 = self._const_vec(tau.parents[0], 1), self._const_vec(tau.parents[1], 1)
+            if ta0 is None or tb0 is None:
+                return None
+            h["ta0"], h["tb0"] = ta0[:1], tb0[:1]
+        else:
+            h["ta0"] = h["tb0"] = np.ones(1)
+            tc = self._const_vec(tau, 1)
+            if tc is None:
+                return None
+            h["tau_const"] = tc[:1]
+        if any(v is None for v in h.values()):
+            return None
+        if np.any(h["ax"] <= 0):
+            return None
+        return h
+
+    def resident_program(self, vb, nodes):
+        """Opcode list for ONE iteration of ``VB.update(*nodes)`` when the whole sweep can stay on the
+        device (this model, constant hyper-priors, every latent node updated exactly once), else None."""
+        if not self._valid():
+            return None
+        col, row, tau, Y = self.col, self.row, self.tau, self.Y
+        alpha = row.parents[1]
+        latent = {col, row}
+        if isinstance(alpha, Gamma):
+            latent.add(alpha)
+        if isinstance(tau, Gamma):
+            latent.add(tau)
+        model = [n for n in vb.model if n is not self.F]
+        if set(model) != latent | {Y} or len(model) != len(latent) + 1:
+            return None
+        order = [vb[n] for n in nodes]
+        order = [n for n in order if n is not Y and n is not self.F]
+        if set(order) != latent or len(order) != len(latent):
+            return None
+        self._hyper = self._resident_hyper()
+        if self._hyper is None:
+            return None
+        V = _bpk.VBOP
+        ops = []
+        for n in order:
+            if n is col:
+                ops += [V["XPRE"], V["XSWEEP"], V["STATS"], V["SXXT"]]
+            elif n is row:
+                ops.append(V["ROW"])
+            elif n is alpha:
+                ops.append(V["ALPHA"])
+            else:
+                ops.append(V["TAU"])
+        ops.append(V["BOUND"])
+        return ops, order
+
+    def _resident_enter(self, order, lprev):
+        """Build the state vector from the node graph (a handful of small D2H reads, once per update call)."""
+        be = _bpk.get()
+        M, N, K, h = self.M, self.N, self.K, self._hyper
+        lay, total = be.pca_vb_layout(M, K)
+        st = np.zeros(total)
+
+        def put(name, v):
+            o, n = lay[name]
+            st[o:o + n] = np.asarray(v, dtype=np.float64).reshape(-1)
+        for k in ("mux", "ax", "muc", "a0", "b0", "ta0", "tb0"):
+            put(k, h[k])
+        put("ng", float(self.Ng))
+        put("sumsq", self._sumsq_y().numpy())
+        put("lprev", lprev)
+        W = self._mean(self.row)
+        if W.shape[0] != M:
+            W = self.row.u[0].broadcast_to((M, 1, K)).reshape((M, K))
+        put("w", W.numpy())
+        put("sww", self._sum_second_moment(self.row, M).numpy())
+        alpha = self.row.parents[1]
+        if isinstance(alpha, Gamma):
+            put("al_u0", np.broadcast_to(alpha.u[0].numpy(), (K,)))
+            put("al_u1", np.broadcast_to(alpha.u[1].numpy(), (K,)))
+        else:
+            put("al_u0", h["alpha_const"])
+            with np.errstate(divide="ignore"):
+                put("al_u1", np.log(h["alpha_const"]))
+        if isinstance(self.tau, Gamma):
+            put("tau_u0", self.tau.u[0].numpy())
+            put("tau_u1", self.tau.u[1].numpy())
+        else:
+            put("tau_u0", h["tau_const"])
+            put("tau_u1", np.log(h["tau_const"]))
+        if order[0] is not self.col:
+            # somebody consumes the statistics of the CURRENT q(X) before the first sweep
+            Syx, Sxx, sx = self.stats()
+            put("stats", self._stats[1].numpy())
+            put("sxxt", self._sum_xx().numpy())
+        state = DArray.from_numpy(st)
+        return state, lay
+
+    def run_resident(self, vb, program, repeat, tol, verbose):
+        """``VB.update`` for this model without leaving the device between sweeps."""
+        be = _bpk.get()
+        ops, order = program
+        M, N, K = self.M, self.N, self.K
+        import time
+        import warnings
+        check = not vb.ignore_bound_checks
+        tol_dev = (vb.tol if tol is None else tol) if check else -1.0
+        lprev = np.nan
+        if check and not vb.annealing_changed and vb.iter > 0:
+            lprev = vb.L[vb.iter - 1]
+        state, lay = self._resident_enter(order, lprev)
+        X = DArray.empty((1, N, K))
+        fast = M <= 64 and K <= 16
+        alpha = self.row.parents[1]
+        has_alpha, has_tau = isinstance(alpha, Gamma), isinstance(self.tau, Gamma)
+        terms_of = {self.Y: 0, self.col: 1, self.row: 2, alpha: 3, self.tau: 4}
+        Yd = self._Yd()
+        done, converged = 0, False
+        ctrl = DArray.zeros((2,))                 # 16 bytes = int[4]
+        while (repeat is None or done < repeat) and not converged:
+            left = 50 if repeat is None else repeat - done
+            chunk = 1 if (verbose or not fast) else min(left, 50)
+            Lh = DArray.empty((chunk, 6))
+            be.memset(ctrl.ptr, 0, 16)
+            if self.kernel_timers is not None:
+                ids = self.kernel_timers[self._timer_pos:self._timer_pos + chunk]
+                be.pca_vb_set_timers(ids)
+            t0 = time.time()
+            be.pca_vb_run(Yd.ptr, M, N, K, X.ptr, state.ptr, ops, chunk, has_alpha, has_tau, tol_dev,
+                          Lh.ptr, chunk, ctrl.ptr)
+            c = ctrl.numpy().view(np.int32)       # blocks until the chunk has run
+            if self.kernel_timers is not None:
+                self._timer_pos += be.pca_vb_timers_used()
+                be.pca_vb_set_timers([])
+            dt = (time.time() - t0)
+            n_it, stop, err = int(c[0]), int(c[1]), int(c[2])
+            if err & 1:
+                raise _bpk.NotPositiveDefinite("Matrix not positive definite")
+            if err & 2:
+                raise ValueError("Natural parameters should be positive")
+            Lrows = Lh.numpy()[:n_it]
+            for r in range(n_it):
+                if vb.iter >= len(vb.L):
+                    vb._append_iterations(100)
+                for node in vb.model:
+                    vb.l[node][vb.iter] = Lrows[r, terms_of[node]] if node in terms_of else 0.0
+                L = float(Lrows[r, 5])
+                vb.L[vb.iter] = L
+                vb.cputime[vb.iter] = dt / max(n_it, 1)
+                if verbose:
+                    vb.print("Iteration %d: loglike=%e (%.3f seconds)" % (vb.iter + 1, L, dt / max(n_it, 1)))
+                vb.converged = False
+                if check and not vb.annealing_changed and vb.iter > 0:
+                    L0 = vb.L[vb.iter - 1]
+                    if L0 - L > 1e-6:
+                        warnings.warn("Lower bound decreased %e! Bug somewhere or numerical inaccuracy?" % (L0 - L))
+                    if r == n_it - 1 and stop:
+                        if verbose:
+                            vb.print("Converged at iteration %d." % (vb.iter + 1))
+                        vb.converged = True
+                vb.annealing_changed = False
+                vb.iter += 1
+            done += n_it
+            self.fused_calls += n_it
+            converged = bool(stop)
+            # later chunks compare against the last bound even if this one started without one
+            if check and n_it > 0 and not stop:
+                pass
+            if n_it == 0:
+                break
+        if done > 0:
+            self._resident_publish(state, lay, X, order)
+        return converged
+
+    def _resident_publish(self, state, lay, X, order):
+        """Point the node objects at the device state the loop left behind."""
+        M, N, K = self.M, self.N, self.K
+        col, row, tau = self.col, self.row, self.tau
+
+        def view(name, shape):
+            o, n = lay[name]
+            return state.slice_axis(0, o, o + n).reshape(shape)
+        # X
+        Lam = view("lamx", (K, K))
+        cov = view("covx", (1, 1, K, K))
+        logdet = view("logdetx", ())
+        phi1 = D.mul(Lam, -0.5).reshape((1, 1, K, K))
+
+        def phi0_fn():
+            return D.sum_product([Lam, X], [["i", "j"], ["o", "n", "j"]], ["o", "n", "i"])
+
+        def g_fn():
+            q = D.sum_product([X, Lam, X], [["o", "n", "i"], ["i", "j"], ["o", "n", "j"]], ["o", "n"])
+            return D.axpby(-0.5, q, 0.5, logdet)
+        col.phi = [LazyArray((1, N, K), phi0_fn), phi1]
+        col.u = [X, FactoredSecondMoment(X, cov, (K,))]
+        col.g = LazyArray((1, N), g_fn)
+        col._version += 1
+        u_par = col.moments_from_parents()
+        col._fused = dict(Lam=Lam, logdet=logdet, cov=cov,
+                          phi_p=col._canonical_phi(col._distribution.compute_phi_from_parents(*u_par)))
+        self._stats = (col._version, view("stats", (M * K + K * K + K,)))
+        # C
+        W = view("w", (M, 1, K))
+        row.phi = [view("phi0c", (M, 1, K)), D.mul(view("lamc", (1, 1, K, K)), -0.5)]
+        row.u = [W, FactoredSecondMoment(W, view("covc", (1, 1, K, K)), (K,))]
+        row.g = view("gc", (M, 1))
+        row._version += 1
+        alpha = row.parents[1]
+        if isinstance(alpha, Gamma):
+            alpha.phi = [view("al_phi0", (K,)), view("al_phi1", (K,))]
+            alpha.u = [view("al_u0", (K,)), view("al_u1", (K,))]
+            alpha.g = view("al_g", (K,))
+            alpha._version += 1
+        if isinstance(tau, Gamma):
+            shp = tuple(tau.plates)
+            tau.phi = [view("tau_phi0", shp), view("tau_phi1", shp)]
+            tau.u = [view("tau_u0", shp), view("tau_u1", shp)]
+            tau.g = view("tau_g", shp)
+            tau._version += 1
+        self._e2 = None
+
+
 class GaussianMixturePlan:
     """Y = Mixture(Z, Gaussian, mu, Lambda) with Y fully observed (gmm.rst:71-98).
 

@@ -27,7 +27,7 @@ from ..engine.node import Node
 class VB:
 
     def __init__(self, *nodes, tol=1e-5, autosave_filename=None, autosave_iterations=0,
-                 use_logging=False, user_data=None, callback=None, fused=True):
+                 use_logging=False, user_data=None, callback=None, fused=True, resident=True):
         self.user_data = user_data
         for ind, node in enumerate(nodes):
             if not isinstance(node, Node):
@@ -57,6 +57,7 @@ class VB:
         self.callback = callback
         self.callback_output = None
         self.tol = tol
+        self.resident = resident        # allow whole sweeps to stay on the device (plans.run_resident)
         self.plans = []
         if fused:
             from ..engine import plans
@@ -81,6 +82,14 @@ class VB:
     def update(self, *nodes, repeat=1, plot=False, tol=None, verbose=True, tqdm=None):
         if len(nodes) == 0:
             nodes = self.model
+        # whole sweeps that can stay on the device do (engine/plans.py: FactorModelPlan.run_resident)
+        if self.resident and tqdm is None and not plot and not callable(self.callback) \
+                and self.autosave_iterations == 0:
+            for plan in self.plans:
+                prog = plan.resident_program(self, nodes) if hasattr(plan, "resident_program") else None
+                if prog is not None:
+                    plan.run_resident(self, prog, repeat, tol, verbose)
+                    return
         if tqdm is not None:
             tqdm = tqdm(total=repeat)
         i = 0

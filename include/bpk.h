@@ -78,6 +78,8 @@ int bpk_comm_unique_id(char id[128]);
 int bpk_comm_init(const char id[128], int nranks, int rank);
 int bpk_comm_size(int *nranks, int *rank);
 int bpk_allreduce_sum_f64(double *dev, uint64_t count);     /* in place, on the compute stream */
+/* out of place: dst = sum over ranks of src (dst may equal src)                */
+int bpk_allreduce_sum_f64_oop(const double *src, double *dst, uint64_t count);
 int bpk_comm_destroy(void);
 
 /* ---- generic broadcast kernels (seam 1) -------------------------------- */
@@ -201,6 +203,39 @@ int bpk_gmm_sweep(const double *Y, int64_t N, int D, int K,
 /* statistics only, for responsibilities P [N][K] that did not come from bpk_gmm_sweep
  * (e.g. a random initialisation): stats[0..K+K*D+K*D*D) += sums, stats[last] unchanged.   */
 int bpk_gmm_stats(const double *Y, int64_t N, int D, int K, const double *P, double *stats);
+
+/* ---- device-resident VB loop of the factor model (seam 3: VB.update, vmp.py:132-172) ----
+ * Model: X=GaussianARD(mu_x,a_x,plates=(1,N),shape=(K,)), C=GaussianARD(mu_c,alpha,plates=(M,1),
+ * shape=(K,)), alpha~Gamma(a0,b0) plates (K,) or constant, tau~Gamma(ta0,tb0) or constant,
+ * Y=GaussianARD(SumMultiply(X,C),tau) fully observed (doc/source/examples/pca.rst:40-66).
+ * `ops` is ONE iteration of the user's update order as opcodes; it is replayed `niter` times
+ * with no host round trip: the big op is the one-pass sweep kernel, every run of small ops is
+ * one single-CTA launch.  BOUND evaluates all lower-bound terms (expfamily.py:400-480), appends
+ * [L_Y, L_X, L_C, L_alpha, L_tau, L] to Lhist, and applies the convergence test of vmp.py:738-747
+ * on device (tol < 0 disables it); once it fires, ctrl[1] is raised and every later kernel of the
+ * run is a no-op, so the state is exactly the one the reference would have stopped at.
+ * state: fp64 vector laid out per bpk_pca_vb_layout (hyper-parameters, q(C), q(alpha), q(tau),
+ * shared part of q(X), plate-summed statistics); X: [N][K] posterior means, rewritten every sweep.
+ * ctrl: device int[4] = {iterations finished, stop, error bits (1 = not SPD, 2 = domain), 0}.
+ * With a communicator (bpk_comm_init) STATS is followed by the sweep's one all-reduce.          */
+enum {
+    BPK_VBOP_XSWEEP = 1,  /* X.update(): one pass over Y (pca_xsweep_kernel)                    */
+    BPK_VBOP_STATS = 2,   /* grid reduction of the sweep's partial statistics (+ all-reduce)    */
+    BPK_VBOP_SXXT = 3,    /* sum_n <x x^T> = N Cov_x + S_xx                                     */
+    BPK_VBOP_XPRE = 4,    /* shared part of q(X): Cov_x, A = tau Cov_x <W>^T, b                 */
+    BPK_VBOP_ROW = 5,     /* C.update()                                                         */
+    BPK_VBOP_ALPHA = 6,   /* alpha.update()                                                     */
+    BPK_VBOP_TAU = 7,     /* tau.update()                                                       */
+    BPK_VBOP_BOUND = 8    /* lower bound + convergence test                                     */
+};
+int bpk_pca_vb_layout(int M, int K, int64_t *offsets /* [nfields+1] */, int *nfields);
+const char *bpk_pca_vb_field_name(int i);
+int bpk_pca_vb_run(const double *Y, int64_t M, int64_t N, int K, double *X, double *state,
+                   const int *ops, int nops, int niter, int has_alpha, int has_tau, double tol,
+                   double *Lhist, int cap, int *ctrl);
+/* bench.py: record these timers (bpk_timer_create ids) around the next n sweep-kernel launches */
+int bpk_pca_vb_set_timers(const int *ids, int n);
+int bpk_pca_vb_timers_used(void);
 
 #ifdef __cplusplus
 }

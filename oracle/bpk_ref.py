@@ -127,6 +127,12 @@ class RefBackend:
             v = _dense(dev, (count,))
             v[...] = self._allreduce_hook(v.copy())
 
+    def allreduce_sum_f64_oop(self, src, dst, count):
+        v = _dense(src, (count,)).copy()
+        if self._allreduce_hook is not None:
+            v = self._allreduce_hook(v)
+        _dense(dst, (count,))[...] = v
+
     def comm_destroy(self):
         self.nranks, self.rank = 1, 0
 
@@ -426,3 +432,147 @@ class RefBackend:
         s[:K] += p.sum(axis=0)
         s[K:K + K * D] += (p.T @ y).ravel()
         s[K + K * D:K + K * D + K * D * D] += np.einsum("nk,ni,nj->kij", p, y, y).ravel()
+
+    # ---- device-resident VB loop of the factor model (csrc/pca_vb.cu) ------------------------------
+    VB_FIELDS = ["mux", "ax", "muc", "a0", "b0", "ta0", "tb0", "sumsq", "ng", "reserved",
+                 "w", "sww", "covc", "lamc", "logdetc", "phi0c", "gc",
+                 "al_phi0", "al_phi1", "al_u0", "al_u1", "al_g",
+                 "tau_phi0", "tau_phi1", "tau_u0", "tau_u1", "tau_g",
+                 "covx", "lamx", "logdetx", "A", "bx", "stats", "sxxt", "lprev", "stats_local"]
+
+    def pca_vb_layout(self, M, K):
+        KK, MK = K * K, M * K
+        NS = MK + KK + K
+        size = dict(mux=K, ax=K, muc=K, a0=K, b0=K, w=MK, sww=KK, covc=KK, lamc=KK, phi0c=MK, gc=M,
+                    al_phi0=K, al_phi1=K, al_u0=K, al_u1=K, al_g=K, covx=KK, lamx=KK, A=MK, bx=K,
+                    stats=NS, sxxt=KK, stats_local=NS)
+        out, o = {}, 0
+        for f in self.VB_FIELDS:
+            n = size.get(f, 1)
+            out[f] = (o, n)
+            o += n
+        return out, o
+
+    def pca_vb_set_timers(self, ids):
+        self._vb_timers = list(ids)
+        self._vb_timer_pos = 0
+
+    def pca_vb_timers_used(self):
+        return getattr(self, "_vb_timer_pos", 0)
+
+    @staticmethod
+    def _gamma(phi0, phi1):
+        """gamma.py:124-148."""
+        a, b = phi1, -phi0
+        if np.any(a <= 0) or np.any(b <= 0):
+            raise ValueError("Natural parameters should be positive")
+        return a / b, sp.psi(a) - np.log(b), a * np.log(b) - sp.gammaln(a)
+
+    def pca_vb_run(self, Y, M, N, K, X, state, ops, niter, has_alpha, has_tau, tol, Lhist, cap, ctrl):
+        """The VB.update loop of vmp.py:132-172 for the PCA model of pca.rst:40-66, node by node:
+        X: gaussian.py:649-706 + dot.py:581; C: same with roles swapped; alpha, tau: gamma.py:96-148 with
+        the messages of gaussian.py:609-637 / :2351-2371; bound: expfamily.py:400-480; stop: vmp.py:738-747."""
+        lay, total = self.pca_vb_layout(M, K)
+        st = _dense(state, (total,))
+        f = {k: st[o:o + n] for k, (o, n) in lay.items()}
+        c = _dense(ctrl, (4,), np.int32)
+        Lh = _dense(Lhist, (cap, 6))
+        y = _dense(Y, (M, N))
+        x = _dense(X, (N, K))
+        MK, KK = M * K, K * K
+        W = f["w"].reshape(M, K)
+        LOG2PI = np.log(2 * np.pi)
+        Ng = float(f["ng"][0])
+
+        def E2():
+            return f["sumsq"][0] - 2 * np.sum(W * f["stats"][:MK].reshape(M, K)) + np.sum(f["sww"] * f["sxxt"])
+
+        for _ in range(niter):
+            for op in ops:
+                if c[1]:
+                    return
+                tau = f["tau_u0"][0]
+                if op == 4:      # XPRE
+                    lam = np.diag(f["ax"]) + tau * f["sww"].reshape(K, K)
+                    cov = np.linalg.inv(lam)
+                    f["lamx"][:] = lam.ravel()
+                    f["covx"][:] = cov.ravel()
+                    f["logdetx"][0] = np.linalg.slogdet(lam)[1]
+                    f["bx"][:] = cov @ (f["ax"] * f["mux"])
+                    f["A"][:] = (tau * cov @ W.T).ravel()
+                elif op == 1:    # XSWEEP
+                    self._launches += 1
+                    tp = getattr(self, "_vb_timer_pos", 0)
+                    if tp < len(getattr(self, "_vb_timers", [])):
+                        self._vb_timer_pos = tp + 1
+                    x[...] = y.T @ f["A"].reshape(K, M).T + f["bx"]
+                    self._vb_local = np.concatenate([(y @ x).ravel(), (x.T @ x).ravel(), x.sum(0)])
+                elif op == 2:    # STATS (+ the sweep's one all-reduce)
+                    self._launches += 1
+                    v = self._vb_local
+                    if self._allreduce_hook is not None:
+                        f["stats_local"][:] = v
+                        v = self._allreduce_hook(v.copy())
+                    f["stats"][:] = v
+                elif op == 3:    # SXXT
+                    f["sxxt"][:] = Ng * f["covx"] + f["stats"][MK:MK + KK]
+                elif op == 5:    # ROW
+                    lam = np.diag(f["al_u0"]) + tau * f["sxxt"].reshape(K, K)
+                    cov = np.linalg.inv(lam)
+                    ld = np.linalg.slogdet(lam)[1]
+                    phi0 = f["al_u0"] * f["muc"] + tau * f["stats"][:MK].reshape(M, K)
+                    W[...] = phi0 @ cov.T
+                    f["lamc"][:] = lam.ravel()
+                    f["covc"][:] = cov.ravel()
+                    f["logdetc"][0] = ld
+                    f["phi0c"][:] = phi0.ravel()
+                    f["gc"][:] = -0.5 * np.sum(W * phi0, axis=1) + 0.5 * ld
+                    f["sww"][:] = (M * cov + W.T @ W).ravel()
+                elif op == 6:    # ALPHA
+                    mu = f["muc"]
+                    d = np.diag(f["sww"].reshape(K, K)) - 2 * mu * W.sum(0) + M * mu * mu
+                    f["al_phi0"][:] = -f["b0"] - 0.5 * d
+                    f["al_phi1"][:] = f["a0"] + 0.5 * M
+                    f["al_u0"][:], f["al_u1"][:], f["al_g"][:] = self._gamma(f["al_phi0"], f["al_phi1"])
+                elif op == 7:    # TAU
+                    f["tau_phi0"][0] = -f["tb0"][0] - 0.5 * E2()
+                    f["tau_phi1"][0] = f["ta0"][0] + 0.5 * M * Ng
+                    f["tau_u0"][0], f["tau_u1"][0], f["tau_g"][0] = self._gamma(f["tau_phi0"][0], f["tau_phi1"][0])
+                elif op == 8:    # BOUND
+                    self._launches += 1
+                    logtau = f["tau_u1"][0]
+                    LY = -0.5 * tau * E2() + 0.5 * M * Ng * (logtau - LOG2PI)
+                    Sxx = f["stats"][MK:MK + KK]
+                    sx = f["stats"][MK + KK:]
+                    ax, mux = f["ax"], f["mux"]
+                    trLS = np.sum(f["lamx"] * Sxx)
+                    dphi1 = 0.5 * f["lamx"].reshape(K, K) - 0.5 * np.diag(ax)
+                    LX = (np.sum(ax * mux * sx) - trLS + np.sum(dphi1.ravel() * f["sxxt"]) + 0.5 * trLS
+                          - 0.5 * Ng * f["logdetx"][0] + Ng * np.sum(-0.5 * ax * mux ** 2 + 0.5 * np.log(ax)))
+                    al, lal, muc = f["al_u0"], f["al_u1"], f["muc"]
+                    phi0c = f["phi0c"].reshape(M, K)
+                    LC = (np.sum((al * muc - phi0c) * W)
+                          + np.sum((0.5 * f["lamc"].reshape(K, K) - 0.5 * np.diag(al)).ravel() * f["sww"])
+                          - np.sum(f["gc"]) + M * np.sum(-0.5 * al * muc ** 2 + 0.5 * lal))
+                    LA = 0.0
+                    if has_alpha:
+                        a0, b0 = f["a0"], f["b0"]
+                        LA = np.sum((-b0 - f["al_phi0"]) * al + (a0 - f["al_phi1"]) * lal
+                                    + a0 * np.log(b0) - sp.gammaln(a0) - f["al_g"])
+                    LT = 0.0
+                    if has_tau:
+                        a0, b0 = f["ta0"][0], f["tb0"][0]
+                        LT = ((-b0 - f["tau_phi0"][0]) * tau + (a0 - f["tau_phi1"][0]) * logtau
+                              + a0 * np.log(b0) - sp.gammaln(a0) - f["tau_g"][0])
+                    L = LY + LX + LC + LA + LT
+                    it = int(c[0])
+                    if it < cap:
+                        Lh[it] = [LY, LX, LC, LA, LT, L]
+                    L0 = f["lprev"][0]
+                    f["lprev"][0] = L
+                    c[0] = it + 1
+                    if tol >= 0 and not np.isnan(L0):
+                        if (L - L0) / (0.5 * (abs(L0) + abs(L))) < tol:
+                            c[1] = 1
+                else:
+                    raise ValueError("unknown opcode %d" % op)

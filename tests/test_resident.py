@@ -1,0 +1,138 @@
+"""The device-resident VB loop (bpk_pca_vb_run, csrc/pca_vb.cu) against the per-node path.
+
+Both paths run the same model on the same backend; the per-node path is the one pinned to the
+reference's goldens in test_models.py, so agreement here extends that pin to the resident loop.
+Covers: every update order, non-zero prior means, constant alpha / tau, the device-side
+convergence stop (must end at the same iteration), chunked updates, and the generic-shape path."""
+import ctypes
+import itertools
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def _pca(y, K, order="XCat", mux=0.0, ax=1.0, muc=0.0, alpha_const=None, tau_const=None, resident=True,
+         seed=3):
+    from bayespy_b200.nodes import GaussianARD, Gamma, SumMultiply
+    from bayespy_b200.inference import VB
+    M, N = y.shape
+    X = GaussianARD(mux, ax, plates=(1, N), shape=(K,), name="X")
+    alpha = Gamma(1e-3, 1e-3, plates=(K,), name="alpha") if alpha_const is None else alpha_const
+    C = GaussianARD(muc, alpha, plates=(M, 1), shape=(K,), name="C")
+    F = SumMultiply("d,d->", X, C)
+    tau = Gamma(1e-3, 1e-3, name="tau") if tau_const is None else tau_const
+    Y = GaussianARD(F, tau, name="Y")
+    Y.observe(y)
+    C.initialize_from_value(np.random.RandomState(seed).randn(M, 1, K))
+    nodes = dict(X=X, C=C, a=alpha, t=tau)
+    model = [Y] + [nodes[c] for c in order if not isinstance(nodes[c], (int, float, np.ndarray))]
+    Q = VB(*model, resident=resident)
+    return Q, dict(X=X, C=C, alpha=alpha, tau=tau, Y=Y)
+
+
+def _data(M, N, K, seed=0):
+    rs = np.random.RandomState(seed)
+    return rs.randn(M, 3) @ rs.randn(3, N) + 0.3 * rs.randn(M, N)
+
+
+def _compare(Qa, na, Qb, nb, iters, rtol=1e-9):
+    np.testing.assert_allclose(Qa.L[:iters], Qb.L[:iters], rtol=rtol)
+    for node in Qa.model:
+        np.testing.assert_allclose(Qa.l[node][:iters], Qb.l[Qb[node.name]][:iters], rtol=1e-7, atol=1e-6)
+    for name in ("X", "C", "alpha", "tau"):
+        a, b = na[name], nb[name]
+        if not hasattr(a, "u"):
+            continue
+        for i in range(2):
+            np.testing.assert_allclose(np.asarray(a.u[i]), np.asarray(b.u[i]), rtol=1e-7, atol=1e-9,
+                                       err_msg="%s.u[%d]" % (name, i))
+            np.testing.assert_allclose(np.broadcast_to(np.asarray(a.phi[i]), np.shape(np.asarray(b.phi[i]))),
+                                       np.asarray(b.phi[i]), rtol=1e-7, atol=1e-9, err_msg="%s.phi[%d]" % (name, i))
+        np.testing.assert_allclose(np.broadcast_to(np.asarray(a.g), np.shape(np.asarray(b.g))), np.asarray(b.g),
+                                   rtol=1e-7, atol=1e-8, err_msg="%s.g" % name)
+
+
+@pytest.mark.parametrize("order", ["".join(p) for p in itertools.permutations("XCat")][::3])
+def test_resident_matches_per_node_every_order(backend, order):
+    y = _data(12, 150, 4)
+    Qa, na = _pca(y, 4, order, resident=True)
+    Qb, nb = _pca(y, 4, order, resident=False)
+    Qa.update(repeat=6, verbose=False, tol=0)
+    Qb.update(repeat=6, verbose=False, tol=0)
+    assert Qa.plans[0].fused_calls >= 6
+    _compare(Qa, na, Qb, nb, 6)
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 700, 16), (20, 129, 5), (80, 90, 3), (10, 60, 20)])
+def test_resident_shapes_and_priors(backend, M, N, K):
+    y = _data(M, N, K, seed=M)
+    rs = np.random.RandomState(1)
+    kw = dict(mux=0.1 * rs.randn(K), ax=0.5 + rs.rand(K), muc=0.2 * rs.randn(K))
+    Qa, na = _pca(y, K, resident=True, **kw)
+    Qb, nb = _pca(y, K, resident=False, **kw)
+    for _ in range(2):                       # two calls: re-entry from a published state
+        Qa.update(repeat=3, verbose=False, tol=0)
+        Qb.update(repeat=3, verbose=False, tol=0)
+    _compare(Qa, na, Qb, nb, 6)
+
+
+def test_resident_constant_alpha_tau(backend):
+    y = _data(16, 200, 4)
+    Qa, na = _pca(y, 4, alpha_const=0.7, tau_const=2.5, resident=True)
+    Qb, nb = _pca(y, 4, alpha_const=0.7, tau_const=2.5, resident=False)
+    Qa.update(repeat=4, verbose=False, tol=0)
+    Qb.update(repeat=4, verbose=False, tol=0)
+    assert Qa.plans[0].fused_calls >= 4
+    np.testing.assert_allclose(Qa.L[:4], Qb.L[:4], rtol=1e-9)
+    np.testing.assert_allclose(np.asarray(na["C"].u[0]), np.asarray(nb["C"].u[0]), rtol=1e-8, atol=1e-10)
+
+
+def test_resident_converges_at_the_same_iteration(backend, capsys):
+    y = _data(12, 300, 3, seed=4)
+    Qa, na = _pca(y, 3, resident=True)
+    Qb, nb = _pca(y, 3, resident=False)
+    Qa.update(repeat=400, verbose=False, tol=1e-6)
+    Qb.update(repeat=400, verbose=False, tol=1e-6)
+    assert Qa.converged and Qb.converged
+    assert Qa.iter == Qb.iter and Qa.iter < 400
+    _compare(Qa, na, Qb, nb, Qa.iter)
+    # verbose output keeps the reference's format (vmp.py:725,745)
+    Qc, _ = _pca(y, 3, resident=True)
+    Qc.update(repeat=400, tol=1e-6)
+    out = capsys.readouterr().out.strip().splitlines()
+    assert out[0].startswith("Iteration 1: loglike=") and out[-1] == "Converged at iteration %d." % Qa.iter
+
+
+def test_resident_mixed_with_single_node_updates(backend):
+    """A resident run followed by hand-driven node updates (and back) stays consistent."""
+    y = _data(12, 150, 4, seed=7)
+    Qa, na = _pca(y, 4, resident=True)
+    Qb, nb = _pca(y, 4, resident=False)
+    for Q, n in ((Qa, na), (Qb, nb)):
+        Q.update(repeat=2, verbose=False, tol=0)
+        Q.update(n["C"], n["tau"], repeat=1, verbose=False, tol=0)      # not a full sweep: per-node path
+        Q.update(repeat=2, verbose=False, tol=0)
+    _compare(Qa, na, Qb, nb, 5)
+
+
+def test_layout_of_the_library_matches_the_oracle():
+    """Host-only entry point: callable without a GPU."""
+    from bayespy_b200 import _bpk
+    from oracle.bpk_ref import RefBackend
+    if not os.path.exists(_bpk.LIB_PATH):
+        pytest.skip("libbpk.so not built")
+    lib = ctypes.CDLL(_bpk.LIB_PATH)
+    lib.bpk_pca_vb_field_name.restype = ctypes.c_char_p
+    for M, K in ((64, 16), (7, 3), (100, 20)):
+        n = ctypes.c_int()
+        assert lib.bpk_pca_vb_layout(M, K, None, ctypes.byref(n)) == 0
+        off = (ctypes.c_int64 * (n.value + 1))()
+        assert lib.bpk_pca_vb_layout(M, K, off, ctypes.byref(n)) == 0
+        lay, total = RefBackend().pca_vb_layout(M, K)
+        assert total == off[n.value]
+        for i in range(n.value):
+            name = lib.bpk_pca_vb_field_name(i).decode()
+            assert lay[name] == (off[i], off[i + 1] - off[i]), name
