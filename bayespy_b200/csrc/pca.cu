@@ -23,6 +23,7 @@
 // partials are reduced warp->CTA in smem and CTA->grid by a second tiny
 // kernel in a fixed order (deterministic, no atomics).
 #include "common.cuh"
+#include <stdlib.h>
 #include "pca_common.cuh"
 #include "spd.cuh"
 
@@ -230,6 +231,253 @@ pca_xsweep_kernel(const double *__restrict__ Y, int64_t M, int64_t N, int K,
     }
 }
 
+// =====================================================================================
+// v2: warp-specialised sweep (aligned inputs).  16 warps per SM instead of 8:
+//   X-warps 0..7  hold the A fragments, compute x = A y + b for their 1/8 of the tile's
+//                 columns on the fp64 tensor pipe, store x to HBM straight from the
+//                 accumulators, and hand the tile to their partner through shared memory;
+//   S-warps 8..15 hold the S_yx / S_xx accumulators and run the second contraction.
+// Each role fits 128 registers, so four warps per scheduler keep the DMMA pipe fed while
+// others wait on shared-memory loads or barriers (v1: two 220-register warps, 58% pipe
+// utilisation).  Y tiles arrive through a ring of padded shared-memory stages filled by
+// cp.async.bulk row copies (the TMA engine; one warp issues 64 copies per tile) that
+// complete on per-stage mbarriers; stages are released through "empty" mbarriers, and each
+// X/S warp pair hands x tiles over through its own double-buffered mbarrier pair, so there
+// is no CTA-wide barrier inside the main loop.
+// =====================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}\n"
+                 ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile("{\n.reg .pred P1;\nWAIT_LOOP:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+                 "@P1 bra WAIT_DONE;\nbra WAIT_LOOP;\nWAIT_DONE:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+#define WS_PAIRS 8
+
+template <int NT, int STAGES, int DIST, bool COMPUTE_X>
+__global__ void __launch_bounds__(2 * WS_PAIRS * 32, 1)
+pca_xsweep_ws_kernel(const double *__restrict__ Y, int64_t M, int64_t N, int K,
+                     const double *__restrict__ A, const double *__restrict__ bvec,
+                     double *__restrict__ X, double *__restrict__ partial, int64_t ntiles,
+                     const int *__restrict__ stop) {
+    constexpr int T = WS_PAIRS * NT, LDY = T + 4, NS = NT / 4, CB = NT / 8;
+    static_assert(DIST >= 1 && DIST < STAGES, "prefetch distance must leave one stage for the consumers");
+    if (stop && *stop) return;
+    extern __shared__ __align__(128) double smem[];
+    double *Ysm = smem;                                              // [STAGES][64][LDY]
+    double *Xsm = Ysm + (size_t)STAGES * PCA_MP * LDY;               // [PAIRS][2][NT][LDX]
+    uint64_t *bars = (uint64_t *)(Xsm + (size_t)WS_PAIRS * 2 * NT * PCA_LDX);
+    uint64_t *full = bars, *empty = bars + STAGES;
+    uint64_t *xfull = bars + 2 * STAGES, *xfree = xfull + 2 * WS_PAIRS;   // [pair][2]
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int gr = lane >> 2, tg = lane & 3;
+    const bool is_x = w < WS_PAIRS;
+    const int p = w & (WS_PAIRS - 1);
+
+    for (int e = threadIdx.x; e < STAGES * PCA_MP * LDY; e += blockDim.x) Ysm[e] = 0.0;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 2 * WS_PAIRS); }
+        for (int i = 0; i < 2 * WS_PAIRS; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xfree[i], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // zero fill (generic) before bulk writes (async proxy)
+    __syncthreads();
+
+    const int64_t first = blockIdx.x, stride = gridDim.x;
+    const int64_t ntl = first < ntiles ? (ntiles - first + stride - 1) / stride : 0;   // tiles of this CTA
+
+    auto issue = [&](int64_t j) {        // whole warp 0: bulk-copy the rows of local tile j
+        const int slot = (int)(j % STAGES);
+        if (j >= STAGES) mbar_wait(&empty[slot], (uint32_t)((j / STAGES - 1) & 1));
+        const int64_t n0 = (first + j * stride) * T;
+        const int64_t rem = N - n0;
+        const uint32_t ncols = (uint32_t)(rem < T ? rem : T);
+        if (lane == 0) mbar_expect_tx(&full[slot], (uint32_t)M * ncols * 8u);
+        __syncwarp();
+        double *dst = Ysm + (size_t)slot * PCA_MP * LDY;
+        for (int m = lane; m < (int)M; m += 32) bulk_g2s(dst + m * LDY, Y + (int64_t)m * N + n0, ncols * 8u, &full[slot]);
+    };
+
+    if (is_x) {
+        double afrag[2][16];
+        double bk[2] = {0.0, 0.0};
+        if (COMPUTE_X) {
+#pragma unroll
+            for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                for (int ms = 0; ms < 16; ++ms) {
+                    int k = kb * 8 + gr, m = ms * 4 + tg;
+                    afrag[kb][ms] = (k < K && m < M) ? A[(int64_t)k * M + m] : 0.0;
+                }
+            if (bvec) {
+                if (gr < K) bk[0] = bvec[gr];
+                if (8 + gr < K) bk[1] = bvec[8 + gr];
+            }
+        }
+        if (w == 0)
+            for (int64_t j = 0; j < DIST && j < ntl; ++j) issue(j);
+        for (int64_t i = 0; i < ntl; ++i) {
+            if (w == 0 && i + DIST < ntl) issue(i + DIST);
+            const int slot = (int)(i % STAGES), b = (int)(i & 1);
+            const int c0 = p * NT;
+            const int64_t nbase = (first + i * stride) * T + c0;
+            double *Xs = Xsm + ((size_t)(p * 2 + b) * NT) * PCA_LDX;
+            if (COMPUTE_X) {
+                mbar_wait(&full[slot], (uint32_t)((i / STAGES) & 1));
+                const double *Ys = Ysm + (size_t)slot * PCA_MP * LDY;
+                // two partial sums over the m blocks per accumulator: 4*CB independent DMMA chains
+                double acc[2][2][CB][2];
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                    for (int cb = 0; cb < CB; ++cb) {
+                        acc[0][kb][cb][0] = acc[0][kb][cb][1] = bk[kb];
+                        acc[1][kb][cb][0] = acc[1][kb][cb][1] = 0.0;
+                    }
+#pragma unroll
+                for (int ms = 0; ms < 16; ++ms) {
+#pragma unroll
+                    for (int cb = 0; cb < CB; ++cb) {
+                        double yb = Ys[(ms * 4 + tg) * LDY + c0 + cb * 8 + gr];
+                        dmma884(acc[ms & 1][0][cb][0], acc[ms & 1][0][cb][1], afrag[0][ms], yb);
+                        dmma884(acc[ms & 1][1][cb][0], acc[ms & 1][1][cb][1], afrag[1][ms], yb);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[slot]);           // this warp no longer reads the Y stage
+                if (i >= 2) mbar_wait(&xfree[p * 2 + b], (uint32_t)(((i >> 1) - 1) & 1));
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                    for (int cb = 0; cb < CB; ++cb)
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const int nl = cb * 8 + 2 * tg + j, k = kb * 8 + gr;
+                            const bool inb = nbase + nl < N;
+                            double v = inb ? acc[0][kb][cb][j] + acc[1][kb][cb][j] : 0.0;   // padded columns add nothing
+                            Xs[nl * PCA_LDX + k] = v;
+                            if (inb && k < K) X[(nbase + nl) * K + k] = v;
+                        }
+            } else {
+                if (lane == 0) {
+                    mbar_wait(&full[slot], (uint32_t)((i / STAGES) & 1));
+                    mbar_arrive(&empty[slot]);
+                }
+                if (i >= 2) mbar_wait(&xfree[p * 2 + b], (uint32_t)(((i >> 1) - 1) & 1));
+                for (int e = lane; e < NT * PCA_KP; e += 32) {
+                    int nl = e >> 4, k = e & 15;
+                    Xs[nl * PCA_LDX + k] = (nbase + nl < N && k < K) ? X[(nbase + nl) * K + k] : 0.0;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&xfull[p * 2 + b]);
+        }
+    } else {
+        double syx[8][2][2];
+        double sxx[3][2];
+        double sx = 0.0;
+#pragma unroll
+        for (int mb = 0; mb < 8; ++mb)
+#pragma unroll
+            for (int kb = 0; kb < 2; ++kb) syx[mb][kb][0] = syx[mb][kb][1] = 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) sxx[i][0] = sxx[i][1] = 0.0;
+        for (int64_t i = 0; i < ntl; ++i) {
+            const int slot = (int)(i % STAGES), b = (int)(i & 1);
+            const int c0 = p * NT;
+            const double *Ys = Ysm + (size_t)slot * PCA_MP * LDY;
+            const double *Xs = Xsm + ((size_t)(p * 2 + b) * NT) * PCA_LDX;
+            mbar_wait(&full[slot], (uint32_t)((i / STAGES) & 1));
+            mbar_wait(&xfull[p * 2 + b], (uint32_t)((i >> 1) & 1));
+            if (lane < PCA_KP) {
+#pragma unroll
+                for (int nl = 0; nl < NT; ++nl) sx += Xs[nl * PCA_LDX + lane];
+            }
+#pragma unroll
+            for (int ns = 0; ns < NS; ++ns) {
+                double xf0 = Xs[(ns * 4 + tg) * PCA_LDX + gr];
+                double xf1 = Xs[(ns * 4 + tg) * PCA_LDX + 8 + gr];
+#pragma unroll
+                for (int mb = 0; mb < 8; ++mb) {
+                    double ya = Ys[(mb * 8 + gr) * LDY + c0 + ns * 4 + tg];
+                    dmma884(syx[mb][0][0], syx[mb][0][1], ya, xf0);
+                    dmma884(syx[mb][1][0], syx[mb][1][1], ya, xf1);
+                }
+                dmma884(sxx[0][0], sxx[0][1], xf0, xf0);
+                dmma884(sxx[1][0], sxx[1][1], xf0, xf1);
+                dmma884(sxx[2][0], sxx[2][1], xf1, xf1);
+            }
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&xfree[p * 2 + b]); mbar_arrive(&empty[slot]); }
+        }
+        // every issued tile has been consumed by every warp once all warps pass the barrier below
+        __syncthreads();
+        double *mine = smem + (size_t)p * PCA_NSTAT;
+#pragma unroll
+        for (int mb = 0; mb < 8; ++mb)
+#pragma unroll
+            for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                    mine[(mb * 8 + gr) * PCA_KP + kb * 8 + 2 * tg + j] = syx[mb][kb][j];
+        double *mxx = mine + PCA_MP * PCA_KP;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            mxx[gr * PCA_KP + 2 * tg + j] = sxx[0][j];
+            mxx[gr * PCA_KP + 8 + 2 * tg + j] = sxx[1][j];
+            mxx[(8 + 2 * tg + j) * PCA_KP + gr] = sxx[1][j];
+            mxx[(8 + gr) * PCA_KP + 8 + 2 * tg + j] = sxx[2][j];
+        }
+        if (lane < PCA_KP) mine[PCA_MP * PCA_KP + PCA_KP * PCA_KP + lane] = sx;
+    }
+    if (is_x) __syncthreads();     // pairs with the S-warps' barrier above
+    __syncthreads();
+    double *pout = partial + (size_t)blockIdx.x * PCA_NSTAT;
+    for (int e = threadIdx.x; e < PCA_NSTAT; e += blockDim.x) {
+        double s = 0.0;
+#pragma unroll
+        for (int ww = 0; ww < WS_PAIRS; ++ww) s += smem[(size_t)ww * PCA_NSTAT + e];
+        pout[e] = s;
+    }
+}
+
+template <int NT, int STAGES, int DIST, bool COMPUTE_X>
+static int pca_launch_ws(const double *Y, int64_t M, int64_t N, int K, const double *A, const double *b,
+                         double *X, const int *stop, double **partial_out, int *nparts_out) {
+    constexpr int T = WS_PAIRS * NT, LDY = T + 4;
+    size_t ring = (size_t)STAGES * PCA_MP * LDY * sizeof(double);
+    size_t xs = (size_t)WS_PAIRS * 2 * NT * PCA_LDX * sizeof(double);
+    size_t bars = (size_t)(2 * STAGES + 4 * WS_PAIRS) * sizeof(uint64_t);
+    size_t redb = (size_t)WS_PAIRS * PCA_NSTAT * sizeof(double);
+    size_t smem = ring + xs + bars;
+    if (smem < redb) smem = redb;
+    int64_t ntiles = (N + T - 1) / T;
+    int grid = g_bpk.sm_count;
+    if (ntiles < grid) grid = (int)ntiles;
+    double *partial = bpk_scratch((size_t)grid * PCA_NSTAT * sizeof(double));
+    if (!partial) return bpk_set_error(BPK_ECUDA, "pca: scratch allocation failed");
+    auto kern = pca_xsweep_ws_kernel<NT, STAGES, DIST, COMPUTE_X>;
+    BPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BPK_LAUNCH(kern, grid, 2 * WS_PAIRS * 32, smem, Y, M, N, K, A, b, X, partial, ntiles, stop);
+    *partial_out = partial;
+    *nparts_out = grid;
+    return BPK_OK;
+}
+
 // grid-level reduction of the per-CTA partials into the caller's (unpadded) stats
 __global__ void pca_stats_final_kernel(const double *__restrict__ partial, int nblocks, int M, int K,
                                        double *__restrict__ stats) {
@@ -243,6 +491,17 @@ __global__ void pca_stats_final_kernel(const double *__restrict__ partial, int n
     double s = 0.0;
     for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * PCA_NSTAT + pe];
     stats[e] += s;
+}
+
+// BPK_PCA_VARIANT (A/B measurements, tools/bench_xsweep.py): -1 = the 8-warp v1 kernel,
+// 0..3 = tile/ring shapes of the warp-specialised kernel; default 0.
+static int pca_variant() {
+    static int v = -2;
+    if (v == -2) {
+        const char *e = getenv("BPK_PCA_VARIANT");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
 }
 
 template <int NT, int STAGES, bool COMPUTE_X>
@@ -260,6 +519,14 @@ static int pca_launch_partials(const double *Y, int64_t M, int64_t N, int K, con
     double *partial = bpk_scratch((size_t)grid * PCA_NSTAT * sizeof(double));
     if (!partial) return bpk_set_error(BPK_ECUDA, "pca: scratch allocation failed");
     bool al = (N % 2 == 0) && (((uintptr_t)Y & 15u) == 0);
+    if (al && pca_variant() >= 0) {
+        switch (pca_variant()) {
+        case 1: return pca_launch_ws<8, 6, 4, COMPUTE_X>(Y, M, N, K, A, b, X, stop, partial_out, nparts_out);
+        case 2: return pca_launch_ws<16, 2, 1, COMPUTE_X>(Y, M, N, K, A, b, X, stop, partial_out, nparts_out);
+        case 3: return pca_launch_ws<8, 4, 2, COMPUTE_X>(Y, M, N, K, A, b, X, stop, partial_out, nparts_out);
+        default: return pca_launch_ws<8, 5, 3, COMPUTE_X>(Y, M, N, K, A, b, X, stop, partial_out, nparts_out);
+        }
+    }
     if (al) {
         auto kern = pca_xsweep_kernel<NT, STAGES, true, COMPUTE_X>;
         BPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
