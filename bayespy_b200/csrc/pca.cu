@@ -23,6 +23,7 @@
 // partials are reduced warp->CTA in smem and CTA->grid by a second tiny
 // kernel in a fixed order (deterministic, no atomics).
 #include "common.cuh"
+#include <cuda.h>
 #include <stdlib.h>
 #include "pca_common.cuh"
 #include "spd.cuh"
@@ -232,18 +233,22 @@ pca_xsweep_kernel(const double *__restrict__ Y, int64_t M, int64_t N, int K,
 }
 
 // =====================================================================================
-// v2: warp-specialised sweep (aligned inputs).  16 warps per SM instead of 8:
+// v2: warp-specialised sweep fed by TMA (aligned inputs).  16 warps per SM instead of 8:
 //   X-warps 0..7  hold the A fragments, compute x = A y + b for their 1/8 of the tile's
 //                 columns on the fp64 tensor pipe, store x to HBM straight from the
 //                 accumulators, and hand the tile to their partner through shared memory;
 //   S-warps 8..15 hold the S_yx / S_xx accumulators and run the second contraction.
-// Each role fits 128 registers, so four warps per scheduler keep the DMMA pipe fed while
-// others wait on shared-memory loads or barriers (v1: two 220-register warps, 58% pipe
-// utilisation).  Y tiles arrive through a ring of padded shared-memory stages filled by
-// cp.async.bulk row copies (the TMA engine; one warp issues 64 copies per tile) that
-// complete on per-stage mbarriers; stages are released through "empty" mbarriers, and each
-// X/S warp pair hands x tiles over through its own double-buffered mbarrier pair, so there
-// is no CTA-wide barrier inside the main loop.
+// Each role fits 128 registers.  Y tiles (64 rows x T columns) arrive as T/16 TMA boxes of
+// 64 x 16 doubles (cp.async.bulk.tensor.2d, SWIZZLE_128B, zero fill out of bounds) that
+// complete on per-stage "full" mbarriers; stages are released through "empty" mbarriers and
+// each X/S warp pair hands x tiles over through its own double-buffered mbarrier pair — no
+// CTA-wide barrier inside the main loop.  The shared-memory image of a box is dense
+// (row pitch 128 B, 16-byte chunk index XOR row%8); the k-slot -> row map of the first
+// contraction (m = 8*(ms>>1) + 2*tg + (ms&1)) and the row map of the second
+// (m = 8*mb + 2*(gr&3) + (gr>>2)) are chosen so that every fragment load hits 32 distinct
+// banks per half-warp under that swizzle.
+// (A first version used 64 cp.async.bulk row copies of 512 B per tile into padded rows: it
+// was limited by the per-copy cost of the TMA unit, 2.8 ms; profiles/r01_*.)
 // =====================================================================================
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
@@ -261,25 +266,33 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
                  "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
                  "@P1 bra WAIT_DONE;\nbra WAIT_LOOP;\nWAIT_DONE:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tmap, int c0, int c1, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
+                 ::"r"(smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
 
 #define WS_PAIRS 8
+#define WS_BOXC 16                       // columns per TMA box (128 B: the SWIZZLE_128B span)
+#define WS_BOX (PCA_MP * WS_BOXC)        // doubles per box
+
+// offset (in doubles) of element (row m, column c) inside a stage of T/16 swizzled boxes
+__device__ __forceinline__ int ws_off(int m, int c) {
+    return (c >> 4) * WS_BOX + m * WS_BOXC + ((((c & 15) >> 1) ^ (m & 7)) << 1) + (c & 1);
+}
 
 template <int NT, int STAGES, int DIST, bool COMPUTE_X>
 __global__ void __launch_bounds__(2 * WS_PAIRS * 32, 1)
-pca_xsweep_ws_kernel(const double *__restrict__ Y, int64_t M, int64_t N, int K,
+pca_xsweep_ws_kernel(const __grid_constant__ CUtensorMap tmapY, int64_t M, int64_t N, int K,
                      const double *__restrict__ A, const double *__restrict__ bvec,
                      double *__restrict__ X, double *__restrict__ partial, int64_t ntiles,
                      const int *__restrict__ stop) {
-    constexpr int T = WS_PAIRS * NT, LDY = T + 4, NS = NT / 4, CB = NT / 8;
+    constexpr int T = WS_PAIRS * NT, NS = NT / 4, CB = NT / 8, NBOX = T / WS_BOXC, STG = NBOX * WS_BOX;
     static_assert(DIST >= 1 && DIST < STAGES, "prefetch distance must leave one stage for the consumers");
     if (stop && *stop) return;
-    extern __shared__ __align__(128) double smem[];
-    double *Ysm = smem;                                              // [STAGES][64][LDY]
-    double *Xsm = Ysm + (size_t)STAGES * PCA_MP * LDY;               // [PAIRS][2][NT][LDX]
+    extern __shared__ __align__(1024) double smem_ws[];
+    double *smem = smem_ws;
+    double *Ysm = smem;                                              // [STAGES][NBOX][64][16] swizzled
+    double *Xsm = Ysm + (size_t)STAGES * STG;                        // [PAIRS][2][NT][LDX]
     uint64_t *bars = (uint64_t *)(Xsm + (size_t)WS_PAIRS * 2 * NT * PCA_LDX);
     uint64_t *full = bars, *empty = bars + STAGES;
     uint64_t *xfull = bars + 2 * STAGES, *xfree = xfull + 2 * WS_PAIRS;   // [pair][2]
@@ -288,28 +301,25 @@ pca_xsweep_ws_kernel(const double *__restrict__ Y, int64_t M, int64_t N, int K,
     const bool is_x = w < WS_PAIRS;
     const int p = w & (WS_PAIRS - 1);
 
-    for (int e = threadIdx.x; e < STAGES * PCA_MP * LDY; e += blockDim.x) Ysm[e] = 0.0;
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 2 * WS_PAIRS); }
         for (int i = 0; i < 2 * WS_PAIRS; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xfree[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmapY) : "memory");
     }
-    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // zero fill (generic) before bulk writes (async proxy)
     __syncthreads();
 
     const int64_t first = blockIdx.x, stride = gridDim.x;
     const int64_t ntl = first < ntiles ? (ntiles - first + stride - 1) / stride : 0;   // tiles of this CTA
 
-    auto issue = [&](int64_t j) {        // whole warp 0: bulk-copy the rows of local tile j
+    auto issue = [&](int64_t j) {        // lanes 0..NBOX-1 of warp 0: one TMA box each
         const int slot = (int)(j % STAGES);
         if (j >= STAGES) mbar_wait(&empty[slot], (uint32_t)((j / STAGES - 1) & 1));
         const int64_t n0 = (first + j * stride) * T;
-        const int64_t rem = N - n0;
-        const uint32_t ncols = (uint32_t)(rem < T ? rem : T);
-        if (lane == 0) mbar_expect_tx(&full[slot], (uint32_t)M * ncols * 8u);
+        if (lane == 0) mbar_expect_tx(&full[slot], (uint32_t)(STG * sizeof(double)));
         __syncwarp();
-        double *dst = Ysm + (size_t)slot * PCA_MP * LDY;
-        for (int m = lane; m < (int)M; m += 32) bulk_g2s(dst + m * LDY, Y + (int64_t)m * N + n0, ncols * 8u, &full[slot]);
+        if (lane < NBOX)
+            tma_load_2d(Ysm + (size_t)slot * STG + lane * WS_BOX, &tmapY, (int)(n0 + lane * WS_BOXC), 0, &full[slot]);
     };
 
     if (is_x) {
@@ -320,7 +330,7 @@ pca_xsweep_ws_kernel(const double *__restrict__ Y, int64_t M, int64_t N, int K,
             for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
                 for (int ms = 0; ms < 16; ++ms) {
-                    int k = kb * 8 + gr, m = ms * 4 + tg;
+                    int k = kb * 8 + gr, m = (ms >> 1) * 8 + 2 * tg + (ms & 1);
                     afrag[kb][ms] = (k < K && m < M) ? A[(int64_t)k * M + m] : 0.0;
                 }
             if (bvec) {
@@ -338,7 +348,7 @@ pca_xsweep_ws_kernel(const double *__restrict__ Y, int64_t M, int64_t N, int K,
             double *Xs = Xsm + ((size_t)(p * 2 + b) * NT) * PCA_LDX;
             if (COMPUTE_X) {
                 mbar_wait(&full[slot], (uint32_t)((i / STAGES) & 1));
-                const double *Ys = Ysm + (size_t)slot * PCA_MP * LDY;
+                const double *Ys = Ysm + (size_t)slot * STG;
                 // two partial sums over the m blocks per accumulator: 4*CB independent DMMA chains
                 double acc[2][2][CB][2];
 #pragma unroll
@@ -352,7 +362,7 @@ pca_xsweep_ws_kernel(const double *__restrict__ Y, int64_t M, int64_t N, int K,
                 for (int ms = 0; ms < 16; ++ms) {
 #pragma unroll
                     for (int cb = 0; cb < CB; ++cb) {
-                        double yb = Ys[(ms * 4 + tg) * LDY + c0 + cb * 8 + gr];
+                        double yb = Ys[ws_off((ms >> 1) * 8 + 2 * tg + (ms & 1), c0 + cb * 8 + gr)];
                         dmma884(acc[ms & 1][0][cb][0], acc[ms & 1][0][cb][1], afrag[0][ms], yb);
                         dmma884(acc[ms & 1][1][cb][0], acc[ms & 1][1][cb][1], afrag[1][ms], yb);
                     }
@@ -387,6 +397,7 @@ pca_xsweep_ws_kernel(const double *__restrict__ Y, int64_t M, int64_t N, int K,
             if (lane == 0) mbar_arrive(&xfull[p * 2 + b]);
         }
     } else {
+        const int rr = 2 * (gr & 3) + (gr >> 2);      // S_yx row within an 8-row block held by this lane group
         double syx[8][2][2];
         double sxx[3][2];
         double sx = 0.0;
@@ -399,7 +410,7 @@ pca_xsweep_ws_kernel(const double *__restrict__ Y, int64_t M, int64_t N, int K,
         for (int64_t i = 0; i < ntl; ++i) {
             const int slot = (int)(i % STAGES), b = (int)(i & 1);
             const int c0 = p * NT;
-            const double *Ys = Ysm + (size_t)slot * PCA_MP * LDY;
+            const double *Ys = Ysm + (size_t)slot * STG;
             const double *Xs = Xsm + ((size_t)(p * 2 + b) * NT) * PCA_LDX;
             mbar_wait(&full[slot], (uint32_t)((i / STAGES) & 1));
             mbar_wait(&xfull[p * 2 + b], (uint32_t)((i >> 1) & 1));
@@ -413,7 +424,7 @@ pca_xsweep_ws_kernel(const double *__restrict__ Y, int64_t M, int64_t N, int K,
                 double xf1 = Xs[(ns * 4 + tg) * PCA_LDX + 8 + gr];
 #pragma unroll
                 for (int mb = 0; mb < 8; ++mb) {
-                    double ya = Ys[(mb * 8 + gr) * LDY + c0 + ns * 4 + tg];
+                    double ya = Ys[ws_off(mb * 8 + rr, c0 + ns * 4 + tg)];
                     dmma884(syx[mb][0][0], syx[mb][0][1], ya, xf0);
                     dmma884(syx[mb][1][0], syx[mb][1][1], ya, xf1);
                 }
@@ -433,7 +444,7 @@ pca_xsweep_ws_kernel(const double *__restrict__ Y, int64_t M, int64_t N, int K,
             for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
                 for (int j = 0; j < 2; ++j)
-                    mine[(mb * 8 + gr) * PCA_KP + kb * 8 + 2 * tg + j] = syx[mb][kb][j];
+                    mine[(mb * 8 + rr) * PCA_KP + kb * 8 + 2 * tg + j] = syx[mb][kb][j];
         double *mxx = mine + PCA_MP * PCA_KP;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
@@ -455,11 +466,38 @@ pca_xsweep_ws_kernel(const double *__restrict__ Y, int64_t M, int64_t N, int K,
     }
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link dependency)
+typedef CUresult (*bpk_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                         const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                         CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                         CUtensorMapFloatOOBfill);
+static int pca_make_tmap(const double *Y, int64_t M, int64_t N, CUtensorMap *out) {
+    static bpk_encode_tiled_fn enc = nullptr;
+    if (!enc) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+        if (e != cudaSuccess || !fn || q != cudaDriverEntryPointSuccess)
+            return bpk_set_error(BPK_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+        enc = (bpk_encode_tiled_fn)fn;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
+    cuuint64_t strides[1] = {(cuuint64_t)N * sizeof(double)};
+    cuuint32_t box[2] = {WS_BOXC, PCA_MP};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)Y, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return bpk_set_error(BPK_ECUDA, "cuTensorMapEncodeTiled failed (%d) for Y[%lld][%lld]", (int)r,
+                                                (long long)M, (long long)N);
+    return BPK_OK;
+}
+
 template <int NT, int STAGES, int DIST, bool COMPUTE_X>
 static int pca_launch_ws(const double *Y, int64_t M, int64_t N, int K, const double *A, const double *b,
                          double *X, const int *stop, double **partial_out, int *nparts_out) {
-    constexpr int T = WS_PAIRS * NT, LDY = T + 4;
-    size_t ring = (size_t)STAGES * PCA_MP * LDY * sizeof(double);
+    constexpr int T = WS_PAIRS * NT;
+    size_t ring = (size_t)STAGES * (T / WS_BOXC) * WS_BOX * sizeof(double);
     size_t xs = (size_t)WS_PAIRS * 2 * NT * PCA_LDX * sizeof(double);
     size_t bars = (size_t)(2 * STAGES + 4 * WS_PAIRS) * sizeof(uint64_t);
     size_t redb = (size_t)WS_PAIRS * PCA_NSTAT * sizeof(double);
@@ -470,9 +508,12 @@ static int pca_launch_ws(const double *Y, int64_t M, int64_t N, int K, const dou
     if (ntiles < grid) grid = (int)ntiles;
     double *partial = bpk_scratch((size_t)grid * PCA_NSTAT * sizeof(double));
     if (!partial) return bpk_set_error(BPK_ECUDA, "pca: scratch allocation failed");
+    CUtensorMap tmap;
+    int rc = pca_make_tmap(Y, M, N, &tmap);
+    if (rc) return rc;
     auto kern = pca_xsweep_ws_kernel<NT, STAGES, DIST, COMPUTE_X>;
     BPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    BPK_LAUNCH(kern, grid, 2 * WS_PAIRS * 32, smem, Y, M, N, K, A, b, X, partial, ntiles, stop);
+    BPK_LAUNCH(kern, grid, 2 * WS_PAIRS * 32, smem, tmap, M, N, K, A, b, X, partial, ntiles, stop);
     *partial_out = partial;
     *nparts_out = grid;
     return BPK_OK;
