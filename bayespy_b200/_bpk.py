@@ -58,6 +58,9 @@ PROTOTYPES = {
     "bpk_allreduce_sum_f64": (C.c_int, [_dp, C.c_uint64]),
     "bpk_allreduce_sum_f64_oop": (C.c_int, [_dp, _dp, C.c_uint64]),
     "bpk_comm_destroy": (C.c_int, []),
+    "bpk_xchg_create": (C.c_int, [C.c_char_p]),
+    "bpk_xchg_open": (C.c_int, [C.c_char_p, C.c_int, C.c_int]),
+    "bpk_xchg_close": (C.c_int, []),
     "bpk_ewise": (C.c_int, [C.c_int, C.c_int, _i64p, _dp, _i64p, C.c_int, C.POINTER(C.c_void_p), _ip, _i64p,
                             C.c_double, C.c_double]),
     "bpk_sum_multiply": (C.c_int, [C.c_int, _i64p, C.c_int, C.POINTER(C.c_void_p), _ip, _i64p, _dp, _i64p,
@@ -87,6 +90,7 @@ PROTOTYPES = {
                                  C.c_int, C.c_double, _dp, C.c_int, _vp]),
     "bpk_pca_vb_set_timers": (C.c_int, [_ip, C.c_int]),
     "bpk_pca_vb_timers_used": (C.c_int, []),
+    "bpk_debug_stamps": (C.c_int, [C.POINTER(C.c_uint64), C.c_int]),
 }
 
 # opcodes of bpk_pca_vb_run (include/bpk.h)
@@ -224,6 +228,19 @@ class CudaBackend:
     def comm_destroy(self):
         self._chk(self.lib.bpk_comm_destroy())
 
+    def xchg_create(self):
+        buf = C.create_string_buffer(64)
+        self._chk(self.lib.bpk_xchg_create(buf))
+        return buf.raw
+
+    def xchg_open(self, handles, nranks, rank):
+        blob = b"".join(handles)
+        assert len(blob) == 64 * nranks
+        self._chk(self.lib.bpk_xchg_open(C.create_string_buffer(blob, len(blob)), nranks, rank))
+
+    def xchg_close(self):
+        self._chk(self.lib.bpk_xchg_close())
+
     # -- generic kernels
     def ewise(self, op, shape, out, out_stride, ins, dtypes, in_strides, alpha=0.0, beta=0.0):
         nd, n_in = len(shape), len(ins)
@@ -317,6 +334,11 @@ class CudaBackend:
 
     def pca_vb_timers_used(self):
         return int(self.lib.bpk_pca_vb_timers_used())
+
+    def debug_stamps(self, n=32):
+        out = (C.c_uint64 * n)()
+        self._chk(self.lib.bpk_debug_stamps(out, n))
+        return [int(v) for v in out]
 
 
 _backend = None

@@ -24,6 +24,23 @@ struct BpkCtx {
 
 extern BpkCtx g_bpk;
 
+// peer-memory exchange window (runtime.cu); layout in doubles:
+//   [0]                      exchanges completed by this rank (written by its own kernels)
+//   [8 + par*R + r]          flag: sequence number of rank r's latest deposit with parity par
+//   [64 + (par*R + r)*CAP..] rank r's deposit (CAP doubles), R = BPK_XCHG_MAXRANKS
+#define BPK_XCHG_MAXRANKS 8
+#define BPK_XCHG_CAP 2048
+#define BPK_XCHG_FLAGS 8
+#define BPK_XCHG_DATA 64
+#define BPK_XCHG_BYTES ((BPK_XCHG_DATA + 2 * BPK_XCHG_MAXRANKS * BPK_XCHG_CAP) * sizeof(double))
+struct BpkXchg {
+    bool ready = false;
+    int nranks = 1, rank = 0;
+    double *own = nullptr;
+    double *win[BPK_XCHG_MAXRANKS] = {nullptr};
+};
+extern BpkXchg g_xchg;
+
 int bpk_set_error(int code, const char *fmt, ...);
 int bpk_check_flag(int what_if_set);    // sync + read d_flag, clear it
 double *bpk_scratch(size_t bytes);      // stream-ordered scratch (grown on demand)

@@ -27,6 +27,7 @@
 #include <stdlib.h>
 #include "pca_common.cuh"
 #include "spd.cuh"
+#include "pca_vb_ops.cuh"
 
 #define PCA_WARPS 8
 #define PCA_LDX 20     // pitch of the per-warp X staging tile
@@ -280,15 +281,40 @@ __device__ __forceinline__ int ws_off(int m, int c) {
     return (c >> 4) * WS_BOX + m * WS_BOXC + ((((c & 15) >> 1) ^ (m & 7)) << 1) + (c & 1);
 }
 
-template <int NT, int STAGES, int DIST, bool COMPUTE_X>
+// Self-resetting grid barrier (all CTAs are co-resident: one persistent CTA per SM).
+// bar[0] = arrival count, bar[1] = epoch.
+__device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int &epoch) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int target = epoch + 1;
+        if (atomicAdd(&bar[0], 1u) == gridDim.x - 1) {
+            atomicExch(&bar[0], 0u);
+            __threadfence();
+            atomicExch(&bar[1], target);
+        } else {
+            while (*(volatile unsigned int *)&bar[1] != target) { __nanosleep(32); }
+        }
+        __threadfence();
+    }
+    epoch += 1;
+    __syncthreads();
+}
+
+// FUSED: the launch is one whole VB sweep of the resident loop — after the data pass the grid
+// reduces its partial statistics in place (two grid barriers, fixed order) and CTA 0 runs the
+// sweep's small ops (pca_vb_ops: STATS .. BOUND, XPRE of the next sweep) before the kernel ends.
+template <int NT, int STAGES, int DIST, bool COMPUTE_X, bool FUSED>
 __global__ void __launch_bounds__(2 * WS_PAIRS * 32, 1)
 pca_xsweep_ws_kernel(const __grid_constant__ CUtensorMap tmapY, int64_t M, int64_t N, int K,
                      const double *__restrict__ A, const double *__restrict__ bvec,
                      double *__restrict__ X, double *__restrict__ partial, int64_t ntiles,
-                     const int *__restrict__ stop) {
+                     const int *__restrict__ stop, unsigned int *gbar, const __grid_constant__ PcaVbArgs vb,
+                     size_t vb_sm_doubles) {
     constexpr int T = WS_PAIRS * NT, NS = NT / 4, CB = NT / 8, NBOX = T / WS_BOXC, STG = NBOX * WS_BOX;
     static_assert(DIST >= 1 && DIST < STAGES, "prefetch distance must leave one stage for the consumers");
     if (stop && *stop) return;
+    if (FUSED && blockIdx.x == 0) vb_stamp(vb.dbg, 0);
     extern __shared__ __align__(1024) double smem_ws[];
     double *smem = smem_ws;
     double *Ysm = smem;                                              // [STAGES][NBOX][64][16] swizzled
@@ -464,9 +490,39 @@ pca_xsweep_ws_kernel(const __grid_constant__ CUtensorMap tmapY, int64_t M, int64
         for (int ww = 0; ww < WS_PAIRS; ++ww) s += smem[(size_t)ww * PCA_NSTAT + e];
         pout[e] = s;
     }
+    if (FUSED) {
+        if (blockIdx.x == 0) vb_stamp(vb.dbg, 1);
+        unsigned int epoch = 0;
+        if (threadIdx.x == 0) epoch = *(volatile unsigned int *)&gbar[1];
+        epoch = __shfl_sync(0xffffffffu, epoch, 0);      // thread 0's value is the only one used
+        grid_barrier(gbar, epoch);
+        if (blockIdx.x == 0) vb_stamp(vb.dbg, 2);
+        // distributed, fixed-order reduction over the CTAs: CTA c owns elements [c*per, (c+1)*per)
+        double *fin = partial + (size_t)gridDim.x * PCA_NSTAT;
+        const int per = (PCA_NSTAT + gridDim.x - 1) / gridDim.x;
+        const int e0 = blockIdx.x * per;
+        for (int ee = w; ee < per; ee += 2 * WS_PAIRS) {
+            const int e = e0 + ee;
+            if (e < PCA_NSTAT) {
+                double s = 0.0;
+                for (int bb = lane; bb < (int)gridDim.x; bb += 32) s += __ldcg(partial + (size_t)bb * PCA_NSTAT + e);
+                s = warp_sum(s);
+                if (lane == 0) fin[e] = s;
+            }
+        }
+        if (blockIdx.x == 0) vb_stamp(vb.dbg, 3);
+        grid_barrier(gbar, epoch);
+        if (blockIdx.x == 0) {
+            vb_stamp(vb.dbg, 4);
+            pca_vb_ops(vb, smem, vb_sm_doubles);
+            vb_stamp(vb.dbg, 5);
+        }
+    }
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link dependency)
+static unsigned int *g_pca_gbar = nullptr;     // grid barrier of the fused sweep (count, epoch)
+
 typedef CUresult (*bpk_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                          const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
                                          CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -495,7 +551,8 @@ static int pca_make_tmap(const double *Y, int64_t M, int64_t N, CUtensorMap *out
 
 template <int NT, int STAGES, int DIST, bool COMPUTE_X>
 static int pca_launch_ws(const double *Y, int64_t M, int64_t N, int K, const double *A, const double *b,
-                         double *X, const int *stop, double **partial_out, int *nparts_out) {
+                         double *X, const int *stop, double **partial_out, int *nparts_out,
+                         const PcaVbArgs *tail = nullptr) {
     constexpr int T = WS_PAIRS * NT;
     size_t ring = (size_t)STAGES * (T / WS_BOXC) * WS_BOX * sizeof(double);
     size_t xs = (size_t)WS_PAIRS * 2 * NT * PCA_LDX * sizeof(double);
@@ -506,14 +563,32 @@ static int pca_launch_ws(const double *Y, int64_t M, int64_t N, int K, const dou
     int64_t ntiles = (N + T - 1) / T;
     int grid = g_bpk.sm_count;
     if (ntiles < grid) grid = (int)ntiles;
-    double *partial = bpk_scratch((size_t)grid * PCA_NSTAT * sizeof(double));
+    double *partial = bpk_scratch((size_t)(grid + 1) * PCA_NSTAT * sizeof(double));
     if (!partial) return bpk_set_error(BPK_ECUDA, "pca: scratch allocation failed");
     CUtensorMap tmap;
     int rc = pca_make_tmap(Y, M, N, &tmap);
     if (rc) return rc;
-    auto kern = pca_xsweep_ws_kernel<NT, STAGES, DIST, COMPUTE_X>;
+    if (tail && COMPUTE_X) {
+        // one launch = data pass + grid reduction + the sweep's small ops
+        if (!g_pca_gbar) {
+            BPK_CUDA(cudaMalloc(&g_pca_gbar, 2 * sizeof(unsigned int)));
+            BPK_CUDA(cudaMemsetAsync(g_pca_gbar, 0, 2 * sizeof(unsigned int), g_bpk.stream));
+        }
+        PcaVbArgs vb = *tail;
+        vb.partial = partial + (size_t)grid * PCA_NSTAT;     // the grid-reduced statistics
+        vb.nparts = 1;
+        auto kern = pca_xsweep_ws_kernel<NT, STAGES, DIST, true, true>;
+        BPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        BPK_LAUNCH(kern, grid, 2 * WS_PAIRS * 32, smem, tmap, M, N, K, A, b, X, partial, ntiles, stop, g_pca_gbar, vb, smem / sizeof(double));
+        *partial_out = partial + (size_t)grid * PCA_NSTAT;
+        *nparts_out = 1;
+        return BPK_OK;
+    }
+    PcaVbArgs none;
+    none.nops = 0;
+    auto kern = pca_xsweep_ws_kernel<NT, STAGES, DIST, COMPUTE_X, false>;
     BPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    BPK_LAUNCH(kern, grid, 2 * WS_PAIRS * 32, smem, tmap, M, N, K, A, b, X, partial, ntiles, stop);
+    BPK_LAUNCH(kern, grid, 2 * WS_PAIRS * 32, smem, tmap, M, N, K, A, b, X, partial, ntiles, stop, (unsigned int *)nullptr, none, (size_t)0);
     *partial_out = partial;
     *nparts_out = grid;
     return BPK_OK;
@@ -547,7 +622,8 @@ static int pca_variant() {
 
 template <int NT, int STAGES, bool COMPUTE_X>
 static int pca_launch_partials(const double *Y, int64_t M, int64_t N, int K, const double *A, const double *b,
-                               double *X, const int *stop, double **partial_out, int *nparts_out) {
+                               double *X, const int *stop, double **partial_out, int *nparts_out,
+                               const PcaVbArgs *tail = nullptr, int *tail_done = nullptr) {
     constexpr int T = PCA_WARPS * NT, LDY = T + 4;
     size_t ring = (size_t)STAGES * PCA_MP * LDY * sizeof(double);
     size_t xs = (size_t)PCA_WARPS * NT * PCA_LDX * sizeof(double);
@@ -561,11 +637,12 @@ static int pca_launch_partials(const double *Y, int64_t M, int64_t N, int K, con
     if (!partial) return bpk_set_error(BPK_ECUDA, "pca: scratch allocation failed");
     bool al = (N % 2 == 0) && (((uintptr_t)Y & 15u) == 0);
     if (al && pca_variant() >= 0) {
+        if (tail_done) *tail_done = (tail != nullptr && COMPUTE_X);
         switch (pca_variant()) {
-        case 1: return pca_launch_ws<8, 6, 4, COMPUTE_X>(Y, M, N, K, A, b, X, stop, partial_out, nparts_out);
-        case 2: return pca_launch_ws<16, 2, 1, COMPUTE_X>(Y, M, N, K, A, b, X, stop, partial_out, nparts_out);
-        case 3: return pca_launch_ws<8, 4, 2, COMPUTE_X>(Y, M, N, K, A, b, X, stop, partial_out, nparts_out);
-        default: return pca_launch_ws<8, 5, 3, COMPUTE_X>(Y, M, N, K, A, b, X, stop, partial_out, nparts_out);
+        case 1: return pca_launch_ws<8, 6, 4, COMPUTE_X>(Y, M, N, K, A, b, X, stop, partial_out, nparts_out, tail);
+        case 2: return pca_launch_ws<16, 2, 1, COMPUTE_X>(Y, M, N, K, A, b, X, stop, partial_out, nparts_out, tail);
+        case 3: return pca_launch_ws<8, 4, 2, COMPUTE_X>(Y, M, N, K, A, b, X, stop, partial_out, nparts_out, tail);
+        default: return pca_launch_ws<8, 5, 3, COMPUTE_X>(Y, M, N, K, A, b, X, stop, partial_out, nparts_out, tail);
         }
     }
     if (al) {
@@ -596,8 +673,10 @@ static int pca_launch(const double *Y, int64_t M, int64_t N, int K, const double
 
 // resident VB loop (pca_vb.cu): sweep only, per-CTA partials left in scratch
 int pca_xsweep_partials(const double *Y, int64_t M, int64_t N, int K, const double *A, const double *b,
-                        double *X, const int *stop, double **partial_out, int *nparts_out) {
-    return pca_launch_partials<16, 2, true>(Y, M, N, K, A, b, X, stop, partial_out, nparts_out);
+                        double *X, const int *stop, double **partial_out, int *nparts_out,
+                        const PcaVbArgs *tail, int *tail_done) {
+    if (tail_done) *tail_done = 0;
+    return pca_launch_partials<16, 2, true>(Y, M, N, K, A, b, X, stop, partial_out, nparts_out, tail, tail_done);
 }
 
 // ---- generic shapes (M > 64 or K > 16): plain kernels, not roofline-tuned -----------

@@ -1,0 +1,388 @@
+// pca_vb_ops.cuh — state layout, opcodes and the single-CTA "small ops" of the device-resident PCA VB loop.
+// Included by pca_vb.cu (standalone small kernel, driver) and pca.cu (tail of the fused sweep kernel).
+#pragma once
+#include "common.cuh"
+#include "pca_common.cuh"
+#include "spd.cuh"
+
+#define VB_THREADS 256      // block size of the standalone small kernel
+#define VB_MAXOPS 24
+#define LOG2PI_D 1.8378770664093454835606594728112
+
+enum {
+    F_MUX = 0, F_AX, F_MUC, F_A0, F_B0, F_TA0, F_TB0, F_SUMSQ, F_NG, F_RESERVED,
+    F_W, F_SWW, F_COVC, F_LAMC, F_LOGDETC, F_PHI0C, F_GC,
+    F_AL_PHI0, F_AL_PHI1, F_AL_U0, F_AL_U1, F_AL_G,
+    F_TAU_PHI0, F_TAU_PHI1, F_TAU_U0, F_TAU_U1, F_TAU_G,
+    F_COVX, F_LAMX, F_LOGDETX, F_A, F_BX,
+    F_STATS, F_SXXT, F_LPREV, F_STATS_LOCAL,
+    F_COUNT
+};
+
+__attribute__((unused)) static const char *const kFieldNames[F_COUNT] = {
+    "mux", "ax", "muc", "a0", "b0", "ta0", "tb0", "sumsq", "ng", "reserved",
+    "w", "sww", "covc", "lamc", "logdetc", "phi0c", "gc",
+    "al_phi0", "al_phi1", "al_u0", "al_u1", "al_g",
+    "tau_phi0", "tau_phi1", "tau_u0", "tau_u1", "tau_g",
+    "covx", "lamx", "logdetx", "A", "bx",
+    "stats", "sxxt", "lprev", "stats_local",
+};
+
+__device__ __forceinline__ void vb_stamp(unsigned long long *dbg, int slot) {
+    if (dbg && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        dbg[slot] = t;
+    }
+}
+
+__host__ __device__ inline void pca_vb_offsets(int M, int K, int64_t *off /* [F_COUNT+1] */) {
+    const int64_t KK = (int64_t)K * K, MK = (int64_t)M * K, NS = MK + KK + K;
+    const int64_t size[F_COUNT] = {
+        K, K, K, K, K, 1, 1, 1, 1, 1,
+        MK, KK, KK, KK, 1, MK, M,
+        K, K, K, K, K,
+        1, 1, 1, 1, 1,
+        KK, KK, 1, MK, K,
+        NS, KK, 1, NS,
+    };
+    int64_t o = 0;
+    for (int f = 0; f < F_COUNT; ++f) { off[f] = o; o += size[f]; }
+    off[F_COUNT] = o;
+}
+
+// SPD scratch (two K x K tiles, a K x 32 solve tile, reduction slots) in doubles
+__host__ __device__ inline size_t pca_vb_smem_doubles(int K) { return (size_t)2 * K * SPD_LD(K) + (size_t)K * 32 + 48; }
+
+struct PcaVbArgs {
+    int M, K, has_alpha, has_tau;
+    double tol;
+    double *st;
+    const double *partial;   // per-CTA partials of the preceding sweep kernel (padded layout) or NULL
+    int nparts;
+    int local_stats;         // 1: STATS writes F_STATS_LOCAL (an all-reduce into F_STATS follows)
+    double *Lhist;           // [cap][6]: Y, X, C, alpha, tau, total
+    int cap;
+    int *ctrl;               // [0] iterations finished, [1] stop, [2] error bits (1 not SPD, 2 domain, 4 exchange timeout)
+    unsigned long long *dbg; // optional %globaltimer stamps (tools/vb_tail_timing.py), NULL in production
+    int xranks, xrank;       // > 1: STATS all-reduces over the peer-memory windows below (no NCCL call)
+    double *xwin[BPK_XCHG_MAXRANKS];
+    int nops;
+    int ops[VB_MAXOPS];
+};
+
+__device__ __forceinline__ double vb_block_sum(double v, double *red) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+    const int nw = blockDim.x >> 5;
+    for (int w = 0; w < nw; ++w) s += red[w];
+    return s;
+}
+
+// S filled by the whole CTA -> warp 0 factors and inverts it into C; scal[0] = log det
+__device__ __forceinline__ void vb_spd_inverse(double *S, double *B, double *C, int K, int ld, double *scal, int *ctrl) {
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        int bad = spd_warp_chol_upper(S, K, ld, lane);
+        double ldt = spd_warp_logdet(S, K, ld, lane);
+        spd_warp_inverse(S, B, C, K, ld, lane);
+        if (lane == 0) {
+            scal[0] = ldt;
+            if (bad) atomicOr(&ctrl[2], BPK_FLAG_NOTSPD);
+        }
+    }
+    __syncthreads();
+}
+
+// gamma.py:124-148: a = phi1, b = -phi0
+__device__ __forceinline__ void vb_gamma(double phi0, double phi1, double &u0, double &u1, double &g, int *ctrl) {
+    double a = phi1, b = -phi0;
+    if (!(a > 0.0) || !(b > 0.0)) atomicOr(&ctrl[2], BPK_FLAG_DOMAIN);
+    double lb = log(b);
+    u0 = a / b;
+    u1 = bpk_digamma(a) - lb;
+    g = a * lb - lgamma(a);
+}
+
+// sum_mn <(y - f)^2> = sum y^2 - 2 <W>:S_yx + tr(sum_m<ww^T> sum_n<xx^T>)   (dot.py:355,403 summed)
+__device__ __forceinline__ double vb_E2(const double *st, const int64_t *o, int M, int K, double *red) {
+    const double *W = st + o[F_W], *Syx = st + o[F_STATS], *SWW = st + o[F_SWW], *SXXT = st + o[F_SXXT];
+    double a = 0.0, b = 0.0;
+    for (int e = threadIdx.x; e < M * K; e += blockDim.x) a += W[e] * Syx[e];
+    for (int e = threadIdx.x; e < K * K; e += blockDim.x) b += SWW[e] * SXXT[e];
+    return st[o[F_SUMSQ]] + vb_block_sum(b - 2.0 * a, red);
+}
+
+// One run of small ops by ONE CTA (any multiple of 32 threads up to 1024).  sm: scratch of
+// pca_vb_smem_doubles(K) doubles in shared memory.
+// sm_doubles: size of that scratch; when the whole state vector fits behind the SPD scratch it is
+// staged in shared memory for the duration of the ops (every dependent step then costs a
+// shared-memory round trip instead of an L2 one) and written back at the end.
+static __device__ __noinline__ void pca_vb_ops(const PcaVbArgs &p, double *sm, size_t sm_doubles) {
+    const int VBT = blockDim.x;
+    const int M = p.M, K = p.K, ld = SPD_LD(K), t = threadIdx.x;
+    double *S = sm, *C = S + (size_t)K * ld, *B = C + (size_t)K * ld, *red = B + (size_t)K * 32, *scal = red + 32;
+    __shared__ int64_t o[F_COUNT + 1];
+    if (t == 0) pca_vb_offsets(M, K, o);
+    __syncthreads();
+    double *st = p.st;
+    const int64_t nstate = o[F_COUNT];
+    const bool staged = pca_vb_smem_doubles(K) + (size_t)nstate <= sm_doubles;
+    if (staged) {
+        st = sm + pca_vb_smem_doubles(K);
+        for (int64_t e = t; e < nstate; e += VBT) st[e] = __ldcg(p.st + e);
+        __syncthreads();
+    }
+    volatile int *stop = p.ctrl + 1;
+    const double Ng = st[o[F_NG]];
+
+    for (int ip = 0; ip < p.nops; ++ip) {
+        __syncthreads();
+        if (*stop) break;
+        const int op = p.ops[ip];
+        vb_stamp(p.dbg, 8 + ip);
+        if (op == BPK_VBOP_STATS) {
+            // fixed-order grid reduction of the sweep kernel's per-CTA partials
+            const bool xch = p.xranks > 1;
+            double *dst = st + ((p.local_stats || xch) ? o[F_STATS_LOCAL] : o[F_STATS]);
+            const int total = M * K + K * K + K;
+            if (p.partial) {
+                for (int e = t; e < total; e += VBT) {
+                    int pe;
+                    if (e < M * K) { int m = e / K, k = e - m * K; pe = m * PCA_KP + k; }
+                    else if (e < M * K + K * K) { int r = e - M * K; int i = r / K, j = r - i * K; pe = PCA_MP * PCA_KP + i * PCA_KP + j; }
+                    else pe = PCA_MP * PCA_KP + PCA_KP * PCA_KP + (e - M * K - K * K);
+                    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                    int b = 0;
+                    for (; b + 3 < p.nparts; b += 4) {
+                        s0 += p.partial[(size_t)b * PCA_NSTAT + pe];
+                        s1 += p.partial[(size_t)(b + 1) * PCA_NSTAT + pe];
+                        s2 += p.partial[(size_t)(b + 2) * PCA_NSTAT + pe];
+                        s3 += p.partial[(size_t)(b + 3) * PCA_NSTAT + pe];
+                    }
+                    for (; b < p.nparts; ++b) s0 += p.partial[(size_t)b * PCA_NSTAT + pe];
+                    dst[e] = (s0 + s1) + (s2 + s3);
+                }
+            }
+            if (xch) {
+                // the sweep's one exchange, in this kernel: deposit into every rank's window over NVLink,
+                // raise a sequence flag, wait for everybody's flag, add up in rank order (bit-identical
+                // on every rank).  Two parities of slots: a rank cannot get more than one exchange ahead
+                // of a peer, because it needs that peer's flag to finish the one in between.
+                __syncthreads();
+                double *own = p.xwin[p.xrank];
+                const unsigned long long seq = *(volatile unsigned long long *)own + 1ull;
+                const int par = (int)(seq & 1ull);
+                for (int r = 0; r < p.xranks; ++r) {
+                    double *slot = p.xwin[r] + BPK_XCHG_DATA + (size_t)(par * BPK_XCHG_MAXRANKS + p.xrank) * BPK_XCHG_CAP;
+                    for (int e = t; e < total; e += VBT) slot[e] = dst[e];
+                }
+                __threadfence_system();
+                __syncthreads();
+                if (t < p.xranks) {
+                    unsigned long long *f = (unsigned long long *)(p.xwin[t] + BPK_XCHG_FLAGS) + par * BPK_XCHG_MAXRANKS + p.xrank;
+                    asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(f), "l"(seq) : "memory");
+                    const unsigned long long *g = (const unsigned long long *)(own + BPK_XCHG_FLAGS) + par * BPK_XCHG_MAXRANKS + t;
+                    const long long t0 = clock64();
+                    unsigned long long v;
+                    do {
+                        asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(g) : "memory");
+                        if (v < seq && clock64() - t0 > 6000000000ll) { atomicOr(&p.ctrl[2], 4); break; }   // ~3 s: a peer died
+                    } while (v < seq);
+                }
+                __syncthreads();
+                for (int e = t; e < total; e += VBT) {
+                    double s = 0.0;
+                    for (int r = 0; r < p.xranks; ++r)
+                        s += __ldcv(own + BPK_XCHG_DATA + (size_t)(par * BPK_XCHG_MAXRANKS + r) * BPK_XCHG_CAP + e);
+                    st[o[F_STATS] + e] = s;
+                }
+                __syncthreads();
+                if (t == 0) *(volatile unsigned long long *)own = seq;
+            }
+        } else if (op == BPK_VBOP_SXXT) {
+            // sum_n <x x^T> = N Cov_x + S_xx
+            for (int e = t; e < K * K; e += VBT)
+                st[o[F_SXXT] + e] = Ng * st[o[F_COVX] + e] + st[o[F_STATS] + M * K + e];
+        } else if (op == BPK_VBOP_XPRE) {
+            // q(X) shared part: Lam_x = diag(a_x) + tau sum_m<ww^T>; x_n = Cov_x (a_x mu_x + tau W^T y_n)
+            const double tau = st[o[F_TAU_U0]];
+            for (int e = t; e < K * K; e += VBT) {
+                int i = e / K, j = e - i * K;
+                double lam = tau * st[o[F_SWW] + e] + (i == j ? st[o[F_AX] + i] : 0.0);
+                S[i * ld + j] = lam;
+                st[o[F_LAMX] + e] = lam;
+            }
+            vb_spd_inverse(S, B, C, K, ld, scal, p.ctrl);
+            for (int e = t; e < K * K; e += VBT) st[o[F_COVX] + e] = C[(e / K) * ld + (e % K)];
+            if (t == 0) st[o[F_LOGDETX]] = scal[0];
+            for (int k = t; k < K; k += VBT) {
+                double s = 0.0;
+                for (int j = 0; j < K; ++j) s += C[k * ld + j] * (st[o[F_AX] + j] * st[o[F_MUX] + j]);
+                st[o[F_BX] + k] = s;
+            }
+            for (int e = t; e < K * M; e += VBT) {
+                int k = e / M, m = e - k * M;
+                double s = 0.0;
+                for (int j = 0; j < K; ++j) s += C[k * ld + j] * st[o[F_W] + m * K + j];
+                st[o[F_A] + e] = tau * s;
+            }
+        } else if (op == BPK_VBOP_ROW) {
+            // q(C): Lam_c = diag<alpha> + tau sum_n<xx^T> (shared by all rows); phi0_m = <alpha> mu_c + tau S_yx[m]
+            const double tau = st[o[F_TAU_U0]];
+            for (int e = t; e < K * K; e += VBT) {
+                int i = e / K, j = e - i * K;
+                double lam = tau * st[o[F_SXXT] + e] + (i == j ? st[o[F_AL_U0] + i] : 0.0);
+                S[i * ld + j] = lam;
+                st[o[F_LAMC] + e] = lam;
+            }
+            vb_spd_inverse(S, B, C, K, ld, scal, p.ctrl);
+            for (int e = t; e < K * K; e += VBT) st[o[F_COVC] + e] = C[(e / K) * ld + (e % K)];
+            if (t == 0) st[o[F_LOGDETC]] = scal[0];
+            for (int e = t; e < M * K; e += VBT) {
+                int k = e % K;
+                st[o[F_PHI0C] + e] = st[o[F_AL_U0] + k] * st[o[F_MUC] + k] + tau * st[o[F_STATS] + e];
+            }
+            __syncthreads();
+            for (int e = t; e < M * K; e += VBT) {
+                int m = e / K, i = e - m * K;
+                double s = 0.0;
+                for (int j = 0; j < K; ++j) s += C[i * ld + j] * st[o[F_PHI0C] + m * K + j];
+                st[o[F_W] + e] = s;
+            }
+            __syncthreads();
+            const double ldc = scal[0];
+            for (int m = t; m < M; m += VBT) {
+                double s = 0.0;
+                for (int k = 0; k < K; ++k) s += st[o[F_W] + m * K + k] * st[o[F_PHI0C] + m * K + k];
+                st[o[F_GC] + m] = -0.5 * s + 0.5 * ldc;
+            }
+            for (int e = t; e < K * K; e += VBT) {
+                int i = e / K, j = e - i * K;
+                double s = 0.0;
+                for (int m = 0; m < M; ++m) s += st[o[F_W] + m * K + i] * st[o[F_W] + m * K + j];
+                st[o[F_SWW] + e] = (double)M * C[i * ld + j] + s;
+            }
+        } else if (op == BPK_VBOP_ALPHA) {
+            // gaussian.py:609-637 index 1 summed over the M rows, then gamma.py:124-148
+            for (int k = t; k < K; k += VBT) {
+                double sw = 0.0;
+                for (int m = 0; m < M; ++m) sw += st[o[F_W] + m * K + k];
+                double mu = st[o[F_MUC] + k];
+                double d = st[o[F_SWW] + k * K + k] - 2.0 * mu * sw + (double)M * mu * mu;
+                double phi0 = -st[o[F_B0] + k] - 0.5 * d;
+                double phi1 = st[o[F_A0] + k] + 0.5 * (double)M;
+                double u0, u1, g;
+                vb_gamma(phi0, phi1, u0, u1, g, p.ctrl);
+                st[o[F_AL_PHI0] + k] = phi0;
+                st[o[F_AL_PHI1] + k] = phi1;
+                st[o[F_AL_U0] + k] = u0;
+                st[o[F_AL_U1] + k] = u1;
+                st[o[F_AL_G] + k] = g;
+            }
+        } else if (op == BPK_VBOP_TAU) {
+            // gaussian.py:2351-2371 summed over (M,N), then gamma.py:124-148
+            double E2 = vb_E2(st, o, M, K, red);
+            if (t == 0) {
+                double phi0 = -st[o[F_TB0]] - 0.5 * E2;
+                double phi1 = st[o[F_TA0]] + 0.5 * (double)M * Ng;
+                double u0, u1, g;
+                vb_gamma(phi0, phi1, u0, u1, g, p.ctrl);
+                st[o[F_TAU_PHI0]] = phi0;
+                st[o[F_TAU_PHI1]] = phi1;
+                st[o[F_TAU_U0]] = u0;
+                st[o[F_TAU_U1]] = u1;
+                st[o[F_TAU_G]] = g;
+            }
+        } else if (op == BPK_VBOP_BOUND) {
+            // expfamily.py:400-480 for Y, X, C, alpha, tau from the plate-summed statistics
+            const double tau = st[o[F_TAU_U0]], logtau = st[o[F_TAU_U1]];
+            double E2 = vb_E2(st, o, M, K, red);
+            double LY = -0.5 * tau * E2 + 0.5 * (double)M * Ng * (logtau - LOG2PI_D);
+            // X
+            const double *Sxx = st + o[F_STATS] + M * K, *sx = Sxx + K * K;
+            double a = 0.0;   // tr(Lam_x S_xx), (phi1_p - phi1_q):sum<xx^T>
+            double b = 0.0;
+            for (int e = t; e < K * K; e += VBT) {
+                int i = e / K, j = e - i * K;
+                double lam = st[o[F_LAMX] + e];
+                a += lam * Sxx[e];
+                b += (0.5 * lam - (i == j ? 0.5 * st[o[F_AX] + i] : 0.0)) * st[o[F_SXXT] + e];
+            }
+            double c = 0.0;   // phi0_p . s_x  and the prior cgf
+            for (int k = t; k < K; k += VBT) {
+                double ax = st[o[F_AX] + k], mu = st[o[F_MUX] + k];
+                c += ax * mu * sx[k] + Ng * (-0.5 * ax * mu * mu + 0.5 * log(ax));
+            }
+            double trLS = vb_block_sum(a, red);
+            double LX = vb_block_sum(b + c, red) - trLS + 0.5 * trLS - 0.5 * Ng * st[o[F_LOGDETX]];
+            // C
+            double d = 0.0;
+            for (int e = t; e < M * K; e += VBT) {
+                int k = e % K;
+                d += (st[o[F_AL_U0] + k] * st[o[F_MUC] + k] - st[o[F_PHI0C] + e]) * st[o[F_W] + e];
+            }
+            for (int e = t; e < K * K; e += VBT) {
+                int i = e / K, j = e - i * K;
+                d += (0.5 * st[o[F_LAMC] + e] - (i == j ? 0.5 * st[o[F_AL_U0] + i] : 0.0)) * st[o[F_SWW] + e];
+            }
+            for (int m = t; m < M; m += VBT) d -= st[o[F_GC] + m];
+            for (int k = t; k < K; k += VBT) {
+                double mu = st[o[F_MUC] + k];
+                d += (double)M * (-0.5 * st[o[F_AL_U0] + k] * mu * mu + 0.5 * st[o[F_AL_U1] + k]);
+            }
+            double LC = vb_block_sum(d, red);
+            // alpha
+            double f = 0.0;
+            if (p.has_alpha) {
+                for (int k = t; k < K; k += VBT) {
+                    double a0 = st[o[F_A0] + k], b0 = st[o[F_B0] + k];
+                    f += (-b0 - st[o[F_AL_PHI0] + k]) * st[o[F_AL_U0] + k]
+                       + (a0 - st[o[F_AL_PHI1] + k]) * st[o[F_AL_U1] + k]
+                       + (a0 * log(b0) - lgamma(a0)) - st[o[F_AL_G] + k];
+                }
+            }
+            double LA = vb_block_sum(f, red);
+            if (t == 0) {
+                double LT = 0.0;
+                if (p.has_tau) {
+                    double a0 = st[o[F_TA0]], b0 = st[o[F_TB0]];
+                    LT = (-b0 - st[o[F_TAU_PHI0]]) * tau + (a0 - st[o[F_TAU_PHI1]]) * logtau
+                       + (a0 * log(b0) - lgamma(a0)) - st[o[F_TAU_G]];
+                }
+                double L = (((LY + LX) + LC) + LA) + LT;
+                int it = p.ctrl[0];
+                if (it < p.cap) {
+                    double *row = p.Lhist + (size_t)it * 6;
+                    row[0] = LY; row[1] = LX; row[2] = LC; row[3] = LA; row[4] = LT; row[5] = L;
+                }
+                double L0 = st[o[F_LPREV]];
+                st[o[F_LPREV]] = L;
+                p.ctrl[0] = it + 1;
+                // vmp.py:738-747 (tol < 0 or no previous bound: test disabled)
+                if (p.tol >= 0.0 && L0 == L0) {
+                    double div = 0.5 * (fabs(L0) + fabs(L));
+                    if ((L - L0) / div < p.tol) p.ctrl[1] = 1;
+                }
+                if (p.ctrl[2]) p.ctrl[1] = 1;
+                __threadfence();
+            }
+        }
+    }
+    if (staged) {
+        __syncthreads();
+        for (int64_t e = o[F_W] + t; e < nstate; e += VBT) p.st[e] = st[e];      // hyper-parameters are read-only
+    }
+}
+
+
+// pca.cu: the one-pass sweep (requires M<=64, K<=16).  Without `tail` the per-CTA partial statistics
+// are left in scratch for the caller to reduce; with `tail` (aligned inputs) the launch also reduces
+// them and runs the given small ops in its last CTA (*tail_done = 1), i.e. one launch per VB sweep.
+int pca_xsweep_partials(const double *Y, int64_t M, int64_t N, int K, const double *A, const double *b,
+                        double *X, const int *stop, double **partial_out, int *nparts_out,
+                        const PcaVbArgs *tail, int *tail_done);

@@ -287,6 +287,52 @@ extern "C" int bpk_allreduce_sum_f64_oop(const double *src, double *dst, uint64_
     g_bpk.launches++;
     return BPK_OK;
 }
+// ---- peer-memory exchange window (in-kernel all-reduce over NVLink) ---------------------------
+// Every rank cudaMalloc's one window and opens its peers' through CUDA IPC; kernels then
+// store their partial statistics straight into every peer's window and spin on sequence
+// flags (pca_vb_ops.cuh: STATS), so the sweep's one exchange costs no launch and no NCCL call.
+BpkXchg g_xchg;
+
+extern "C" int bpk_xchg_create(char handle[64]) {
+    BPK_REQUIRE_INIT();
+    if (!g_xchg.own) {
+        BPK_CUDA(cudaMalloc((void **)&g_xchg.own, BPK_XCHG_BYTES));
+        BPK_CUDA(cudaMemset(g_xchg.own, 0, BPK_XCHG_BYTES));
+    }
+    cudaIpcMemHandle_t h;
+    BPK_CUDA(cudaIpcGetMemHandle(&h, g_xchg.own));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle, &h, 64);
+    return BPK_OK;
+}
+extern "C" int bpk_xchg_open(const char *handles, int nranks, int rank) {
+    BPK_REQUIRE_INIT();
+    if (nranks < 1 || nranks > BPK_XCHG_MAXRANKS || rank < 0 || rank >= nranks)
+        return bpk_set_error(BPK_EINVAL, "bpk_xchg_open: bad rank/nranks (max %d ranks)", BPK_XCHG_MAXRANKS);
+    if (!g_xchg.own) return bpk_set_error(BPK_EINVAL, "bpk_xchg_open: bpk_xchg_create has not been called");
+    for (int r = 0; r < nranks; ++r) {
+        if (r == rank) { g_xchg.win[r] = g_xchg.own; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)r * 64, 64);
+        void *p = nullptr;
+        BPK_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        g_xchg.win[r] = (double *)p;
+    }
+    g_xchg.nranks = nranks;
+    g_xchg.rank = rank;
+    g_xchg.ready = true;
+    return BPK_OK;
+}
+extern "C" int bpk_xchg_close(void) {
+    if (!g_xchg.own) return BPK_OK;
+    cudaStreamSynchronize(g_bpk.stream);
+    for (int r = 0; r < g_xchg.nranks; ++r)
+        if (r != g_xchg.rank && g_xchg.win[r]) cudaIpcCloseMemHandle(g_xchg.win[r]);
+    cudaFree(g_xchg.own);
+    g_xchg = BpkXchg();
+    return BPK_OK;
+}
+
 extern "C" int bpk_comm_destroy(void) {
     if (g_comm) {
         cudaStreamSynchronize(g_bpk.stream);

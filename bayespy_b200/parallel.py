@@ -73,6 +73,7 @@ def init_from_env(timeout=300.0):
         be.comm_init(uid, w, r)
         _state.update(world=w, rank=r, ready=True)
         barrier()
+        _open_peer_windows(be, w, r, path, timeout)
         if r == 0:
             try:
                 os.remove(path)
@@ -80,6 +81,59 @@ def init_from_env(timeout=300.0):
                 pass
     _state.update(world=w, rank=r, ready=True)
     return w, r
+
+
+def _open_peer_windows(be, w, r, path, timeout):
+    """Exchange CUDA IPC handles of the peer-memory windows (files next to the NCCL id) so that the
+    resident loop can all-reduce its statistics inside the sweep kernel over NVLink.  Falls back to
+    the NCCL all-reduce (with a warning) if IPC is not available; BPK_NO_P2P=1 forces the fallback."""
+    _state["p2p"] = False
+    if os.environ.get("BPK_NO_P2P") or w > 8 or not hasattr(be, "xchg_create"):
+        return
+    ok = 1.0
+    try:
+        mine = be.xchg_create()
+        tmp = "%s.ipc%d.tmp" % (path, r)
+        with open(tmp, "wb") as f:
+            f.write(mine)
+        os.replace(tmp, "%s.ipc%d" % (path, r))
+    except Exception:
+        ok = 0.0
+    handles = []
+    t0 = time.time()
+    for q in range(w):
+        h = None
+        while ok and time.time() - t0 < timeout:
+            try:
+                with open("%s.ipc%d" % (path, q), "rb") as f:
+                    h = f.read()
+                if len(h) == 64:
+                    break
+            except FileNotFoundError:
+                pass
+            time.sleep(0.02)
+        if h is None or len(h) != 64:
+            ok = 0.0
+            h = b"\0" * 64
+        handles.append(h)
+    if ok:
+        try:
+            be.xchg_open(handles, w, r)
+        except Exception as e:
+            ok = 0.0
+            import sys
+            sys.stderr.write("bayespy_b200: peer-memory windows unavailable (%s); using NCCL all-reduce\n" % e)
+    allok = float(np.min(allgather_scalar(ok)))
+    barrier()
+    try:
+        os.remove("%s.ipc%d" % (path, r))
+    except OSError:
+        pass
+    if allok < 1.0:
+        if ok:
+            be.xchg_close()
+        return
+    _state["p2p"] = True
 
 
 def set_world_for_testing(world_size, r):

@@ -123,18 +123,21 @@ class ClockSampler:
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, interval_ms=200):
         self.gpu = gpu_index
+        self.interval_ms = int(interval_ms)
         self.proc = None
         self.path = None
 
     def start(self):
+        if self.interval_ms <= 0:
+            return
         try:
             fd, self.path = tempfile.mkstemp(prefix="bpk_clocks_", suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                 "-lms", str(self.interval_ms)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -212,7 +215,7 @@ def run_gpu(args):
     Q.update(repeat=warmup, verbose=False)
     parallel.barrier()
 
-    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")), args.clock_interval_ms)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
@@ -283,7 +286,8 @@ def run_gpu(args):
                                "[X,C,alpha,tau] incl. lower bound" % n_total,
                    "n_total": n_total, "n_per_gpu": n_local_max, "parallelism": "plate-shard x%d" % world,
                    "l2": "inputs (%.2f GB of Y per GPU) larger than the 126 MB L2; no flush" % (y.nbytes / 1e9),
-                   "lower_bound_last": L_last},
+                   "lower_bound_last": L_last, "device_ms_per_step": ms_dev / steps,
+                   "host_wall_ms_per_step": 1e3 * wall / steps},
         "clocks": clocks,
         "e2e": {"value": 1.0 / e2e_s, "unit": "it/s", "h2d_bytes_per_step": int(nbytes),
                 "d2h_bytes_per_step": 8 * len(Q.model), "steps": e2e_steps,
@@ -317,6 +321,8 @@ def main():
     ap.add_argument("--n", type=int, default=N_TOTAL, help="total number of columns (default: the metric's 1e7)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--clock-interval-ms", type=int, default=200,
+                    help="nvidia-smi sampling period during the timed region (B200_PROFILING.md recipe: 200); 0 = off")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -81,6 +81,12 @@ int bpk_allreduce_sum_f64(double *dev, uint64_t count);     /* in place, on the 
 /* out of place: dst = sum over ranks of src (dst may equal src)                */
 int bpk_allreduce_sum_f64_oop(const double *src, double *dst, uint64_t count);
 int bpk_comm_destroy(void);
+/* Peer-memory exchange window for the in-kernel all-reduce of the resident loop: each rank
+ * creates one window, the 64-byte CUDA IPC handles are exchanged by the host (any side
+ * channel), and every rank opens all of them.  Up to 8 ranks on one NVLink/NVSwitch box.     */
+int bpk_xchg_create(char handle[64]);
+int bpk_xchg_open(const char *handles /* [nranks][64] */, int nranks, int rank);
+int bpk_xchg_close(void);
 
 /* ---- generic broadcast kernels (seam 1) -------------------------------- */
 /* Elementwise out[i] = op(in0[i], in1[i], in2[i]; alpha, beta) over an
@@ -236,6 +242,8 @@ int bpk_pca_vb_run(const double *Y, int64_t M, int64_t N, int K, double *X, doub
 /* bench.py: record these timers (bpk_timer_create ids) around the next n sweep-kernel launches */
 int bpk_pca_vb_set_timers(const int *ids, int n);
 int bpk_pca_vb_timers_used(void);
+/* diagnostics: device-clock stamps of the last fused sweep launch (needs BPK_VB_DEBUG=1 in the environment) */
+int bpk_debug_stamps(uint64_t *out, int n);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,39 @@
+"""Where does the tail of the fused sweep launch spend its time?  (BPK_VB_DEBUG stamps)
+    BPK_VB_DEBUG=1 python tools/vb_tail_timing.py [N]
+"""
+import os
+import sys
+
+os.environ["BPK_VB_DEBUG"] = "1"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np          # noqa: E402
+import bench                # noqa: E402
+from bayespy_b200 import _bpk   # noqa: E402
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
+y = bench.synth_shard(64, 0, N, 1)
+Q, nodes = bench.build_model(y)
+Q.update(repeat=5, verbose=False)
+be = _bpk.get()
+s = be.debug_stamps(32)
+t0 = s[0]
+names = {1: "data pass done (CTA 0)", 2: "after grid barrier 1", 3: "CTA 0 reduction share done", 4: "after grid barrier 2",
+         5: "tail done"}
+print("N=%d: stamps relative to kernel start (us)" % N)
+for i in (1, 2, 3, 4):
+    print("  %-32s %10.2f" % (names[i], (s[i] - t0) / 1e3))
+opn = {2: "STATS", 3: "SXXT", 4: "XPRE", 5: "ROW", 6: "ALPHA", 7: "TAU", 8: "BOUND"}
+plan = Q.plans[0]
+ops = [o for o in plan.resident_program(Q, Q.model)[0] if o != 1]
+# tail of one sweep = ops after XSWEEP of iteration i + ops before XSWEEP of iteration i+1
+prog = plan.resident_program(Q, Q.model)[0]
+k = prog.index(1)
+tail = prog[k + 1:] + prog[:k]
+prev = s[4]
+for i, op in enumerate(tail):
+    st = s[8 + i]
+    nxt = s[8 + i + 1] if i + 1 < len(tail) else s[5]
+    print("  op %-6s %10.2f us" % (opn[op], (nxt - st) / 1e3))
+print("  %-32s %10.2f" % (names[5], (s[5] - t0) / 1e3))
+print("  tail total (after data pass)     %10.2f" % ((s[5] - s[1]) / 1e3))
