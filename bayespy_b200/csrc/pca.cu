@@ -514,6 +514,7 @@ pca_xsweep_ws_kernel(const __grid_constant__ CUtensorMap tmapY, int64_t M, int64
         grid_barrier(gbar, epoch);
         if (blockIdx.x == 0) {
             vb_stamp(vb.dbg, 4);
+            if (vb.dbg && vb.dbg[63]) { pca_vb_ops(vb, smem, vb_sm_doubles, true); __syncthreads(); vb_stamp(vb.dbg, 6); }   // experiment
             pca_vb_ops(vb, smem, vb_sm_doubles);
             vb_stamp(vb.dbg, 5);
         }

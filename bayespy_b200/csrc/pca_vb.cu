@@ -83,7 +83,6 @@ extern "C" int bpk_pca_vb_run(const double *Y, int64_t M, int64_t N, int K, doub
     bpk_comm_size(&nranks, &rank);
     int64_t off[F_COUNT + 1];
     pca_vb_offsets((int)M, K, off);
-    const int ld = SPD_LD(K);
     size_t smem = pca_vb_smem_doubles(K) * sizeof(double);
     if (smem + (size_t)off[F_COUNT] * sizeof(double) <= (200u << 10)) smem += (size_t)off[F_COUNT] * sizeof(double);   // stage the state
     if (smem > (48u << 10))
@@ -99,6 +98,11 @@ extern "C" int bpk_pca_vb_run(const double *Y, int64_t M, int64_t N, int K, doub
         if (!g_vb_dbg) {
             BPK_CUDA(cudaMalloc((void **)&g_vb_dbg, 64 * sizeof(unsigned long long)));
             BPK_CUDA(cudaMemsetAsync(g_vb_dbg, 0, 64 * sizeof(unsigned long long), g_bpk.stream));
+            if (getenv("BPK_VB_DRYTEST")) {
+                unsigned long long one = 1;
+                BPK_CUDA(cudaMemcpyAsync(g_vb_dbg + 63, &one, 8, cudaMemcpyHostToDevice, g_bpk.stream));
+                BPK_CUDA(cudaStreamSynchronize(g_bpk.stream));
+            }
         }
         a.dbg = g_vb_dbg;
     }

@@ -35,5 +35,7 @@ for i, op in enumerate(tail):
     st = s[8 + i]
     nxt = s[8 + i + 1] if i + 1 < len(tail) else s[5]
     print("  op %-6s %10.2f us" % (opn[op], (nxt - st) / 1e3))
+if s[6] > s[4]:
+    print("  dry run (cold) before the real ops %8.2f us ; real ops (warm) %8.2f us" % ((s[6] - s[4]) / 1e3, (s[5] - s[6]) / 1e3))
 print("  %-32s %10.2f" % (names[5], (s[5] - t0) / 1e3))
 print("  tail total (after data pass)     %10.2f" % ((s[5] - s[1]) / 1e3))
