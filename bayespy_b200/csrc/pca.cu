@@ -273,6 +273,7 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tmap, 
 }
 
 #define WS_PAIRS 8
+#define WS_SKIP 64                       // tiles CTA 0 gives away in the fused kernel (~1.4 us each)
 #define WS_BOXC 16                       // columns per TMA box (128 B: the SWIZZLE_128B span)
 #define WS_BOX (PCA_MP * WS_BOXC)        // doubles per box
 
@@ -295,6 +296,26 @@ __device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int &ep
         } else {
             while (*(volatile unsigned int *)&bar[1] != target) { __nanosleep(32); }
         }
+        __threadfence();
+    }
+    epoch += 1;
+    __syncthreads();
+}
+
+__device__ __forceinline__ void grid_arrive(unsigned int *bar, unsigned int epoch) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&bar[0], 1u) == gridDim.x - 1) {
+            atomicExch(&bar[0], 0u);
+            __threadfence();
+            atomicExch(&bar[1], epoch + 1);
+        }
+    }
+}
+__device__ __forceinline__ void grid_wait(unsigned int *bar, unsigned int &epoch) {
+    if (threadIdx.x == 0) {
+        while (*(volatile unsigned int *)&bar[1] != epoch + 1) { __nanosleep(32); }
         __threadfence();
     }
     epoch += 1;
@@ -336,12 +357,27 @@ pca_xsweep_ws_kernel(const __grid_constant__ CUtensorMap tmapY, int64_t M, int64
     __syncthreads();
 
     const int64_t first = blockIdx.x, stride = gridDim.x;
-    const int64_t ntl = first < ntiles ? (ntiles - first + stride - 1) / stride : 0;   // tiles of this CTA
+    const int64_t ntl_own = first < ntiles ? (ntiles - first + stride - 1) / stride : 0;   // round-robin share
+    // FUSED: CTA 0 runs the sweep's small ops after the grid reduction.  That code executes once per launch
+    // from a cold instruction cache (60 us cold, 30 us warm), so CTA 0 hands its last `skip` tiles to the
+    // CTAs at the other end of the grid (one each), finishes early and spends the head start on a dry run
+    // of the ops (no side effects) while everybody else is still streaming.  Static, hence deterministic.
+    int64_t skip = 0;
+    if (FUSED && vb.nops > 0 && stride > 1) {
+        const int64_t ntl0 = (ntiles + stride - 1) / stride;
+        skip = ntl0 / 2 < WS_SKIP ? ntl0 / 2 : WS_SKIP;
+        if (skip > stride - 1) skip = stride - 1;
+    }
+    const int64_t xtra = stride - 1 - first;          // CTA G-1 takes CTA 0's first surplus tile, G-2 the next ...
+    const bool has_xtra = skip > 0 && first != 0 && xtra < skip;
+    const int64_t ntl = (first == 0 ? ntl_own - skip : ntl_own) + (has_xtra ? 1 : 0);
+    const int64_t xtra_tile = ((ntiles + stride - 1) / stride - skip + xtra) * stride;     // a tile of CTA 0's list
+    auto tile_of = [&](int64_t i) -> int64_t { return (has_xtra && i == ntl - 1) ? xtra_tile : first + i * stride; };
 
     auto issue = [&](int64_t j) {        // lanes 0..NBOX-1 of warp 0: one TMA box each
         const int slot = (int)(j % STAGES);
         if (j >= STAGES) mbar_wait(&empty[slot], (uint32_t)((j / STAGES - 1) & 1));
-        const int64_t n0 = (first + j * stride) * T;
+        const int64_t n0 = tile_of(j) * T;
         if (lane == 0) mbar_expect_tx(&full[slot], (uint32_t)(STG * sizeof(double)));
         __syncwarp();
         if (lane < NBOX)
@@ -370,7 +406,7 @@ pca_xsweep_ws_kernel(const __grid_constant__ CUtensorMap tmapY, int64_t M, int64
             if (w == 0 && i + DIST < ntl) issue(i + DIST);
             const int slot = (int)(i % STAGES), b = (int)(i & 1);
             const int c0 = p * NT;
-            const int64_t nbase = (first + i * stride) * T + c0;
+            const int64_t nbase = tile_of(i) * T + c0;
             double *Xs = Xsm + ((size_t)(p * 2 + b) * NT) * PCA_LDX;
             if (COMPUTE_X) {
                 mbar_wait(&full[slot], (uint32_t)((i / STAGES) & 1));
@@ -495,7 +531,9 @@ pca_xsweep_ws_kernel(const __grid_constant__ CUtensorMap tmapY, int64_t M, int64
         unsigned int epoch = 0;
         if (threadIdx.x == 0) epoch = *(volatile unsigned int *)&gbar[1];
         epoch = __shfl_sync(0xffffffffu, epoch, 0);      // thread 0's value is the only one used
-        grid_barrier(gbar, epoch);
+        grid_arrive(gbar, epoch);
+        if (blockIdx.x == 0 && skip > 0) pca_vb_ops(vb, smem, vb_sm_doubles, true);      // warm the instruction cache
+        grid_wait(gbar, epoch);
         if (blockIdx.x == 0) vb_stamp(vb.dbg, 2);
         // distributed, fixed-order reduction over the CTAs: CTA c owns elements [c*per, (c+1)*per)
         double *fin = partial + (size_t)gridDim.x * PCA_NSTAT;
@@ -514,7 +552,6 @@ pca_xsweep_ws_kernel(const __grid_constant__ CUtensorMap tmapY, int64_t M, int64
         grid_barrier(gbar, epoch);
         if (blockIdx.x == 0) {
             vb_stamp(vb.dbg, 4);
-            if (vb.dbg && vb.dbg[63]) { pca_vb_ops(vb, smem, vb_sm_doubles, true); __syncthreads(); vb_stamp(vb.dbg, 6); }   // experiment
             pca_vb_ops(vb, smem, vb_sm_doubles);
             vb_stamp(vb.dbg, 5);
         }
