@@ -221,6 +221,7 @@ static __device__ __noinline__ void pca_vb_ops_t(const PcaVbArgs &p, double *sm,
                 // on every rank).  Two parities of slots: a rank cannot get more than one exchange ahead
                 // of a peer, because it needs that peer's flag to finish the one in between.
                 __syncthreads();
+                vb_stamp(dbg, 40);
                 double *own = p.xwin[p.xrank];
                 const unsigned long long seq = *(volatile unsigned long long *)own + 1ull;
                 const int par = (int)(seq & 1ull);
@@ -230,6 +231,7 @@ static __device__ __noinline__ void pca_vb_ops_t(const PcaVbArgs &p, double *sm,
                 }
                 __threadfence_system();
                 __syncthreads();
+                vb_stamp(dbg, 41);
                 if (t < xranks) {
                     unsigned long long *f = (unsigned long long *)(p.xwin[t] + BPK_XCHG_FLAGS) + par * BPK_XCHG_MAXRANKS + p.xrank;
                     asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(f), "l"(seq) : "memory");
@@ -242,6 +244,7 @@ static __device__ __noinline__ void pca_vb_ops_t(const PcaVbArgs &p, double *sm,
                     } while (v < seq);
                 }
                 __syncthreads();
+                vb_stamp(dbg, 42);
                 for (int e = t; e < total; e += VBT) {
                     double s = 0.0;
                     for (int r = 0; r < xranks; ++r)
@@ -250,6 +253,7 @@ static __device__ __noinline__ void pca_vb_ops_t(const PcaVbArgs &p, double *sm,
                 }
                 __syncthreads();
                 if (t == 0) *(volatile unsigned long long *)own = seq;
+                vb_stamp(dbg, 43);
             }
         } else if (op == BPK_VBOP_SXXT) {
             // sum_n <x x^T> = N Cov_x + S_xx

@@ -574,9 +574,7 @@ class FactorModelPlan:
         col.u = [X, FactoredSecondMoment(X, cov, (K,))]
         col.g = LazyArray((1, N), g_fn)
         col._version += 1
-        u_par = col.moments_from_parents()
-        col._fused = dict(Lam=Lam, logdet=logdet, cov=cov,
-                          phi_p=col._canonical_phi(col._distribution.compute_phi_from_parents(*u_par)))
+        col._fused = dict(Lam=Lam, logdet=logdet, cov=cov, phi_p=None)     # bound_col re-evaluates the prior itself
         self._stats = (col._version, view("stats", (M * K + K * K + K,)))
         # C
         W = view("w", (M, 1, K))
