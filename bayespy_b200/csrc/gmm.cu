@@ -20,6 +20,7 @@
 // TODO(next): move both contractions onto the fp64 tensor pipe (DMMA) — the
 // quadratic form is a (rows x F) x (F x K) GEMM in the monomial features of y.
 #include "common.cuh"
+#include <stdlib.h>
 
 #define GMM_ROWS 128
 #define GMM_MAXK 128
@@ -161,6 +162,228 @@ __global__ void __launch_bounds__(GMM_ROWS, 1) gmm_sweep_kernel(GmmArgs a) {
     }
 }
 
+// =====================================================================================
+// v1: both contractions on the fp64 tensor pipe (D <= 8, K <= 64).
+// Per data row the monomial features z = [1, y_i (8), y_i y_j for i<=j (36), 0,0,0] (48, symmetric half
+// only: 38 % fewer flops than the full y y^T) turn the E-step into the GEMM  L (rows x K) = Z Theta^T
+// with Theta_k = [c_k + logpi_k, h_k, -1/2 Lam_ii, -(Lam_ij + Lam_ji)/2 ...] and the statistics into
+// S (K x 48) = P^T Z.  CTA = 8 warps, tile = 128 rows:
+//   E phase  warp w owns rows 16w..16w+15: builds its Z rows in shared memory, 192 DMMA.8x8x4 for L,
+//            softmax in the accumulator layout (a row's 64 components live in 4 lanes: 2 shuffles),
+//            writes P to HBM (16-byte stores, 64 B contiguous per lane group) and to the P tile;
+//   M phase  warp w owns a 16 x 24 block of S and contracts it over all 128 rows of the tile (192 DMMA).
+// 24 DMMA per row = 12.3 kflop; 576 B per row of HBM traffic: fp64-pipe bound.
+// Pitches 52 / 68 doubles (= 4 mod 16) make every fragment load conflict-free.
+// =====================================================================================
+#define G1_ROWS 128
+#define G1_WARPS 8
+#define G1_KP 64
+#define G1_DP 8
+#define G1_FP 48
+#define G1_LDZ 52
+#define G1_LDP 68
+#define G1_NF 45
+
+__device__ __forceinline__ void g1_dmma(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// feature f -> (i, j): f = 0 -> 1; 1..8 -> y_{f-1}; 9..44 -> y_i y_j (i <= j, row-major upper triangle)
+__device__ __forceinline__ void g1_pair(int f, int &i, int &j) {
+    int r = f - 9, ii = 0;
+    while (r >= G1_DP - ii) { r -= G1_DP - ii; ++ii; }
+    i = ii; j = ii + r;
+}
+
+__global__ void __launch_bounds__(G1_WARPS * 32, 1) gmm_sweep_dmma_kernel(GmmArgs a) {
+    extern __shared__ __align__(16) double sm[];
+    double *sT = sm;                                   // [64][52]  Theta
+    double *sZ = sT + G1_KP * G1_LDZ;                  // [128][52] features of the tile
+    double *sP = sZ + G1_ROWS * G1_LDZ;                // [128][68] responsibilities of the tile
+    double *sY = sP + G1_ROWS * G1_LDP;                // [128][8]
+    __shared__ unsigned char fi[G1_FP], fj[G1_FP];
+    __shared__ double red[G1_WARPS];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5, gr = lane >> 2, tg = lane & 3;
+    const int D = a.D, K = a.K;
+
+    if (t < G1_FP) {
+        int i = 0, j = 0;
+        if (t >= 9 && t < G1_NF) g1_pair(t, i, j);
+        fi[t] = (unsigned char)i; fj[t] = (unsigned char)j;
+    }
+    for (int e = t; e < G1_KP * G1_FP; e += blockDim.x) {
+        const int k = e / G1_FP, f = e - k * G1_FP;
+        double v = 0.0;
+        if (k >= K) v = (f == 0) ? -1e300 : 0.0;        // padded components never win the softmax
+        else if (f == 0) v = a.c[k] + a.logpi[k];
+        else if (f <= G1_DP) v = (f - 1 < D) ? a.h[k * D + f - 1] : 0.0;
+        else if (f < G1_NF) {
+            int i, j;
+            g1_pair(f, i, j);
+            if (i < D && j < D)
+                v = (i == j) ? -0.5 * a.Lam[(k * D + i) * D + i]
+                             : -0.5 * (a.Lam[(k * D + i) * D + j] + a.Lam[(k * D + j) * D + i]);
+        }
+        sT[k * G1_LDZ + f] = v;
+    }
+    // statistics block of this warp: components 16*(w&3) .. +15, features 24*(w>>2) .. +23
+    const int mb0 = 2 * (w & 3), fb0 = 3 * (w >> 2);
+    double acc[2][3][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    double lse_acc = 0.0;
+    __syncthreads();
+
+    const int64_t ntiles = (a.N + G1_ROWS - 1) / G1_ROWS;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t row0 = tile * G1_ROWS;
+        // ---- stage y (coalesced) ----
+        {
+            const int64_t base = row0 * D;
+            int64_t lim = a.N * D - base;
+            if (lim > (int64_t)G1_ROWS * D) lim = (int64_t)G1_ROWS * D;
+            for (int e = t; e < G1_ROWS * D; e += blockDim.x) {
+                const int r = e / D, d = e - r * D;
+                sY[r * G1_DP + d] = e < lim ? a.Y[base + e] : 0.0;
+            }
+            if (D < G1_DP)
+                for (int e = t; e < G1_ROWS * (G1_DP - D); e += blockDim.x) {
+                    const int r = e / (G1_DP - D), d = D + e % (G1_DP - D);
+                    sY[r * G1_DP + d] = 0.0;
+                }
+        }
+        __syncthreads();
+        // ---- E phase: this warp's 16 rows ----
+        const int r0 = w * 16;
+        for (int e = lane; e < 16 * G1_FP; e += 32) {
+            const int r = r0 + e / G1_FP, f = e % G1_FP;
+            const bool live = row0 + r < a.N;
+            double v;
+            if (f == 0) v = live ? 1.0 : 0.0;
+            else if (f <= G1_DP) v = sY[r * G1_DP + f - 1];
+            else if (f < G1_NF) v = sY[r * G1_DP + fi[f]] * sY[r * G1_DP + fj[f]];
+            else v = 0.0;
+            sZ[r * G1_LDZ + f] = v;
+        }
+        __syncwarp();
+        double L[2][8][2];
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) L[g][nb][0] = L[g][nb][1] = 0.0;
+#pragma unroll 2
+        for (int s = 0; s < G1_FP / 4; ++s) {
+            const double z0 = sZ[(r0 + gr) * G1_LDZ + 4 * s + tg];
+            const double z1 = sZ[(r0 + 8 + gr) * G1_LDZ + 4 * s + tg];
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) {
+                const double th = sT[(nb * 8 + gr) * G1_LDZ + 4 * s + tg];
+                g1_dmma(L[0][nb][0], L[0][nb][1], z0, th);
+                g1_dmma(L[1][nb][0], L[1][nb][1], z1, th);
+            }
+        }
+        // softmax over the 64 components of row (g*8 + gr): 16 values here, the rest in lanes tg^1, tg^2
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            const int r = r0 + g * 8 + gr;
+            const int64_t n = row0 + r;
+            const bool live = n < a.N;
+            double m = -INFINITY;
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) m = fmax(m, fmax(L[g][nb][0], L[g][nb][1]));
+            m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 1));
+            m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 2));
+            if (!isfinite(m)) m = 0.0;
+            double ssum = 0.0;
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) {
+                L[g][nb][0] = exp(L[g][nb][0] - m);
+                L[g][nb][1] = exp(L[g][nb][1] - m);
+                ssum += L[g][nb][0] + L[g][nb][1];
+            }
+            ssum += __shfl_xor_sync(0xffffffffu, ssum, 1);
+            ssum += __shfl_xor_sync(0xffffffffu, ssum, 2);
+            const double lse = log(ssum) + m;
+            const double inv = 1.0 / ssum;
+            double s2 = 0.0;
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) {
+                L[g][nb][0] *= inv; L[g][nb][1] *= inv;
+                s2 += L[g][nb][0] + L[g][nb][1];
+            }
+            s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+            const double inv2 = live ? 1.0 / s2 : 0.0;       // misc.py:1398-1401 second renormalisation
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) {
+                const double p0 = L[g][nb][0] * inv2, p1 = L[g][nb][1] * inv2;
+                const int k = nb * 8 + 2 * tg;
+                sP[r * G1_LDP + k] = p0;
+                sP[r * G1_LDP + k + 1] = p1;
+                if (live && a.P) {
+                    double *dst = a.P + n * K + k;
+                    if (K == G1_KP) *reinterpret_cast<double2 *>(dst) = make_double2(p0, p1);
+                    else { if (k < K) dst[0] = p0; if (k + 1 < K) dst[1] = p1; }
+                }
+            }
+            if (live && tg == 0) {
+                lse_acc += lse;
+                if (a.g) a.g[n] = -lse;
+            }
+        }
+        __syncthreads();
+        // ---- M phase: S[16 x 24 block] += P^T Z over the 128 rows of the tile ----
+#pragma unroll 4
+        for (int q = 0; q < G1_ROWS / 4; ++q) {
+            const int r = 4 * q + tg;
+            const double pa0 = sP[r * G1_LDP + mb0 * 8 + gr], pa1 = sP[r * G1_LDP + (mb0 + 1) * 8 + gr];
+#pragma unroll
+            for (int fb = 0; fb < 3; ++fb) {
+                const double zb = sZ[r * G1_LDZ + (fb0 + fb) * 8 + gr];
+                g1_dmma(acc[0][fb][0], acc[0][fb][1], pa0, zb);
+                g1_dmma(acc[1][fb][0], acc[1][fb][1], pa1, zb);
+            }
+        }
+        __syncthreads();
+    }
+    // per-CTA partial in the v0 (k, f) layout with F = 1 + D + D*D, so that gmm_final_kernel serves both
+    const int F = a.nfeat;
+    double *pout = a.partial + (size_t)blockIdx.x * (K * F + 1);
+    __syncthreads();
+    double *sS = sZ;                                    // [64][48] staging of the CTA's S
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int fb = 0; fb < 3; ++fb)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                sS[((mb0 + i) * 8 + gr) * G1_FP + (fb0 + fb) * 8 + 2 * tg + j] = acc[i][fb][j];
+    __syncthreads();
+    for (int e = t; e < K * F; e += blockDim.x) {
+        const int k = e / F, f = e - k * F;
+        double v;
+        if (f <= D) v = sS[k * G1_FP + f];              // 1, y_i  (f-1 < D <= 8: same slot)
+        else {
+            int i = (f - 1 - D) / D, j = (f - 1 - D) % D;
+            if (i > j) { int tmp = i; i = j; j = tmp; }
+            const int sf = 9 + i * G1_DP - (i * (i - 1)) / 2 + (j - i);
+            v = sS[k * G1_FP + sf];
+        }
+        pout[e] = v;
+    }
+    lse_acc = warp_sum(lse_acc);
+    if (lane == 0) red[w] = lse_acc;
+    __syncthreads();
+    if (t == 0) {
+        double sum = 0.0;
+        for (int ww = 0; ww < G1_WARPS; ++ww) sum += red[ww];
+        pout[K * F] = sum;
+    }
+}
+
 // partial (k, f) layout -> caller's [sum p (K) | sum p y (K*D) | sum p yy^T (K*D*D) | lse]
 __global__ void gmm_final_kernel(const double *__restrict__ partial, int nblocks, int K, int D,
                                  double *__restrict__ stats) {
@@ -213,6 +436,20 @@ static int gmm_run(const double *Y, int64_t N, int D, int K,
     if (ntiles < grid) grid = (int)ntiles;
     a.partial = bpk_scratch((size_t)grid * (K * a.nfeat + 1) * sizeof(double));
     if (!a.partial) return bpk_set_error(BPK_ECUDA, "gmm: scratch allocation failed");
+    if (!given_p && D <= G1_DP && K <= G1_KP && !getenv("BPK_GMM_V0")) {
+        size_t smem1 = ((size_t)G1_KP * G1_LDZ + (size_t)G1_ROWS * G1_LDZ + (size_t)G1_ROWS * G1_LDP +
+                        (size_t)G1_ROWS * G1_DP) * sizeof(double);
+        int64_t nt1 = (N + G1_ROWS - 1) / G1_ROWS;
+        int grid1 = g_bpk.sm_count;
+        if (nt1 < grid1) grid1 = (int)nt1;
+        a.partial = bpk_scratch((size_t)grid1 * (K * a.nfeat + 1) * sizeof(double));
+        if (!a.partial) return bpk_set_error(BPK_ECUDA, "gmm: scratch allocation failed");
+        BPK_CUDA(cudaFuncSetAttribute(gmm_sweep_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+        BPK_LAUNCH(gmm_sweep_dmma_kernel, grid1, G1_WARPS * 32, smem1, a);
+        int total1 = K * a.nfeat + 1;
+        BPK_LAUNCH(gmm_final_kernel, (total1 + 127) / 128, 128, 0, a.partial, grid1, K, D, stats);
+        return BPK_OK;
+    }
 #define GMM_LAUNCH(PT)                                                                                  \
     do {                                                                                                \
         BPK_CUDA(cudaFuncSetAttribute(gmm_sweep_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
