@@ -69,6 +69,7 @@ PROTOTYPES = {
     "bpk_chol_solve": (C.c_int, [_dp, C.c_int64, _dp, C.c_int64, _dp, C.c_int64, C.c_int, C.c_int]),
     "bpk_chol_inv": (C.c_int, [_dp, _dp, C.c_int64, C.c_int]),
     "bpk_chol_logdet": (C.c_int, [_dp, _dp, C.c_int64, C.c_int]),
+    "bpk_block_banded_solve": (C.c_int, [_dp, _dp, _dp, C.c_int64, C.c_int64, C.c_int, _dp, _dp, _dp, _dp, C.c_int]),
     "bpk_gaussian_moments": (C.c_int, [_dp, C.c_int64, _dp, C.c_int64, C.c_int64, C.c_int, _dp, _dp, _dp, _dp,
                                        C.c_int]),
     "bpk_outer_add": (C.c_int, [_dp, _dp, C.c_int64, C.c_int64, C.c_int, _dp]),
@@ -270,6 +271,9 @@ class CudaBackend:
 
     def chol_logdet(self, U, out, batch, D):
         self._chk(self.lib.bpk_chol_logdet(U, out, batch, D))
+
+    def block_banded_solve(self, A, B, y, batch, T, D, V, Cb, x, logdet, check=True):
+        self._chk(self.lib.bpk_block_banded_solve(A, B, y, batch, T, D, V, Cb, x, logdet, int(check)))
 
     # -- node kernels
     def gaussian_moments(self, phi0, n0, phi1, n1, N, K, u0, cov, g, logdet, check=True):

@@ -3,6 +3,7 @@
 #pragma once
 #include "common.cuh"
 #include "pca_common.cuh"
+#include "spd.cuh"
 
 #define VB_THREADS 256      // block size of the standalone small kernel
 #define VB_MAXOPS 24
@@ -80,56 +81,6 @@ __device__ __forceinline__ double vb_block_sum(double v, double *red) {
     const int nw = blockDim.x >> 5;
     for (int w = 0; w < nw; ++w) s += red[w];
     return s;
-}
-
-// In-place inverse of the SPD matrix held in the left half of the augmented tile G (K x 2K, pitch ldg,
-// right half = identity) by Gauss-Jordan elimination without pivoting, ALL threads of the CTA working on
-// every step (K steps of two barriers each; a warp-level Cholesky + triangular solves of the same tile
-// took ~13 us, this takes ~3).  On exit G[:, K:2K] = A^-1, scal[0] = log det A (sum of log pivots;
-// linalg.py:209-223 gives the same number as 2 sum log diag U).  Non-positive pivot -> BPK_FLAG_NOTSPD.
-template <int KC>
-__device__ __forceinline__ void vb_spd_inverse(double *G, double *rowk, double *colk, double *piv, int Krt, double *scal,
-                                               int *ctrl) {
-    const int K = KC ? KC : Krt, K2 = 2 * K, ldg = K2 + 1;
-    const int t = threadIdx.x, nt = blockDim.x;
-    for (int k = 0; k < K; ++k) {
-        __syncthreads();
-        const double p = G[k * ldg + k];
-        const double r = 1.0 / p;
-        if (t < K2) rowk[t] = G[k * ldg + t] * r;
-        else if (t < K2 + K) colk[t - K2] = G[(t - K2) * ldg + k];
-        if (t == K2 + K) piv[k] = p;
-        if (nt < K2 + K + 1) {          // narrow blocks: let the first threads take the leftovers
-            for (int e = t + nt; e < K2 + K + 1; e += nt) {
-                if (e < K2) rowk[e] = G[k * ldg + e] * r;
-                else if (e < K2 + K) colk[e - K2] = G[(e - K2) * ldg + k];
-                else piv[k] = p;
-            }
-        }
-        __syncthreads();
-        for (int e = t; e < K * K2; e += nt) {
-            const int i = e / K2, j = e - i * K2;
-            const double rj = rowk[j];
-            G[i * ldg + j] = (i == k) ? rj : G[i * ldg + j] - colk[i] * rj;
-        }
-    }
-    __syncthreads();
-    if (t < 32) {
-        double s = 0.0;
-        int bad = 0;
-        for (int k = t; k < K; k += 32) {
-            const double p = piv[k];
-            if (!(p > 0.0) || !isfinite(p)) bad = 1;
-            s += log(p);
-        }
-        s = warp_sum(s);
-        bad = __any_sync(0xffffffffu, bad);
-        if (t == 0) {
-            scal[0] = s;
-            if (bad) atomicOr(&ctrl[2], BPK_FLAG_NOTSPD);
-        }
-    }
-    __syncthreads();
 }
 
 // gamma.py:124-148: a = phi1, b = -phi0
@@ -271,7 +222,7 @@ static __device__ __noinline__ void pca_vb_ops_t(const PcaVbArgs &p, double *sm,
                 } else v = (j - K == i) ? 1.0 : 0.0;
                 G[i * ldg + j] = v;
             }
-            vb_spd_inverse<KC>(G, rowk, colk, piv, K, scal, ctrl);
+            spd_cta_inverse_gj<KC>(G, rowk, colk, piv, K, scal, &ctrl[2]);
             for (int e = t; e < K * K; e += VBT) st[o[F_COVX] + e] = CINV(e / K, e % K);
             if (t == 0) st[o[F_LOGDETX]] = scal[0];
             for (int k = t; k < K; k += VBT) {
@@ -302,7 +253,7 @@ static __device__ __noinline__ void pca_vb_ops_t(const PcaVbArgs &p, double *sm,
                 const int k = e % K;
                 st[o[F_PHI0C] + e] = st[o[F_AL_U0] + k] * st[o[F_MUC] + k] + tau * st[o[F_STATS] + e];
             }
-            vb_spd_inverse<KC>(G, rowk, colk, piv, K, scal, ctrl);
+            spd_cta_inverse_gj<KC>(G, rowk, colk, piv, K, scal, &ctrl[2]);
             for (int e = t; e < K * K; e += VBT) st[o[F_COVC] + e] = CINV(e / K, e % K);
             const double ldc = scal[0];
             if (t == 0) st[o[F_LOGDETC]] = ldc;

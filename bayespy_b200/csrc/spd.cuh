@@ -67,3 +67,54 @@ __device__ __forceinline__ void spd_warp_inverse(const double *S, double *B, dou
     }
     __syncwarp();
 }
+
+// In-place inverse of the SPD matrix held in the left half of the augmented tile G (K x 2K, pitch ldg,
+// right half = identity) by Gauss-Jordan elimination without pivoting, ALL threads of the CTA working on
+// every step (K steps of two barriers each; a warp-level Cholesky + triangular solves of the same tile
+// took ~13 us, this takes ~3).  On exit G[:, K:2K] = A^-1, scal[0] = log det A (sum of log pivots;
+// linalg.py:209-223 gives the same number as 2 sum log diag U).  Non-positive pivot -> BPK_FLAG_NOTSPD.
+template <int KC>
+__device__ __forceinline__ void spd_cta_inverse_gj(double *G, double *rowk, double *colk, double *piv, int Krt, double *scal,
+                                                   int *flagword) {
+    const int K = KC ? KC : Krt, K2 = 2 * K, ldg = K2 + 1;
+    const int t = threadIdx.x, nt = blockDim.x;
+    for (int k = 0; k < K; ++k) {
+        __syncthreads();
+        const double p = G[k * ldg + k];
+        const double r = 1.0 / p;
+        if (t < K2) rowk[t] = G[k * ldg + t] * r;
+        else if (t < K2 + K) colk[t - K2] = G[(t - K2) * ldg + k];
+        if (t == K2 + K) piv[k] = p;
+        if (nt < K2 + K + 1) {          // narrow blocks: let the first threads take the leftovers
+            for (int e = t + nt; e < K2 + K + 1; e += nt) {
+                if (e < K2) rowk[e] = G[k * ldg + e] * r;
+                else if (e < K2 + K) colk[e - K2] = G[(e - K2) * ldg + k];
+                else piv[k] = p;
+            }
+        }
+        __syncthreads();
+        for (int e = t; e < K * K2; e += nt) {
+            const int i = e / K2, j = e - i * K2;
+            const double rj = rowk[j];
+            G[i * ldg + j] = (i == k) ? rj : G[i * ldg + j] - colk[i] * rj;
+        }
+    }
+    __syncthreads();
+    if (t < 32) {
+        double s = 0.0;
+        int bad = 0;
+        for (int k = t; k < K; k += 32) {
+            const double p = piv[k];
+            if (!(p > 0.0) || !isfinite(p)) bad = 1;
+            s += log(p);
+        }
+        s = warp_sum(s);
+        bad = __any_sync(0xffffffffu, bad);
+        if (t == 0) {
+            scal[0] = s;
+            if (bad) atomicOr(flagword, BPK_FLAG_NOTSPD);
+        }
+    }
+    __syncthreads();
+}
+

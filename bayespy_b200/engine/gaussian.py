@@ -102,6 +102,8 @@ def gamma_constant(a):
 
 
 def ensure_gaussian(x, ndim):
+    if isinstance(x, Node) and hasattr(x, "_to_gaussian"):
+        x = x._to_gaussian()          # e.g. a Gaussian Markov chain seen as Gaussians plated over time
     if isinstance(x, Node):
         if x.moment_kind != "gaussian":
             raise ValueError("Expected a Gaussian-like node, got %s" % type(x).__name__)

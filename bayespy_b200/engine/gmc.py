@@ -1,0 +1,222 @@
+"""Gaussian Markov chain node on device (nodes/gaussian_markov_chain.py:270-927 restricted to the
+time-invariant chain without input signals):
+
+    x_0 ~ N(mu, Lambda^-1),   x_n ~ N(A x_{n-1}, diag(nu)^-1),  n = 1..N-1
+
+Moments u = [<x_n> (N,D), <x_n x_n^T> (N,D,D), <x_n x_{n+1}^T> (N-1,D,D)]; the time axis is part of the
+variable dims exactly as in the reference.  The natural parameters form a block-tridiagonal precision
+(:542-627); the update is one call of ``bpk_block_banded_solve`` (linalg.py:468-575, the RTS smoother in
+information form) instead of the reference's Python loop over time steps.
+
+The reference routes (mu, Lambda) and (A, nu) through the joint-moment wrapper nodes
+WrapToGaussianWishart / WrapToGaussianGamma (gaussian.py:2299-2527); here the node has four plain parents
+and forms those products itself, so the messages arriving at mu, Lambda, A and nu are the same arrays.
+"""
+import numpy as np
+
+from .. import _bpk
+from .. import darray as D
+from ..darray import DArray
+from .expfam import Distribution, ExponentialFamily
+from .gaussian import LOG2PI, dense, ensure_gamma, ensure_gaussian
+from .node import Deterministic, Node
+from .wishart import ensure_wishart
+
+
+class GaussianMarkovChainDistribution(Distribution):
+
+    def __init__(self, N, Dm):
+        self.N, self.D = int(N), int(Dm)
+
+    # -- plates: (mu, Lambda) see the chain's plates; A and nu additionally carry the state axis (D,)
+    def plates_to_parent(self, index, plates):
+        return tuple(plates) if index < 2 else tuple(plates) + (self.D,)
+
+    def plates_from_parent(self, index, plates):
+        return tuple(plates) if index < 2 else tuple(plates[:-1])
+
+    def compute_weights_to_parent(self, index, weights):
+        w = np.asarray(weights)
+        return w if index < 2 else w.reshape(w.shape + (1,))
+
+    def _check_static(self, u_A, u_nu):
+        if u_A[0].ndim != 2 or D.asarray(u_nu[0]).ndim > 1:
+            raise NotImplementedError("GaussianMarkovChain: plated chains and time-varying dynamics are not "
+                                      "supported yet (A must have plates (D,), nu plates (D,))")
+
+    # -- natural parameters (gaussian_markov_chain.py:542-627)
+    def compute_phi_from_parents(self, u_mu, u_Lambda, u_A, u_nu, mask=True):
+        N, Dm = self.N, self.D
+        self._check_static(u_A, u_nu)
+        Lam = D.asarray(u_Lambda[0]).reshape((Dm, Dm))
+        mu = D.asarray(u_mu[0]).reshape((Dm,))
+        A = u_A[0]                                   # (D, D): row d = <a_d>
+        AA = dense(u_A[1])                           # (D, D, D): <a_d a_d^T>
+        nu = D.asarray(u_nu[0]).broadcast_to((Dm,)).contiguous()
+        phi0 = DArray.zeros((N, Dm))
+        D.sum_product([Lam, mu], [["i", "j"], ["j"]], ["i"], out=phi0.slice_axis(0, 0, 1).reshape((Dm,)))
+        phi1 = DArray.zeros((N, Dm, Dm))
+        D._ew("AFFINE", (Dm, Dm), phi1.slice_axis(0, 0, 1).reshape((Dm, Dm)), [Lam], alpha=-0.5, beta=0.0)
+        if N > 1:
+            # diagonal blocks n >= 1: -1/2 diag(nu);  blocks n <= N-2: -1/2 sum_d nu_d <a_d a_d^T>
+            tail = phi1.slice_axis(0, 1, N)
+            D._ew("AFFINE", (N - 1, Dm), tail.diag_view(1), [nu.reshape((1, Dm))], alpha=-0.5, beta=0.0)
+            S = D.sum_product([nu, AA], [["d"], ["d", "i", "j"]], ["i", "j"], scale=-0.5)
+            head = phi1.slice_axis(0, 0, N - 1)
+            D._ew("ADD", (N - 1, Dm, Dm), head, [head, S.reshape((1, Dm, Dm))])
+        # super-diagonal blocks (sum of super and sub): phi2[n, i, j] = nu_j <A>[j, i]
+        phi2 = DArray.empty((max(N - 1, 0), Dm, Dm))
+        if N > 1:
+            nuA_T = D.mul(A, nu.reshape((Dm, 1))).swap_last2()
+            D.copy_into(phi2, nuA_T.reshape((1, Dm, Dm)))
+        return [phi0, phi1, phi2]
+
+    # -- E[log normaliser of the prior] (:251-267, :629-657)
+    def compute_cgf_from_parents(self, u_mu, u_Lambda, u_A, u_nu):
+        Dm = self.D
+        Lam = D.asarray(u_Lambda[0]).reshape((Dm, Dm))
+        mumu = dense(u_mu[1]).reshape((Dm, Dm))
+        t = D.sum_product([Lam, mumu], [["i", "j"], ["i", "j"]], [])
+        g = D.axpby(-0.5, t, 0.5, D.asarray(u_Lambda[1]).reshape(()))
+        lognu = D.asarray(u_nu[1]).broadcast_to((Dm,))
+        s = D.sum_product([lognu], [["d"]], [], scale=0.5 * (self.N - 1))
+        return D.add(g, s)
+
+    # -- smoother (:89-123)
+    def compute_moments_and_cgf(self, phi, mask=True):
+        N, Dm = self.N, self.D
+        be = _bpk.get()
+        y = phi[0].contiguous()
+        A = D.mul(phi[1], -2.0)
+        B = D.mul(phi[2], -1.0) if N > 1 else DArray.empty((1,))
+        V, x = DArray.empty((N, Dm, Dm)), DArray.empty((N, Dm))
+        C = DArray.empty((max(N - 1, 1), Dm, Dm))
+        ld = DArray.empty(())
+        be.block_banded_solve(A.ptr, B.ptr, y.ptr, 1, N, Dm, V.ptr, C.ptr, x.ptr, ld.ptr, True)
+        u1 = D.add(V, D.mul(x.add_trailing(1), x.expand_dims(-2)))
+        if N > 1:
+            xp = x.slice_axis(0, 0, N - 1)
+            xn = x.slice_axis(0, 1, N)
+            u2 = D.add(C.slice_axis(0, 0, N - 1), D.mul(xp.add_trailing(1), xn.expand_dims(-2)))
+        else:
+            u2 = DArray.empty((0, Dm, Dm))
+        g = D.axpby(-0.5, D.sum_product([x, y], [["n", "i"], ["n", "i"]], []), 0.5, ld)
+        return [x, u1, u2], g
+
+    def compute_fixed_moments_and_f(self, x, mask=True):
+        x = np.asarray(x, dtype=np.float64)
+        if x.shape[-2:] != (self.N, self.D):
+            raise ValueError("Invalid shape")
+        u1 = x[..., :, None] * x[..., None, :]
+        u2 = x[..., :-1, :, None] * x[..., 1:, None, :]
+        return [D.asarray(x), D.asarray(u1), D.asarray(u2)], -0.5 * self.N * self.D * LOG2PI
+
+    # -- messages (:443-527 combined with gaussian.py:2351-2371 / :2496-2522)
+    def compute_message_to_parent(self, parent, index, u, u_mu, u_Lambda, u_A, u_nu):
+        N, Dm = self.N, self.D
+        x, xx, xpxn = u
+        if index in (0, 1):
+            x0 = x.slice_axis(0, 0, 1).reshape((Dm,))
+            x0x0 = xx.slice_axis(0, 0, 1).reshape((Dm, Dm))
+            if index == 0:
+                Lam = D.asarray(u_Lambda[0]).reshape((Dm, Dm))
+                return [D.sum_product([Lam, x0], [["i", "j"], ["j"]], ["i"]), D.mul(Lam, -0.5)]
+            mu = D.asarray(u_mu[0]).reshape((Dm,))
+            mumu = dense(u_mu[1]).reshape((Dm, Dm))
+            xm = D.mul(x0.reshape((Dm, 1)), mu.reshape((1, Dm)))
+            t = D.add(D.sub(D.sub(x0x0, xm), xm.swap_last2()), mumu)
+            return [D.mul(t, -0.5), D.asarray(0.5)]
+        self._check_static(u_A if u_A is not None else [DArray.empty((Dm, Dm))], u_nu if u_nu is not None else [0.0])
+        if N < 2:
+            return [None, None]
+        # time sums of the chain's second moments
+        Sxx_head = D.sum_product([xx.slice_axis(0, 0, N - 1)], [["n", "i", "j"]], ["i", "j"])     # sum_{n<N-1} <x_n x_n^T>
+        Sxpxn = D.sum_product([xpxn], [["n", "i", "j"]], ["i", "j"])                              # sum_n <x_n x_{n+1}^T>
+        if index == 2:
+            nu = D.asarray(u_nu[0]).broadcast_to((Dm,))
+            # to a_d: [nu_d sum_n <x_{n+1,d} x_n>, -1/2 nu_d sum_n <x_n x_n^T>]
+            m0 = D.mul(Sxpxn.swap_last2(), nu.reshape((Dm, 1)))
+            m1 = D.mul(D.mul(Sxx_head.reshape((1, Dm, Dm)), nu.reshape((Dm, 1, 1))), -0.5)
+            return [m0, m1]
+        if index == 3:
+            A = u_A[0]
+            AA = dense(u_A[1])
+            dxx = D.sum_product([xx.slice_axis(0, 1, N).diag_view(1)], [["n", "d"]], ["d"], scale=-0.5)
+            a = D.sum_product([Sxpxn, A], [["i", "d"], ["d", "i"]], ["d"])
+            b = D.sum_product([Sxx_head, AA], [["i", "j"], ["d", "i", "j"]], ["d"], scale=-0.5)
+            return [D.add(D.add(dxx, a), b), DArray.full((Dm,), 0.5 * (N - 1))]
+        raise ValueError("Parent index out of bounds")
+
+
+class GaussianMarkovChain(ExponentialFamily):
+    """``GaussianMarkovChain(mu, Lambda, A, nu, n=None, name="")`` (gaussian_markov_chain.py:660-927)."""
+    moment_kind = "gaussian_markov_chain"
+
+    def __init__(self, mu, Lambda, A, nu, n=None, inputs=None, plates=None, name="", initialize=True):
+        if inputs is not None:
+            raise NotImplementedError("Input signals are not supported yet")
+        Lambda = ensure_wishart(Lambda)
+        Dm = Lambda.dims[0][-1]
+        mu = ensure_gaussian(mu, 1)
+        A = ensure_gaussian(A, 1)
+        nu = ensure_gamma(nu)
+        if tuple(A.dims[0]) != (Dm,) or tuple(A.plates[-1:]) != (Dm,):
+            raise ValueError("A must be a collection of D vectors of length D: plates (D,), shape (D,)")
+        if len(A.plates) > 1 or len(nu.plates) > 1:
+            if n is None:
+                n = (A.plates[-2] if len(A.plates) > 1 else nu.plates[-2]) + 1
+            raise NotImplementedError("Time-varying dynamics (plates (N-1, D)) are not supported yet")
+        if n is None:
+            raise ValueError("The length of the chain (keyword n) is required when the dynamics have no time plate")
+        self.N, self.D = int(n), int(Dm)
+        if plates not in (None, ()):
+            raise NotImplementedError("Plated chains are not supported yet")
+        dist = GaussianMarkovChainDistribution(self.N, self.D)
+        super().__init__(mu, Lambda, A, nu, dims=((self.N, Dm), (self.N, Dm, Dm), (self.N - 1, Dm, Dm)),
+                         distribution=dist, plates=(), name=name, initialize=initialize)
+
+    def _to_gaussian(self):
+        if getattr(self, "_as_gaussian", None) is None:
+            self._as_gaussian = _MarkovChainToGaussian(self, name=self.name)
+        return self._as_gaussian
+
+    def random(self):
+        raise NotImplementedError("Sampling from a Gaussian Markov chain is not implemented")
+
+
+class _MarkovChainToGaussian(Deterministic):
+    """The chain seen as N Gaussian vectors plated over time (gaussian_markov_chain.py:1988-2098): the
+    time axis of the parent's dims is the last plate here; the cross-time moment is not exposed."""
+    moment_kind = "gaussian"
+
+    def __init__(self, X, name=""):
+        self.N, self.D = X.N, X.D
+        super().__init__(X, dims=((X.D,), (X.D, X.D)), plates=tuple(X.plates) + (X.N,), name=name)
+
+    def _plates_from_parent(self, index):
+        return tuple(self.parents[0].plates) + (self.N,)
+
+    def _plates_to_parent(self, index):
+        return tuple(self.plates[:-1])
+
+    def _weights_to_parent(self, index, mask):
+        mask = np.asarray(mask)
+        return np.any(mask, axis=-1) if mask.ndim >= 1 else mask
+
+    def _compute_moments(self, u):
+        return [u[0], u[1]]
+
+    def message_to_parent(self, index):
+        # every child masks its own message, so the time axis can simply turn from plate into dim
+        m = self.message_from_children()
+        out = []
+        for i, mi in enumerate(m):
+            if mi is None:
+                out.append(None)
+                continue
+            want = (self.N,) + (self.D,) * (i + 1)
+            mi = D.asarray(mi)
+            if mi.ndim < len(want):
+                mi = mi.add_leading(len(want) - mi.ndim)
+            out.append(mi)
+        return out + [None]

@@ -9,3 +9,4 @@ from ..engine.wishart import Wishart                                          # 
 from ..engine.dirichlet import Dirichlet                                      # noqa: F401
 from ..engine.categorical import Categorical                                  # noqa: F401
 from ..engine.mixture import Mixture                                          # noqa: F401
+from ..engine.gmc import GaussianMarkovChain                                  # noqa: F401

@@ -142,6 +142,15 @@ int bpk_chol_solve(const double *U, int64_t batchU, const double *B, int64_t bat
 int bpk_chol_inv(const double *U, double *Ainv, int64_t batch, int D);
 int bpk_chol_logdet(const double *U, double *out, int64_t batch, int D);
 
+/* Block-tridiagonal SPD system of a Gaussian Markov chain (linalg.py:468-575 block_banded_solve,
+ * called from gaussian_markov_chain.py:89-123): A [batch][T][D][D] diagonal blocks, B [batch][T-1][D][D]
+ * super-diagonal blocks (sub-diagonal = transposes), y [batch][T][D].  Returns the diagonal blocks V
+ * [batch][T][D][D] and super-diagonal blocks C [batch][T-1][D][D] of the INVERSE, the solution x
+ * [batch][T][D] and log det [batch] — i.e. the Kalman/RTS smoother in information form.            */
+int bpk_block_banded_solve(const double *A, const double *B, const double *y,
+                           int64_t batch, int64_t T, int D,
+                           double *V, double *C, double *x, double *logdet, int check);
+
 /* ---- fused per-node moment kernels (seam 2) ---------------------------- */
 /* Gaussian / GaussianARD (gaussian.py:397-446, :672-706):
  *   Lambda = -2 phi1,  Cov = Lambda^-1,  u0 = Cov phi0,

@@ -433,6 +433,48 @@ class RefBackend:
         s[K:K + K * D] += (p.T @ y).ravel()
         s[K + K * D:K + K * D + K * D * D] += np.einsum("nk,ni,nj->kij", p, y, y).ravel()
 
+    # ---- block-tridiagonal SPD solver (csrc/gmc.cu) -------------------------------------------------
+    def block_banded_solve(self, A, B, y, batch, T, D, V, C, x, logdet, check=True):
+        """utils/linalg.py:468-575: forward block elimination storing the factor of every pivot block,
+        then the backward recursion for the solution and the diagonal / super-diagonal blocks of the
+        inverse (= the RTS smoother's covariances), restated with dense NumPy solves."""
+        self._launches += 1
+        Aa = _dense(A, (batch, T, D, D))
+        Ba = _dense(B, (batch, max(T - 1, 0), D, D)) if T > 1 else np.zeros((batch, 0, D, D))
+        ya = _dense(y, (batch, T, D))
+        Vo = _dense(V, (batch, T, D, D))
+        Co = _dense(C, (batch, max(T - 1, 0), D, D)) if T > 1 else None
+        xo = _dense(x, (batch, T, D))
+        ld = _dense(logdet, (batch,))
+        for b in range(batch):
+            Vt = np.empty((T, D, D))
+            Ct = np.empty((max(T - 1, 0), D, D))
+            xt = np.empty((T, D))
+            piv = Aa[b, 0].copy()
+            xt[0] = ya[b, 0]
+            ldet = 0.0
+            for n in range(T):
+                try:
+                    U = scipy.linalg.cho_factor(piv)[0]
+                except np.linalg.LinAlgError:
+                    raise NotPositiveDefinite("Matrix not positive definite")
+                ldet += 2 * np.sum(np.log(np.diag(U)))
+                Vt[n] = scipy.linalg.cho_solve((U, False), np.identity(D))       # inverse of the pivot block
+                if n < T - 1:
+                    Ct[n] = Vt[n] @ Ba[b, n]
+                    xt[n + 1] = ya[b, n + 1] - Ba[b, n].T @ (Vt[n] @ xt[n])
+                    piv = Aa[b, n + 1] - Ba[b, n].T @ Ct[n]
+                    piv = 0.5 * (piv + piv.T)
+            xt[T - 1] = Vt[T - 1] @ xt[T - 1]
+            for n in range(T - 2, -1, -1):
+                xt[n] = Vt[n] @ (xt[n] - Ba[b, n] @ xt[n + 1])
+                Vn = Vt[n] + Ct[n] @ Vt[n + 1] @ Ct[n].T
+                Ct[n] = -Ct[n] @ Vt[n + 1]
+                Vt[n] = 0.5 * (Vn + Vn.T)
+            Vo[b], xo[b], ld[b] = Vt, xt, ldet
+            if T > 1:
+                Co[b] = Ct
+
     # ---- device-resident VB loop of the factor model (csrc/pca_vb.cu) ------------------------------
     VB_FIELDS = ["mux", "ax", "muc", "a0", "b0", "ta0", "tb0", "sumsq", "ng", "reserved",
                  "w", "sww", "covc", "lamc", "logdetc", "phi0c", "gc",

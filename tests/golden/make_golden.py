@@ -216,8 +216,67 @@ def gmm_doc():
     save("gmm_doc", y=y, Z_init=Zi, L=Q.L[:Q.iter], iters=Q.iter)
 
 
+def block_banded_vectors():
+    """utils/linalg.py:468-575 block_banded_solve on random SPD block-tridiagonal systems
+    (same construction as utils/tests/test_linalg.py:112-182)."""
+    out = {}
+    rs = np.random.RandomState(11)
+    for tag, (N, D) in dict(a=(7, 3), b=(40, 5), c=(3, 1), d=(12, 16)).items():
+        # SPD by construction: diagonally dominant blocks
+        R = rs.randn(N * D, N * D)
+        full = R @ R.T + N * D * np.identity(N * D)
+        A = np.stack([full[n * D:(n + 1) * D, n * D:(n + 1) * D] for n in range(N)])
+        B = np.stack([full[n * D:(n + 1) * D, (n + 1) * D:(n + 2) * D] for n in range(N - 1)]) \
+            if N > 1 else np.zeros((0, D, D))
+        y = rs.randn(N, D)
+        V, C, x, ldet = linalg.block_banded_solve(A, B, y)
+        out.update({"A_" + tag: A, "B_" + tag: B, "y_" + tag: y, "V_" + tag: V, "C_" + tag: C, "x_" + tag: x,
+                    "ldet_" + tag: np.asarray(ldet)})
+    save("block_banded", **out)
+
+
+def lssm(name, M, N, D, mask_p=None, iters=6):
+    """doc/source/examples/lssm.rst:45-181 scaled down: X = GaussianMarkovChain(0, 1e-3 I, A, 1), F = Dot(C, X)."""
+    from bayespy.nodes import GaussianMarkovChain, Dot
+    np.random.seed(5)
+    # two noisy oscillators + random walk (lssm.rst:153-175 pattern)
+    w = 0.3
+    a = np.array([[np.cos(w), -np.sin(w), 0], [np.sin(w), np.cos(w), 0], [0, 0, 1.0]])
+    x = np.empty((N, 3))
+    x[0] = 10 * np.random.randn(3)
+    for n in range(N - 1):
+        x[n + 1] = a @ x[n] + [1, 1, 10] * np.random.randn(3) * 0.1
+    c = np.random.randn(M, 3)
+    y = x @ c.T + 0.5 * np.random.randn(N, M)
+    y = y.T                                              # (M, N)
+    alpha = Gamma(1e-5, 1e-5, plates=(D,), name="alpha")
+    A = GaussianARD(0, alpha, shape=(D,), plates=(D,), name="A")
+    X = GaussianMarkovChain(np.zeros(D), 1e-3 * np.identity(D), A, np.ones(D), n=N, name="X")
+    gamma = Gamma(1e-5, 1e-5, plates=(D,), name="gamma")
+    C = GaussianARD(0, gamma, shape=(D,), plates=(M, 1), name="C")
+    F = Dot(C, X, name="F")
+    C_init = np.random.RandomState(3).randn(M, 1, D)
+    C.initialize_from_value(C_init)
+    tau = Gamma(1e-5, 1e-5, name="tau")
+    Y = GaussianARD(F, tau, name="Y")
+    mask = True
+    if mask_p is not None:
+        mask = random.mask(M, N, p=mask_p)
+        Y.observe(y, mask=mask)
+    else:
+        Y.observe(y)
+    Q = VB(X, C, gamma, A, alpha, tau, Y)
+    Q.update(repeat=iters, verbose=False, tol=0)
+    out = dict(y=y, C_init=C_init, L=Q.L[:iters], mask=np.asarray(mask))
+    for nm, node in (("X", X), ("C", C), ("gamma", gamma), ("A", A), ("alpha", alpha), ("tau", tau)):
+        node_state(nm, node, out)
+    for node in Q.model:
+        out["l_" + node.name] = Q.l[node][:iters]
+    save(name, **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["quickstart", "pca", "linalg", "summul", "dist", "gmm"]
+    which = sys.argv[1:] or ["quickstart", "pca", "linalg", "summul", "dist", "gmm", "gmc"]
     if "quickstart" in which:
         quickstart()
     if "pca" in which:
@@ -233,3 +292,7 @@ if __name__ == "__main__":
     if "gmm" in which:
         gmm("gmm_small", 300, 3, 5)
         gmm_doc()
+    if "gmc" in which:
+        block_banded_vectors()
+        lssm("lssm_small", 6, 40, 3)
+        lssm("lssm_masked", 6, 40, 3, mask_p=0.7)

@@ -1,0 +1,120 @@
+"""Gaussian Markov chain: bpk_block_banded_solve against the reference's
+utils.linalg.block_banded_solve, and a small linear state-space model (lssm.rst:45-181 scaled down)
+against the reference's own VB run — lower-bound trajectory and every node's moments."""
+import numpy as np
+import pytest
+
+from conftest import golden
+from bayespy_b200.darray import DArray
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
+def test_block_banded_solve_golden(backend, tag):
+    g = golden("block_banded")
+    A, B, y = g["A_" + tag], g["B_" + tag], g["y_" + tag]
+    T, Dm = y.shape
+    Ad, yd = DArray.from_numpy(A), DArray.from_numpy(y)
+    Bd = DArray.from_numpy(B) if T > 1 else DArray.empty((1,))
+    V, C, x, ld = DArray.empty((T, Dm, Dm)), DArray.empty((max(T - 1, 1), Dm, Dm)), DArray.empty((T, Dm)), DArray.empty(())
+    backend.block_banded_solve(Ad.ptr, Bd.ptr, yd.ptr, 1, T, Dm, V.ptr, C.ptr, x.ptr, ld.ptr, True)
+    np.testing.assert_allclose(V.numpy(), g["V_" + tag], rtol=1e-9, atol=1e-12)
+    if T > 1:
+        np.testing.assert_allclose(C.numpy()[:T - 1], g["C_" + tag], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(x.numpy(), g["x_" + tag], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(float(ld.numpy()), float(g["ldet_" + tag]), rtol=1e-12)
+
+
+def test_block_banded_solve_batched_and_dense_inverse(backend):
+    """Several chains in one launch, checked against the dense inverse of the assembled matrix."""
+    rs = np.random.RandomState(2)
+    batch, T, Dm = 3, 9, 4
+    A = np.empty((batch, T, Dm, Dm)); B = np.empty((batch, T - 1, Dm, Dm)); y = rs.randn(batch, T, Dm)
+    dense = []
+    for b in range(batch):
+        R = rs.randn(T * Dm, T * Dm)
+        full = R @ R.T + T * Dm * np.identity(T * Dm)
+        for n in range(T):
+            A[b, n] = full[n * Dm:(n + 1) * Dm, n * Dm:(n + 1) * Dm]
+            if n < T - 1:
+                B[b, n] = full[n * Dm:(n + 1) * Dm, (n + 1) * Dm:(n + 2) * Dm]
+        P = np.zeros_like(full)
+        for n in range(T):
+            P[n * Dm:(n + 1) * Dm, n * Dm:(n + 1) * Dm] = A[b, n]
+            if n < T - 1:
+                P[n * Dm:(n + 1) * Dm, (n + 1) * Dm:(n + 2) * Dm] = B[b, n]
+                P[(n + 1) * Dm:(n + 2) * Dm, n * Dm:(n + 1) * Dm] = B[b, n].T
+        dense.append(P)
+    d = [DArray.from_numpy(a) for a in (A, B, y)]
+    V, C, x, ld = DArray.empty((batch, T, Dm, Dm)), DArray.empty((batch, T - 1, Dm, Dm)), DArray.empty((batch, T, Dm)), \
+        DArray.empty((batch,))
+    backend.block_banded_solve(d[0].ptr, d[1].ptr, d[2].ptr, batch, T, Dm, V.ptr, C.ptr, x.ptr, ld.ptr, True)
+    Vn, Cn, xn, ldn = V.numpy(), C.numpy(), x.numpy(), ld.numpy()
+    for b in range(batch):
+        Pinv = np.linalg.inv(dense[b])
+        for n in range(T):
+            np.testing.assert_allclose(Vn[b, n], Pinv[n * Dm:(n + 1) * Dm, n * Dm:(n + 1) * Dm], rtol=1e-8, atol=1e-12)
+            if n < T - 1:
+                np.testing.assert_allclose(Cn[b, n], Pinv[n * Dm:(n + 1) * Dm, (n + 1) * Dm:(n + 2) * Dm], rtol=1e-8,
+                                           atol=1e-12)
+        np.testing.assert_allclose(xn[b].ravel(), Pinv @ y[b].ravel(), rtol=1e-8, atol=1e-12)
+        np.testing.assert_allclose(ldn[b], np.linalg.slogdet(dense[b])[1], rtol=1e-11)
+
+
+def test_block_banded_not_spd(backend):
+    from bayespy_b200 import _bpk
+    from oracle import bpk_ref
+    T, Dm = 4, 3
+    A = np.tile(np.identity(Dm), (T, 1, 1))
+    A[2] = -np.identity(Dm)
+    B = np.zeros((T - 1, Dm, Dm)); y = np.ones((T, Dm))
+    d = [DArray.from_numpy(a) for a in (A, B, y)]
+    V, C, x, ld = DArray.empty((T, Dm, Dm)), DArray.empty((T - 1, Dm, Dm)), DArray.empty((T, Dm)), DArray.empty(())
+    with pytest.raises((_bpk.NotPositiveDefinite, bpk_ref.NotPositiveDefinite)):
+        backend.block_banded_solve(d[0].ptr, d[1].ptr, d[2].ptr, 1, T, Dm, V.ptr, C.ptr, x.ptr, ld.ptr, True)
+
+
+def _lssm(g, M, N, Dm, masked):
+    from bayespy_b200.nodes import GaussianARD, GaussianMarkovChain, Gamma, Dot
+    from bayespy_b200.inference import VB
+    alpha = Gamma(1e-5, 1e-5, plates=(Dm,), name="alpha")
+    A = GaussianARD(0, alpha, shape=(Dm,), plates=(Dm,), name="A")
+    X = GaussianMarkovChain(np.zeros(Dm), 1e-3 * np.identity(Dm), A, np.ones(Dm), n=N, name="X")
+    gamma = Gamma(1e-5, 1e-5, plates=(Dm,), name="gamma")
+    C = GaussianARD(0, gamma, shape=(Dm,), plates=(M, 1), name="C")
+    F = Dot(C, X, name="F")
+    C.initialize_from_value(g["C_init"])
+    tau = Gamma(1e-5, 1e-5, name="tau")
+    Y = GaussianARD(F, tau, name="Y")
+    if masked:
+        Y.observe(g["y"], mask=g["mask"])
+    else:
+        Y.observe(g["y"])
+    Q = VB(X, C, gamma, A, alpha, tau, Y)
+    return Q, dict(X=X, C=C, gamma=gamma, A=A, alpha=alpha, tau=tau)
+
+
+@pytest.mark.parametrize("name,masked", [("lssm_small", False), ("lssm_masked", True)])
+def test_lssm_matches_reference(backend, name, masked):
+    g = golden(name)
+    M, N, Dm = 6, 40, 3
+    Q, nodes = _lssm(g, M, N, Dm, masked)
+    assert F_plates(Q) == (M, N)
+    iters = len(g["L"])
+    Q.update(repeat=iters, verbose=False, tol=0)
+    np.testing.assert_allclose(Q.L[:iters], g["L"], rtol=1e-8)
+    for node in Q.model:
+        np.testing.assert_allclose(Q.l[node][:iters], g["l_" + node.name], rtol=1e-6, atol=1e-6, err_msg=node.name)
+    for nm, node in nodes.items():
+        for i in range(len(node.u)):
+            np.testing.assert_allclose(np.asarray(node.u[i]), g["%s_u%d" % (nm, i)], rtol=1e-6, atol=1e-9,
+                                       err_msg="%s.u[%d]" % (nm, i))
+        for i in range(len(node.phi)):
+            ref = g["%s_phi%d" % (nm, i)]
+            np.testing.assert_allclose(np.broadcast_to(np.asarray(node.phi[i]), ref.shape), ref, rtol=1e-6, atol=1e-9,
+                                       err_msg="%s.phi[%d]" % (nm, i))
+        np.testing.assert_allclose(np.broadcast_to(np.asarray(node.g), np.shape(g[nm + "_g"])), g[nm + "_g"], rtol=1e-6,
+                                   atol=1e-8, err_msg=nm + ".g")
+
+
+def F_plates(Q):
+    return tuple(Q["Y"].plates)
