@@ -294,7 +294,7 @@ def run_gpu(args):
                 "note": "per step: Y.observe(pinned host array) + Q.update() + read of L"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "pca_xsweep_kernel", "kernel_ms": kern_avg,
+                     "traffic": traffic, "kernel": "pca_xsweep_ws_kernel (one fused launch per VB sweep: data pass + grid reduction + node updates + bound)", "kernel_ms": kern_avg,
                      "kernel_share_of_step": kern_avg / (ms_max / steps),
                      "algorithmic_bytes_per_col": BYTES_PER_COL, "peak_source": peak_src,
                      "fp64_tflops": FLOPS_PER_COL * n_local_max / (kern_avg * 1e-3) / 1e12},
