@@ -328,9 +328,9 @@ __device__ __forceinline__ void grid_wait(unsigned int *bar, unsigned int &epoch
 template <int NT, int STAGES, int DIST, bool COMPUTE_X, bool FUSED>
 __global__ void __launch_bounds__(2 * WS_PAIRS * 32, 1)
 pca_xsweep_ws_kernel(const __grid_constant__ CUtensorMap tmapY, int64_t M, int64_t N, int K,
-                     const double *__restrict__ A, const double *__restrict__ bvec,
-                     double *__restrict__ X, double *__restrict__ partial, int64_t ntiles,
-                     const int *__restrict__ stop, unsigned int *gbar, const __grid_constant__ PcaVbArgs vb,
+                     const double *A, const double *bvec,
+                     double *__restrict__ X, double *partial, int64_t ntiles,
+                     const int *stop, unsigned int *gbar, const __grid_constant__ PcaVbArgs vb,
                      size_t vb_sm_doubles) {
     constexpr int T = WS_PAIRS * NT, NS = NT / 4, CB = NT / 8, NBOX = T / WS_BOXC, STG = NBOX * WS_BOX;
     static_assert(DIST >= 1 && DIST < STAGES, "prefetch distance must leave one stage for the consumers");
@@ -348,11 +348,13 @@ pca_xsweep_ws_kernel(const __grid_constant__ CUtensorMap tmapY, int64_t M, int64
     const bool is_x = w < WS_PAIRS;
     const int p = w & (WS_PAIRS - 1);
 
+    unsigned int epoch = 0;                       // grid-barrier epoch (FUSED); thread 0's copy is the one used
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 2 * WS_PAIRS); }
         for (int i = 0; i < 2 * WS_PAIRS; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xfree[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmapY) : "memory");
+        if (FUSED) epoch = *(volatile unsigned int *)&gbar[1];
     }
     __syncthreads();
 
@@ -374,16 +376,26 @@ pca_xsweep_ws_kernel(const __grid_constant__ CUtensorMap tmapY, int64_t M, int64
     const int64_t xtra_tile = ((ntiles + stride - 1) / stride - skip + xtra) * stride;     // a tile of CTA 0's list
     auto tile_of = [&](int64_t i) -> int64_t { return (has_xtra && i == ntl - 1) ? xtra_tile : first + i * stride; };
 
-    auto issue = [&](int64_t j) {        // lanes 0..NBOX-1 of warp 0: one TMA box each
+    // FUSED: the launch runs vb.niter whole sweeps.  The mbarrier phases simply keep counting across sweeps
+    // (tbase = tiles this CTA has consumed so far), so nothing is re-initialised between them.
+    const int niter = FUSED ? vb.niter : 1;
+    int64_t tbase = 0;
+    auto issue = [&](int64_t jl) {       // lanes 0..NBOX-1 of warp 0: one TMA box each
+        const int64_t j = tbase + jl;
         const int slot = (int)(j % STAGES);
         if (j >= STAGES) mbar_wait(&empty[slot], (uint32_t)((j / STAGES - 1) & 1));
-        const int64_t n0 = tile_of(j) * T;
+        const int64_t n0 = tile_of(jl) * T;
         if (lane == 0) mbar_expect_tx(&full[slot], (uint32_t)(STG * sizeof(double)));
         __syncwarp();
         if (lane < NBOX)
             tma_load_2d(Ysm + (size_t)slot * STG + lane * WS_BOX, &tmapY, (int)(n0 + lane * WS_BOXC), 0, &full[slot]);
     };
 
+    for (int it = 0; it < niter; ++it, tbase += ntl) {
+    if (it > 0) {
+        if (*(volatile const int *)stop) break;                       // converged inside this launch (uniform)
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");    // ring was scratch for the tail: order before TMA
+    }
     if (is_x) {
         double afrag[2][16];
         double bk[2] = {0.0, 0.0};
@@ -393,23 +405,24 @@ pca_xsweep_ws_kernel(const __grid_constant__ CUtensorMap tmapY, int64_t M, int64
 #pragma unroll
                 for (int ms = 0; ms < 16; ++ms) {
                     int k = kb * 8 + gr, m = (ms >> 1) * 8 + 2 * tg + (ms & 1);
-                    afrag[kb][ms] = (k < K && m < M) ? A[(int64_t)k * M + m] : 0.0;
+                    afrag[kb][ms] = (k < K && m < M) ? __ldcg(A + (int64_t)k * M + m) : 0.0;   // rewritten by the tail of every sweep
                 }
             if (bvec) {
-                if (gr < K) bk[0] = bvec[gr];
-                if (8 + gr < K) bk[1] = bvec[8 + gr];
+                if (gr < K) bk[0] = __ldcg(bvec + gr);
+                if (8 + gr < K) bk[1] = __ldcg(bvec + 8 + gr);
             }
         }
         if (w == 0)
             for (int64_t j = 0; j < DIST && j < ntl; ++j) issue(j);
         for (int64_t i = 0; i < ntl; ++i) {
             if (w == 0 && i + DIST < ntl) issue(i + DIST);
-            const int slot = (int)(i % STAGES), b = (int)(i & 1);
+            const int64_t ig = tbase + i;                 // tiles consumed by this CTA since the launch began
+            const int slot = (int)(ig % STAGES), b = (int)(ig & 1);
             const int c0 = p * NT;
             const int64_t nbase = tile_of(i) * T + c0;
             double *Xs = Xsm + ((size_t)(p * 2 + b) * NT) * PCA_LDX;
             if (COMPUTE_X) {
-                mbar_wait(&full[slot], (uint32_t)((i / STAGES) & 1));
+                mbar_wait(&full[slot], (uint32_t)((ig / STAGES) & 1));
                 const double *Ys = Ysm + (size_t)slot * STG;
                 // two partial sums over the m blocks per accumulator: 4*CB independent DMMA chains
                 double acc[2][2][CB][2];
@@ -431,7 +444,7 @@ pca_xsweep_ws_kernel(const __grid_constant__ CUtensorMap tmapY, int64_t M, int64
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[slot]);           // this warp no longer reads the Y stage
-                if (i >= 2) mbar_wait(&xfree[p * 2 + b], (uint32_t)(((i >> 1) - 1) & 1));
+                if (ig >= 2) mbar_wait(&xfree[p * 2 + b], (uint32_t)(((ig >> 1) - 1) & 1));
 #pragma unroll
                 for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
@@ -446,10 +459,10 @@ pca_xsweep_ws_kernel(const __grid_constant__ CUtensorMap tmapY, int64_t M, int64
                         }
             } else {
                 if (lane == 0) {
-                    mbar_wait(&full[slot], (uint32_t)((i / STAGES) & 1));
+                    mbar_wait(&full[slot], (uint32_t)((ig / STAGES) & 1));
                     mbar_arrive(&empty[slot]);
                 }
-                if (i >= 2) mbar_wait(&xfree[p * 2 + b], (uint32_t)(((i >> 1) - 1) & 1));
+                if (ig >= 2) mbar_wait(&xfree[p * 2 + b], (uint32_t)(((ig >> 1) - 1) & 1));
                 for (int e = lane; e < NT * PCA_KP; e += 32) {
                     int nl = e >> 4, k = e & 15;
                     Xs[nl * PCA_LDX + k] = (nbase + nl < N && k < K) ? X[(nbase + nl) * K + k] : 0.0;
@@ -470,12 +483,13 @@ pca_xsweep_ws_kernel(const __grid_constant__ CUtensorMap tmapY, int64_t M, int64
 #pragma unroll
         for (int i = 0; i < 3; ++i) sxx[i][0] = sxx[i][1] = 0.0;
         for (int64_t i = 0; i < ntl; ++i) {
-            const int slot = (int)(i % STAGES), b = (int)(i & 1);
+            const int64_t ig = tbase + i;
+            const int slot = (int)(ig % STAGES), b = (int)(ig & 1);
             const int c0 = p * NT;
             const double *Ys = Ysm + (size_t)slot * STG;
             const double *Xs = Xsm + ((size_t)(p * 2 + b) * NT) * PCA_LDX;
-            mbar_wait(&full[slot], (uint32_t)((i / STAGES) & 1));
-            mbar_wait(&xfull[p * 2 + b], (uint32_t)((i >> 1) & 1));
+            mbar_wait(&full[slot], (uint32_t)((ig / STAGES) & 1));
+            mbar_wait(&xfull[p * 2 + b], (uint32_t)((ig >> 1) & 1));
             if (lane < PCA_KP) {
 #pragma unroll
                 for (int nl = 0; nl < NT; ++nl) sx += Xs[nl * PCA_LDX + lane];
@@ -528,11 +542,9 @@ pca_xsweep_ws_kernel(const __grid_constant__ CUtensorMap tmapY, int64_t M, int64
     }
     if (FUSED) {
         if (blockIdx.x == 0) vb_stamp(vb.dbg, 1);
-        unsigned int epoch = 0;
-        if (threadIdx.x == 0) epoch = *(volatile unsigned int *)&gbar[1];
-        epoch = __shfl_sync(0xffffffffu, epoch, 0);      // thread 0's value is the only one used
+        const int nops_it = (it == niter - 1) ? vb.nops_last : vb.nops;
         grid_arrive(gbar, epoch);
-        if (blockIdx.x == 0 && skip > 0) pca_vb_ops(vb, smem, vb_sm_doubles, true);      // warm the instruction cache
+        if (blockIdx.x == 0 && skip > 0 && (it == 0 || vb.dry_every)) pca_vb_ops(vb, smem, vb_sm_doubles, true, nops_it);   // warm the instruction cache
         grid_wait(gbar, epoch);
         if (blockIdx.x == 0) vb_stamp(vb.dbg, 2);
         // distributed, fixed-order reduction over the CTAs: CTA c owns elements [c*per, (c+1)*per)
@@ -552,10 +564,12 @@ pca_xsweep_ws_kernel(const __grid_constant__ CUtensorMap tmapY, int64_t M, int64
         grid_barrier(gbar, epoch);
         if (blockIdx.x == 0) {
             vb_stamp(vb.dbg, 4);
-            pca_vb_ops(vb, smem, vb_sm_doubles);
+            pca_vb_ops(vb, smem, vb_sm_doubles, false, nops_it);
             vb_stamp(vb.dbg, 5);
         }
+        if (it + 1 < niter) grid_barrier(gbar, epoch);      // the next sweep's A, b (and the stop word) are visible to every CTA
     }
+    }   // sweeps of this launch
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link dependency)
@@ -623,7 +637,7 @@ static int pca_launch_ws(const double *Y, int64_t M, int64_t N, int K, const dou
         return BPK_OK;
     }
     PcaVbArgs none;
-    none.nops = 0;
+    none.nops = 0; none.nops_last = 0; none.niter = 1; none.dry_every = 0;
     auto kern = pca_xsweep_ws_kernel<NT, STAGES, DIST, COMPUTE_X, false>;
     BPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     BPK_LAUNCH(kern, grid, 2 * WS_PAIRS * 32, smem, tmap, M, N, K, A, b, X, partial, ntiles, stop, (unsigned int *)nullptr, none, (size_t)0);
@@ -707,6 +721,11 @@ static int pca_launch(const double *Y, int64_t M, int64_t N, int K, const double
     int total = (int)(M * K + K * K + K);
     BPK_LAUNCH(pca_stats_final_kernel, (total + 127) / 128, 128, 0, partial, grid, (int)M, K, stats);
     return BPK_OK;
+}
+
+// will bpk_pca_xsweep use the TMA kernel for this input (16-byte aligned rows)?
+bool pca_ws_available(const double *Y, int64_t N) {
+    return (N % 2 == 0) && (((uintptr_t)Y & 15u) == 0) && pca_variant() >= 0;
 }
 
 // resident VB loop (pca_vb.cu): sweep only, per-CTA partials left in scratch

@@ -93,6 +93,8 @@ extern "C" int bpk_pca_vb_run(const double *Y, int64_t M, int64_t N, int K, doub
     a.st = state; a.partial = nullptr; a.nparts = 0; a.local_stats = nranks > 1;
     a.Lhist = Lhist; a.cap = cap; a.ctrl = ctrl; a.nops = 0;
     a.xranks = 1; a.xrank = 0;
+    a.niter = 1; a.nops_last = 0;
+    a.dry_every = getenv("BPK_VB_DRY_FIRST_ONLY") ? 0 : 1;
     a.dbg = nullptr;
     if (getenv("BPK_VB_DEBUG")) {
         if (!g_vb_dbg) {
@@ -117,6 +119,40 @@ extern "C" int bpk_pca_vb_run(const double *Y, int64_t M, int64_t N, int K, doub
         }
         // One launch per sweep: the small ops that follow an XSWEEP (up to the next one) ride in the
         // tail of the sweep kernel; only what precedes the first sweep of the run is a launch of its own.
+        // Whole chunk in ONE launch when the program has a single XSWEEP per iteration and the exchange (if any)
+        // happens inside the kernel: ops after the sweep (+ the ops that precede the next one) form the tail.
+        {
+            int nx = 0, kx = -1;
+            for (int i = 0; i < nops; ++i)
+                if (ops[i] == BPK_VBOP_XSWEEP) { ++nx; kx = i; }
+            const bool loopable = nx == 1 && (nranks == 1 || p2p) && nops - 1 <= VB_MAXOPS && niter >= 1 &&
+                                  pca_ws_available(Y, N) && !getenv("BPK_VB_NO_LOOP");
+            if (loopable) {
+                for (int i = 0; i < nops; ++i)
+                    if (ops[i] < BPK_VBOP_XSWEEP || ops[i] > BPK_VBOP_BOUND || (ops[i] == BPK_VBOP_STATS && i < kx))
+                        return bpk_set_error(BPK_EINVAL, "bpk_pca_vb_run: bad opcode %d at %d", ops[i], i);
+                for (int i = 0; i < kx; ++i) a.ops[a.nops++] = ops[i];          // head of the first sweep
+                int rc = vb_launch_small(a, smem);
+                if (rc) return rc;
+                PcaVbArgs tail = a;
+                tail.nops = 0;
+                for (int i = kx + 1; i < nops; ++i) tail.ops[tail.nops++] = ops[i];
+                tail.nops_last = tail.nops;
+                for (int i = 0; i < kx; ++i) tail.ops[tail.nops++] = ops[i];
+                tail.niter = niter;
+                int tid = -1;
+                if (g_vb_timer_pos < g_vb_ntimers) tid = g_vb_timers[g_vb_timer_pos++];
+                if (tid >= 0) bpk_timer_record(tid, 0);
+                double *partial = nullptr;
+                int nparts = 0, tail_done = 0;
+                rc = pca_xsweep_partials(Y, M, N, K, state + off[F_A], state + off[F_BX], X, ctrl + 1, &partial, &nparts,
+                                         &tail, &tail_done);
+                if (rc) return rc;
+                if (tid >= 0) bpk_timer_record(tid, 1);
+                if (!tail_done) return bpk_set_error(BPK_ECUDA, "bpk_pca_vb_run: fused sweep kernel was not used");
+                return BPK_OK;
+            }
+        }
         std::vector<int> seq;
         seq.reserve((size_t)niter * nops);
         for (int it = 0; it < niter; ++it)
@@ -147,6 +183,8 @@ extern "C" int bpk_pca_vb_run(const double *Y, int64_t M, int64_t N, int K, doub
                 ++j;
                 if (seq[j - 1] == BPK_VBOP_STATS && nranks > 1 && !p2p) { exchange = true; break; }
             }
+            tail.nops_last = tail.nops;
+            tail.niter = 1;
             int tid = -1;
             if (g_vb_timer_pos < g_vb_ntimers) tid = g_vb_timers[g_vb_timer_pos++];
             if (tid >= 0) bpk_timer_record(tid, 0);

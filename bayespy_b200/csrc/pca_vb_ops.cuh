@@ -15,7 +15,7 @@ enum {
     F_AL_PHI0, F_AL_PHI1, F_AL_U0, F_AL_U1, F_AL_G,
     F_TAU_PHI0, F_TAU_PHI1, F_TAU_U0, F_TAU_U1, F_TAU_G,
     F_COVX, F_LAMX, F_LOGDETX, F_A, F_BX,
-    F_STATS, F_SXXT, F_LPREV, F_STATS_LOCAL,
+    F_STATS, F_SXXT, F_LPREV, F_STATS_LOCAL, F_PHI1X, F_PHI1C,
     F_COUNT
 };
 
@@ -25,7 +25,7 @@ __attribute__((unused)) static const char *const kFieldNames[F_COUNT] = {
     "al_phi0", "al_phi1", "al_u0", "al_u1", "al_g",
     "tau_phi0", "tau_phi1", "tau_u0", "tau_u1", "tau_g",
     "covx", "lamx", "logdetx", "A", "bx",
-    "stats", "sxxt", "lprev", "stats_local",
+    "stats", "sxxt", "lprev", "stats_local", "phi1x", "phi1c",
 };
 
 __device__ __forceinline__ void vb_stamp(unsigned long long *dbg, int slot) {
@@ -44,7 +44,7 @@ __host__ __device__ inline void pca_vb_offsets(int M, int K, int64_t *off /* [F_
         K, K, K, K, K,
         1, 1, 1, 1, 1,
         KK, KK, 1, MK, K,
-        NS, KK, 1, NS,
+        NS, KK, 1, NS, KK, KK,
     };
     int64_t o = 0;
     for (int f = 0; f < F_COUNT; ++f) { off[f] = o; o += size[f]; }
@@ -68,6 +68,9 @@ struct PcaVbArgs {
     unsigned long long *dbg; // optional %globaltimer stamps (tools/vb_tail_timing.py), NULL in production
     int xranks, xrank;       // > 1: STATS all-reduces over the peer-memory windows below (no NCCL call)
     double *xwin[BPK_XCHG_MAXRANKS];
+    int niter;               // fused sweep kernel: sweeps per launch; ops[0..nops) follow every sweep but the last,
+    int dry_every;           // 1: CTA 0 dry-runs the tail in every sweep of the launch, 0: only in the first
+    int nops_last;           // ops[0..nops_last) the last one (the ops of the next sweep's head are dropped)
     int nops;
     int ops[VB_MAXOPS];
 };
@@ -109,7 +112,7 @@ __device__ __forceinline__ double vb_E2(const double *st, const int64_t *o, int 
 // (index arithmetic becomes shifts; this code runs once per launch from a cold instruction cache, so small
 // and fast matters more than general).
 template <int KC, int MC>
-static __device__ __noinline__ void pca_vb_ops_t(const PcaVbArgs &p, double *sm, size_t sm_doubles, bool dry) {
+static __device__ __noinline__ void pca_vb_ops_t(const PcaVbArgs &p, double *sm, size_t sm_doubles, bool dry, int nops_run) {
     const int VBT = blockDim.x;
     const int M = MC ? MC : p.M, K = KC ? KC : p.K, K2 = 2 * K, ldg = K2 + 1, t = threadIdx.x;
     double *G = sm, *rowk = G + (size_t)K * ldg, *colk = rowk + K2, *piv = colk + K, *red = piv + K, *scal = red + 32;
@@ -138,7 +141,7 @@ static __device__ __noinline__ void pca_vb_ops_t(const PcaVbArgs &p, double *sm,
     const double Ng = st[o[F_NG]];
 #define CINV(i, j) G[(i) * ldg + K + (j)]
 
-    for (int ip = 0; ip < p.nops; ++ip) {
+    for (int ip = 0; ip < nops_run; ++ip) {
         __syncthreads();
         if (*stop) break;
         const int op = p.ops[ip];
@@ -219,6 +222,7 @@ static __device__ __noinline__ void pca_vb_ops_t(const PcaVbArgs &p, double *sm,
                 if (j < K) {
                     v = tau * st[o[F_SWW] + i * K + j] + (i == j ? st[o[F_AX] + i] : 0.0);
                     st[o[F_LAMX] + i * K + j] = v;
+                    st[o[F_PHI1X] + i * K + j] = -0.5 * v;          // natural parameter phi_1 of q(X) (shared by all columns)
                 } else v = (j - K == i) ? 1.0 : 0.0;
                 G[i * ldg + j] = v;
             }
@@ -246,6 +250,7 @@ static __device__ __noinline__ void pca_vb_ops_t(const PcaVbArgs &p, double *sm,
                 if (j < K) {
                     v = tau * st[o[F_SXXT] + i * K + j] + (i == j ? st[o[F_AL_U0] + i] : 0.0);
                     st[o[F_LAMC] + i * K + j] = v;
+                    st[o[F_PHI1C] + i * K + j] = -0.5 * v;
                 } else v = (j - K == i) ? 1.0 : 0.0;
                 G[i * ldg + j] = v;
             }
@@ -395,9 +400,11 @@ static __device__ __noinline__ void pca_vb_ops_t(const PcaVbArgs &p, double *sm,
 #undef CINV
 }
 
-static __device__ __forceinline__ void pca_vb_ops(const PcaVbArgs &p, double *sm, size_t sm_doubles, bool dry = false) {
-    if (p.M == PCA_MP && p.K == PCA_KP) pca_vb_ops_t<PCA_KP, PCA_MP>(p, sm, sm_doubles, dry);
-    else pca_vb_ops_t<0, 0>(p, sm, sm_doubles, dry);
+static __device__ __forceinline__ void pca_vb_ops(const PcaVbArgs &p, double *sm, size_t sm_doubles, bool dry = false,
+                                                  int nops_run = -1) {
+    if (nops_run < 0) nops_run = p.nops;
+    if (p.M == PCA_MP && p.K == PCA_KP) pca_vb_ops_t<PCA_KP, PCA_MP>(p, sm, sm_doubles, dry, nops_run);
+    else pca_vb_ops_t<0, 0>(p, sm, sm_doubles, dry, nops_run);
 }
 
 
@@ -407,3 +414,4 @@ static __device__ __forceinline__ void pca_vb_ops(const PcaVbArgs &p, double *sm
 int pca_xsweep_partials(const double *Y, int64_t M, int64_t N, int K, const double *A, const double *b,
                         double *X, const int *stop, double **partial_out, int *nparts_out,
                         const PcaVbArgs *tail, int *tail_done);
+bool pca_ws_available(const double *Y, int64_t N);

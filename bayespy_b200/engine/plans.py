@@ -77,6 +77,7 @@ class FactorModelPlan:
         self.world = parallel.world()
         self.Ng = int(round(float(np.sum(parallel.allgather_scalar(self.N))))) if self.world > 1 else self.N
         self.kernel_timers = None     # bench.py: list of timer ids to record around the sweep kernel
+        self.kernel_timer_log = []    # [(timer ids used by a chunk, sweeps the chunk ran)]
         self._timer_pos = 0
         self._stats = None            # (col._version, DArray)
         self._sumsq = None            # (Y._version, DArray[2])
@@ -400,7 +401,12 @@ class FactorModelPlan:
         order = [n for n in order if n is not Y and n is not self.F]
         if set(order) != latent or len(order) != len(latent):
             return None
-        self._hyper = self._resident_hyper()
+        hk = tuple(id(pp) for n in (col, row, alpha, tau) for pp in getattr(n, "parents", ())) + (id(alpha), id(tau))
+        if getattr(self, "_hyper_key", None) != hk:
+            self._hyper = self._resident_hyper()
+            self._hyper_key = hk
+            self._hsig = None if self._hyper is None else \
+                tuple(np.asarray(v, dtype=np.float64).tobytes() for _, v in sorted(self._hyper.items()))
         if self._hyper is None:
             return None
         V = _bpk.VBOP
@@ -475,7 +481,7 @@ class FactorModelPlan:
         # state vector and the X buffer of that run are still exact — skip the host-side rebuild
         alpha_n = self.row.parents[1]
         watched = [self.Y, self.col, self.row] + [n for n in (alpha_n, self.tau) if isinstance(n, Gamma)]
-        hsig = tuple(np.asarray(v, dtype=np.float64).tobytes() for _, v in sorted(self._hyper.items()))
+        hsig = self._hsig
         cache = getattr(self, "_res_cache", None)
         if cache is not None and cache["versions"] == [n._version for n in watched] and cache["hsig"] == hsig \
                 and cache["nodes"] == [id(n) for n in watched] and not (check and np.isnan(lprev) and vb.iter > 0):
@@ -504,10 +510,15 @@ class FactorModelPlan:
                           Lh.ptr, chunk, ctrl.ptr)
             c = ctrl.numpy().view(np.int32)       # blocks until the chunk has run
             if self.kernel_timers is not None:
-                self._timer_pos += be.pca_vb_timers_used()
+                used = be.pca_vb_timers_used()
+                # one timer may bracket several sweeps (the whole chunk is one launch when it can be)
+                self.kernel_timer_log.append((self.kernel_timers[self._timer_pos:self._timer_pos + used], None))
+                self._timer_pos += used
                 be.pca_vb_set_timers([])
             dt = (time.time() - t0)
             n_it, stop, err = int(c[0]), int(c[1]), int(c[2])
+            if self.kernel_timers is not None and self.kernel_timer_log and self.kernel_timer_log[-1][1] is None:
+                self.kernel_timer_log[-1] = (self.kernel_timer_log[-1][0], n_it)
             if err & 1:
                 raise _bpk.NotPositiveDefinite("Matrix not positive definite")
             if err & 2:
@@ -545,10 +556,41 @@ class FactorModelPlan:
             if n_it == 0:
                 break
         if done > 0:
-            self._resident_publish(state, lay, X, order)
+            if cache is not None and state is cache["state"]:
+                self._resident_republish(X)
+            else:
+                self._resident_publish(state, lay, X, order)
             self._res_cache = dict(state=state, lay=lay, X=X, hsig=hsig, nodes=[id(n) for n in watched],
                                    versions=[n._version for n in watched])
         return converged
+
+    def _resident_republish(self, X):
+        """Same state vector and X buffer as the previous resident run: the node objects already view them;
+        only what caches derived values has to be renewed (no kernel launches)."""
+        col, row, tau = self.col, self.row, self.tau
+        N, K = self.N, self.K
+        fz = col._fused
+        Lam, logdet, cov = fz["Lam"], fz["logdet"], fz["cov"]
+
+        def phi0_fn():
+            return D.sum_product([Lam, X], [["i", "j"], ["o", "n", "j"]], ["o", "n", "i"])
+
+        def g_fn():
+            q = D.sum_product([X, Lam, X], [["o", "n", "i"], ["i", "j"], ["o", "n", "j"]], ["o", "n"])
+            return D.axpby(-0.5, q, 0.5, logdet)
+        col.phi = [LazyArray((1, N, K), phi0_fn), col.phi[1]]
+        col.u = [X, FactoredSecondMoment(X, cov, (K,))]
+        col.g = LazyArray((1, N), g_fn)
+        col._version += 1
+        self._stats = (col._version, self._stats[1])
+        row.u = [row.u[0], FactoredSecondMoment(row.u[0], row.u[1].cov, (K,))]
+        row._version += 1
+        alpha = row.parents[1]
+        if isinstance(alpha, Gamma):
+            alpha._version += 1
+        if isinstance(tau, Gamma):
+            tau._version += 1
+        self._e2 = None
 
     def _resident_publish(self, state, lay, X, order):
         """Point the node objects at the device state the loop left behind."""
@@ -562,7 +604,7 @@ class FactorModelPlan:
         Lam = view("lamx", (K, K))
         cov = view("covx", (1, 1, K, K))
         logdet = view("logdetx", ())
-        phi1 = D.mul(Lam, -0.5).reshape((1, 1, K, K))
+        phi1 = view("phi1x", (1, 1, K, K))
 
         def phi0_fn():
             return D.sum_product([Lam, X], [["i", "j"], ["o", "n", "j"]], ["o", "n", "i"])
@@ -578,7 +620,7 @@ class FactorModelPlan:
         self._stats = (col._version, view("stats", (M * K + K * K + K,)))
         # C
         W = view("w", (M, 1, K))
-        row.phi = [view("phi0c", (M, 1, K)), D.mul(view("lamc", (1, 1, K, K)), -0.5)]
+        row.phi = [view("phi0c", (M, 1, K)), view("phi1c", (1, 1, K, K))]
         row.u = [W, FactoredSecondMoment(W, view("covc", (1, 1, K, K)), (K,))]
         row.g = view("gc", (M, 1))
         row._version += 1

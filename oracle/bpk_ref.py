@@ -480,14 +480,14 @@ class RefBackend:
                  "w", "sww", "covc", "lamc", "logdetc", "phi0c", "gc",
                  "al_phi0", "al_phi1", "al_u0", "al_u1", "al_g",
                  "tau_phi0", "tau_phi1", "tau_u0", "tau_u1", "tau_g",
-                 "covx", "lamx", "logdetx", "A", "bx", "stats", "sxxt", "lprev", "stats_local"]
+                 "covx", "lamx", "logdetx", "A", "bx", "stats", "sxxt", "lprev", "stats_local", "phi1x", "phi1c"]
 
     def pca_vb_layout(self, M, K):
         KK, MK = K * K, M * K
         NS = MK + KK + K
         size = dict(mux=K, ax=K, muc=K, a0=K, b0=K, w=MK, sww=KK, covc=KK, lamc=KK, phi0c=MK, gc=M,
                     al_phi0=K, al_phi1=K, al_u0=K, al_u1=K, al_g=K, covx=KK, lamx=KK, A=MK, bx=K,
-                    stats=NS, sxxt=KK, stats_local=NS)
+                    stats=NS, sxxt=KK, stats_local=NS, phi1x=KK, phi1c=KK)
         out, o = {}, 0
         for f in self.VB_FIELDS:
             n = size.get(f, 1)
@@ -538,6 +538,7 @@ class RefBackend:
                     lam = np.diag(f["ax"]) + tau * f["sww"].reshape(K, K)
                     cov = np.linalg.inv(lam)
                     f["lamx"][:] = lam.ravel()
+                    f["phi1x"][:] = -0.5 * lam.ravel()
                     f["covx"][:] = cov.ravel()
                     f["logdetx"][0] = np.linalg.slogdet(lam)[1]
                     f["bx"][:] = cov @ (f["ax"] * f["mux"])
@@ -565,6 +566,7 @@ class RefBackend:
                     phi0 = f["al_u0"] * f["muc"] + tau * f["stats"][:MK].reshape(M, K)
                     W[...] = phi0 @ cov.T
                     f["lamc"][:] = lam.ravel()
+                    f["phi1c"][:] = -0.5 * lam.ravel()
                     f["covc"][:] = cov.ravel()
                     f["logdetc"][0] = ld
                     f["phi0c"][:] = phi0.ravel()
