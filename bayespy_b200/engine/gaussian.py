@@ -419,6 +419,69 @@ class GaussianARD(_GaussianNode):
         super().__init__(mu, alpha, dims=(shape, shape + shape), distribution=dist, plates=plates,
                          name=name, initialize=initialize)
 
+    def rotate(self, R, inv=None, logdet=None, axis=-1, Q=None, subset=None):
+        """Transform q(x) -> q(R x) along the variable axis (gaussian.py:1693-1745): natural parameters by
+        R^-T, moments by R, log-normaliser by -log|det R|.  R is a host K x K matrix; the plated arrays are
+        transformed on the device (one pass over u0; the covariance stays factored when it is shared)."""
+        if Q is not None or subset is not None or axis not in (-1, 0) or len(self.dims[0]) != 1:
+            raise NotImplementedError("rotate: only axis=-1 of a one-axis GaussianARD, without Q / subset")
+        from .plans import LazyArray
+        R = np.asarray(R, dtype=np.float64)
+        invR = np.linalg.inv(R) if inv is None else np.asarray(inv, dtype=np.float64)
+        logdetR = np.linalg.slogdet(R)[1] if logdet is None else float(logdet)
+        K = self.dims[0][0]
+        Rd, iRT = D.asarray(R), D.asarray(np.ascontiguousarray(invR.T))
+
+        def rot_vec(a, Mx):         # a[..., i] <- sum_k Mx[i, k] a[..., k]
+            a = D.asarray(a)
+            flat = a.reshape((-1, K))
+            return D.sum_product([Mx, flat], [["i", "k"], ["n", "k"]], ["n", "i"]).reshape(a.shape)
+
+        def rot_mat(a, Mx):         # a[..., i, j] <- sum_kl Mx[i, k] a[..., k, l] Mx[j, l]
+            a = D.asarray(a)
+            flat = a.reshape((-1, K, K))
+            return D.sum_product([Mx, flat, Mx], [["i", "k"], ["n", "k", "l"], ["j", "l"]], ["n", "i", "j"]).reshape(a.shape)
+
+        u0 = rot_vec(self.u[0], Rd)
+        if isinstance(self.u[1], FactoredSecondMoment):
+            u1 = FactoredSecondMoment(u0.reshape(self.u[1].u0.shape), rot_mat(self.u[1].cov, Rd), self.u[1].var_shape)
+        else:
+            u1 = rot_mat(self.u[1], Rd)
+        phi1 = rot_mat(self.phi[1], iRT)
+        if isinstance(self.phi[0], LazyArray):
+            # fused sweeps keep phi0 = Lam x and g virtual: rebuild them from the rotated pieces
+            fz = getattr(self, "_fused", None)
+            Lam = D.mul(phi1.reshape((K, K)), -2.0)
+            X = u0
+            old_g = self.g
+            logdet_q = fz["logdet"] if fz is not None else None
+            shape0, shapeg = self.phi[0].shape, self.g.shape if isinstance(self.g, LazyArray) else None
+
+            def phi0_fn():
+                return D.sum_product([Lam, X.reshape((-1, K))], [["i", "j"], ["n", "j"]], ["n", "i"]).reshape(shape0)
+            phi0 = LazyArray(shape0, phi0_fn)
+            if isinstance(old_g, LazyArray) and logdet_q is not None:
+                new_logdet = D.affine(logdet_q, 1.0, -2.0 * logdetR)      # log|Lam'| = log|Lam| - 2 log|det R|
+
+                def g_fn():
+                    xf = X.reshape((-1, K))
+                    q = D.sum_product([xf, Lam, xf], [["n", "i"], ["i", "j"], ["n", "j"]], ["n"]).reshape(shapeg)
+                    return D.axpby(-0.5, q, 0.5, new_logdet)
+                g = LazyArray(shapeg, g_fn)
+                self._fused = dict(fz, Lam=Lam, logdet=new_logdet, cov=u1.cov if isinstance(u1, FactoredSecondMoment) else None)
+            else:
+                g = D.affine(D.asarray(old_g.materialize() if isinstance(old_g, LazyArray) else old_g), 1.0, -logdetR)
+        else:
+            phi0 = rot_vec(self.phi[0], iRT)
+            g = D.affine(D.asarray(self.g), 1.0, -logdetR)
+        self.phi = [phi0, phi1]
+        self.u = [u0, u1]
+        self.g = g
+        old_version = self._version
+        self._version += 1
+        for hook in getattr(self, "_rotate_hooks", ()):
+            hook(Rd, old_version)          # e.g. a plan's cached plate sums rotate with the node
+
     def initialize_from_parameters(self, mu, alpha):
         mu = np.asarray(mu, dtype=np.float64) * np.ones(np.shape(alpha))
         alpha = np.asarray(alpha, dtype=np.float64) * np.ones(np.shape(mu))

@@ -117,6 +117,23 @@ class FactorModelPlan:
         def Y_lb(node):
             return plan.bound_Y() if plan.valid() else o["Y.lb"]()
 
+        def col_rotated(Rd, old_version):
+            # S_yx = sum y x^T, S_xx = sum x x^T, s_x = sum x follow x -> R x without another pass over Y
+            if plan._stats is not None and plan._stats[0] == old_version:
+                M, K = plan.M, plan.K
+                Syx, Sxx, sx = plan._split(plan._stats[1])
+                st = DArray.empty((M * K + K * K + K,))
+                a, b, c = plan._split(st)
+                D.sum_product([Syx, Rd], [["m", "k"], ["i", "k"]], ["m", "i"], out=a)
+                D.sum_product([Rd, Sxx, Rd], [["i", "k"], ["k", "l"], ["j", "l"]], ["i", "j"], out=b)
+                D.sum_product([Rd, sx], [["i", "k"], ["k"]], ["i"], out=c)
+                plan._stats = (plan.col._version, st)
+            plan._e2 = None
+            plan._res_cache = None
+        hooks = list(getattr(self.col, "_rotate_hooks", ()))
+        hooks.append(col_rotated)
+        self.col._rotate_hooks = hooks
+
         self.col.update = types.MethodType(col_update, self.col)
         self.col.lower_bound_contribution = types.MethodType(col_lb, self.col)
         self.F.message_to_parent = types.MethodType(F_msg, self.F)

@@ -275,8 +275,43 @@ def lssm(name, M, N, D, mask_p=None, iters=6):
     save(name, **out)
 
 
+def pca_rotated(name="pca_rotated", M=10, N=60, D=4, iters=6):
+    """doc/source/examples/pca.rst:26-112: Bayesian PCA with the rotation parameter expansion as VB callback
+    (inference/vmp/transformations.py:23-222 RotationOptimizer, :376-1110 RotateGaussianARD)."""
+    from bayespy.inference.vmp.transformations import RotateGaussianARD, RotationOptimizer
+    np.random.seed(1)
+    c = np.random.randn(M, 2)
+    x = np.random.randn(2, N)
+    y = np.dot(c, x) + 0.1 * np.random.randn(M, N)
+    X = GaussianARD(0, 1, shape=(D,), plates=(1, N), name="X")
+    alpha = Gamma(1e-5, 1e-5, plates=(D,), name="alpha")
+    C = GaussianARD(0, alpha, shape=(D,), plates=(M, 1), name="C")
+    F = SumMultiply("d,d->", X, C)
+    tau = Gamma(1e-5, 1e-5, name="tau")
+    Y = GaussianARD(F, tau, name="Y")
+    Y.observe(y)
+    C_init = np.random.RandomState(7).randn(M, 1, D)
+    C.initialize_from_value(C_init)
+    Q = VB(Y, X, C, alpha, tau)
+    rot_X = RotateGaussianARD(X)
+    rot_C = RotateGaussianARD(C, alpha)
+    R = RotationOptimizer(rot_X, rot_C, D)
+    # one explicit rotation from a known state, to pin the cost function and its gradient
+    Q.update(repeat=2, verbose=False, tol=0)
+    rot_X.setup(); rot_C.setup()
+    Rtest = np.identity(D) + 0.1 * np.random.RandomState(3).randn(D, D)
+    bX, dbX = rot_X.bound(Rtest)
+    bC, dbC = rot_C.bound(np.linalg.inv(Rtest).T)
+    Q.set_callback(R.rotate)
+    Q.update(repeat=iters, verbose=False, tol=0)
+    out = dict(y=y, C_init=C_init, L=Q.L[:iters + 2], Rtest=Rtest, bX=np.asarray(bX), dbX=dbX, bC=np.asarray(bC), dbC=dbC)
+    for nm, node in (("X", X), ("C", C), ("alpha", alpha), ("tau", tau)):
+        node_state(nm, node, out)
+    save(name, **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["quickstart", "pca", "linalg", "summul", "dist", "gmm", "gmc"]
+    which = sys.argv[1:] or ["quickstart", "pca", "linalg", "summul", "dist", "gmm", "gmc", "rot"]
     if "quickstart" in which:
         quickstart()
     if "pca" in which:
@@ -292,6 +327,8 @@ if __name__ == "__main__":
     if "gmm" in which:
         gmm("gmm_small", 300, 3, 5)
         gmm_doc()
+    if "rot" in which:
+        pca_rotated()
     if "gmc" in which:
         block_banded_vectors()
         lssm("lssm_small", 6, 40, 3)
