@@ -118,3 +118,26 @@ def test_lssm_matches_reference(backend, name, masked):
 
 def F_plates(Q):
     return tuple(Q["Y"].plates)
+
+
+@pytest.mark.parametrize("T,Dm", [(777, 6), (64, 32), (1025, 3), (9, 2)])
+def test_block_banded_long_chain_vs_oracle(backend, T, Dm):
+    """Chains long enough for the parallel-in-time (block cyclic reduction) path, any T (not only powers of two),
+    against the oracle's sequential restatement of linalg.block_banded_solve."""
+    from oracle.bpk_ref import RefBackend
+    rs = np.random.RandomState(T + Dm)
+    a = 0.9 * np.linalg.qr(rs.randn(Dm, Dm))[0]
+    A = np.tile(2.5 * np.identity(Dm) + a.T @ a, (T, 1, 1)) + 0.05 * np.eye(Dm) * rs.rand(T, 1, 1)
+    B = np.tile(-a.T, (T - 1, 1, 1)) * (1 + 0.1 * rs.randn(T - 1, 1, 1))
+    y = rs.randn(T, Dm)
+    ref = RefBackend()
+    hV, hC, hx, hl = np.empty((T, Dm, Dm)), np.empty((T - 1, Dm, Dm)), np.empty((T, Dm)), np.empty(1)
+    ref.block_banded_solve(A.ctypes.data, B.ctypes.data, y.ctypes.data, 1, T, Dm, hV.ctypes.data, hC.ctypes.data,
+                           hx.ctypes.data, hl.ctypes.data)
+    d = [DArray.from_numpy(v) for v in (A, B, y)]
+    V, C, x, ld = DArray.empty((T, Dm, Dm)), DArray.empty((T - 1, Dm, Dm)), DArray.empty((T, Dm)), DArray.empty(())
+    backend.block_banded_solve(d[0].ptr, d[1].ptr, d[2].ptr, 1, T, Dm, V.ptr, C.ptr, x.ptr, ld.ptr, True)
+    np.testing.assert_allclose(V.numpy(), hV, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(C.numpy(), hC, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(x.numpy(), hx, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(float(ld.numpy()), hl[0], rtol=1e-12)
