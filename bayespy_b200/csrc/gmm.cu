@@ -201,17 +201,10 @@ __global__ void __launch_bounds__(G1_WARPS * 32, 1) gmm_sweep_dmma_kernel(GmmArg
     double *sT = sm;                                   // [64][52]  Theta
     double *sZ = sT + G1_KP * G1_LDZ;                  // [128][52] features of the tile
     double *sP = sZ + G1_ROWS * G1_LDZ;                // [128][68] responsibilities of the tile
-    double *sY = sP + G1_ROWS * G1_LDP;                // [128][8]
-    __shared__ unsigned char fi[G1_FP], fj[G1_FP];
     __shared__ double red[G1_WARPS];
     const int t = threadIdx.x, lane = t & 31, w = t >> 5, gr = lane >> 2, tg = lane & 3;
     const int D = a.D, K = a.K;
 
-    if (t < G1_FP) {
-        int i = 0, j = 0;
-        if (t >= 9 && t < G1_NF) g1_pair(t, i, j);
-        fi[t] = (unsigned char)i; fj[t] = (unsigned char)j;
-    }
     for (int e = t; e < G1_KP * G1_FP; e += blockDim.x) {
         const int k = e / G1_FP, f = e - k * G1_FP;
         double v = 0.0;
@@ -238,35 +231,43 @@ __global__ void __launch_bounds__(G1_WARPS * 32, 1) gmm_sweep_dmma_kernel(GmmArg
     __syncthreads();
 
     const int64_t ntiles = (a.N + G1_ROWS - 1) / G1_ROWS;
+    double ynext[G1_DP];
+    {
+        const int64_t n = (int64_t)blockIdx.x * G1_ROWS + w * 16 + (lane >> 1);
+#pragma unroll
+        for (int d = 0; d < G1_DP; ++d) ynext[d] = (n < a.N && d < D) ? a.Y[n * D + d] : 0.0;
+    }
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t row0 = tile * G1_ROWS;
-        // ---- stage y (coalesced) ----
-        {
-            const int64_t base = row0 * D;
-            int64_t lim = a.N * D - base;
-            if (lim > (int64_t)G1_ROWS * D) lim = (int64_t)G1_ROWS * D;
-            for (int e = t; e < G1_ROWS * D; e += blockDim.x) {
-                const int r = e / D, d = e - r * D;
-                sY[r * G1_DP + d] = e < lim ? a.Y[base + e] : 0.0;
-            }
-            if (D < G1_DP)
-                for (int e = t; e < G1_ROWS * (G1_DP - D); e += blockDim.x) {
-                    const int r = e / (G1_DP - D), d = D + e % (G1_DP - D);
-                    sY[r * G1_DP + d] = 0.0;
-                }
-        }
-        __syncthreads();
-        // ---- E phase: this warp's 16 rows ----
+        // ---- E phase: this warp's 16 rows; two lanes per row build its 48 monomial features from registers ----
         const int r0 = w * 16;
-        for (int e = lane; e < 16 * G1_FP; e += 32) {
-            const int r = r0 + e / G1_FP, f = e % G1_FP;
-            const bool live = row0 + r < a.N;
-            double v;
-            if (f == 0) v = live ? 1.0 : 0.0;
-            else if (f <= G1_DP) v = sY[r * G1_DP + f - 1];
-            else if (f < G1_NF) v = sY[r * G1_DP + fi[f]] * sY[r * G1_DP + fj[f]];
-            else v = 0.0;
-            sZ[r * G1_LDZ + f] = v;
+        {
+            const int r = r0 + (lane >> 1);
+            const int64_t n = row0 + r;
+            const bool live = n < a.N;
+            double y[G1_DP];
+#pragma unroll
+            for (int d = 0; d < G1_DP; ++d) y[d] = (live && d < D) ? ynext[d] : 0.0;
+            double *zr = sZ + r * G1_LDZ;
+            if ((lane & 1) == 0) {
+                zr[0] = live ? 1.0 : 0.0;
+#pragma unroll
+                for (int d = 0; d < G1_DP; ++d) zr[1 + d] = y[d];
+            }
+            {
+                // the 36 products y_i y_j (i <= j) in feature order; features < 24 belong to the even lane
+                int f = 9;
+#pragma unroll
+                for (int i = 0; i < G1_DP; ++i)
+#pragma unroll
+                    for (int j = i; j < G1_DP; ++j, ++f)
+                        if ((f < 24) == ((lane & 1) == 0)) zr[f] = y[i] * y[j];
+                if (lane & 1) zr[45] = zr[46] = zr[47] = 0.0;
+            }
+            // prefetch this lane's row of the next tile (hides the HBM latency behind both contraction phases)
+            const int64_t nn = n + (int64_t)gridDim.x * G1_ROWS;
+#pragma unroll
+            for (int d = 0; d < G1_DP; ++d) ynext[d] = (nn < a.N && d < D) ? a.Y[nn * D + d] : 0.0;
         }
         __syncwarp();
         double L[2][8][2];
