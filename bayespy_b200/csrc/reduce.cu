@@ -4,6 +4,7 @@
 // reduction trees, no atomics.
 #include "common.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 struct SmArgs {
     int n_in, nk, ns;
@@ -133,6 +134,82 @@ __global__ void __launch_bounds__(256) sm_final_kernel(SmArgs A) {
     }
 }
 
+// ---- GEMM-shaped contractions on the fp64 tensor pipe -------------------------------------------------------
+// When a two-operand sum_multiply collapses to  C[m,n] (+)= scale * sum_k A[m,k] B[k,n]  (one axis only in
+// operand 0, one only in operand 1, one summed axis in both — e.g. <f f> = sum_ij <cc>[m,ij] <xx>[n,ij] of
+// dot.py:403, the messages of dot.py:581, the W^T Lambda W style products of the Gaussian messages), it runs
+// as a DMMA GEMM with arbitrary element strides: 64 x 64 tile per CTA, 4 warps of 32 x 32, k-step 16 staged in
+// shared memory k-contiguous (pitch 20 = 4 mod 16: conflict-free fragment loads).  Fixed summation order.
+struct GemmArgs {
+    const double *A, *B;
+    double *C;
+    int64_t M, N, K;
+    int64_t sAm, sAk, sBk, sBn, sCm, sCn;
+    double scale;
+    int accumulate;
+};
+#define GM_BM 64
+#define GM_BN 64
+#define GM_BK 16
+#define GM_LD 20
+
+__device__ __forceinline__ void gm_dmma(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(128) dgemm_dmma_kernel(GemmArgs g) {
+    __shared__ double As[GM_BM * GM_LD], Bs[GM_BN * GM_LD];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5, gr = lane >> 2, tg = lane & 3;
+    const int wm = (w >> 1) * 32, wn = (w & 1) * 32;
+    const int64_t m0 = (int64_t)blockIdx.y * GM_BM, n0 = (int64_t)blockIdx.x * GM_BN;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const bool a_kfast = g.sAk == 1 || g.sAm != 1, b_kfast = g.sBk == 1 || g.sBn != 1;
+    for (int64_t k0 = 0; k0 < g.K; k0 += GM_BK) {
+        for (int e = t; e < GM_BM * GM_BK; e += 128) {
+            const int m = a_kfast ? e / GM_BK : e % GM_BM, k = a_kfast ? e % GM_BK : e / GM_BM;
+            const int64_t mm = m0 + m, kk = k0 + k;
+            As[m * GM_LD + k] = (mm < g.M && kk < g.K) ? g.A[mm * g.sAm + kk * g.sAk] : 0.0;
+        }
+        for (int e = t; e < GM_BN * GM_BK; e += 128) {
+            const int n = b_kfast ? e / GM_BK : e % GM_BN, k = b_kfast ? e % GM_BK : e / GM_BN;
+            const int64_t nn = n0 + n, kk = k0 + k;
+            Bs[n * GM_LD + k] = (nn < g.N && kk < g.K) ? g.B[kk * g.sBk + nn * g.sBn] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int ks = 0; ks < GM_BK; ks += 4) {
+            double af[4], bf[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) af[i] = As[(wm + i * 8 + gr) * GM_LD + ks + tg];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bf[j] = Bs[(wn + j * 8 + gr) * GM_LD + ks + tg];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) gm_dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int64_t m = m0 + wm + i * 8 + gr, n = n0 + wn + j * 8 + 2 * tg + q;
+                if (m < g.M && n < g.N) {
+                    double *c = g.C + m * g.sCm + n * g.sCn;
+                    const double v = g.scale * acc[i][j][q];
+                    *c = g.accumulate ? *c + v : v;
+                }
+            }
+}
+
 extern "C" int bpk_sum_multiply(int nd, const int64_t *shape,
                                 int n_in, const void *const *in, const int *in_dtype,
                                 const int64_t *in_stride,
@@ -193,6 +270,32 @@ extern "C" int bpk_sum_multiply(int nd, const int64_t *shape,
         // empty sum: the result is zero (or unchanged when accumulating) over the kept space;
         // an empty kept space writes nothing.
         return BPK_OK;
+    }
+    // GEMM-shaped: two fp64 operands, kept axes {m: operand 0 only, n: operand 1 only}, one summed axis in both
+    if (n_in == 2 && A.dtype[0] == BPK_F64 && A.dtype[1] == BPK_F64 && A.nk == 2 && A.ns == 1 &&
+        A.sin[0][0] != 0 && A.sin[1][0] != 0) {
+        int im = -1, in_ = -1;
+        for (int d = 0; d < 2; ++d) {
+            if (A.kin[0][d] != 0 && A.kin[1][d] == 0) im = d;
+            else if (A.kin[0][d] == 0 && A.kin[1][d] != 0) in_ = d;
+        }
+        if (im >= 0 && in_ >= 0 && A.kshape[im] >= 8 && A.kshape[in_] >= 8 && A.sshape[0] >= 4 &&
+            (double)A.n_kept * (double)A.n_sum >= 262144.0 && !getenv("BPK_NO_GEMM")) {
+            GemmArgs g;
+            g.A = (const double *)A.in[0]; g.B = (const double *)A.in[1]; g.C = out;
+            g.M = A.kshape[im]; g.N = A.kshape[in_]; g.K = A.sshape[0];
+            g.sAm = A.kin[0][im]; g.sAk = A.sin[0][0]; g.sBk = A.sin[1][0]; g.sBn = A.kin[1][in_];
+            g.sCm = A.kout[im]; g.sCn = A.kout[in_];
+            g.scale = A.scale; g.accumulate = accumulate;
+            dim3 grid((unsigned)((g.N + GM_BN - 1) / GM_BN), (unsigned)((g.M + GM_BM - 1) / GM_BM));
+            if (grid.y <= 65535u) {
+                dgemm_dmma_kernel<<<grid, 128, 0, g_bpk.stream>>>(g);
+                g_bpk.launches++;
+                cudaError_t e_ = cudaPeekAtLastError();
+                if (e_ != cudaSuccess) return bpk_set_error(BPK_ECUDA, "launch of dgemm_dmma_kernel failed: %s", cudaGetErrorString(e_));
+                return BPK_OK;
+            }
+        }
     }
     if (A.ns == 0) { A.ns = 1; A.sshape[0] = 1; }   // pure broadcast product
 

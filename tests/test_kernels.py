@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 
 from conftest import golden
+from bayespy_b200.darray import DArray
 
 RTOL = 1e-9
 
@@ -194,3 +195,29 @@ def test_raw_moment_kernels_golden(backend):
     with pytest.raises(ValueError):
         bad = DArray.from_numpy(np.array([0, 6], dtype=np.int64), "i8")
         be.one_hot(bad.ptr, 2, 6, DArray.empty((2, 6)).ptr, True)
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 64, 64), (70, 130, 33), (256, 1000, 1024), (9, 3000, 17), (300, 8, 128)])
+def test_sum_product_gemm_shapes(backend, M, N, K):
+    """Contractions that collapse to C[m,n] = sum_k A[m,k] B[k,n] (dot.py:403,581 patterns) take the tensor-pipe
+    GEMM path of bpk_sum_multiply on the GPU: every operand layout (k-contiguous / m-contiguous, transposed output),
+    scale, accumulate, ragged tiles."""
+    from bayespy_b200 import darray as D
+    rs = np.random.RandomState(M + N + K)
+    a, b = rs.randn(M, K), rs.randn(N, K)
+    A, B = DArray.from_numpy(a), DArray.from_numpy(b)
+    ref = a @ b.T
+    out = D.sum_product([A, B], [["m", "k"], ["n", "k"]], ["m", "n"])                       # both k-contiguous
+    np.testing.assert_allclose(out.numpy(), ref, rtol=1e-11, atol=1e-10)
+    At, Bt = DArray.from_numpy(np.ascontiguousarray(a.T)), DArray.from_numpy(np.ascontiguousarray(b.T))
+    out = D.sum_product([At, Bt], [["k", "m"], ["k", "n"]], ["n", "m"], scale=-0.5)         # m-/n-contiguous, C^T
+    np.testing.assert_allclose(out.numpy(), -0.5 * ref.T, rtol=1e-11, atol=1e-10)
+    acc = DArray.from_numpy(np.ones((M, N)))
+    D.sum_product([A, Bt], [["m", "k"], ["k", "n"]], ["m", "n"], out=acc, accumulate=True)  # accumulate onto ones
+    np.testing.assert_allclose(acc.numpy(), 1.0 + ref, rtol=1e-11, atol=1e-10)
+    # the <f f> pattern of SumMultiply: sum_ij cc[m,1,i,j] xx[n,i,j]
+    if K == 64:
+        cc, xx = rs.randn(M, 1, 8, 8), rs.randn(N, 8, 8)
+        out = D.sum_product([DArray.from_numpy(cc), DArray.from_numpy(xx)],
+                            [["m", "o", "i", "j"], ["n", "i", "j"]], ["m", "n"])
+        np.testing.assert_allclose(out.numpy(), np.einsum("moij,nij->mn", cc, xx), rtol=1e-11, atol=1e-10)
