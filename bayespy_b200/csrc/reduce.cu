@@ -158,7 +158,7 @@ __device__ __forceinline__ void gm_dmma(double &d0, double &d1, double a, double
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(128) dgemm_dmma_kernel(GemmArgs g) {
+__global__ void __launch_bounds__(128, 3) dgemm_dmma_kernel(GemmArgs g) {
     __shared__ double As[GM_BM * GM_LD], Bs[GM_BN * GM_LD];
     const int t = threadIdx.x, lane = t & 31, w = t >> 5, gr = lane >> 2, tg = lane & 3;
     const int wm = (w >> 1) * 32, wn = (w & 1) * 32;
@@ -169,18 +169,34 @@ __global__ void __launch_bounds__(128) dgemm_dmma_kernel(GemmArgs g) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     const bool a_kfast = g.sAk == 1 || g.sAm != 1, b_kfast = g.sBk == 1 || g.sBn != 1;
-    for (int64_t k0 = 0; k0 < g.K; k0 += GM_BK) {
-        for (int e = t; e < GM_BM * GM_BK; e += 128) {
-            const int m = a_kfast ? e / GM_BK : e % GM_BM, k = a_kfast ? e % GM_BK : e / GM_BM;
-            const int64_t mm = m0 + m, kk = k0 + k;
-            As[m * GM_LD + k] = (mm < g.M && kk < g.K) ? g.A[mm * g.sAm + kk * g.sAk] : 0.0;
+    // each thread stages 8 + 8 elements of a k-tile; the NEXT tile is fetched into registers while the
+    // current one is multiplied, so the HBM / L2 latency hides behind the 64 DMMA of the tile
+    constexpr int PT = GM_BM * GM_BK / 128;
+    // tile element e -> (row, k): k fastest when the operand is k-contiguous, row fastest otherwise
+    auto arow = [&](int e) { return a_kfast ? e / GM_BK : e % GM_BM; };
+    auto acol = [&](int e) { return a_kfast ? e % GM_BK : e / GM_BM; };
+    auto brow = [&](int e) { return b_kfast ? e / GM_BK : e % GM_BN; };
+    auto bcol = [&](int e) { return b_kfast ? e % GM_BK : e / GM_BN; };
+    double ra[PT], rb[PT];
+    auto fetch = [&](int64_t k0) {
+#pragma unroll
+        for (int q = 0; q < PT; ++q) {
+            const int e = t + q * 128;
+            const int64_t mm = m0 + arow(e), ka = k0 + acol(e), nn = n0 + brow(e), kb = k0 + bcol(e);
+            ra[q] = (mm < g.M && ka < g.K) ? g.A[mm * g.sAm + ka * g.sAk] : 0.0;
+            rb[q] = (nn < g.N && kb < g.K) ? g.B[kb * g.sBk + nn * g.sBn] : 0.0;
         }
-        for (int e = t; e < GM_BN * GM_BK; e += 128) {
-            const int n = b_kfast ? e / GM_BK : e % GM_BN, k = b_kfast ? e % GM_BK : e / GM_BN;
-            const int64_t nn = n0 + n, kk = k0 + k;
-            Bs[n * GM_LD + k] = (nn < g.N && kk < g.K) ? g.B[kk * g.sBk + nn * g.sBn] : 0.0;
+    };
+    fetch(0);
+    for (int64_t k0 = 0; k0 < g.K; k0 += GM_BK) {
+#pragma unroll
+        for (int q = 0; q < PT; ++q) {
+            const int e = t + q * 128;
+            As[arow(e) * GM_LD + acol(e)] = ra[q];
+            Bs[brow(e) * GM_LD + bcol(e)] = rb[q];
         }
         __syncthreads();
+        if (k0 + GM_BK < g.K) fetch(k0 + GM_BK);
 #pragma unroll
         for (int ks = 0; ks < GM_BK; ks += 4) {
             double af[4], bf[4];
@@ -289,6 +305,11 @@ extern "C" int bpk_sum_multiply(int nd, const int64_t *shape,
             g.scale = A.scale; g.accumulate = accumulate;
             dim3 grid((unsigned)((g.N + GM_BN - 1) / GM_BN), (unsigned)((g.M + GM_BM - 1) / GM_BM));
             if (grid.y <= 65535u) {
+                static bool carve = false;
+                if (!carve) {     // several CTAs per SM: ask for the shared-memory carve-out up front
+                    cudaFuncSetAttribute(dgemm_dmma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+                    carve = true;
+                }
                 dgemm_dmma_kernel<<<grid, 128, 0, g_bpk.stream>>>(g);
                 g_bpk.launches++;
                 cudaError_t e_ = cudaPeekAtLastError();
