@@ -158,7 +158,7 @@ __device__ __forceinline__ void gm_dmma(double &d0, double &d1, double a, double
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(128, 3) dgemm_dmma_kernel(GemmArgs g) {
+__global__ void __launch_bounds__(128, 2) dgemm_dmma_kernel(GemmArgs g) {
     __shared__ double As[GM_BM * GM_LD], Bs[GM_BN * GM_LD];
     const int t = threadIdx.x, lane = t & 31, w = t >> 5, gr = lane >> 2, tg = lane & 3;
     const int wm = (w >> 1) * 32, wn = (w & 1) * 32;
