@@ -42,7 +42,7 @@ Y = GaussianARD(F, tau, name="Y")
 Y.observe(y)
 Q = VB(X, C, gamma, A, alpha, tau, Y)
 be = _bpk.get()
-Q.update(repeat=1, verbose=False, tol=0)
+Q.update(repeat=3, verbose=False, tol=0)     # warm-up: lets the stream-ordered memory pool reach its steady size
 be.sync()
 l0 = be.launch_count()
 t0 = time.perf_counter()
