@@ -295,6 +295,9 @@ def run_gpu(args):
                                "[X,C,alpha,tau] incl. lower bound" % n_total,
                    "n_total": n_total, "n_per_gpu": n_local_max, "parallelism": "plate-shard x%d" % world,
                    "l2": "inputs (%.2f GB of Y per GPU) larger than the 126 MB L2; no flush" % (y.nbytes / 1e9),
+                   "launch_note": "a chunk of up to 50 VB sweeps is ONE persistent launch of the fused sweep kernel "
+                                  "(data pass + grid reduction + node updates + bound per sweep, grid barriers in between); "
+                                  "gpu_launches counts launches, roofline.sweeps_per_launch the sweeps inside each",
                    "lower_bound_last": L_last, "device_ms_per_step": ms_dev / steps,
                    "host_wall_ms_per_step": 1e3 * wall / steps},
         "clocks": clocks,
