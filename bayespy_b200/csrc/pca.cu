@@ -284,7 +284,19 @@ __device__ __forceinline__ int ws_off(int m, int c) {
 
 // Self-resetting grid barrier (all CTAs are co-resident: one persistent CTA per SM).
 // bar[0] = arrival count, bar[1] = epoch.
-__device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int &epoch) {
+// Spin with a watchdog: if the grid is not fully co-resident (another context on the GPU) or a CTA died, give up
+// after ~4 s, raise error bit 8 in *err and let the kernel terminate instead of hanging the device.
+__device__ __forceinline__ void grid_spin(unsigned int *bar, unsigned int target, int *err) {
+    const long long t0 = clock64();
+    while (*(volatile unsigned int *)&bar[1] != target) {
+        __nanosleep(32);
+        if (clock64() - t0 > 8000000000ll) {
+            if (err) atomicOr(err, 8);
+            break;
+        }
+    }
+}
+__device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int &epoch, int *err = nullptr) {
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
@@ -294,7 +306,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int &ep
             __threadfence();
             atomicExch(&bar[1], target);
         } else {
-            while (*(volatile unsigned int *)&bar[1] != target) { __nanosleep(32); }
+            grid_spin(bar, target, err);
         }
         __threadfence();
     }
@@ -313,9 +325,9 @@ __device__ __forceinline__ void grid_arrive(unsigned int *bar, unsigned int epoc
         }
     }
 }
-__device__ __forceinline__ void grid_wait(unsigned int *bar, unsigned int &epoch) {
+__device__ __forceinline__ void grid_wait(unsigned int *bar, unsigned int &epoch, int *err = nullptr) {
     if (threadIdx.x == 0) {
-        while (*(volatile unsigned int *)&bar[1] != epoch + 1) { __nanosleep(32); }
+        grid_spin(bar, epoch + 1, err);
         __threadfence();
     }
     epoch += 1;
@@ -545,7 +557,7 @@ pca_xsweep_ws_kernel(const __grid_constant__ CUtensorMap tmapY, int64_t M, int64
         const int nops_it = (it == niter - 1) ? vb.nops_last : vb.nops;
         grid_arrive(gbar, epoch);
         if (blockIdx.x == 0 && skip > 0 && (it == 0 || vb.dry_every)) pca_vb_ops(vb, smem, vb_sm_doubles, true, nops_it);   // warm the instruction cache
-        grid_wait(gbar, epoch);
+        grid_wait(gbar, epoch, vb.ctrl + 2);
         if (blockIdx.x == 0) vb_stamp(vb.dbg, 2);
         // distributed, fixed-order reduction over the CTAs: CTA c owns elements [c*per, (c+1)*per)
         double *fin = partial + (size_t)gridDim.x * PCA_NSTAT;
@@ -561,13 +573,13 @@ pca_xsweep_ws_kernel(const __grid_constant__ CUtensorMap tmapY, int64_t M, int64
             }
         }
         if (blockIdx.x == 0) vb_stamp(vb.dbg, 3);
-        grid_barrier(gbar, epoch);
+        grid_barrier(gbar, epoch, vb.ctrl + 2);
         if (blockIdx.x == 0) {
             vb_stamp(vb.dbg, 4);
             pca_vb_ops(vb, smem, vb_sm_doubles, false, nops_it);
             vb_stamp(vb.dbg, 5);
         }
-        if (it + 1 < niter) grid_barrier(gbar, epoch);      // the next sweep's A, b (and the stop word) are visible to every CTA
+        if (it + 1 < niter) grid_barrier(gbar, epoch, vb.ctrl + 2);      // the next sweep's A, b (and the stop word) are visible to every CTA
     }
     }   // sweeps of this launch
 }
@@ -626,6 +638,8 @@ static int pca_launch_ws(const double *Y, int64_t M, int64_t N, int K, const dou
             BPK_CUDA(cudaMalloc(&g_pca_gbar, 2 * sizeof(unsigned int)));
             BPK_CUDA(cudaMemsetAsync(g_pca_gbar, 0, 2 * sizeof(unsigned int), g_bpk.stream));
         }
+        // the arrival count is 0 between launches; re-zeroing it heals the barrier after a watchdog exit
+        BPK_CUDA(cudaMemsetAsync(g_pca_gbar, 0, sizeof(unsigned int), g_bpk.stream));
         PcaVbArgs vb = *tail;
         vb.partial = partial + (size_t)grid * PCA_NSTAT;     // the grid-reduced statistics
         vb.nparts = 1;

@@ -542,6 +542,9 @@ class FactorModelPlan:
                 raise ValueError("Natural parameters should be positive")
             if err & 4:
                 raise _bpk.BpkError(_bpk.ENCCL, "peer-memory exchange timed out (a rank stopped responding)")
+            if err & 8:
+                raise _bpk.BpkError(_bpk.ECUDA, "grid barrier of the fused sweep kernel timed out (is another process "
+                                                "using this GPU? the persistent grid must be fully resident)")
             Lrows = Lh.numpy()[:n_it]
             for r in range(n_it):
                 if vb.iter >= len(vb.L):

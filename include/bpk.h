@@ -231,7 +231,8 @@ int bpk_gmm_stats(const double *Y, int64_t N, int D, int K, const double *P, dou
  * run is a no-op, so the state is exactly the one the reference would have stopped at.
  * state: fp64 vector laid out per bpk_pca_vb_layout (hyper-parameters, q(C), q(alpha), q(tau),
  * shared part of q(X), plate-summed statistics); X: [N][K] posterior means, rewritten every sweep.
- * ctrl: device int[4] = {iterations finished, stop, error bits (1 = not SPD, 2 = domain), 0}.
+ * ctrl: device int[4] = {iterations finished, stop, error bits (1 = not SPD, 2 = domain, 4 = peer exchange
+ * timed out, 8 = grid barrier timed out), 0}.
  * With a communicator (bpk_comm_init) STATS is followed by the sweep's one all-reduce.          */
 enum {
     BPK_VBOP_XSWEEP = 1,  /* X.update(): one pass over Y (pca_xsweep_kernel)                    */
