@@ -1,0 +1,83 @@
+"""The reference's PUBLISHED doctest outputs reproduced by running the documented model
+scripts through this package: doc/source/examples/lssm.rst (first 10 iterations, 80 % missing values) and
+doc/source/examples/pca.rst (with the rotation callback).  The scripts below are the doc examples verbatim apart
+from the import lines; seeds are the doc build's (numpy.random.seed(1), set in each file's hidden testsetup)."""
+import re
+
+import numpy as np
+
+
+def _loglikes(out):
+    return [float(m) for m in re.findall(r"loglike=([-+0-9.e]+)", out)]
+
+
+def test_lssm_doc_example_first_ten_iterations(backend, capsys):
+    """lssm.rst:8-11,45-181,199-203: 'Iteration 1: loglike=-1.439704e+05 ... Iteration 10: loglike=-1.051441e+04'."""
+    from bayespy_b200.nodes import GaussianARD, GaussianMarkovChain, Gamma, Dot
+    from bayespy_b200.inference import VB
+    from bayespy_b200.utils import random
+    np.random.seed(1)
+    M, N, D = 30, 400, 10
+    alpha = Gamma(1e-5, 1e-5, plates=(D,), name="alpha")
+    A = GaussianARD(0, alpha, shape=(D,), plates=(D,), name="A")
+    X = GaussianMarkovChain(np.zeros(D), 1e-3 * np.identity(D), A, np.ones(D), n=N, name="X")
+    gamma = Gamma(1e-5, 1e-5, plates=(D,), name="gamma")
+    C = GaussianARD(0, gamma, shape=(D,), plates=(M, 1), name="C")
+    F = Dot(C, X, name="F")
+    assert tuple(F.plates) == (30, 400)
+    C.initialize_from_random()
+    tau = Gamma(1e-5, 1e-5, name="tau")
+    Y = GaussianARD(F, tau, name="Y")
+    Q = VB(X, C, gamma, A, alpha, tau, Y)
+    w = 0.3
+    a = np.array([[np.cos(w), -np.sin(w), 0, 0], [np.sin(w), np.cos(w), 0, 0], [0, 0, 1, 0], [0, 0, 0, 0]])
+    c = np.random.randn(M, 4)
+    x = np.empty((N, 4)); f = np.empty((M, N)); y = np.empty((M, N))
+    x[0] = 10 * np.random.randn(4)
+    f[:, 0] = np.dot(c, x[0])
+    y[:, 0] = f[:, 0] + 3 * np.random.randn(M)
+    for n in range(N - 1):
+        x[n + 1] = np.dot(a, x[n]) + [1, 1, 10, 10] * np.random.randn(4)
+        f[:, n + 1] = np.dot(c, x[n + 1])
+        y[:, n + 1] = f[:, n + 1] + 3 * np.random.randn(M)
+    mask = random.mask(M, N, p=0.2)
+    Y.observe(y, mask=mask)
+    Q.update(repeat=10)
+    L = _loglikes(capsys.readouterr().out)
+    assert len(L) == 10
+    # the doc prints 7 significant digits
+    np.testing.assert_allclose(L[0], -1.439704e+05, rtol=5e-7)
+    np.testing.assert_allclose(L[9], -1.051441e+04, rtol=5e-7)
+
+
+def test_pca_doc_example_with_rotations(backend, capsys):
+    """pca.rst:8-11,26-112,114-118: 'Iteration 1: loglike=-2.33...e+03 ... loglike=6.500...e+02, Converged'."""
+    from bayespy_b200.nodes import GaussianARD, Gamma, SumMultiply
+    from bayespy_b200.inference import VB
+    from bayespy_b200.inference.vmp.transformations import RotateGaussianARD, RotationOptimizer
+    np.random.seed(1)
+    M, N = 20, 100
+    x = np.random.randn(N, 2)
+    w = np.random.randn(M, 2)
+    f = np.einsum("ik,jk->ij", w, x)
+    y = f + 0.1 * np.random.randn(M, N)
+    D = 10
+    X = GaussianARD(0, 1, plates=(1, N), shape=(D,))
+    alpha = Gamma(1e-5, 1e-5, plates=(D,))
+    C = GaussianARD(0, alpha, plates=(M, 1), shape=(D,))
+    F = SumMultiply("d,d->", X, C)
+    tau = Gamma(1e-5, 1e-5)
+    Y = GaussianARD(F, tau)
+    Y.observe(y)
+    Q = VB(Y, X, C, alpha, tau)
+    C.initialize_from_random()
+    rot_X = RotateGaussianARD(X)
+    rot_C = RotateGaussianARD(C, alpha)
+    R = RotationOptimizer(rot_X, rot_C, D)
+    Q.set_callback(R.rotate)
+    Q.update(repeat=1000)
+    out = capsys.readouterr().out
+    L = _loglikes(out)
+    np.testing.assert_allclose(L[0], -2.33e+03, rtol=2.5e-3)          # doc: -2.33...e+03
+    np.testing.assert_allclose(L[-1], 6.500e+02, rtol=1e-4)           # doc: 6.500...e+02
+    assert "Converged at iteration" in out
