@@ -306,7 +306,9 @@ def run_gpu(args):
                 "note": "per step: Y.observe(pinned host array) + Q.update() + read of L"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "pca_xsweep_ws_kernel (one fused launch per VB sweep: data pass + grid reduction + node updates + bound)", "kernel_ms": kern_avg,
+                     "traffic": traffic, "kernel": "pca_xsweep_ws_kernel<...,FUSED> (persistent launch of sweeps_per_launch VB sweeps; per sweep: data pass + grid reduction + node updates + bound)", "kernel_ms": kern_avg,
+                     "kernel_ms_note": "launch duration / sweeps_per_launch (CUDA events on the library stream)",
+                     "traffic_note": "DRAM bytes per sweep, ncu --set full capture of a one-sweep launch (profiles/pca_xsweep_traffic.json)",
                      "kernel_share_of_step": kern_avg / (ms_max / steps),
                      "algorithmic_bytes_per_col": BYTES_PER_COL, "peak_source": peak_src,
                      "sweeps_per_launch": sweeps_per_launch,
