@@ -310,8 +310,50 @@ def pca_rotated(name="pca_rotated", M=10, N=60, D=4, iters=6):
     save(name, **out)
 
 
+def summultiply_nodes():
+    """nodes/dot.py:19-633 SumMultiply: moments and messages for several key patterns and plate layouts
+    (the cases of nodes/tests/test_dot.py), as computed by the reference."""
+    out = {}
+    rs = np.random.RandomState(21)
+
+    def gauss(shape, plates, nm):
+        n = len(shape)
+        x = GaussianARD(rs.randn(*(plates + shape)), 1 + rs.rand(*(plates + shape)), shape=shape, plates=plates, name=nm)
+        return x
+    cases = {
+        "dot":      ("i,i", [((4,), (3, 1)), ((4,), (1, 5))]),
+        "matvec":   ("ij,j->i", [((3, 4), (2,)), ((4,), (2,))]),
+        "outer":    ("i,j->ij", [((3,), (5,)), ((2,), (1,))]),
+        "triple":   ("i,i,i->", [((3,), (2, 1)), ((3,), (1, 4)), ((3,), ())]),
+        "keepdim":  ("ij,ik->jk", [((2, 3), ()), ((2, 4), (3,))]),
+    }
+    for tag, (spec, ins) in cases.items():
+        nodes = [gauss(sh, pl, "%s_x%d" % (tag, i)) for i, (sh, pl) in enumerate(ins)]
+        F = SumMultiply(spec, *nodes)
+        u = F.get_moments()
+        out[tag + "_u0"] = np.asarray(u[0])
+        out[tag + "_u1"] = np.asarray(u[1])
+        out[tag + "_plates"] = np.asarray(F.plates, dtype=np.int64)
+        # a child so that messages flow: Y ~ GaussianARD(F, tau) observed
+        tau = 0.7 + rs.rand()
+        ndim = len(F.dims[0])
+        Y = GaussianARD(F, tau, ndim=ndim)
+        yv = rs.randn(*(tuple(F.plates) + tuple(F.dims[0])))
+        Y.observe(yv)
+        out[tag + "_y"] = yv
+        out[tag + "_tau"] = np.asarray(tau)
+        for i, nd in enumerate(nodes):
+            out["%s_in%d_mu" % (tag, i)] = np.asarray(nd.parents[0].get_moments()[0]) / np.asarray(nd.parents[0].get_moments()[2]) \
+                if False else np.asarray(nd.u[0])
+            out["%s_in%d_u1" % (tag, i)] = np.asarray(nd.u[1])
+            m = F._message_to_parent(i)
+            out["%s_m%d_0" % (tag, i)] = np.asarray(m[0])
+            out["%s_m%d_1" % (tag, i)] = np.asarray(m[1])
+    save("summultiply_nodes", **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["quickstart", "pca", "linalg", "summul", "dist", "gmm", "gmc", "rot"]
+    which = sys.argv[1:] or ["quickstart", "pca", "linalg", "summul", "dist", "gmm", "gmc", "rot", "dot"]
     if "quickstart" in which:
         quickstart()
     if "pca" in which:
@@ -327,6 +369,8 @@ if __name__ == "__main__":
     if "gmm" in which:
         gmm("gmm_small", 300, 3, 5)
         gmm_doc()
+    if "dot" in which:
+        summultiply_nodes()
     if "rot" in which:
         pca_rotated()
     if "gmc" in which:
