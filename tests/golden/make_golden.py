@@ -352,8 +352,28 @@ def summultiply_nodes():
     save("summultiply_nodes", **out)
 
 
+def mixture_ard(name="mixture_ard", N=120, K=3, iters=6):
+    """Mixture of scalar GaussianARD components (mixture.py:26-488 with a mixed class other than Gaussian)."""
+    np.random.seed(8)
+    y = np.concatenate([np.random.randn(N // 3) - 4, 0.5 * np.random.randn(N // 3), 2 * np.random.randn(N - 2 * (N // 3)) + 5])
+    alpha = Dirichlet(1e-3 * np.ones(K), name="alpha")
+    Z = Categorical(alpha, plates=(N,), name="Z")
+    mu = GaussianARD(0, 1e-3, plates=(K,), name="mu")
+    tau = Gamma(1e-3, 1e-3, plates=(K,), name="tau")
+    Y = Mixture(Z, GaussianARD, mu, tau, name="Y")
+    Z_init = np.random.RandomState(2).dirichlet(np.ones(K), size=N)
+    Z.initialize_from_value(np.argmax(Z_init, axis=-1))
+    Y.observe(y)
+    Q = VB(Y, mu, tau, Z, alpha)
+    Q.update(repeat=iters, verbose=False, tol=0)
+    out = dict(y=y, Z_init=Z_init, L=Q.L[:iters])
+    for nm, node in (("Z", Z), ("mu", mu), ("tau", tau), ("alpha", alpha)):
+        node_state(nm, node, out)
+    save(name, **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["quickstart", "pca", "linalg", "summul", "dist", "gmm", "gmc", "rot", "dot"]
+    which = sys.argv[1:] or ["quickstart", "pca", "linalg", "summul", "dist", "gmm", "gmc", "rot", "dot", "mixard"]
     if "quickstart" in which:
         quickstart()
     if "pca" in which:
@@ -369,6 +389,8 @@ if __name__ == "__main__":
     if "gmm" in which:
         gmm("gmm_small", 300, 3, 5)
         gmm_doc()
+    if "mixard" in which:
+        mixture_ard()
     if "dot" in which:
         summultiply_nodes()
     if "rot" in which:

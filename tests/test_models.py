@@ -216,3 +216,25 @@ def test_gmm_doc_example(backend, fused, capsys):
     assert "Iteration 61: loglike=-8.888464e+02" in out
     assert "Converged at iteration 61." in out
     close(Q.L[:Q.iter], g["L"], rtol=1e-7)
+
+
+def test_mixture_of_gaussian_ard_components(backend):
+    """mixture.py:26-488 with a mixed class other than Gaussian (per-node path: no fused plan for it)."""
+    from bayespy_b200.nodes import GaussianARD, Gamma, Dirichlet, Categorical, Mixture
+    from bayespy_b200.inference import VB
+    g = golden("mixture_ard")
+    N, K = len(g["y"]), 3
+    alpha = Dirichlet(1e-3 * np.ones(K), name="alpha")
+    Z = Categorical(alpha, plates=(N,), name="Z")
+    mu = GaussianARD(0, 1e-3, plates=(K,), name="mu")
+    tau = Gamma(1e-3, 1e-3, plates=(K,), name="tau")
+    Y = Mixture(Z, GaussianARD, mu, tau, name="Y")
+    Z.initialize_from_value(np.argmax(g["Z_init"], axis=-1))
+    Y.observe(g["y"])
+    Q = VB(Y, mu, tau, Z, alpha)
+    iters = len(g["L"])
+    Q.update(repeat=iters, verbose=False, tol=0)
+    np.testing.assert_allclose(Q.L[:iters], g["L"], rtol=1e-8)
+    np.testing.assert_allclose(np.asarray(Z.u[0]), g["Z_u0"], rtol=1e-7, atol=1e-12)
+    np.testing.assert_allclose(np.asarray(mu.u[0]), g["mu_u0"], rtol=1e-8)
+    np.testing.assert_allclose(np.asarray(tau.u[0]), g["tau_u0"], rtol=1e-8)
