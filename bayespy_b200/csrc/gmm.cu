@@ -17,8 +17,7 @@
 // then the CTA accumulates the K*(1+D+D^2) statistics in registers, each
 // thread owning a fixed subset of (k, feature) pairs across all tiles.
 // Deterministic: per-CTA partials reduced in a fixed order by a second kernel.
-// TODO(next): move both contractions onto the fp64 tensor pipe (DMMA) — the
-// quadratic form is a (rows x F) x (F x K) GEMM in the monomial features of y.
+// (Kept for D > 8, K > 64 and for bpk_gmm_stats; the tensor-pipe kernel v1 below serves the rest.)
 #include "common.cuh"
 #include <stdlib.h>
 

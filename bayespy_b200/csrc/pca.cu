@@ -14,14 +14,15 @@
 //   S_yx = sum_n y_n x_n^T (M x K),  S_xx = sum_n x_n x_n^T (K x K),  s_x = sum_n x_n.
 // Algorithmic traffic: M*8 B read + K*8 B written per column (640 B at 64x16).
 //
-// Mapping (sm_100a): persistent grid of one 256-thread CTA per SM; Y tiles of
-// 64 x T doubles stream through a cp.async ring in shared memory (padded pitch
-// T+4 -> conflict-free fragment reads); both GEMM-shaped contractions run on
-// the fp64 tensor pipe with mma.sync.m8n8k4.f64 (tcgen05 has no fp64 kind);
-// A lives in registers as 32 fragments for the whole kernel; each warp owns
-// NT columns of a tile and a private S_yx/S_xx accumulator set in registers;
-// partials are reduced warp->CTA in smem and CTA->grid by a second tiny
-// kernel in a fixed order (deterministic, no atomics).
+// Two kernels implement it (both: persistent grid, one CTA per SM, both GEMM-shaped
+// contractions on the fp64 tensor pipe with mma.sync.m8n8k4.f64 — tcgen05 has no fp64
+// kind —, per-CTA partial statistics reduced in a fixed order: deterministic, no atomics):
+//   pca_xsweep_ws_kernel  (16-byte aligned inputs, the normal case; further down) 16 warps,
+//       warp-specialised X / S roles, TMA tensor-map loads with 128B swizzle, mbarrier ring;
+//       as <FUSED> it is the whole device-resident VB loop (pca_vb_ops.cuh tail, grid barriers).
+//   pca_xsweep_kernel     (v1, kept for odd N / unaligned Y) 8 warps of 220 registers, Y tiles of
+//       64 x T doubles through a cp.async ring (padded pitch T+4), A as 32 register fragments,
+//       each warp a private S_yx/S_xx accumulator set, grid reduction by pca_stats_final_kernel.
 #include "common.cuh"
 #include <cuda.h>
 #include <stdlib.h>
@@ -862,7 +863,7 @@ extern "C" int bpk_sumsq(const double *Y, const uint8_t *mask, int64_t count, do
 // v0: one warp per column builds Lam_n = diag(alpha) + tau sum_m mask[m,n] <w_m w_m^T>
 // in shared memory, factors/inverts it with the warp-cooperative routines of linalg.cu,
 // and writes x_n, Cov_n, g_n.  The mask-weighted statistics are then two plate-sums over
-// n (bpk_sum_multiply).  TODO(next): fuse the statistics into the column kernel and move
+// n (bpk_sum_multiply).  Next: fuse the statistics into the column kernel and move
 // the two M x K^2 contractions onto DMMA (they are GEMMs with the mask as one operand).
 #define MLD(D) SPD_LD(D)
 #define m_warp_chol_upper spd_warp_chol_upper
