@@ -154,3 +154,38 @@ def mvdot(A, b, ndim=1):
     cols = [("c", i) for i in range(ndim)]
     r = D.sum_product([A, b], [pk[npl - pa:] + rows + cols, pk[npl - pb:] + cols], pk + rows)
     return r if on_dev else r.numpy()
+
+
+def block_banded_solve(A, B, y):
+    """Symmetric block-tridiagonal SPD system (linalg.py:468-575): ``A`` (..., N, D, D) diagonal blocks,
+    ``B`` (..., N-1, D, D) super-diagonal blocks, ``y`` (..., N, D).  Returns the diagonal blocks ``V`` and the
+    super-diagonal blocks ``C`` of the inverse, the solution ``x`` and the log-determinant — one
+    ``bpk_block_banded_solve`` launch sequence (parallel in time) instead of the reference's loop over N.
+    Leading plate axes of the three arguments broadcast like in the reference."""
+    on_dev = _dev(A) or _dev(B) or _dev(y)
+    A, B, y = D.asarray(A), D.asarray(B), D.asarray(y)
+    if y.ndim < 2 or A.ndim < 3 or B.ndim < 3:
+        raise ValueError("block_banded_solve: A (...,N,D,D), B (...,N-1,D,D), y (...,N,D) expected")
+    N, Dn = y.shape[-2], y.shape[-1]
+    if A.shape[-3] != N:
+        raise ValueError("The number of diagonal blocks is incorrect")
+    if tuple(A.shape[-2:]) != (Dn, Dn):
+        raise ValueError("The diagonal blocks have wrong shape")
+    if B.shape[-3] != N - 1:
+        raise ValueError("The number of super-diagonal blocks is incorrect")
+    if N > 1 and tuple(B.shape[-2:]) != (Dn, Dn):
+        raise ValueError("The diagonal blocks have wrong shape")
+    plates = tuple(np.broadcast_shapes(tuple(A.shape[:-3]), tuple(B.shape[:-3]), tuple(y.shape[:-2])))
+    batch = _flat(plates)
+    Ab = A.broadcast_to(plates + (N, Dn, Dn)).contiguous()
+    Bb = B.broadcast_to(plates + (N - 1, Dn, Dn)).contiguous() if N > 1 else DArray.empty((1,))
+    yb = y.broadcast_to(plates + (N, Dn)).contiguous()
+    V = DArray.empty(plates + (N, Dn, Dn))
+    C = DArray.empty(plates + (max(N - 1, 1), Dn, Dn))
+    x = DArray.empty(plates + (N, Dn))
+    ld = DArray.empty(plates)
+    _bpk.get().block_banded_solve(Ab.ptr, Bb.ptr, yb.ptr, batch, N, Dn, V.ptr, C.ptr, x.ptr, ld.ptr, True)
+    C = C.slice_axis(len(plates), 0, N - 1) if N > 1 else DArray.empty(plates + (0, Dn, Dn))
+    if on_dev:
+        return V, C, x, ld
+    return V.numpy(), C.numpy(), x.numpy(), ld.numpy()

@@ -141,3 +141,22 @@ def test_block_banded_long_chain_vs_oracle(backend, T, Dm):
     np.testing.assert_allclose(C.numpy(), hC, rtol=1e-9, atol=1e-12)
     np.testing.assert_allclose(x.numpy(), hx, rtol=1e-9, atol=1e-12)
     np.testing.assert_allclose(float(ld.numpy()), hl[0], rtol=1e-12)
+
+
+def test_utils_linalg_block_banded_solve_api(backend):
+    """The drop-in function of seam 1 (utils.linalg.block_banded_solve): NumPy in -> NumPy out, plates broadcast."""
+    from bayespy_b200.utils import linalg
+    g = golden("block_banded")
+    V, C, x, ld = linalg.block_banded_solve(g["A_b"], g["B_b"], g["y_b"])
+    np.testing.assert_allclose(V, g["V_b"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(C, g["C_b"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(x, g["x_b"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(ld, g["ldet_b"], rtol=1e-12)
+    # two right-hand sides against one matrix: plates (2,) from y only
+    y2 = np.stack([g["y_b"], 2 * g["y_b"]])
+    V2, C2, x2, ld2 = linalg.block_banded_solve(g["A_b"], g["B_b"], y2)
+    assert V2.shape == (2,) + g["V_b"].shape and ld2.shape == (2,)
+    np.testing.assert_allclose(x2[1], 2 * g["x_b"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(V2[1], g["V_b"], rtol=1e-9, atol=1e-12)
+    with pytest.raises(ValueError):
+        linalg.block_banded_solve(g["A_b"][:-1], g["B_b"], g["y_b"])
