@@ -286,12 +286,12 @@ __device__ __forceinline__ int ws_off(int m, int c) {
 // Self-resetting grid barrier (all CTAs are co-resident: one persistent CTA per SM).
 // bar[0] = arrival count, bar[1] = epoch.
 // Spin with a watchdog: if the grid is not fully co-resident (another context on the GPU) or a CTA died, give up
-// after ~4 s, raise error bit 8 in *err and let the kernel terminate instead of hanging the device.
+// after ~60 s, raise error bit 8 in *err and let the kernel terminate instead of hanging the device.
 __device__ __forceinline__ void grid_spin(unsigned int *bar, unsigned int target, int *err) {
     const long long t0 = clock64();
     while (*(volatile unsigned int *)&bar[1] != target) {
         __nanosleep(32);
-        if (clock64() - t0 > 8000000000ll) {
+        if (clock64() - t0 > 120000000000ll) {     // ~60 s: longer than the peer-exchange watchdog of CTA 0
             if (err) atomicOr(err, 8);
             break;
         }

@@ -194,7 +194,7 @@ static __device__ __noinline__ void pca_vb_ops_t(const PcaVbArgs &p, double *sm,
                     unsigned long long v;
                     do {
                         asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(g) : "memory");
-                        if (v < seq && clock64() - t0 > 6000000000ll) { atomicOr(&ctrl[2], 4); break; }   // ~3 s: a peer died
+                        if (v < seq && clock64() - t0 > 40000000000ll) { atomicOr(&ctrl[2], 4); break; }   // ~20 s: a peer died (ranks may start seconds apart on a busy host)
                     } while (v < seq);
                 }
                 __syncthreads();
