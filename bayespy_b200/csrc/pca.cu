@@ -338,7 +338,10 @@ __device__ __forceinline__ void grid_wait(unsigned int *bar, unsigned int &epoch
 // FUSED: the launch is one whole VB sweep of the resident loop — after the data pass the grid
 // reduces its partial statistics in place (two grid barriers, fixed order) and CTA 0 runs the
 // sweep's small ops (pca_vb_ops: STATS .. BOUND, XPRE of the next sweep) before the kernel ends.
-template <int NT, int STAGES, int DIST, bool COMPUTE_X, bool FUSED>
+// DERIVE_SXX (fused launches only): the S-warps skip the three S_xx DMMAs per 4 columns; since x_n = A y_n + b
+// exactly, sum x x^T = A (sum y x^T) + b (sum x)^T is formed from S_yx and s_x in the tail (pca_vb_ops, STATS),
+// after the cross-rank exchange — 8.6 % less work on the binding fp64 pipe, still one pass over Y per sweep.
+template <int NT, int STAGES, int DIST, bool COMPUTE_X, bool FUSED, bool DERIVE_SXX>
 __global__ void __launch_bounds__(2 * WS_PAIRS * 32, 1)
 pca_xsweep_ws_kernel(const __grid_constant__ CUtensorMap tmapY, int64_t M, int64_t N, int K,
                      const double *A, const double *bvec,
@@ -517,9 +520,11 @@ pca_xsweep_ws_kernel(const __grid_constant__ CUtensorMap tmapY, int64_t M, int64
                     dmma884(syx[mb][0][0], syx[mb][0][1], ya, xf0);
                     dmma884(syx[mb][1][0], syx[mb][1][1], ya, xf1);
                 }
-                dmma884(sxx[0][0], sxx[0][1], xf0, xf0);
-                dmma884(sxx[1][0], sxx[1][1], xf0, xf1);
-                dmma884(sxx[2][0], sxx[2][1], xf1, xf1);
+                if (!DERIVE_SXX) {
+                    dmma884(sxx[0][0], sxx[0][1], xf0, xf0);
+                    dmma884(sxx[1][0], sxx[1][1], xf0, xf1);
+                    dmma884(sxx[2][0], sxx[2][1], xf1, xf1);
+                }
             }
             __syncwarp();
             if (lane == 0) { mbar_arrive(&xfree[p * 2 + b]); mbar_arrive(&empty[slot]); }
@@ -644,16 +649,22 @@ static int pca_launch_ws(const double *Y, int64_t M, int64_t N, int K, const dou
         PcaVbArgs vb = *tail;
         vb.partial = partial + (size_t)grid * PCA_NSTAT;     // the grid-reduced statistics
         vb.nparts = 1;
-        auto kern = pca_xsweep_ws_kernel<NT, STAGES, DIST, true, true>;
-        BPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        BPK_LAUNCH(kern, grid, 2 * WS_PAIRS * 32, smem, tmap, M, N, K, A, b, X, partial, ntiles, stop, g_pca_gbar, vb, smem / sizeof(double));
+        if (vb.derive_sxx) {
+            auto kern = pca_xsweep_ws_kernel<NT, STAGES, DIST, true, true, true>;
+            BPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            BPK_LAUNCH(kern, grid, 2 * WS_PAIRS * 32, smem, tmap, M, N, K, A, b, X, partial, ntiles, stop, g_pca_gbar, vb, smem / sizeof(double));
+        } else {
+            auto kern = pca_xsweep_ws_kernel<NT, STAGES, DIST, true, true, false>;
+            BPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            BPK_LAUNCH(kern, grid, 2 * WS_PAIRS * 32, smem, tmap, M, N, K, A, b, X, partial, ntiles, stop, g_pca_gbar, vb, smem / sizeof(double));
+        }
         *partial_out = partial + (size_t)grid * PCA_NSTAT;
         *nparts_out = 1;
         return BPK_OK;
     }
     PcaVbArgs none;
-    none.nops = 0; none.nops_last = 0; none.niter = 1; none.dry_every = 0;
-    auto kern = pca_xsweep_ws_kernel<NT, STAGES, DIST, COMPUTE_X, false>;
+    none.nops = 0; none.nops_last = 0; none.niter = 1; none.dry_every = 0; none.derive_sxx = 0;
+    auto kern = pca_xsweep_ws_kernel<NT, STAGES, DIST, COMPUTE_X, false, false>;
     BPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     BPK_LAUNCH(kern, grid, 2 * WS_PAIRS * 32, smem, tmap, M, N, K, A, b, X, partial, ntiles, stop, (unsigned int *)nullptr, none, (size_t)0);
     *partial_out = partial;

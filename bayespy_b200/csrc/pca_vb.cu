@@ -93,7 +93,7 @@ extern "C" int bpk_pca_vb_run(const double *Y, int64_t M, int64_t N, int K, doub
     a.st = state; a.partial = nullptr; a.nparts = 0; a.local_stats = nranks > 1;
     a.Lhist = Lhist; a.cap = cap; a.ctrl = ctrl; a.nops = 0;
     a.xranks = 1; a.xrank = 0;
-    a.niter = 1; a.nops_last = 0;
+    a.niter = 1; a.nops_last = 0; a.derive_sxx = 0;
     a.dry_every = getenv("BPK_VB_DRY_FIRST_ONLY") ? 0 : 1;
     a.dbg = nullptr;
     if (getenv("BPK_VB_DEBUG")) {
@@ -140,6 +140,7 @@ extern "C" int bpk_pca_vb_run(const double *Y, int64_t M, int64_t N, int K, doub
                 tail.nops_last = tail.nops;
                 for (int i = 0; i < kx; ++i) tail.ops[tail.nops++] = ops[i];
                 tail.niter = niter;
+                tail.derive_sxx = getenv("BPK_PCA_SXX_DMMA") ? 0 : 1;
                 int tid = -1;
                 if (g_vb_timer_pos < g_vb_ntimers) tid = g_vb_timers[g_vb_timer_pos++];
                 if (tid >= 0) bpk_timer_record(tid, 0);

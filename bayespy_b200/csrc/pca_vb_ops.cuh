@@ -69,6 +69,7 @@ struct PcaVbArgs {
     int xranks, xrank;       // > 1: STATS all-reduces over the peer-memory windows below (no NCCL call)
     double *xwin[BPK_XCHG_MAXRANKS];
     int niter;               // fused sweep kernel: sweeps per launch; ops[0..nops) follow every sweep but the last,
+    int derive_sxx;          // 1: the sweep kernel did not accumulate S_xx; STATS forms it as A S_yx + b s_x^T
     int dry_every;           // 1: CTA 0 dry-runs the tail in every sweep of the launch, 0: only in the first
     int nops_last;           // ops[0..nops_last) the last one (the ops of the next sweep's head are dropped)
     int nops;
@@ -208,6 +209,27 @@ static __device__ __noinline__ void pca_vb_ops_t(const PcaVbArgs &p, double *sm,
                 __syncthreads();
                 if (t == 0) *(volatile unsigned long long *)own = seq;
                 vb_stamp(dbg, 43);
+            }
+            if (p.derive_sxx) {
+                // x_n = A y_n + b  =>  sum_n x_n x_n^T = A (sum_n y_n x_n^T) + b (sum_n x_n)^T, with the A, b this sweep used
+                __syncthreads();
+                const double *Sg = st + o[F_STATS];
+                for (int e = t; e < K * K; e += VBT) {
+                    const int i = e / K, j = e - i * K;
+                    double s0 = 0.0, s1 = 0.0;
+                    int m = 0;
+                    for (; m + 1 < M; m += 2) {
+                        s0 += st[o[F_A] + i * M + m] * Sg[m * K + j];
+                        s1 += st[o[F_A] + i * M + m + 1] * Sg[(m + 1) * K + j];
+                    }
+                    if (m < M) s0 += st[o[F_A] + i * M + m] * Sg[m * K + j];
+                    G[i * K + j] = (s0 + s1) + st[o[F_BX] + i] * Sg[M * K + K * K + j];
+                }
+                __syncthreads();
+                for (int e = t; e < K * K; e += VBT) {
+                    const int i = e / K, j = e - i * K;
+                    st[o[F_STATS] + M * K + e] = 0.5 * (G[i * K + j] + G[j * K + i]);
+                }
             }
         } else if (op == BPK_VBOP_SXXT) {
             // sum_n <x x^T> = N Cov_x + S_xx
