@@ -113,3 +113,74 @@ def test_shard_bounds():
         assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
         sizes = [b - a for a, b in blocks]
         assert max(sizes) - min(sizes) <= 1
+
+
+def _rdzv_worker(rank, world, port, gloo_port, q):
+    """parallel.init_from_env end to end on CPU: NCCL-id file rendezvous, IPC-handle exchange, cleanup."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_PORT=str(port),
+                      TORCHELASTIC_RUN_ID="pytest-%d" % port)
+    import torch
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % gloo_port, rank=rank, world_size=world)
+    from oracle.bpk_ref import RefBackend
+    from bayespy_b200 import _bpk, parallel
+
+    class FakeDevice(RefBackend):
+        opened = None
+
+        def comm_unique_id(self):
+            return bytes([7]) * 128
+
+        def comm_init(self, uid, nranks, r):
+            assert uid == bytes([7]) * 128
+            super().comm_init(uid, nranks, r)
+
+        def xchg_create(self):
+            return bytes([100 + rank]) * 64
+
+        def xchg_open(self, handles, nranks, r):
+            FakeDevice.opened = (list(handles), nranks, r)
+
+        def xchg_close(self):
+            FakeDevice.opened = None
+
+    be = FakeDevice()
+
+    def hook(v):
+        t = torch.from_numpy(np.ascontiguousarray(v))
+        dist.all_reduce(t)
+        return t.numpy()
+    be._allreduce_hook = hook
+    _bpk._set_backend_for_testing(be)
+    try:
+        w, r = parallel.init_from_env(timeout=60.0)
+        ok = (w, r) == (world, rank) and parallel._state.get("p2p") is True
+        handles, nr, rr = FakeDevice.opened
+        ok = ok and nr == world and rr == rank and handles == [bytes([100 + k]) * 64 for k in range(world)]
+        parallel.barrier()
+        left = [f for f in os.listdir("/tmp") if f.startswith("bpk_rdzv_%d_pytest-%d" % (port, port))]
+        q.put((rank, bool(ok), left if rank == 0 else []))
+    except Exception:                                         # pragma: no cover
+        import traceback
+        q.put((rank, False, traceback.format_exc()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_init_from_env_rendezvous_and_peer_window_exchange(world):
+    import multiprocessing as mp
+    import time
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port, gloo_port = _free_port(), _free_port()
+    procs = [ctx.Process(target=_rdzv_worker, args=(r, world, port, gloo_port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, ok, info in res:
+        assert ok, "rank %d: %s" % (rank, info)
+    time.sleep(0.2)
+    assert not [f for f in os.listdir("/tmp") if f.startswith("bpk_rdzv_%d_pytest-%d" % (port, port))]
