@@ -48,6 +48,9 @@ def init_from_env(timeout=300.0):
     r = int(os.environ.get("RANK", "0"))
     be = _bpk.get()              # device = LOCAL_RANK (see _bpk.get)
     if w > 1:
+        # NCCL writes its version / debug lines to stdout by default; keep stdout for the caller's own output
+        # (bench.py prints exactly one JSON line there)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         path = _rdzv_path()
         t_start = time.time()
         if r == 0:
