@@ -1,0 +1,1 @@
+"""Host-side node graph of the engine: plates, masks, moments and messages on device arrays."""
