@@ -23,7 +23,10 @@ from .node import Deterministic, Node
 from .wishart import ensure_wishart
 
 
-class GaussianMarkovChainDistribution(Distribution):
+class _SingleChainDistribution(Distribution):
+    """The plates == () case, kept verbatim as measured and validated on the GPU in round 1; the general
+    class below delegates to it whenever the chain has no plates."""
+
 
     def __init__(self, N, Dm):
         self.N, self.D = int(N), int(Dm)
@@ -148,6 +151,169 @@ class GaussianMarkovChainDistribution(Distribution):
         raise ValueError("Parent index out of bounds")
 
 
+
+def _pk(n):
+    """Plate keys, right-aligned: n keys ('p', n) ... ('p', 1)."""
+    return [("p", j) for j in range(n, 0, -1)]
+
+
+class GaussianMarkovChainDistribution(Distribution):
+    """All arrays carry the chain's plates P in front: phi / u are P+(N,D), P+(N,D,D), P+(N-1,D,D).
+    Parents may have fewer (broadcast) plates; A and nu additionally carry the state axis as their last plate."""
+
+    def __init__(self, N, Dm, plates=()):
+        self.N, self.D = int(N), int(Dm)
+        self.plates = tuple(int(p) for p in plates)
+        self._single = _SingleChainDistribution(N, Dm) if not self.plates else None
+
+    # -- plates: (mu, Lambda) see the chain's plates; A and nu additionally carry the state axis (D,)
+    def plates_to_parent(self, index, plates):
+        return tuple(plates) if index < 2 else tuple(plates) + (self.D,)
+
+    def plates_from_parent(self, index, plates):
+        return tuple(plates) if index < 2 else tuple(plates[:-1])
+
+    def compute_weights_to_parent(self, index, weights):
+        w = np.asarray(weights)
+        return w if index < 2 else w.reshape(w.shape + (1,))
+
+    def _parents(self, u_mu, u_Lambda, u_A, u_nu):
+        """Parent moments with their own (possibly shorter) plate axes in front of fixed trailing dims."""
+        Dm = self.D
+        mu = D.asarray(u_mu[0]) if u_mu is not None else None                 # Pm + (D,)
+        mumu = dense(u_mu[1]) if u_mu is not None else None                  # Pm + (D, D)
+        Lam = D.asarray(u_Lambda[0]) if u_Lambda is not None else None        # PL + (D, D)
+        logdetL = D.asarray(u_Lambda[1]) if u_Lambda is not None else None    # PL
+        A = D.asarray(u_A[0]) if u_A is not None else None                    # PA + (D, D): row d = <a_d>
+        AA = dense(u_A[1]) if u_A is not None else None                      # PA + (D, D, D)
+        nu = lognu = None
+        if u_nu is not None:
+            nu = D.asarray(u_nu[0])
+            lognu = D.asarray(u_nu[1])
+            if nu.ndim == 0 or nu.shape[-1] != Dm:
+                nu = nu.broadcast_to(tuple(nu.shape[:-1]) + (Dm,)) if nu.ndim else nu.broadcast_to((Dm,))
+                lognu = lognu.broadcast_to(tuple(lognu.shape[:-1]) + (Dm,)) if lognu.ndim else lognu.broadcast_to((Dm,))
+        for arr, nd, what in ((A, 2, "A"), (nu, 1, "nu")):
+            if arr is not None and arr.ndim - nd > len(self.plates):
+                raise NotImplementedError("GaussianMarkovChain: time-varying %s (plates (N-1, D)) is not supported yet" % what)
+        return mu, mumu, Lam, logdetL, A, AA, nu, lognu
+
+    # -- natural parameters (gaussian_markov_chain.py:542-627)
+    def compute_phi_from_parents(self, u_mu, u_Lambda, u_A, u_nu, mask=True):
+        if self._single is not None:
+            return self._single.compute_phi_from_parents(u_mu, u_Lambda, u_A, u_nu, mask=mask)
+        N, Dm, P = self.N, self.D, self.plates
+        npl = len(P)
+        mu, _, Lam, _, A, AA, nu, _ = self._parents(u_mu, u_Lambda, u_A, u_nu)
+        pk = _pk(npl)
+        # x_0: phi0[..., 0, :] = <Lambda> <mu>,  phi1[..., 0, :, :] = -1/2 <Lambda>
+        Lmu = D.sum_product([Lam, mu], [pk[npl - (Lam.ndim - 2):] + ["i", "j"], pk[npl - (mu.ndim - 1):] + ["j"]], pk + ["i"])
+        phi0 = DArray.zeros(P + (N, Dm))
+        D.copy_into(phi0.slice_axis(npl, 0, 1), Lmu.reshape(tuple(Lmu.shape[:-1]) + (1, Dm)))
+        phi1 = DArray.zeros(P + (N, Dm, Dm))
+        first = phi1.slice_axis(npl, 0, 1)
+        D._ew("AFFINE", first.shape, first, [Lam.reshape(tuple(Lam.shape[:-2]) + (1, Dm, Dm))], alpha=-0.5, beta=0.0)
+        phi2 = DArray.empty(P + (max(N - 1, 0), Dm, Dm))
+        if N > 1:
+            # blocks n >= 1: -1/2 diag(nu);  blocks n <= N-2: -1/2 sum_d nu_d <a_d a_d^T>
+            tail = phi1.slice_axis(npl, 1, N)
+            D._ew("AFFINE", tail.diag_view(1).shape, tail.diag_view(1), [nu.reshape(tuple(nu.shape[:-1]) + (1, Dm))],
+                  alpha=-0.5, beta=0.0)
+            nk, ak = nu.ndim - 1, AA.ndim - 3
+            S = D.sum_product([nu, AA], [pk[npl - nk:] + ["d"], pk[npl - ak:] + ["d", "i", "j"]], pk + ["i", "j"], scale=-0.5)
+            head = phi1.slice_axis(npl, 0, N - 1)
+            D._ew("ADD", head.shape, head, [head, S.reshape(tuple(S.shape[:-2]) + (1, Dm, Dm))])
+            # super-diagonal blocks (sum of super and sub): phi2[..., n, i, j] = nu_j <A>[j, i]
+            nuA_T = D.mul(A, nu.add_trailing(1)).swap_last2()
+            D.copy_into(phi2, nuA_T.reshape(tuple(nuA_T.shape[:-2]) + (1, Dm, Dm)))
+        return [phi0, phi1, phi2]
+
+    # -- E[log normaliser of the prior] (:251-267, :629-657)
+    def compute_cgf_from_parents(self, u_mu, u_Lambda, u_A, u_nu):
+        if self._single is not None:
+            return self._single.compute_cgf_from_parents(u_mu, u_Lambda, u_A, u_nu)
+        npl = len(self.plates)
+        _, mumu, Lam, logdetL, _, _, _, lognu = self._parents(u_mu, u_Lambda, u_A, u_nu)
+        pk = _pk(npl)
+        kL, km = pk[npl - (Lam.ndim - 2):], pk[npl - (mumu.ndim - 2):]
+        out_pl = pk[npl - max(Lam.ndim - 2, mumu.ndim - 2):]
+        t = D.sum_product([Lam, mumu], [kL + ["i", "j"], km + ["i", "j"]], out_pl)
+        g = D.axpby(-0.5, t, 0.5, logdetL)
+        s = D.sum_product([lognu], [pk[npl - (lognu.ndim - 1):] + ["d"]], pk[npl - (lognu.ndim - 1):], scale=0.5 * (self.N - 1))
+        return D.add(g, s)
+
+    # -- smoother (:89-123)
+    def compute_moments_and_cgf(self, phi, mask=True):
+        if self._single is not None:
+            return self._single.compute_moments_and_cgf(phi, mask=mask)
+        N, Dm, P = self.N, self.D, self.plates
+        npl = len(P)
+        batch = int(np.prod(P, dtype=np.int64)) if P else 1
+        be = _bpk.get()
+        y = phi[0].broadcast_to(P + (N, Dm)).contiguous()
+        A = D.mul(phi[1].broadcast_to(P + (N, Dm, Dm)), -2.0)
+        B = D.mul(phi[2].broadcast_to(P + (N - 1, Dm, Dm)), -1.0) if N > 1 else DArray.empty((1,))
+        V, x = DArray.empty(P + (N, Dm, Dm)), DArray.empty(P + (N, Dm))
+        C = DArray.empty(P + (max(N - 1, 1), Dm, Dm))
+        ld = DArray.empty(P)
+        be.block_banded_solve(A.ptr, B.ptr, y.ptr, batch, N, Dm, V.ptr, C.ptr, x.ptr, ld.ptr, True)
+        u1 = D.add(V, D.mul(x.add_trailing(1), x.expand_dims(-2)))
+        if N > 1:
+            xp = x.slice_axis(npl, 0, N - 1)
+            xn = x.slice_axis(npl, 1, N)
+            u2 = D.add(C.slice_axis(npl, 0, N - 1), D.mul(xp.add_trailing(1), xn.expand_dims(-2)))
+        else:
+            u2 = DArray.empty(P + (0, Dm, Dm))
+        pk = _pk(npl)
+        g = D.axpby(-0.5, D.sum_product([x, y], [pk + ["n", "i"], pk + ["n", "i"]], pk), 0.5, ld)
+        return [x, u1, u2], g
+
+    def compute_fixed_moments_and_f(self, x, mask=True):
+        x = np.asarray(x, dtype=np.float64)
+        if x.shape[-2:] != (self.N, self.D):
+            raise ValueError("Invalid shape")
+        u1 = x[..., :, None] * x[..., None, :]
+        u2 = x[..., :-1, :, None] * x[..., 1:, None, :]
+        return [D.asarray(x), D.asarray(u1), D.asarray(u2)], -0.5 * self.N * self.D * LOG2PI
+
+    # -- messages (:443-527 combined with gaussian.py:2351-2371 / :2496-2522)
+    def compute_message_to_parent(self, parent, index, u, u_mu, u_Lambda, u_A, u_nu):
+        if self._single is not None:
+            return self._single.compute_message_to_parent(parent, index, u, u_mu, u_Lambda, u_A, u_nu)
+        N, Dm, P = self.N, self.D, self.plates
+        npl = len(P)
+        pk = _pk(npl)
+        x, xx, xpxn = u
+        mu, mumu, Lam, _, A, AA, nu, _ = self._parents(u_mu, u_Lambda, u_A, u_nu)
+        if index in (0, 1):
+            x0 = x.slice_axis(npl, 0, 1).reshape(P + (Dm,))
+            x0x0 = xx.slice_axis(npl, 0, 1).reshape(P + (Dm, Dm))
+            if index == 0:
+                kL = pk[npl - (Lam.ndim - 2):]
+                m0 = D.sum_product([Lam, x0], [kL + ["i", "j"], pk + ["j"]], pk + ["i"])
+                return [m0, D.mul(Lam, -0.5)]
+            xm = D.mul(x0.add_trailing(1), mu.expand_dims(-2))           # x0 mu^T, P + (D, D)
+            t = D.add(D.sub(D.sub(x0x0, xm), xm.swap_last2()), mumu)
+            return [D.mul(t, -0.5), D.asarray(0.5)]
+        if N < 2:
+            return [None, None]
+        # time sums of the chain's second moments (plates kept)
+        Sxx_head = D.sum_product([xx.slice_axis(npl, 0, N - 1)], [pk + ["n", "i", "j"]], pk + ["i", "j"])
+        Sxpxn = D.sum_product([xpxn], [pk + ["n", "i", "j"]], pk + ["i", "j"])
+        if index == 2:
+            # to a_d: [nu_d sum_n <x_{n+1,d} x_n>, -1/2 nu_d sum_n <x_n x_n^T>]   plates P + (D,), dims (D,), (D, D)
+            m0 = D.mul(Sxpxn.swap_last2(), nu.add_trailing(1))
+            m1 = D.mul(D.mul(Sxx_head.expand_dims(-3), nu.add_trailing(2)), -0.5)
+            return [m0, m1]
+        if index == 3:
+            ka = pk[npl - (A.ndim - 2):]
+            dxx = D.sum_product([xx.slice_axis(npl, 1, N).diag_view(1)], [pk + ["n", "d"]], pk + ["d"], scale=-0.5)
+            a = D.sum_product([Sxpxn, A], [pk + ["i", "d"], ka + ["d", "i"]], pk + ["d"])
+            b = D.sum_product([Sxx_head, AA], [pk + ["i", "j"], ka + ["d", "i", "j"]], pk + ["d"], scale=-0.5)
+            return [D.add(D.add(dxx, a), b), DArray.full(P + (Dm,), 0.5 * (N - 1)) if P else DArray.full((Dm,), 0.5 * (N - 1))]
+        raise ValueError("Parent index out of bounds")
+
+
 class GaussianMarkovChain(ExponentialFamily):
     """``GaussianMarkovChain(mu, Lambda, A, nu, n=None, name="")`` (gaussian_markov_chain.py:660-927)."""
     moment_kind = "gaussian_markov_chain"
@@ -162,18 +328,22 @@ class GaussianMarkovChain(ExponentialFamily):
         nu = ensure_gamma(nu)
         if tuple(A.dims[0]) != (Dm,) or tuple(A.plates[-1:]) != (Dm,):
             raise ValueError("A must be a collection of D vectors of length D: plates (D,), shape (D,)")
-        if len(A.plates) > 1 or len(nu.plates) > 1:
-            if n is None:
-                n = (A.plates[-2] if len(A.plates) > 1 else nu.plates[-2]) + 1
-            raise NotImplementedError("Time-varying dynamics (plates (N-1, D)) are not supported yet")
         if n is None:
-            raise ValueError("The length of the chain (keyword n) is required when the dynamics have no time plate")
+            raise ValueError("The length of the chain (keyword n) is required (time-varying dynamics, which would "
+                             "define it, are not supported yet)")
         self.N, self.D = int(n), int(Dm)
-        if plates not in (None, ()):
-            raise NotImplementedError("Plated chains are not supported yet")
-        dist = GaussianMarkovChainDistribution(self.N, self.D)
+        from .node import broadcast_plates
+        nu_pl = tuple(nu.plates[:-1]) if len(nu.plates) else ()
+        chain_plates = broadcast_plates(tuple(mu.plates), tuple(Lambda.plates), tuple(A.plates[:-1]), nu_pl)
+        if plates is not None:
+            plates = tuple(int(p) for p in plates)
+            chain_plates = broadcast_plates(chain_plates, plates)
+            if chain_plates != plates:
+                raise ValueError("The plates %s of the parents are not broadcastable to the given plates %s."
+                                 % (chain_plates, plates))
+        dist = GaussianMarkovChainDistribution(self.N, self.D, chain_plates)
         super().__init__(mu, Lambda, A, nu, dims=((self.N, Dm), (self.N, Dm, Dm), (self.N - 1, Dm, Dm)),
-                         distribution=dist, plates=(), name=name, initialize=initialize)
+                         distribution=dist, plates=chain_plates, name=name, initialize=initialize)
 
     def _to_gaussian(self):
         if getattr(self, "_as_gaussian", None) is None:

@@ -372,8 +372,36 @@ def mixture_ard(name="mixture_ard", N=120, K=3, iters=6):
     save(name, **out)
 
 
+def lssm_plated(name="lssm_plated", M=5, N=30, D=3, P=2, iters=5):
+    """Two independent chains (plates (P,)) sharing the dynamics A and the loadings C
+    (gaussian_markov_chain.py:660-927 with plates)."""
+    from bayespy.nodes import GaussianMarkovChain, Dot
+    rs = np.random.RandomState(12)
+    y = rs.randn(M, P, N).cumsum(axis=-1) * 0.3 + rs.randn(M, P, N)
+    alpha = Gamma(1e-5, 1e-5, plates=(D,), name="alpha")
+    A = GaussianARD(0, alpha, shape=(D,), plates=(D,), name="A")
+    mu0 = rs.randn(P, D)
+    X = GaussianMarkovChain(mu0, 1e-3 * np.identity(D), A, np.ones(D), n=N, name="X")
+    assert X.plates == (P,)
+    gamma = Gamma(1e-5, 1e-5, plates=(D,), name="gamma")
+    C = GaussianARD(0, gamma, shape=(D,), plates=(M, 1, 1), name="C")
+    F = Dot(C, X, name="F")
+    assert F.plates == (M, P, N)
+    C_init = rs.randn(M, 1, 1, D)
+    C.initialize_from_value(C_init)
+    tau = Gamma(1e-5, 1e-5, name="tau")
+    Y = GaussianARD(F, tau, name="Y")
+    Y.observe(y)
+    Q = VB(X, C, gamma, A, alpha, tau, Y)
+    Q.update(repeat=iters, verbose=False, tol=0)
+    out = dict(y=y, C_init=C_init, mu0=mu0, L=Q.L[:iters])
+    for nm, node in (("X", X), ("C", C), ("A", A), ("alpha", alpha), ("tau", tau)):
+        node_state(nm, node, out)
+    save(name, **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["quickstart", "pca", "linalg", "summul", "dist", "gmm", "gmc", "rot", "dot", "mixard"]
+    which = sys.argv[1:] or ["quickstart", "pca", "linalg", "summul", "dist", "gmm", "gmc", "rot", "dot", "mixard", "gmcplates"]
     if "quickstart" in which:
         quickstart()
     if "pca" in which:
@@ -395,6 +423,8 @@ if __name__ == "__main__":
         summultiply_nodes()
     if "rot" in which:
         pca_rotated()
+    if "gmcplates" in which:
+        lssm_plated()
     if "gmc" in which:
         block_banded_vectors()
         lssm("lssm_small", 6, 40, 3)

@@ -160,3 +160,34 @@ def test_utils_linalg_block_banded_solve_api(backend):
     np.testing.assert_allclose(V2[1], g["V_b"], rtol=1e-9, atol=1e-12)
     with pytest.raises(ValueError):
         linalg.block_banded_solve(g["A_b"][:-1], g["B_b"], g["y_b"])
+
+
+def test_plated_chains_match_reference(oracle_backend):
+    """Two independent chains (plates (2,)) sharing A and C (gaussian_markov_chain.py with plates): bound trajectory
+    and moments against the reference.  Host logic + oracle only: the batched solver kernel itself is covered on the
+    GPU by test_block_banded_solve_batched_and_dense_inverse."""
+    from bayespy_b200.nodes import GaussianARD, GaussianMarkovChain, Gamma, Dot
+    from bayespy_b200.inference import VB
+    g = golden("lssm_plated")
+    M, P, N = g["y"].shape
+    Dm = g["mu0"].shape[-1]
+    alpha = Gamma(1e-5, 1e-5, plates=(Dm,), name="alpha")
+    A = GaussianARD(0, alpha, shape=(Dm,), plates=(Dm,), name="A")
+    X = GaussianMarkovChain(g["mu0"], 1e-3 * np.identity(Dm), A, np.ones(Dm), n=N, name="X")
+    assert tuple(X.plates) == (P,)
+    gamma = Gamma(1e-5, 1e-5, plates=(Dm,), name="gamma")
+    C = GaussianARD(0, gamma, shape=(Dm,), plates=(M, 1, 1), name="C")
+    F = Dot(C, X, name="F")
+    assert tuple(F.plates) == (M, P, N)
+    C.initialize_from_value(g["C_init"])
+    tau = Gamma(1e-5, 1e-5, name="tau")
+    Y = GaussianARD(F, tau, name="Y")
+    Y.observe(g["y"])
+    Q = VB(X, C, gamma, A, alpha, tau, Y)
+    iters = len(g["L"])
+    Q.update(repeat=iters, verbose=False, tol=0)
+    np.testing.assert_allclose(Q.L[:iters], g["L"], rtol=1e-8)
+    for nm, node in (("X", X), ("C", C), ("A", A), ("alpha", alpha), ("tau", tau)):
+        for i in range(len(node.u)):
+            np.testing.assert_allclose(np.asarray(node.u[i]), g["%s_u%d" % (nm, i)], rtol=1e-6, atol=1e-9,
+                                       err_msg="%s.u[%d]" % (nm, i))
