@@ -38,6 +38,7 @@ PROTOTYPES = {
     "bpk_shutdown": (C.c_int, []),
     "bpk_last_error": (C.c_char_p, []),
     "bpk_device_info": (C.c_int, [_ip, _ip, _ip, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "bpk_device_pci_bus_id": (C.c_int, [C.c_char_p, C.c_int]),
     "bpk_sync": (C.c_int, []),
     "bpk_launch_count": (C.c_uint64, []),
     "bpk_malloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint64]),
@@ -89,6 +90,7 @@ PROTOTYPES = {
     "bpk_pca_vb_field_name": (C.c_char_p, [C.c_int]),
     "bpk_pca_vb_run": (C.c_int, [_dp, C.c_int64, C.c_int64, C.c_int, _dp, _dp, _ip, C.c_int, C.c_int, C.c_int,
                                  C.c_int, C.c_double, _dp, C.c_int, _vp]),
+    "bpk_pca_vb_set_mode": (C.c_int, [C.c_int, _ip]),
     "bpk_pca_vb_set_timers": (C.c_int, [_ip, C.c_int]),
     "bpk_pca_vb_timers_used": (C.c_int, []),
     "bpk_debug_stamps": (C.c_int, [C.POINTER(C.c_uint64), C.c_int]),
@@ -155,6 +157,11 @@ class CudaBackend:
         t, f = C.c_uint64(), C.c_uint64()
         self._chk(self.lib.bpk_device_info(C.byref(a), C.byref(b), C.byref(c), C.byref(t), C.byref(f)))
         return dict(sm_count=a.value, cc=(b.value, c.value), hbm_total=t.value, hbm_free=f.value)
+
+    def pci_bus_id(self):
+        buf = C.create_string_buffer(32)
+        self._chk(self.lib.bpk_device_pci_bus_id(buf, 32))
+        return buf.value.decode().lower()
 
     def malloc(self, nbytes):
         p = C.c_void_p()
@@ -331,6 +338,11 @@ class CudaBackend:
         arr = (C.c_int * len(ops))(*ops)
         self._chk(self.lib.bpk_pca_vb_run(Y, M, N, K, X, state, arr, len(ops), int(niter), int(has_alpha),
                                           int(has_tau), float(tol), Lhist, int(cap), ctrl))
+
+    def pca_vb_set_mode(self, no_loop):
+        prev = C.c_int()
+        self._chk(self.lib.bpk_pca_vb_set_mode(int(bool(no_loop)), C.byref(prev)))
+        return bool(prev.value)
 
     def pca_vb_set_timers(self, ids):
         arr = (C.c_int * max(len(ids), 1))(*ids)

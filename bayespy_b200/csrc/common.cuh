@@ -24,15 +24,23 @@ struct BpkCtx {
 
 extern BpkCtx g_bpk;
 
-// peer-memory exchange window (runtime.cu); layout in doubles:
-//   [0]                      exchanges completed by this rank (written by its own kernels)
-//   [8 + par*R + r]          flag: sequence number of rank r's latest deposit with parity par
-//   [64 + (par*R + r)*CAP..] rank r's deposit (CAP doubles), R = BPK_XCHG_MAXRANKS
+// peer-memory exchange window (runtime.cu), one per rank, mapped into every peer through CUDA IPC.
+// Layout in 8-byte words:
+//   [0]                               exchanges completed by this rank (written by its own kernels only)
+//   [BPK_XCHG_DATA + ((par*R + r)*CAP + e)*2 .. +2)
+//                                     rank r's deposit of element e with sequence parity par, as two
+//                                     "LL" packets {seq32 : low half} {seq32 : high half} of the double.
+//   [BPK_XCHG_TOTALS + (par*CAP + e)*2 .. +2)
+//                                     the sum over ranks of element e, same packet format (local hand-off from
+//                                     the CTA that owns e to the CTA that runs the sweep's small ops).
+// Every 8-byte packet carries its own sequence tag and is written with ONE atomic store, so a reader
+// that sees the expected tag in both packets has the whole value: no fence, no separate flag, one NVLink
+// one-way latency per exchange (the protocol of NCCL's LL mode, widened to fp64 payloads).
 #define BPK_XCHG_MAXRANKS 8
 #define BPK_XCHG_CAP 2048
-#define BPK_XCHG_FLAGS 8
 #define BPK_XCHG_DATA 64
-#define BPK_XCHG_BYTES ((BPK_XCHG_DATA + 2 * BPK_XCHG_MAXRANKS * BPK_XCHG_CAP) * sizeof(double))
+#define BPK_XCHG_TOTALS (BPK_XCHG_DATA + 2 * 2 * BPK_XCHG_MAXRANKS * BPK_XCHG_CAP)
+#define BPK_XCHG_BYTES ((BPK_XCHG_TOTALS + 2 * 2 * BPK_XCHG_CAP) * sizeof(double))
 struct BpkXchg {
     bool ready = false;
     int nranks = 1, rank = 0;
@@ -40,6 +48,7 @@ struct BpkXchg {
     double *win[BPK_XCHG_MAXRANKS] = {nullptr};
 };
 extern BpkXchg g_xchg;
+int bpk_xchg_local(void);            // make sure this rank's own window exists (single-GPU hand-off)
 
 int bpk_set_error(int code, const char *fmt, ...);
 int bpk_check_flag(int what_if_set);    // sync + read d_flag, clear it

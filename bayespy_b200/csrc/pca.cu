@@ -566,24 +566,68 @@ pca_xsweep_ws_kernel(const __grid_constant__ CUtensorMap tmapY, int64_t M, int64
         grid_wait(gbar, epoch, vb.ctrl + 2);
         if (blockIdx.x == 0) vb_stamp(vb.dbg, 2);
         // distributed, fixed-order reduction over the CTAs: CTA c owns elements [c*per, (c+1)*per)
-        double *fin = partial + (size_t)gridDim.x * PCA_NSTAT;
         const int per = (PCA_NSTAT + gridDim.x - 1) / gridDim.x;
         const int e0 = blockIdx.x * per;
-        for (int ee = w; ee < per; ee += 2 * WS_PAIRS) {
-            const int e = e0 + ee;
-            if (e < PCA_NSTAT) {
+        if (vb.ll) {
+            // ... and the sweep's one exchange rides on it: the owner of a slice pushes its sum straight into every
+            // rank's peer-memory window (lane r -> rank r, this GPU's own window included) as self-tagged LL packets.
+            // No second grid barrier and no flag: CTA 0 (here and on every peer) gathers the packets in STATS as they
+            // land, so the exchange costs one NVLink one-way latency instead of a single-CTA deposit + fence + flag
+            // round trip.
+            // exchanges this rank has completed so far = word 0 of its own window, advanced by CTA 0's STATS before the
+            // grid barrier that ended the previous sweep (or the previous launch)
+            const unsigned long long xseq = *(volatile const unsigned long long *)vb.xown + 1ull;
+            const int par = (int)(xseq & 1ull);
+            const unsigned int seq = (unsigned int)xseq;
+            double *mywin = vb.xwin[0];            // lane r serves rank r (static selects: no dynamic index into the parameter block)
+#pragma unroll
+            for (int r = 1; r < BPK_XCHG_MAXRANKS; ++r)
+                if (lane == r) mywin = vb.xwin[r];
+            const int xr = vb.xranks;
+            for (int ee = w; ee < per; ee += 2 * WS_PAIRS) {
+                const int e = e0 + ee;
+                if (e >= PCA_NSTAT) continue;
+                if (DERIVE_SXX && e >= PCA_MP * PCA_KP && e < PCA_MP * PCA_KP + PCA_KP * PCA_KP) continue;   // S_xx is formed in the tail
                 double s = 0.0;
                 for (int bb = lane; bb < (int)gridDim.x; bb += 32) s += __ldcg(partial + (size_t)bb * PCA_NSTAT + e);
                 s = warp_sum(s);
-                if (lane == 0) fin[e] = s;
+                if (xr > 1) {
+                    if (lane < xr) ll_store(ll_slot(mywin, par, vb.xrank, e), s, seq);          // my share -> every rank
+                    double v = 0.0;
+                    if (lane < xr) v = ll_wait(ll_slot(vb.xown, par, lane, e), seq, vb.ctrl + 2);   // every rank's share -> me
+                    s = 0.0;
+#pragma unroll
+                    for (int r = 0; r < BPK_XCHG_MAXRANKS; ++r) {                                // rank order: same bits everywhere
+                        const double vr = __shfl_sync(0xffffffffu, v, r);
+                        if (r < xr) s += vr;
+                    }
+                }
+                if (lane == 0) ll_store(ll_total_slot(vb.xown, par, e), s, seq);
             }
-        }
-        if (blockIdx.x == 0) vb_stamp(vb.dbg, 3);
-        grid_barrier(gbar, epoch, vb.ctrl + 2);
-        if (blockIdx.x == 0) {
-            vb_stamp(vb.dbg, 4);
-            pca_vb_ops(vb, smem, vb_sm_doubles, false, nops_it);
-            vb_stamp(vb.dbg, 5);
+            if (blockIdx.x == 0) {
+                vb_stamp(vb.dbg, 3);
+                vb_stamp(vb.dbg, 4);
+                pca_vb_ops(vb, smem, vb_sm_doubles, false, nops_it, xseq);
+                vb_stamp(vb.dbg, 5);
+            }
+        } else {
+            double *fin = partial + (size_t)gridDim.x * PCA_NSTAT;
+            for (int ee = w; ee < per; ee += 2 * WS_PAIRS) {
+                const int e = e0 + ee;
+                if (e < PCA_NSTAT) {
+                    double s = 0.0;
+                    for (int bb = lane; bb < (int)gridDim.x; bb += 32) s += __ldcg(partial + (size_t)bb * PCA_NSTAT + e);
+                    s = warp_sum(s);
+                    if (lane == 0) fin[e] = s;
+                }
+            }
+            if (blockIdx.x == 0) vb_stamp(vb.dbg, 3);
+            grid_barrier(gbar, epoch, vb.ctrl + 2);
+            if (blockIdx.x == 0) {
+                vb_stamp(vb.dbg, 4);
+                pca_vb_ops(vb, smem, vb_sm_doubles, false, nops_it);
+                vb_stamp(vb.dbg, 5);
+            }
         }
         if (it + 1 < niter) grid_barrier(gbar, epoch, vb.ctrl + 2);      // the next sweep's A, b (and the stop word) are visible to every CTA
     }
@@ -663,7 +707,8 @@ static int pca_launch_ws(const double *Y, int64_t M, int64_t N, int K, const dou
         return BPK_OK;
     }
     PcaVbArgs none;
-    none.nops = 0; none.nops_last = 0; none.niter = 1; none.dry_every = 0; none.derive_sxx = 0;
+    none.nops = 0; none.nops_last = 0; none.niter = 1; none.dry_every = 0; none.derive_sxx = 0; none.ll = 0; none.gj2 = 0;
+    none.xranks = 1; none.xrank = 0; none.dbg = nullptr; none.xown = nullptr;
     auto kern = pca_xsweep_ws_kernel<NT, STAGES, DIST, COMPUTE_X, false, false>;
     BPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     BPK_LAUNCH(kern, grid, 2 * WS_PAIRS * 32, smem, tmap, M, N, K, A, b, X, partial, ntiles, stop, (unsigned int *)nullptr, none, (size_t)0);

@@ -63,6 +63,13 @@ extern "C" int bpk_pca_vb_set_timers(const int *ids, int n) {
 }
 extern "C" int bpk_pca_vb_timers_used(void) { return g_vb_timer_pos; }
 
+static int g_vb_no_loop = 0;
+extern "C" int bpk_pca_vb_set_mode(int no_loop, int *prev) {
+    if (prev) *prev = g_vb_no_loop;
+    g_vb_no_loop = no_loop ? 1 : 0;
+    return BPK_OK;
+}
+
 static int vb_launch_small(PcaVbArgs &a, size_t smem) {
     if (a.nops == 0) return BPK_OK;
     BPK_LAUNCH(pca_vb_small_kernel, 1, VB_THREADS, smem, a, smem / sizeof(double));
@@ -94,6 +101,8 @@ extern "C" int bpk_pca_vb_run(const double *Y, int64_t M, int64_t N, int K, doub
     a.Lhist = Lhist; a.cap = cap; a.ctrl = ctrl; a.nops = 0;
     a.xranks = 1; a.xrank = 0;
     a.niter = 1; a.nops_last = 0; a.derive_sxx = 0;
+    a.ll = 0;
+    a.gj2 = getenv("BPK_VB_GJ1") ? 0 : 1;
     a.dry_every = getenv("BPK_VB_DRY_FIRST_ONLY") ? 0 : 1;
     a.dbg = nullptr;
     if (getenv("BPK_VB_DEBUG")) {
@@ -109,13 +118,26 @@ extern "C" int bpk_pca_vb_run(const double *Y, int64_t M, int64_t N, int K, doub
         a.dbg = g_vb_dbg;
     }
     for (int r = 0; r < BPK_XCHG_MAXRANKS; ++r) a.xwin[r] = nullptr;
+    a.xown = nullptr;
     const int64_t nstat = M * K + (int64_t)K * K + K;
     double *stats_dst = state + (nranks > 1 ? off[F_STATS_LOCAL] : off[F_STATS]);
     if (fast && N > 0) {
-        const bool p2p = g_xchg.ready && g_xchg.nranks > 1 && nstat <= BPK_XCHG_CAP;
+        const bool p2p = g_xchg.ready && g_xchg.nranks > 1 && PCA_NSTAT <= BPK_XCHG_CAP;
         if (p2p) {
             a.xranks = g_xchg.nranks; a.xrank = g_xchg.rank; a.local_stats = 0;
             for (int r = 0; r < g_xchg.nranks; ++r) a.xwin[r] = g_xchg.win[r];
+            a.xown = g_xchg.win[g_xchg.rank];
+        }
+        // Fused launches hand the reduced statistics to CTA 0 as LL packets through a window (the peers' windows
+        // with p2p, this GPU's own otherwise): no second grid barrier.  BPK_VB_NO_LL=1 (single rank only) keeps the
+        // scratch buffer + grid barrier hand-off for A/B measurements.
+        bool ll_ok = p2p;
+        if (nranks == 1 && !getenv("BPK_VB_NO_LL")) {
+            int rc = bpk_xchg_local();
+            if (rc) return rc;
+            a.xwin[0] = g_xchg.own;
+            a.xown = g_xchg.own;
+            ll_ok = true;
         }
         // One launch per sweep: the small ops that follow an XSWEEP (up to the next one) ride in the
         // tail of the sweep kernel; only what precedes the first sweep of the run is a launch of its own.
@@ -126,7 +148,7 @@ extern "C" int bpk_pca_vb_run(const double *Y, int64_t M, int64_t N, int K, doub
             for (int i = 0; i < nops; ++i)
                 if (ops[i] == BPK_VBOP_XSWEEP) { ++nx; kx = i; }
             const bool loopable = nx == 1 && (nranks == 1 || p2p) && nops - 1 <= VB_MAXOPS && niter >= 1 &&
-                                  pca_ws_available(Y, N) && !getenv("BPK_VB_NO_LOOP");
+                                  pca_ws_available(Y, N) && !g_vb_no_loop && !getenv("BPK_VB_NO_LOOP");
             if (loopable) {
                 for (int i = 0; i < nops; ++i)
                     if (ops[i] < BPK_VBOP_XSWEEP || ops[i] > BPK_VBOP_BOUND || (ops[i] == BPK_VBOP_STATS && i < kx))
@@ -141,6 +163,8 @@ extern "C" int bpk_pca_vb_run(const double *Y, int64_t M, int64_t N, int K, doub
                 for (int i = 0; i < kx; ++i) tail.ops[tail.nops++] = ops[i];
                 tail.niter = niter;
                 tail.derive_sxx = getenv("BPK_PCA_SXX_DMMA") ? 0 : 1;
+                tail.ll = (ll_ok && tail.nops_last > 0 && tail.ops[0] == BPK_VBOP_STATS) ? 1 : 0;
+                if (p2p && !tail.ll) return bpk_set_error(BPK_EINVAL, "bpk_pca_vb_run: STATS must follow XSWEEP");
                 int tid = -1;
                 if (g_vb_timer_pos < g_vb_ntimers) tid = g_vb_timers[g_vb_timer_pos++];
                 if (tid >= 0) bpk_timer_record(tid, 0);
@@ -186,6 +210,7 @@ extern "C" int bpk_pca_vb_run(const double *Y, int64_t M, int64_t N, int K, doub
             }
             tail.nops_last = tail.nops;
             tail.niter = 1;
+            tail.ll = (ll_ok && !exchange && tail.nops > 0 && tail.ops[0] == BPK_VBOP_STATS && pca_ws_available(Y, N)) ? 1 : 0;
             int tid = -1;
             if (g_vb_timer_pos < g_vb_ntimers) tid = g_vb_timers[g_vb_timer_pos++];
             if (tid >= 0) bpk_timer_record(tid, 0);

@@ -36,6 +36,40 @@ __device__ __forceinline__ void vb_stamp(unsigned long long *dbg, int slot) {
     }
 }
 
+// ---- LL packets of the peer-memory exchange (layout: common.cuh) ---------------------------------------
+// slot of element e deposited by rank r with parity par, inside the window `win`
+__device__ __forceinline__ unsigned long long *ll_slot(double *win, int par, int r, int e) {
+    return (unsigned long long *)win + BPK_XCHG_DATA + ((size_t)(par * BPK_XCHG_MAXRANKS + r) * BPK_XCHG_CAP + e) * 2;
+}
+// one fp64 value as two self-tagged 8-byte packets (each store is atomic; no fence needed around it)
+__device__ __forceinline__ void ll_store(unsigned long long *slot, double v, unsigned int seq) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    const unsigned long long w0 = ((unsigned long long)seq << 32) | (b & 0xffffffffull);
+    const unsigned long long w1 = ((unsigned long long)seq << 32) | (b >> 32);
+    asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};\n" ::"l"(slot), "l"(w0), "l"(w1) : "memory");
+}
+__device__ __forceinline__ void ll_load(const unsigned long long *slot, unsigned long long &w0, unsigned long long &w1) {
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];\n" : "=l"(w0), "=l"(w1) : "l"(slot) : "memory");
+}
+// slot of the rank-summed element e (written by the local CTA that owns e, read by the CTA that runs the small ops)
+__device__ __forceinline__ unsigned long long *ll_total_slot(double *win, int par, int e) {
+    return (unsigned long long *)win + BPK_XCHG_TOTALS + ((size_t)par * BPK_XCHG_CAP + e) * 2;
+}
+// spin until both packets of the slot carry this exchange's tag; ~20 s watchdog -> error bit 4 (a peer died; ranks
+// may start seconds apart on a busy host)
+__device__ __forceinline__ double ll_wait(const unsigned long long *slot, unsigned int seq, int *errword) {
+    unsigned long long w0, w1;
+    long long t0 = 0;
+    bool timing = false;
+    for (;;) {
+        ll_load(slot, w0, w1);
+        if ((unsigned int)(w0 >> 32) == seq && (unsigned int)(w1 >> 32) == seq) break;
+        if (!timing) { t0 = clock64(); timing = true; }
+        else if (clock64() - t0 > 40000000000ll) { atomicOr(errword, 4); return 0.0; }
+    }
+    return __longlong_as_double((long long)((w1 << 32) | (w0 & 0xffffffffull)));
+}
+
 __host__ __device__ inline void pca_vb_offsets(int M, int K, int64_t *off /* [F_COUNT+1] */) {
     const int64_t KK = (int64_t)K * K, MK = (int64_t)M * K, NS = MK + KK + K;
     const int64_t size[F_COUNT] = {
@@ -51,9 +85,9 @@ __host__ __device__ inline void pca_vb_offsets(int M, int K, int64_t *off /* [F_
     off[F_COUNT] = o;
 }
 
-// scratch of the small ops in doubles: augmented K x 2K Gauss-Jordan tile (odd pitch), pivot row / column
-// copies, pivots, reduction slots
-__host__ __device__ inline size_t pca_vb_smem_doubles(int K) { return (size_t)K * (2 * K + 1) + 4 * (size_t)K + 64; }
+// scratch of the small ops in doubles: augmented K x 2K Gauss-Jordan tile (odd pitch), two pivot rows / columns
+// (the elimination takes two pivots per step), pivots, reduction slots
+__host__ __device__ inline size_t pca_vb_smem_doubles(int K) { return (size_t)K * (2 * K + 1) + 7 * (size_t)K + 64; }
 
 struct PcaVbArgs {
     int M, K, has_alpha, has_tau;
@@ -68,6 +102,10 @@ struct PcaVbArgs {
     unsigned long long *dbg; // optional %globaltimer stamps (tools/vb_tail_timing.py), NULL in production
     int xranks, xrank;       // > 1: STATS all-reduces over the peer-memory windows below (no NCCL call)
     double *xwin[BPK_XCHG_MAXRANKS];
+    double *xown;            // = xwin[xrank]
+    int ll;                  // 1 (fused sweep kernel): every CTA has pushed its slice of the reduced statistics into the
+                             // windows as LL packets (xranks may be 1: the window is then this GPU's own); STATS gathers
+    int gj2;                 // 1: K x K inverses eliminate two pivots per step (half the barriers)
     int niter;               // fused sweep kernel: sweeps per launch; ops[0..nops) follow every sweep but the last,
     int derive_sxx;          // 1: the sweep kernel did not accumulate S_xx; STATS forms it as A S_yx + b s_x^T
     int dry_every;           // 1: CTA 0 dry-runs the tail in every sweep of the launch, 0: only in the first
@@ -113,10 +151,11 @@ __device__ __forceinline__ double vb_E2(const double *st, const int64_t *o, int 
 // (index arithmetic becomes shifts; this code runs once per launch from a cold instruction cache, so small
 // and fast matters more than general).
 template <int KC, int MC>
-static __device__ __noinline__ void pca_vb_ops_t(const PcaVbArgs &p, double *sm, size_t sm_doubles, bool dry, int nops_run) {
+static __device__ __noinline__ void pca_vb_ops_t(const PcaVbArgs &p, double *sm, size_t sm_doubles, bool dry, int nops_run,
+                                                  unsigned long long xseq) {
     const int VBT = blockDim.x;
     const int M = MC ? MC : p.M, K = KC ? KC : p.K, K2 = 2 * K, ldg = K2 + 1, t = threadIdx.x;
-    double *G = sm, *rowk = G + (size_t)K * ldg, *colk = rowk + K2, *piv = colk + K, *red = piv + K, *scal = red + 32;
+    double *G = sm, *rowk = G + (size_t)K * ldg, *colk = rowk + 2 * K2, *piv = colk + 2 * K, *red = piv + K, *scal = red + 32;
     __shared__ int64_t o[F_COUNT + 1];
     __shared__ int dry_ctrl[4];
     if (t == 0) pca_vb_offsets(M, K, o);
@@ -148,16 +187,19 @@ static __device__ __noinline__ void pca_vb_ops_t(const PcaVbArgs &p, double *sm,
         const int op = p.ops[ip];
         vb_stamp(dbg, 8 + ip);
         if (op == BPK_VBOP_STATS) {
-            // fixed-order grid reduction of the sweep kernel's per-CTA partials
-            const bool xch = xranks > 1;
-            double *dst = st + ((p.local_stats || xch) ? o[F_STATS_LOCAL] : o[F_STATS]);
+            // fixed-order grid reduction of the sweep kernel's per-CTA partials + the sweep's ONE exchange
             const int total = M * K + K * K + K;
-            if (p.partial) {
+            const bool llx = !dry && p.ll;                   // fused kernel: the grid has already pushed its slices
+            const bool xch = !dry && !p.ll && xranks > 1;    // single-CTA launch: push and gather here
+            double *dst = st + ((p.local_stats || xch) ? o[F_STATS_LOCAL] : o[F_STATS]);
+            auto padded = [&](int e) -> int {
+                if (e < M * K) { const int m = e / K; return m * PCA_KP + (e - m * K); }
+                if (e < M * K + K * K) { const int r = e - M * K, i = r / K; return PCA_MP * PCA_KP + i * PCA_KP + (r - i * K); }
+                return PCA_MP * PCA_KP + PCA_KP * PCA_KP + (e - M * K - K * K);
+            };
+            if (!llx && p.partial) {
                 for (int e = t; e < total; e += VBT) {
-                    int pe;
-                    if (e < M * K) { int m = e / K, k = e - m * K; pe = m * PCA_KP + k; }
-                    else if (e < M * K + K * K) { int r = e - M * K; int i = r / K, j = r - i * K; pe = PCA_MP * PCA_KP + i * PCA_KP + j; }
-                    else pe = PCA_MP * PCA_KP + PCA_KP * PCA_KP + (e - M * K - K * K);
+                    const int pe = padded(e);
                     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
                     int b = 0;
                     for (; b + 3 < p.nparts; b += 4) {
@@ -170,60 +212,65 @@ static __device__ __noinline__ void pca_vb_ops_t(const PcaVbArgs &p, double *sm,
                     dst[e] = (s0 + s1) + (s2 + s3);
                 }
             }
-            if (xch) {
-                // the sweep's one exchange, in this kernel: deposit into every rank's window over NVLink,
-                // raise a sequence flag, wait for everybody's flag, add up in rank order (bit-identical
-                // on every rank).  Two parities of slots: a rank cannot get more than one exchange ahead
-                // of a peer, because it needs that peer's flag to finish the one in between.
+            if (llx || xch) {
+                // The exchange, inside this kernel: every rank's deposit lands in MY window as self-tagged LL packets
+                // (pushed over NVLink by the peers' CTAs, by this GPU's own CTAs for its own share) and is summed in
+                // rank order — bit-identical on every rank — as soon as the tags show this exchange's number: by the
+                // CTA that owns the element (fused sweep kernel; this CTA then only collects the totals) or here.
+                // Two parities of slots: a rank cannot get more than one exchange ahead of a peer, because it needs
+                // that peer's deposit to finish the one in between.
                 __syncthreads();
                 vb_stamp(dbg, 40);
-                double *own = p.xwin[p.xrank];
-                const unsigned long long seq = *(volatile unsigned long long *)own + 1ull;
-                const int par = (int)(seq & 1ull);
-                for (int r = 0; r < xranks; ++r) {
-                    double *slot = p.xwin[r] + BPK_XCHG_DATA + (size_t)(par * BPK_XCHG_MAXRANKS + p.xrank) * BPK_XCHG_CAP;
-                    for (int e = t; e < total; e += VBT) slot[e] = dst[e];
+                double *own = p.xown;
+                const unsigned long long seq64 = llx ? xseq : *(volatile unsigned long long *)own + 1ull;
+                const unsigned int seq = (unsigned int)seq64;
+                const int par = (int)(seq & 1u);
+                if (xch) {
+                    for (int e = t; e < total; e += VBT) {
+                        const int pe = padded(e);
+                        const double v = dst[e];
+                        for (int r = 0; r < xranks; ++r) ll_store(ll_slot(p.xwin[r], par, p.xrank, pe), v, seq);
+                    }
                 }
-                __threadfence_system();
-                __syncthreads();
                 vb_stamp(dbg, 41);
-                if (t < xranks) {
-                    unsigned long long *f = (unsigned long long *)(p.xwin[t] + BPK_XCHG_FLAGS) + par * BPK_XCHG_MAXRANKS + p.xrank;
-                    asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(f), "l"(seq) : "memory");
-                    const unsigned long long *g = (const unsigned long long *)(own + BPK_XCHG_FLAGS) + par * BPK_XCHG_MAXRANKS + t;
-                    const long long t0 = clock64();
-                    unsigned long long v;
-                    do {
-                        asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(g) : "memory");
-                        if (v < seq && clock64() - t0 > 40000000000ll) { atomicOr(&ctrl[2], 4); break; }   // ~20 s: a peer died (ranks may start seconds apart on a busy host)
-                    } while (v < seq);
-                }
-                __syncthreads();
-                vb_stamp(dbg, 42);
                 for (int e = t; e < total; e += VBT) {
-                    double s = 0.0;
-                    for (int r = 0; r < xranks; ++r)
-                        s += __ldcv(own + BPK_XCHG_DATA + (size_t)(par * BPK_XCHG_MAXRANKS + r) * BPK_XCHG_CAP + e);
+                    if (p.derive_sxx && e >= M * K && e < M * K + K * K) continue;      // formed below
+                    const int pe = padded(e);
+                    double s;
+                    if (llx) s = ll_wait(ll_total_slot(own, par, pe), seq, &ctrl[2]);    // the owner CTA summed over ranks
+                    else {
+                        s = 0.0;
+                        for (int r = 0; r < xranks; ++r) s += ll_wait(ll_slot(own, par, r, pe), seq, &ctrl[2]);
+                    }
                     st[o[F_STATS] + e] = s;
                 }
                 __syncthreads();
-                if (t == 0) *(volatile unsigned long long *)own = seq;
-                vb_stamp(dbg, 43);
+                if (t == 0) *(volatile unsigned long long *)own = seq64;
+                vb_stamp(dbg, 42);
             }
             if (p.derive_sxx) {
-                // x_n = A y_n + b  =>  sum_n x_n x_n^T = A (sum_n y_n x_n^T) + b (sum_n x_n)^T, with the A, b this sweep used
+                // x_n = A y_n + b  =>  sum_n x_n x_n^T = A (sum_n y_n x_n^T) + b (sum_n x_n)^T, with the A, b this sweep used.
+                // Two threads per output element (halves of the m range), combined by one shuffle.
                 __syncthreads();
                 const double *Sg = st + o[F_STATS];
-                for (int e = t; e < K * K; e += VBT) {
-                    const int i = e / K, j = e - i * K;
-                    double s0 = 0.0, s1 = 0.0;
-                    int m = 0;
-                    for (; m + 1 < M; m += 2) {
+                const int half = t & 1, mh = (M + 1) >> 1;
+                const int m0 = half ? mh : 0, m1 = half ? M : mh;
+                for (int eb = 0; eb < K * K; eb += VBT >> 1) {
+                    const int e = eb + (t >> 1);
+                    const bool act = e < K * K;
+                    const int i = act ? e / K : 0, j = act ? e - i * K : 0;
+                    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                    int m = m0;
+                    for (; m + 3 < m1; m += 4) {
                         s0 += st[o[F_A] + i * M + m] * Sg[m * K + j];
                         s1 += st[o[F_A] + i * M + m + 1] * Sg[(m + 1) * K + j];
+                        s2 += st[o[F_A] + i * M + m + 2] * Sg[(m + 2) * K + j];
+                        s3 += st[o[F_A] + i * M + m + 3] * Sg[(m + 3) * K + j];
                     }
-                    if (m < M) s0 += st[o[F_A] + i * M + m] * Sg[m * K + j];
-                    G[i * K + j] = (s0 + s1) + st[o[F_BX] + i] * Sg[M * K + K * K + j];
+                    for (; m < m1; ++m) s0 += st[o[F_A] + i * M + m] * Sg[m * K + j];
+                    double s = (s0 + s1) + (s2 + s3);
+                    s += __shfl_xor_sync(0xffffffffu, s, 1);
+                    if (act && half == 0) G[i * K + j] = s + st[o[F_BX] + i] * Sg[M * K + K * K + j];
                 }
                 __syncthreads();
                 for (int e = t; e < K * K; e += VBT) {
@@ -248,7 +295,7 @@ static __device__ __noinline__ void pca_vb_ops_t(const PcaVbArgs &p, double *sm,
                 } else v = (j - K == i) ? 1.0 : 0.0;
                 G[i * ldg + j] = v;
             }
-            spd_cta_inverse_gj<KC>(G, rowk, colk, piv, K, scal, &ctrl[2]);
+            spd_cta_inverse_gj<KC>(G, rowk, colk, piv, K, scal, &ctrl[2], p.gj2);
             for (int e = t; e < K * K; e += VBT) st[o[F_COVX] + e] = CINV(e / K, e % K);
             if (t == 0) st[o[F_LOGDETX]] = scal[0];
             for (int k = t; k < K; k += VBT) {
@@ -280,7 +327,7 @@ static __device__ __noinline__ void pca_vb_ops_t(const PcaVbArgs &p, double *sm,
                 const int k = e % K;
                 st[o[F_PHI0C] + e] = st[o[F_AL_U0] + k] * st[o[F_MUC] + k] + tau * st[o[F_STATS] + e];
             }
-            spd_cta_inverse_gj<KC>(G, rowk, colk, piv, K, scal, &ctrl[2]);
+            spd_cta_inverse_gj<KC>(G, rowk, colk, piv, K, scal, &ctrl[2], p.gj2);
             for (int e = t; e < K * K; e += VBT) st[o[F_COVC] + e] = CINV(e / K, e % K);
             const double ldc = scal[0];
             if (t == 0) st[o[F_LOGDETC]] = ldc;
@@ -422,11 +469,13 @@ static __device__ __noinline__ void pca_vb_ops_t(const PcaVbArgs &p, double *sm,
 #undef CINV
 }
 
+// xseq: sequence number of this sweep's exchange when the caller (fused sweep kernel) has already pushed the grid's
+// slices (p.ll); ignored otherwise.
 static __device__ __forceinline__ void pca_vb_ops(const PcaVbArgs &p, double *sm, size_t sm_doubles, bool dry = false,
-                                                  int nops_run = -1) {
+                                                  int nops_run = -1, unsigned long long xseq = 0ull) {
     if (nops_run < 0) nops_run = p.nops;
-    if (p.M == PCA_MP && p.K == PCA_KP) pca_vb_ops_t<PCA_KP, PCA_MP>(p, sm, sm_doubles, dry, nops_run);
-    else pca_vb_ops_t<0, 0>(p, sm, sm_doubles, dry, nops_run);
+    if (p.M == PCA_MP && p.K == PCA_KP) pca_vb_ops_t<PCA_KP, PCA_MP>(p, sm, sm_doubles, dry, nops_run, xseq);
+    else pca_vb_ops_t<0, 0>(p, sm, sm_doubles, dry, nops_run, xseq);
 }
 
 

@@ -105,6 +105,13 @@ extern "C" int bpk_device_info(int *sm_count, int *cc_major, int *cc_minor,
     return BPK_OK;
 }
 
+extern "C" int bpk_device_pci_bus_id(char *buf, int len) {
+    BPK_REQUIRE_INIT();
+    if (!buf || len < 13) return bpk_set_error(BPK_EINVAL, "bpk_device_pci_bus_id: buffer too small");
+    BPK_CUDA(cudaDeviceGetPCIBusId(buf, len, g_bpk.device));
+    return BPK_OK;
+}
+
 extern "C" int bpk_sync(void) {
     BPK_REQUIRE_INIT();
     BPK_CUDA(cudaStreamSynchronize(g_bpk.stream));
@@ -303,6 +310,17 @@ extern "C" int bpk_xchg_create(char handle[64]) {
     BPK_CUDA(cudaIpcGetMemHandle(&h, g_xchg.own));
     static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
     memcpy(handle, &h, 64);
+    return BPK_OK;
+}
+// single-GPU runs: the same window, local only (the fused sweep kernel hands its reduced statistics to the
+// tail through it with the same packet protocol the multi-GPU exchange uses)
+int bpk_xchg_local(void) {
+    BPK_REQUIRE_INIT();
+    if (!g_xchg.own) {
+        BPK_CUDA(cudaMalloc((void **)&g_xchg.own, BPK_XCHG_BYTES));
+        BPK_CUDA(cudaMemset(g_xchg.own, 0, BPK_XCHG_BYTES));
+    }
+    if (!g_xchg.ready) g_xchg.win[0] = g_xchg.own;
     return BPK_OK;
 }
 extern "C" int bpk_xchg_open(const char *handles, int nranks, int rank) {

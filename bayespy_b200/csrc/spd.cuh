@@ -70,14 +70,47 @@ __device__ __forceinline__ void spd_warp_inverse(const double *S, double *B, dou
 
 // In-place inverse of the SPD matrix held in the left half of the augmented tile G (K x 2K, pitch ldg,
 // right half = identity) by Gauss-Jordan elimination without pivoting, ALL threads of the CTA working on
-// every step (K steps of two barriers each; a warp-level Cholesky + triangular solves of the same tile
-// took ~13 us, this takes ~3).  On exit G[:, K:2K] = A^-1, scal[0] = log det A (sum of log pivots;
-// linalg.py:209-223 gives the same number as 2 sum log diag U).  Non-positive pivot -> BPK_FLAG_NOTSPD.
+// every step (a warp-level Cholesky + triangular solves of the same tile took ~13 us, this takes ~3).
+// On exit G[:, K:2K] = A^-1, scal[0] = log det A (sum of log pivots; linalg.py:209-223 gives the same
+// number as 2 sum log diag U).  Non-positive pivot -> BPK_FLAG_NOTSPD.
+// two = 1 (K even, >= 6K+1 threads): TWO pivots per step — the 2 x 2 pivot block of an SPD Schur complement is
+// SPD, so it is inverted in closed form and rows k, k+1 are eliminated together: K/2 steps of two barriers
+// instead of K (the steps are barrier-latency bound, not flop bound).  rowk: 2 x 2K, colk: 2 x K scratch.
 template <int KC>
 __device__ __forceinline__ void spd_cta_inverse_gj(double *G, double *rowk, double *colk, double *piv, int Krt, double *scal,
-                                                   int *flagword) {
+                                                   int *flagword, int two = 0) {
     const int K = KC ? KC : Krt, K2 = 2 * K, ldg = K2 + 1;
     const int t = threadIdx.x, nt = blockDim.x;
+    if (two && (K & 1) == 0 && nt >= 2 * K2 + 2 * K + 1) {
+        for (int k = 0; k < K; k += 2) {
+            __syncthreads();
+            const double p00 = G[k * ldg + k], p01 = G[k * ldg + k + 1];
+            const double p10 = G[(k + 1) * ldg + k], p11 = G[(k + 1) * ldg + k + 1];
+            const double det = p00 * p11 - p01 * p10;
+            const double rd = 1.0 / det;
+            if (t < 2 * K2) {
+                const int r = t >= K2, j = t - r * K2;
+                const double g0 = G[k * ldg + j], g1 = G[(k + 1) * ldg + j];
+                rowk[t] = r ? (p00 * g1 - p10 * g0) * rd : (p11 * g0 - p01 * g1) * rd;     // P^-1 [row k; row k+1]
+            } else if (t < 2 * K2 + 2 * K) {
+                const int c = (t - 2 * K2) >= K, i = t - 2 * K2 - c * K;
+                colk[c * K + i] = G[i * ldg + k + c];
+            } else if (t == 2 * K2 + 2 * K) {
+                piv[k] = p00;                 // both must be positive for an SPD matrix; their product is the block's det
+                piv[k + 1] = det / p00;
+            }
+            __syncthreads();
+            for (int e = t; e < K * K2; e += nt) {
+                const int i = e / K2, j = e - i * K2;
+                const double r0 = rowk[j], r1 = rowk[K2 + j];
+                double v;
+                if (i == k) v = r0;
+                else if (i == k + 1) v = r1;
+                else v = G[i * ldg + j] - (colk[i] * r0 + colk[K + i] * r1);
+                G[i * ldg + j] = v;
+            }
+        }
+    } else {
     for (int k = 0; k < K; ++k) {
         __syncthreads();
         const double p = G[k * ldg + k];
@@ -98,6 +131,7 @@ __device__ __forceinline__ void spd_cta_inverse_gj(double *G, double *rowk, doub
             const double rj = rowk[j];
             G[i * ldg + j] = (i == k) ? rj : G[i * ldg + j] - colk[i] * rj;
         }
+    }
     }
     __syncthreads();
     if (t < 32) {

@@ -1,7 +1,9 @@
-"""Gaussian Markov chain node on device (nodes/gaussian_markov_chain.py:270-927 restricted to the
-time-invariant chain without input signals):
+"""Gaussian Markov chain node on device (nodes/gaussian_markov_chain.py:270-927 without input signals):
 
-    x_0 ~ N(mu, Lambda^-1),   x_n ~ N(A x_{n-1}, diag(nu)^-1),  n = 1..N-1
+    x_0 ~ N(mu, Lambda^-1),   x_n ~ N(A_{n-1} x_{n-1}, diag(nu_{n-1})^-1),  n = 1..N-1
+
+with time-invariant (A plates (..., 1, D) or (D,)) or per-step (plates (..., N-1, D)) dynamics and independent
+chains over leading plates, in the reference's plate layout.
 
 Moments u = [<x_n> (N,D), <x_n x_n^T> (N,D,D), <x_n x_{n+1}^T> (N-1,D,D)]; the time axis is part of the
 variable dims exactly as in the reference.  The natural parameters form a block-tridiagonal precision
@@ -158,44 +160,75 @@ def _pk(n):
 
 
 class GaussianMarkovChainDistribution(Distribution):
-    """All arrays carry the chain's plates P in front: phi / u are P+(N,D), P+(N,D,D), P+(N-1,D,D).
-    Parents may have fewer (broadcast) plates; A and nu additionally carry the state axis as their last plate."""
+    """General case, in the reference's plate layout (gaussian_markov_chain.py:660-720): with chain plates P,
+    (mu, Lambda) have plates P and (A, nu) have plates P + (N-1 | 1, D) — the second-last plate of the dynamics
+    is the TIME axis (1 = time-invariant, N-1 = one transition matrix / innovation precision per step), the last
+    one the state axis.  phi / u are P+(N,D), P+(N,D,D), P+(N-1,D,D).  Parents may have fewer (broadcast) plates.
 
-    def __init__(self, N, Dm, plates=()):
+    ``TA`` / ``Tn``: time extents (1 or N-1) of the A and nu parents.  When both are 1 the messages to A and nu
+    are summed over time here and carry a time axis of length 1 (so that no (N-1, D, D, D) array is ever formed);
+    otherwise they keep the time axis and the generic plate reduction (node.py:570-655) does what is left."""
+
+    def __init__(self, N, Dm, plates=(), TA=1, Tn=1):
         self.N, self.D = int(N), int(Dm)
         self.plates = tuple(int(p) for p in plates)
-        self._single = _SingleChainDistribution(N, Dm) if not self.plates else None
+        self.TA, self.Tn = int(TA), int(Tn)
+        self.static = self.TA == 1 and self.Tn == 1
+        self._single = _SingleChainDistribution(N, Dm) if (not self.plates and self.static) else None
 
-    # -- plates: (mu, Lambda) see the chain's plates; A and nu additionally carry the state axis (D,)
+    def _t_msg(self):
+        return 1 if self.static else self.N - 1
+
+    # -- plates (:660-706)
     def plates_to_parent(self, index, plates):
-        return tuple(plates) if index < 2 else tuple(plates) + (self.D,)
+        if self._single is not None:
+            return self._single.plates_to_parent(index, plates)
+        return tuple(plates) if index < 2 else tuple(plates) + (self._t_msg(), self.D)
 
     def plates_from_parent(self, index, plates):
-        return tuple(plates) if index < 2 else tuple(plates[:-1])
+        if index < 2:
+            return tuple(plates)
+        return tuple(plates[:-2])
 
     def compute_weights_to_parent(self, index, weights):
+        if self._single is not None:
+            return self._single.compute_weights_to_parent(index, weights)
         w = np.asarray(weights)
-        return w if index < 2 else w.reshape(w.shape + (1,))
+        return w if index < 2 else w.reshape(w.shape + (1, 1))
 
     def _parents(self, u_mu, u_Lambda, u_A, u_nu):
-        """Parent moments with their own (possibly shorter) plate axes in front of fixed trailing dims."""
+        """Parent moments with their own (possibly shorter) plate axes in front of fixed trailing axes:
+        A: PA+(TA,D,D) (row d = <a_d>), AA: PA+(TA,D,D,D), nu / lognu: Pn+(Tn,D)."""
         Dm = self.D
         mu = D.asarray(u_mu[0]) if u_mu is not None else None                 # Pm + (D,)
         mumu = dense(u_mu[1]) if u_mu is not None else None                  # Pm + (D, D)
         Lam = D.asarray(u_Lambda[0]) if u_Lambda is not None else None        # PL + (D, D)
         logdetL = D.asarray(u_Lambda[1]) if u_Lambda is not None else None    # PL
-        A = D.asarray(u_A[0]) if u_A is not None else None                    # PA + (D, D): row d = <a_d>
-        AA = dense(u_A[1]) if u_A is not None else None                      # PA + (D, D, D)
+        A = AA = None
+        if u_A is not None:
+            A = D.asarray(u_A[0])
+            AA = dense(u_A[1])
+            if A.ndim == 1:
+                A, AA = A.add_leading(1), AA.add_leading(1)
+            # the state plate may be stored compressed (a prior shared by all rows)
+            A = A.broadcast_to(tuple(A.shape[:-2]) + (Dm, Dm))
+            AA = AA.broadcast_to(tuple(AA.shape[:-3]) + (Dm, Dm, Dm))
+            if A.ndim == 2:                                                   # plates (D,): no time axis
+                A, AA = A.add_leading(1), AA.add_leading(1)
+            if A.shape[-3] not in (1, self.N - 1):
+                raise ValueError("The second last plate of the dynamics matrix should have length one or N-1")
         nu = lognu = None
         if u_nu is not None:
-            nu = D.asarray(u_nu[0])
-            lognu = D.asarray(u_nu[1])
-            if nu.ndim == 0 or nu.shape[-1] != Dm:
-                nu = nu.broadcast_to(tuple(nu.shape[:-1]) + (Dm,)) if nu.ndim else nu.broadcast_to((Dm,))
-                lognu = lognu.broadcast_to(tuple(lognu.shape[:-1]) + (Dm,)) if lognu.ndim else lognu.broadcast_to((Dm,))
-        for arr, nd, what in ((A, 2, "A"), (nu, 1, "nu")):
-            if arr is not None and arr.ndim - nd > len(self.plates):
-                raise NotImplementedError("GaussianMarkovChain: time-varying %s (plates (N-1, D)) is not supported yet" % what)
+            nu, lognu = D.asarray(u_nu[0]), D.asarray(u_nu[1])
+            if nu.ndim == 0:
+                nu, lognu = nu.reshape((1, 1)), lognu.reshape((1, 1))
+            elif nu.ndim == 1:
+                nu, lognu = nu.reshape((1, nu.shape[0])), lognu.reshape((1, lognu.shape[0]))
+            if nu.shape[-1] != Dm:
+                nu = nu.broadcast_to(tuple(nu.shape[:-1]) + (Dm,))
+                lognu = lognu.broadcast_to(tuple(lognu.shape[:-1]) + (Dm,))
+            if nu.shape[-2] not in (1, self.N - 1):
+                raise ValueError("The second last plate of the innovation precision should have length one or N-1")
         return mu, mumu, Lam, logdetL, A, AA, nu, lognu
 
     # -- natural parameters (gaussian_markov_chain.py:542-627)
@@ -215,17 +248,17 @@ class GaussianMarkovChainDistribution(Distribution):
         D._ew("AFFINE", first.shape, first, [Lam.reshape(tuple(Lam.shape[:-2]) + (1, Dm, Dm))], alpha=-0.5, beta=0.0)
         phi2 = DArray.empty(P + (max(N - 1, 0), Dm, Dm))
         if N > 1:
-            # blocks n >= 1: -1/2 diag(nu);  blocks n <= N-2: -1/2 sum_d nu_d <a_d a_d^T>
+            # blocks n >= 1: -1/2 diag(nu_{n-1});  blocks n <= N-2: -1/2 sum_d nu_{n,d} <a_{n,d} a_{n,d}^T>
             tail = phi1.slice_axis(npl, 1, N)
-            D._ew("AFFINE", tail.diag_view(1).shape, tail.diag_view(1), [nu.reshape(tuple(nu.shape[:-1]) + (1, Dm))],
-                  alpha=-0.5, beta=0.0)
-            nk, ak = nu.ndim - 1, AA.ndim - 3
-            S = D.sum_product([nu, AA], [pk[npl - nk:] + ["d"], pk[npl - ak:] + ["d", "i", "j"]], pk + ["i", "j"], scale=-0.5)
+            D._ew("AFFINE", tail.diag_view(1).shape, tail.diag_view(1), [nu], alpha=-0.5, beta=0.0)
+            nk, ak = nu.ndim - 2, AA.ndim - 4
+            S = D.sum_product([nu, AA], [pk[npl - nk:] + ["n", "d"], pk[npl - ak:] + ["n", "d", "i", "j"]],
+                              pk + ["n", "i", "j"], scale=-0.5)
             head = phi1.slice_axis(npl, 0, N - 1)
-            D._ew("ADD", head.shape, head, [head, S.reshape(tuple(S.shape[:-2]) + (1, Dm, Dm))])
-            # super-diagonal blocks (sum of super and sub): phi2[..., n, i, j] = nu_j <A>[j, i]
+            D._ew("ADD", head.shape, head, [head, S])
+            # super-diagonal blocks (sum of super and sub): phi2[..., n, i, j] = nu_{n,j} <A_n>[j, i]
             nuA_T = D.mul(A, nu.add_trailing(1)).swap_last2()
-            D.copy_into(phi2, nuA_T.reshape(tuple(nuA_T.shape[:-2]) + (1, Dm, Dm)))
+            D.copy_into(phi2, nuA_T)
         return [phi0, phi1, phi2]
 
     # -- E[log normaliser of the prior] (:251-267, :629-657)
@@ -239,7 +272,9 @@ class GaussianMarkovChainDistribution(Distribution):
         out_pl = pk[npl - max(Lam.ndim - 2, mumu.ndim - 2):]
         t = D.sum_product([Lam, mumu], [kL + ["i", "j"], km + ["i", "j"]], out_pl)
         g = D.axpby(-0.5, t, 0.5, logdetL)
-        s = D.sum_product([lognu], [pk[npl - (lognu.ndim - 1):] + ["d"]], pk[npl - (lognu.ndim - 1):], scale=0.5 * (self.N - 1))
+        kn = pk[npl - (lognu.ndim - 2):]
+        per_step = 0.5 * ((self.N - 1) if lognu.shape[-2] == 1 else 1.0)      # a time-invariant nu counts N-1 times
+        s = D.sum_product([lognu], [kn + ["n", "d"]], kn, scale=per_step)
         return D.add(g, s)
 
     # -- smoother (:89-123)
@@ -297,20 +332,35 @@ class GaussianMarkovChainDistribution(Distribution):
             return [D.mul(t, -0.5), D.asarray(0.5)]
         if N < 2:
             return [None, None]
-        # time sums of the chain's second moments (plates kept)
-        Sxx_head = D.sum_product([xx.slice_axis(npl, 0, N - 1)], [pk + ["n", "i", "j"]], pk + ["i", "j"])
-        Sxpxn = D.sum_product([xpxn], [pk + ["n", "i", "j"]], pk + ["i", "j"])
+        xx_head = xx.slice_axis(npl, 0, N - 1)                          # <x_n x_n^T>, n <= N-2
+        if self.static:
+            # time sums first (plates kept, time axis of length 1): nothing of size (N-1, D, D, D) is formed
+            t1 = ["t"]
+            Sxx_head = D.sum_product([xx_head], [pk + ["n", "i", "j"]], pk + t1 + ["i", "j"])
+            Sxpxn = D.sum_product([xpxn], [pk + ["n", "i", "j"]], pk + t1 + ["i", "j"])
+            if index == 2:
+                # to a_d: [nu_d sum_n <x_{n+1,d} x_n>, -1/2 nu_d sum_n <x_n x_n^T>]   plates P + (1, D)
+                m0 = D.mul(Sxpxn.swap_last2(), nu.add_trailing(1))
+                m1 = D.mul(D.mul(Sxx_head.expand_dims(-3), nu.add_trailing(2)), -0.5)
+                return [m0, m1]
+            if index == 3:
+                ka = pk[npl - (A.ndim - 3):]
+                dxx = D.sum_product([xx.slice_axis(npl, 1, N).diag_view(1)], [pk + ["n", "d"]], pk + t1 + ["d"], scale=-0.5)
+                a = D.sum_product([Sxpxn, A], [pk + t1 + ["i", "d"], ka + t1 + ["d", "i"]], pk + t1 + ["d"])
+                b = D.sum_product([Sxx_head, AA], [pk + t1 + ["i", "j"], ka + t1 + ["d", "i", "j"]], pk + t1 + ["d"], scale=-0.5)
+                return [D.add(D.add(dxx, a), b), DArray.full(P + (1, Dm), 0.5 * (N - 1))]
+            raise ValueError("Parent index out of bounds")
+        # time-varying dynamics: the messages keep the time axis (plates P + (N-1, D))
         if index == 2:
-            # to a_d: [nu_d sum_n <x_{n+1,d} x_n>, -1/2 nu_d sum_n <x_n x_n^T>]   plates P + (D,), dims (D,), (D, D)
-            m0 = D.mul(Sxpxn.swap_last2(), nu.add_trailing(1))
-            m1 = D.mul(D.mul(Sxx_head.expand_dims(-3), nu.add_trailing(2)), -0.5)
+            m0 = D.mul(xpxn.swap_last2(), nu.add_trailing(1))                                   # nu_{n,d} <x_{n+1,d} x_n>
+            m1 = D.mul(D.mul(xx_head.expand_dims(-3), nu.add_trailing(2)), -0.5)                # -1/2 nu_{n,d} <x_n x_n^T>
             return [m0, m1]
         if index == 3:
-            ka = pk[npl - (A.ndim - 2):]
-            dxx = D.sum_product([xx.slice_axis(npl, 1, N).diag_view(1)], [pk + ["n", "d"]], pk + ["d"], scale=-0.5)
-            a = D.sum_product([Sxpxn, A], [pk + ["i", "d"], ka + ["d", "i"]], pk + ["d"])
-            b = D.sum_product([Sxx_head, AA], [pk + ["i", "j"], ka + ["d", "i", "j"]], pk + ["d"], scale=-0.5)
-            return [D.add(D.add(dxx, a), b), DArray.full(P + (Dm,), 0.5 * (N - 1)) if P else DArray.full((Dm,), 0.5 * (N - 1))]
+            ka = pk[npl - (A.ndim - 3):]
+            dxx = D.mul(xx.slice_axis(npl, 1, N).diag_view(1), -0.5)
+            a = D.sum_product([xpxn, A], [pk + ["n", "i", "d"], ka + ["n", "d", "i"]], pk + ["n", "d"])
+            b = D.sum_product([xx_head, AA], [pk + ["n", "i", "j"], ka + ["n", "d", "i", "j"]], pk + ["n", "d"], scale=-0.5)
+            return [D.add(D.add(dxx, a), b), DArray.full(P + (N - 1, Dm), 0.5)]
         raise ValueError("Parent index out of bounds")
 
 
@@ -327,21 +377,33 @@ class GaussianMarkovChain(ExponentialFamily):
         A = ensure_gaussian(A, 1)
         nu = ensure_gamma(nu)
         if tuple(A.dims[0]) != (Dm,) or tuple(A.plates[-1:]) != (Dm,):
-            raise ValueError("A must be a collection of D vectors of length D: plates (D,), shape (D,)")
+            raise ValueError("Dynamics matrix should have a last plate equal to the dimensionality of the system: "
+                             "plates (..., N-1 or 1, D), shape (D,)")
+        # time extents of the dynamics (gaussian_markov_chain.py:840-880): the second-last plate of A / nu
+        TA = int(A.plates[-2]) if len(A.plates) >= 2 else 1
+        Tn = int(nu.plates[-2]) if len(nu.plates) >= 2 else 1
+        n_parents = max(TA, Tn)
+        if TA != 1 and Tn != 1 and TA != Tn:
+            raise ValueError("Plates of parents are giving different number of time instances")
         if n is None:
-            raise ValueError("The length of the chain (keyword n) is required (time-varying dynamics, which would "
-                             "define it, are not supported yet)")
+            if n_parents == 1:
+                raise ValueError("The number of time instances could not be determined automatically. "
+                                 "Give the number of time instances.")
+            n = n_parents + 1
+        elif n_parents != 1 and n_parents + 1 != int(n):
+            raise ValueError("The number of time instances must match the number of last plates of parents: "
+                             "%d != %d+1" % (int(n), n_parents))
         self.N, self.D = int(n), int(Dm)
         from .node import broadcast_plates
-        nu_pl = tuple(nu.plates[:-1]) if len(nu.plates) else ()
-        chain_plates = broadcast_plates(tuple(mu.plates), tuple(Lambda.plates), tuple(A.plates[:-1]), nu_pl)
+        chain_plates = broadcast_plates(tuple(mu.plates), tuple(Lambda.plates), tuple(A.plates[:-2]),
+                                        tuple(nu.plates[:-2]))
         if plates is not None:
             plates = tuple(int(p) for p in plates)
             chain_plates = broadcast_plates(chain_plates, plates)
             if chain_plates != plates:
                 raise ValueError("The plates %s of the parents are not broadcastable to the given plates %s."
                                  % (chain_plates, plates))
-        dist = GaussianMarkovChainDistribution(self.N, self.D, chain_plates)
+        dist = GaussianMarkovChainDistribution(self.N, self.D, chain_plates, TA=TA, Tn=Tn)
         super().__init__(mu, Lambda, A, nu, dims=((self.N, Dm), (self.N, Dm, Dm), (self.N - 1, Dm, Dm)),
                          distribution=dist, plates=chain_plates, name=name, initialize=initialize)
 

@@ -147,8 +147,18 @@ class FactorModelPlan:
                                       "(fully observed data, no annealing)")
         return ok
 
+    def _structure_ok(self):
+        """The graph still has the shape ``attach`` matched: nobody hung another child on the factors, the
+        product node or the data since (their messages would be dropped by the fused updates).  Cheap; checked on
+        every call, because nodes can be added to a model after VB(...) was built."""
+        return (len(self.col.children) == 1 and len(self.row.children) == 1 and len(self.F.children) == 1
+                and not self.Y.children)
+
     def _valid(self):
         Y, col, row = self.Y, self.col, self.row
+        if not self._structure_ok():
+            self._res_cache = None
+            return False
         if not (Y.observed is True or (isinstance(Y.observed, np.ndarray) and Y.observed.all())):
             return False
         if not mask_is_full(Y.mask):
@@ -418,8 +428,12 @@ class FactorModelPlan:
         order = [n for n in order if n is not Y and n is not self.F]
         if set(order) != latent or len(order) != len(latent):
             return None
-        hk = tuple(id(pp) for n in (col, row, alpha, tau) for pp in getattr(n, "parents", ())) + (id(alpha), id(tau))
+        # everything _resident_hyper() decides on: parent identities, observed state and fan-out of the hyper nodes
+        hk = tuple(id(pp) for n in (col, row, alpha, tau) for pp in getattr(n, "parents", ())) + (id(alpha), id(tau)) \
+            + tuple((repr(getattr(n, "observed", None)) if not isinstance(getattr(n, "observed", None), np.ndarray)
+                     else "array", len(getattr(n, "children", ()))) for n in (alpha, tau))
         if getattr(self, "_hyper_key", None) != hk:
+            self._res_cache = None
             self._hyper = self._resident_hyper()
             self._hyper_key = hk
             self._hsig = None if self._hyper is None else \
@@ -489,6 +503,16 @@ class FactorModelPlan:
         M, N, K = self.M, self.N, self.K
         import time
         import warnings
+        if self.world > 1 and hasattr(be, "pca_vb_set_mode"):
+            # the persistent multi-sweep launch needs 16-byte aligned rows (even N, aligned Y); every rank must
+            # take the same route through the in-kernel exchange, so agree on it once per data buffer
+            Yp = self._Yd().ptr
+            key = (Yp, N)
+            if getattr(self, "_loop_key", None) != key:
+                mine = 1.0 if (N % 2 == 0 and Yp % 16 == 0) else 0.0
+                self._loop_all = bool(np.min(parallel.allgather_scalar(mine)) > 0.5)
+                self._loop_key = key
+            be.pca_vb_set_mode(not self._loop_all)
         check = not vb.ignore_bound_checks
         tol_dev = (vb.tol if tol is None else tol) if check else -1.0
         lprev = np.nan

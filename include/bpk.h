@@ -57,6 +57,9 @@ int bpk_shutdown(void);
 const char *bpk_last_error(void);
 int bpk_device_info(int *sm_count, int *cc_major, int *cc_minor,
                     uint64_t *hbm_total, uint64_t *hbm_free);
+/* PCI bus id ("0000:1b:00.0") of the bound GPU: lets the host pin a rank's threads and pinned buffers to the
+ * GPU's NUMA node (parallel.bind_to_gpu_numa).  The reference is single-process NumPy and has no such notion.   */
+int bpk_device_pci_bus_id(char *buf, int len);
 int bpk_sync(void);
 uint64_t bpk_launch_count(void);      /* kernels launched since bpk_init    */
 int bpk_malloc(void **dev, uint64_t bytes);
@@ -249,6 +252,11 @@ const char *bpk_pca_vb_field_name(int i);
 int bpk_pca_vb_run(const double *Y, int64_t M, int64_t N, int K, double *X, double *state,
                    const int *ops, int nops, int niter, int has_alpha, int has_tau, double tol,
                    double *Lhist, int cap, int *ctrl);
+/* Multi-rank runs: every rank must drive the in-kernel exchange the same way.  The persistent multi-sweep launch
+ * needs 16-byte aligned rows on THIS rank (even N); no_loop = 1 makes this rank use one launch per sweep with the
+ * full statistics vector on the wire, which is what ranks with unaligned shards do anyway (the host agrees on the
+ * flag collectively, plans.FactorModelPlan).  Returns the previous value through *prev (nullable).              */
+int bpk_pca_vb_set_mode(int no_loop, int *prev);
 /* bench.py: record these timers (bpk_timer_create ids) around the next n sweep-kernel launches */
 int bpk_pca_vb_set_timers(const int *ids, int n);
 int bpk_pca_vb_timers_used(void);

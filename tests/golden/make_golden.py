@@ -400,8 +400,64 @@ def lssm_plated(name="lssm_plated", M=5, N=30, D=3, P=2, iters=5):
     save(name, **out)
 
 
+def lssm_varying(name="lssm_varying", M=5, N=12, D=2, iters=4):
+    """One chain with a transition matrix and an innovation precision PER STEP: A and nu with plates (N-1, D)
+    (gaussian_markov_chain.py:660-706, 840-880; the chain length is inferred from the parents)."""
+    from bayespy.nodes import GaussianMarkovChain, Dot
+    rs = np.random.RandomState(21)
+    y = rs.randn(M, N).cumsum(axis=-1) * 0.3 + rs.randn(M, N)
+    alpha = Gamma(1e-5, 1e-5, plates=(D,), name="alpha")
+    A = GaussianARD(0, alpha, shape=(D,), plates=(N - 1, D), name="A")
+    A_init = 0.5 * rs.randn(N - 1, D, D)
+    A.initialize_from_value(A_init)
+    nu = Gamma(1e-3, 1e-3, plates=(N - 1, D), name="nu")
+    X = GaussianMarkovChain(np.zeros(D), 1e-3 * np.identity(D), A, nu, name="X")
+    assert X.plates == () and X.dims[0] == (N, D)
+    gamma = Gamma(1e-5, 1e-5, plates=(D,), name="gamma")
+    C = GaussianARD(0, gamma, shape=(D,), plates=(M, 1), name="C")
+    F = Dot(C, X, name="F")
+    C_init = rs.randn(M, 1, D)
+    C.initialize_from_value(C_init)
+    tau = Gamma(1e-5, 1e-5, name="tau")
+    Y = GaussianARD(F, tau, name="Y")
+    Y.observe(y)
+    Q = VB(X, C, gamma, A, alpha, nu, tau, Y)
+    Q.update(repeat=iters, verbose=False, tol=0)
+    out = dict(y=y, C_init=C_init, A_init=A_init, L=Q.L[:iters])
+    for nm, node in (("X", X), ("C", C), ("A", A), ("alpha", alpha), ("nu", nu), ("tau", tau)):
+        node_state(nm, node, out)
+    save(name, **out)
+
+
+def lssm_plated_dynamics(name="lssm_plated_dynamics", M=4, N=15, D=2, P=3, iters=4):
+    """P independent chains, each with ITS OWN time-invariant dynamics: A with plates (P, 1, D)."""
+    from bayespy.nodes import GaussianMarkovChain, Dot
+    rs = np.random.RandomState(22)
+    y = rs.randn(M, P, N).cumsum(axis=-1) * 0.3 + rs.randn(M, P, N)
+    alpha = Gamma(1e-5, 1e-5, plates=(D,), name="alpha")
+    A = GaussianARD(0, alpha, shape=(D,), plates=(P, 1, D), name="A")
+    A_init = 0.5 * rs.randn(P, 1, D, D)
+    A.initialize_from_value(A_init)
+    X = GaussianMarkovChain(np.zeros(D), 1e-3 * np.identity(D), A, np.ones(D), n=N, name="X")
+    assert X.plates == (P,)
+    gamma = Gamma(1e-5, 1e-5, plates=(D,), name="gamma")
+    C = GaussianARD(0, gamma, shape=(D,), plates=(M, 1, 1), name="C")
+    F = Dot(C, X, name="F")
+    C_init = rs.randn(M, 1, 1, D)
+    C.initialize_from_value(C_init)
+    tau = Gamma(1e-5, 1e-5, name="tau")
+    Y = GaussianARD(F, tau, name="Y")
+    Y.observe(y)
+    Q = VB(X, C, gamma, A, alpha, tau, Y)
+    Q.update(repeat=iters, verbose=False, tol=0)
+    out = dict(y=y, C_init=C_init, A_init=A_init, L=Q.L[:iters])
+    for nm, node in (("X", X), ("C", C), ("A", A), ("alpha", alpha), ("tau", tau)):
+        node_state(nm, node, out)
+    save(name, **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["quickstart", "pca", "linalg", "summul", "dist", "gmm", "gmc", "rot", "dot", "mixard", "gmcplates"]
+    which = sys.argv[1:] or ["quickstart", "pca", "linalg", "summul", "dist", "gmm", "gmc", "rot", "dot", "mixard", "gmcplates", "gmcvarying"]
     if "quickstart" in which:
         quickstart()
     if "pca" in which:
@@ -425,6 +481,9 @@ if __name__ == "__main__":
         pca_rotated()
     if "gmcplates" in which:
         lssm_plated()
+    if "gmcvarying" in which:
+        lssm_varying()
+        lssm_plated_dynamics()
     if "gmc" in which:
         block_banded_vectors()
         lssm("lssm_small", 6, 40, 3)

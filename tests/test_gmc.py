@@ -162,10 +162,9 @@ def test_utils_linalg_block_banded_solve_api(backend):
         linalg.block_banded_solve(g["A_b"][:-1], g["B_b"], g["y_b"])
 
 
-def test_plated_chains_match_reference(oracle_backend):
+def test_plated_chains_match_reference(backend):
     """Two independent chains (plates (2,)) sharing A and C (gaussian_markov_chain.py with plates): bound trajectory
-    and moments against the reference.  Host logic + oracle only: the batched solver kernel itself is covered on the
-    GPU by test_block_banded_solve_batched_and_dense_inverse."""
+    and moments against the reference (oracle on CPU, libbpk under -m gpu)."""
     from bayespy_b200.nodes import GaussianARD, GaussianMarkovChain, Gamma, Dot
     from bayespy_b200.inference import VB
     g = golden("lssm_plated")
@@ -191,3 +190,80 @@ def test_plated_chains_match_reference(oracle_backend):
         for i in range(len(node.u)):
             np.testing.assert_allclose(np.asarray(node.u[i]), g["%s_u%d" % (nm, i)], rtol=1e-6, atol=1e-9,
                                        err_msg="%s.u[%d]" % (nm, i))
+
+
+def _check_nodes(g, nodes, rtol=1e-6):
+    for nm, node in nodes:
+        for i in range(len(node.u)):
+            np.testing.assert_allclose(np.asarray(node.u[i]), g["%s_u%d" % (nm, i)], rtol=rtol, atol=1e-9,
+                                       err_msg="%s.u[%d]" % (nm, i))
+
+
+def test_time_varying_dynamics_match_reference(backend):
+    """A and nu with plates (N-1, D): one transition matrix / innovation precision per step, chain length inferred
+    from the parents (gaussian_markov_chain.py:660-706, 840-880) — the reference's own plate layout."""
+    from bayespy_b200.nodes import GaussianARD, GaussianMarkovChain, Gamma, Dot
+    from bayespy_b200.inference import VB
+    g = golden("lssm_varying")
+    M, N = g["y"].shape
+    Dm = g["C_init"].shape[-1]
+    alpha = Gamma(1e-5, 1e-5, plates=(Dm,), name="alpha")
+    A = GaussianARD(0, alpha, shape=(Dm,), plates=(N - 1, Dm), name="A")
+    A.initialize_from_value(g["A_init"])
+    nu = Gamma(1e-3, 1e-3, plates=(N - 1, Dm), name="nu")
+    X = GaussianMarkovChain(np.zeros(Dm), 1e-3 * np.identity(Dm), A, nu, name="X")
+    assert tuple(X.plates) == () and tuple(X.dims[0]) == (N, Dm)
+    gamma = Gamma(1e-5, 1e-5, plates=(Dm,), name="gamma")
+    C = GaussianARD(0, gamma, shape=(Dm,), plates=(M, 1), name="C")
+    F = Dot(C, X, name="F")
+    C.initialize_from_value(g["C_init"])
+    tau = Gamma(1e-5, 1e-5, name="tau")
+    Y = GaussianARD(F, tau, name="Y")
+    Y.observe(g["y"])
+    Q = VB(X, C, gamma, A, alpha, nu, tau, Y)
+    iters = len(g["L"])
+    Q.update(repeat=iters, verbose=False, tol=0)
+    np.testing.assert_allclose(Q.L[:iters], g["L"], rtol=1e-8)
+    _check_nodes(g, (("X", X), ("C", C), ("A", A), ("alpha", alpha), ("nu", nu), ("tau", tau)))
+
+
+def test_plated_dynamics_match_reference(backend):
+    """A with plates (P, 1, D): P independent chains, each with its own time-invariant transition matrix."""
+    from bayespy_b200.nodes import GaussianARD, GaussianMarkovChain, Gamma, Dot
+    from bayespy_b200.inference import VB
+    g = golden("lssm_plated_dynamics")
+    M, P, N = g["y"].shape
+    Dm = g["C_init"].shape[-1]
+    alpha = Gamma(1e-5, 1e-5, plates=(Dm,), name="alpha")
+    A = GaussianARD(0, alpha, shape=(Dm,), plates=(P, 1, Dm), name="A")
+    A.initialize_from_value(g["A_init"])
+    X = GaussianMarkovChain(np.zeros(Dm), 1e-3 * np.identity(Dm), A, np.ones(Dm), n=N, name="X")
+    assert tuple(X.plates) == (P,)
+    gamma = Gamma(1e-5, 1e-5, plates=(Dm,), name="gamma")
+    C = GaussianARD(0, gamma, shape=(Dm,), plates=(M, 1, 1), name="C")
+    F = Dot(C, X, name="F")
+    C.initialize_from_value(g["C_init"])
+    tau = Gamma(1e-5, 1e-5, name="tau")
+    Y = GaussianARD(F, tau, name="Y")
+    Y.observe(g["y"])
+    Q = VB(X, C, gamma, A, alpha, tau, Y)
+    iters = len(g["L"])
+    Q.update(repeat=iters, verbose=False, tol=0)
+    np.testing.assert_allclose(Q.L[:iters], g["L"], rtol=1e-8)
+    _check_nodes(g, (("X", X), ("C", C), ("A", A), ("alpha", alpha), ("tau", tau)))
+
+
+def test_dynamics_plates_follow_the_reference_layout(oracle_backend):
+    """(N-1, D) is ONE time-varying chain, not N-1 chains; a wrong time extent is rejected."""
+    from bayespy_b200.nodes import GaussianARD, GaussianMarkovChain
+    Dm, N = 2, 6
+    A = GaussianARD(0, 1, shape=(Dm,), plates=(N - 1, Dm))
+    X = GaussianMarkovChain(np.zeros(Dm), np.identity(Dm), A, np.ones(Dm), n=N)
+    assert tuple(X.plates) == () and np.asarray(X.u[0]).shape == (N, Dm)
+    with pytest.raises(ValueError):
+        GaussianMarkovChain(np.zeros(Dm), np.identity(Dm), A, np.ones(Dm), n=N + 2)
+    A3 = GaussianARD(0, 1, shape=(Dm,), plates=(4, 1, Dm))
+    X3 = GaussianMarkovChain(np.zeros(Dm), np.identity(Dm), A3, np.ones(Dm), n=N)
+    assert tuple(X3.plates) == (4,)
+    with pytest.raises(ValueError):
+        GaussianMarkovChain(np.zeros(Dm), np.identity(Dm), GaussianARD(0, 1, shape=(Dm,), plates=(Dm,)), np.ones(Dm))

@@ -136,3 +136,57 @@ def test_layout_of_the_library_matches_the_oracle():
         for i in range(n.value):
             name = lib.bpk_pca_vb_field_name(i).decode()
             assert lay[name] == (off[i], off[i + 1] - off[i]), name
+
+
+# ---- plan preconditions are re-validated on every call (round-1 advisor findings) -------------------------------
+def test_observing_a_hyper_node_after_a_resident_run_leaves_the_resident_path(backend):
+    """tau.observe(...) between two updates: the resident loop must not keep updating tau as latent."""
+    y = _data(12, 150, 4, seed=9)
+    out = []
+    for resident, fused in ((True, True), (False, False)):
+        from bayespy_b200.nodes import GaussianARD, Gamma, SumMultiply
+        from bayespy_b200.inference import VB
+        M, N, K = 12, 150, 4
+        X = GaussianARD(0, 1, plates=(1, N), shape=(K,), name="X")
+        alpha = Gamma(1e-3, 1e-3, plates=(K,), name="alpha")
+        C = GaussianARD(0, alpha, plates=(M, 1), shape=(K,), name="C")
+        F = SumMultiply("d,d->", X, C)
+        tau = Gamma(1e-3, 1e-3, name="tau")
+        Y = GaussianARD(F, tau, name="Y")
+        Y.observe(y)
+        C.initialize_from_value(np.random.RandomState(3).randn(M, 1, K))
+        Q = VB(Y, X, C, alpha, tau, resident=resident, fused=fused)
+        Q.update(repeat=2, verbose=False, tol=0)
+        tau.observe(7.0)
+        Q.update(repeat=2, verbose=False, tol=0)
+        out.append((Q.L[:4].copy(), np.asarray(tau.u[0]).copy(), np.asarray(C.u[0]).copy()))
+    np.testing.assert_allclose(out[0][0], out[1][0], rtol=1e-9)
+    np.testing.assert_allclose(out[0][1], 7.0)
+    np.testing.assert_allclose(out[0][2], out[1][2], rtol=1e-8, atol=1e-10)
+
+
+def test_a_child_added_after_vb_is_not_dropped(backend):
+    """A second child hung on X after VB(...) was built: the fused X update would drop its message."""
+    from bayespy_b200.nodes import GaussianARD
+    y = _data(12, 150, 4, seed=10)
+    res = []
+    for fused in (True, False):
+        Q, n = _pca(y, 4, resident=fused)
+        if not fused:
+            for plan in Q.plans:          # take the plans out entirely: the per-node path pinned to the reference
+                for k, fn in (("col.update", "update"), ("col.lb", "lower_bound_contribution")):
+                    setattr(plan.col, fn, plan._orig[k])
+                plan.F.message_to_parent = plan._orig["F.msg"]
+                plan.Y.message_to_parent = plan._orig["Y.msg"]
+                plan.Y.lower_bound_contribution = plan._orig["Y.lb"]
+            Q.plans = []
+        Q.update(repeat=2, verbose=False, tol=0)
+        W = GaussianARD(n["X"], 5.0, name="W")
+        W.observe(0.3 * np.ones((1, 150, 4)))
+        Q.update(repeat=2, verbose=False, tol=0)
+        res.append(np.asarray(n["X"].u[0]).copy())
+    np.testing.assert_allclose(res[0], res[1], rtol=1e-8, atol=1e-10)
+    # and the extra child really mattered (the result differs from the model without it)
+    Q0, n0 = _pca(y, 4, resident=True)
+    Q0.update(repeat=4, verbose=False, tol=0)
+    assert np.max(np.abs(np.asarray(n0["X"].u[0]) - res[0])) > 1e-3
