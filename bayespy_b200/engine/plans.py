@@ -496,6 +496,73 @@ class FactorModelPlan:
         state = DArray.from_numpy(st)
         return state, lay
 
+    def _resident_state(self, order, lprev, need_prev=False):
+        """Device state vector + X buffer for a resident run: re-used straight after a resident run when nothing
+        touched the nodes in between (the state and X of that run are still exact), else rebuilt from the nodes."""
+        alpha_n = self.row.parents[1]
+        watched = [self.Y, self.col, self.row] + [n for n in (alpha_n, self.tau) if isinstance(n, Gamma)]
+        hsig = self._hsig
+        cache = getattr(self, "_res_cache", None)
+        if cache is not None and cache["versions"] == [n._version for n in watched] and cache["hsig"] == hsig \
+                and cache["nodes"] == [id(n) for n in watched] and not (need_prev and np.isnan(lprev)):
+            state, lay, X = cache["state"], cache["lay"], cache["X"]
+        else:
+            cache = None
+            state, lay = self._resident_enter(order, lprev)
+            X = DArray.empty((1, self.N, self.K))
+        self._res_cache = None
+        return state, lay, X, cache, watched, hsig
+
+    @staticmethod
+    def _raise_ctrl_errors(err):
+        if err & 1:
+            raise _bpk.NotPositiveDefinite("Matrix not positive definite")
+        if err & 2:
+            raise ValueError("Natural parameters should be positive")
+        if err & 4:
+            raise _bpk.BpkError(_bpk.ENCCL, "peer-memory exchange timed out (a rank stopped responding)")
+        if err & 8:
+            raise _bpk.BpkError(_bpk.ECUDA, "grid barrier of the fused sweep kernel timed out (is another process "
+                                            "using this GPU? the persistent grid must be fully resident)")
+
+    def sweep_resident(self, vb, program):
+        """ONE sweep of ``VB.update`` — every node update of the user's order, no lower bound — as one fused launch.
+        Used when a callback (e.g. the rotation of transformations.py) must run between the node updates and the
+        bound evaluation (vmp.py:702-713): the heavy part of the iteration stays on the device path, the callback
+        sees and may modify the node objects, and the bound is then evaluated from the plate-summed statistics."""
+        be = _bpk.get()
+        ops, order = program
+        ops = [o for o in ops if o != _bpk.VBOP["BOUND"]]
+        M, N, K = self.M, self.N, self.K
+        self._agree_on_loop_mode(be)
+        state, lay, X, cache, watched, hsig = self._resident_state(order, np.nan)
+        alpha = self.row.parents[1]
+        ctrl = DArray.zeros((2,))
+        Lh = DArray.empty((1, 6))
+        be.pca_vb_run(self._Yd().ptr, M, N, K, X.ptr, state.ptr, ops, 1, isinstance(alpha, Gamma),
+                      isinstance(self.tau, Gamma), -1.0, Lh.ptr, 0, ctrl.ptr)
+        c = ctrl.numpy().view(np.int32)
+        self._raise_ctrl_errors(int(c[2]))
+        self.fused_calls += 1
+        if cache is not None and state is cache["state"]:
+            self._resident_republish(X)
+        else:
+            self._resident_publish(state, lay, X, order)
+        self._res_cache = dict(state=state, lay=lay, X=X, hsig=hsig, nodes=[id(n) for n in watched],
+                               versions=[n._version for n in watched])
+
+    def _agree_on_loop_mode(self, be):
+        if self.world > 1 and hasattr(be, "pca_vb_set_mode"):
+            # the persistent multi-sweep launch needs 16-byte aligned rows (even N, aligned Y); every rank must
+            # take the same route through the in-kernel exchange, so agree on it once per data buffer
+            Yp = self._Yd().ptr
+            key = (Yp, self.N)
+            if getattr(self, "_loop_key", None) != key:
+                mine = 1.0 if (self.N % 2 == 0 and Yp % 16 == 0) else 0.0
+                self._loop_all = bool(np.min(parallel.allgather_scalar(mine)) > 0.5)
+                self._loop_key = key
+            be.pca_vb_set_mode(not self._loop_all)
+
     def run_resident(self, vb, program, repeat, tol, verbose):
         """``VB.update`` for this model without leaving the device between sweeps."""
         be = _bpk.get()
@@ -503,34 +570,13 @@ class FactorModelPlan:
         M, N, K = self.M, self.N, self.K
         import time
         import warnings
-        if self.world > 1 and hasattr(be, "pca_vb_set_mode"):
-            # the persistent multi-sweep launch needs 16-byte aligned rows (even N, aligned Y); every rank must
-            # take the same route through the in-kernel exchange, so agree on it once per data buffer
-            Yp = self._Yd().ptr
-            key = (Yp, N)
-            if getattr(self, "_loop_key", None) != key:
-                mine = 1.0 if (N % 2 == 0 and Yp % 16 == 0) else 0.0
-                self._loop_all = bool(np.min(parallel.allgather_scalar(mine)) > 0.5)
-                self._loop_key = key
-            be.pca_vb_set_mode(not self._loop_all)
+        self._agree_on_loop_mode(be)
         check = not vb.ignore_bound_checks
         tol_dev = (vb.tol if tol is None else tol) if check else -1.0
         lprev = np.nan
         if check and not vb.annealing_changed and vb.iter > 0:
             lprev = vb.L[vb.iter - 1]
-        # re-entry straight after a resident run (nothing touched the nodes in between): the device
-        # state vector and the X buffer of that run are still exact — skip the host-side rebuild
-        alpha_n = self.row.parents[1]
-        watched = [self.Y, self.col, self.row] + [n for n in (alpha_n, self.tau) if isinstance(n, Gamma)]
-        hsig = self._hsig
-        cache = getattr(self, "_res_cache", None)
-        if cache is not None and cache["versions"] == [n._version for n in watched] and cache["hsig"] == hsig \
-                and cache["nodes"] == [id(n) for n in watched] and not (check and np.isnan(lprev) and vb.iter > 0):
-            state, lay, X = cache["state"], cache["lay"], cache["X"]
-        else:
-            state, lay = self._resident_enter(order, lprev)
-            X = DArray.empty((1, N, K))
-        self._res_cache = None
+        state, lay, X, cache, watched, hsig = self._resident_state(order, lprev, need_prev=check and vb.iter > 0)
         fast = M <= 64 and K <= 16
         alpha = self.row.parents[1]
         has_alpha, has_tau = isinstance(alpha, Gamma), isinstance(self.tau, Gamma)
@@ -560,15 +606,7 @@ class FactorModelPlan:
             n_it, stop, err = int(c[0]), int(c[1]), int(c[2])
             if self.kernel_timers is not None and self.kernel_timer_log and self.kernel_timer_log[-1][1] is None:
                 self.kernel_timer_log[-1] = (self.kernel_timer_log[-1][0], n_it)
-            if err & 1:
-                raise _bpk.NotPositiveDefinite("Matrix not positive definite")
-            if err & 2:
-                raise ValueError("Natural parameters should be positive")
-            if err & 4:
-                raise _bpk.BpkError(_bpk.ENCCL, "peer-memory exchange timed out (a rank stopped responding)")
-            if err & 8:
-                raise _bpk.BpkError(_bpk.ECUDA, "grid barrier of the fused sweep kernel timed out (is another process "
-                                                "using this GPU? the persistent grid must be fully resident)")
+            self._raise_ctrl_errors(err)
             Lrows = Lh.numpy()[:n_it]
             for r in range(n_it):
                 if vb.iter >= len(vb.L):

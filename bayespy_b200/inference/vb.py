@@ -83,22 +83,37 @@ class VB:
         if len(nodes) == 0:
             nodes = self.model
         # whole sweeps that can stay on the device do (engine/plans.py: FactorModelPlan.run_resident)
-        if self.resident and tqdm is None and not plot and not callable(self.callback) \
-                and self.autosave_iterations == 0:
+        sweep_plan = None
+        if self.resident and self.autosave_iterations == 0:
             for plan in self.plans:
                 prog = plan.resident_program(self, nodes) if hasattr(plan, "resident_program") else None
-                if prog is not None:
+                if prog is None:
+                    continue
+                if tqdm is None and not plot and not callable(self.callback):
                     plan.run_resident(self, prog, repeat, tol, verbose)
                     return
+                # a callback / progress bar / plot wants the host between the node updates and the bound
+                # (vmp.py:702-713): keep every node update of the sweep in ONE fused launch, then hand over
+                if hasattr(plan, "sweep_resident"):
+                    sweep_plan = (plan, prog)
+                break
         if tqdm is not None:
             tqdm = tqdm(total=repeat)
         i = 0
         while repeat is None or i < repeat:
             t = time.time()
-            for node in nodes:
-                X = self[node]
-                if hasattr(X, "update") and callable(X.update):
-                    X.update()
+            if sweep_plan is not None:
+                # the program is re-derived every iteration: the callback may have changed the graph
+                prog = sweep_plan[0].resident_program(self, nodes)
+                if prog is None:
+                    sweep_plan = None
+            if sweep_plan is not None:
+                sweep_plan[0].sweep_resident(self, prog)
+            else:
+                for node in nodes:
+                    X = self[node]
+                    if hasattr(X, "update") and callable(X.update):
+                        X.update()
             cputime = time.time() - t
             i += 1
             if tqdm is not None:

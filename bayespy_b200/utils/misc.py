@@ -39,6 +39,9 @@ def sum_multiply(*args, axis=None, sumaxis=True, keepdims=False):
         else:
             ax = [axis] if np.isscalar(axis) else list(axis)
             keep = sorted(i if i >= 0 else i + max_dim for i in ax)
+            if len(set(keep)) != len(keep):
+                # the reference's einsum rejects a repeated output axis (misc.py:906)
+                raise ValueError("Axis %s given several times" % (axis,))
     if keep and (min(keep) < 0 or max(keep) >= max_dim):
         raise ValueError("Axis index out of bounds")
     ksets = [list(range(max_dim - a.ndim, max_dim)) for a in arrs]

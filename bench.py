@@ -4,7 +4,7 @@
     python bench.py --gpus 1 --steps 20 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
-    python bench.py --impl reference --steps K --warmup W      # CPU arm (oracle port of the reference)
+    python bench.py --impl reference --steps K --warmup W      # CPU arm: the unmodified reference (oracle/_ref)
 
 One "step" = one full ``Q.update()`` sweep over [X, C, alpha, tau] INCLUDING the lower-bound
 evaluation VB.update always performs (vmp.py:154-172, :713).  Model and synthetic data follow
@@ -19,6 +19,10 @@ library's compute stream, max over ranks.  Inputs (5.12 GB of Y at N=10M) are la
 import argparse
 import json
 import os
+import sys as _sys
+if "reference" in _sys.argv:
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm may use every host thread BLAS wants (fixed across N)
+    os.environ.pop("OMP_NUM_THREADS", None)
 import subprocess
 import sys
 import tempfile
@@ -34,7 +38,8 @@ M_DIM, K_DIM = 64, 16
 N_TOTAL = 10_000_000
 METRIC = "VB iterations/sec on PCA N=10M D=64 K=16"
 BYTES_PER_COL = M_DIM * 8 + K_DIM * 8                       # 640 B
-FLOPS_PER_COL = 2 * M_DIM * K_DIM * 2 + 2 * K_DIM * K_DIM + K_DIM * (K_DIM + 1)   # ~4.9 kflop
+FLOPS_PER_COL = 2 * M_DIM * K_DIM * 2 + 2 * K_DIM * K_DIM + K_DIM * (K_DIM + 1)   # ~4.9 kflop (algorithmic)
+EXEC_FLOPS_PER_COL = 8 * 512                                # the sweep kernel executes 8 DMMA.8x8x4 per column
 
 
 def load_peaks():
@@ -48,38 +53,38 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+BLOCK = 65536      # columns per independently seeded block of synthetic data
+
+
 def synth_shard(M, n0, n1, seed):
-    """Columns [n0, n1) of y = w x^T + 0.1 eps (pca.rst:29-32 pattern); w is shared by all
-    ranks (seed), x / eps are per-shard streams."""
-    rng_w = np.random.default_rng(seed)
-    w = rng_w.standard_normal((M, 4))
-    rng = np.random.default_rng([seed, n0])
-    n = n1 - n0
-    x = rng.standard_normal((4, n))
-    y = rng.standard_normal((M, n))
-    y *= 0.1
-    y += w @ x
-    return y
+    """Columns [n0, n1) of y = w x^T + 0.1 eps (pca.rst:29-32 pattern).  The stream is seeded per fixed block of
+    65 536 columns, so column n holds the same numbers whatever the world size or the shard bounds: every SCALE
+    line works on the same 10M columns, and the reference arm's sample is a prefix of the GPU arm's data."""
+    w = np.random.default_rng(seed).standard_normal((M, 4))
+    out = np.empty((M, n1 - n0))
+    for blk in range(n0 // BLOCK, (max(n1, n0 + 1) - 1) // BLOCK + 1):
+        c0, c1 = blk * BLOCK, (blk + 1) * BLOCK
+        rng = np.random.default_rng([seed, blk])
+        x = rng.standard_normal((4, BLOCK))
+        y = rng.standard_normal((M, BLOCK))
+        y *= 0.1
+        y += w @ x
+        lo, hi = max(c0, n0), min(c1, n1)
+        if hi > lo:
+            out[:, lo - n0:hi - n0] = y[:, lo - c0:hi - c0]
+    return out
+
+
+def init_C(M, K):
+    """Replicated initial <C>: identical on every rank and in the reference arm."""
+    return np.random.RandomState(1).randn(M, 1, K)
 
 
 # =============================================================================================
-# reference arm / cpu_baseline: the oracle port of the reference's NumPy/SciPy sweep
+# reference arm / cpu_baseline: the UNMODIFIED reference package (oracle/_ref, staged by
+# oracle/make_ref.py) running the same model script on a prefix of the same data; falls back to
+# the oracle port (oracle/pca_ref.py) only if the staged package is missing.
 # =============================================================================================
-def cpu_sweeps(n_sample, steps, warmup, seed=1):
-    from oracle.pca_ref import PcaOracle
-    y = synth_shard(M_DIM, 0, n_sample, seed)
-    rs = np.random.RandomState(seed)
-    C0 = rs.randn(M_DIM, 1, K_DIM)
-    o = PcaOracle(y, K_DIM, C0)
-    for _ in range(warmup):
-        o.sweep()
-    t = time.perf_counter()
-    for _ in range(steps):
-        o.sweep()
-    dt = (time.perf_counter() - t) / max(steps, 1)
-    return dt
-
-
 def blas_threads():
     try:
         from threadpoolctl import threadpool_info
@@ -88,27 +93,65 @@ def blas_threads():
         return os.cpu_count() or 1
 
 
+def reference_sweep_seconds(n_sample, steps, warmup):
+    """(seconds per sweep, kind) of the reference's Q.update() on the first n_sample columns."""
+    y = synth_shard(M_DIM, 0, n_sample, 1)
+    try:
+        from oracle import make_ref, ref_models
+        if not make_ref.available():
+            raise RuntimeError("oracle/_ref not staged")
+        Q, _ = ref_models.pca(y, K_DIM, init_C(M_DIM, K_DIM))
+        return ref_models.time_sweeps(Q, steps, warmup), "reference"
+    except Exception as e:                                   # pragma: no cover - only without oracle/_ref
+        sys.stderr.write("bench: reference package unavailable (%s); timing the oracle port instead\n" % e)
+        from oracle.pca_ref import PcaOracle
+        o = PcaOracle(y, K_DIM, init_C(M_DIM, K_DIM))
+        for _ in range(warmup):
+            o.sweep()
+        t = time.perf_counter()
+        for _ in range(steps):
+            o.sweep()
+        return (time.perf_counter() - t) / max(steps, 1), "port"
+
+
+def reference_sample_size(steps, warmup, budget_s):
+    """Columns per step such that warmup+steps sweeps of the reference take about budget_s seconds
+    (calibrated on one 10k-column sweep; the reference is O(N) per sweep, ~45 us/col on this class of host)."""
+    dt, _ = reference_sweep_seconds(10_000, 1, 1)
+    per_col = dt / 10_000
+    n = int(budget_s / max(steps + warmup, 1) / per_col)
+    n = max(20_000, min(200_000, n))
+    return (n // 1000) * 1000, per_col
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_sample = 30_000
-    dt = cpu_sweeps(n_sample, args.steps, args.warmup)
-    scale = N_TOTAL / n_sample
+    n_total = args.n
+    n_sample, _ = reference_sample_size(args.steps, args.warmup, args.ref_budget_s)
+    dt, kind = reference_sweep_seconds(n_sample, args.steps, args.warmup)
+    scale = n_total / n_sample
     value = 1.0 / (dt * scale)
     cores = blas_threads()
-    sample = ("oracle/pca_ref.py (NumPy/SciPy port of the reference sweep) on the first %d of %d columns, "
-              "%d timed sweeps; it/s extrapolated linearly in N (the reference is O(N) per sweep and needs "
-              "~9 KB/col, so N=10M does not fit a practical host run); np.einsum is single-threaded, BLAS "
-              "threads=%d of %d host cores" % (n_sample, N_TOTAL, args.steps, cores, os.cpu_count() or 1))
+    what = ("the unmodified reference package (oracle/_ref, staged from /root/reference by oracle/make_ref.py)"
+            if kind == "reference" else "oracle/pca_ref.py (NumPy/SciPy port of the reference sweep)")
+    sample = ("%s running pca.rst:40-66 on the first %d of %d columns of the GPU arm's data, %d timed Q.update() sweeps "
+              "after %d warm-up; it/s extrapolated linearly in N (x%.1f: the reference is O(N) per sweep and needs "
+              "~9 KB/col of host RAM, N=1e7 does not fit a practical host run); np.einsum and the per-plate loops are "
+              "single-threaded, BLAS threads=%d of %d host cores"
+              % (what, n_sample, n_total, args.steps, args.warmup, scale, cores, os.cpu_count() or 1))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "it/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt * scale,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "Bayesian PCA N=1e7 M=64 K=16 fully observed, one VB sweep incl. lower bound",
-                   "cpu_sample_columns": n_sample},
-        "cpu_baseline": {"value": value, "unit": "it/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": "Bayesian PCA N=%d M=64 K=16 fully observed (pca.rst:40-66), one VB sweep over "
+                               "[X,C,alpha,tau] incl. lower bound" % n_total,
+                   "n_total": n_total, "cpu_sample_columns": n_sample, "value_is_extrapolated": True,
+                   "extrapolation_factor": scale, "ms_per_step_note": "measured, one step = one sweep over the sample",
+                   "ms_per_step_full_n_extrapolated": 1e3 * dt * scale},
+        "cpu_baseline": {"value": value, "unit": "it/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -192,17 +235,27 @@ def build_model(y_host, fused=True):
     tau = Gamma(1e-5, 1e-5, name="tau")
     Y = GaussianARD(F, tau, name="Y")
     Y.observe(y_host)
-    rs = np.random.RandomState(1)                      # replicated factor: identical on every rank
-    C.initialize_from_value(rs.randn(M, 1, K))
+    C.initialize_from_value(init_C(M, K))              # replicated factor: identical on every rank
     Q = VB(Y, X, C, alpha, tau, fused=fused)
     Q.ignore_bound_checks = True                       # time exactly K sweeps (no early convergence return)
     return Q, dict(X=X, C=C, alpha=alpha, tau=tau, Y=Y)
+
+
+def expected_bound(n_total, sweeps):
+    """Lower bound after `sweeps` sweeps as measured on ONE GPU (profiles/bench_expected.json), so that every
+    multi-GPU line can show that N ranks computed what one rank computes."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "bench_expected.json")))
+        return float(d["pca"]["%d:%d" % (n_total, sweeps)])
+    except Exception:
+        return None
 
 
 def run_gpu(args):
     from bayespy_b200 import _bpk, parallel
     world, rank = parallel.init_from_env()
     be = _bpk.get()
+    cpus = parallel.bind_to_gpu_numa()          # host threads and pinned buffers next to this rank's GPU
     if world != args.gpus and rank == 0:
         sys.stderr.write("warning: --gpus %d but WORLD_SIZE=%d\n" % (args.gpus, world))
     n_total = args.n
@@ -254,24 +307,29 @@ def run_gpu(args):
     L_last = float(Q.L[Q.iter - 1])
 
     # ---- e2e: host buffers in, host scalars out, every step (public API: observe + update) ----
-    e2e_steps = max(2, min(steps, args.e2e_steps))
+    e2e_steps = max(10, args.e2e_steps)
     nbytes = y.nbytes
     hptr = be.host_alloc(nbytes)
     import ctypes
     pinned = np.ctypeslib.as_array((ctypes.c_double * y.size).from_address(hptr)).reshape(y.shape)
     pinned[...] = y
     Y = nodes["Y"]
-    Y.observe(pinned)
-    Q.update(repeat=1, verbose=False)
-    parallel.barrier()
-    t0 = time.perf_counter()
+    for _ in range(2):                         # warm-up: pinned pages touched, copy engine and pool warm
+        Y.observe(pinned)
+        Q.update(repeat=1, verbose=False)
+    e2e_t = []
     for _ in range(e2e_steps):
+        parallel.barrier()
+        t0 = time.perf_counter()
         Y.observe(pinned)                      # H2D of this step's inputs from pinned host memory
         Q.update(repeat=1, verbose=False)      # sweep + D2H of the per-node bound terms
         _ = float(Q.L[Q.iter - 1])
-    be.sync()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    e2e_s = float(np.max(parallel.allgather_scalar(e2e_s)))
+        be.sync()
+        e2e_t.append(time.perf_counter() - t0)
+    # per step the slowest rank counts; the reported figure is the median step
+    e2e_mat = np.array([parallel.allgather_scalar(t) for t in e2e_t])          # (steps, world)
+    e2e_s = float(np.median(e2e_mat.max(axis=1)))
+    e2e_best = float(e2e_mat.max(axis=1).min())
     be.host_free(hptr)
 
     if rank != 0:
@@ -302,8 +360,11 @@ def run_gpu(args):
                    "host_wall_ms_per_step": 1e3 * wall / steps},
         "clocks": clocks,
         "e2e": {"value": 1.0 / e2e_s, "unit": "it/s", "h2d_bytes_per_step": int(nbytes),
-                "d2h_bytes_per_step": 8 * len(Q.model), "steps": e2e_steps,
-                "note": "per step: Y.observe(pinned host array) + Q.update() + read of L"},
+                "d2h_bytes_per_step": 8 * len(Q.model), "steps": e2e_steps, "statistic": "median over steps of the max over ranks",
+                "best_step_its": 1.0 / e2e_best, "h2d_gbs_per_gpu": nbytes / e2e_s / 1e9,
+                "numa_bound_cpus": (len(cpus) if cpus else None),
+                "note": "per step: Y.observe(pinned host array) + Q.update() + read of L; the step is the H2D copy of "
+                        "Y (PCIe-bound: %.2f GB per GPU per step) followed by a %.1f ms sweep" % (nbytes / 1e9, ms_max / steps)},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "pca_xsweep_ws_kernel<...,FUSED> (persistent launch of sweeps_per_launch VB sweeps; per sweep: data pass + grid reduction + node updates + bound)", "kernel_ms": kern_avg,
@@ -312,18 +373,28 @@ def run_gpu(args):
                      "kernel_share_of_step": kern_avg / (ms_max / steps),
                      "algorithmic_bytes_per_col": BYTES_PER_COL, "peak_source": peak_src,
                      "sweeps_per_launch": sweeps_per_launch,
-                     "fp64_tflops": FLOPS_PER_COL * n_local_max / (kern_avg * 1e-3) / 1e12},
+                     "fp64_tflops_algorithmic": FLOPS_PER_COL * n_local_max / (kern_avg * 1e-3) / 1e12,
+                     "fp64_tflops_executed": EXEC_FLOPS_PER_COL * n_local_max / (kern_avg * 1e-3) / 1e12,
+                     "fp64_note": "algorithmic = %d flop/col (SURVEY 8d); executed = 8 DMMA.8x8x4 x 512 flop per column "
+                                  "(S_xx is derived in the tail from S_yx and s_x); measured DMMA peak 36.9 TFLOP/s "
+                                  "(profiles/r01_ubench_*)" % FLOPS_PER_COL},
     }
+    exp = expected_bound(n_total, warmup + steps)
+    if exp is not None:
+        line["config"]["lower_bound_expected_1gpu"] = exp
+        line["config"]["lower_bound_rel_err_vs_1gpu"] = abs(L_last - exp) / abs(exp)
     if world == 1 and not args.no_cpu_baseline:
-        n_sample = 50_000
-        dt = cpu_sweeps(n_sample, 2, 1)
+        n_sample = 100_000
+        dt, kind = reference_sweep_seconds(n_sample, 2, 1)
         scale = n_total / n_sample
         cores = blas_threads()
         line["cpu_baseline"] = {
-            "value": 1.0 / (dt * scale), "unit": "it/s", "cores": cores, "kind": "port",
-            "sample": "oracle/pca_ref.py (NumPy/SciPy port of the reference sweep) on %d of %d columns, 2 timed "
-                      "sweeps after 1 warm-up, extrapolated linearly in N; BLAS threads=%d of %d host cores"
-                      % (n_sample, n_total, cores, os.cpu_count() or 1)}
+            "value": 1.0 / (dt * scale), "unit": "it/s", "cores": cores, "kind": kind,
+            "sample": "%s on the first %d of %d columns of the same data, 2 timed Q.update() sweeps after 1 warm-up "
+                      "(%.1f s per sweep measured), extrapolated linearly in N (x%.0f); BLAS threads=%d of %d host cores, "
+                      "the einsum / per-plate loops of the reference are single-threaded"
+                      % ("unmodified reference package (oracle/_ref)" if kind == "reference" else "oracle port",
+                         n_sample, n_total, dt, scale, cores, os.cpu_count() or 1)}
     print(json.dumps(line), flush=True)
 
 
@@ -334,7 +405,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=N_TOTAL, help="total number of columns (default: the metric's 1e7)")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--ref-budget-s", type=float, default=150.0,
+                    help="--impl reference: wall-clock budget of the whole run; sets the column sample per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--clock-interval-ms", type=int, default=200,
                     help="nvidia-smi sampling period during the timed region (B200_PROFILING.md recipe: 200); 0 = off")

@@ -456,8 +456,37 @@ def lssm_plated_dynamics(name="lssm_plated_dynamics", M=4, N=15, D=2, P=3, iters
     save(name, **out)
 
 
+def pca_bench_prefix(name="pca_bench_100k", N=100_000, iters=5):
+    """The benchmark's own model and data (bench.py: synth_shard / init_C, M=64, K=16) on the first N columns:
+    the reference trajectory of the data the GPU numbers are measured on.  N = 1e5 makes the multi-tile hand-off
+    of the fused sweep kernel live (ntiles >= 2 x 148).  y is regenerated from the seed by the test."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    import bench
+    M, K = bench.M_DIM, bench.K_DIM
+    y = bench.synth_shard(M, 0, N, 1)
+    X = GaussianARD(0, 1, plates=(1, N), shape=(K,))
+    alpha = Gamma(1e-5, 1e-5, plates=(K,))
+    C = GaussianARD(0, alpha, plates=(M, 1), shape=(K,))
+    F = SumMultiply('d,d->', X, C)
+    tau = Gamma(1e-5, 1e-5)
+    Y = GaussianARD(F, tau)
+    Y.observe(y)
+    C.initialize_from_value(bench.init_C(M, K))
+    Q = VB(Y, X, C, alpha, tau)
+    Q.update(repeat=iters, verbose=False, tol=0)
+    sel = np.r_[0:64, N // 2:N // 2 + 64, N - 64:N]
+    out = dict(N=N, L=Q.L[:iters], X_sel=sel, X_u0_sel=np.asarray(X.u[0])[0, sel, :],
+               X_cov=np.asarray(X.u[1])[0, 0] - np.outer(np.asarray(X.u[0])[0, 0], np.asarray(X.u[0])[0, 0]),
+               y_checksum=np.array([y.sum(), (y * y).sum(), y[:, -1].sum()]))
+    for k, node in (("Y", Y), ("X", X), ("C", C), ("alpha", alpha), ("tau", tau)):
+        out["l_" + k] = Q.l[node][:iters]
+    for nm, node in (("C", C), ("alpha", alpha), ("tau", tau)):
+        node_state(nm, node, out)
+    save(name, **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["quickstart", "pca", "linalg", "summul", "dist", "gmm", "gmc", "rot", "dot", "mixard", "gmcplates", "gmcvarying"]
+    which = sys.argv[1:] or ["quickstart", "pca", "linalg", "summul", "dist", "gmm", "gmc", "rot", "dot", "mixard", "gmcplates", "gmcvarying", "pcabench"]
     if "quickstart" in which:
         quickstart()
     if "pca" in which:
@@ -481,6 +510,8 @@ if __name__ == "__main__":
         pca_rotated()
     if "gmcplates" in which:
         lssm_plated()
+    if "pcabench" in which:
+        pca_bench_prefix()
     if "gmcvarying" in which:
         lssm_varying()
         lssm_plated_dynamics()

@@ -190,3 +190,22 @@ def test_a_child_added_after_vb_is_not_dropped(backend):
     Q0, n0 = _pca(y, 4, resident=True)
     Q0.update(repeat=4, verbose=False, tol=0)
     assert np.max(np.abs(np.asarray(n0["X"].u[0]) - res[0])) > 1e-3
+
+
+def test_callback_keeps_the_node_updates_on_the_fused_path(backend):
+    """With a callback (here: the rotation of pca.rst:86-112) the host is needed between the node updates and the
+    bound (vmp.py:702-713): every sweep is still ONE fused launch (sweep_resident), and the trajectory equals the
+    per-node tier's for as long as rounding differences stay below the optimiser's sensitivity."""
+    from bayespy_b200.inference.vmp.transformations import RotateGaussianARD, RotationOptimizer
+    y = _data(20, 100, 6, seed=11)
+    res = []
+    for resident in (True, False):
+        Q, n = _pca(y, 6, resident=resident)
+        R = RotationOptimizer(RotateGaussianARD(n["X"]), RotateGaussianARD(n["C"], n["alpha"]), 6)
+        Q.set_callback(R.rotate)
+        before = Q.plans[0].fused_calls
+        Q.update(repeat=5, verbose=False, tol=0)
+        res.append((Q.L[:5].copy(), np.asarray(n["C"].u[0]).copy(), Q.plans[0].fused_calls - before))
+    assert res[0][2] >= 5
+    np.testing.assert_allclose(res[0][0], res[1][0], rtol=1e-7)
+    np.testing.assert_allclose(res[0][1], res[1][1], rtol=1e-5, atol=1e-7)
