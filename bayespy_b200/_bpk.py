@@ -83,6 +83,8 @@ PROTOTYPES = {
     "bpk_pca_stats": (C.c_int, [_dp, C.c_int64, C.c_int64, C.c_int, _dp, _dp]),
     "bpk_pca_xsweep_masked": (C.c_int, [_dp, _vp, C.c_int64, C.c_int64, C.c_int, _dp, _dp, C.c_double, _dp, _dp,
                                         _dp, _dp, _dp, _dp, C.c_int]),
+    "bpk_pca_xsweep_masked_fused": (C.c_int, [_dp, _vp, C.c_int64, C.c_int64, C.c_int, _dp, _dp, C.c_double, _dp, _dp,
+                                              _dp, _dp, _dp, C.c_int]),
     "bpk_sumsq": (C.c_int, [_dp, _vp, C.c_int64, _dp]),
     "bpk_gmm_sweep": (C.c_int, [_dp, C.c_int64, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
     "bpk_gmm_stats": (C.c_int, [_dp, C.c_int64, C.c_int, C.c_int, _dp, _dp]),
@@ -314,6 +316,10 @@ class CudaBackend:
     def pca_xsweep_masked(self, Y, mask, M, N, K, W, WW, tau, alpha, amu, X, COV, g, stats, check=True):
         self._chk(self.lib.bpk_pca_xsweep_masked(Y, mask, M, N, K, W, WW, float(tau), alpha, amu, X, COV, g, stats,
                                                  int(check)))
+
+    def pca_xsweep_masked_fused(self, Y, mask, M, N, K, W, WW, tau, alpha, amu, X, g, stats, check=True):
+        self._chk(self.lib.bpk_pca_xsweep_masked_fused(Y, mask, M, N, K, W, WW, float(tau), alpha, amu, X, g, stats,
+                                                       int(check)))
 
     def sumsq(self, Y, mask, count, out2):
         self._chk(self.lib.bpk_sumsq(Y, mask, count, out2))

@@ -384,6 +384,212 @@ __global__ void __launch_bounds__(G1_WARPS * 32, 1) gmm_sweep_dmma_kernel(GmmArg
     }
 }
 
+// =====================================================================================
+// v2: the same two contractions, but the CTA-wide barriers between the E and M phases are gone.  The 8 warps
+// form 4 PAIRS; a pair owns a tile of 32 rows: each warp runs the E phase of 16 of them (192 DMMA), the pair
+// meets at its own named barrier (64 threads), then each warp contracts ALL 32 rows into its half of the
+// statistics (all 64 components x 24 features: 48 accumulators, 192 DMMA).  The four pairs drift apart, so one
+// pair's exp / softmax / stores overlap another pair's DMMA streams instead of everybody idling at a
+// __syncthreads (v1: 56 % of the fp64 pipe).  255 registers per thread (8 warps per SM fit the register file).
+// =====================================================================================
+#define G2_PAIRS 4
+#define G2_ROWS 32
+__device__ __forceinline__ void g2_pair_sync(int p) {
+    asm volatile("bar.sync %0, 64;\n" ::"r"(p + 1) : "memory");
+}
+
+__global__ void __launch_bounds__(G2_PAIRS * 64, 1) gmm_sweep_dmma2_kernel(GmmArgs a) {
+    extern __shared__ __align__(16) double sm[];
+    double *sT = sm;                                                  // [64][52]  Theta
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5, gr = lane >> 2, tg = lane & 3;
+    const int pr = w >> 1, hf = w & 1;
+    double *sZ = sT + G1_KP * G1_LDZ + (size_t)pr * (G2_ROWS * G1_LDZ + G2_ROWS * G1_LDP);   // [32][52] this pair's features
+    double *sP = sZ + G2_ROWS * G1_LDZ;                                                       // [32][68] responsibilities
+    __shared__ double red[2 * G2_PAIRS];
+    const int D = a.D, K = a.K;
+
+    for (int e = t; e < G1_KP * G1_FP; e += blockDim.x) {
+        const int k = e / G1_FP, f = e - k * G1_FP;
+        double v = 0.0;
+        if (k >= K) v = (f == 0) ? -1e300 : 0.0;        // padded components never win the softmax
+        else if (f == 0) v = a.c[k] + a.logpi[k];
+        else if (f <= G1_DP) v = (f - 1 < D) ? a.h[k * D + f - 1] : 0.0;
+        else if (f < G1_NF) {
+            int i, j;
+            g1_pair(f, i, j);
+            if (i < D && j < D)
+                v = (i == j) ? -0.5 * a.Lam[(k * D + i) * D + i]
+                             : -0.5 * (a.Lam[(k * D + i) * D + j] + a.Lam[(k * D + j) * D + i]);
+        }
+        sT[k * G1_LDZ + f] = v;
+    }
+    // this warp's half of the statistics: all 8 component blocks x feature blocks 3*hf .. 3*hf+2
+    const int fb0 = 3 * hf;
+    double acc[8][3][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    double lse_acc = 0.0;
+    __syncthreads();
+
+    const int64_t ntiles = (a.N + G2_ROWS - 1) / G2_ROWS;
+    const int64_t tstride = (int64_t)gridDim.x * G2_PAIRS;
+    const int r0 = hf * 16;                              // this warp's rows inside the pair tile
+    double ynext[G1_DP];
+    {
+        const int64_t n = ((int64_t)blockIdx.x * G2_PAIRS + pr) * G2_ROWS + r0 + (lane >> 1);
+#pragma unroll
+        for (int d = 0; d < G1_DP; ++d) ynext[d] = (n < a.N && d < D) ? a.Y[n * D + d] : 0.0;
+    }
+    for (int64_t tile = (int64_t)blockIdx.x * G2_PAIRS + pr; tile < ntiles; tile += tstride) {
+        const int64_t row0 = tile * G2_ROWS;
+        // ---- E phase: this warp's 16 rows; two lanes per row build its 48 monomial features from registers ----
+        {
+            const int r = r0 + (lane >> 1);
+            const int64_t n = row0 + r;
+            const bool live = n < a.N;
+            double y[G1_DP];
+#pragma unroll
+            for (int d = 0; d < G1_DP; ++d) y[d] = (live && d < D) ? ynext[d] : 0.0;
+            double *zr = sZ + r * G1_LDZ;
+            if ((lane & 1) == 0) {
+                zr[0] = live ? 1.0 : 0.0;
+#pragma unroll
+                for (int d = 0; d < G1_DP; ++d) zr[1 + d] = y[d];
+            }
+            {
+                int f = 9;
+#pragma unroll
+                for (int i = 0; i < G1_DP; ++i)
+#pragma unroll
+                    for (int j = i; j < G1_DP; ++j, ++f)
+                        if ((f < 24) == ((lane & 1) == 0)) zr[f] = y[i] * y[j];
+                if (lane & 1) zr[45] = zr[46] = zr[47] = 0.0;
+            }
+            const int64_t nn = n + tstride * G2_ROWS;       // this lane's row of the pair's next tile
+#pragma unroll
+            for (int d = 0; d < G1_DP; ++d) ynext[d] = (nn < a.N && d < D) ? a.Y[nn * D + d] : 0.0;
+        }
+        __syncwarp();
+        double L[2][8][2];
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) L[g][nb][0] = L[g][nb][1] = 0.0;
+#pragma unroll 2
+        for (int s = 0; s < G1_FP / 4; ++s) {
+            const double z0 = sZ[(r0 + gr) * G1_LDZ + 4 * s + tg];
+            const double z1 = sZ[(r0 + 8 + gr) * G1_LDZ + 4 * s + tg];
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) {
+                const double th = sT[(nb * 8 + gr) * G1_LDZ + 4 * s + tg];
+                g1_dmma(L[0][nb][0], L[0][nb][1], z0, th);
+                g1_dmma(L[1][nb][0], L[1][nb][1], z1, th);
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            const int r = r0 + g * 8 + gr;
+            const int64_t n = row0 + r;
+            const bool live = n < a.N;
+            double m = -INFINITY;
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) m = fmax(m, fmax(L[g][nb][0], L[g][nb][1]));
+            m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 1));
+            m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 2));
+            if (!isfinite(m)) m = 0.0;
+            double ssum = 0.0;
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) {
+                L[g][nb][0] = exp(L[g][nb][0] - m);
+                L[g][nb][1] = exp(L[g][nb][1] - m);
+                ssum += L[g][nb][0] + L[g][nb][1];
+            }
+            ssum += __shfl_xor_sync(0xffffffffu, ssum, 1);
+            ssum += __shfl_xor_sync(0xffffffffu, ssum, 2);
+            const double lse = log(ssum) + m;
+            const double inv = 1.0 / ssum;
+            double s2 = 0.0;
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) {
+                L[g][nb][0] *= inv; L[g][nb][1] *= inv;
+                s2 += L[g][nb][0] + L[g][nb][1];
+            }
+            s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+            const double inv2 = live ? 1.0 / s2 : 0.0;       // misc.py:1398-1401 second renormalisation
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) {
+                const double p0 = L[g][nb][0] * inv2, p1 = L[g][nb][1] * inv2;
+                const int k = nb * 8 + 2 * tg;
+                sP[r * G1_LDP + k] = p0;
+                sP[r * G1_LDP + k + 1] = p1;
+                if (live && a.P) {
+                    double *dst = a.P + n * K + k;
+                    if (K == G1_KP) *reinterpret_cast<double2 *>(dst) = make_double2(p0, p1);
+                    else { if (k < K) dst[0] = p0; if (k + 1 < K) dst[1] = p1; }
+                }
+            }
+            if (live && tg == 0) {
+                lse_acc += lse;
+                if (a.g) a.g[n] = -lse;
+            }
+        }
+        g2_pair_sync(pr);
+        // ---- M phase: S[all 64 components x 24 features] += P^T Z over the pair's 32 rows ----
+#pragma unroll 2
+        for (int q = 0; q < G2_ROWS / 4; ++q) {
+            const int r = 4 * q + tg;
+            double zb[3];
+#pragma unroll
+            for (int fb = 0; fb < 3; ++fb) zb[fb] = sZ[r * G1_LDZ + (fb0 + fb) * 8 + gr];
+#pragma unroll
+            for (int mb = 0; mb < 8; ++mb) {
+                const double pa = sP[r * G1_LDP + mb * 8 + gr];
+#pragma unroll
+                for (int fb = 0; fb < 3; ++fb) g1_dmma(acc[mb][fb][0], acc[mb][fb][1], pa, zb[fb]);
+            }
+        }
+        g2_pair_sync(pr);          // the pair's buffers are free for its next tile
+    }
+    // per-CTA partial in the v0 (k, f) layout with F = 1 + D + D*D, so that gmm_final_kernel serves both
+    const int F = a.nfeat;
+    double *pout = a.partial + (size_t)blockIdx.x * (K * F + 1);
+    __syncthreads();
+    double *sS = sT + G1_KP * G1_LDZ;                   // [4 pairs][64][48] staging over the pair buffers (4 x 30.7 KB >= 96 KB)
+#pragma unroll
+    for (int mb = 0; mb < 8; ++mb)
+#pragma unroll
+        for (int fb = 0; fb < 3; ++fb)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                sS[(size_t)pr * G1_KP * G1_FP + (mb * 8 + gr) * G1_FP + (fb0 + fb) * 8 + 2 * tg + j] = acc[mb][fb][j];
+    __syncthreads();
+    for (int e = t; e < K * F; e += blockDim.x) {
+        const int k = e / F, f = e - k * F;
+        int sf;
+        if (f <= D) sf = f;                               // 1, y_i  (f-1 < D <= 8: same slot)
+        else {
+            int i = (f - 1 - D) / D, j = (f - 1 - D) % D;
+            if (i > j) { int tmp = i; i = j; j = tmp; }
+            sf = 9 + i * G1_DP - (i * (i - 1)) / 2 + (j - i);
+        }
+        double v = 0.0;
+#pragma unroll
+        for (int pp = 0; pp < G2_PAIRS; ++pp) v += sS[(size_t)pp * G1_KP * G1_FP + k * G1_FP + sf];
+        pout[e] = v;
+    }
+    lse_acc = warp_sum(lse_acc);
+    if (lane == 0) red[w] = lse_acc;
+    __syncthreads();
+    if (t == 0) {
+        double sum = 0.0;
+        for (int ww = 0; ww < 2 * G2_PAIRS; ++ww) sum += red[ww];
+        pout[K * F] = sum;
+    }
+}
+
 // partial (k, f) layout -> caller's [sum p (K) | sum p y (K*D) | sum p yy^T (K*D*D) | lse]
 __global__ void gmm_final_kernel(const double *__restrict__ partial, int nblocks, int K, int D,
                                  double *__restrict__ stats) {
@@ -444,8 +650,15 @@ static int gmm_run(const double *Y, int64_t N, int D, int K,
         if (nt1 < grid1) grid1 = (int)nt1;
         a.partial = bpk_scratch((size_t)grid1 * (K * a.nfeat + 1) * sizeof(double));
         if (!a.partial) return bpk_set_error(BPK_ECUDA, "gmm: scratch allocation failed");
-        BPK_CUDA(cudaFuncSetAttribute(gmm_sweep_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-        BPK_LAUNCH(gmm_sweep_dmma_kernel, grid1, G1_WARPS * 32, smem1, a);
+        if (getenv("BPK_GMM_V1")) {
+            BPK_CUDA(cudaFuncSetAttribute(gmm_sweep_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+            BPK_LAUNCH(gmm_sweep_dmma_kernel, grid1, G1_WARPS * 32, smem1, a);
+        } else {
+            // v2: warp pairs on 32-row tiles (no CTA-wide barrier in the main loop)
+            size_t smem2 = ((size_t)G1_KP * G1_LDZ + (size_t)G2_PAIRS * (G2_ROWS * G1_LDZ + G2_ROWS * G1_LDP)) * sizeof(double);
+            BPK_CUDA(cudaFuncSetAttribute(gmm_sweep_dmma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            BPK_LAUNCH(gmm_sweep_dmma2_kernel, grid1, G2_PAIRS * 64, smem2, a);
+        }
         int total1 = K * a.nfeat + 1;
         BPK_LAUNCH(gmm_final_kernel, (total1 + 127) / 128, 128, 0, a.partial, grid1, K, D, stats);
         return BPK_OK;

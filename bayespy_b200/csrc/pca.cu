@@ -407,7 +407,13 @@ pca_xsweep_ws_kernel(const __grid_constant__ CUtensorMap tmapY, int64_t M, int64
             tma_load_2d(Ysm + (size_t)slot * STG + lane * WS_BOX, &tmapY, (int)(n0 + lane * WS_BOXC), 0, &full[slot]);
     };
 
+    // BPK_VB_DEBUG: the last CTA of the grid (a full data pass plus one of CTA 0's tiles) stamps the phases of the
+    // second-to-last sweep of the launch into dbg[48..57] (tools/vb_tail_timing.py)
+    const bool probe = FUSED && vb.dbg != nullptr && blockIdx.x == gridDim.x - 1;
     for (int it = 0; it < niter; ++it, tbase += ntl) {
+    const bool pr = probe && (it == niter - 2 || niter == 1);
+    if (probe && it == niter - 1 && niter > 1) vb_stamp(vb.dbg, 57);
+    if (pr) vb_stamp(vb.dbg, 48);
     if (it > 0) {
         if (*(volatile const int *)stop) break;                       // converged inside this launch (uniform)
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");    // ring was scratch for the tail: order before TMA
@@ -428,6 +434,7 @@ pca_xsweep_ws_kernel(const __grid_constant__ CUtensorMap tmapY, int64_t M, int64
                 if (8 + gr < K) bk[1] = __ldcg(bvec + 8 + gr);
             }
         }
+        if (pr && w == 0) vb_stamp_lane(vb.dbg, 49);
         if (w == 0)
             for (int64_t j = 0; j < DIST && j < ntl; ++j) issue(j);
         for (int64_t i = 0; i < ntl; ++i) {
@@ -439,6 +446,7 @@ pca_xsweep_ws_kernel(const __grid_constant__ CUtensorMap tmapY, int64_t M, int64
             double *Xs = Xsm + ((size_t)(p * 2 + b) * NT) * PCA_LDX;
             if (COMPUTE_X) {
                 mbar_wait(&full[slot], (uint32_t)((ig / STAGES) & 1));
+                if (pr && w == 0 && i == 0) vb_stamp_lane(vb.dbg, 50);
                 const double *Ys = Ysm + (size_t)slot * STG;
                 // two partial sums over the m blocks per accumulator: 4*CB independent DMMA chains
                 double acc[2][2][CB][2];
@@ -487,6 +495,7 @@ pca_xsweep_ws_kernel(const __grid_constant__ CUtensorMap tmapY, int64_t M, int64
             __syncwarp();
             if (lane == 0) mbar_arrive(&xfull[p * 2 + b]);
         }
+        if (pr && w == 0) vb_stamp_lane(vb.dbg, 51);
     } else {
         const int rr = 2 * (gr & 3) + (gr >> 2);      // S_yx row within an 8-row block held by this lane group
         double syx[8][2][2];
@@ -529,6 +538,7 @@ pca_xsweep_ws_kernel(const __grid_constant__ CUtensorMap tmapY, int64_t M, int64
             __syncwarp();
             if (lane == 0) { mbar_arrive(&xfree[p * 2 + b]); mbar_arrive(&empty[slot]); }
         }
+        if (pr && w == WS_PAIRS) vb_stamp_lane(vb.dbg, 52);
         // every issued tile has been consumed by every warp once all warps pass the barrier below
         __syncthreads();
         double *mine = smem + (size_t)p * PCA_NSTAT;
@@ -560,11 +570,13 @@ pca_xsweep_ws_kernel(const __grid_constant__ CUtensorMap tmapY, int64_t M, int64
     }
     if (FUSED) {
         if (blockIdx.x == 0) vb_stamp(vb.dbg, 1);
+        if (pr) vb_stamp(vb.dbg, 53);
         const int nops_it = (it == niter - 1) ? vb.nops_last : vb.nops;
         grid_arrive(gbar, epoch);
         if (blockIdx.x == 0 && skip > 0 && (it == 0 || vb.dry_every)) pca_vb_ops(vb, smem, vb_sm_doubles, true, nops_it);   // warm the instruction cache
         grid_wait(gbar, epoch, vb.ctrl + 2);
         if (blockIdx.x == 0) vb_stamp(vb.dbg, 2);
+        if (pr) vb_stamp(vb.dbg, 54);
         // distributed, fixed-order reduction over the CTAs: CTA c owns elements [c*per, (c+1)*per)
         const int per = (PCA_NSTAT + gridDim.x - 1) / gridDim.x;
         const int e0 = blockIdx.x * per;
@@ -604,6 +616,7 @@ pca_xsweep_ws_kernel(const __grid_constant__ CUtensorMap tmapY, int64_t M, int64
                 }
                 if (lane == 0) ll_store(ll_total_slot(vb.xown, par, e), s, seq);
             }
+            if (pr) vb_stamp(vb.dbg, 55);
             if (blockIdx.x == 0) {
                 vb_stamp(vb.dbg, 3);
                 vb_stamp(vb.dbg, 4);
@@ -630,6 +643,7 @@ pca_xsweep_ws_kernel(const __grid_constant__ CUtensorMap tmapY, int64_t M, int64
             }
         }
         if (it + 1 < niter) grid_barrier(gbar, epoch, vb.ctrl + 2);      // the next sweep's A, b (and the stop word) are visible to every CTA
+        if (pr) vb_stamp(vb.dbg, 56);
     }
     }   // sweeps of this launch
 }

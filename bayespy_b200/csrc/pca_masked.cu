@@ -1,0 +1,339 @@
+// pca_masked.cu — the factor-model sweep with MISSING VALUES (per-column precision), fused: nothing of size
+// (N, K, K) is ever stored.
+//
+//   y[m,n] ~ N(w_m . x_n, 1/tau) observed only where mask[m,n];   q(x_n) = N(x_n | Cov_n phi_n, Cov_n)
+//   Lam_n = diag(a_x) + tau sum_m mask[m,n] <w_m w_m^T>,   phi_n = a_x mu_x + tau sum_m mask[m,n] y[m,n] <w_m>
+//
+// Reference path being replaced, per VB sweep (SURVEY.md 3.3, 8d variant (ii)): dot.py:581 builds the (N,K) and
+// (N,K,K) messages, gaussian.py:672-706 calls linalg.chol / chol_solve / chol_inv / chol_logdet, each a Python loop
+// of SciPy calls over the N columns (linalg.py:50-59, 111-146, 185-195), stores <x x^T> as (N,K,K), and the parents'
+// messages re-contract it with the mask (dot.py:581, node.py:650).  150-180 us per column on a CPU core.
+//
+// Here, per chunk of columns (a fixed-size scratch of 232 rows x chunk, reused by every chunk — it never scales
+// with N and lives in the 126 MB L2), three kernels:
+//   build    Lam_n (packed upper triangle, 136 rows) and phi_n (16 rows) for every column of the chunk as ONE GEMM on
+//            the fp64 tensor pipe with the bit-packed mask as an operand:  [136+16 rows] x [64 m] x [columns]
+//   inverse  one THREAD per column: block Cholesky on 8 x 8 register tiles (spd16.cuh) -> x_n, Cov_n + x_n x_n^T,
+//            phi_n . x_n, log det Lam_n, in place in the scratch rows
+//   stats    the plate sums every other node needs, again as one masked GEMM:
+//            S_xx[m] = sum_n mask[m,n] <x_n x_n^T>,  S_yx[m] = sum_n mask[m,n] y[m,n] x_n,  sum_n <x x^T>, sum_n x_n,
+//            sum_n phi.x, sum_n log det;  and the coalesced store of X.
+// 38 + 38 DMMA.8x8x4 per column on the tensor pipe (the symmetric half only: 136 of 256 entries) + ~3 kflop per
+// column of register-resident DFMA; algorithmic HBM traffic M*8 (y) + M (byte mask) + K*8 (x out) = 704 B/col.
+#include "common.cuh"
+#include "spd16.cuh"
+#include <stdlib.h>
+
+#define PM_MP 64
+#define PM_KP 16
+#define PM_NT 19                         // row tiles of the scratch matrix: 17 of Lam / <xx^T>, 2 of phi / x
+#define PM_TILE 128                      // columns per CTA tile
+#define PM_WARPS PM_NT
+#define PM_THREADS (PM_WARPS * 32)
+#define PM_NPART (PM_MP * (SPD16_NPACK + PM_KP) + SPD16_NPACK + PM_KP + 2)     // per-CTA partial statistics
+
+__device__ __forceinline__ void pm_dmma(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// (i, j) of packed row p (i <= j)
+__device__ __forceinline__ void pm_unpack(int p, int &i, int &j) {
+    int ii = 0, r = p;
+    while (r >= PM_KP - ii) { r -= PM_KP - ii; ++ii; }
+    i = ii; j = ii + r;
+}
+
+// 64-bit observation words of the tile's columns: bit m of bits[c] = mask[m][n0 + c]
+__device__ __forceinline__ void pm_pack_mask(const uint8_t *__restrict__ mask, int64_t M, int64_t N, int64_t n0,
+                                             unsigned long long *bits) {
+    for (int c = threadIdx.x; c < PM_TILE; c += blockDim.x) bits[c] = 0ull;
+    __syncthreads();
+    // 4 threads per column, 16 rows each; byte loads are coalesced along the column axis
+    for (int e = threadIdx.x; e < PM_TILE * 4; e += blockDim.x) {
+        const int c = e % PM_TILE, q = e / PM_TILE;
+        const int64_t n = n0 + c;
+        unsigned long long wbits = 0ull;
+        if (n < N) {
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const int64_t m = q * 16 + r;
+                if (m < M && mask[m * N + n]) wbits |= 1ull << (q * 16 + r);
+            }
+        }
+        if (wbits) atomicOr(&bits[c], wbits);
+    }
+    __syncthreads();
+}
+
+struct PmArgs {
+    const double *Y;
+    const uint8_t *mask;
+    int64_t M, N;
+    int K;
+    const double *W, *WW, *alpha, *amu;
+    double tau;
+    double *S;                 // scratch [SPD16_ROWS][chp]
+    int64_t chp;               // scratch pitch (columns of a chunk, multiple of PM_TILE)
+    int64_t c0, nc;            // this chunk: columns [c0, c0 + nc)
+    double *X, *g;
+    double *partial;           // [grid][PM_NPART] running per-CTA statistics
+    int *flag;
+};
+
+// ---- build: rows 0..151 of the scratch for every column of the chunk ------------------------------------------
+__global__ void __launch_bounds__(PM_THREADS, 1) pmask_build_kernel(PmArgs a) {
+    __shared__ unsigned long long bits[PM_TILE];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, gr = lane >> 2, tg = lane & 3;
+    const int M = (int)a.M, K = a.K;
+    // A fragments of this warp's row tile (constant over the sweep): T[p][m] = tau <ww^T>[m][ij(p)]  or  tau <w>[m][k]
+    double af[16];
+    const int p = w * 8 + gr;                          // scratch row of this lane's accumulator row
+    double addv = 0.0;                                 // prior term of that row
+    {
+        int i = 0, j = 0;
+        const bool is_phi = w >= 17;
+        if (!is_phi) pm_unpack(p, i, j);
+        const int k = p - SPD16_NPACK;
+#pragma unroll
+        for (int ks = 0; ks < 16; ++ks) {
+            const int m = ks * 4 + tg;
+            double v = 0.0;
+            if (m < M) {
+                if (is_phi) v = (k < K) ? a.tau * a.W[(int64_t)m * K + k] : 0.0;
+                else if (i < K && j < K) v = a.tau * a.WW[((int64_t)m * K + i) * K + j];
+            }
+            af[ks] = v;
+        }
+        if (is_phi) addv = (k < K && a.amu) ? a.amu[k] : 0.0;
+        else if (i == j) addv = (i < K) ? a.alpha[i] : 1.0;        // padded dimensions: identity precision
+    }
+    const int64_t ntiles = (a.nc + PM_TILE - 1) / PM_TILE;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t cl0 = tile * PM_TILE;            // first column of the tile inside the chunk
+        const int64_t n0 = a.c0 + cl0;
+        __syncthreads();
+        pm_pack_mask(a.mask, a.M, a.N, n0, bits);
+        // 16 column tiles of 8, four at a time (4 independent DMMA chains)
+#pragma unroll 1
+        for (int nq = 0; nq < 4; ++nq) {
+            double acc[4][2];
+            unsigned long long wd[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                acc[q][0] = acc[q][1] = 0.0;
+                wd[q] = bits[(nq * 4 + q) * 8 + gr];
+            }
+            if (w < 17) {
+#pragma unroll
+                for (int ks = 0; ks < 16; ++ks)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const double b = ((wd[q] >> (ks * 4 + tg)) & 1ull) ? 1.0 : 0.0;
+                        pm_dmma(acc[q][0], acc[q][1], af[ks], b);
+                    }
+            } else {
+#pragma unroll
+                for (int ks = 0; ks < 16; ++ks)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int m = ks * 4 + tg;
+                        const int64_t n = n0 + (nq * 4 + q) * 8 + gr;
+                        const bool on = (wd[q] >> m) & 1ull;
+                        const double b = on ? __ldg(a.Y + (int64_t)m * a.N + n) : 0.0;
+                        pm_dmma(acc[q][0], acc[q][1], af[ks], b);
+                    }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int64_t cl = cl0 + (nq * 4 + q) * 8 + 2 * tg;
+                double2 v = make_double2(acc[q][0] + addv, acc[q][1] + addv);
+                *reinterpret_cast<double2 *>(a.S + (int64_t)p * a.chp + cl) = v;
+            }
+        }
+    }
+}
+
+// ---- inverse: one thread per column -----------------------------------------------------------------------------
+struct PmColAcc {
+    double *base;              // &S[0][col]
+    int64_t pitch;
+    __device__ __forceinline__ double ld(int row) const { return base[(int64_t)row * pitch]; }
+    __device__ __forceinline__ void st(int row, double v) { base[(int64_t)row * pitch] = v; }
+};
+
+__global__ void __launch_bounds__(128) pmask_inverse_kernel(PmArgs a) {
+    const int64_t cl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (cl >= a.nc) return;
+    PmColAcc acc{a.S + cl, a.chp};
+    double q, ld;
+    const bool ok = spd16_solve_inverse(acc, q, ld);
+    if (!ok) atomicOr(a.flag, BPK_FLAG_NOTSPD);
+    // per-column scalars for the bound, parked in two scratch rows that are free again
+    acc.st(SPD16_G, q);
+    acc.st(SPD16_G + 1, ld);
+}
+
+// ---- stats: masked plate sums + store of X -------------------------------------------------------------------------
+__global__ void __launch_bounds__(PM_THREADS, 1) pmask_stats_kernel(PmArgs a, int first_chunk) {
+    __shared__ unsigned long long bits[PM_TILE];
+    __shared__ double red[PM_WARPS][2];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, gr = lane >> 2, tg = lane & 3;
+    const int K = a.K;
+    const bool is_x = w >= 17;                         // row tiles 17, 18 of the scratch hold x (S_yx), the others <xx^T>
+    double acc[8][2];                                  // [m tile][..]: rows m = mt*8 + gr, columns p = w*8 + 2tg + {0,1}
+#pragma unroll
+    for (int mt = 0; mt < 8; ++mt) acc[mt][0] = acc[mt][1] = 0.0;
+    double colsum = 0.0;                               // sum over columns of scratch row w*8 + gr (this lane's tg share)
+    double sq = 0.0, sld = 0.0;
+    const int64_t ntiles = (a.nc + PM_TILE - 1) / PM_TILE;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t cl0 = tile * PM_TILE;
+        const int64_t n0 = a.c0 + cl0;
+        __syncthreads();
+        pm_pack_mask(a.mask, a.M, a.N, n0, bits);
+        const double *Srow = a.S + (int64_t)(w * 8 + gr) * a.chp + cl0;       // B operand: scratch row p, columns of the tile
+#pragma unroll 4
+        for (int ks = 0; ks < PM_TILE / 4; ++ks) {
+            const int c = ks * 4 + tg;
+            const int64_t n = n0 + c;
+            const double b = (n < a.N) ? Srow[c] : 0.0;
+            colsum += b;
+            const unsigned long long wd = bits[c];
+            if (!is_x) {
+#pragma unroll
+                for (int mt = 0; mt < 8; ++mt) {
+                    const double av = ((wd >> (mt * 8 + gr)) & 1ull) ? 1.0 : 0.0;
+                    pm_dmma(acc[mt][0], acc[mt][1], av, b);
+                }
+            } else {
+#pragma unroll
+                for (int mt = 0; mt < 8; ++mt) {
+                    const int m = mt * 8 + gr;
+                    const bool on = (wd >> m) & 1ull;
+                    const double av = on ? __ldg(a.Y + (int64_t)m * a.N + n) : 0.0;
+                    pm_dmma(acc[mt][0], acc[mt][1], av, b);
+                }
+            }
+        }
+        // X[n][k] (coalesced), g[n], and the per-column scalars
+        for (int e = threadIdx.x; e < PM_TILE * PM_KP; e += blockDim.x) {
+            const int c = e >> 4, k = e & 15;
+            const int64_t n = n0 + c;
+            if (n < a.N && k < K) a.X[n * K + k] = a.S[(int64_t)(SPD16_PHI + k) * a.chp + cl0 + c];
+        }
+        for (int c = threadIdx.x; c < PM_TILE; c += blockDim.x) {
+            const int64_t n = n0 + c;
+            if (n < a.N) {
+                const double q = a.S[(int64_t)SPD16_G * a.chp + cl0 + c], ld = a.S[(int64_t)(SPD16_G + 1) * a.chp + cl0 + c];
+                sq += q;
+                sld += ld;
+                if (a.g) a.g[n] = -0.5 * q + 0.5 * ld;
+            }
+        }
+    }
+    // fold into this CTA's running partial (fixed order: deterministic)
+    double *part = a.partial + (size_t)blockIdx.x * PM_NPART;
+    const int ncol = SPD16_NPACK + PM_KP;               // 152 scratch rows = columns of the [64][152] statistics block
+#pragma unroll
+    for (int mt = 0; mt < 8; ++mt)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            double *dst = part + (size_t)(mt * 8 + gr) * ncol + w * 8 + 2 * tg + j;
+            *dst = first_chunk ? acc[mt][j] : *dst + acc[mt][j];
+        }
+    colsum += __shfl_xor_sync(0xffffffffu, colsum, 1);
+    colsum += __shfl_xor_sync(0xffffffffu, colsum, 2);
+    if (tg == 0) {
+        double *dst = part + (size_t)PM_MP * ncol + w * 8 + gr;
+        *dst = first_chunk ? colsum : *dst + colsum;
+    }
+    sq = warp_sum(sq);
+    sld = warp_sum(sld);
+    if (lane == 0) { red[w][0] = sq; red[w][1] = sld; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s0 = 0.0, s1 = 0.0;
+        for (int ww = 0; ww < PM_WARPS; ++ww) { s0 += red[ww][0]; s1 += red[ww][1]; }
+        double *dst = part + (size_t)PM_MP * ncol + ncol;
+        dst[0] = first_chunk ? s0 : dst[0] + s0;
+        dst[1] = first_chunk ? s1 : dst[1] + s1;
+    }
+}
+
+// partials -> caller's layout  [ S_yx (M*K) | S_xx (M*K*K, symmetric, full) | sum<xx^T> (K*K) | sum x (K) | sum phi.x | sum logdet ]
+__global__ void pmask_final_kernel(const double *__restrict__ partial, int nblocks, int M, int K, double *__restrict__ stats) {
+    const int ncol = SPD16_NPACK + PM_KP;
+    const int total = M * K + M * K * K + K * K + K + 2;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    int src;
+    if (e < M * K) { const int m = e / K, k = e - m * K; src = m * ncol + SPD16_NPACK + k; }
+    else if (e < M * K + M * K * K) {
+        const int r = e - M * K, m = r / (K * K), ij = r - m * K * K;
+        int i = ij / K, j = ij - i * K;
+        if (i > j) { const int t = i; i = j; j = t; }
+        src = m * ncol + spd16_pu(i, j);
+    } else if (e < M * K + M * K * K + K * K) {
+        const int ij = e - M * K - M * K * K;
+        int i = ij / K, j = ij - i * K;
+        if (i > j) { const int t = i; i = j; j = t; }
+        src = PM_MP * ncol + spd16_pu(i, j);
+    } else if (e < total - 2) src = PM_MP * ncol + SPD16_NPACK + (e - (M * K + M * K * K + K * K));
+    else src = PM_MP * ncol + ncol + (e - (total - 2));
+    double s = 0.0;
+    for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * PM_NPART + src];
+    stats[e] += s;
+}
+
+static double *g_pm_scratch = nullptr;
+static size_t g_pm_scratch_bytes = 0;
+
+extern "C" int bpk_pca_xsweep_masked_fused(const double *Y, const uint8_t *mask, int64_t M, int64_t N, int K,
+                                           const double *W, const double *WW, double tau,
+                                           const double *alpha, const double *amu,
+                                           double *X, double *g, double *stats, int check) {
+    BPK_REQUIRE_INIT();
+    if (M < 1 || M > PM_MP || K < 1 || K > PM_KP || N < 0)
+        return bpk_set_error(BPK_EINVAL, "bpk_pca_xsweep_masked_fused: needs M <= %d and K <= %d (got M=%lld, K=%d)",
+                             PM_MP, PM_KP, (long long)M, K);
+    if (!Y || !mask || !W || !WW || !alpha || !X || !stats)
+        return bpk_set_error(BPK_EINVAL, "bpk_pca_xsweep_masked_fused: null argument");
+    if (N == 0) return BPK_OK;
+    const int grid = g_bpk.sm_count;
+    int tiles_per_cta = 2;
+    if (const char *e = getenv("BPK_PMASK_CHUNK_TILES")) { tiles_per_cta = atoi(e); if (tiles_per_cta < 1) tiles_per_cta = 1; }
+    int64_t chunk = (int64_t)grid * tiles_per_cta * PM_TILE;
+    if (chunk > ((N + PM_TILE - 1) / PM_TILE) * PM_TILE) chunk = ((N + PM_TILE - 1) / PM_TILE) * PM_TILE;
+    const size_t need = (size_t)SPD16_ROWS * chunk * sizeof(double) + (size_t)grid * PM_NPART * sizeof(double);
+    if (need > g_pm_scratch_bytes) {
+        if (g_pm_scratch) BPK_CUDA(cudaFreeAsync(g_pm_scratch, g_bpk.stream));
+        g_pm_scratch = nullptr;
+        g_pm_scratch_bytes = 0;
+        BPK_CUDA(cudaMallocAsync((void **)&g_pm_scratch, need, g_bpk.stream));
+        g_pm_scratch_bytes = need;
+    }
+    PmArgs a;
+    a.Y = Y; a.mask = mask; a.M = M; a.N = N; a.K = K; a.W = W; a.WW = WW; a.alpha = alpha; a.amu = amu; a.tau = tau;
+    a.S = g_pm_scratch; a.chp = chunk; a.X = X; a.g = g;
+    a.partial = g_pm_scratch + (size_t)SPD16_ROWS * chunk;
+    a.flag = g_bpk.d_flag;
+    int first = 1;
+    for (int64_t c0 = 0; c0 < N; c0 += chunk) {
+        a.c0 = c0;
+        a.nc = (N - c0 < chunk) ? N - c0 : chunk;
+        const int64_t ntiles = (a.nc + PM_TILE - 1) / PM_TILE;
+        const int gtiles = (int)(ntiles < grid ? ntiles : grid);
+        BPK_LAUNCH(pmask_build_kernel, gtiles, PM_THREADS, 0, a);
+        // the inverse runs on whole tiles: padded columns of the last tile hold the prior precision (SPD), results unused
+        PmArgs b = a;
+        b.nc = ntiles * PM_TILE;
+        BPK_LAUNCH(pmask_inverse_kernel, (unsigned)((b.nc + 127) / 128), 128, 0, b);
+        BPK_LAUNCH(pmask_stats_kernel, grid, PM_THREADS, 0, a, first);
+        first = 0;
+    }
+    const int total = (int)(M * K + M * K * K + (int64_t)K * K + K + 2);
+    BPK_LAUNCH(pmask_final_kernel, (total + 127) / 128, 128, 0, a.partial, grid, (int)M, K, stats);
+    if (check) return bpk_check_flag(BPK_ENOTSPD);
+    return BPK_OK;
+}

@@ -36,6 +36,14 @@ __device__ __forceinline__ void vb_stamp(unsigned long long *dbg, int slot) {
     }
 }
 
+__device__ __forceinline__ void vb_stamp_lane(unsigned long long *dbg, int slot) {       // lane 0 of the calling warp
+    if (dbg && (threadIdx.x & 31) == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        dbg[slot] = t;
+    }
+}
+
 // ---- LL packets of the peer-memory exchange (layout: common.cuh) ---------------------------------------
 // slot of element e deposited by rank r with parity par, inside the window `win`
 __device__ __forceinline__ unsigned long long *ll_slot(double *win, int par, int r, int e) {

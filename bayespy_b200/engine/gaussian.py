@@ -51,7 +51,7 @@ class FactoredSecondMoment:
             u0 = self.u0 if self.u0.shape[:-1] == pl else self.u0.broadcast_to(pl + (K,))
             u0 = u0.contiguous()
             ncov = int(np.prod(self.cov.shape[:-2], dtype=np.int64)) if self.cov.ndim > 2 else 1
-            cov = self.cov
+            cov = dense(self.cov)             # the covariance itself may be produced on demand
             if ncov != 1 and tuple(cov.shape[:-2]) != pl:
                 cov = cov.broadcast_to(pl + (K, K))
                 ncov = N

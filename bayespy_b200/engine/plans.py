@@ -91,6 +91,7 @@ class FactorModelPlan:
         plan = self
         o = self._orig
         o["col.update"] = self.col.update
+        o["Y.update"] = self.Y.update
         o["col.lb"] = self.col.lower_bound_contribution
         o["F.msg"] = self.F.message_to_parent
         o["Y.msg"] = self.Y.message_to_parent
@@ -98,24 +99,52 @@ class FactorModelPlan:
 
         def col_update(node, annealing=1.0):
             if annealing == 1.0 and plan.valid():
+                if plan.masked():
+                    return plan.update_col_masked()
                 return plan.update_col()
             return o["col.update"](annealing) if annealing != 1.0 else o["col.update"]()
 
+        def Y_update(node, annealing=1.0):
+            if annealing == 1.0 and plan.valid() and plan.masked():
+                return plan.update_Y_lazy()
+            return o["Y.update"](annealing) if annealing != 1.0 else o["Y.update"]()
+
         def col_lb(node):
-            return plan.bound_col() if plan.valid() and plan._col_is_fused() else o["col.lb"]()
+            if plan.valid():
+                if plan.masked():
+                    if plan._mstats_ready():
+                        return plan.bound_col_masked()
+                elif plan._col_is_fused():
+                    return plan.bound_col()
+            plan._materialize_Y()
+            return o["col.lb"]()
 
         def F_msg(node, index):
             if index == plan.i_row and plan.valid():
-                return plan.message_to_row()
+                if not plan.masked():
+                    return plan.message_to_row()
+                if plan._mstats_ready():
+                    return plan.message_to_row_masked()
+            plan._materialize_Y()
             return o["F.msg"](index)
 
         def Y_msg(node, index):
             if index == 1 and plan.valid():
-                return plan.message_to_tau()
+                if not plan.masked():
+                    return plan.message_to_tau()
+                if plan._mstats_ready():
+                    return plan.message_to_tau_masked()
+            plan._materialize_Y()
             return o["Y.msg"](index)
 
         def Y_lb(node):
-            return plan.bound_Y() if plan.valid() else o["Y.lb"]()
+            if plan.valid():
+                if not plan.masked():
+                    return plan.bound_Y()
+                if plan._mstats_ready():
+                    return plan.bound_Y_masked()
+            plan._materialize_Y()
+            return o["Y.lb"]()
 
         def col_rotated(Rd, old_version):
             # S_yx = sum y x^T, S_xx = sum x x^T, s_x = sum x follow x -> R x without another pass over Y
@@ -135,6 +164,7 @@ class FactorModelPlan:
         self.col._rotate_hooks = hooks
 
         self.col.update = types.MethodType(col_update, self.col)
+        self.Y.update = types.MethodType(Y_update, self.Y)
         self.col.lower_bound_contribution = types.MethodType(col_lb, self.col)
         self.F.message_to_parent = types.MethodType(F_msg, self.F)
         self.Y.message_to_parent = types.MethodType(Y_msg, self.Y)
@@ -160,8 +190,9 @@ class FactorModelPlan:
             self._res_cache = None
             return False
         if not (Y.observed is True or (isinstance(Y.observed, np.ndarray) and Y.observed.all())):
-            return False
-        if not mask_is_full(Y.mask):
+            if not self.masked():
+                return False
+        elif not mask_is_full(Y.mask):
             return False
         if any(n.annealing != 1.0 for n in (Y, col, row) if hasattr(n, "annealing")):
             return False
@@ -169,13 +200,209 @@ class FactorModelPlan:
             return False
         return True
 
+    # ---- missing values: per-column precision, fused (csrc/pca_masked.cu) -----------------------------------------
+    def masked(self):
+        """True when Y is observed through an (M, N) mask the fused masked sweep can serve: every column and every row
+        has at least one observation (so that no plate of X or C is switched off: node.py:446-526), M <= 64, K <= 16."""
+        Y = self.Y
+        key = (id(Y.observed), id(Y.mask))
+        if getattr(self, "_masked_key", None) != key:
+            ok = False
+            obs = Y.observed
+            if isinstance(obs, np.ndarray) and not obs.all() and obs.shape == (self.M, self.N) \
+                    and self.M <= 64 and self.K <= 16 and hasattr(_bpk.get(), "pca_xsweep_masked_fused"):
+                mk = np.broadcast_to(np.asarray(Y.mask, dtype=bool), (self.M, self.N))
+                ok = bool(np.array_equal(mk, obs) and obs.any(axis=0).all() and obs.any(axis=1).all())
+            self._masked_ok = ok
+            self._masked_key = key
+            self._mstats = None
+        return self._masked_ok
+
+    def _mstats_ready(self):
+        """The masked statistics describe the CURRENT q(X) (they were produced by the sweep that formed it)."""
+        ms = getattr(self, "_mstats", None)
+        return ms is not None and ms[0] == self.col._version
+
+    def _msplit(self):
+        M, K = self.M, self.K
+        st = self._mstats[1]
+        o = [0, M * K, M * K + M * K * K, M * K + M * K * K + K * K, M * K + M * K * K + K * K + K]
+        return (st.slice_axis(0, o[0], o[1]).reshape((M, K)), st.slice_axis(0, o[1], o[2]).reshape((M, K, K)),
+                st.slice_axis(0, o[2], o[3]).reshape((K, K)), st.slice_axis(0, o[3], o[4]),
+                st.slice_axis(0, o[4], o[4] + 1).reshape(()), st.slice_axis(0, o[4] + 1, o[4] + 2).reshape(()))
+
+    def _row_moments(self):
+        M, K = self.M, self.K
+        W = self.row.u[0].broadcast_to((M, 1, K)).reshape((M, K)).contiguous()
+        WW = dense(self.row.u[1])
+        WW = D.asarray(WW).broadcast_to((M, 1, K, K)).reshape((M, K, K)).contiguous()
+        return W, WW
+
+    def _sumsq_masked(self):
+        v = id(self.Y.observed)
+        if getattr(self, "_msumsq", None) is None or self._msumsq[0] != v:
+            out = DArray.empty((2,))
+            _bpk.get().sumsq(self._Yd().ptr, self.Y.mask_device().contiguous().ptr, self.M * self.N, out.ptr)
+            parallel.allreduce_sum(out)
+            self._msumsq = (v, out, float(out.numpy()[1]))
+        return self._msumsq[1].slice_axis(0, 0, 1).reshape(()), self._msumsq[2]
+
+    def _materialize_Y(self):
+        """Generic code is about to read Y's moments: make the pending latent entries concrete."""
+        Y = self.Y
+        for name in ("u", "phi"):
+            lst = getattr(Y, name, None)
+            if isinstance(lst, list) and any(isinstance(a, LazyArray) for a in lst):
+                setattr(Y, name, [dense(a) for a in lst])
+        if isinstance(getattr(Y, "g", None), LazyArray):
+            Y.g = dense(Y.g)
+
+    def update_Y_lazy(self):
+        """Y.update() for a partially observed Y (stochastic.py:276-282: the unobserved entries of Y are latent and get
+        the predictive moments of their parents).  Nothing downstream of the sweep uses them — messages and the bound
+        only see the observed entries — so they are produced ON DEMAND (``np.asarray(Y.u[0])``), from the parents'
+        moments as they are NOW (the arrays are captured; forming them needs <f f> over (M, N) and the per-column
+        second moments, i.e. exactly the passes the fused sweep avoids)."""
+        Y, F = self.Y, self.F
+        snaps = [list(p.u) for p in F.parents]
+        utau = list(self.tau.get_moments())
+        ydata, obs = self._Yd(), Y.mask_device()
+        memo = {}
+
+        def compute():
+            if not memo:
+                uF = F._compute_moments(*[[D.asarray(u[0]), dense(u[1])] for u in snaps])
+                phi = Y._canonical_phi(Y._distribution.compute_phi_from_parents(uF, utau))
+                u_new, g_new = Y._distribution.compute_moments_and_cgf(phi)
+                fixed = [ydata, D.square(ydata)]
+                memo["u"] = [D.where(obs.add_trailing(Y.ndims[i]), fixed[i], D.asarray(u_new[i]).broadcast_to(Y.get_shape(i)))
+                             for i in range(2)]
+                memo["phi"] = [D.asarray(p) for p in phi]
+                memo["g"] = D.asarray(g_new)
+            return memo
+        Y.u = [LazyArray(Y.get_shape(0), lambda: compute()["u"][0]), LazyArray(Y.get_shape(1), lambda: compute()["u"][1])]
+        Y.phi = [LazyArray(Y.get_shape(0), lambda: compute()["phi"][0]), LazyArray(Y.get_shape(1), lambda: compute()["phi"][1])]
+        Y.g = LazyArray(tuple(Y.plates), lambda: compute()["g"])
+        Y._version += 1
+
+    def update_col_masked(self):
+        """col.update() with missing values: one fused sweep builds, inverts and contracts the per-column precisions
+        (gaussian.py:672-706 + linalg.py:50-59,111-146,185-195 + dot.py:581 in the reference)."""
+        col, M, N, K = self.col, self.M, self.N, self.K
+        be = _bpk.get()
+        u_par = col.moments_from_parents()
+        phi_p = col._canonical_phi(col._distribution.compute_phi_from_parents(*u_par))
+        if not (all(n == 1 for n in phi_p[0].shape[:-1]) and all(n == 1 for n in phi_p[1].shape[:-2])):
+            return self._orig["col.update"]()          # prior differs per column: generic path
+        tau = float(self._tau_moments()[0].numpy())
+        W, WW = self._row_moments()
+        amu = phi_p[0].reshape((K,)).contiguous()
+        alpha = D.mul(phi_p[1].reshape((K, K)).diag_view(1), -2.0).contiguous()        # prior precision (diagonal)
+        X = DArray.empty((1, N, K))
+        g = DArray.empty((1, N))
+        st = DArray.zeros((M * K + M * K * K + K * K + K + 2,))
+        Yd, mk = self._Yd(), self.Y.mask_device().contiguous()
+        if self.kernel_timers is not None and self._timer_pos < len(self.kernel_timers):
+            tid = self.kernel_timers[self._timer_pos]
+            self._timer_pos += 1
+            be.timer_record(tid, 0)
+            be.pca_xsweep_masked_fused(Yd.ptr, mk.ptr, M, N, K, W.ptr, WW.ptr, tau, alpha.ptr, amu.ptr, X.ptr, g.ptr, st.ptr)
+            be.timer_record(tid, 1)
+        else:
+            be.pca_xsweep_masked_fused(Yd.ptr, mk.ptr, M, N, K, W.ptr, WW.ptr, tau, alpha.ptr, amu.ptr, X.ptr, g.ptr, st.ptr)
+        parallel.allreduce_sum(st)
+        self.fused_calls += 1
+
+        def cov_fn():
+            """(1,N,K,K) covariances on demand only (the sweep itself never stores them)."""
+            cov = DArray.empty((1, N, K, K))
+            Xs, gs = DArray.empty((N, K)), DArray.empty((N,))
+            s2 = DArray.zeros((M * K + M * K * K,))
+            be.pca_xsweep_masked(Yd.ptr, mk.ptr, M, N, K, W.ptr, WW.ptr, tau, alpha.ptr, amu.ptr, Xs.ptr, cov.ptr, gs.ptr,
+                                 s2.ptr)
+            return cov
+        lazy_cov = LazyArray((1, N, K, K), cov_fn)
+
+        def phi1_fn():
+            c = dense(lazy_cov)
+            out = DArray.empty((1, N, K, K))
+            # -1/2 Lam_n = -1/2 Cov_n^-1: re-inverting is only for users who look at phi; the bound does not need it
+            U = DArray.empty((N, K, K))
+            be.chol(c.reshape((N, K, K)).contiguous().ptr, U.ptr, N, K)
+            be.chol_inv(U.ptr, out.ptr, N, K)
+            return D.mul(out, -0.5)
+
+        def phi0_fn():
+            Lam = D.mul(phi1_fn(), -2.0)
+            return D.sum_product([Lam, X], [["o", "n", "i", "j"], ["o", "n", "j"]], ["o", "n", "i"])
+        col.phi = [LazyArray((1, N, K), phi0_fn), LazyArray((1, N, K, K), phi1_fn)]
+        col.u = [X, FactoredSecondMoment(X, lazy_cov, (K,))]
+        col.g = g
+        col._version += 1
+        col._fused = None
+        self._mstats = (col._version, st)
+        self._stats = None
+
+    def message_to_row_masked(self):
+        """F -> row factor with missing values: m0[m] = tau S_yx[m], m1[m] = -1/2 tau sum_n mask[m,n] <x_n x_n^T>
+        (dot.py:581 masked and summed over n by node.py:650)."""
+        tau, _ = self._tau_moments()
+        Syx, Sxx, _, _, _, _ = self._msplit()
+        M, K = self.M, self.K
+        self.fused_calls += 1
+        return [D.mul(Syx, tau).reshape((M, 1, K)), D.mul(D.mul(Sxx, tau), -0.5).reshape((M, 1, K, K))]
+
+    def _E2_masked(self):
+        """sum over the observed entries of <(y - f)^2>."""
+        key = (self.row._version, self.col._version)
+        if getattr(self, "_me2", None) is None or self._me2[0] != key:
+            Syx, Sxx, _, _, _, _ = self._msplit()
+            W, WW = self._row_moments()
+            t1 = D.sum_product([W, Syx], [["m", "k"], ["m", "k"]], [])
+            t2 = D.sum_product([WW, Sxx], [["m", "i", "j"], ["m", "i", "j"]], [])
+            ssq, _ = self._sumsq_masked()
+            self._me2 = (key, D.add(D.axpby(1.0, ssq, -2.0, t1), t2))
+        return self._me2[1]
+
+    def message_to_tau_masked(self):
+        self.fused_calls += 1
+        shp = tuple(self.tau.plates)
+        _, count = self._sumsq_masked()
+        return [D.mul(self._E2_masked(), -0.5).reshape(shp), D.asarray(0.5 * count).reshape(shp)]
+
+    def bound_Y_masked(self):
+        """Observed entries only (expfamily.py:470-476 sums where the node's mask is set)."""
+        tau, logtau = self._tau_moments()
+        _, count = self._sumsq_masked()
+        a = D.mul(D.mul(self._E2_masked(), tau), -0.5)
+        return D.add(a, D.affine(logtau, 0.5 * count, -0.5 * count * LOG2PI))
+
+    def bound_col_masked(self):
+        """E[log p(X)] - E[log q(X)]: the q-side terms reduce to N K / 2 - 1/2 sum_n log det Lam_n; the prior is
+        evaluated with the parents' CURRENT moments (expfamily.py:400-480)."""
+        col, N, K = self.col, self.Ng, self.K
+        u_par = col.moments_from_parents()
+        phi_p = col._canonical_phi(col._distribution.compute_phi_from_parents(*u_par))
+        if not (all(n == 1 for n in phi_p[0].shape[:-1]) and all(n == 1 for n in phi_p[1].shape[:-2])):
+            return self._orig["col.lb"]()
+        cgf = D.asarray(col._distribution.compute_cgf_from_parents(*u_par))
+        _, _, sumXX, sumx, _, sumld = self._msplit()
+        t0 = D.sum_product([phi_p[0].reshape((K,)), sumx], [["k"], ["k"]], [])
+        t1 = D.sum_product([phi_p[1].reshape((K, K)), sumXX], [["i", "j"], ["i", "j"]], [])
+        ncgf = D.mul(D.reduce_to_shape(cgf, (), from_shape=col.plates), float(self.Ng) / float(self.N))
+        return D.add(D.add(D.add(t0, t1), D.affine(sumld, -0.5, 0.5 * N * K)), ncgf)
+
     def _col_is_fused(self):
         return isinstance(self.col.u[1], FactoredSecondMoment) and \
             all(n == 1 for n in self.col.u[1].cov.shape[:-2])
 
     # ---- small shared quantities ---------------------------------------------------------------------
     def _Yd(self):
-        return self.Y.u[0].contiguous()
+        u0 = self.Y.u[0]
+        if isinstance(u0, LazyArray):            # latent entries pending (update_Y_lazy): the observed values are unchanged
+            return self._ydata
+        self._ydata = u0.contiguous()
+        return self._ydata
 
     def _tau_moments(self):
         u = self.tau.get_moments()
@@ -412,7 +639,7 @@ class FactorModelPlan:
     def resident_program(self, vb, nodes):
         """Opcode list for ONE iteration of ``VB.update(*nodes)`` when the whole sweep can stay on the
         device (this model, constant hyper-priors, every latent node updated exactly once), else None."""
-        if not self._valid():
+        if not self._valid() or self.masked():
             return None
         col, row, tau, Y = self.col, self.row, self.tau, self.Y
         alpha = row.parents[1]

@@ -346,7 +346,7 @@ def run_gpu(args):
             traffic = None
     value = steps / (ms_max * 1e-3)
     line = {
-        "metric": METRIC, "value": value, "unit": "it/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+        "metric": METRIC if n_total == N_TOTAL else "VB iterations/sec on PCA N=%d D=64 K=16" % n_total, "value": value, "unit": "it/s", "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "Bayesian PCA N=%d M=64 K=16 fully observed (pca.rst:40-66), one VB sweep over "
@@ -404,6 +404,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="pca", choices=["pca", "pca_masked", "gmm", "lssm"],
+                    help="pca = the headline metric (BASELINE.json configs[1] scaled to N=1e7); gmm / lssm = configs[2] / [3] "
+                         "(tools/bench_workloads.py)")
     ap.add_argument("--n", type=int, default=N_TOTAL, help="total number of columns (default: the metric's 1e7)")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--ref-budget-s", type=float, default=150.0,
@@ -412,6 +415,15 @@ def main():
     ap.add_argument("--clock-interval-ms", type=int, default=200,
                     help="nvidia-smi sampling period during the timed region (B200_PROFILING.md recipe: 200); 0 = off")
     args = ap.parse_args()
+    if args.workload != "pca":
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_workloads as bw
+        if args.impl == "reference":
+            {"gmm": bw.run_gmm_reference}.get(args.workload, lambda a: print(json.dumps(
+                {"impl": "reference", "unavailable": "no reference arm for workload %s" % a.workload})))(args)
+        else:
+            {"gmm": bw.run_gmm, "lssm": bw.run_lssm, "pca_masked": bw.run_pca_masked}[args.workload](args)
+        return
     if args.impl == "reference":
         run_reference(args)
     else:

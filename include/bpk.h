@@ -206,6 +206,16 @@ int bpk_pca_xsweep_masked(const double *Y, const uint8_t *mask, int64_t M, int64
                           double tau, const double *alpha /*[K]*/, const double *amu /*[K]*/,
                           double *X, double *COV /*nullable*/, double *g /*[N]*/,
                           double *stats, int check);
+/* The same sweep FUSED (csrc/pca_masked.cu; M <= 64, K <= 16): per-column precisions are built, inverted and
+ * contracted chunk by chunk through a fixed-size scratch; nothing of size (N,K,K) is stored.  Replaces, per sweep,
+ * the per-plate SciPy loops of linalg.py:50-59,111-146,185-195 driven by gaussian.py:672-706 and the two masked
+ * plate sums of dot.py:581 / node.py:650.  Writes X [N][K], g [N] (nullable: cgf of q(x_n)), and ADDS to
+ *   stats = [ S_yx (M*K) | S_xx (M*K*K: sum_n mask[m,n] <x_n x_n^T>) | sum_n <x_n x_n^T> (K*K) | sum_n x_n (K)
+ *             | sum_n phi_n.x_n | sum_n log det Lam_n ]          (caller zeroes it).  704 B/col of HBM traffic.   */
+int bpk_pca_xsweep_masked_fused(const double *Y, const uint8_t *mask, int64_t M, int64_t N, int K,
+                                const double *W /*[M][K]*/, const double *WW /*[M][K][K]*/,
+                                double tau, const double *alpha /*[K]*/, const double *amu /*[K] or NULL*/,
+                                double *X, double *g /*nullable*/, double *stats, int check);
 /* sum_{m,n} mask*y^2 and count (constants of the tau update)                */
 int bpk_sumsq(const double *Y, const uint8_t *mask /*nullable*/, int64_t count,
               double *out2 /* [2]: sum y^2, #observed */);

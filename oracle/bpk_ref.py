@@ -390,6 +390,37 @@ class RefBackend:
         s[:M * K] += np.einsum("mn,mn,nk->mk", mk, y, x).ravel()
         s[M * K:] += np.einsum("mn,nij->mij", mk, xx).ravel()
 
+    def pca_xsweep_masked_fused(self, Y, mask, M, N, K, W, WW, tau, alpha, amu, X, g, stats, check=True):
+        """csrc/pca_masked.cu restated: per-column precision (gaussian.py:672-706 with per-plate phi1, the per-plate
+        loops of linalg.py:50-59,111-146,185-195) and the masked plate sums of dot.py:581 / node.py:650."""
+        self._launches += 1
+        y = _dense(Y, (M, N))
+        mk = _dense(mask, (M, N), np.uint8).astype(np.float64)
+        w = _dense(W, (M, K))
+        ww = _dense(WW, (M, K, K))
+        al = _dense(alpha, (K,))
+        am = _dense(amu, (K,)) if amu else np.zeros(K)
+        Lam = np.diag(al)[None] + tau * np.einsum("mn,mij->nij", mk, ww)
+        phi0 = tau * np.einsum("mn,mn,mk->nk", mk, y, w) + am
+        if check and np.any(np.linalg.eigvalsh(Lam)[:, 0] <= 0):
+            raise NotPositiveDefinite("Matrix not positive definite")
+        cov = np.linalg.inv(Lam)
+        x = np.einsum("nij,nj->ni", cov, phi0)
+        _dense(X, (N, K))[...] = x
+        q = np.einsum("ni,ni->n", x, phi0)
+        ld = np.linalg.slogdet(Lam)[1]
+        if g:
+            _dense(g, (N,))[...] = -0.5 * q + 0.5 * ld
+        xx = cov + x[:, :, None] * x[:, None, :]
+        s = _dense(stats, (M * K + M * K * K + K * K + K + 2,))
+        o = 0
+        s[o:o + M * K] += np.einsum("mn,mn,nk->mk", mk, y, x).ravel(); o += M * K
+        s[o:o + M * K * K] += np.einsum("mn,nij->mij", mk, xx).ravel(); o += M * K * K
+        s[o:o + K * K] += xx.sum(axis=0).ravel(); o += K * K
+        s[o:o + K] += x.sum(axis=0); o += K
+        s[o] += q.sum()
+        s[o + 1] += ld.sum()
+
     def sumsq(self, Y, mask, count, out2):
         self._launches += 1
         y = _dense(Y, (count,))

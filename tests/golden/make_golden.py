@@ -486,7 +486,7 @@ def pca_bench_prefix(name="pca_bench_100k", N=100_000, iters=5):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["quickstart", "pca", "linalg", "summul", "dist", "gmm", "gmc", "rot", "dot", "mixard", "gmcplates", "gmcvarying", "pcabench"]
+    which = sys.argv[1:] or ["quickstart", "pca", "linalg", "summul", "dist", "gmm", "gmc", "rot", "dot", "mixard", "gmcplates", "gmcvarying", "pcabench", "pcamasked64"]
     if "quickstart" in which:
         quickstart()
     if "pca" in which:
@@ -510,6 +510,8 @@ if __name__ == "__main__":
         pca_rotated()
     if "gmcplates" in which:
         lssm_plated()
+    if "pcamasked64" in which:
+        pca("pca_masked_64x16", 64, 300, 16, mask_p=0.8, iters=4)
     if "pcabench" in which:
         pca_bench_prefix()
     if "gmcvarying" in which:

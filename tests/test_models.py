@@ -110,6 +110,40 @@ def test_pca_masked_generic(backend):
         check_node(g, nm, n[nm])
 
 
+@pytest.mark.parametrize("name,M,N,K", [("pca_masked", 12, 40, 4), ("pca_masked_64x16", 64, 300, 16)])
+def test_pca_masked_fused(backend, name, M, N, K):
+    """Missing values through the FUSED masked sweep (csrc/pca_masked.cu: masked tensor-pipe GEMMs + one thread per
+    column for the K x K inverse; nothing of size (N,K,K) is stored) against the reference's trajectory."""
+    g = golden(name)
+    Q, n = build_pca(g, M, N, K, fused=True)
+    iters = len(g["L"])
+    Q.update(repeat=iters, verbose=False, tol=0)
+    assert Q.plans[0].masked() and Q.plans[0].fused_calls >= 3 * iters - 2
+    close(Q.L[:iters], g["L"], rtol=1e-8)
+    for nm in ("X", "C", "alpha", "tau"):
+        check_node(g, nm, n[nm])
+    # the latent (unobserved) entries of Y are produced on demand and equal the per-node tier's
+    Q0, n0 = build_pca(g, M, N, K, fused=False)
+    Q0.update(repeat=iters, verbose=False, tol=0)
+    for i in range(2):
+        close(np.asarray(n["Y"].u[i]), np.asarray(n0["Y"].u[i]), rtol=1e-7)
+
+
+def test_pca_masked_fused_any_update_order(backend):
+    """Stale masked statistics (somebody else changed X, or C is updated first) fall back to the generic messages."""
+    g = golden("pca_masked")
+    res = []
+    for fused in (False, True):
+        Q, n = build_pca(g, 12, 40, 4, fused)
+        for _ in range(3):
+            Q.update("C", "tau", "X", "alpha", "X", "C", verbose=False, tol=0)
+        res.append((Q.L[:3].copy(), np.asarray(n["X"].u[0]), np.asarray(n["C"].u[1]), np.asarray(n["X"].u[1])))
+    close(res[0][0], res[1][0], rtol=1e-9)
+    close(res[0][1], res[1][1], rtol=1e-8)
+    close(res[0][2], res[1][2], rtol=1e-8)
+    close(res[0][3], res[1][3], rtol=1e-7)
+
+
 def test_pca_update_order_independent_of_plan(backend):
     """Arbitrary user update orders give the same answer with and without the fused plan
     (stale statistics must be detected through the version tags)."""

@@ -109,6 +109,69 @@ def test_pca_xsweep_masked(backend, M, N, K):
     np.testing.assert_allclose(s[M * K:].reshape(M, K, K), np.einsum("mn,nij->mij", mk, xx), rtol=1e-9, atol=1e-9)
 
 
+@pytest.mark.parametrize("M,N,K,chunk_tiles", [(12, 40, 4, None), (64, 130, 16, None), (5, 33, 7, None), (64, 40000, 16, 1),
+                                               (64, 19001, 16, 1), (33, 1025, 16, None)])
+def test_pca_xsweep_masked_fused(backend, M, N, K, chunk_tiles, monkeypatch):
+    """The fused masked sweep (csrc/pca_masked.cu): masked tensor-pipe GEMMs + one thread per column, several chunks
+    of the fixed-size scratch, ragged last tile, padded M and K — against a dense NumPy restatement."""
+    if N > 5000 and backend.name != "cuda":
+        pytest.skip("multi-chunk sizes run on the GPU only (the dense NumPy restatement is the checker there)")
+    if chunk_tiles is not None:
+        monkeypatch.setenv("BPK_PMASK_CHUNK_TILES", str(chunk_tiles))      # 148 x 128 columns per chunk
+    rng = np.random.RandomState(N % 1000)
+    y = rng.randn(M, N)
+    mask = rng.rand(M, N) > 0.25
+    W = rng.randn(M, K)
+    Cw = rng.randn(M, K, K)
+    WW = W[:, :, None] * W[:, None, :] + 0.1 * Cw @ np.swapaxes(Cw, -1, -2)
+    tau, alpha, amu = 1.7, rng.gamma(2.0, 1.0, K) + 0.1, rng.randn(K)
+    mk = mask.astype(float)
+    Lam = np.diag(alpha)[None] + tau * np.einsum("mn,mij->nij", mk, WW)
+    phi0 = tau * np.einsum("mn,mn,mk->nk", mk, y, W) + amu
+    cov = np.linalg.inv(Lam)
+    x = np.einsum("nij,nj->ni", cov, phi0)
+    q = np.einsum("ni,ni->n", x, phi0)
+    ld = np.linalg.slogdet(Lam)[1]
+    xx = cov + x[:, :, None] * x[:, None, :]
+    d = {k: DArray.from_numpy(v) for k, v in dict(y=y, W=W, WW=WW, alpha=alpha, amu=amu).items()}
+    md = DArray.from_numpy(mask)
+    X, G = DArray.empty((N, K)), DArray.empty((N,))
+    st = DArray.zeros((M * K + M * K * K + K * K + K + 2,))
+    backend.pca_xsweep_masked_fused(d["y"].ptr, md.ptr, M, N, K, d["W"].ptr, d["WW"].ptr, tau, d["alpha"].ptr,
+                                    d["amu"].ptr, X.ptr, G.ptr, st.ptr, True)
+    np.testing.assert_allclose(X.numpy(), x, rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(G.numpy(), -0.5 * q + 0.5 * ld, rtol=1e-10, atol=1e-10)
+    s = st.numpy()
+    o = 0
+    np.testing.assert_allclose(s[o:o + M * K].reshape(M, K), np.einsum("mn,mn,nk->mk", mk, y, x), rtol=1e-9, atol=1e-8)
+    o += M * K
+    np.testing.assert_allclose(s[o:o + M * K * K].reshape(M, K, K), np.einsum("mn,nij->mij", mk, xx), rtol=1e-9, atol=1e-8)
+    o += M * K * K
+    np.testing.assert_allclose(s[o:o + K * K].reshape(K, K), xx.sum(axis=0), rtol=1e-9, atol=1e-8)
+    o += K * K
+    np.testing.assert_allclose(s[o:o + K], x.sum(axis=0), rtol=1e-9, atol=1e-8)
+    np.testing.assert_allclose(s[o + K], q.sum(), rtol=1e-10)
+    np.testing.assert_allclose(s[o + K + 1], ld.sum(), rtol=1e-10)
+    # a second call ADDS to the statistics (the caller zeroes them)
+    backend.pca_xsweep_masked_fused(d["y"].ptr, md.ptr, M, N, K, d["W"].ptr, d["WW"].ptr, tau, d["alpha"].ptr,
+                                    d["amu"].ptr, X.ptr, G.ptr, st.ptr, True)
+    np.testing.assert_allclose(st.numpy()[o + K], 2 * q.sum(), rtol=1e-10)
+
+
+def test_pca_xsweep_masked_fused_rejects_a_non_spd_precision(backend):
+    M, N, K = 8, 20, 4
+    rng = np.random.RandomState(0)
+    W = rng.randn(M, K)
+    WW = -np.tile(np.identity(K), (M, 1, 1))                     # "second moments" that make Lam_n indefinite
+    d = {k: DArray.from_numpy(v) for k, v in dict(y=rng.randn(M, N), W=W, WW=WW, alpha=np.ones(K), amu=np.zeros(K)).items()}
+    md = DArray.from_numpy(np.ones((M, N), dtype=bool))
+    X, G = DArray.empty((N, K)), DArray.empty((N,))
+    st = DArray.zeros((M * K + M * K * K + K * K + K + 2,))
+    with pytest.raises(Exception, match="positive definite"):
+        backend.pca_xsweep_masked_fused(d["y"].ptr, md.ptr, M, N, K, d["W"].ptr, d["WW"].ptr, 1.0, d["alpha"].ptr,
+                                        d["amu"].ptr, X.ptr, G.ptr, st.ptr, True)
+
+
 @pytest.mark.parametrize("N,D,K", [(300, 3, 5), (1000, 8, 64), (129, 2, 10), (77, 1, 2)])
 def test_gmm_sweep(backend, N, D, K):
     rng = np.random.RandomState(N + D)

@@ -1,0 +1,455 @@
+"""The other BASELINE.json configs as bench.py workloads (``bench.py --workload gmm | lssm``): same JSON contract as
+the headline PCA line (value, ms_per_step, roofline, cpu_baseline, e2e, clocks, gpu_launches).
+
+gmm   config 3: Gaussian mixture N=1e7, D=8, K=64 (gmm.rst:71-98), one VB sweep over [mu, Lambda, Z, alpha] incl.
+      the lower bound; sample axis block-sharded over ranks, one all-reduce of the mixture statistics per sweep.
+lssm  config 4: linear state-space model T=1e5, D=32, M=256 (lssm.rst:45-181 scaled up); does not shard over time:
+      replicas only.
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+GMM_D, GMM_K = 8, 64
+GMM_BYTES_PER_ROW = GMM_D * 8 + GMM_K * 8                       # 576 B
+GMM_FLOPS_PER_ROW = 4 * GMM_K * (GMM_D * GMM_D + GMM_D)        # ~18.4 kflop algorithmic
+GMM_EXEC_FLOPS_PER_ROW = 24 * 512                              # 24 DMMA.8x8x4 per row (symmetric monomial features)
+FP64_DMMA_PEAK_TFLOPS = 36.9                                   # measured: profiles/r01_ubench_dmma_occupancy.txt
+
+
+def gmm_rows(n0, n1, seed=1):
+    """Rows [n0, n1) of 64 unit-variance blobs (means 5 randn(K, D); demos/stochastic_inference.py:49-54 pattern),
+    and the random initial labels; seeded per 65 536-row block (independent of the sharding)."""
+    K, D, B = GMM_K, GMM_D, bench.BLOCK
+    means = 5.0 * np.random.default_rng(seed).standard_normal((K, D))
+    y = np.empty((n1 - n0, D))
+    z0 = np.empty(n1 - n0, dtype=np.int64)
+    for blk in range(n0 // B, (max(n1, n0 + 1) - 1) // B + 1):
+        c0 = blk * B
+        rng = np.random.default_rng([seed, 7, blk])
+        z = rng.integers(0, K, size=B)
+        yb = means[z] + rng.standard_normal((B, D))
+        zi = rng.integers(0, K, size=B)
+        lo, hi = max(c0, n0), min(c0 + B, n1)
+        if hi > lo:
+            y[lo - n0:hi - n0] = yb[lo - c0:hi - c0]
+            z0[lo - n0:hi - n0] = zi[lo - c0:hi - c0]
+    return y, z0
+
+
+def build_gmm(y, z0):
+    from bayespy_b200.nodes import Dirichlet, Categorical, Gaussian, Wishart, Mixture
+    from bayespy_b200.inference import VB
+    N, D = y.shape
+    K = GMM_K
+    alpha = Dirichlet(1e-5 * np.ones(K), name="alpha")
+    Z = Categorical(alpha, plates=(N,), name="Z")
+    mu = Gaussian(np.zeros(D), 1e-5 * np.identity(D), plates=(K,), name="mu")
+    Lam = Wishart(D, 1e-5 * np.identity(D), plates=(K,), name="Lambda")
+    Y = Mixture(Z, Gaussian, mu, Lam, name="Y")
+    Z.initialize_from_value(z0)
+    Y.observe(y)
+    Q = VB(Y, mu, Lam, Z, alpha)
+    Q.ignore_bound_checks = True
+    return Q, dict(Y=Y, mu=mu, Lam=Lam, Z=Z, alpha=alpha)
+
+
+def gmm_reference_seconds(n_sample, steps, warmup):
+    y, z0 = gmm_rows(0, n_sample)
+    from oracle import make_ref, ref_models
+    if not make_ref.available():
+        raise RuntimeError("oracle/_ref not staged")
+    Q, _ = ref_models.gmm(y, GMM_K, z0)
+    return ref_models.time_sweeps(Q, steps, warmup)
+
+
+def run_gmm_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    n_total = args.n if args.n != bench.N_TOTAL or args.workload != "gmm" else 10_000_000
+    per_row = gmm_reference_seconds(1000, 1, 1) / 1000
+    n_sample = int(max(1000, min(20000, args.ref_budget_s / max(args.steps + args.warmup, 1) / per_row)))
+    dt = gmm_reference_seconds(n_sample, args.steps, args.warmup)
+    scale = n_total / n_sample
+    value = 1.0 / (dt * scale)
+    cores = bench.blas_threads()
+    line = {
+        "impl": "reference", "metric": "VB iterations/sec on GMM N=%d D=8 K=64" % n_total, "value": value, "unit": "it/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "Gaussian mixture N=%d D=8 K=64 (gmm.rst:71-98), one VB sweep incl. lower bound" % n_total,
+                   "cpu_sample_rows": n_sample, "value_is_extrapolated": True, "extrapolation_factor": scale},
+        "cpu_baseline": {"value": value, "unit": "it/s", "cores": cores, "kind": "reference",
+                         "sample": "unmodified reference package (oracle/_ref) running gmm.rst:71-98 on the first %d of %d rows "
+                                   "(its (N,K,D,D) temporaries cap it near 1e5 rows), %d timed sweeps, extrapolated linearly (x%.0f)"
+                                   % (n_sample, n_total, args.steps, scale)},
+        "e2e": {"value": value, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_gmm(args):
+    from bayespy_b200 import _bpk, parallel
+    world, rank = parallel.init_from_env()
+    be = _bpk.get()
+    cpus = parallel.bind_to_gpu_numa()
+    n_total = args.n if args.n != bench.N_TOTAL else 10_000_000
+    n0, n1 = parallel.shard_bounds(n_total, world, rank)
+    y, z0 = gmm_rows(n0, n1)
+    Q, nodes = build_gmm(y, z0)
+    plan = Q.plans[0]
+    steps, warmup = args.steps, max(args.warmup, 3)
+    Q.update(repeat=warmup, verbose=False)
+    parallel.barrier()
+    sampler = bench.ClockSampler(int(os.environ.get("LOCAL_RANK", "0")), args.clock_interval_ms)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    plan.kernel_timers = [be.timer_create() for _ in range(steps)]
+    plan._timer_pos = 0
+    t_all = be.timer_create()
+    parallel.barrier()
+    l0 = be.launch_count()
+    wall0 = time.perf_counter()
+    be.timer_record(t_all, 0)
+    Q.update(repeat=steps, verbose=False)
+    be.timer_record(t_all, 1)
+    be.sync()
+    wall = time.perf_counter() - wall0
+    launches = be.launch_count() - l0
+    ms_dev = be.timer_elapsed_ms(t_all)
+    parallel.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_max = float(np.max(parallel.allgather_scalar(max(ms_dev, 1e3 * wall))))
+    kern = [be.timer_elapsed_ms(t) for t in plan.kernel_timers[:plan._timer_pos]]
+    plan.kernel_timers = None
+    kern_avg = float(np.max(parallel.allgather_scalar(float(np.mean(kern)) if kern else float("nan"))))
+    L_last = float(Q.L[Q.iter - 1])
+
+    # e2e: rows in from pinned host memory, bound out, every step
+    import ctypes
+    e2e_steps = max(10, args.e2e_steps)
+    hptr = be.host_alloc(y.nbytes)
+    pinned = np.ctypeslib.as_array((ctypes.c_double * y.size).from_address(hptr)).reshape(y.shape)
+    pinned[...] = y
+    Y = nodes["Y"]
+    for _ in range(2):
+        Y.observe(pinned)
+        Q.update(repeat=1, verbose=False)
+    e2e_t = []
+    for _ in range(e2e_steps):
+        parallel.barrier()
+        t0 = time.perf_counter()
+        Y.observe(pinned)
+        Q.update(repeat=1, verbose=False)
+        _ = float(Q.L[Q.iter - 1])
+        be.sync()
+        e2e_t.append(time.perf_counter() - t0)
+    e2e_mat = np.array([parallel.allgather_scalar(t) for t in e2e_t])
+    e2e_s = float(np.median(e2e_mat.max(axis=1)))
+    be.host_free(hptr)
+    if rank != 0:
+        return
+    hbm_peak, peak_src = bench.load_peaks()
+    n_loc = parallel.shard_bounds(n_total, world, 0)[1]
+    tf_alg = GMM_FLOPS_PER_ROW * n_loc / (kern_avg * 1e-3) / 1e12
+    line = {
+        "metric": "VB iterations/sec on GMM N=%d D=8 K=64" % n_total, "value": steps / (ms_max * 1e-3), "unit": "it/s",
+        "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_max / steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "Gaussian mixture N=%d D=8 K=64 (gmm.rst:71-98; Mixture + Gaussian + Wishart + Dirichlet), one VB "
+                               "sweep over [mu, Lambda, Z, alpha] incl. lower bound" % n_total,
+                   "n_total": n_total, "n_per_gpu": n_loc, "parallelism": "plate-shard x%d" % world,
+                   "l2": "inputs (%.2f GB of y + %.2f GB of responsibilities per GPU) larger than the 126 MB L2; no flush"
+                         % (y.nbytes / 1e9, y.shape[0] * GMM_K * 8 / 1e9),
+                   "lower_bound_last": L_last, "device_ms_per_step": ms_dev / steps, "host_wall_ms_per_step": 1e3 * wall / steps},
+        "clocks": clocks,
+        "e2e": {"value": 1.0 / e2e_s, "unit": "it/s", "h2d_bytes_per_step": int(y.nbytes), "d2h_bytes_per_step": 8 * len(Q.model),
+                "steps": e2e_steps, "statistic": "median over steps of the max over ranks",
+                "numa_bound_cpus": (len(cpus) if cpus else None)},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "achieved": tf_alg, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
+                     "frac": tf_alg / FP64_DMMA_PEAK_TFLOPS, "traffic": None,
+                     "kernel": "gmm_sweep_dmma_kernel (E-step + statistics, one pass over y)", "kernel_ms": kern_avg,
+                     "kernel_share_of_step": kern_avg / (ms_max / steps),
+                     "peak_source": "fp64 tensor pipe (DMMA.8x8x4), measured with tools/ubench_dmma_occ.cu: 36.9 TFLOP/s "
+                                    "(MEASURED_PEAKS.json has no fp64 figure)",
+                     "algorithmic_flops_per_row": GMM_FLOPS_PER_ROW, "executed_flops_per_row": GMM_EXEC_FLOPS_PER_ROW,
+                     "fp64_tflops_executed": GMM_EXEC_FLOPS_PER_ROW * n_loc / (kern_avg * 1e-3) / 1e12,
+                     "hbm_gbs": GMM_BYTES_PER_ROW * n_loc / (kern_avg * 1e-3) / 1e9, "hbm_peak_gbs": hbm_peak,
+                     "hbm_frac": GMM_BYTES_PER_ROW * n_loc / (kern_avg * 1e-3) / 1e9 / hbm_peak,
+                     "algorithmic_bytes_per_row": GMM_BYTES_PER_ROW, "hbm_peak_source": peak_src},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            n_sample = 4000
+            dt = gmm_reference_seconds(n_sample, 2, 1)
+            scale = n_total / n_sample
+            line["cpu_baseline"] = {
+                "value": 1.0 / (dt * scale), "unit": "it/s", "cores": bench.blas_threads(), "kind": "reference",
+                "sample": "unmodified reference package (oracle/_ref) on the first %d of %d rows of the same data, 2 timed sweeps "
+                          "(%.2f s each), extrapolated linearly (x%.0f); the reference's (N,K,D,D) temporaries cap it near 1e5 rows"
+                          % (n_sample, n_total, dt, scale)}
+        except Exception as e:
+            line["cpu_baseline"] = {"unavailable": str(e)}
+    print(json.dumps(line), flush=True)
+
+
+# =============================================================================================
+PM_BYTES_PER_COL = 64 * 8 + 64 + 16 * 8          # y + byte mask + x out = 704 B (variant (ii))
+PM_EXEC_FLOPS_PER_COL = 76 * 512 + 3000          # 76 DMMA.8x8x4 + ~3 kflop of per-column DFMA (symmetric half only)
+PM_ALG_FLOPS_PER_COL = 75000                     # SURVEY 8d figure (full K x K contractions)
+
+
+def masked_mask(n0, n1, p=0.8, seed=1):
+    """Observation mask of columns [n0, n1) (bayespy.utils.random.mask pattern: Bernoulli(p)), block-seeded."""
+    B = bench.BLOCK
+    out = np.empty((bench.M_DIM, n1 - n0), dtype=bool)
+    for blk in range(n0 // B, (max(n1, n0 + 1) - 1) // B + 1):
+        c0 = blk * B
+        mb = np.random.default_rng([seed, 11, blk]).random((bench.M_DIM, B)) < p
+        lo, hi = max(c0, n0), min(c0 + B, n1)
+        if hi > lo:
+            out[:, lo - n0:hi - n0] = mb[:, lo - c0:hi - c0]
+    return out
+
+
+def masked_reference_seconds(n_sample, steps, warmup):
+    from oracle import make_ref, ref_models
+    if not make_ref.available():
+        raise RuntimeError("oracle/_ref not staged")
+    y = bench.synth_shard(bench.M_DIM, 0, n_sample, 1)
+    Q, _ = ref_models.pca(y, bench.K_DIM, bench.init_C(bench.M_DIM, bench.K_DIM), mask=masked_mask(0, n_sample))
+    return ref_models.time_sweeps(Q, steps, warmup)
+
+
+def run_pca_masked(args):
+    from bayespy_b200 import _bpk, parallel
+    from bayespy_b200.nodes import GaussianARD, Gamma, SumMultiply
+    from bayespy_b200.inference import VB
+    world, rank = parallel.init_from_env()
+    be = _bpk.get()
+    cpus = parallel.bind_to_gpu_numa()
+    n_total = args.n
+    n0, n1 = parallel.shard_bounds(n_total, world, rank)
+    y = bench.synth_shard(bench.M_DIM, n0, n1, 1)
+    mask = masked_mask(n0, n1)
+    M, N = y.shape
+    K = bench.K_DIM
+    X = GaussianARD(0, 1, plates=(1, N), shape=(K,), name="X")
+    alpha = Gamma(1e-5, 1e-5, plates=(K,), name="alpha")
+    C = GaussianARD(0, alpha, plates=(M, 1), shape=(K,), name="C")
+    F = SumMultiply("d,d->", X, C, name="F")
+    tau = Gamma(1e-5, 1e-5, name="tau")
+    Y = GaussianARD(F, tau, name="Y")
+    Y.observe(y, mask=mask)
+    C.initialize_from_value(bench.init_C(M, K))
+    Q = VB(Y, X, C, alpha, tau)
+    Q.ignore_bound_checks = True
+    plan = Q.plans[0]
+    steps, warmup = args.steps, max(args.warmup, 3)
+    Q.update(repeat=warmup, verbose=False)
+    assert plan.masked() and plan.fused_calls > 0
+    parallel.barrier()
+    sampler = bench.ClockSampler(int(os.environ.get("LOCAL_RANK", "0")), args.clock_interval_ms)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    plan.kernel_timers = [be.timer_create() for _ in range(steps)]
+    plan._timer_pos = 0
+    t_all = be.timer_create()
+    parallel.barrier()
+    l0 = be.launch_count()
+    wall0 = time.perf_counter()
+    be.timer_record(t_all, 0)
+    Q.update(repeat=steps, verbose=False)
+    be.timer_record(t_all, 1)
+    be.sync()
+    wall = time.perf_counter() - wall0
+    launches = be.launch_count() - l0
+    ms_dev = be.timer_elapsed_ms(t_all)
+    parallel.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_max = float(np.max(parallel.allgather_scalar(max(ms_dev, 1e3 * wall))))
+    kern = [be.timer_elapsed_ms(t) for t in plan.kernel_timers[:plan._timer_pos]]
+    plan.kernel_timers = None
+    kern_avg = float(np.max(parallel.allgather_scalar(float(np.mean(kern)) if kern else float("nan"))))
+    L_last = float(Q.L[Q.iter - 1])
+    # e2e: data and mask in from the host every step
+    e2e_t = []
+    for _ in range(max(5, args.e2e_steps // 2)):
+        parallel.barrier()
+        t0 = time.perf_counter()
+        Y.observe(y, mask=mask)
+        Q.update(repeat=1, verbose=False)
+        _ = float(Q.L[Q.iter - 1])
+        be.sync()
+        e2e_t.append(time.perf_counter() - t0)
+    e2e_s = float(np.median(np.array([parallel.allgather_scalar(t) for t in e2e_t]).max(axis=1)))
+    if rank != 0:
+        return
+    hbm_peak, peak_src = bench.load_peaks()
+    n_loc = parallel.shard_bounds(n_total, world, 0)[1]
+    tf = PM_EXEC_FLOPS_PER_COL * n_loc / (kern_avg * 1e-3) / 1e12
+    line = {
+        "metric": "VB iterations/sec on masked PCA N=%d D=64 K=16 (80 %% observed)" % n_total, "value": steps / (ms_max * 1e-3),
+        "unit": "it/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_max / steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "Bayesian PCA N=%d M=64 K=16 with missing values (random.mask p=0.8; per-column precision), one VB "
+                               "sweep over [Y, X, C, alpha, tau] incl. lower bound" % n_total,
+                   "n_total": n_total, "n_per_gpu": n_loc, "parallelism": "plate-shard x%d" % world,
+                   "l2": "inputs (%.2f GB of Y per GPU) larger than the 126 MB L2; no flush" % (y.nbytes / 1e9),
+                   "lower_bound_last": L_last, "device_ms_per_step": ms_dev / steps, "host_wall_ms_per_step": 1e3 * wall / steps},
+        "clocks": clocks,
+        "e2e": {"value": 1.0 / e2e_s, "unit": "it/s", "h2d_bytes_per_step": int(y.nbytes + mask.nbytes),
+                "d2h_bytes_per_step": 8 * len(Q.model), "numa_bound_cpus": (len(cpus) if cpus else None)},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "achieved": tf, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": tf / FP64_DMMA_PEAK_TFLOPS,
+                     "traffic": None, "kernel": "bpk_pca_xsweep_masked_fused (build / inverse / stats kernels per chunk of columns)",
+                     "kernel_ms": kern_avg, "kernel_share_of_step": kern_avg / (ms_max / steps),
+                     "executed_flops_per_col": PM_EXEC_FLOPS_PER_COL, "survey_flops_per_col": PM_ALG_FLOPS_PER_COL,
+                     "note": "achieved counts the flops the kernels execute (symmetric half of the K x K contractions: 76 DMMA + ~3 kflop "
+                             "DFMA per column); SURVEY 8d's 75 kflop/col assumes the full contractions",
+                     "peak_source": "fp64 tensor pipe (DMMA.8x8x4), tools/ubench_dmma_occ.cu: 36.9 TFLOP/s",
+                     "hbm_gbs": PM_BYTES_PER_COL * n_loc / (kern_avg * 1e-3) / 1e9, "hbm_peak_gbs": hbm_peak,
+                     "algorithmic_bytes_per_col": PM_BYTES_PER_COL, "hbm_peak_source": peak_src},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            n_sample = 5000
+            dt = masked_reference_seconds(n_sample, 2, 1)
+            line["cpu_baseline"] = {"value": 1.0 / (dt * n_total / n_sample), "unit": "it/s", "cores": bench.blas_threads(),
+                                    "kind": "reference",
+                                    "sample": "unmodified reference package (oracle/_ref), same model and mask on the first %d of %d columns, "
+                                              "2 timed sweeps (%.2f s each: per-column SciPy Cholesky loops), extrapolated linearly (x%.0f)"
+                                              % (n_sample, n_total, dt, n_total / n_sample)}
+        except Exception as e:
+            line["cpu_baseline"] = {"unavailable": str(e)}
+    print(json.dumps(line), flush=True)
+
+
+# =============================================================================================
+def lssm_data(T, M, seed=0):
+    """lssm.rst:153-175 pattern: two noisy rotators observed through random loadings, obs. noise sigma = 3."""
+    rs = np.random.RandomState(seed)
+    w = 0.05
+    a = np.array([[np.cos(w), -np.sin(w), 0, 0], [np.sin(w), np.cos(w), 0, 0],
+                  [0, 0, np.cos(3 * w), -np.sin(3 * w)], [0, 0, np.sin(3 * w), np.cos(3 * w)]])
+    x = np.empty((T, 4))
+    x[0] = rs.randn(4)
+    noise = 0.1 * rs.randn(T, 4)
+    for n in range(T - 1):
+        x[n + 1] = a @ x[n] + noise[n]
+    c = rs.randn(M, 4)
+    return c @ x.T + 3.0 * rs.randn(M, T)
+
+
+def build_lssm(y, Dm, mod):
+    """lssm.rst:45-141: X = GaussianMarkovChain(0, 1e-3 I, A, 1, n=T), F = Dot(C, X), Y = GaussianARD(F, tau)."""
+    GaussianARD, GaussianMarkovChain, Gamma, Dot, VB = mod
+    M, T = y.shape
+    alpha = Gamma(1e-5, 1e-5, plates=(Dm,), name="alpha")
+    A = GaussianARD(0, alpha, shape=(Dm,), plates=(Dm,), name="A")
+    X = GaussianMarkovChain(np.zeros(Dm), 1e-3 * np.identity(Dm), A, np.ones(Dm), n=T, name="X")
+    gamma = Gamma(1e-5, 1e-5, plates=(Dm,), name="gamma")
+    C = GaussianARD(0, gamma, shape=(Dm,), plates=(M, 1), name="C")
+    F = Dot(C, X, name="F")
+    C.initialize_from_value(np.random.RandomState(1).randn(M, 1, Dm))
+    tau = Gamma(1e-5, 1e-5, name="tau")
+    Y = GaussianARD(F, tau, name="Y")
+    Y.observe(y)
+    Q = VB(X, C, gamma, A, alpha, tau, Y)
+    Q.ignore_bound_checks = True
+    return Q, Y
+
+
+def lssm_reference_seconds(T, Dm, M, steps, warmup):
+    from oracle import make_ref, ref_models
+    make_ref.import_reference()
+    from bayespy.nodes import GaussianARD, GaussianMarkovChain, Gamma, Dot
+    from bayespy.inference import VB
+    Q, _ = build_lssm(lssm_data(T, M), Dm, (GaussianARD, GaussianMarkovChain, Gamma, Dot, VB))
+    return ref_models.time_sweeps(Q, steps, warmup)
+
+
+def run_lssm(args):
+    from bayespy_b200 import _bpk, parallel
+    from bayespy_b200.nodes import GaussianARD, GaussianMarkovChain, Gamma, Dot
+    from bayespy_b200.inference import VB
+    world, rank = parallel.init_from_env()
+    be = _bpk.get()
+    T, Dm, M = (args.n if args.n != bench.N_TOTAL else 100_000), 32, 256
+    y = lssm_data(T, M)                               # every rank runs the same replica (the path does not shard over T)
+    Q, Y = build_lssm(y, Dm, (GaussianARD, GaussianMarkovChain, Gamma, Dot, VB))
+    steps, warmup = args.steps, max(args.warmup, 3)
+    Q.update(repeat=warmup, verbose=False)
+    parallel.barrier()
+    sampler = bench.ClockSampler(int(os.environ.get("LOCAL_RANK", "0")), args.clock_interval_ms)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    t_all = be.timer_create()
+    l0 = be.launch_count()
+    wall0 = time.perf_counter()
+    be.timer_record(t_all, 0)
+    Q.update(repeat=steps, verbose=False)
+    be.timer_record(t_all, 1)
+    be.sync()
+    wall = time.perf_counter() - wall0
+    launches = be.launch_count() - l0
+    ms_dev = be.timer_elapsed_ms(t_all)
+    parallel.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_max = float(np.max(parallel.allgather_scalar(max(ms_dev, 1e3 * wall))))
+    e2e_t = []
+    for _ in range(max(5, args.e2e_steps // 2)):
+        t0 = time.perf_counter()
+        Y.observe(y)
+        Q.update(repeat=1, verbose=False)
+        _ = float(Q.L[Q.iter - 1])
+        be.sync()
+        e2e_t.append(time.perf_counter() - t0)
+    e2e_s = float(np.median(e2e_t))
+    if rank != 0:
+        return
+    # algorithmic traffic of one iteration: the chain's moments and natural parameters (u1, u2, phi1, phi2: 4 T D^2 doubles)
+    # are written and read once each by the smoother and by the messages; the observations M T once per message pass
+    bytes_iter = (8 * T * Dm * Dm + 4 * M * T) * 8
+    hbm_peak, peak_src = bench.load_peaks()
+    line = {
+        "metric": "VB iterations/sec on LSSM T=%d D=32 M=256" % T, "value": world * steps / (ms_max * 1e-3), "unit": "it/s",
+        "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_max / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "linear state-space model T=%d D=32 M=256 (lssm.rst:45-181 scaled up; GaussianMarkovChain + Dot), one "
+                               "VB iteration over [X, C, gamma, A, alpha, tau] incl. lower bound" % T,
+                   "parallelism": "replicas only x%d (the smoother does not shard over time; SURVEY 8e)" % world,
+                   "lower_bound_last": float(Q.L[Q.iter - 1]), "launches_per_iteration": launches / steps},
+        "clocks": clocks,
+        "e2e": {"value": 1.0 / e2e_s, "unit": "it/s", "h2d_bytes_per_step": int(y.nbytes), "d2h_bytes_per_step": 8 * len(Q.model)},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": bytes_iter / (ms_max / steps * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": bytes_iter / (ms_max / steps * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                     "kernel": "whole iteration (block cyclic reduction smoother + GEMM-shaped messages + node kernels)",
+                     "kernel_ms": ms_max / steps, "peak_source": peak_src,
+                     "note": "algorithmic bytes per iteration = (8 T D^2 + 4 M T) doubles; per-kernel numbers in profiles/"},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            Ts = 2000
+            dt = lssm_reference_seconds(Ts, Dm, M, 1, 1)
+            line["cpu_baseline"] = {"value": 1.0 / (dt * T / Ts), "unit": "it/s", "cores": bench.blas_threads(), "kind": "reference",
+                                    "sample": "unmodified reference package (oracle/_ref), same model at T=%d (%.1f s per iteration), "
+                                              "extrapolated linearly in T (x%.0f): its smoother is a Python loop over time steps"
+                                              % (Ts, dt, T / Ts)}
+        except Exception as e:
+            line["cpu_baseline"] = {"unavailable": str(e)}
+    print(json.dumps(line), flush=True)

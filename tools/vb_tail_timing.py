@@ -16,15 +16,15 @@ world, rank = parallel.init_from_env()
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000      # columns PER RANK
 y = bench.synth_shard(64, rank * N, (rank + 1) * N, 1)
 Q, nodes = bench.build_model(y)
-Q.update(repeat=5, verbose=False)
+Q.update(repeat=int(os.environ.get("TAIL_SWEEPS", "5")), verbose=False)
 be = _bpk.get()
 s = be.debug_stamps(64)
 parallel.barrier()
 if rank != 0:
     sys.exit(0)
 t0 = s[0]
-names = {1: "data pass done (CTA 0)", 2: "after grid barrier 1", 3: "CTA 0 reduction share done", 4: "after grid barrier 2",
-         5: "tail done"}
+names = {1: "data pass done (CTA 0)", 2: "after grid barrier 1", 3: "CTA 0 reduction share / push done",
+         4: "tail starts (after grid barrier 2, if any)", 5: "tail done"}
 print("N=%d: stamps relative to kernel start (us)" % N)
 for i in (1, 2, 3, 4):
     print("  %-32s %10.2f" % (names[i], (s[i] - t0) / 1e3))
@@ -42,9 +42,8 @@ for i, op in enumerate(tail):
     print("  op %-6s %10.2f us" % (opn[op], (nxt - st) / 1e3))
 if s[6] > s[4]:
     print("  dry run (cold) before the real ops %8.2f us ; real ops (warm) %8.2f us" % ((s[6] - s[4]) / 1e3, (s[5] - s[6]) / 1e3))
-if world > 1:
-    print("  p2p windows open: %s ; raw stamps 40..43: %s" % (parallel._state.get("p2p"), s[40:44]))
-    print("  exchange: deposit+fence %.2f us, wait for flags %.2f us, sum %.2f us"
-          % ((s[41] - s[40]) / 1e3, (s[42] - s[41]) / 1e3, (s[43] - s[42]) / 1e3))
+if s[40] and s[42]:
+    print("  p2p windows open: %s ; exchange inside STATS: push (single-CTA path only) %.2f us, gather %.2f us"
+          % (parallel._state.get("p2p"), (s[41] - s[40]) / 1e3, (s[42] - s[41]) / 1e3))
 print("  %-32s %10.2f" % (names[5], (s[5] - t0) / 1e3))
 print("  tail total (after data pass)     %10.2f" % ((s[5] - s[1]) / 1e3))
