@@ -66,6 +66,17 @@ __device__ __forceinline__ void pm_pack_mask(const uint8_t *__restrict__ mask, i
     __syncthreads();
 }
 
+#define PM_LDY 132                        // pitch of the staged Y tile (= 4 mod 16: conflict-free fragment loads)
+
+// Y[0:64, n0:n0+128] -> shared memory (zero beyond M / N); every load is independent, so the whole tile is in flight
+__device__ __forceinline__ void pm_stage_y(const double *__restrict__ Y, int64_t M, int64_t N, int64_t n0, double *sY) {
+    for (int e = threadIdx.x; e < PM_MP * PM_TILE; e += blockDim.x) {
+        const int m = e / PM_TILE, c = e - m * PM_TILE;
+        const int64_t n = n0 + c;
+        sY[m * PM_LDY + c] = (m < M && n < N) ? __ldg(Y + (int64_t)m * N + n) : 0.0;
+    }
+}
+
 struct PmArgs {
     const double *Y;
     const uint8_t *mask;
@@ -84,6 +95,8 @@ struct PmArgs {
 // ---- build: rows 0..151 of the scratch for every column of the chunk ------------------------------------------
 __global__ void __launch_bounds__(PM_THREADS, 1) pmask_build_kernel(PmArgs a) {
     __shared__ unsigned long long bits[PM_TILE];
+    extern __shared__ __align__(16) double pm_smem[];
+    double *sY = pm_smem;                              // [64][PM_LDY]: the tile's observations (operand of the phi rows)
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, gr = lane >> 2, tg = lane & 3;
     const int M = (int)a.M, K = a.K;
     // A fragments of this warp's row tile (constant over the sweep): T[p][m] = tau <ww^T>[m][ij(p)]  or  tau <w>[m][k]
@@ -113,6 +126,7 @@ __global__ void __launch_bounds__(PM_THREADS, 1) pmask_build_kernel(PmArgs a) {
         const int64_t cl0 = tile * PM_TILE;            // first column of the tile inside the chunk
         const int64_t n0 = a.c0 + cl0;
         __syncthreads();
+        pm_stage_y(a.Y, a.M, a.N, n0, sY);
         pm_pack_mask(a.mask, a.M, a.N, n0, bits);
         // 16 column tiles of 8, four at a time (4 independent DMMA chains)
 #pragma unroll 1
@@ -138,9 +152,8 @@ __global__ void __launch_bounds__(PM_THREADS, 1) pmask_build_kernel(PmArgs a) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const int m = ks * 4 + tg;
-                        const int64_t n = n0 + (nq * 4 + q) * 8 + gr;
                         const bool on = (wd[q] >> m) & 1ull;
-                        const double b = on ? __ldg(a.Y + (int64_t)m * a.N + n) : 0.0;
+                        const double b = on ? sY[m * PM_LDY + (nq * 4 + q) * 8 + gr] : 0.0;
                         pm_dmma(acc[q][0], acc[q][1], af[ks], b);
                     }
             }
@@ -162,7 +175,7 @@ struct PmColAcc {
     __device__ __forceinline__ void st(int row, double v) { base[(int64_t)row * pitch] = v; }
 };
 
-__global__ void __launch_bounds__(128) pmask_inverse_kernel(PmArgs a) {
+__device__ __forceinline__ void pmask_inverse_body(const PmArgs &a) {
     const int64_t cl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (cl >= a.nc) return;
     PmColAcc acc{a.S + cl, a.chp};
@@ -173,11 +186,17 @@ __global__ void __launch_bounds__(128) pmask_inverse_kernel(PmArgs a) {
     acc.st(SPD16_G, q);
     acc.st(SPD16_G + 1, ld);
 }
+// two register budgets: 255 registers / 8 warps per SM, or 128 registers / 16 warps per SM (more spills to L1, twice
+// the threads to hide the latency of the dependent chains); BPK_PMASK_INV_REGS=128 selects the latter
+__global__ void __launch_bounds__(128, 2) pmask_inverse_kernel(PmArgs a) { pmask_inverse_body(a); }
+__global__ void __launch_bounds__(128, 4) pmask_inverse128_kernel(PmArgs a) { pmask_inverse_body(a); }
 
 // ---- stats: masked plate sums + store of X -------------------------------------------------------------------------
 __global__ void __launch_bounds__(PM_THREADS, 1) pmask_stats_kernel(PmArgs a, int first_chunk) {
     __shared__ unsigned long long bits[PM_TILE];
     __shared__ double red[PM_WARPS][2];
+    extern __shared__ __align__(16) double pm_smem[];
+    double *sY = pm_smem;                              // [64][PM_LDY]: the tile's observations (operand of the S_yx rows)
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, gr = lane >> 2, tg = lane & 3;
     const int K = a.K;
     const bool is_x = w >= 17;                         // row tiles 17, 18 of the scratch hold x (S_yx), the others <xx^T>
@@ -190,29 +209,45 @@ __global__ void __launch_bounds__(PM_THREADS, 1) pmask_stats_kernel(PmArgs a, in
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t cl0 = tile * PM_TILE;
         const int64_t n0 = a.c0 + cl0;
-        __syncthreads();
-        pm_pack_mask(a.mask, a.M, a.N, n0, bits);
         const double *Srow = a.S + (int64_t)(w * 8 + gr) * a.chp + cl0;       // B operand: scratch row p, columns of the tile
-#pragma unroll 4
-        for (int ks = 0; ks < PM_TILE / 4; ++ks) {
-            const int c = ks * 4 + tg;
-            const int64_t n = n0 + c;
-            const double b = (n < a.N) ? Srow[c] : 0.0;
-            colsum += b;
-            const unsigned long long wd = bits[c];
-            if (!is_x) {
+        // the B fragments of the first 8 k-steps are requested before anything else (they come from L2)
+        double bnext[8];
 #pragma unroll
-                for (int mt = 0; mt < 8; ++mt) {
-                    const double av = ((wd >> (mt * 8 + gr)) & 1ull) ? 1.0 : 0.0;
-                    pm_dmma(acc[mt][0], acc[mt][1], av, b);
+        for (int u = 0; u < 8; ++u) bnext[u] = (n0 + u * 4 + tg < a.N) ? Srow[u * 4 + tg] : 0.0;
+        __syncthreads();
+        pm_stage_y(a.Y, a.M, a.N, n0, sY);
+        pm_pack_mask(a.mask, a.M, a.N, n0, bits);
+#pragma unroll 1
+        for (int kg = 0; kg < PM_TILE / 32; ++kg) {
+            double bcur[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) bcur[u] = bnext[u];
+            if (kg + 1 < PM_TILE / 32) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int c = (kg + 1) * 32 + u * 4 + tg;
+                    bnext[u] = (n0 + c < a.N) ? Srow[c] : 0.0;
                 }
-            } else {
+            }
 #pragma unroll
-                for (int mt = 0; mt < 8; ++mt) {
-                    const int m = mt * 8 + gr;
-                    const bool on = (wd >> m) & 1ull;
-                    const double av = on ? __ldg(a.Y + (int64_t)m * a.N + n) : 0.0;
-                    pm_dmma(acc[mt][0], acc[mt][1], av, b);
+            for (int u = 0; u < 8; ++u) {
+                const int c = kg * 32 + u * 4 + tg;
+                const double b = bcur[u];
+                colsum += b;
+                const unsigned long long wd = bits[c];
+                if (!is_x) {
+#pragma unroll
+                    for (int mt = 0; mt < 8; ++mt) {
+                        const double av = ((wd >> (mt * 8 + gr)) & 1ull) ? 1.0 : 0.0;
+                        pm_dmma(acc[mt][0], acc[mt][1], av, b);
+                    }
+                } else {
+#pragma unroll
+                    for (int mt = 0; mt < 8; ++mt) {
+                        const int m = mt * 8 + gr;
+                        const double av = ((wd >> m) & 1ull) ? sY[m * PM_LDY + c] : 0.0;
+                        pm_dmma(acc[mt][0], acc[mt][1], av, b);
+                    }
                 }
             }
         }
@@ -301,7 +336,7 @@ extern "C" int bpk_pca_xsweep_masked_fused(const double *Y, const uint8_t *mask,
         return bpk_set_error(BPK_EINVAL, "bpk_pca_xsweep_masked_fused: null argument");
     if (N == 0) return BPK_OK;
     const int grid = g_bpk.sm_count;
-    int tiles_per_cta = 2;
+    int tiles_per_cta = 4;
     if (const char *e = getenv("BPK_PMASK_CHUNK_TILES")) { tiles_per_cta = atoi(e); if (tiles_per_cta < 1) tiles_per_cta = 1; }
     int64_t chunk = (int64_t)grid * tiles_per_cta * PM_TILE;
     if (chunk > ((N + PM_TILE - 1) / PM_TILE) * PM_TILE) chunk = ((N + PM_TILE - 1) / PM_TILE) * PM_TILE;
@@ -318,18 +353,24 @@ extern "C" int bpk_pca_xsweep_masked_fused(const double *Y, const uint8_t *mask,
     a.S = g_pm_scratch; a.chp = chunk; a.X = X; a.g = g;
     a.partial = g_pm_scratch + (size_t)SPD16_ROWS * chunk;
     a.flag = g_bpk.d_flag;
+    const size_t ysm = (size_t)PM_MP * PM_LDY * sizeof(double);
+    BPK_CUDA(cudaFuncSetAttribute(pmask_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ysm));
+    BPK_CUDA(cudaFuncSetAttribute(pmask_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ysm));
+    const char *ir = getenv("BPK_PMASK_INV_REGS");
+    const bool inv255 = !(ir && atoi(ir) == 128);
     int first = 1;
     for (int64_t c0 = 0; c0 < N; c0 += chunk) {
         a.c0 = c0;
         a.nc = (N - c0 < chunk) ? N - c0 : chunk;
         const int64_t ntiles = (a.nc + PM_TILE - 1) / PM_TILE;
         const int gtiles = (int)(ntiles < grid ? ntiles : grid);
-        BPK_LAUNCH(pmask_build_kernel, gtiles, PM_THREADS, 0, a);
+        BPK_LAUNCH(pmask_build_kernel, gtiles, PM_THREADS, ysm, a);
         // the inverse runs on whole tiles: padded columns of the last tile hold the prior precision (SPD), results unused
         PmArgs b = a;
         b.nc = ntiles * PM_TILE;
-        BPK_LAUNCH(pmask_inverse_kernel, (unsigned)((b.nc + 127) / 128), 128, 0, b);
-        BPK_LAUNCH(pmask_stats_kernel, grid, PM_THREADS, 0, a, first);
+        if (inv255) BPK_LAUNCH(pmask_inverse_kernel, (unsigned)((b.nc + 127) / 128), 128, 0, b);
+        else BPK_LAUNCH(pmask_inverse128_kernel, (unsigned)((b.nc + 127) / 128), 128, 0, b);
+        BPK_LAUNCH(pmask_stats_kernel, grid, PM_THREADS, ysm, a, first);
         first = 0;
     }
     const int total = (int)(M * K + M * K * K + (int64_t)K * K + K + 2);

@@ -147,6 +147,8 @@ struct GemmArgs {
     int64_t sAm, sAk, sBk, sBn, sCm, sCn;
     double scale;
     int accumulate;
+    int64_t kchunk;            // split-K: CTA z contracts k in [z*kchunk, (z+1)*kchunk) into partial slab z of `part`
+    double *part;              // [nsplit][M][N] (NULL: single pass straight into C)
 };
 #define GM_BM 64
 #define GM_BN 64
@@ -178,17 +180,19 @@ __global__ void __launch_bounds__(128, 2) dgemm_dmma_kernel(GemmArgs g) {
     auto brow = [&](int e) { return b_kfast ? e / GM_BK : e % GM_BN; };
     auto bcol = [&](int e) { return b_kfast ? e % GM_BK : e / GM_BN; };
     double ra[PT], rb[PT];
+    const int64_t kbeg = (int64_t)blockIdx.z * g.kchunk;
+    const int64_t kend = (kbeg + g.kchunk < g.K) ? kbeg + g.kchunk : g.K;
     auto fetch = [&](int64_t k0) {
 #pragma unroll
         for (int q = 0; q < PT; ++q) {
             const int e = t + q * 128;
             const int64_t mm = m0 + arow(e), ka = k0 + acol(e), nn = n0 + brow(e), kb = k0 + bcol(e);
-            ra[q] = (mm < g.M && ka < g.K) ? g.A[mm * g.sAm + ka * g.sAk] : 0.0;
-            rb[q] = (nn < g.N && kb < g.K) ? g.B[kb * g.sBk + nn * g.sBn] : 0.0;
+            ra[q] = (mm < g.M && ka < kend) ? g.A[mm * g.sAm + ka * g.sAk] : 0.0;
+            rb[q] = (nn < g.N && kb < kend) ? g.B[kb * g.sBk + nn * g.sBn] : 0.0;
         }
     };
-    fetch(0);
-    for (int64_t k0 = 0; k0 < g.K; k0 += GM_BK) {
+    fetch(kbeg);
+    for (int64_t k0 = kbeg; k0 < kend; k0 += GM_BK) {
 #pragma unroll
         for (int q = 0; q < PT; ++q) {
             const int e = t + q * 128;
@@ -196,7 +200,7 @@ __global__ void __launch_bounds__(128, 2) dgemm_dmma_kernel(GemmArgs g) {
             Bs[brow(e) * GM_LD + bcol(e)] = rb[q];
         }
         __syncthreads();
-        if (k0 + GM_BK < g.K) fetch(k0 + GM_BK);
+        if (k0 + GM_BK < kend) fetch(k0 + GM_BK);
 #pragma unroll
         for (int ks = 0; ks < GM_BK; ks += 4) {
             double af[4], bf[4];
@@ -219,11 +223,29 @@ __global__ void __launch_bounds__(128, 2) dgemm_dmma_kernel(GemmArgs g) {
             for (int q = 0; q < 2; ++q) {
                 const int64_t m = m0 + wm + i * 8 + gr, n = n0 + wn + j * 8 + 2 * tg + q;
                 if (m < g.M && n < g.N) {
-                    double *c = g.C + m * g.sCm + n * g.sCn;
-                    const double v = g.scale * acc[i][j][q];
-                    *c = g.accumulate ? *c + v : v;
+                    if (g.part) {
+                        g.part[((int64_t)blockIdx.z * g.M + m) * g.N + n] = acc[i][j][q];
+                    } else {
+                        double *c = g.C + m * g.sCm + n * g.sCn;
+                        const double v = g.scale * acc[i][j][q];
+                        *c = g.accumulate ? *c + v : v;
+                    }
                 }
             }
+}
+
+// split-K epilogue: C (+)= scale * sum_z part[z] in a fixed order (deterministic)
+__global__ void __launch_bounds__(256) dgemm_splitk_final_kernel(GemmArgs g, int nsplit) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = g.M * g.N;
+    for (; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t m = e / g.N, n = e - m * g.N;
+        double s = 0.0;
+        for (int z = 0; z < nsplit; ++z) s += g.part[(int64_t)z * total + e];
+        double *c = g.C + m * g.sCm + n * g.sCn;
+        const double v = g.scale * s;
+        *c = g.accumulate ? *c + v : v;
+    }
 }
 
 extern "C" int bpk_sum_multiply(int nd, const int64_t *shape,
@@ -304,6 +326,28 @@ extern "C" int bpk_sum_multiply(int nd, const int64_t *shape,
             g.sCm = A.kout[im]; g.sCn = A.kout[in_];
             g.scale = A.scale; g.accumulate = accumulate;
             dim3 grid((unsigned)((g.N + GM_BN - 1) / GM_BN), (unsigned)((g.M + GM_BM - 1) / GM_BM));
+            // split-K when the output tiles cannot fill the machine and the contraction is long (e.g. the
+            // plate-summed messages of dot.py:581: 256 x 1024 outputs over 1e5 time steps): slabs of k, partial
+            // results to scratch, fixed-order epilogue
+            g.kchunk = g.K;
+            g.part = nullptr;
+            int nsplit = 1;
+            const int64_t ctas = (int64_t)grid.x * grid.y, want = 2 * (int64_t)g_bpk.sm_count;
+            if (ctas < want && g.K >= 4096 && !getenv("BPK_GEMM_NO_SPLITK")) {
+                nsplit = (int)((want + ctas - 1) / ctas);
+                const int64_t maxs = g.K / 1024;
+                if (nsplit > maxs) nsplit = (int)maxs;
+                if (nsplit > 64) nsplit = 64;
+                if (nsplit > 1) {
+                    int64_t kc = (g.K + nsplit - 1) / nsplit;
+                    kc = ((kc + GM_BK - 1) / GM_BK) * GM_BK;
+                    nsplit = (int)((g.K + kc - 1) / kc);
+                    g.kchunk = kc;
+                    g.part = bpk_scratch((size_t)nsplit * g.M * g.N * sizeof(double));
+                    if (!g.part) return bpk_set_error(BPK_ECUDA, "bpk_sum_multiply: scratch allocation failed");
+                    grid.z = nsplit;
+                }
+            }
             if (grid.y <= 65535u) {
                 static bool carve = false;
                 if (!carve) {     // several CTAs per SM: ask for the shared-memory carve-out up front
@@ -314,6 +358,11 @@ extern "C" int bpk_sum_multiply(int nd, const int64_t *shape,
                 g_bpk.launches++;
                 cudaError_t e_ = cudaPeekAtLastError();
                 if (e_ != cudaSuccess) return bpk_set_error(BPK_ECUDA, "launch of dgemm_dmma_kernel failed: %s", cudaGetErrorString(e_));
+                if (nsplit > 1) {
+                    int64_t fb = (g.M * g.N + 255) / 256;
+                    if (fb > (int64_t)g_bpk.sm_count * 8) fb = (int64_t)g_bpk.sm_count * 8;
+                    BPK_LAUNCH(dgemm_splitk_final_kernel, (unsigned)fb, 256, 0, g, nsplit);
+                }
                 return BPK_OK;
             }
         }

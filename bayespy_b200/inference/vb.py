@@ -49,6 +49,10 @@ class VB:
         self.L = np.array(())
         self.cputime = np.array(())
         self.l = {node: np.array([]) for node in self.model}
+        if autosave_iterations:
+            # vmp.py:237-356, 750-758 write HDF5 checkpoints; that on-disk format is not implemented here,
+            # so refuse loudly instead of silently never saving
+            raise NotImplementedError("autosave / VB.save / VB.load (HDF5 checkpoints) are not implemented in bayespy_b200")
         self.autosave_iterations = autosave_iterations
         self.autosave_filename = autosave_filename
         names = [node.name for node in self.model]
@@ -71,6 +75,12 @@ class VB:
             if node.name == name:
                 return node
         raise ValueError("Node %s not found" % (name,))
+
+    def save(self, *args, **kwargs):
+        raise NotImplementedError("VB.save (HDF5, vmp.py:237-330) is not implemented in bayespy_b200")
+
+    def load(self, *args, **kwargs):
+        raise NotImplementedError("VB.load (HDF5, vmp.py:332-356) is not implemented in bayespy_b200")
 
     def set_callback(self, callback):
         self.callback = callback

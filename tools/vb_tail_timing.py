@@ -45,5 +45,15 @@ if s[6] > s[4]:
 if s[40] and s[42]:
     print("  p2p windows open: %s ; exchange inside STATS: push (single-CTA path only) %.2f us, gather %.2f us"
           % (parallel._state.get("p2p"), (s[41] - s[40]) / 1e3, (s[42] - s[41]) / 1e3))
+if s[48] and s[56]:
+    # probe CTA (last of the grid), second-to-last sweep of the launch
+    b = s[48]
+    lab = [(49, "A fragments loaded (X-warp 0)"), (50, "first tile landed (X-warp 0)"), (51, "last tile done (X-warp 0)"),
+           (52, "last tile done (S-warp 0)"), (53, "CTA partial written"), (54, "after grid barrier 1"),
+           (55, "slice reduced + pushed"), (56, "after grid barrier 3 (next sweep may start)"), (57, "next sweep starts")]
+    print("  probe CTA %d, one steady-state sweep (us from its start):" % (-1))
+    for i, nm in lab:
+        if s[i]:
+            print("    %-44s %10.2f" % (nm, (s[i] - b) / 1e3))
 print("  %-32s %10.2f" % (names[5], (s[5] - t0) / 1e3))
 print("  tail total (after data pass)     %10.2f" % ((s[5] - s[1]) / 1e3))
