@@ -590,6 +590,206 @@ __global__ void __launch_bounds__(G2_PAIRS * 64, 1) gmm_sweep_dmma2_kernel(GmmAr
     }
 }
 
+// =====================================================================================
+// v3: sixteen warps of 128 registers instead of eight of 255 (the v2 profile shows the fp64 tensor pipe 58 % busy with
+// "wait" stalls on top: two warps per scheduler cannot cover each other's exp / softmax sections).  The warps form 4
+// QUADS; a quad owns a tile of 32 rows: each warp runs the E phase of 8 of them (96 DMMA), the quad meets at its own
+// named barrier (128 threads), then each warp contracts all 32 rows into a quarter of the statistics (32 components x
+// 24 features: 24 accumulators, 96 DMMA).
+// =====================================================================================
+#define G3_QUADS 4
+__device__ __forceinline__ void g3_quad_sync(int q) {
+    asm volatile("bar.sync %0, 128;\n" ::"r"(q + 1) : "memory");
+}
+
+__global__ void __launch_bounds__(G3_QUADS * 128, 1) gmm_sweep_dmma3_kernel(GmmArgs a) {
+    extern __shared__ __align__(16) double sm[];
+    double *sT = sm;                                                  // [64][52]  Theta
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5, gr = lane >> 2, tg = lane & 3;
+    const int qd = w >> 2, hf = w & 3;
+    double *sZ = sT + G1_KP * G1_LDZ + (size_t)qd * (G2_ROWS * G1_LDZ + G2_ROWS * G1_LDP);   // [32][52] this quad's features
+    double *sP = sZ + G2_ROWS * G1_LDZ;                                                       // [32][68] responsibilities
+    __shared__ double red[4 * G3_QUADS];
+    const int D = a.D, K = a.K;
+
+    for (int e = t; e < G1_KP * G1_FP; e += blockDim.x) {
+        const int k = e / G1_FP, f = e - k * G1_FP;
+        double v = 0.0;
+        if (k >= K) v = (f == 0) ? -1e300 : 0.0;        // padded components never win the softmax
+        else if (f == 0) v = a.c[k] + a.logpi[k];
+        else if (f <= G1_DP) v = (f - 1 < D) ? a.h[k * D + f - 1] : 0.0;
+        else if (f < G1_NF) {
+            int i, j;
+            g1_pair(f, i, j);
+            if (i < D && j < D)
+                v = (i == j) ? -0.5 * a.Lam[(k * D + i) * D + i]
+                             : -0.5 * (a.Lam[(k * D + i) * D + j] + a.Lam[(k * D + j) * D + i]);
+        }
+        sT[k * G1_LDZ + f] = v;
+    }
+    // this warp's quarter of the statistics: component blocks 4*(hf&1) .. +3, feature blocks 3*(hf>>1) .. +2
+    const int mb0 = 4 * (hf & 1), fb0 = 3 * (hf >> 1);
+    double acc[4][3][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    double lse_acc = 0.0;
+    __syncthreads();
+
+    const int64_t ntiles = (a.N + G2_ROWS - 1) / G2_ROWS;
+    const int64_t tstride = (int64_t)gridDim.x * G3_QUADS;
+    const int r0 = hf * 8;                               // this warp's rows inside the quad tile
+    const int part = lane & 3;                           // four lanes per row build 12 features each
+    double ynext[G1_DP];
+    {
+        const int64_t n = ((int64_t)blockIdx.x * G3_QUADS + qd) * G2_ROWS + r0 + (lane >> 2);
+#pragma unroll
+        for (int d = 0; d < G1_DP; ++d) ynext[d] = (n < a.N && d < D) ? a.Y[n * D + d] : 0.0;
+    }
+    for (int64_t tile = (int64_t)blockIdx.x * G3_QUADS + qd; tile < ntiles; tile += tstride) {
+        const int64_t row0 = tile * G2_ROWS;
+        // ---- E phase: this warp's 8 rows; four lanes per row build its 48 monomial features from registers ----
+        {
+            const int r = r0 + (lane >> 2);
+            const int64_t n = row0 + r;
+            const bool live = n < a.N;
+            double y[G1_DP];
+#pragma unroll
+            for (int d = 0; d < G1_DP; ++d) y[d] = (live && d < D) ? ynext[d] : 0.0;
+            double *zr = sZ + r * G1_LDZ;
+            if (part == 0) {
+                zr[0] = live ? 1.0 : 0.0;
+#pragma unroll
+                for (int d = 0; d < G1_DP; ++d) zr[1 + d] = y[d];
+            }
+            {
+                // the 36 products y_i y_j (i <= j) in feature order; lane `part` owns features 12*part .. 12*part+11
+                int f = 9;
+#pragma unroll
+                for (int i = 0; i < G1_DP; ++i)
+#pragma unroll
+                    for (int j = i; j < G1_DP; ++j, ++f)
+                        if (f / 12 == part) zr[f] = y[i] * y[j];
+                if (part == 3) zr[45] = zr[46] = zr[47] = 0.0;
+            }
+            const int64_t nn = n + tstride * G2_ROWS;       // this lane's row of the quad's next tile
+#pragma unroll
+            for (int d = 0; d < G1_DP; ++d) ynext[d] = (nn < a.N && d < D) ? a.Y[nn * D + d] : 0.0;
+        }
+        __syncwarp();
+        double L[8][2];
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) L[nb][0] = L[nb][1] = 0.0;
+#pragma unroll 3
+        for (int s = 0; s < G1_FP / 4; ++s) {
+            const double z0 = sZ[(r0 + gr) * G1_LDZ + 4 * s + tg];
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) {
+                const double th = sT[(nb * 8 + gr) * G1_LDZ + 4 * s + tg];
+                g1_dmma(L[nb][0], L[nb][1], z0, th);
+            }
+        }
+        {
+            const int r = r0 + gr;
+            const int64_t n = row0 + r;
+            const bool live = n < a.N;
+            double m = -INFINITY;
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) m = fmax(m, fmax(L[nb][0], L[nb][1]));
+            m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 1));
+            m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 2));
+            if (!isfinite(m)) m = 0.0;
+            double ssum = 0.0;
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) {
+                L[nb][0] = exp(L[nb][0] - m);
+                L[nb][1] = exp(L[nb][1] - m);
+                ssum += L[nb][0] + L[nb][1];
+            }
+            ssum += __shfl_xor_sync(0xffffffffu, ssum, 1);
+            ssum += __shfl_xor_sync(0xffffffffu, ssum, 2);
+            const double lse = log(ssum) + m;
+            const double inv = 1.0 / ssum;
+            double s2 = 0.0;
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) {
+                L[nb][0] *= inv; L[nb][1] *= inv;
+                s2 += L[nb][0] + L[nb][1];
+            }
+            s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+            const double inv2 = live ? 1.0 / s2 : 0.0;       // misc.py:1398-1401 second renormalisation
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) {
+                const double p0 = L[nb][0] * inv2, p1 = L[nb][1] * inv2;
+                const int k = nb * 8 + 2 * tg;
+                sP[r * G1_LDP + k] = p0;
+                sP[r * G1_LDP + k + 1] = p1;
+                if (live && a.P) {
+                    double *dst = a.P + n * K + k;
+                    if (K == G1_KP) *reinterpret_cast<double2 *>(dst) = make_double2(p0, p1);
+                    else { if (k < K) dst[0] = p0; if (k + 1 < K) dst[1] = p1; }
+                }
+            }
+            if (live && tg == 0) {
+                lse_acc += lse;
+                if (a.g) a.g[n] = -lse;
+            }
+        }
+        g3_quad_sync(qd);
+        // ---- M phase: S[32 components x 24 features] += P^T Z over the quad's 32 rows ----
+#pragma unroll 2
+        for (int q = 0; q < G2_ROWS / 4; ++q) {
+            const int r = 4 * q + tg;
+            double zb[3];
+#pragma unroll
+            for (int fb = 0; fb < 3; ++fb) zb[fb] = sZ[r * G1_LDZ + (fb0 + fb) * 8 + gr];
+#pragma unroll
+            for (int mb = 0; mb < 4; ++mb) {
+                const double pa = sP[r * G1_LDP + (mb0 + mb) * 8 + gr];
+#pragma unroll
+                for (int fb = 0; fb < 3; ++fb) g1_dmma(acc[mb][fb][0], acc[mb][fb][1], pa, zb[fb]);
+            }
+        }
+        g3_quad_sync(qd);          // the quad's buffers are free for its next tile
+    }
+    const int F = a.nfeat;
+    double *pout = a.partial + (size_t)blockIdx.x * (K * F + 1);
+    __syncthreads();
+    double *sS = sT + G1_KP * G1_LDZ;                   // [4 quads][64][48] staging over the quad buffers
+#pragma unroll
+    for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+        for (int fb = 0; fb < 3; ++fb)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                sS[(size_t)qd * G1_KP * G1_FP + ((mb0 + mb) * 8 + gr) * G1_FP + (fb0 + fb) * 8 + 2 * tg + j] = acc[mb][fb][j];
+    __syncthreads();
+    for (int e = t; e < K * F; e += blockDim.x) {
+        const int k = e / F, f = e - k * F;
+        int sf;
+        if (f <= D) sf = f;
+        else {
+            int i = (f - 1 - D) / D, j = (f - 1 - D) % D;
+            if (i > j) { int tmp = i; i = j; j = tmp; }
+            sf = 9 + i * G1_DP - (i * (i - 1)) / 2 + (j - i);
+        }
+        double v = 0.0;
+#pragma unroll
+        for (int pp = 0; pp < G3_QUADS; ++pp) v += sS[(size_t)pp * G1_KP * G1_FP + k * G1_FP + sf];
+        pout[e] = v;
+    }
+    lse_acc = warp_sum(lse_acc);
+    if (lane == 0) red[w] = lse_acc;
+    __syncthreads();
+    if (t == 0) {
+        double sum = 0.0;
+        for (int ww = 0; ww < 4 * G3_QUADS; ++ww) sum += red[ww];
+        pout[K * F] = sum;
+    }
+}
+
 // partial (k, f) layout -> caller's [sum p (K) | sum p y (K*D) | sum p yy^T (K*D*D) | lse]
 __global__ void gmm_final_kernel(const double *__restrict__ partial, int nblocks, int K, int D,
                                  double *__restrict__ stats) {
@@ -653,6 +853,11 @@ static int gmm_run(const double *Y, int64_t N, int D, int K,
         if (getenv("BPK_GMM_V1")) {
             BPK_CUDA(cudaFuncSetAttribute(gmm_sweep_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
             BPK_LAUNCH(gmm_sweep_dmma_kernel, grid1, G1_WARPS * 32, smem1, a);
+        } else if (getenv("BPK_GMM_V3")) {
+            // v3: warp quads, 16 warps of 128 registers
+            size_t smem3 = ((size_t)G1_KP * G1_LDZ + (size_t)G3_QUADS * (G2_ROWS * G1_LDZ + G2_ROWS * G1_LDP)) * sizeof(double);
+            BPK_CUDA(cudaFuncSetAttribute(gmm_sweep_dmma3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+            BPK_LAUNCH(gmm_sweep_dmma3_kernel, grid1, G3_QUADS * 128, smem3, a);
         } else {
             // v2: warp pairs on 32-row tiles (no CTA-wide barrier in the main loop)
             size_t smem2 = ((size_t)G1_KP * G1_LDZ + (size_t)G2_PAIRS * (G2_ROWS * G1_LDZ + G2_ROWS * G1_LDP)) * sizeof(double);

@@ -648,8 +648,329 @@ pca_xsweep_ws_kernel(const __grid_constant__ CUtensorMap tmapY, int64_t M, int64
     }   // sweeps of this launch
 }
 
+// =====================================================================================
+// v3: the persistent VB loop with a SERVICE CTA and DYNAMIC tile scheduling (what the resident loop launches when the
+// shard is large enough).  Measured on one steady-state sweep of the v2 loop at 1.25 M columns per GPU (the per-rank size
+// of the 8-GPU strong-scaling run; profiles/r02_probe_*): 10 us until the A fragments had arrived (148 x 8 warps
+// fetching the same 8 KB from L2), 12-18 us between the first and the last CTA reaching the grid barrier (equal tile
+// counts, unequal SM speed), 74 us of tail + barrier on CTA 0 (state staged in and out of shared memory every sweep,
+// code re-warmed by a dry run) — 287 us per sweep of which 184 us stream data.  Here:
+//   * CTA 0 does no data pass at all: it keeps the state vector resident in shared memory for the whole launch, its
+//     instruction cache holds nothing but the small ops, and it only publishes A, b for the next sweep;
+//   * the other CTAs take their tiles from a global counter (the producer warp grabs the next tile when it issues the
+//     TMA load and hands the tile index to the consumers through shared memory; a sentinel ends the sweep), so the grid
+//     reaches the barrier within about one tile time.  X does not depend on the assignment; the per-CTA partial sums do
+//     (fixed reduction order, but which tiles a CTA summed varies): statistics agree to rounding between runs, and
+//     every rank still ends up with bit-identical totals after the exchange.  BPK_PCA_STATIC=1 keeps the v2 loop.
+//   * A and b enter shared memory once per CTA and sweep (coalesced), after the first TMA loads have been issued.
+// =====================================================================================
+#define VL_LDA 65                        // pitch of the A tile in shared memory
+
+// distributed, fixed-order reduction of the per-CTA partials + LL push/gather of the owner's slice (see the v2 kernel)
+template <bool DERIVE_SXX>
+__device__ __forceinline__ void vl_reduce_push(const PcaVbArgs &vb, const double *partial, int w, int lane) {
+    const int per = (PCA_NSTAT + gridDim.x - 1) / gridDim.x;
+    const int e0 = blockIdx.x * per;
+    const unsigned long long xseq = *(volatile const unsigned long long *)vb.xown + 1ull;
+    const int par = (int)(xseq & 1ull);
+    const unsigned int seq = (unsigned int)xseq;
+    double *mywin = vb.xwin[0];
+#pragma unroll
+    for (int r = 1; r < BPK_XCHG_MAXRANKS; ++r)
+        if (lane == r) mywin = vb.xwin[r];
+    const int xr = vb.xranks;
+    for (int ee = w; ee < per; ee += 2 * WS_PAIRS) {
+        const int e = e0 + ee;
+        if (e >= PCA_NSTAT) continue;
+        if (DERIVE_SXX && e >= PCA_MP * PCA_KP && e < PCA_MP * PCA_KP + PCA_KP * PCA_KP) continue;
+        double s = 0.0;
+        for (int bb = lane; bb < (int)gridDim.x; bb += 32) s += __ldcg(partial + (size_t)bb * PCA_NSTAT + e);
+        s = warp_sum(s);
+        if (xr > 1) {
+            if (lane < xr) ll_store(ll_slot(mywin, par, vb.xrank, e), s, seq);
+            double v = 0.0;
+            if (lane < xr) v = ll_wait(ll_slot(vb.xown, par, lane, e), seq, vb.ctrl + 2);
+            s = 0.0;
+#pragma unroll
+            for (int r = 0; r < BPK_XCHG_MAXRANKS; ++r) {
+                const double vr = __shfl_sync(0xffffffffu, v, r);
+                if (r < xr) s += vr;
+            }
+        }
+        if (lane == 0) ll_store(ll_total_slot(vb.xown, par, e), s, seq);
+    }
+}
+
+template <int NT, int STAGES, int DIST, bool DERIVE_SXX>
+__global__ void __launch_bounds__(2 * WS_PAIRS * 32, 1)
+pca_vbloop_kernel(const __grid_constant__ CUtensorMap tmapY, int64_t M, int64_t N, int K,
+                  const double *A, const double *bvec, double *__restrict__ X, double *partial, int64_t ntiles,
+                  const int *stop, unsigned int *gbar, unsigned long long *tctr, const __grid_constant__ PcaVbArgs vb,
+                  size_t vb_sm_doubles) {
+    constexpr int T = WS_PAIRS * NT, NS = NT / 4, CB = NT / 8, NBOX = T / WS_BOXC, STG = NBOX * WS_BOX;
+    static_assert(DIST >= 1 && DIST < STAGES, "prefetch distance must leave one stage for the consumers");
+    static_assert(CB == 1, "the loop kernel is written for 8 columns per X-warp");
+    if (*stop) return;
+    extern __shared__ __align__(1024) double smem_ws[];
+    double *smem = smem_ws;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int gr = lane >> 2, tg = lane & 3;
+    const int niter = vb.niter;
+    unsigned int epoch = 0;
+    if (threadIdx.x == 0) epoch = *(volatile unsigned int *)&gbar[1];
+
+    // ------------------------------------------------------------------------------------------------------------
+    if (blockIdx.x == 0) {
+        // SERVICE CTA: grid reduction share, the sweep's small ops on the shared-memory resident state, nothing else
+        vb_stamp(vb.dbg, 0);
+        for (int e = threadIdx.x; e < PCA_NSTAT; e += blockDim.x) partial[e] = 0.0;       // it sums no tiles
+        pca_vb_state_load(vb, smem);
+        for (int it = 0; it < niter; ++it) {
+            if (it > 0 && *(volatile const int *)stop) break;
+            const int nops_it = (it == niter - 1) ? vb.nops_last : vb.nops;
+            vb_stamp(vb.dbg, 1);
+            grid_arrive(gbar, epoch);
+            grid_wait(gbar, epoch, vb.ctrl + 2);
+            vb_stamp(vb.dbg, 2);
+            vl_reduce_push<DERIVE_SXX>(vb, partial, w, lane);
+            vb_stamp(vb.dbg, 3);
+            const unsigned long long xseq = *(volatile const unsigned long long *)vb.xown + 1ull;
+            vb_stamp(vb.dbg, 4);
+            pca_vb_ops(vb, smem, vb_sm_doubles, false, nops_it, xseq, 1);
+            vb_stamp(vb.dbg, 5);
+            if (threadIdx.x == 0) *(volatile unsigned long long *)tctr = 0ull;    // next sweep's tile counter
+            if (it + 1 < niter) grid_barrier(gbar, epoch, vb.ctrl + 2);
+        }
+        pca_vb_state_store(vb, smem);
+        return;
+    }
+
+    // ------------------------------------------------------------------------------------------------------------
+    // WORKER CTAs
+    double *Ysm = smem;                                              // [STAGES][NBOX][64][16] swizzled
+    double *Xsm = Ysm + (size_t)STAGES * STG;                        // [PAIRS][2][NT][LDX]
+    double *Asm = Xsm + (size_t)WS_PAIRS * 2 * NT * PCA_LDX;         // [16][VL_LDA] + b[16]
+    uint64_t *bars = (uint64_t *)(Asm + PCA_KP * VL_LDA + PCA_KP);
+    uint64_t *full = bars, *empty = bars + STAGES;
+    uint64_t *xfull = bars + 2 * STAGES, *xfree = xfull + 2 * WS_PAIRS;   // [pair][2]
+    long long *stile = (long long *)(xfree + 2 * WS_PAIRS);          // [STAGES] tile index of the stage, -1 = end of sweep
+    const bool is_x = w < WS_PAIRS;
+    const int p = w & (WS_PAIRS - 1);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 2 * WS_PAIRS); }
+        for (int i = 0; i < 2 * WS_PAIRS; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xfree[i], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmapY) : "memory");
+    }
+    __syncthreads();
+    const bool probe = vb.dbg != nullptr && blockIdx.x == gridDim.x - 1;
+
+    int ig = 0;                  // stages consumed by this CTA since the launch began (every warp counts the same)
+    int xg = 0;                  // X -> S hand-offs (stages that carried a tile)
+    int issued = 0;              // producer (warp 0): stages issued
+    // producer: take the next tile from the global counter and start its load (or post the end-of-sweep sentinel)
+    bool ended = false;
+    auto issue = [&]() {
+        const int pos = issued;
+        const int slot = pos % STAGES;
+        long long tile = 0;
+        if (lane == 0) tile = (long long)atomicAdd(tctr, 1ull);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (pos >= STAGES) mbar_wait(&empty[slot], (uint32_t)((pos / STAGES - 1) & 1));
+        if (tile < ntiles) {
+            if (lane == 0) {
+                stile[slot] = tile;
+                mbar_expect_tx(&full[slot], (uint32_t)(STG * sizeof(double)));
+            }
+            __syncwarp();
+            if (lane < NBOX)
+                tma_load_2d(Ysm + (size_t)slot * STG + lane * WS_BOX, &tmapY, (int)(tile * T + lane * WS_BOXC), 0, &full[slot]);
+        } else {
+            if (lane == 0) {
+                stile[slot] = -1;
+                mbar_arrive(&full[slot]);
+            }
+            __syncwarp();
+            ended = true;
+        }
+        issued = pos + 1;
+    };
+
+    for (int it = 0; it < niter; ++it) {
+        const bool pr = probe && (it == niter - 2 || niter == 1);
+        if (probe && it == niter - 1 && niter > 1) vb_stamp(vb.dbg, 57);
+        if (pr) vb_stamp(vb.dbg, 48);
+        if (it > 0) {
+            if (*(volatile const int *)stop) break;                       // converged inside this launch (uniform)
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        }
+        ended = false;
+        if (w == 0)
+            while (!ended && issued < ig + DIST) issue();                 // loads first ...
+        // ... then this sweep's A, b -> shared memory (coalesced; one L2 fetch per CTA instead of one per warp)
+        for (int e = threadIdx.x; e < PCA_KP * PCA_MP; e += blockDim.x) {
+            const int k = e / PCA_MP, m = e - k * PCA_MP;
+            Asm[k * VL_LDA + m] = (k < K && m < M) ? __ldcg(A + (int64_t)k * M + m) : 0.0;
+        }
+        if (threadIdx.x < PCA_KP) Asm[PCA_KP * VL_LDA + threadIdx.x] = (bvec && (int)threadIdx.x < K) ? __ldcg(bvec + threadIdx.x) : 0.0;
+        __syncthreads();
+        if (is_x) {
+            double afrag[2][16];
+            double bk[2];
+#pragma unroll
+            for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                for (int ms = 0; ms < 16; ++ms)
+                    afrag[kb][ms] = Asm[(kb * 8 + gr) * VL_LDA + (ms >> 1) * 8 + 2 * tg + (ms & 1)];
+            bk[0] = Asm[PCA_KP * VL_LDA + gr];
+            bk[1] = Asm[PCA_KP * VL_LDA + 8 + gr];
+            if (pr && w == 0) vb_stamp_lane(vb.dbg, 49);
+            bool first = true;
+            for (;;) {
+                if (w == 0)
+                    while (!ended && issued < ig + DIST + 1) issue();
+                const int slot = (int)(ig % STAGES);
+                mbar_wait(&full[slot], (uint32_t)((ig / STAGES) & 1));
+                const long long tile = *(volatile long long *)&stile[slot];
+                if (tile < 0) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[slot]);
+                    ++ig;
+                    break;
+                }
+                if (pr && w == 0 && first) vb_stamp_lane(vb.dbg, 50);
+                first = false;
+                const int b = (int)(xg & 1);
+                const int c0 = p * NT;
+                const int64_t nbase = tile * T + c0;
+                double *Xs = Xsm + ((size_t)(p * 2 + b) * NT) * PCA_LDX;
+                const double *Ys = Ysm + (size_t)slot * STG;
+                double acc[2][2][2];
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb) {
+                    acc[0][kb][0] = acc[0][kb][1] = bk[kb];
+                    acc[1][kb][0] = acc[1][kb][1] = 0.0;
+                }
+#pragma unroll
+                for (int ms = 0; ms < 16; ++ms) {
+                    const double yb = Ys[ws_off((ms >> 1) * 8 + 2 * tg + (ms & 1), c0 + gr)];
+                    dmma884(acc[ms & 1][0][0], acc[ms & 1][0][1], afrag[0][ms], yb);
+                    dmma884(acc[ms & 1][1][0], acc[ms & 1][1][1], afrag[1][ms], yb);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[slot]);           // this warp no longer reads the Y stage
+                if (xg >= 2) mbar_wait(&xfree[p * 2 + b], (uint32_t)(((xg >> 1) - 1) & 1));
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int nl = 2 * tg + j, k = kb * 8 + gr;
+                        const bool inb = nbase + nl < N;
+                        const double v = inb ? acc[0][kb][j] + acc[1][kb][j] : 0.0;   // padded columns add nothing
+                        Xs[nl * PCA_LDX + k] = v;
+                        if (inb && k < K) X[(nbase + nl) * K + k] = v;
+                    }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&xfull[p * 2 + b]);
+                ++ig;
+                ++xg;
+            }
+            if (pr && w == 0) vb_stamp_lane(vb.dbg, 51);
+        } else {
+            const int rr = 2 * (gr & 3) + (gr >> 2);      // S_yx row within an 8-row block held by this lane group
+            double syx[8][2][2];
+            double sxx[3][2];
+            double sx = 0.0;
+#pragma unroll
+            for (int mb = 0; mb < 8; ++mb)
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb) syx[mb][kb][0] = syx[mb][kb][1] = 0.0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) sxx[i][0] = sxx[i][1] = 0.0;
+            for (;;) {
+                const int slot = (int)(ig % STAGES);
+                mbar_wait(&full[slot], (uint32_t)((ig / STAGES) & 1));
+                const long long tile = *(volatile long long *)&stile[slot];
+                if (tile < 0) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[slot]);
+                    ++ig;
+                    break;
+                }
+                const int b = (int)(xg & 1);
+                const int c0 = p * NT;
+                const double *Ys = Ysm + (size_t)slot * STG;
+                const double *Xs = Xsm + ((size_t)(p * 2 + b) * NT) * PCA_LDX;
+                mbar_wait(&xfull[p * 2 + b], (uint32_t)((xg >> 1) & 1));
+                if (lane < PCA_KP) {
+#pragma unroll
+                    for (int nl = 0; nl < NT; ++nl) sx += Xs[nl * PCA_LDX + lane];
+                }
+#pragma unroll
+                for (int ns = 0; ns < NS; ++ns) {
+                    const double xf0 = Xs[(ns * 4 + tg) * PCA_LDX + gr];
+                    const double xf1 = Xs[(ns * 4 + tg) * PCA_LDX + 8 + gr];
+#pragma unroll
+                    for (int mb = 0; mb < 8; ++mb) {
+                        const double ya = Ys[ws_off(mb * 8 + rr, c0 + ns * 4 + tg)];
+                        dmma884(syx[mb][0][0], syx[mb][0][1], ya, xf0);
+                        dmma884(syx[mb][1][0], syx[mb][1][1], ya, xf1);
+                    }
+                    if (!DERIVE_SXX) {
+                        dmma884(sxx[0][0], sxx[0][1], xf0, xf0);
+                        dmma884(sxx[1][0], sxx[1][1], xf0, xf1);
+                        dmma884(sxx[2][0], sxx[2][1], xf1, xf1);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(&xfree[p * 2 + b]); mbar_arrive(&empty[slot]); }
+                ++ig;
+                ++xg;
+            }
+            if (pr && w == WS_PAIRS) vb_stamp_lane(vb.dbg, 52);
+            // every stage has been consumed by every warp once all warps pass the barrier below
+            __syncthreads();
+            double *mine = smem + (size_t)p * PCA_NSTAT;
+#pragma unroll
+            for (int mb = 0; mb < 8; ++mb)
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+                        mine[(mb * 8 + rr) * PCA_KP + kb * 8 + 2 * tg + j] = syx[mb][kb][j];
+            double *mxx = mine + PCA_MP * PCA_KP;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                mxx[gr * PCA_KP + 2 * tg + j] = sxx[0][j];
+                mxx[gr * PCA_KP + 8 + 2 * tg + j] = sxx[1][j];
+                mxx[(8 + 2 * tg + j) * PCA_KP + gr] = sxx[1][j];
+                mxx[(8 + gr) * PCA_KP + 8 + 2 * tg + j] = sxx[2][j];
+            }
+            if (lane < PCA_KP) mine[PCA_MP * PCA_KP + PCA_KP * PCA_KP + lane] = sx;
+        }
+        if (is_x) __syncthreads();     // pairs with the S-warps' barrier above
+        __syncthreads();
+        double *pout = partial + (size_t)blockIdx.x * PCA_NSTAT;
+        for (int e = threadIdx.x; e < PCA_NSTAT; e += blockDim.x) {
+            double s = 0.0;
+#pragma unroll
+            for (int ww = 0; ww < WS_PAIRS; ++ww) s += smem[(size_t)ww * PCA_NSTAT + e];
+            pout[e] = s;
+        }
+        if (pr) vb_stamp(vb.dbg, 53);
+        grid_arrive(gbar, epoch);
+        grid_wait(gbar, epoch, vb.ctrl + 2);
+        if (pr) vb_stamp(vb.dbg, 54);
+        vl_reduce_push<DERIVE_SXX>(vb, partial, w, lane);
+        if (pr) vb_stamp(vb.dbg, 55);
+        if (it + 1 < niter) grid_barrier(gbar, epoch, vb.ctrl + 2);      // the next sweep's A, b, the stop word and the tile counter
+        if (pr) vb_stamp(vb.dbg, 56);
+    }
+}
+
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link dependency)
 static unsigned int *g_pca_gbar = nullptr;     // grid barrier of the fused sweep (count, epoch)
+static unsigned long long *g_pca_tctr = nullptr;   // tile counter of the persistent loop kernel (dynamic scheduling)
 
 typedef CUresult (*bpk_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                          const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
@@ -707,6 +1028,23 @@ static int pca_launch_ws(const double *Y, int64_t M, int64_t N, int K, const dou
         PcaVbArgs vb = *tail;
         vb.partial = partial + (size_t)grid * PCA_NSTAT;     // the grid-reduced statistics
         vb.nparts = 1;
+        if constexpr (NT == 8) {
+            // the persistent loop with a service CTA and dynamic tile scheduling: large shards, exchange through the windows
+            if (vb.derive_sxx && vb.ll && grid >= 8 && ntiles >= 8 * (int64_t)grid && !getenv("BPK_PCA_STATIC")) {
+                if (!g_pca_tctr) BPK_CUDA(cudaMalloc(&g_pca_tctr, sizeof(unsigned long long)));
+                BPK_CUDA(cudaMemsetAsync(g_pca_tctr, 0, sizeof(unsigned long long), g_bpk.stream));
+                size_t smem3 = ring + xs + (size_t)(PCA_KP * VL_LDA + PCA_KP) * sizeof(double) +
+                               (size_t)(2 * STAGES + 4 * WS_PAIRS) * sizeof(uint64_t) + (size_t)STAGES * sizeof(long long);
+                if (smem3 < redb) smem3 = redb;
+                auto kern = pca_vbloop_kernel<NT, STAGES, DIST, true>;
+                BPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+                BPK_LAUNCH(kern, grid, 2 * WS_PAIRS * 32, smem3, tmap, M, N, K, A, b, X, partial, ntiles, stop, g_pca_gbar,
+                           g_pca_tctr, vb, smem3 / sizeof(double));
+                *partial_out = partial + (size_t)grid * PCA_NSTAT;
+                *nparts_out = 1;
+                return BPK_OK;
+            }
+        }
         if (vb.derive_sxx) {
             auto kern = pca_xsweep_ws_kernel<NT, STAGES, DIST, true, true, true>;
             BPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

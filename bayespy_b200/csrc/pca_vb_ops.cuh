@@ -159,8 +159,11 @@ __device__ __forceinline__ double vb_E2(const double *st, const int64_t *o, int 
 // (index arithmetic becomes shifts; this code runs once per launch from a cold instruction cache, so small
 // and fast matters more than general).
 template <int KC, int MC>
+// rmode 1 (service CTA of the persistent loop kernel): the state vector is RESIDENT in shared memory for the whole launch
+// (pca_vb_state_load / pca_vb_state_store bracket the launch): nothing is staged in or out here; only what the rest of
+// the grid reads — A and b of the next sweep — is published to global memory.
 static __device__ __noinline__ void pca_vb_ops_t(const PcaVbArgs &p, double *sm, size_t sm_doubles, bool dry, int nops_run,
-                                                  unsigned long long xseq) {
+                                                  unsigned long long xseq, int rmode) {
     const int VBT = blockDim.x;
     const int M = MC ? MC : p.M, K = KC ? KC : p.K, K2 = 2 * K, ldg = K2 + 1, t = threadIdx.x;
     double *G = sm, *rowk = G + (size_t)K * ldg, *colk = rowk + 2 * K2, *piv = colk + 2 * K, *red = piv + K, *scal = red + 32;
@@ -182,8 +185,10 @@ static __device__ __noinline__ void pca_vb_ops_t(const PcaVbArgs &p, double *sm,
     unsigned long long *dbg = dry ? nullptr : p.dbg;
     if (staged) {
         st = sm + pca_vb_smem_doubles(K);
-        for (int64_t e = t; e < nstate; e += VBT) st[e] = __ldcg(p.st + e);
-        __syncthreads();
+        if (rmode == 0) {
+            for (int64_t e = t; e < nstate; e += VBT) st[e] = __ldcg(p.st + e);
+            __syncthreads();
+        }
     }
     volatile int *stop = ctrl + 1;
     const double Ng = st[o[F_NG]];
@@ -472,18 +477,39 @@ static __device__ __noinline__ void pca_vb_ops_t(const PcaVbArgs &p, double *sm,
     }
     if (staged && !dry) {
         __syncthreads();
-        for (int64_t e = o[F_W] + t; e < nstate; e += VBT) p.st[e] = st[e];      // hyper-parameters are read-only
+        if (rmode == 0) {
+            for (int64_t e = o[F_W] + t; e < nstate; e += VBT) p.st[e] = st[e];      // hyper-parameters are read-only
+        } else {
+            for (int64_t e = o[F_A] + t; e < o[F_BX + 1]; e += VBT) p.st[e] = st[e]; // A, b: all the other CTAs need
+        }
     }
 #undef CINV
+}
+
+// state vector <-> shared memory, once per launch (service CTA of the persistent loop kernel; requires that the state
+// fits behind the scratch, which it does whenever the fast sweep kernel applies: M <= 64, K <= 16)
+static __device__ __forceinline__ void pca_vb_state_load(const PcaVbArgs &p, double *sm) {
+    int64_t o[F_COUNT + 1];
+    pca_vb_offsets(p.M, p.K, o);
+    double *st = sm + pca_vb_smem_doubles(p.K);
+    for (int64_t e = threadIdx.x; e < o[F_COUNT]; e += blockDim.x) st[e] = __ldcg(p.st + e);
+    __syncthreads();
+}
+static __device__ __forceinline__ void pca_vb_state_store(const PcaVbArgs &p, double *sm) {
+    int64_t o[F_COUNT + 1];
+    pca_vb_offsets(p.M, p.K, o);
+    const double *st = sm + pca_vb_smem_doubles(p.K);
+    __syncthreads();
+    for (int64_t e = o[F_W] + threadIdx.x; e < o[F_COUNT]; e += blockDim.x) p.st[e] = st[e];
 }
 
 // xseq: sequence number of this sweep's exchange when the caller (fused sweep kernel) has already pushed the grid's
 // slices (p.ll); ignored otherwise.
 static __device__ __forceinline__ void pca_vb_ops(const PcaVbArgs &p, double *sm, size_t sm_doubles, bool dry = false,
-                                                  int nops_run = -1, unsigned long long xseq = 0ull) {
+                                                  int nops_run = -1, unsigned long long xseq = 0ull, int rmode = 0) {
     if (nops_run < 0) nops_run = p.nops;
-    if (p.M == PCA_MP && p.K == PCA_KP) pca_vb_ops_t<PCA_KP, PCA_MP>(p, sm, sm_doubles, dry, nops_run, xseq);
-    else pca_vb_ops_t<0, 0>(p, sm, sm_doubles, dry, nops_run, xseq);
+    if (p.M == PCA_MP && p.K == PCA_KP) pca_vb_ops_t<PCA_KP, PCA_MP>(p, sm, sm_doubles, dry, nops_run, xseq, rmode);
+    else pca_vb_ops_t<0, 0>(p, sm, sm_doubles, dry, nops_run, xseq, rmode);
 }
 
 

@@ -407,7 +407,9 @@ def main():
     ap.add_argument("--workload", default="pca", choices=["pca", "pca_masked", "gmm", "lssm"],
                     help="pca = the headline metric (BASELINE.json configs[1] scaled to N=1e7); gmm / lssm = configs[2] / [3] "
                          "(tools/bench_workloads.py)")
-    ap.add_argument("--n", type=int, default=N_TOTAL, help="total number of columns (default: the metric's 1e7)")
+    ap.add_argument("--n", "--columns", dest="n", type=int, default=N_TOTAL,
+                    help="total number of columns / rows / time steps of the workload (default: the metric's 1e7; under torchrun "
+                         "spell it --columns: torchrun's own parser claims the prefix --n)")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--ref-budget-s", type=float, default=150.0,
                     help="--impl reference: wall-clock budget of the whole run; sets the column sample per step")

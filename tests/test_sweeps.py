@@ -172,8 +172,17 @@ def test_pca_xsweep_masked_fused_rejects_a_non_spd_precision(backend):
                                         d["amu"].ptr, X.ptr, G.ptr, st.ptr, True)
 
 
-@pytest.mark.parametrize("N,D,K", [(300, 3, 5), (1000, 8, 64), (129, 2, 10), (77, 1, 2)])
-def test_gmm_sweep(backend, N, D, K):
+@pytest.mark.parametrize("variant", [None, "BPK_GMM_V1", "BPK_GMM_V3", "BPK_GMM_V0"])
+@pytest.mark.parametrize("N,D,K", [(300, 3, 5), (1000, 8, 64), (129, 2, 10), (77, 1, 2), (70001, 8, 64)])
+def test_gmm_sweep(backend, N, D, K, variant, monkeypatch):
+    """Every variant of the mixture sweep kernel (default: warp pairs; V1: CTA barriers; V3: warp quads of 128
+    registers; V0: scalar) against the dense NumPy restatement."""
+    if variant is not None:
+        if backend.name != "cuda":
+            pytest.skip("kernel variants exist on the GPU only")
+        monkeypatch.setenv(variant, "1")
+    if N > 5000 and backend.name != "cuda":
+        pytest.skip("large case runs on the GPU only")
     rng = np.random.RandomState(N + D)
     y = 3 * rng.randn(N, D)
     c = rng.randn(K)
