@@ -725,12 +725,54 @@ pca_vbloop_kernel(const __grid_constant__ CUtensorMap tmapY, int64_t M, int64_t 
         vb_stamp(vb.dbg, 0);
         for (int e = threadIdx.x; e < PCA_NSTAT; e += blockDim.x) partial[e] = 0.0;       // it sums no tiles
         pca_vb_state_load(vb, smem);
+        // The small ops run once per sweep; in between this SM idles at the grid barrier for the whole data pass and the
+        // ops' code (transcendentals, two K x K inversions, the bound) falls out of the instruction caches: measured
+        // 78 us per tail cold against ~50 us right after a run.  So the ops are DRY-RUN (scratch copy of the state, no
+        // side effects) while the grid streams data, timed from the previous sweep's data-pass duration to finish just
+        // before the grid arrives.
+        __shared__ unsigned long long svc_t[4];       // [0] sweep start, [1] data-pass duration of the previous sweep, [2] dry-run duration
+        if (threadIdx.x == 0) {
+            unsigned long long t0;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            svc_t[0] = t0; svc_t[1] = 0ull; svc_t[2] = 0ull;
+        }
+        __syncthreads();
         for (int it = 0; it < niter; ++it) {
             if (it > 0 && *(volatile const int *)stop) break;
             const int nops_it = (it == niter - 1) ? vb.nops_last : vb.nops;
+            if (vb.dry_every || it == 0) {
+                if (threadIdx.x == 0 && svc_t[1] > 0ull) {
+                    // start so that the run ends ~5 us before the expected arrival of the grid
+                    const unsigned long long lead = svc_t[2] + (svc_t[2] >> 2) + 5000ull;
+                    if (svc_t[1] > lead) {
+                        const unsigned long long until = svc_t[0] + svc_t[1] - lead;
+                        unsigned long long now;
+                        for (;;) {
+                            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                            if (now >= until || *(volatile unsigned int *)&gbar[0] > 0u) break;   // or somebody is already there
+                            __nanosleep(256);
+                        }
+                    }
+                }
+                __syncthreads();
+                unsigned long long d0 = 0ull;
+                if (threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(d0));
+                pca_vb_ops(vb, smem, vb_sm_doubles, true, nops_it, 0ull, 1);
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    unsigned long long d1;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(d1));
+                    svc_t[2] = d1 - d0;
+                }
+            }
             vb_stamp(vb.dbg, 1);
             grid_arrive(gbar, epoch);
             grid_wait(gbar, epoch, vb.ctrl + 2);
+            if (threadIdx.x == 0) {
+                unsigned long long tb;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tb));
+                svc_t[1] = tb - svc_t[0];
+            }
             vb_stamp(vb.dbg, 2);
             vl_reduce_push<DERIVE_SXX>(vb, partial, w, lane);
             vb_stamp(vb.dbg, 3);
@@ -740,6 +782,11 @@ pca_vbloop_kernel(const __grid_constant__ CUtensorMap tmapY, int64_t M, int64_t 
             vb_stamp(vb.dbg, 5);
             if (threadIdx.x == 0) *(volatile unsigned long long *)tctr = 0ull;    // next sweep's tile counter
             if (it + 1 < niter) grid_barrier(gbar, epoch, vb.ctrl + 2);
+            if (threadIdx.x == 0) {
+                unsigned long long ts;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts));
+                svc_t[0] = ts;
+            }
         }
         pca_vb_state_store(vb, smem);
         return;
@@ -1059,7 +1106,7 @@ static int pca_launch_ws(const double *Y, int64_t M, int64_t N, int K, const dou
         return BPK_OK;
     }
     PcaVbArgs none;
-    none.nops = 0; none.nops_last = 0; none.niter = 1; none.dry_every = 0; none.derive_sxx = 0; none.ll = 0; none.gj2 = 0;
+    none.nops = 0; none.nops_last = 0; none.niter = 1; none.dry_every = 0; none.derive_sxx = 0; none.ll = 0; none.gj2 = 0; none.par = 0;
     none.xranks = 1; none.xrank = 0; none.dbg = nullptr; none.xown = nullptr;
     auto kern = pca_xsweep_ws_kernel<NT, STAGES, DIST, COMPUTE_X, false, false>;
     BPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

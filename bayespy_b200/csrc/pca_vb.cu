@@ -103,6 +103,7 @@ extern "C" int bpk_pca_vb_run(const double *Y, int64_t M, int64_t N, int K, doub
     a.niter = 1; a.nops_last = 0; a.derive_sxx = 0;
     a.ll = 0;
     a.gj2 = getenv("BPK_VB_GJ1") ? 0 : 1;
+    a.par = getenv("BPK_VB_SERIAL") ? 0 : 1;
     a.dry_every = getenv("BPK_VB_DRY_FIRST_ONLY") ? 0 : 1;
     a.dbg = nullptr;
     if (getenv("BPK_VB_DEBUG")) {

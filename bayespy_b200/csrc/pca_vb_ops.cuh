@@ -94,8 +94,9 @@ __host__ __device__ inline void pca_vb_offsets(int M, int K, int64_t *off /* [F_
 }
 
 // scratch of the small ops in doubles: augmented K x 2K Gauss-Jordan tile (odd pitch), two pivot rows / columns
-// (the elimination takes two pivots per step), pivots, reduction slots
-__host__ __device__ inline size_t pca_vb_smem_doubles(int K) { return (size_t)K * (2 * K + 1) + 7 * (size_t)K + 64; }
+// (the elimination takes two pivots per step), pivots, reduction slots; then a copy of Lam_x and a second set of
+// reduction slots for the op that runs side by side with another one (BOUND next to XPRE, TAU next to ALPHA)
+__host__ __device__ inline size_t pca_vb_smem_doubles(int K) { return (size_t)K * (2 * K + 1) + 7 * (size_t)K + 64 + (size_t)K * K + 64; }
 
 struct PcaVbArgs {
     int M, K, has_alpha, has_tau;
@@ -114,6 +115,7 @@ struct PcaVbArgs {
     int ll;                  // 1 (fused sweep kernel): every CTA has pushed its slice of the reduced statistics into the
                              // windows as LL packets (xranks may be 1: the window is then this GPU's own); STATS gathers
     int gj2;                 // 1: K x K inverses eliminate two pivots per step (half the barriers)
+    int par;                 // 1: independent neighbours in the op list run side by side on two halves of the CTA
     int niter;               // fused sweep kernel: sweeps per launch; ops[0..nops) follow every sweep but the last,
     int derive_sxx;          // 1: the sweep kernel did not accumulate S_xx; STATS forms it as A S_yx + b s_x^T
     int dry_every;           // 1: CTA 0 dry-runs the tail in every sweep of the launch, 0: only in the first
@@ -133,6 +135,23 @@ __device__ __forceinline__ double vb_block_sum(double v, double *red) {
     return s;
 }
 
+// a TEAM: n threads (a multiple of 32; thread index t within it) that meet at named barrier `bar` (0 = the whole CTA)
+struct VbTeam { int t, n, bar; };
+__device__ __forceinline__ void vb_team_sync(const VbTeam &T) {
+    if (T.bar == 0) __syncthreads();
+    else asm volatile("bar.sync %0, %1;\n" ::"r"(T.bar), "r"(T.n) : "memory");
+}
+__device__ __forceinline__ double vb_team_sum(double v, double *red, const VbTeam &T) {
+    v = warp_sum(v);
+    vb_team_sync(T);
+    if ((T.t & 31) == 0) red[T.t >> 5] = v;
+    vb_team_sync(T);
+    double s = 0.0;
+    const int nw = T.n >> 5;
+    for (int w = 0; w < nw; ++w) s += red[w];
+    return s;
+}
+
 // gamma.py:124-148: a = phi1, b = -phi0
 __device__ __forceinline__ void vb_gamma(double phi0, double phi1, double &u0, double &u1, double &g, int *ctrl) {
     double a = phi1, b = -phi0;
@@ -144,12 +163,12 @@ __device__ __forceinline__ void vb_gamma(double phi0, double phi1, double &u0, d
 }
 
 // sum_mn <(y - f)^2> = sum y^2 - 2 <W>:S_yx + tr(sum_m<ww^T> sum_n<xx^T>)   (dot.py:355,403 summed)
-__device__ __forceinline__ double vb_E2(const double *st, const int64_t *o, int M, int K, double *red) {
+__device__ __forceinline__ double vb_E2(const double *st, const int64_t *o, int M, int K, double *red, const VbTeam &T) {
     const double *W = st + o[F_W], *Syx = st + o[F_STATS], *SWW = st + o[F_SWW], *SXXT = st + o[F_SXXT];
     double a = 0.0, b = 0.0;
-    for (int e = threadIdx.x; e < M * K; e += blockDim.x) a += W[e] * Syx[e];
-    for (int e = threadIdx.x; e < K * K; e += blockDim.x) b += SWW[e] * SXXT[e];
-    return st[o[F_SUMSQ]] + vb_block_sum(b - 2.0 * a, red);
+    for (int e = T.t; e < M * K; e += T.n) a += W[e] * Syx[e];
+    for (int e = T.t; e < K * K; e += T.n) b += SWW[e] * SXXT[e];
+    return st[o[F_SUMSQ]] + vb_team_sum(b - 2.0 * a, red, T);
 }
 
 // One run of small ops by ONE CTA (any multiple of 32 threads up to 1024).  sm: shared-memory scratch of
@@ -167,6 +186,7 @@ static __device__ __noinline__ void pca_vb_ops_t(const PcaVbArgs &p, double *sm,
     const int VBT = blockDim.x;
     const int M = MC ? MC : p.M, K = KC ? KC : p.K, K2 = 2 * K, ldg = K2 + 1, t = threadIdx.x;
     double *G = sm, *rowk = G + (size_t)K * ldg, *colk = rowk + 2 * K2, *piv = colk + 2 * K, *red = piv + K, *scal = red + 32;
+    double *lamx_old = scal + 32, *red2 = lamx_old + (size_t)K * K;
     __shared__ int64_t o[F_COUNT + 1];
     __shared__ int dry_ctrl[4];
     if (t == 0) pca_vb_offsets(M, K, o);
@@ -188,17 +208,191 @@ static __device__ __noinline__ void pca_vb_ops_t(const PcaVbArgs &p, double *sm,
         if (rmode == 0) {
             for (int64_t e = t; e < nstate; e += VBT) st[e] = __ldcg(p.st + e);
             __syncthreads();
+        } else if (dry) {
+            // resident state: the warm-up run works on a scratch copy behind it
+            if (pca_vb_smem_doubles(K) + 2 * (size_t)nstate > sm_doubles) return;
+            double *st2 = st + nstate;
+            for (int64_t e = t; e < nstate; e += VBT) st2[e] = st[e];
+            st = st2;
+            __syncthreads();
         }
     }
     volatile int *stop = ctrl + 1;
     const double Ng = st[o[F_NG]];
 #define CINV(i, j) G[(i) * ldg + K + (j)]
 
+
+    // ---- ops that may run on a TEAM (half of the CTA) next to an independent neighbour ----------------------------
+    const VbTeam full{t, VBT, 0};
+    auto op_xpre = [&](const VbTeam &T) {
+        // q(X) shared part: Lam_x = diag(a_x) + tau sum_m<ww^T>; x_n = Cov_x (a_x mu_x + tau W^T y_n)
+        const double tau = st[o[F_TAU_U0]];
+        for (int e = T.t; e < K * K2; e += T.n) {
+            const int i = e / K2, j = e - i * K2;
+            double v;
+            if (j < K) {
+                v = tau * st[o[F_SWW] + i * K + j] + (i == j ? st[o[F_AX] + i] : 0.0);
+                st[o[F_LAMX] + i * K + j] = v;
+                st[o[F_PHI1X] + i * K + j] = -0.5 * v;          // natural parameter phi_1 of q(X) (shared by all columns)
+            } else v = (j - K == i) ? 1.0 : 0.0;
+            G[i * ldg + j] = v;
+        }
+        if (T.bar == 0) spd_cta_inverse_gj<KC>(G, rowk, colk, piv, K, scal, &ctrl[2], p.gj2);
+        else spd_cta_inverse_gj<KC>(G, rowk, colk, piv, K, scal, &ctrl[2], p.gj2, T.t, T.n, T.bar);
+        for (int e = T.t; e < K * K; e += T.n) st[o[F_COVX] + e] = CINV(e / K, e % K);
+        if (T.t == 0) st[o[F_LOGDETX]] = scal[0];
+        for (int k = T.t; k < K; k += T.n) {
+            double s = 0.0;
+            for (int j = 0; j < K; ++j) s += CINV(k, j) * (st[o[F_AX] + j] * st[o[F_MUX] + j]);
+            st[o[F_BX] + k] = s;
+        }
+        for (int e = T.t; e < K * M; e += T.n) {
+            const int k = e / M, m = e - k * M;
+            double s = 0.0;
+#pragma unroll 4
+            for (int j = 0; j < K; ++j) s += CINV(k, j) * st[o[F_W] + m * K + j];
+            st[o[F_A] + e] = tau * s;
+        }
+    };
+    auto op_alpha = [&](const VbTeam &T) {
+        // gaussian.py:609-637 index 1 summed over the M rows, then gamma.py:124-148
+        for (int k = T.t; k < K; k += T.n) {
+            double sw = 0.0;
+            for (int m = 0; m < M; ++m) sw += st[o[F_W] + m * K + k];
+            double mu = st[o[F_MUC] + k];
+            double d = st[o[F_SWW] + k * K + k] - 2.0 * mu * sw + (double)M * mu * mu;
+            double phi0 = -st[o[F_B0] + k] - 0.5 * d;
+            double phi1 = st[o[F_A0] + k] + 0.5 * (double)M;
+            double u0, u1, g;
+            vb_gamma(phi0, phi1, u0, u1, g, ctrl);
+            st[o[F_AL_PHI0] + k] = phi0;
+            st[o[F_AL_PHI1] + k] = phi1;
+            st[o[F_AL_U0] + k] = u0;
+            st[o[F_AL_U1] + k] = u1;
+            st[o[F_AL_G] + k] = g;
+        }
+    };
+    auto op_tau = [&](const VbTeam &T, double *redp) {
+        // gaussian.py:2351-2371 summed over (M,N), then gamma.py:124-148
+        double E2 = vb_E2(st, o, M, K, redp, T);
+        if (T.t == 0) {
+            double phi0 = -st[o[F_TB0]] - 0.5 * E2;
+            double phi1 = st[o[F_TA0]] + 0.5 * (double)M * Ng;
+            double u0, u1, g;
+            vb_gamma(phi0, phi1, u0, u1, g, ctrl);
+            st[o[F_TAU_PHI0]] = phi0;
+            st[o[F_TAU_PHI1]] = phi1;
+            st[o[F_TAU_U0]] = u0;
+            st[o[F_TAU_U1]] = u1;
+            st[o[F_TAU_G]] = g;
+        }
+    };
+    auto op_bound = [&](const VbTeam &T, double *redp, const double *lamx, const double logdetx) {
+        // expfamily.py:400-480 for Y, X, C, alpha, tau from the plate-summed statistics
+        const double tau = st[o[F_TAU_U0]], logtau = st[o[F_TAU_U1]];
+        double E2 = vb_E2(st, o, M, K, redp, T);
+        double LY = -0.5 * tau * E2 + 0.5 * (double)M * Ng * (logtau - LOG2PI_D);
+        // X
+        const double *Sxx = st + o[F_STATS] + M * K, *sx = Sxx + K * K;
+        double a = 0.0;   // tr(Lam_x S_xx), (phi1_p - phi1_q):sum<xx^T>
+        double b = 0.0;
+        for (int e = T.t; e < K * K; e += T.n) {
+            int i = e / K, j = e - i * K;
+            double lam = lamx[e];
+            a += lam * Sxx[e];
+            b += (0.5 * lam - (i == j ? 0.5 * st[o[F_AX] + i] : 0.0)) * st[o[F_SXXT] + e];
+        }
+        double c = 0.0;   // phi0_p . s_x  and the prior cgf
+        for (int k = T.t; k < K; k += T.n) {
+            double ax = st[o[F_AX] + k], mu = st[o[F_MUX] + k];
+            c += ax * mu * sx[k] + Ng * (-0.5 * ax * mu * mu + 0.5 * log(ax));
+        }
+        double trLS = vb_team_sum(a, redp, T);
+        double LX = vb_team_sum(b + c, redp, T) - trLS + 0.5 * trLS - 0.5 * Ng * logdetx;
+        // C
+        double d = 0.0;
+        for (int e = T.t; e < M * K; e += T.n) {
+            int k = e % K;
+            d += (st[o[F_AL_U0] + k] * st[o[F_MUC] + k] - st[o[F_PHI0C] + e]) * st[o[F_W] + e];
+        }
+        for (int e = T.t; e < K * K; e += T.n) {
+            int i = e / K, j = e - i * K;
+            d += (0.5 * st[o[F_LAMC] + e] - (i == j ? 0.5 * st[o[F_AL_U0] + i] : 0.0)) * st[o[F_SWW] + e];
+        }
+        for (int m = T.t; m < M; m += T.n) d -= st[o[F_GC] + m];
+        for (int k = T.t; k < K; k += T.n) {
+            double mu = st[o[F_MUC] + k];
+            d += (double)M * (-0.5 * st[o[F_AL_U0] + k] * mu * mu + 0.5 * st[o[F_AL_U1] + k]);
+        }
+        double LC = vb_team_sum(d, redp, T);
+        // alpha
+        double f = 0.0;
+        if (p.has_alpha) {
+            for (int k = T.t; k < K; k += T.n) {
+                double a0 = st[o[F_A0] + k], b0 = st[o[F_B0] + k];
+                f += (-b0 - st[o[F_AL_PHI0] + k]) * st[o[F_AL_U0] + k]
+                   + (a0 - st[o[F_AL_PHI1] + k]) * st[o[F_AL_U1] + k]
+                   + (a0 * log(b0) - lgamma(a0)) - st[o[F_AL_G] + k];
+            }
+        }
+        double LA = vb_team_sum(f, redp, T);
+        if (T.t == 0) {
+            double LT = 0.0;
+            if (p.has_tau) {
+                double a0 = st[o[F_TA0]], b0 = st[o[F_TB0]];
+                LT = (-b0 - st[o[F_TAU_PHI0]]) * tau + (a0 - st[o[F_TAU_PHI1]]) * logtau
+                   + (a0 * log(b0) - lgamma(a0)) - st[o[F_TAU_G]];
+            }
+            double L = (((LY + LX) + LC) + LA) + LT;
+            int it = ctrl[0];
+            if (it < cap) {
+                double *row = p.Lhist + (size_t)it * 6;
+                row[0] = LY; row[1] = LX; row[2] = LC; row[3] = LA; row[4] = LT; row[5] = L;
+            }
+            double L0 = st[o[F_LPREV]];
+            st[o[F_LPREV]] = L;
+            ctrl[0] = it + 1;
+            // vmp.py:738-747 (tol < 0 or no previous bound: test disabled)
+            if (p.tol >= 0.0 && L0 == L0) {
+                double div = 0.5 * (fabs(L0) + fabs(L));
+                if ((L - L0) / div < p.tol) ctrl[1] = 1;
+            }
+            if (ctrl[2]) ctrl[1] = 1;
+            __threadfence();
+        }
+    };
+    // side-by-side execution needs whole warps on both sides and enough threads for the two-pivot elimination
+    const bool can_pair = p.par && (VBT % 64) == 0 && VBT / 2 >= 2 * K2 + 2 * K + 1;
+
     for (int ip = 0; ip < nops_run; ++ip) {
         __syncthreads();
         if (*stop) break;
         const int op = p.ops[ip];
         vb_stamp(dbg, 8 + ip);
+        if (can_pair && ip + 1 < nops_run) {
+            const int op2 = p.ops[ip + 1];
+            if ((op == BPK_VBOP_ALPHA && op2 == BPK_VBOP_TAU) || (op == BPK_VBOP_TAU && op2 == BPK_VBOP_ALPHA)) {
+                // alpha.update() and tau.update() read <W>, sum<ww^T>, the statistics; neither reads what the other writes
+                if (t < 32) op_alpha(VbTeam{t, 32, 1});
+                else op_tau(VbTeam{t - 32, VBT - 32, 2}, red2);
+                vb_stamp(dbg, 8 + ip + 1);
+                ++ip;
+                continue;
+            }
+            if (op == BPK_VBOP_BOUND && op2 == BPK_VBOP_XPRE) {
+                // the bound of this sweep next to the shared part of the NEXT q(X): XPRE overwrites Lam_x and log det Lam_x,
+                // which the bound still needs from the q(X) that is in force — it reads them from a copy
+                for (int e = t; e < K * K; e += VBT) lamx_old[e] = st[o[F_LAMX] + e];
+                const double logdetx_old = st[o[F_LOGDETX]];
+                __syncthreads();
+                const int h = VBT / 2;
+                if (t < h) op_xpre(VbTeam{t, h, 1});
+                else op_bound(VbTeam{t - h, h, 2}, red2, lamx_old, logdetx_old);
+                vb_stamp(dbg, 8 + ip + 1);
+                ++ip;
+                continue;
+            }
+        }
         if (op == BPK_VBOP_STATS) {
             // fixed-order grid reduction of the sweep kernel's per-CTA partials + the sweep's ONE exchange
             const int total = M * K + K * K + K;
@@ -296,33 +490,7 @@ static __device__ __noinline__ void pca_vb_ops_t(const PcaVbArgs &p, double *sm,
             for (int e = t; e < K * K; e += VBT)
                 st[o[F_SXXT] + e] = Ng * st[o[F_COVX] + e] + st[o[F_STATS] + M * K + e];
         } else if (op == BPK_VBOP_XPRE) {
-            // q(X) shared part: Lam_x = diag(a_x) + tau sum_m<ww^T>; x_n = Cov_x (a_x mu_x + tau W^T y_n)
-            const double tau = st[o[F_TAU_U0]];
-            for (int e = t; e < K * K2; e += VBT) {
-                const int i = e / K2, j = e - i * K2;
-                double v;
-                if (j < K) {
-                    v = tau * st[o[F_SWW] + i * K + j] + (i == j ? st[o[F_AX] + i] : 0.0);
-                    st[o[F_LAMX] + i * K + j] = v;
-                    st[o[F_PHI1X] + i * K + j] = -0.5 * v;          // natural parameter phi_1 of q(X) (shared by all columns)
-                } else v = (j - K == i) ? 1.0 : 0.0;
-                G[i * ldg + j] = v;
-            }
-            spd_cta_inverse_gj<KC>(G, rowk, colk, piv, K, scal, &ctrl[2], p.gj2);
-            for (int e = t; e < K * K; e += VBT) st[o[F_COVX] + e] = CINV(e / K, e % K);
-            if (t == 0) st[o[F_LOGDETX]] = scal[0];
-            for (int k = t; k < K; k += VBT) {
-                double s = 0.0;
-                for (int j = 0; j < K; ++j) s += CINV(k, j) * (st[o[F_AX] + j] * st[o[F_MUX] + j]);
-                st[o[F_BX] + k] = s;
-            }
-            for (int e = t; e < K * M; e += VBT) {
-                const int k = e / M, m = e - k * M;
-                double s = 0.0;
-#pragma unroll 4
-                for (int j = 0; j < K; ++j) s += CINV(k, j) * st[o[F_W] + m * K + j];
-                st[o[F_A] + e] = tau * s;
-            }
+            op_xpre(full);
         } else if (op == BPK_VBOP_ROW) {
             // q(C): Lam_c = diag<alpha> + tau sum_n<xx^T> (shared by all rows); phi0_m = <alpha> mu_c + tau S_yx[m]
             const double tau = st[o[F_TAU_U0]];
@@ -370,109 +538,11 @@ static __device__ __noinline__ void pca_vb_ops_t(const PcaVbArgs &p, double *sm,
                 st[o[F_SWW] + e] = (double)M * CINV(i, j) + (s0 + s1);
             }
         } else if (op == BPK_VBOP_ALPHA) {
-            // gaussian.py:609-637 index 1 summed over the M rows, then gamma.py:124-148
-            for (int k = t; k < K; k += VBT) {
-                double sw = 0.0;
-                for (int m = 0; m < M; ++m) sw += st[o[F_W] + m * K + k];
-                double mu = st[o[F_MUC] + k];
-                double d = st[o[F_SWW] + k * K + k] - 2.0 * mu * sw + (double)M * mu * mu;
-                double phi0 = -st[o[F_B0] + k] - 0.5 * d;
-                double phi1 = st[o[F_A0] + k] + 0.5 * (double)M;
-                double u0, u1, g;
-                vb_gamma(phi0, phi1, u0, u1, g, ctrl);
-                st[o[F_AL_PHI0] + k] = phi0;
-                st[o[F_AL_PHI1] + k] = phi1;
-                st[o[F_AL_U0] + k] = u0;
-                st[o[F_AL_U1] + k] = u1;
-                st[o[F_AL_G] + k] = g;
-            }
+            op_alpha(full);
         } else if (op == BPK_VBOP_TAU) {
-            // gaussian.py:2351-2371 summed over (M,N), then gamma.py:124-148
-            double E2 = vb_E2(st, o, M, K, red);
-            if (t == 0) {
-                double phi0 = -st[o[F_TB0]] - 0.5 * E2;
-                double phi1 = st[o[F_TA0]] + 0.5 * (double)M * Ng;
-                double u0, u1, g;
-                vb_gamma(phi0, phi1, u0, u1, g, ctrl);
-                st[o[F_TAU_PHI0]] = phi0;
-                st[o[F_TAU_PHI1]] = phi1;
-                st[o[F_TAU_U0]] = u0;
-                st[o[F_TAU_U1]] = u1;
-                st[o[F_TAU_G]] = g;
-            }
+            op_tau(full, red);
         } else if (op == BPK_VBOP_BOUND) {
-            // expfamily.py:400-480 for Y, X, C, alpha, tau from the plate-summed statistics
-            const double tau = st[o[F_TAU_U0]], logtau = st[o[F_TAU_U1]];
-            double E2 = vb_E2(st, o, M, K, red);
-            double LY = -0.5 * tau * E2 + 0.5 * (double)M * Ng * (logtau - LOG2PI_D);
-            // X
-            const double *Sxx = st + o[F_STATS] + M * K, *sx = Sxx + K * K;
-            double a = 0.0;   // tr(Lam_x S_xx), (phi1_p - phi1_q):sum<xx^T>
-            double b = 0.0;
-            for (int e = t; e < K * K; e += VBT) {
-                int i = e / K, j = e - i * K;
-                double lam = st[o[F_LAMX] + e];
-                a += lam * Sxx[e];
-                b += (0.5 * lam - (i == j ? 0.5 * st[o[F_AX] + i] : 0.0)) * st[o[F_SXXT] + e];
-            }
-            double c = 0.0;   // phi0_p . s_x  and the prior cgf
-            for (int k = t; k < K; k += VBT) {
-                double ax = st[o[F_AX] + k], mu = st[o[F_MUX] + k];
-                c += ax * mu * sx[k] + Ng * (-0.5 * ax * mu * mu + 0.5 * log(ax));
-            }
-            double trLS = vb_block_sum(a, red);
-            double LX = vb_block_sum(b + c, red) - trLS + 0.5 * trLS - 0.5 * Ng * st[o[F_LOGDETX]];
-            // C
-            double d = 0.0;
-            for (int e = t; e < M * K; e += VBT) {
-                int k = e % K;
-                d += (st[o[F_AL_U0] + k] * st[o[F_MUC] + k] - st[o[F_PHI0C] + e]) * st[o[F_W] + e];
-            }
-            for (int e = t; e < K * K; e += VBT) {
-                int i = e / K, j = e - i * K;
-                d += (0.5 * st[o[F_LAMC] + e] - (i == j ? 0.5 * st[o[F_AL_U0] + i] : 0.0)) * st[o[F_SWW] + e];
-            }
-            for (int m = t; m < M; m += VBT) d -= st[o[F_GC] + m];
-            for (int k = t; k < K; k += VBT) {
-                double mu = st[o[F_MUC] + k];
-                d += (double)M * (-0.5 * st[o[F_AL_U0] + k] * mu * mu + 0.5 * st[o[F_AL_U1] + k]);
-            }
-            double LC = vb_block_sum(d, red);
-            // alpha
-            double f = 0.0;
-            if (p.has_alpha) {
-                for (int k = t; k < K; k += VBT) {
-                    double a0 = st[o[F_A0] + k], b0 = st[o[F_B0] + k];
-                    f += (-b0 - st[o[F_AL_PHI0] + k]) * st[o[F_AL_U0] + k]
-                       + (a0 - st[o[F_AL_PHI1] + k]) * st[o[F_AL_U1] + k]
-                       + (a0 * log(b0) - lgamma(a0)) - st[o[F_AL_G] + k];
-                }
-            }
-            double LA = vb_block_sum(f, red);
-            if (t == 0) {
-                double LT = 0.0;
-                if (p.has_tau) {
-                    double a0 = st[o[F_TA0]], b0 = st[o[F_TB0]];
-                    LT = (-b0 - st[o[F_TAU_PHI0]]) * tau + (a0 - st[o[F_TAU_PHI1]]) * logtau
-                       + (a0 * log(b0) - lgamma(a0)) - st[o[F_TAU_G]];
-                }
-                double L = (((LY + LX) + LC) + LA) + LT;
-                int it = ctrl[0];
-                if (it < cap) {
-                    double *row = p.Lhist + (size_t)it * 6;
-                    row[0] = LY; row[1] = LX; row[2] = LC; row[3] = LA; row[4] = LT; row[5] = L;
-                }
-                double L0 = st[o[F_LPREV]];
-                st[o[F_LPREV]] = L;
-                ctrl[0] = it + 1;
-                // vmp.py:738-747 (tol < 0 or no previous bound: test disabled)
-                if (p.tol >= 0.0 && L0 == L0) {
-                    double div = 0.5 * (fabs(L0) + fabs(L));
-                    if ((L - L0) / div < p.tol) ctrl[1] = 1;
-                }
-                if (ctrl[2]) ctrl[1] = 1;
-                __threadfence();
-            }
+            op_bound(full, red, st + o[F_LAMX], st[o[F_LOGDETX]]);
         }
     }
     if (staged && !dry) {

@@ -76,14 +76,21 @@ __device__ __forceinline__ void spd_warp_inverse(const double *S, double *B, dou
 // two = 1 (K even, >= 6K+1 threads): TWO pivots per step — the 2 x 2 pivot block of an SPD Schur complement is
 // SPD, so it is inverted in closed form and rows k, k+1 are eliminated together: K/2 steps of two barriers
 // instead of K (the steps are barrier-latency bound, not flop bound).  rowk: 2 x 2K, colk: 2 x K scratch.
+// tt >= 0: the routine is run by a TEAM of tn threads (thread index tt within it) that meets at named barrier tbar
+// instead of the whole CTA (pca_vb_ops runs two small ops side by side on the two halves of its CTA).
+#define SPD_GJ_SYNC()                                                                        \
+    do {                                                                                     \
+        if (tt < 0) __syncthreads();                                                         \
+        else asm volatile("bar.sync %0, %1;\n" ::"r"(tbar), "r"(nt) : "memory");             \
+    } while (0)
 template <int KC>
 __device__ __forceinline__ void spd_cta_inverse_gj(double *G, double *rowk, double *colk, double *piv, int Krt, double *scal,
-                                                   int *flagword, int two = 0) {
+                                                   int *flagword, int two = 0, int tt = -1, int tn = 0, int tbar = 0) {
     const int K = KC ? KC : Krt, K2 = 2 * K, ldg = K2 + 1;
-    const int t = threadIdx.x, nt = blockDim.x;
+    const int t = tt < 0 ? (int)threadIdx.x : tt, nt = tt < 0 ? (int)blockDim.x : tn;
     if (two && (K & 1) == 0 && nt >= 2 * K2 + 2 * K + 1) {
         for (int k = 0; k < K; k += 2) {
-            __syncthreads();
+            SPD_GJ_SYNC();
             const double p00 = G[k * ldg + k], p01 = G[k * ldg + k + 1];
             const double p10 = G[(k + 1) * ldg + k], p11 = G[(k + 1) * ldg + k + 1];
             const double det = p00 * p11 - p01 * p10;
@@ -99,7 +106,7 @@ __device__ __forceinline__ void spd_cta_inverse_gj(double *G, double *rowk, doub
                 piv[k] = p00;                 // both must be positive for an SPD matrix; their product is the block's det
                 piv[k + 1] = det / p00;
             }
-            __syncthreads();
+            SPD_GJ_SYNC();
             for (int e = t; e < K * K2; e += nt) {
                 const int i = e / K2, j = e - i * K2;
                 const double r0 = rowk[j], r1 = rowk[K2 + j];
@@ -112,7 +119,7 @@ __device__ __forceinline__ void spd_cta_inverse_gj(double *G, double *rowk, doub
         }
     } else {
     for (int k = 0; k < K; ++k) {
-        __syncthreads();
+        SPD_GJ_SYNC();
         const double p = G[k * ldg + k];
         const double r = 1.0 / p;
         if (t < K2) rowk[t] = G[k * ldg + t] * r;
@@ -125,7 +132,7 @@ __device__ __forceinline__ void spd_cta_inverse_gj(double *G, double *rowk, doub
                 else piv[k] = p;
             }
         }
-        __syncthreads();
+        SPD_GJ_SYNC();
         for (int e = t; e < K * K2; e += nt) {
             const int i = e / K2, j = e - i * K2;
             const double rj = rowk[j];
@@ -133,7 +140,7 @@ __device__ __forceinline__ void spd_cta_inverse_gj(double *G, double *rowk, doub
         }
     }
     }
-    __syncthreads();
+    SPD_GJ_SYNC();
     if (t < 32) {
         double s = 0.0;
         int bad = 0;
@@ -149,9 +156,11 @@ __device__ __forceinline__ void spd_cta_inverse_gj(double *G, double *rowk, doub
             if (bad) atomicOr(flagword, BPK_FLAG_NOTSPD);
         }
     }
-    __syncthreads();
+    SPD_GJ_SYNC();
 }
 
+
+#undef SPD_GJ_SYNC
 
 // (A single-warp, register-resident variant of this elimination for K = 16 — lane = column, shuffles instead of
 // barriers — was measured SLOWER inside the fused sweep's tail: 20.6 us vs 10.4 us per ROW op; it is not kept.)
