@@ -49,10 +49,6 @@ class VB:
         self.L = np.array(())
         self.cputime = np.array(())
         self.l = {node: np.array([]) for node in self.model}
-        if autosave_iterations:
-            # vmp.py:237-356, 750-758 write HDF5 checkpoints; that on-disk format is not implemented here,
-            # so refuse loudly instead of silently never saving
-            raise NotImplementedError("autosave / VB.save / VB.load (HDF5 checkpoints) are not implemented in bayespy_b200")
         self.autosave_iterations = autosave_iterations
         self.autosave_filename = autosave_filename
         names = [node.name for node in self.model]
@@ -76,11 +72,66 @@ class VB:
                 return node
         raise ValueError("Node %s not found" % (name,))
 
-    def save(self, *args, **kwargs):
-        raise NotImplementedError("VB.save (HDF5, vmp.py:237-330) is not implemented in bayespy_b200")
+    # ---- checkpoints (vmp.py:237-356; container and hierarchy: inference/checkpoint.py) ------------------------
+    def save(self, *nodes, filename=None):
+        from . import checkpoint
+        nodes = self.model if len(nodes) == 0 else [self[n] for n in nodes if n is not None]
+        if not filename:
+            if self.autosave_filename:
+                filename = self.autosave_filename
+            else:
+                raise Exception("Filename must be given.")
+        w = checkpoint.open_writer(filename)
+        try:
+            for node in nodes:
+                if node.name == "":
+                    raise Exception("In order to save nodes, they must have (unique) names.")
+                if hasattr(node, "u") and hasattr(node, "observed"):
+                    checkpoint.save_node(w, node, "nodes/%s" % node.name)
+            w.put("L", self.L)
+            w.put("cputime", self.cputime)
+            w.put("iter", self.iter)
+            w.put("converged", self.converged)
+            if self.callback_output is not None:
+                w.put("callback_output", self.callback_output)
+            for node in nodes:
+                w.put("boundterms/%s" % node.name, self.l[node])
+            if self.user_data is not None:
+                for key, value in self.user_data.items():
+                    w.put("user_data/%s" % key, value)
+        finally:
+            w.close()
 
-    def load(self, *args, **kwargs):
-        raise NotImplementedError("VB.load (HDF5, vmp.py:332-356) is not implemented in bayespy_b200")
+    def load(self, *nodes, filename=None, nodes_only=False):
+        from . import checkpoint
+        if not filename:
+            if self.autosave_filename:
+                filename = self.autosave_filename
+            else:
+                raise Exception("Filename must be given.")
+        r = checkpoint._Reader(filename)
+        try:
+            nodes = self.model if len(nodes) == 0 else [self[n] for n in nodes if n is not None]
+            for node in nodes:
+                if node.name == "":
+                    raise Exception("In order to load nodes, they must have (unique) names.")
+                if hasattr(node, "u") and hasattr(node, "observed"):
+                    checkpoint.load_node(r, node, "nodes/%s" % node.name)
+            for plan in self.plans:                      # cached statistics / device state describe the old posterior
+                for attr in ("_stats", "_mstats", "_e2", "_me2", "_res_cache"):
+                    if hasattr(plan, attr):
+                        setattr(plan, attr, None)
+            if not nodes_only:
+                self.L = r.get("L")
+                self.cputime = r.get("cputime")
+                self.iter = int(r.get("iter"))
+                self.converged = bool(r.get("converged"))
+                for node in nodes:
+                    self.l[node] = r.get("boundterms/%s" % node.name)
+                if r.has("callback_output"):
+                    self.callback_output = r.get("callback_output")
+        finally:
+            r.close()
 
     def set_callback(self, callback):
         self.callback = callback
@@ -212,6 +263,12 @@ class VB:
                 self.converged = True
         self.annealing_changed = False
         self.iter += 1
+        # vmp.py:750-758
+        if self.autosave_iterations > 0 and np.mod(self.iter, self.autosave_iterations) == 0:
+            if self.autosave_filename is not None:
+                self.save(filename=self.autosave_filename)
+                if verbose:
+                    self.print("Auto-saved to %s" % self.autosave_filename)
         return self.converged
 
     def set_annealing(self, annealing):
