@@ -79,6 +79,8 @@ PROTOTYPES = {
     "bpk_dirichlet_moments": (C.c_int, [_dp, C.c_int64, C.c_int, _dp, _dp, C.c_int]),
     "bpk_softmax_moments": (C.c_int, [_dp, C.c_int64, C.c_int, _dp, _dp]),
     "bpk_one_hot": (C.c_int, [_vp, C.c_int64, C.c_int, _dp, C.c_int]),
+    "bpk_take": (C.c_int, [_dp, C.c_int64, C.c_int64, C.c_int64, _vp, C.c_int64, _dp]),
+    "bpk_put_add": (C.c_int, [_dp, C.c_int64, C.c_int64, C.c_int64, _vp, _vp, C.c_int64, _dp]),
     "bpk_pca_xsweep": (C.c_int, [_dp, C.c_int64, C.c_int64, C.c_int, _dp, _dp, _dp, _dp]),
     "bpk_pca_stats": (C.c_int, [_dp, C.c_int64, C.c_int64, C.c_int, _dp, _dp]),
     "bpk_pca_xsweep_masked": (C.c_int, [_dp, _vp, C.c_int64, C.c_int64, C.c_int, _dp, _dp, C.c_double, _dp, _dp,
@@ -305,6 +307,12 @@ class CudaBackend:
 
     def one_hot(self, labels, n, K, u, check=True):
         self._chk(self.lib.bpk_one_hot(labels, n, K, u, int(check)))
+
+    def take(self, src, pre, L, post, idx, J, out):
+        self._chk(self.lib.bpk_take(src, pre, L, post, idx, J, out))
+
+    def put_add(self, src, pre, J, post, order, start, L, out):
+        self._chk(self.lib.bpk_put_add(src, pre, J, post, order, start, L, out))
 
     # -- fused sweeps
     def pca_xsweep(self, Y, M, N, K, A, b, X, stats):

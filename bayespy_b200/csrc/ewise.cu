@@ -94,3 +94,46 @@ extern "C" int bpk_ewise(int op, int nd, const int64_t *shape,
     BPK_LAUNCH(ewise_kernel, (unsigned)blocks, 256, 0, A);
     return BPK_OK;
 }
+
+// ---- index gathers along one plate axis (nodes/take.py) ---------------------------------------------------------
+// out[a][j][c] = in[a][idx[j]][c]; pure data movement: bit-exact
+__global__ void __launch_bounds__(256) take_kernel(const double *__restrict__ in, int64_t pre, int64_t L, int64_t post,
+                                                   const int64_t *__restrict__ idx, int64_t J, double *__restrict__ out) {
+    const int64_t total = pre * J * post;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = e % post, j = (e / post) % J, a = e / (post * J);
+        out[e] = in[(a * L + idx[j]) * post + c];
+    }
+}
+// out[a][i][c] = sum over the j with idx[j] == i of in[a][j][c], in increasing j (order/start: stable sort of idx, CSR)
+__global__ void __launch_bounds__(256) put_add_kernel(const double *__restrict__ in, int64_t pre, int64_t J, int64_t post,
+                                                      const int64_t *__restrict__ order, const int64_t *__restrict__ start,
+                                                      int64_t L, double *__restrict__ out) {
+    const int64_t total = pre * L * post;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = e % post, i = (e / post) % L, a = e / (post * L);
+        double s = 0.0;
+        for (int64_t q = start[i]; q < start[i + 1]; ++q) s += in[(a * J + order[q]) * post + c];
+        out[e] = s;
+    }
+}
+static unsigned take_grid(int64_t total) {
+    int64_t blocks = (total + 255) / 256, cap = (int64_t)g_bpk.sm_count * 32;
+    if (blocks > cap) blocks = cap;
+    return (unsigned)(blocks < 1 ? 1 : blocks);
+}
+extern "C" int bpk_take(const double *in, int64_t pre, int64_t L, int64_t post, const int64_t *idx, int64_t J, double *out) {
+    BPK_REQUIRE_INIT();
+    if (pre < 0 || L < 1 || post < 0 || J < 0) return bpk_set_error(BPK_EINVAL, "bpk_take: bad shape");
+    if (pre * J * post == 0) return BPK_OK;
+    BPK_LAUNCH(take_kernel, take_grid(pre * J * post), 256, 0, in, pre, L, post, idx, J, out);
+    return BPK_OK;
+}
+extern "C" int bpk_put_add(const double *in, int64_t pre, int64_t J, int64_t post, const int64_t *order,
+                           const int64_t *start, int64_t L, double *out) {
+    BPK_REQUIRE_INIT();
+    if (pre < 0 || L < 1 || post < 0 || J < 0) return bpk_set_error(BPK_EINVAL, "bpk_put_add: bad shape");
+    if (pre * L * post == 0) return BPK_OK;
+    BPK_LAUNCH(put_add_kernel, take_grid(pre * L * post), 256, 0, in, pre, J, post, order, start, L, out);
+    return BPK_OK;
+}

@@ -816,12 +816,20 @@ pca_vbloop_kernel(const __grid_constant__ CUtensorMap tmapY, int64_t M, int64_t 
     int xg = 0;                  // X -> S hand-offs (stages that carried a tile)
     int issued = 0;              // producer (warp 0): stages issued
     // producer: take the next tile from the global counter and start its load (or post the end-of-sweep sentinel)
-    bool ended = false;
+    // The grab is software-pipelined: the counter is read one issue ahead (`pending`), so the L2 round trip of the atomic
+    // overlaps the tile in between instead of sitting on X-warp 0's critical path; no tile is lost, because a producer
+    // processes every valid index it ever drew (after the first index >= ntiles every later one is >= ntiles too).
+    bool ended = false, have_pending = false;
+    long long pending = 0;
     auto issue = [&]() {
         const int pos = issued;
         const int slot = pos % STAGES;
         long long tile = 0;
-        if (lane == 0) tile = (long long)atomicAdd(tctr, 1ull);
+        if (lane == 0) {
+            tile = have_pending ? pending : (long long)atomicAdd(tctr, 1ull);
+            if (tile < ntiles) pending = (long long)atomicAdd(tctr, 1ull);     // needed at the next issue only
+        }
+        have_pending = true;
         tile = __shfl_sync(0xffffffffu, tile, 0);
         if (pos >= STAGES) mbar_wait(&empty[slot], (uint32_t)((pos / STAGES - 1) & 1));
         if (tile < ntiles) {
@@ -852,6 +860,7 @@ pca_vbloop_kernel(const __grid_constant__ CUtensorMap tmapY, int64_t M, int64_t 
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         }
         ended = false;
+        have_pending = false;                                             // the counter was reset for this sweep
         if (w == 0)
             while (!ended && issued < ig + DIST) issue();                 // loads first ...
         // ... then this sweep's A, b -> shared memory (coalesced; one L2 fetch per CTA instead of one per warp)

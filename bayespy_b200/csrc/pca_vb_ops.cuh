@@ -95,8 +95,11 @@ __host__ __device__ inline void pca_vb_offsets(int M, int K, int64_t *off /* [F_
 
 // scratch of the small ops in doubles: augmented K x 2K Gauss-Jordan tile (odd pitch), two pivot rows / columns
 // (the elimination takes two pivots per step), pivots, reduction slots; then a copy of Lam_x and a second set of
-// reduction slots for the op that runs side by side with another one (BOUND next to XPRE, TAU next to ALPHA)
-__host__ __device__ inline size_t pca_vb_smem_doubles(int K) { return (size_t)K * (2 * K + 1) + 7 * (size_t)K + 64 + (size_t)K * K + 64; }
+// reduction slots for the op that runs side by side with another one (BOUND next to XPRE, TAU next to ALPHA), and a
+// backup of what XPRE overwrites (restored if the bound it ran next to raised the stop word; M <= 64 only)
+__host__ __device__ inline size_t pca_vb_smem_doubles(int K) {
+    return (size_t)K * (2 * K + 1) + 7 * (size_t)K + 64 + (size_t)K * K + 256 + ((size_t)PCA_MP * K + 2 * (size_t)K * K + K + 1);
+}
 
 struct PcaVbArgs {
     int M, K, has_alpha, has_tau;
@@ -186,7 +189,7 @@ static __device__ __noinline__ void pca_vb_ops_t(const PcaVbArgs &p, double *sm,
     const int VBT = blockDim.x;
     const int M = MC ? MC : p.M, K = KC ? KC : p.K, K2 = 2 * K, ldg = K2 + 1, t = threadIdx.x;
     double *G = sm, *rowk = G + (size_t)K * ldg, *colk = rowk + 2 * K2, *piv = colk + 2 * K, *red = piv + K, *scal = red + 32;
-    double *lamx_old = scal + 32, *red2 = lamx_old + (size_t)K * K;
+    double *lamx_old = scal + 32, *red2 = lamx_old + (size_t)K * K, *xbak = red2 + 256;
     __shared__ int64_t o[F_COUNT + 1];
     __shared__ int dry_ctrl[4];
     if (t == 0) pca_vb_offsets(M, K, o);
@@ -288,55 +291,55 @@ static __device__ __noinline__ void pca_vb_ops_t(const PcaVbArgs &p, double *sm,
         }
     };
     auto op_bound = [&](const VbTeam &T, double *redp, const double *lamx, const double logdetx) {
-        // expfamily.py:400-480 for Y, X, C, alpha, tau from the plate-summed statistics
+        // expfamily.py:400-480 for Y, X, C, alpha, tau from the plate-summed statistics.  Every thread accumulates its
+        // share of the six sums the bound needs; ONE team reduction (two barriers) combines them.
         const double tau = st[o[F_TAU_U0]], logtau = st[o[F_TAU_U1]];
-        double E2 = vb_E2(st, o, M, K, redp, T);
-        double LY = -0.5 * tau * E2 + 0.5 * (double)M * Ng * (logtau - LOG2PI_D);
-        // X
+        const double *W = st + o[F_W], *Syx = st + o[F_STATS], *SWW = st + o[F_SWW], *SXXT = st + o[F_SXXT];
         const double *Sxx = st + o[F_STATS] + M * K, *sx = Sxx + K * K;
-        double a = 0.0;   // tr(Lam_x S_xx), (phi1_p - phi1_q):sum<xx^T>
-        double b = 0.0;
-        for (int e = T.t; e < K * K; e += T.n) {
-            int i = e / K, j = e - i * K;
-            double lam = lamx[e];
-            a += lam * Sxx[e];
-            b += (0.5 * lam - (i == j ? 0.5 * st[o[F_AX] + i] : 0.0)) * st[o[F_SXXT] + e];
-        }
-        double c = 0.0;   // phi0_p . s_x  and the prior cgf
-        for (int k = T.t; k < K; k += T.n) {
-            double ax = st[o[F_AX] + k], mu = st[o[F_MUX] + k];
-            c += ax * mu * sx[k] + Ng * (-0.5 * ax * mu * mu + 0.5 * log(ax));
-        }
-        double trLS = vb_team_sum(a, redp, T);
-        double LX = vb_team_sum(b + c, redp, T) - trLS + 0.5 * trLS - 0.5 * Ng * logdetx;
-        // C
-        double d = 0.0;
+        double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};   // [0] E2 cross terms, [1] tr(Lam_x S_xx), [2] X prior terms, [3] C, [4] alpha
         for (int e = T.t; e < M * K; e += T.n) {
-            int k = e % K;
-            d += (st[o[F_AL_U0] + k] * st[o[F_MUC] + k] - st[o[F_PHI0C] + e]) * st[o[F_W] + e];
+            const int k = e % K;
+            v[0] -= 2.0 * W[e] * Syx[e];
+            v[3] += (st[o[F_AL_U0] + k] * st[o[F_MUC] + k] - st[o[F_PHI0C] + e]) * W[e];
         }
         for (int e = T.t; e < K * K; e += T.n) {
-            int i = e / K, j = e - i * K;
-            d += (0.5 * st[o[F_LAMC] + e] - (i == j ? 0.5 * st[o[F_AL_U0] + i] : 0.0)) * st[o[F_SWW] + e];
+            const int i = e / K, j = e - i * K;
+            const double lam = lamx[e];
+            v[0] += SWW[e] * SXXT[e];
+            v[1] += lam * Sxx[e];
+            v[2] += (0.5 * lam - (i == j ? 0.5 * st[o[F_AX] + i] : 0.0)) * SXXT[e];
+            v[3] += (0.5 * st[o[F_LAMC] + e] - (i == j ? 0.5 * st[o[F_AL_U0] + i] : 0.0)) * SWW[e];
         }
-        for (int m = T.t; m < M; m += T.n) d -= st[o[F_GC] + m];
         for (int k = T.t; k < K; k += T.n) {
-            double mu = st[o[F_MUC] + k];
-            d += (double)M * (-0.5 * st[o[F_AL_U0] + k] * mu * mu + 0.5 * st[o[F_AL_U1] + k]);
-        }
-        double LC = vb_team_sum(d, redp, T);
-        // alpha
-        double f = 0.0;
-        if (p.has_alpha) {
-            for (int k = T.t; k < K; k += T.n) {
-                double a0 = st[o[F_A0] + k], b0 = st[o[F_B0] + k];
-                f += (-b0 - st[o[F_AL_PHI0] + k]) * st[o[F_AL_U0] + k]
-                   + (a0 - st[o[F_AL_PHI1] + k]) * st[o[F_AL_U1] + k]
-                   + (a0 * log(b0) - lgamma(a0)) - st[o[F_AL_G] + k];
+            const double ax = st[o[F_AX] + k], mux = st[o[F_MUX] + k], muc = st[o[F_MUC] + k];
+            v[2] += ax * mux * sx[k] + Ng * (-0.5 * ax * mux * mux + 0.5 * log(ax));
+            v[3] += (double)M * (-0.5 * st[o[F_AL_U0] + k] * muc * muc + 0.5 * st[o[F_AL_U1] + k]);
+            if (p.has_alpha) {
+                const double a0 = st[o[F_A0] + k], b0 = st[o[F_B0] + k];
+                v[4] += (-b0 - st[o[F_AL_PHI0] + k]) * st[o[F_AL_U0] + k]
+                      + (a0 - st[o[F_AL_PHI1] + k]) * st[o[F_AL_U1] + k]
+                      + (a0 * log(b0) - lgamma(a0)) - st[o[F_AL_G] + k];
             }
         }
-        double LA = vb_team_sum(f, redp, T);
+        for (int m = T.t; m < M; m += T.n) v[3] -= st[o[F_GC] + m];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) v[q] = warp_sum(v[q]);
+        vb_team_sync(T);
+        if ((T.t & 31) == 0) {
+#pragma unroll
+            for (int q = 0; q < 5; ++q) redp[(T.t >> 5) * 8 + q] = v[q];
+        }
+        vb_team_sync(T);
         if (T.t == 0) {
+            double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+            const int nw = T.n >> 5;
+            for (int w = 0; w < nw; ++w)
+#pragma unroll
+                for (int q = 0; q < 5; ++q) s[q] += redp[w * 8 + q];
+            const double E2 = st[o[F_SUMSQ]] + s[0];
+            const double LY = -0.5 * tau * E2 + 0.5 * (double)M * Ng * (logtau - LOG2PI_D);
+            const double LX = s[2] - s[1] + 0.5 * s[1] - 0.5 * Ng * logdetx;
+            const double LC = s[3], LA = s[4];
             double LT = 0.0;
             if (p.has_tau) {
                 double a0 = st[o[F_TA0]], b0 = st[o[F_TB0]];
@@ -379,15 +382,23 @@ static __device__ __noinline__ void pca_vb_ops_t(const PcaVbArgs &p, double *sm,
                 ++ip;
                 continue;
             }
-            if (op == BPK_VBOP_BOUND && op2 == BPK_VBOP_XPRE) {
+            if (op == BPK_VBOP_BOUND && op2 == BPK_VBOP_XPRE && M <= PCA_MP) {
                 // the bound of this sweep next to the shared part of the NEXT q(X): XPRE overwrites Lam_x and log det Lam_x,
-                // which the bound still needs from the q(X) that is in force — it reads them from a copy
-                for (int e = t; e < K * K; e += VBT) lamx_old[e] = st[o[F_LAMX] + e];
+                // which the bound still needs from the q(X) that is in force — it reads them from a copy.  If the bound
+                // raises the stop word (converged: the reference would not have touched X again), XPRE is undone.
+                const int64_t nblk = o[F_BX + 1] - o[F_COVX];          // Cov_x, Lam_x, log det, A, b: one contiguous block
+                for (int e = t; e < K * K; e += VBT) { lamx_old[e] = st[o[F_LAMX] + e]; xbak[nblk + e] = st[o[F_PHI1X] + e]; }
+                for (int64_t e = t; e < nblk; e += VBT) xbak[e] = st[o[F_COVX] + e];
                 const double logdetx_old = st[o[F_LOGDETX]];
                 __syncthreads();
                 const int h = VBT / 2;
                 if (t < h) op_xpre(VbTeam{t, h, 1});
                 else op_bound(VbTeam{t - h, h, 2}, red2, lamx_old, logdetx_old);
+                __syncthreads();
+                if (*stop) {
+                    for (int e = t; e < K * K; e += VBT) st[o[F_PHI1X] + e] = xbak[nblk + e];
+                    for (int64_t e = t; e < nblk; e += VBT) st[o[F_COVX] + e] = xbak[e];
+                }
                 vb_stamp(dbg, 8 + ip + 1);
                 ++ip;
                 continue;
@@ -542,7 +553,7 @@ static __device__ __noinline__ void pca_vb_ops_t(const PcaVbArgs &p, double *sm,
         } else if (op == BPK_VBOP_TAU) {
             op_tau(full, red);
         } else if (op == BPK_VBOP_BOUND) {
-            op_bound(full, red, st + o[F_LAMX], st[o[F_LOGDETX]]);
+            op_bound(full, red2, st + o[F_LAMX], st[o[F_LOGDETX]]);
         }
     }
     if (staged && !dry) {

@@ -10,3 +10,4 @@ from ..engine.dirichlet import Dirichlet                                      # 
 from ..engine.categorical import Categorical                                  # noqa: F401
 from ..engine.mixture import Mixture                                          # noqa: F401
 from ..engine.gmc import GaussianMarkovChain                                  # noqa: F401
+from ..engine.take import Take                                                # noqa: F401

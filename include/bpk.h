@@ -185,6 +185,14 @@ int bpk_softmax_moments(const double *phi, int64_t n, int K, double *u, double *
 /* one-hot encode integer labels (categorical.py:30-47); bit-exact           */
 int bpk_one_hot(const int64_t *labels, int64_t n, int K, double *u, int check);
 
+/* index gathers along one plate axis (nodes/take.py:63-88, misc.py:549-585 put_simple); idx on the device, already
+ * normalised to [0, L).  bpk_take: out[a][j][c] = in[a][idx[j]][c] (bit-exact data movement).  bpk_put_add: the
+ * inverse with accumulation, out[a][i][c] = sum_{j: idx[j]==i} in[a][j][c] in increasing j; order = stable argsort
+ * of idx, start = its CSR offsets (L+1 entries), both built by the host once per node.                              */
+int bpk_take(const double *in, int64_t pre, int64_t L, int64_t post, const int64_t *idx, int64_t J, double *out);
+int bpk_put_add(const double *in, int64_t pre, int64_t J, int64_t post, const int64_t *order,
+                const int64_t *start, int64_t L, double *out);
+
 /* ---- fused sweep kernels (seam 3) -------------------------- */
 /* PCA / factor model  y[m,n] ~ N(w_m . x_n, 1/tau), fully observed.
  * One pass over Y: x_n = A y_n + b for every column n (A: [K][M], b: [K]),

@@ -344,6 +344,23 @@ class RefBackend:
         o[np.nonzero(ok)[0], l[ok]] = 1.0
         _dense(u, (n, K))[...] = o
 
+    def take(self, src, pre, L, post, idx, J, out):
+        """take.py:63-73 (np.take along one plate axis)."""
+        self._launches += 1
+        x = _dense(src, (pre, L, post))
+        ix = _dense(idx, (J,), np.int64)
+        _dense(out, (pre, J, post))[...] = x[:, ix, :]
+
+    def put_add(self, src, pre, J, post, order, start, L, out):
+        """misc.py:549-585 put_simple / take.py:76-88: inverse of take with accumulation."""
+        self._launches += 1
+        x = _dense(src, (pre, J, post))
+        od = _dense(order, (J,), np.int64)
+        stt = _dense(start, (L + 1,), np.int64)
+        o = _dense(out, (pre, L, post))
+        for i in range(L):
+            o[:, i, :] = x[:, od[stt[i]:stt[i + 1]], :].sum(axis=1) if stt[i + 1] > stt[i] else 0.0
+
     # ---- fused sweeps -----------------------------------------------------------------
     def pca_xsweep(self, Y, M, N, K, A, b, X, stats):
         """x_n = A y_n + b and the plate sums of dot.py:581 / :355,403 (see csrc/pca.cu)."""

@@ -485,8 +485,44 @@ def pca_bench_prefix(name="pca_bench_100k", N=100_000, iters=5):
     save(name, **out)
 
 
+def take_models(name="take"):
+    """nodes/take.py: group means picked by integer labels (messages are scatter-added back), a masked observation,
+    and a vector-valued node taken along plate axis -2 with a matrix of indices."""
+    from bayespy.nodes import Take
+    rs = np.random.RandomState(31)
+    N, G = 40, 3
+    idx = rs.randint(0, G, size=N)
+    idx[:3] = [-1, -3, 2]                                  # negative indices count from the end (np.take)
+    y = np.array([-2.0, 0.5, 3.0])[idx % G] + 0.3 * rs.randn(N)
+    mask = rs.rand(N) < 0.85
+    mu = GaussianARD(0, 1e-3, plates=(G,), name="mu")
+    m = Take(mu, idx, name="m")
+    tau = Gamma(1e-3, 1e-3, name="tau")
+    Y = GaussianARD(m, tau, name="Y")
+    Y.observe(y, mask=mask)
+    Q = VB(mu, tau, Y)
+    Q.update(repeat=5, verbose=False, tol=0)
+    out = dict(idx=idx, y=y, mask=mask, L=Q.L[:5], m_u0=np.asarray(m.get_moments()[0]), m_u1=np.asarray(m.get_moments()[1]))
+    node_state("mu", mu, out)
+    node_state("tau", tau, out)
+    # vector-valued, plate axis -2, matrix of indices
+    X = GaussianARD(0, 1, plates=(3, 4), shape=(2,), name="X")
+    X.initialize_from_value(rs.randn(3, 4, 2))
+    idx2 = np.array([[2, 0], [1, 1]])
+    Z = Take(X, idx2, plate_axis=-2, name="Z")
+    assert Z.plates == (2, 2, 4)
+    y2 = rs.randn(2, 2, 4, 2)
+    W = GaussianARD(Z, 2.0, name="W")
+    W.observe(y2)
+    Q2 = VB(X, W)
+    Q2.update(repeat=2, verbose=False, tol=0)
+    out.update(idx2=idx2, y2=y2, X_init=np.asarray(X.u[0]) * 0 + 0, L2=Q2.L[:2], Z_u0=np.asarray(Z.get_moments()[0]))
+    node_state("X", X, out)
+    save(name, **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["quickstart", "pca", "linalg", "summul", "dist", "gmm", "gmc", "rot", "dot", "mixard", "gmcplates", "gmcvarying", "pcabench", "pcamasked64"]
+    which = sys.argv[1:] or ["quickstart", "pca", "linalg", "summul", "dist", "gmm", "gmc", "rot", "dot", "mixard", "gmcplates", "gmcvarying", "pcabench", "pcamasked64", "take"]
     if "quickstart" in which:
         quickstart()
     if "pca" in which:
@@ -510,6 +546,8 @@ if __name__ == "__main__":
         pca_rotated()
     if "gmcplates" in which:
         lssm_plated()
+    if "take" in which:
+        take_models()
     if "pcamasked64" in which:
         pca("pca_masked_64x16", 64, 300, 16, mask_p=0.8, iters=4)
     if "pcabench" in which:
