@@ -11,3 +11,4 @@ from ..engine.categorical import Categorical                                  # 
 from ..engine.mixture import Mixture                                          # noqa: F401
 from ..engine.gmc import GaussianMarkovChain                                  # noqa: F401
 from ..engine.take import Take                                                # noqa: F401
+from ..engine.gate import Gate                                                # noqa: F401

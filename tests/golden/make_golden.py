@@ -521,8 +521,51 @@ def take_models(name="take"):
     save(name, **out)
 
 
+def gate_models(name="gate"):
+    """nodes/gate.py: a mixture written with Gate (scalar and vector-valued gated nodes, gated plate -1 and -2)."""
+    from bayespy.nodes import Gate
+    rs = np.random.RandomState(41)
+    N, K = 50, 3
+    z_true = rs.randint(0, K, size=N)
+    y = np.array([-3.0, 0.0, 4.0])[z_true] + 0.5 * rs.randn(N)
+    alpha = Dirichlet(np.ones(K), name="alpha")
+    Z = Categorical(alpha, plates=(N,), name="Z")
+    z_init = rs.randint(0, K, size=N)
+    Z.initialize_from_value(z_init)
+    mu = GaussianARD(0, 1e-3, plates=(K,), name="mu")
+    mu.initialize_from_value(np.array([-1.0, 0.5, 2.0]))
+    F = Gate(Z, mu, name="F")
+    assert F.plates == (N,)
+    tau = Gamma(1e-3, 1e-3, name="tau")
+    Y = GaussianARD(F, tau, name="Y")
+    Y.observe(y)
+    Q = VB(Z, mu, alpha, tau, Y)
+    Q.update(repeat=5, verbose=False, tol=0)
+    out = dict(y=y, z_init=z_init, L=Q.L[:5], F_u0=np.asarray(F.get_moments()[0]), F_u1=np.asarray(F.get_moments()[1]))
+    for nm, node in (("Z", Z), ("mu", mu), ("alpha", alpha), ("tau", tau)):
+        node_state(nm, node, out)
+    # vector-valued node gated over plate axis -2
+    X = GaussianARD(0, 1, plates=(K, 4), shape=(2,), name="X")
+    X_init = rs.randn(K, 4, 2)
+    X.initialize_from_value(X_init)
+    Z2 = Categorical(np.ones(K) / K, plates=(6, 1), name="Z2")
+    z2_init = rs.randint(0, K, size=(6, 1))
+    Z2.initialize_from_value(z2_init)
+    G2 = Gate(Z2, X, gated_plate=-2, name="G2")
+    assert G2.plates == (6, 4)
+    y2 = rs.randn(6, 4, 2)
+    W = GaussianARD(G2, 1.5, name="W")
+    W.observe(y2)
+    Q2 = VB(Z2, X, W)
+    Q2.update(repeat=3, verbose=False, tol=0)
+    out.update(X_init=X_init, z2_init=z2_init, y2=y2, L2=Q2.L[:3], G2_u0=np.asarray(G2.get_moments()[0]))
+    node_state("Z2", Z2, out)
+    node_state("X", X, out)
+    save(name, **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["quickstart", "pca", "linalg", "summul", "dist", "gmm", "gmc", "rot", "dot", "mixard", "gmcplates", "gmcvarying", "pcabench", "pcamasked64", "take"]
+    which = sys.argv[1:] or ["quickstart", "pca", "linalg", "summul", "dist", "gmm", "gmc", "rot", "dot", "mixard", "gmcplates", "gmcvarying", "pcabench", "pcamasked64", "take", "gate"]
     if "quickstart" in which:
         quickstart()
     if "pca" in which:
@@ -546,6 +589,8 @@ if __name__ == "__main__":
         pca_rotated()
     if "gmcplates" in which:
         lssm_plated()
+    if "gate" in which:
+        gate_models()
     if "take" in which:
         take_models()
     if "pcamasked64" in which:

@@ -1,0 +1,69 @@
+"""``Gate`` (nodes/gate.py): a mixture written with a gating node, scalar and vector-valued, gated plate -1 and -2 —
+bound trajectories and every node's moments against the reference (tests/golden/gate.npz, make_golden.py: gate_models)."""
+import numpy as np
+import pytest
+
+from conftest import golden
+
+
+def _check(g, nodes):
+    for nm, node in nodes:
+        for i in range(len(node.u)):
+            np.testing.assert_allclose(np.asarray(node.u[i]), g["%s_u%d" % (nm, i)], rtol=1e-8, atol=1e-10,
+                                       err_msg="%s.u[%d]" % (nm, i))
+
+
+def test_gate_mixture_matches_the_reference(backend):
+    from bayespy_b200.nodes import Dirichlet, Categorical, GaussianARD, Gamma, Gate
+    from bayespy_b200.inference import VB
+    g = golden("gate")
+    N, K = len(g["y"]), 3
+    alpha = Dirichlet(np.ones(K), name="alpha")
+    Z = Categorical(alpha, plates=(N,), name="Z")
+    Z.initialize_from_value(g["z_init"])
+    mu = GaussianARD(0, 1e-3, plates=(K,), name="mu")
+    mu.initialize_from_value(np.array([-1.0, 0.5, 2.0]))
+    F = Gate(Z, mu, name="F")
+    assert tuple(F.plates) == (N,)
+    tau = Gamma(1e-3, 1e-3, name="tau")
+    Y = GaussianARD(F, tau, name="Y")
+    Y.observe(g["y"])
+    Q = VB(Z, mu, alpha, tau, Y)
+    Q.update(repeat=5, verbose=False, tol=0)
+    np.testing.assert_allclose(Q.L[:5], g["L"], rtol=1e-9)
+    _check(g, (("Z", Z), ("mu", mu), ("alpha", alpha), ("tau", tau)))
+    for i in range(2):
+        np.testing.assert_allclose(np.asarray(F.get_moments()[i]), g["F_u%d" % i], rtol=1e-8)
+
+
+def test_gate_vector_valued_inner_plate(backend):
+    from bayespy_b200.nodes import Categorical, GaussianARD, Gate
+    from bayespy_b200.inference import VB
+    g = golden("gate")
+    K = 3
+    X = GaussianARD(0, 1, plates=(K, 4), shape=(2,), name="X")
+    X.initialize_from_value(g["X_init"])
+    Z2 = Categorical(np.ones(K) / K, plates=(6, 1), name="Z2")
+    Z2.initialize_from_value(g["z2_init"])
+    G2 = Gate(Z2, X, gated_plate=-2, name="G2")
+    assert tuple(G2.plates) == (6, 4)
+    W = GaussianARD(G2, 1.5, name="W")
+    W.observe(g["y2"])
+    Q = VB(Z2, X, W)
+    Q.update(repeat=3, verbose=False, tol=0)
+    np.testing.assert_allclose(Q.L[:3], g["L2"], rtol=1e-9)
+    np.testing.assert_allclose(np.asarray(G2.get_moments()[0]), g["G2_u0"], rtol=1e-8, atol=1e-10)
+    _check(g, (("Z2", Z2), ("X", X)))
+
+
+def test_gate_argument_checks(oracle_backend):
+    from bayespy_b200.nodes import GaussianARD, Gate
+    X = GaussianARD(0, 1, plates=(3,))
+    with pytest.raises(ValueError):
+        Gate([0, 1], X, gated_plate=0)
+    with pytest.raises(ValueError):
+        Gate([0, 1], X, gated_plate=-2)
+    with pytest.raises(ValueError):
+        Gate([0, 5], X)                       # label outside the gated plate
+    F = Gate([0, 0, 2, 1], X)
+    assert tuple(F.plates) == (4,)
