@@ -296,6 +296,194 @@ __global__ void __launch_bounds__(PM_THREADS, 1) pmask_stats_kernel(PmArgs a, in
     }
 }
 
+// =====================================================================================
+// v3 of the two GEMM kernels.  v2 gave a warp ONE row tile of the output, so every DMMA needed its own mask-bit
+// extraction (shift, and, select): issue-bound at a third of the tensor pipe.  Here a warp owns one tile of the
+// OTHER dimension and all 19 row tiles: the mask fragment of a k-step is built once and feeds 19 DMMAs, the second
+// operand of each comes from shared memory (conflict-free pitch), one LDS per DMMA.
+//   build3: warp w <-> column tile w (8 columns); T = tau [<ww^T> | <w>] (152 x 64) staged once per launch
+//   stats3: warp w <-> (row tile m = w & 7, half of the k-steps w >> 3); the scratch tile <xx^T> | x (152 rows) of 64
+//           columns at a time is staged in shared memory
+// =====================================================================================
+#define PM3_WARPS 16
+#define PM3_THREADS (PM3_WARPS * 32)
+#define PM3_LDT 68                       // pitch of T and of the staged scratch sub-tile (= 4 mod 16)
+#define PM3_SUB 64                       // columns per staged scratch sub-tile (stats3)
+
+__global__ void __launch_bounds__(PM3_THREADS, 1) pmask_build3_kernel(PmArgs a) {
+    __shared__ unsigned long long bits[PM_TILE];
+    __shared__ double sAdd[PM_NT * 8];
+    extern __shared__ __align__(16) double pm_smem[];
+    double *sY = pm_smem;                              // [64][PM_LDY]
+    double *sT = sY + PM_MP * PM_LDY;                  // [152][PM3_LDT]: row p, column m
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, gr = lane >> 2, tg = lane & 3;
+    const int M = (int)a.M, K = a.K;
+    for (int e = threadIdx.x; e < PM_NT * 8 * PM_MP; e += blockDim.x) {
+        const int p = e / PM_MP, m = e - p * PM_MP;
+        double v = 0.0;
+        if (m < M) {
+            if (p >= SPD16_NPACK) { const int k = p - SPD16_NPACK; v = (k < K) ? a.tau * a.W[(int64_t)m * K + k] : 0.0; }
+            else { int i, j; pm_unpack(p, i, j); if (i < K && j < K) v = a.tau * a.WW[((int64_t)m * K + i) * K + j]; }
+        }
+        sT[p * PM3_LDT + m] = v;
+    }
+    for (int p = threadIdx.x; p < PM_NT * 8; p += blockDim.x) {
+        double v = 0.0;
+        if (p >= SPD16_NPACK) { const int k = p - SPD16_NPACK; v = (k < K && a.amu) ? a.amu[k] : 0.0; }
+        else { int i, j; pm_unpack(p, i, j); if (i == j) v = (i < K) ? a.alpha[i] : 1.0; }
+        sAdd[p] = v;
+    }
+    const int64_t ntiles = (a.nc + PM_TILE - 1) / PM_TILE;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t cl0 = tile * PM_TILE, n0 = a.c0 + cl0;
+        __syncthreads();
+        pm_stage_y(a.Y, a.M, a.N, n0, sY);
+        pm_pack_mask(a.mask, a.M, a.N, n0, bits);
+        double acc[PM_NT][2];
+#pragma unroll
+        for (int pt = 0; pt < PM_NT; ++pt) acc[pt][0] = acc[pt][1] = 0.0;
+        const int c = w * 8 + gr;                       // this lane's column of the A fragment
+        const unsigned long long wd = bits[c];
+#pragma unroll 2
+        for (int ks = 0; ks < 16; ++ks) {
+            const int m = ks * 4 + tg;
+            const bool on = (wd >> m) & 1ull;
+            const double am = on ? 1.0 : 0.0;
+            const double ay = on ? sY[m * PM_LDY + c] : 0.0;
+            const double *bt = sT + gr * PM3_LDT + m;    // B[k = tg -> m][n = gr -> p]
+#pragma unroll
+            for (int pt = 0; pt < 17; ++pt) pm_dmma(acc[pt][0], acc[pt][1], am, bt[pt * 8 * PM3_LDT]);
+            pm_dmma(acc[17][0], acc[17][1], ay, bt[17 * 8 * PM3_LDT]);
+            pm_dmma(acc[18][0], acc[18][1], ay, bt[18 * 8 * PM3_LDT]);
+        }
+        // D[n = gr][p = pt*8 + 2tg + j] -> scratch row p, column w*8 + gr
+#pragma unroll
+        for (int pt = 0; pt < PM_NT; ++pt)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int p = pt * 8 + 2 * tg + j;
+                a.S[(int64_t)p * a.chp + cl0 + c] = acc[pt][j] + sAdd[p];
+            }
+    }
+}
+
+__global__ void __launch_bounds__(PM3_THREADS, 1) pmask_stats3_kernel(PmArgs a, int first_chunk) {
+    __shared__ unsigned long long bits[PM_TILE];
+    __shared__ double red[PM3_WARPS][2];
+    extern __shared__ __align__(16) double pm_smem[];
+    double *sY = pm_smem;                              // [64][PM_LDY]
+    double *sS = sY + PM_MP * PM_LDY;                  // [152][PM3_LDT]: scratch rows of a 64-column sub-tile
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, gr = lane >> 2, tg = lane & 3;
+    const int K = a.K;
+    const int mt = w & 7, hf = w >> 3;
+    double acc[PM_NT][2];                              // rows m = mt*8 + gr, columns p = pt*8 + 2tg + {0,1}; this warp's half of the k-steps
+#pragma unroll
+    for (int pt = 0; pt < PM_NT; ++pt) acc[pt][0] = acc[pt][1] = 0.0;
+    double rowsum[10];                                 // scratch rows w, w+16, ...: sum over the columns (lane 0 holds it)
+#pragma unroll
+    for (int i = 0; i < 10; ++i) rowsum[i] = 0.0;
+    double sq = 0.0, sld = 0.0;
+    const int64_t ntiles = (a.nc + PM_TILE - 1) / PM_TILE;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t cl0 = tile * PM_TILE, n0 = a.c0 + cl0;
+        __syncthreads();
+        pm_stage_y(a.Y, a.M, a.N, n0, sY);
+        pm_pack_mask(a.mask, a.M, a.N, n0, bits);
+        for (int sub = 0; sub < PM_TILE / PM3_SUB; ++sub) {
+            const int cs = sub * PM3_SUB;
+            __syncthreads();
+            for (int e = threadIdx.x; e < PM_NT * 8 * PM3_SUB; e += blockDim.x) {
+                const int p = e / PM3_SUB, cc = e - p * PM3_SUB;
+                sS[p * PM3_LDT + cc] = (n0 + cs + cc < a.N) ? a.S[(int64_t)p * a.chp + cl0 + cs + cc] : 0.0;
+            }
+            __syncthreads();
+            // column sums of the staged rows (sum_n <xx^T>, sum_n x)
+#pragma unroll
+            for (int i = 0; i < 10; ++i) {
+                const int p = w + 16 * i;
+                if (p < PM_NT * 8) {
+                    double v = sS[p * PM3_LDT + lane] + sS[p * PM3_LDT + 32 + lane];
+                    rowsum[i] += warp_sum(v);
+                }
+            }
+            // this warp's 8 k-steps of the sub-tile
+#pragma unroll 2
+            for (int kk = 0; kk < 8; ++kk) {
+                const int ks = hf * 8 + kk;
+                const int cc = ks * 4 + tg;              // column inside the sub-tile (A: col = tg, B: k = tg)
+                const unsigned long long wd = bits[cs + cc];
+                const int m = mt * 8 + gr;
+                const bool on = (wd >> m) & 1ull;
+                const double am = on ? 1.0 : 0.0;
+                const double ay = on ? sY[m * PM_LDY + cs + cc] : 0.0;
+                const double *bs = sS + gr * PM3_LDT + cc; // B[k = tg -> column][n = gr -> p]
+#pragma unroll
+                for (int pt = 0; pt < 17; ++pt) pm_dmma(acc[pt][0], acc[pt][1], am, bs[pt * 8 * PM3_LDT]);
+                pm_dmma(acc[17][0], acc[17][1], ay, bs[17 * 8 * PM3_LDT]);
+                pm_dmma(acc[18][0], acc[18][1], ay, bs[18 * 8 * PM3_LDT]);
+            }
+        }
+        // X[n][k] (coalesced), g[n], and the per-column scalars
+        for (int e = threadIdx.x; e < PM_TILE * PM_KP; e += blockDim.x) {
+            const int c = e >> 4, k = e & 15;
+            const int64_t n = n0 + c;
+            if (n < a.N && k < K) a.X[n * K + k] = a.S[(int64_t)(SPD16_PHI + k) * a.chp + cl0 + c];
+        }
+        for (int c = threadIdx.x; c < PM_TILE; c += blockDim.x) {
+            const int64_t n = n0 + c;
+            if (n < a.N) {
+                const double q = a.S[(int64_t)SPD16_G * a.chp + cl0 + c], ld = a.S[(int64_t)(SPD16_G + 1) * a.chp + cl0 + c];
+                sq += q;
+                sld += ld;
+                if (a.g) a.g[n] = -0.5 * q + 0.5 * ld;
+            }
+        }
+    }
+    // combine the two halves of the k-steps through shared memory, then fold into this CTA's running partial
+    double *part = a.partial + (size_t)blockIdx.x * PM_NPART;
+    const int ncol = SPD16_NPACK + PM_KP;
+    __syncthreads();
+    double *sH = pm_smem;                               // [64][152] staging (reuses the tile buffers)
+    if (hf == 1) {
+#pragma unroll
+        for (int pt = 0; pt < PM_NT; ++pt)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) sH[(mt * 8 + gr) * ncol + pt * 8 + 2 * tg + j] = acc[pt][j];
+    }
+    __syncthreads();
+    if (hf == 0) {
+#pragma unroll
+        for (int pt = 0; pt < PM_NT; ++pt)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int idx = (mt * 8 + gr) * ncol + pt * 8 + 2 * tg + j;
+                const double v = acc[pt][j] + sH[idx];
+                part[idx] = first_chunk ? v : part[idx] + v;
+            }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+            const int p = w + 16 * i;
+            if (p < PM_NT * 8) {
+                double *dst = part + (size_t)PM_MP * ncol + p;
+                *dst = first_chunk ? rowsum[i] : *dst + rowsum[i];
+            }
+        }
+    }
+    sq = warp_sum(sq);
+    sld = warp_sum(sld);
+    if (lane == 0) { red[w][0] = sq; red[w][1] = sld; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s0 = 0.0, s1 = 0.0;
+        for (int ww = 0; ww < PM3_WARPS; ++ww) { s0 += red[ww][0]; s1 += red[ww][1]; }
+        double *dst = part + (size_t)PM_MP * ncol + ncol;
+        dst[0] = first_chunk ? s0 : dst[0] + s0;
+        dst[1] = first_chunk ? s1 : dst[1] + s1;
+    }
+}
+
 // partials -> caller's layout  [ S_yx (M*K) | S_xx (M*K*K, symmetric, full) | sum<xx^T> (K*K) | sum x (K) | sum phi.x | sum logdet ]
 __global__ void pmask_final_kernel(const double *__restrict__ partial, int nblocks, int M, int K, double *__restrict__ stats) {
     const int ncol = SPD16_NPACK + PM_KP;
@@ -356,6 +544,12 @@ extern "C" int bpk_pca_xsweep_masked_fused(const double *Y, const uint8_t *mask,
     const size_t ysm = (size_t)PM_MP * PM_LDY * sizeof(double);
     BPK_CUDA(cudaFuncSetAttribute(pmask_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ysm));
     BPK_CUDA(cudaFuncSetAttribute(pmask_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ysm));
+    const size_t sm3 = (size_t)(PM_MP * PM_LDY + PM_NT * 8 * PM3_LDT) * sizeof(double);
+    const bool v2 = getenv("BPK_PMASK_V2") != nullptr;
+    if (!v2) {
+        BPK_CUDA(cudaFuncSetAttribute(pmask_build3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
+        BPK_CUDA(cudaFuncSetAttribute(pmask_stats3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
+    }
     const char *ir = getenv("BPK_PMASK_INV_REGS");
     const bool inv255 = !(ir && atoi(ir) == 128);
     int first = 1;
@@ -364,13 +558,15 @@ extern "C" int bpk_pca_xsweep_masked_fused(const double *Y, const uint8_t *mask,
         a.nc = (N - c0 < chunk) ? N - c0 : chunk;
         const int64_t ntiles = (a.nc + PM_TILE - 1) / PM_TILE;
         const int gtiles = (int)(ntiles < grid ? ntiles : grid);
-        BPK_LAUNCH(pmask_build_kernel, gtiles, PM_THREADS, ysm, a);
+        if (v2) BPK_LAUNCH(pmask_build_kernel, gtiles, PM_THREADS, ysm, a);
+        else BPK_LAUNCH(pmask_build3_kernel, gtiles, PM3_THREADS, sm3, a);
         // the inverse runs on whole tiles: padded columns of the last tile hold the prior precision (SPD), results unused
         PmArgs b = a;
         b.nc = ntiles * PM_TILE;
         if (inv255) BPK_LAUNCH(pmask_inverse_kernel, (unsigned)((b.nc + 127) / 128), 128, 0, b);
         else BPK_LAUNCH(pmask_inverse128_kernel, (unsigned)((b.nc + 127) / 128), 128, 0, b);
-        BPK_LAUNCH(pmask_stats_kernel, grid, PM_THREADS, ysm, a, first);
+        if (v2) BPK_LAUNCH(pmask_stats_kernel, grid, PM_THREADS, ysm, a, first);
+        else BPK_LAUNCH(pmask_stats3_kernel, grid, PM3_THREADS, sm3, a, first);
         first = 0;
     }
     const int total = (int)(M * K + M * K * K + (int64_t)K * K + K + 2);

@@ -98,7 +98,7 @@ __host__ __device__ inline void pca_vb_offsets(int M, int K, int64_t *off /* [F_
 // reduction slots for the op that runs side by side with another one (BOUND next to XPRE, TAU next to ALPHA), and a
 // backup of what XPRE overwrites (restored if the bound it ran next to raised the stop word; M <= 64 only)
 __host__ __device__ inline size_t pca_vb_smem_doubles(int K) {
-    return (size_t)K * (2 * K + 1) + 7 * (size_t)K + 64 + (size_t)K * K + 256 + ((size_t)PCA_MP * K + 2 * (size_t)K * K + K + 1);
+    return (size_t)K * (2 * K + 1) + 7 * (size_t)K + 64 + (size_t)K * K + 256 + ((size_t)PCA_MP * K + 3 * (size_t)K * K + K + 1);
 }
 
 struct PcaVbArgs {
