@@ -98,10 +98,17 @@ PROTOTYPES = {
     "bpk_pca_vb_set_timers": (C.c_int, [_ip, C.c_int]),
     "bpk_pca_vb_timers_used": (C.c_int, []),
     "bpk_debug_stamps": (C.c_int, [C.POINTER(C.c_uint64), C.c_int]),
+    "bpk_gmm_vb_layout": (C.c_int, [C.c_int, C.c_int, _i64p, _ip]),
+    "bpk_gmm_vb_field_name": (C.c_char_p, [C.c_int]),
+    "bpk_gmm_vb_run": (C.c_int, [_dp, C.c_int64, C.c_int, C.c_int, _dp, _dp, _dp, _ip, C.c_int, C.c_int, C.c_double,
+                                 _dp, C.c_int, _vp]),
+    "bpk_gmm_vb_set_timers": (C.c_int, [_ip, C.c_int]),
 }
 
 # opcodes of bpk_pca_vb_run (include/bpk.h)
 VBOP = dict(XSWEEP=1, STATS=2, SXXT=3, XPRE=4, ROW=5, ALPHA=6, TAU=7, BOUND=8)
+# opcodes of bpk_gmm_vb_run
+GMMOP = dict(Z=1, MU=2, LAMBDA=3, ALPHA=4, BOUND=5)
 
 
 class BpkError(RuntimeError):
@@ -364,6 +371,25 @@ class CudaBackend:
 
     def pca_vb_timers_used(self):
         return int(self.lib.bpk_pca_vb_timers_used())
+
+    # -- device-resident VB loop of the Gaussian mixture
+    def gmm_vb_layout(self, D, K):
+        """{field: (offset, padded size)} of the fp64 state vector, and its total length."""
+        n = C.c_int()
+        self._chk(self.lib.bpk_gmm_vb_layout(D, K, None, C.byref(n)))
+        off = (C.c_int64 * (n.value + 1))()
+        self._chk(self.lib.bpk_gmm_vb_layout(D, K, off, C.byref(n)))
+        names = [self.lib.bpk_gmm_vb_field_name(i).decode() for i in range(n.value)]
+        return {nm: (off[i], off[i + 1] - off[i]) for i, nm in enumerate(names)}, off[n.value]
+
+    def gmm_vb_run(self, Y, N, D, K, P, gz, state, ops, niter, tol, Lhist, cap, ctrl):
+        arr = (C.c_int * len(ops))(*ops)
+        self._chk(self.lib.bpk_gmm_vb_run(Y, N, D, K, P, gz, state, arr, len(ops), int(niter), float(tol), Lhist,
+                                          int(cap), ctrl))
+
+    def gmm_vb_set_timers(self, ids):
+        arr = (C.c_int * max(len(ids), 1))(*ids)
+        self._chk(self.lib.bpk_gmm_vb_set_timers(arr, len(ids)))
 
     def debug_stamps(self, n=32):
         out = (C.c_uint64 * n)()

@@ -52,6 +52,9 @@ int bpk_xchg_local(void);            // make sure this rank's own window exists 
 
 int bpk_set_error(int code, const char *fmt, ...);
 int bpk_check_flag(int what_if_set);    // sync + read d_flag, clear it
+// gmm.cu: bpk_gmm_sweep with a stop word (a raised word turns the launches into no-ops) — for gmm_vb.cu
+int bpk_gmm_sweep_resident(const double *Y, int64_t N, int D, int K, const double *c, const double *h, const double *Lam,
+                           const double *logpi, double *P, double *g, double *stats, const int *stop);
 double *bpk_scratch(size_t bytes);      // stream-ordered scratch (grown on demand)
 
 #define BPK_REQUIRE_INIT()                                                      \

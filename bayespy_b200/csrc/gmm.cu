@@ -34,10 +34,12 @@ struct GmmArgs {
     int given_p;        // 1: P is an input (statistics only), 0: E-step + statistics
     int nfeat;          // 1 + D + D*D
     int per_thread;     // ceil(K*nfeat / 128)
+    const int *stop;    // resident loop: a raised word makes the launch a no-op (convergence was reached)
 };
 
 template <int PT>
 __global__ void __launch_bounds__(GMM_ROWS, 1) gmm_sweep_kernel(GmmArgs a) {
+    if (a.stop && *a.stop) return;
     extern __shared__ double sm[];
     const int D = a.D, K = a.K, F = a.nfeat;
     const int ldp = K | 1;
@@ -196,6 +198,7 @@ __device__ __forceinline__ void g1_pair(int f, int &i, int &j) {
 }
 
 __global__ void __launch_bounds__(G1_WARPS * 32, 1) gmm_sweep_dmma_kernel(GmmArgs a) {
+    if (a.stop && *a.stop) return;
     extern __shared__ __align__(16) double sm[];
     double *sT = sm;                                   // [64][52]  Theta
     double *sZ = sT + G1_KP * G1_LDZ;                  // [128][52] features of the tile
@@ -399,6 +402,7 @@ __device__ __forceinline__ void g2_pair_sync(int p) {
 }
 
 __global__ void __launch_bounds__(G2_PAIRS * 64, 1) gmm_sweep_dmma2_kernel(GmmArgs a) {
+    if (a.stop && *a.stop) return;
     extern __shared__ __align__(16) double sm[];
     double *sT = sm;                                                  // [64][52]  Theta
     const int t = threadIdx.x, lane = t & 31, w = t >> 5, gr = lane >> 2, tg = lane & 3;
@@ -603,6 +607,7 @@ __device__ __forceinline__ void g3_quad_sync(int q) {
 }
 
 __global__ void __launch_bounds__(G3_QUADS * 128, 1) gmm_sweep_dmma3_kernel(GmmArgs a) {
+    if (a.stop && *a.stop) return;
     extern __shared__ __align__(16) double sm[];
     double *sT = sm;                                                  // [64][52]  Theta
     const int t = threadIdx.x, lane = t & 31, w = t >> 5, gr = lane >> 2, tg = lane & 3;
@@ -792,7 +797,8 @@ __global__ void __launch_bounds__(G3_QUADS * 128, 1) gmm_sweep_dmma3_kernel(GmmA
 
 // partial (k, f) layout -> caller's [sum p (K) | sum p y (K*D) | sum p yy^T (K*D*D) | lse]
 __global__ void gmm_final_kernel(const double *__restrict__ partial, int nblocks, int K, int D,
-                                 double *__restrict__ stats) {
+                                 double *__restrict__ stats, const int *stop) {
+    if (stop && *stop) return;
     const int F = 1 + D + D * D;
     int e = blockIdx.x * blockDim.x + threadIdx.x;
     int total = K * F + 1;
@@ -809,30 +815,36 @@ __global__ void gmm_final_kernel(const double *__restrict__ partial, int nblocks
 
 static int gmm_run(const double *Y, int64_t N, int D, int K,
                    const double *c, const double *h, const double *Lam, const double *logpi,
-                   double *P, double *g, double *stats, int given_p);
+                   double *P, double *g, double *stats, int given_p, const int *stop);
 
 extern "C" int bpk_gmm_sweep(const double *Y, int64_t N, int D, int K,
                              const double *c, const double *h, const double *Lam, const double *logpi,
                              double *P, double *g, double *stats) {
     BPK_REQUIRE_INIT();
-    return gmm_run(Y, N, D, K, c, h, Lam, logpi, P, g, stats, 0);
+    return gmm_run(Y, N, D, K, c, h, Lam, logpi, P, g, stats, 0, nullptr);
+}
+
+int bpk_gmm_sweep_resident(const double *Y, int64_t N, int D, int K, const double *c, const double *h, const double *Lam,
+                           const double *logpi, double *P, double *g, double *stats, const int *stop) {
+    return gmm_run(Y, N, D, K, c, h, Lam, logpi, P, g, stats, 0, stop);
 }
 
 extern "C" int bpk_gmm_stats(const double *Y, int64_t N, int D, int K, const double *P, double *stats) {
     BPK_REQUIRE_INIT();
     if (!P) return bpk_set_error(BPK_EINVAL, "bpk_gmm_stats: P is required");
-    return gmm_run(Y, N, D, K, nullptr, nullptr, nullptr, nullptr, const_cast<double *>(P), nullptr, stats, 1);
+    return gmm_run(Y, N, D, K, nullptr, nullptr, nullptr, nullptr, const_cast<double *>(P), nullptr, stats, 1, nullptr);
 }
 
 static int gmm_run(const double *Y, int64_t N, int D, int K,
                    const double *c, const double *h, const double *Lam, const double *logpi,
-                   double *P, double *g, double *stats, int given_p) {
+                   double *P, double *g, double *stats, int given_p, const int *stop) {
     if (D < 1 || D > GMM_MAXD) return bpk_set_error(BPK_EINVAL, "bpk_gmm_sweep: D=%d outside [1,%d]", D, GMM_MAXD);
     if (K < 1 || K > GMM_MAXK) return bpk_set_error(BPK_EINVAL, "bpk_gmm_sweep: K=%d outside [1,%d]", K, GMM_MAXK);
     if (N <= 0) return BPK_OK;
     GmmArgs a;
     a.Y = Y; a.N = N; a.D = D; a.K = K; a.c = c; a.h = h; a.Lam = Lam; a.logpi = logpi; a.P = P; a.g = g;
     a.given_p = given_p;
+    a.stop = stop;
     a.nfeat = 1 + D + D * D;
     a.per_thread = (K * a.nfeat + GMM_ROWS - 1) / GMM_ROWS;
     size_t smem = ((size_t)K * (1 + D + D * D) + (size_t)GMM_ROWS * ((K | 1) + a.nfeat)) * sizeof(double);
@@ -865,7 +877,7 @@ static int gmm_run(const double *Y, int64_t N, int D, int K,
             BPK_LAUNCH(gmm_sweep_dmma2_kernel, grid1, G2_PAIRS * 64, smem2, a);
         }
         int total1 = K * a.nfeat + 1;
-        BPK_LAUNCH(gmm_final_kernel, (total1 + 127) / 128, 128, 0, a.partial, grid1, K, D, stats);
+        BPK_LAUNCH(gmm_final_kernel, (total1 + 127) / 128, 128, 0, a.partial, grid1, K, D, stats, stop);
         return BPK_OK;
     }
 #define GMM_LAUNCH(PT)                                                                                  \
@@ -879,6 +891,6 @@ static int gmm_run(const double *Y, int64_t N, int D, int K,
     else return bpk_set_error(BPK_EINVAL, "bpk_gmm_sweep: K*(1+D+D^2)=%d too large for the v0 kernel", K * a.nfeat);
 #undef GMM_LAUNCH
     int total = K * a.nfeat + 1;
-    BPK_LAUNCH(gmm_final_kernel, (total + 127) / 128, 128, 0, a.partial, grid, K, D, stats);
+    BPK_LAUNCH(gmm_final_kernel, (total + 127) / 128, 128, 0, a.partial, grid, K, D, stats, stop);
     return BPK_OK;
 }

@@ -669,8 +669,11 @@ pca_xsweep_ws_kernel(const __grid_constant__ CUtensorMap tmapY, int64_t M, int64
 // distributed, fixed-order reduction of the per-CTA partials + LL push/gather of the owner's slice (see the v2 kernel)
 template <bool DERIVE_SXX>
 __device__ __forceinline__ void vl_reduce_push(const PcaVbArgs &vb, const double *partial, int w, int lane) {
-    const int per = (PCA_NSTAT + gridDim.x - 1) / gridDim.x;
-    const int e0 = blockIdx.x * per;
+    // called by the worker CTAs only (blocks 1..): the service CTA takes no slice and goes straight to collecting the
+    // totals, so that its wait for the peers' packets overlaps the workers' instead of preceding it
+    const int nb = (int)gridDim.x - 1;
+    const int per = (PCA_NSTAT + nb - 1) / nb;
+    const int e0 = ((int)blockIdx.x - 1) * per;
     const unsigned long long xseq = *(volatile const unsigned long long *)vb.xown + 1ull;
     const int par = (int)(xseq & 1ull);
     const unsigned int seq = (unsigned int)xseq;
@@ -684,7 +687,7 @@ __device__ __forceinline__ void vl_reduce_push(const PcaVbArgs &vb, const double
         if (e >= PCA_NSTAT) continue;
         if (DERIVE_SXX && e >= PCA_MP * PCA_KP && e < PCA_MP * PCA_KP + PCA_KP * PCA_KP) continue;
         double s = 0.0;
-        for (int bb = lane; bb < (int)gridDim.x; bb += 32) s += __ldcg(partial + (size_t)bb * PCA_NSTAT + e);
+        for (int bb = 1 + lane; bb < (int)gridDim.x; bb += 32) s += __ldcg(partial + (size_t)bb * PCA_NSTAT + e);   // row 0 (service CTA) is empty
         s = warp_sum(s);
         if (xr > 1) {
             if (lane < xr) ll_store(ll_slot(mywin, par, vb.xrank, e), s, seq);
@@ -774,7 +777,7 @@ pca_vbloop_kernel(const __grid_constant__ CUtensorMap tmapY, int64_t M, int64_t 
                 svc_t[1] = tb - svc_t[0];
             }
             vb_stamp(vb.dbg, 2);
-            vl_reduce_push<DERIVE_SXX>(vb, partial, w, lane);
+            if (it < 128) vb_stamp(vb.dbg, 64 + it);
             vb_stamp(vb.dbg, 3);
             const unsigned long long xseq = *(volatile const unsigned long long *)vb.xown + 1ull;
             vb_stamp(vb.dbg, 4);

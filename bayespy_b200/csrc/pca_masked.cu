@@ -545,7 +545,9 @@ extern "C" int bpk_pca_xsweep_masked_fused(const double *Y, const uint8_t *mask,
     BPK_CUDA(cudaFuncSetAttribute(pmask_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ysm));
     BPK_CUDA(cudaFuncSetAttribute(pmask_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ysm));
     const size_t sm3 = (size_t)(PM_MP * PM_LDY + PM_NT * 8 * PM3_LDT) * sizeof(double);
-    const bool v2 = getenv("BPK_PMASK_V2") != nullptr;
+    // v3 (one warp = all 19 row tiles of a column tile, operands staged in shared memory) measured 64.2 ms against
+    // v2's 52.9 ms at N = 1e7 (round 2, session 8; identical results): kept for experiments behind BPK_PMASK_V3
+    const bool v2 = getenv("BPK_PMASK_V3") == nullptr;
     if (!v2) {
         BPK_CUDA(cudaFuncSetAttribute(pmask_build3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
         BPK_CUDA(cudaFuncSetAttribute(pmask_stats3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));

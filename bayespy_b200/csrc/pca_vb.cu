@@ -40,14 +40,15 @@ extern "C" int bpk_pca_vb_layout(int M, int K, int64_t *offsets, int *nfields) {
 }
 extern "C" const char *bpk_pca_vb_field_name(int i) { return (i >= 0 && i < F_COUNT) ? kFieldNames[i] : nullptr; }
 
+#define BPK_VB_NDBG 192
 static unsigned long long *g_vb_dbg = nullptr;
 // BPK_VB_DEBUG=1: %globaltimer stamps of the LAST fused sweep launch: [0] kernel start, [1] data pass done
 // (CTA 0), [2] after grid barrier 1, [3] CTA 0's share of the reduction done, [4] after grid barrier 2,
-// [8+i] start of tail op i, [5] tail done.
+// [8+i] start of tail op i, [5] tail done; [64+it] the service CTA passing grid barrier 1 of sweep `it` of the launch.
 extern "C" int bpk_debug_stamps(uint64_t *out, int n) {
     BPK_REQUIRE_INIT();
     if (!g_vb_dbg) return bpk_set_error(BPK_EINVAL, "no debug stamps (set BPK_VB_DEBUG=1 before the first run)");
-    if (n > 64) n = 64;
+    if (n > BPK_VB_NDBG) n = BPK_VB_NDBG;
     BPK_CUDA(cudaMemcpyAsync(out, g_vb_dbg, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, g_bpk.stream));
     BPK_CUDA(cudaStreamSynchronize(g_bpk.stream));
     return BPK_OK;
@@ -108,8 +109,8 @@ extern "C" int bpk_pca_vb_run(const double *Y, int64_t M, int64_t N, int K, doub
     a.dbg = nullptr;
     if (getenv("BPK_VB_DEBUG")) {
         if (!g_vb_dbg) {
-            BPK_CUDA(cudaMalloc((void **)&g_vb_dbg, 64 * sizeof(unsigned long long)));
-            BPK_CUDA(cudaMemsetAsync(g_vb_dbg, 0, 64 * sizeof(unsigned long long), g_bpk.stream));
+            BPK_CUDA(cudaMalloc((void **)&g_vb_dbg, BPK_VB_NDBG * sizeof(unsigned long long)));
+            BPK_CUDA(cudaMemsetAsync(g_vb_dbg, 0, BPK_VB_NDBG * sizeof(unsigned long long), g_bpk.stream));
             if (getenv("BPK_VB_DRYTEST")) {
                 unsigned long long one = 1;
                 BPK_CUDA(cudaMemcpyAsync(g_vb_dbg + 63, &one, 8, cudaMemcpyHostToDevice, g_bpk.stream));

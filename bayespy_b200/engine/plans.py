@@ -1137,6 +1137,254 @@ class GaussianMixturePlan:
         return D.add(D.sub(lse, fz["T"]), dpi)
 
 
+    # ---- device-resident loop (csrc/gmm_vb.cu): whole sweeps without returning to Python -----------------
+    def _hyper_nodes(self):
+        return self.mu, self.Lam, self.Z.parents[0]
+
+    def _resident_hyper(self):
+        """Prior natural parameters and log-normalisers of mu, Lambda, alpha as host arrays, or None when one of
+        them does not hang off plain constants."""
+        from .dirichlet import Dirichlet
+        K, Dm = self.K, self.D
+        mu, Lam, alpha = self._hyper_nodes()
+        if not isinstance(alpha, Dirichlet) or tuple(alpha.plates) != () or tuple(alpha.dims[0]) != (K,) \
+                or len(alpha.children) != 1:
+            return None
+        h = {}
+        for key, n, shapes, gshape in (("m", mu, [(K, Dm), (K, Dm, Dm)], (K,)), ("l", Lam, [(K, Dm, Dm), (K,)], (K,)),
+                                      ("a", alpha, [(K,)], (1,))):
+            if n.observed is not False or not all(isinstance(pp, Constant) for pp in n.parents) \
+                    or getattr(n, "annealing", 1.0) != 1.0 or not mask_is_full(n.mask):
+                return None
+            u_par = n.moments_from_parents()
+            phi = n._canonical_phi(n._distribution.compute_phi_from_parents(*u_par))
+            g = D.asarray(n._distribution.compute_cgf_from_parents(*u_par))
+            for i, (ph, shp) in enumerate(zip(phi, shapes)):
+                h["p%s%d" % (key, i)] = np.broadcast_to(dense(ph).numpy(), shp).astype(np.float64).ravel()
+            h["gp" + key] = np.broadcast_to(g.numpy(), gshape).astype(np.float64).ravel()
+        return h
+
+    def resident_program(self, vb, nodes):
+        """Opcode list for ONE iteration of ``VB.update(*nodes)`` when the whole sweep can stay on the device
+        (this model, constant hyper-priors, every latent node updated exactly once), else None."""
+        be = _bpk.get()
+        if not hasattr(be, "gmm_vb_run") or not self.valid():
+            return None
+        mu, Lam, alpha = self._hyper_nodes()
+        Z, Y = self.Z, self.Y
+        latent = [Z, mu, Lam, alpha]
+        if len(vb.model) != 5 or any(n not in vb.model for n in latent + [Y]):
+            return None
+        try:
+            order = [vb[n] for n in nodes]
+        except Exception:
+            return None
+        order = [n for n in order if n is not Y]
+        if len(order) != 4 or any(n not in order for n in latent):
+            return None
+        hk = tuple(id(pp) for n in (mu, Lam, alpha) for pp in n.parents) + (id(alpha),) \
+            + tuple((repr(n.observed) if not isinstance(n.observed, np.ndarray) else "array", len(n.children))
+                    for n in (mu, Lam, alpha))
+        if getattr(self, "_hyper_key", None) != hk:
+            self._res_cache = None
+            self._hyper = self._resident_hyper()
+            self._hyper_key = hk
+            self._hsig = None if self._hyper is None else tuple(v.tobytes() for _, v in sorted(self._hyper.items()))
+        if self._hyper is None:
+            return None
+        for n in (mu, Lam, alpha):
+            if n.phi is None or n.u is None or n.g is None or any(x is None for x in list(n.phi) + list(n.u)):
+                return None
+        G = _bpk.GMMOP
+        code = {id(Z): G["Z"], id(mu): G["MU"], id(Lam): G["LAMBDA"], id(alpha): G["ALPHA"]}
+        return [code[id(n)] for n in order] + [G["BOUND"]], order
+
+    def _resident_enter(self, order, lprev):
+        be = _bpk.get()
+        K, Dm, h = self.K, self.D, self._hyper
+        mu, Lam, alpha = self._hyper_nodes()
+        lay, total = be.gmm_vb_layout(Dm, K)
+        st = np.zeros(total)
+
+        def put(name, v, shape=None):
+            v = np.asarray(dense(v).numpy() if hasattr(dense(v), "numpy") else v, dtype=np.float64)
+            if shape is not None:
+                v = np.broadcast_to(v, shape)
+            v = v.reshape(-1)
+            o = lay[name][0]
+            st[o:o + v.size] = v
+        put("pm0", h["pm0"]); put("pm1", h["pm1"]); put("gpm", h["gpm"])
+        put("pl0", h["pl0"]); put("pl1", h["pl1"]); put("gpl", h["gpl"])
+        put("pa", h["pa0"]); put("gpa", h["gpa"])
+        put("ng", float(self.Ng))
+        put("lprev", lprev)
+        put("mu_phi0", mu.phi[0], (K, Dm)); put("mu_phi1", mu.phi[1], (K, Dm, Dm))
+        put("mu_u0", mu.u[0], (K, Dm)); put("mu_u1", mu.u[1], (K, Dm, Dm)); put("mu_g", mu.g, (K,))
+        cov = getattr(mu.u[1], "cov", None)
+        if cov is not None:
+            put("mu_cov", cov, (K, Dm, Dm))
+        put("lam_phi0", Lam.phi[0], (K, Dm, Dm)); put("lam_phi1", Lam.phi[1], (K,))
+        put("lam_u0", Lam.u[0], (K, Dm, Dm)); put("lam_u1", Lam.u[1], (K,)); put("lam_g", Lam.g, (K,))
+        put("al_phi", alpha.phi[0], (K,)); put("al_u", alpha.u[0], (K,)); put("al_g", alpha.g, (1,))
+        if order[0] is not self.Z:
+            # somebody consumes the statistics of the CURRENT q(Z) before the first sweep
+            self.stats()
+            put("stats", self._stats[1])
+            fz = getattr(self.Z, "_fused", None)
+            if fz is not None:
+                put("z_logpi", fz["logpi"], (K,))
+                put("z_t", fz["T"], (1,))
+        return DArray.from_numpy(st), lay
+
+    def _resident_state(self, order, lprev, need_prev=False):
+        mu, Lam, alpha = self._hyper_nodes()
+        watched = [self.Y, self.Z, mu, Lam, alpha]
+        cache = getattr(self, "_res_cache", None)
+        if cache is not None and cache["versions"] == [n._version for n in watched] and cache["hsig"] == self._hsig \
+                and cache["nodes"] == [id(n) for n in watched] and not (need_prev and np.isnan(lprev)):
+            state, lay, P, gz = cache["state"], cache["lay"], cache["P"], cache["gz"]
+        else:
+            cache = None
+            state, lay = self._resident_enter(order, lprev)
+            P, gz = DArray.empty((self.N, self.K)), DArray.empty((self.N,))
+        self._res_cache = None
+        return state, lay, P, gz, cache, watched
+
+    @staticmethod
+    def _raise_ctrl_errors(err):
+        if err & 1:
+            raise _bpk.NotPositiveDefinite("Matrix not positive definite")
+        if err & 2:
+            raise ValueError("Natural parameters should be positive")
+
+    def _resident_publish(self, state, lay, P, gz):
+        """Point the node objects at the device state the loop left behind."""
+        K, Dm, N = self.K, self.D, self.N
+        mu, Lam, alpha = self._hyper_nodes()
+        Z, Y = self.Z, self.Y
+
+        def view(name, shape):
+            o = lay[name][0]
+            n = int(np.prod(shape, dtype=np.int64)) if shape else 1
+            return state.slice_axis(0, o, o + n).reshape(shape)
+        mu.phi = [view("mu_phi0", (K, Dm)), view("mu_phi1", (K, Dm, Dm))]
+        u0 = view("mu_u0", (K, Dm))
+        second = FactoredSecondMoment(u0, view("mu_cov", (K, Dm, Dm)), (Dm,))
+        second._dense = view("mu_u1", (K, Dm, Dm))
+        mu.u = [u0, second]
+        mu.g = view("mu_g", (K,))
+        mu._version += 1
+        Lam.phi = [view("lam_phi0", (K, Dm, Dm)), view("lam_phi1", (K,))]
+        Lam.u = [view("lam_u0", (K, Dm, Dm)), view("lam_u1", (K,))]
+        Lam.g = view("lam_g", (K,))
+        Lam._version += 1
+        alpha.phi = [view("al_phi", (K,))]
+        alpha.u = [view("al_u", (K,))]
+        alpha.g = view("al_g", ())
+        alpha._version += 1
+        logpi = view("z_logpi", (K,))
+        plan = self
+
+        def phi_fn():
+            return D.add(plan._orig["Y.msg"](0)[0], logpi)
+        Z.phi = [LazyArray((N, K), phi_fn)]
+        Z.u = [P]
+        Z.g = gz
+        Z._version += 1
+        Z._fused = dict(logpi=logpi, T=view("z_t", ()))
+        self._stats = ((Z._version, Y._version), view("stats", (K + K * Dm + K * Dm * Dm + 1,)))
+
+    def _resident_finish(self, state, lay, P, gz, watched):
+        self._resident_publish(state, lay, P, gz)
+        self._res_cache = dict(state=state, lay=lay, P=P, gz=gz, hsig=self._hsig, nodes=[id(n) for n in watched],
+                               versions=[n._version for n in watched])
+
+    def sweep_resident(self, vb, program):
+        """ONE sweep of ``VB.update`` — every node update of the user's order, no lower bound — without returning
+        to Python between the nodes (a callback / progress bar wants the host before the bound, vmp.py:702-713)."""
+        be = _bpk.get()
+        ops, order = program
+        ops = [o for o in ops if o != _bpk.GMMOP["BOUND"]]
+        state, lay, P, gz, cache, watched = self._resident_state(order, np.nan)
+        ctrl = DArray.zeros((2,))
+        Lh = DArray.empty((1, 6))
+        be.gmm_vb_run(self._Yd().ptr, self.N, self.D, self.K, P.ptr, gz.ptr, state.ptr, ops, 1, -1.0, Lh.ptr, 0, ctrl.ptr)
+        c = ctrl.numpy().view(np.int32)
+        self._raise_ctrl_errors(int(c[2]))
+        self.fused_calls += 1
+        self._resident_finish(state, lay, P, gz, watched)
+
+    def run_resident(self, vb, program, repeat, tol, verbose):
+        """``VB.update`` for this model without leaving the device between sweeps."""
+        import time
+        import warnings
+        be = _bpk.get()
+        ops, order = program
+        mu, Lam, alpha = self._hyper_nodes()
+        check = not vb.ignore_bound_checks
+        tol_dev = (vb.tol if tol is None else tol) if check else -1.0
+        lprev = np.nan
+        if check and not vb.annealing_changed and vb.iter > 0:
+            lprev = vb.L[vb.iter - 1]
+        state, lay, P, gz, cache, watched = self._resident_state(order, lprev, need_prev=check and vb.iter > 0)
+        if cache is not None:
+            o = lay["lprev"][0]
+            D.copy_into(state.slice_axis(0, o, o + 1), DArray.from_numpy(np.array([lprev])))
+        terms_of = {self.Y: 0, self.Z: 1, mu: 2, Lam: 3, alpha: 4}
+        Yd = self._Yd()
+        done, converged = 0, False
+        ctrl = DArray.zeros((2,))                 # 16 bytes = int[4]
+        while (repeat is None or done < repeat) and not converged:
+            left = 25 if repeat is None else repeat - done
+            chunk = 1 if verbose else min(left, 25)
+            Lh = DArray.empty((chunk, 6))
+            be.memset(ctrl.ptr, 0, 16)
+            ids = []
+            if self.kernel_timers is not None:
+                ids = self.kernel_timers[self._timer_pos:self._timer_pos + chunk]
+                be.gmm_vb_set_timers(ids)
+            t0 = time.time()
+            be.gmm_vb_run(Yd.ptr, self.N, self.D, self.K, P.ptr, gz.ptr, state.ptr, ops, chunk, tol_dev, Lh.ptr, chunk,
+                          ctrl.ptr)
+            c = ctrl.numpy().view(np.int32)       # blocks until the chunk has run
+            dt = time.time() - t0
+            n_it, stop, err = int(c[0]), int(c[1]), int(c[2])
+            if ids:
+                self._timer_pos += min(len(ids), max(n_it, 0))
+                be.gmm_vb_set_timers([])
+            self._raise_ctrl_errors(err)
+            Lrows = Lh.numpy()[:n_it]
+            for r in range(n_it):
+                if vb.iter >= len(vb.L):
+                    vb._append_iterations(100)
+                for node in vb.model:
+                    vb.l[node][vb.iter] = Lrows[r, terms_of[node]] if node in terms_of else 0.0
+                L = float(Lrows[r, 5])
+                vb.L[vb.iter] = L
+                vb.cputime[vb.iter] = dt / max(n_it, 1)
+                if verbose:
+                    vb.print("Iteration %d: loglike=%e (%.3f seconds)" % (vb.iter + 1, L, dt / max(n_it, 1)))
+                vb.converged = False
+                if check and not vb.annealing_changed and vb.iter > 0:
+                    L0 = vb.L[vb.iter - 1]
+                    if L0 - L > 1e-6:
+                        warnings.warn("Lower bound decreased %e! Bug somewhere or numerical inaccuracy?" % (L0 - L))
+                    if r == n_it - 1 and stop:
+                        if verbose:
+                            vb.print("Converged at iteration %d." % (vb.iter + 1))
+                        vb.converged = True
+                vb.annealing_changed = False
+                vb.iter += 1
+            done += n_it
+            self.fused_calls += n_it
+            converged = bool(stop)
+            if n_it == 0:
+                break
+        if done > 0:
+            self._resident_finish(state, lay, P, gz, watched)
+        return converged
+
+
 def _attach_gmm(model, plans):
     from .mixture import Mixture
     from .gaussian import Gaussian

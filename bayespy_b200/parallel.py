@@ -235,3 +235,18 @@ def barrier():
     if _state["world"] > 1:
         allgather_scalar(0.0)
     _bpk.get().sync()
+
+
+def barrier_aligned(lead_s=0.002):
+    """barrier(), then every rank leaves at the same instant.
+
+    A collective releases its ranks tens to hundreds of microseconds apart (each host wakes from its own stream
+    synchronisation).  For a timed region of a few milliseconds that skew is measured as work: the span of the rank
+    that left first covers the wait for the rank that left last.  The ranks of one node share CLOCK_MONOTONIC, so they
+    agree on a deadline (latest clock reading + lead_s) and spin up to it.  Single node only (as torchrun --nnodes=1)."""
+    barrier()
+    if _state["world"] > 1:
+        import time
+        deadline = float(np.max(allgather_scalar(time.monotonic()))) + lead_s
+        while time.monotonic() < deadline:
+            pass

@@ -276,7 +276,7 @@ def run_gpu(args):
     plan._timer_pos = 0
     plan.kernel_timer_log = []
     t_all = be.timer_create()
-    parallel.barrier()
+    parallel.barrier_aligned()               # barrier + common start instant (one node: shared monotonic clock)
     l0 = be.launch_count()
     wall0 = time.perf_counter()
     be.timer_record(t_all, 0)

@@ -281,6 +281,31 @@ int bpk_pca_vb_timers_used(void);
 /* diagnostics: device-clock stamps of the last fused sweep launch (needs BPK_VB_DEBUG=1 in the environment) */
 int bpk_debug_stamps(uint64_t *out, int n);
 
+/* ---- device-resident VB loop of the Gaussian mixture model --------------------------------------
+ * Replaces, for  Y = Mixture(Z, Gaussian, mu, Lambda)  with  Z ~ Categorical(alpha), alpha ~ Dirichlet,
+ * mu ~ Gaussian, Lambda ~ Wishart (doc/source/examples/gmm.rst:71-98), the scheduler loop of VB.update
+ * (bayespy/inference/vmp/vmp.py:132-172) together with the node updates and lower-bound terms it calls:
+ * nodes/mixture.py:108-225, gaussian.py:341-463, wishart.py:136-205, dirichlet.py:120-170,
+ * multinomial.py:83-130, expfamily.py:400-480, and the convergence test vmp.py:717-747.
+ * `ops` is ONE iteration's program in the user's update order (one opcode per node, BOUND last); `state`
+ * is an fp64 vector laid out by bpk_gmm_vb_layout (prior natural parameters in, posterior moments out);
+ * P (N x K responsibilities) and gz (N, nullable) are written by every Z sweep.  ctrl / Lhist / tol / cap
+ * as for bpk_pca_vb_run; a Lhist row is [Y, Z, mu, Lambda, alpha, total].  With a communicator the
+ * statistics of every sweep are all-reduced on the library stream.                                   */
+enum {
+    BPK_GMMOP_Z = 1,       /* Z.update(): responsibilities + plate-summed statistics (bpk_gmm_sweep) */
+    BPK_GMMOP_MU = 2,      /* mu.update()                                                            */
+    BPK_GMMOP_LAMBDA = 3,  /* Lambda.update()                                                        */
+    BPK_GMMOP_ALPHA = 4,   /* alpha.update()                                                         */
+    BPK_GMMOP_BOUND = 5    /* lower bound + convergence test                                         */
+};
+int bpk_gmm_vb_layout(int D, int K, int64_t *offsets /* [nfields+1] */, int *nfields);
+const char *bpk_gmm_vb_field_name(int i);
+int bpk_gmm_vb_run(const double *Y, int64_t N, int D, int K, double *P, double *gz, double *state,
+                   const int *ops, int nops, int niter, double tol, double *Lhist, int cap, int *ctrl);
+/* bench: record these timers around the next n responsibilities-kernel launches of bpk_gmm_vb_run */
+int bpk_gmm_vb_set_timers(const int *ids, int n);
+
 #ifdef __cplusplus
 }
 #endif

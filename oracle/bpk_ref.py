@@ -471,6 +471,124 @@ class RefBackend:
         s[K + K * D:K + K * D + K * D * D] += np.einsum("nk,ni,nj->kij", p, y, y).ravel()
         s[-1] += lse.sum()
 
+    # ---- device-resident mixture loop (CPU restatement of csrc/gmm_vb.cu) ------------------------------
+    GMM_FIELDS = ["pm0", "pm1", "gpm", "pl0", "pl1", "gpl", "pa", "gpa", "ng", "lprev",
+                  "mu_phi0", "mu_phi1", "mu_u0", "mu_cov", "mu_u1", "mu_g",
+                  "lam_phi0", "lam_phi1", "lam_u0", "lam_u1", "lam_g", "al_phi", "al_u", "al_g",
+                  "z_g", "z_h", "z_logpi", "z_t", "stats", "xstats"]
+
+    def gmm_vb_layout(self, D, K):
+        KD, KDD = K * D, K * D * D
+        NS = K + KD + KDD + 1
+        size = dict(pm0=KD, pm1=KDD, gpm=K, pl0=KDD, pl1=K, gpl=K, pa=K, mu_phi0=KD, mu_phi1=KDD, mu_u0=KD,
+                    mu_cov=KDD, mu_u1=KDD, mu_g=K, lam_phi0=KDD, lam_phi1=K, lam_u0=KDD, lam_u1=K, lam_g=K,
+                    al_phi=K, al_u=K, z_g=K, z_h=KD, z_logpi=K, stats=NS, xstats=NS)
+        out, o = {}, 0
+        for f in self.GMM_FIELDS:
+            n = size.get(f, 1)
+            out[f] = (o, n)
+            o += (n + 1) & ~1        # every field starts on a 16-byte boundary, as in csrc/gmm_vb.cu
+        return out, o
+
+    def gmm_vb_set_timers(self, ids):
+        pass
+
+    def gmm_vb_run(self, Y, N, D, K, P, gz, state, ops, niter, tol, Lhist, cap, ctrl):
+        """The VB.update loop of vmp.py:132-172 for the mixture model of gmm.rst:71-98, node by node:
+        Z: mixture.py:53-160 + multinomial.py:101-121; mu: gaussian.py:341-446; Lambda: gaussian.py:2496-2522 +
+        wishart.py:165-188; alpha: multinomial.py:83-90 + dirichlet.py:130-160; bound: expfamily.py:400-480;
+        stop: vmp.py:738-747."""
+        lay, total = self.gmm_vb_layout(D, K)
+        st = _dense(state, (total,))
+        f = {k: st[o:o + n] for k, (o, n) in lay.items()}
+        c = _dense(ctrl, (4,), np.int32)
+        Lh = _dense(Lhist, (max(cap, 1), 6)) if Lhist else None
+        KD, KDD = K * D, K * D * D
+        NS = K + KD + KDD + 1
+        I = np.identity(D)
+        R, S1, S2 = f["stats"][:K], f["stats"][K:K + KD].reshape(K, D), f["stats"][K + KD:K + KD + KDD].reshape(K, D, D)
+        mu, mumu = f["mu_u0"].reshape(K, D), f["mu_u1"].reshape(K, D, D)
+        Lam = f["lam_u0"].reshape(K, D, D)
+
+        def spd(A):
+            try:
+                fac = scipy.linalg.cho_factor(A)
+            except (np.linalg.LinAlgError, ValueError):
+                c[2] |= 1
+                return np.full((D, D), np.nan), np.nan
+            return scipy.linalg.cho_solve(fac, I), 2 * np.sum(np.log(np.diag(fac[0])))
+
+        for _ in range(niter):
+            for op in ops:
+                if c[1]:
+                    return
+                if op == 1:      # Z
+                    f["z_g"][:] = -0.5 * np.einsum("kij,kij->k", mumu, Lam) + 0.5 * f["lam_u1"]
+                    f["z_h"][:] = np.einsum("kij,kj->ki", Lam, mu).ravel()
+                    f["z_logpi"][:] = f["al_u"]
+                    f["xstats"][:] = 0.0
+                    if N > 0:
+                        self.gmm_sweep(Y, N, D, K, f["z_g"].ctypes.data, f["z_h"].ctypes.data, f["lam_u0"].ctypes.data,
+                                       f["z_logpi"].ctypes.data, P, gz, f["xstats"].ctypes.data)
+                    self.allreduce_sum_f64(f["xstats"].ctypes.data, NS)       # identity without a communicator
+                    f["stats"][:] = f["xstats"]
+                    f["z_t"][0] = np.sum(f["z_g"] * R) + np.sum(f["z_h"].reshape(K, D) * S1) - 0.5 * np.sum(Lam * S2)
+                elif op == 2:    # mu
+                    phi0 = f["pm0"].reshape(K, D) + np.einsum("kij,kj->ki", Lam, S1)
+                    phi1 = f["pm1"].reshape(K, D, D) - 0.5 * R[:, None, None] * Lam
+                    f["mu_phi0"][:] = phi0.ravel()
+                    f["mu_phi1"][:] = phi1.ravel()
+                    for k in range(K):
+                        cov, ld = spd(-2 * phi1[k])
+                        u0 = cov @ phi0[k]
+                        f["mu_cov"].reshape(K, D, D)[k] = cov
+                        mu[k] = u0
+                        mumu[k] = cov + np.outer(u0, u0)
+                        f["mu_g"][k] = -0.5 * u0 @ phi0[k] + 0.5 * ld
+                elif op == 3:    # Lambda
+                    t = S2 - S1[:, :, None] * mu[:, None, :] - mu[:, :, None] * S1[:, None, :] + mumu * R[:, None, None]
+                    phi0 = f["pl0"].reshape(K, D, D) - 0.5 * t
+                    nu2 = f["pl1"] + 0.5 * R
+                    f["lam_phi0"][:] = phi0.ravel()
+                    f["lam_phi1"][:] = nu2
+                    for k in range(K):
+                        inv, ld = spd(-phi0[k])
+                        Lam[k] = nu2[k] * inv
+                        f["lam_u1"][k] = -ld + np.sum(sp.digamma(nu2[k] - 0.5 * np.arange(D)))
+                        f["lam_g"][k] = nu2[k] * ld - sp.multigammaln(nu2[k], D)
+                elif op == 4:    # alpha
+                    a = f["pa"] + R
+                    if np.any(~(a > 0)):
+                        c[2] |= 2
+                    f["al_phi"][:] = a
+                    with np.errstate(all="ignore"):
+                        f["al_u"][:] = sp.psi(a) - sp.psi(np.sum(a))
+                        f["al_g"][0] = sp.gammaln(np.sum(a)) - np.sum(sp.gammaln(a))
+                elif op == 5:    # bound
+                    g = -0.5 * np.einsum("kij,kij->k", mumu, Lam) + 0.5 * f["lam_u1"]
+                    h = np.einsum("kij,kj->ki", Lam, mu)
+                    LY = np.sum(g * R) + np.sum(h * S1) - 0.5 * np.sum(Lam * S2) - 0.5 * D * np.log(2 * np.pi) * f["ng"][0]
+                    LZ = f["stats"][NS - 1] - f["z_t"][0] + np.sum((f["al_u"] - f["z_logpi"]) * R)
+                    LM = np.sum(f["gpm"] - f["mu_g"]) + np.sum((f["pm0"] - f["mu_phi0"]) * f["mu_u0"]) \
+                        + np.sum((f["pm1"] - f["mu_phi1"]) * f["mu_u1"])
+                    LL = np.sum(f["gpl"] - f["lam_g"]) + np.sum((f["pl0"] - f["lam_phi0"]) * f["lam_u0"]) \
+                        + np.sum((f["pl1"] - f["lam_phi1"]) * f["lam_u1"])
+                    LA = f["gpa"][0] - f["al_g"][0] + np.sum((f["pa"] - f["al_phi"]) * f["al_u"])
+                    L = LY + LZ + LM + LL + LA
+                    it = int(c[0])
+                    if Lh is not None and it < cap:
+                        Lh[it] = [LY, LZ, LM, LL, LA, L]
+                    L0 = f["lprev"][0]
+                    f["lprev"][0] = L
+                    c[0] = it + 1
+                    if tol >= 0 and L0 == L0:
+                        if (L - L0) / (0.5 * (abs(L0) + abs(L))) < tol:
+                            c[1] = 1
+                    if c[2]:
+                        c[1] = 1
+                else:
+                    raise ValueError("gmm_vb_run: unknown opcode %d" % op)
+
     def gmm_stats(self, Y, N, D, K, P, stats):
         """p-weighted plate sums of mixture.py:108-160 + node.py:650 for given responsibilities."""
         self._launches += 1

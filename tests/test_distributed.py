@@ -159,6 +159,12 @@ def _rdzv_worker(rank, world, port, gloo_port, q):
         handles, nr, rr = FakeDevice.opened
         ok = ok and nr == world and rr == rank and handles == [bytes([100 + k]) * 64 for k in range(world)]
         parallel.barrier()
+        # aligned barrier: every rank leaves within a millisecond of the agreed instant (shared monotonic clock)
+        import time
+        parallel.barrier_aligned(lead_s=0.05)
+        t_leave = time.monotonic()
+        spread = parallel.allgather_scalar(t_leave)
+        ok = ok and float(np.max(spread) - np.min(spread)) < 0.02
         left = [f for f in os.listdir("/tmp") if f.startswith("bpk_rdzv_%d_pytest-%d" % (port, port))]
         q.put((rank, bool(ok), left if rank == 0 else []))
     except Exception:                                         # pragma: no cover

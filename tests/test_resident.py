@@ -209,3 +209,140 @@ def test_callback_keeps_the_node_updates_on_the_fused_path(backend):
     assert res[0][2] >= 5
     np.testing.assert_allclose(res[0][0], res[1][0], rtol=1e-7)
     np.testing.assert_allclose(res[0][1], res[1][1], rtol=1e-5, atol=1e-7)
+
+
+# ---- the mixture model's resident loop (bpk_gmm_vb_run, csrc/gmm_vb.cu) ---------------------------------------------
+def _gmm(N, Dm, K, order="mLZa", resident=True, seed=5, a0=1e-5, m0=None, l0=1e-5, n0=None, v0=1e-5):
+    from bayespy_b200.nodes import Gaussian, Wishart, Dirichlet, Categorical, Mixture
+    from bayespy_b200.inference import VB
+    rs = np.random.RandomState(seed)
+    means = 4 * rs.randn(K, Dm)
+    y = means[rs.randint(0, K, size=N)] + rs.randn(N, Dm)
+    alpha = Dirichlet(a0 * np.ones(K), name="alpha")
+    Z = Categorical(alpha, plates=(N,), name="Z")
+    mu = Gaussian(np.zeros(Dm) if m0 is None else m0, l0 * np.identity(Dm), plates=(K,), name="mu")
+    Lam = Wishart(Dm if n0 is None else n0, v0 * np.identity(Dm), plates=(K,), name="Lambda")
+    Y = Mixture(Z, Gaussian, mu, Lam, name="Y")
+    Z.initialize_from_value(rs.randint(0, K, size=N))
+    Y.observe(y)
+    nodes = dict(m=mu, L=Lam, Z=Z, a=alpha)
+    Q = VB(Y, *[nodes[c] for c in order], resident=resident)
+    return Q, dict(mu=mu, Lambda=Lam, Z=Z, alpha=alpha, Y=Y)
+
+
+def _compare_gmm(Qa, na, Qb, nb, iters, rtol=1e-9):
+    # When Z is swept before mu and Lambda have seen any data, the FIRST bound is a difference of terms of size
+    # ~1e13 (the vague initial q(mu), q(Lambda): tr(<mu mu^T><Lambda>) R_k ~ 1e5 * 1e5 * N), so its last bits are
+    # summation-order noise (2^-9 observed); every later bound, and the state itself, is compared tightly.
+    np.testing.assert_allclose(Qa.L[:1], Qb.L[:1], rtol=1e-5)
+    np.testing.assert_allclose(Qa.L[1:iters], Qb.L[1:iters], rtol=rtol)
+    for node in Qa.model:
+        np.testing.assert_allclose(Qa.l[node][1:iters], Qb.l[Qb[node.name]][1:iters], rtol=1e-7, atol=1e-6,
+                                   err_msg="bound term " + node.name)
+        np.testing.assert_allclose(Qa.l[node][:1], Qb.l[Qb[node.name]][:1], rtol=1e-5, atol=1e-2,
+                                   err_msg="first bound term " + node.name)
+    # entries of a dying cluster (R_k -> 0 exponentially fast) are tiny and amplify rounding differences between
+    # the two summation orders: tolerances are relative to the largest entry of each array
+    for name in ("mu", "Lambda", "alpha", "Z"):
+        a, b = na[name], nb[name]
+        for i in range(len(b.u)):
+            ub, pb = np.asarray(b.u[i]), np.asarray(b.phi[i])
+            np.testing.assert_allclose(np.asarray(a.u[i]), ub, rtol=1e-7, atol=1e-7 * np.max(np.abs(ub)),
+                                       err_msg="%s.u[%d]" % (name, i))
+            np.testing.assert_allclose(np.broadcast_to(np.asarray(a.phi[i]), pb.shape), pb, rtol=1e-7,
+                                       atol=1e-7 * np.max(np.abs(pb)), err_msg="%s.phi[%d]" % (name, i))
+        gb = np.asarray(b.g)
+        np.testing.assert_allclose(np.broadcast_to(np.asarray(a.g), gb.shape), gb, rtol=1e-7,
+                                   atol=1e-7 * np.max(np.abs(gb)), err_msg="%s.g" % name)
+
+
+@pytest.mark.parametrize("order", ["".join(p) for p in itertools.permutations("mLZa")][::3])
+def test_gmm_resident_matches_per_node_every_order(backend, order):
+    Qa, na = _gmm(240, 3, 5, order=order, resident=True)
+    Qb, nb = _gmm(240, 3, 5, order=order, resident=False)
+    Qa.update(repeat=6, verbose=False, tol=0)
+    Qb.update(repeat=6, verbose=False, tol=0)
+    assert Qa.plans[0]._res_cache is not None and getattr(Qb.plans[0], "_res_cache", None) is None
+    _compare_gmm(Qa, na, Qb, nb, 6)
+    # the bound recomputed node by node from the published state is the loop's own
+    np.testing.assert_allclose(Qa.compute_lowerbound(), Qa.L[5], rtol=1e-10)
+
+
+@pytest.mark.parametrize("N,Dm,K", [(500, 8, 16), (131, 2, 3), (300, 5, 40), (64, 1, 2)])
+def test_gmm_resident_shapes_and_priors(backend, N, Dm, K):
+    kw = dict(a0=0.7, m0=0.3 * np.arange(Dm), l0=0.02, n0=Dm + 2.5, v0=0.4)
+    Qa, na = _gmm(N, Dm, K, resident=True, **kw)
+    Qb, nb = _gmm(N, Dm, K, resident=False, **kw)
+    Qa.update(repeat=4, verbose=False, tol=0)
+    Qb.update(repeat=4, verbose=False, tol=0)
+    _compare_gmm(Qa, na, Qb, nb, 4)
+
+
+def test_gmm_resident_converges_at_the_same_iteration(backend, capsys):
+    Qa, na = _gmm(200, 2, 4, resident=True)
+    Qb, nb = _gmm(200, 2, 4, resident=False)
+    Qa.update(repeat=400, tol=1e-6)
+    Qb.update(repeat=400, tol=1e-6)
+    out = capsys.readouterr().out
+    assert out.count("Converged at iteration %d." % Qb.iter) == 2
+    assert Qa.iter == Qb.iter and Qa.iter < 400
+    _compare_gmm(Qa, na, Qb, nb, Qa.iter, rtol=1e-8)
+    # silent run: chunks of sweeps between two host reads, same stopping point
+    Qc, nc = _gmm(200, 2, 4, resident=True)
+    Qc.update(repeat=400, tol=1e-6, verbose=False)
+    assert Qc.iter == Qb.iter and Qc.converged
+    _compare_gmm(Qc, nc, Qb, nb, Qc.iter, rtol=1e-8)
+
+
+def test_gmm_resident_mixed_with_single_node_updates(backend):
+    Qa, na = _gmm(150, 3, 4, resident=True)
+    Qb, nb = _gmm(150, 3, 4, resident=False)
+    for Q, n in ((Qa, na), (Qb, nb)):
+        Q.update(repeat=2, verbose=False, tol=0)
+        Q.update(n["mu"], n["alpha"], repeat=1, verbose=False, tol=0)      # not a full sweep: per-node path
+        Q.update(repeat=2, verbose=False, tol=0)                           # state rebuilt from the nodes
+        Q.update(repeat=1, verbose=False, tol=0)                           # state re-used
+    _compare_gmm(Qa, na, Qb, nb, 6)
+
+
+def test_gmm_callback_keeps_the_node_updates_on_the_device(backend):
+    seen = []
+    res = []
+    for resident in (True, False):
+        Q, n = _gmm(150, 3, 4, resident=resident)
+        Q.set_callback(lambda: seen.append(float(np.asarray(n["alpha"].u[0])[0])))
+        Q.update(repeat=4, verbose=False, tol=0)
+        res.append((Q.L[:4].copy(), np.asarray(n["mu"].u[0]).copy()))
+    assert len(seen) == 8
+    np.testing.assert_allclose(seen[:4], seen[4:], rtol=1e-8)
+    np.testing.assert_allclose(res[0][0], res[1][0], rtol=1e-9)
+    np.testing.assert_allclose(res[0][1], res[1][1], rtol=1e-7, atol=1e-9)
+
+
+def test_gmm_observing_a_hyper_node_leaves_the_resident_path(backend):
+    Q, n = _gmm(120, 2, 3, resident=True)
+    Q.update(repeat=2, verbose=False, tol=0)
+    assert Q.plans[0].resident_program(Q, Q.model) is not None
+    n["alpha"].observe(np.full(3, 1.0 / 3))
+    assert Q.plans[0].resident_program(Q, Q.model) is None
+    Q.update(repeat=2, verbose=False, tol=0)            # generic path, no error
+    assert np.isfinite(Q.L[3])
+
+
+def test_gmm_layout_of_the_library_matches_the_oracle():
+    from bayespy_b200 import _bpk
+    from oracle.bpk_ref import RefBackend
+    if not os.path.exists(_bpk.LIB_PATH):
+        pytest.skip("libbpk.so not built")
+    lib = ctypes.CDLL(_bpk.LIB_PATH)
+    lib.bpk_gmm_vb_field_name.restype = ctypes.c_char_p
+    for Dm, K in ((8, 64), (3, 5), (1, 2), (16, 128)):
+        n = ctypes.c_int()
+        assert lib.bpk_gmm_vb_layout(Dm, K, None, ctypes.byref(n)) == 0
+        off = (ctypes.c_int64 * (n.value + 1))()
+        assert lib.bpk_gmm_vb_layout(Dm, K, off, ctypes.byref(n)) == 0
+        lay, total = RefBackend().gmm_vb_layout(Dm, K)
+        assert total == off[n.value] and len(lay) == n.value
+        for i in range(n.value):
+            name = lib.bpk_gmm_vb_field_name(i).decode()
+            assert lay[name][0] == off[i] and lay[name][1] <= off[i + 1] - off[i], name

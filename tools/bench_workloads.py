@@ -117,7 +117,7 @@ def run_gmm(args):
     plan.kernel_timers = [be.timer_create() for _ in range(steps)]
     plan._timer_pos = 0
     t_all = be.timer_create()
-    parallel.barrier()
+    parallel.barrier_aligned()
     l0 = be.launch_count()
     wall0 = time.perf_counter()
     be.timer_record(t_all, 0)
@@ -267,7 +267,7 @@ def run_pca_masked(args):
     plan.kernel_timers = [be.timer_create() for _ in range(steps)]
     plan._timer_pos = 0
     t_all = be.timer_create()
-    parallel.barrier()
+    parallel.barrier_aligned()
     l0 = be.launch_count()
     wall0 = time.perf_counter()
     be.timer_record(t_all, 0)

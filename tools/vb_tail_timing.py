@@ -18,7 +18,7 @@ y = bench.synth_shard(64, rank * N, (rank + 1) * N, 1)
 Q, nodes = bench.build_model(y)
 Q.update(repeat=int(os.environ.get("TAIL_SWEEPS", "5")), verbose=False)
 be = _bpk.get()
-s = be.debug_stamps(64)
+s = be.debug_stamps(192)
 parallel.barrier()
 if rank != 0:
     sys.exit(0)
@@ -57,3 +57,9 @@ if s[48] and s[56]:
             print("    %-44s %10.2f" % (nm, (s[i] - b) / 1e3))
 print("  %-32s %10.2f" % (names[5], (s[5] - t0) / 1e3))
 print("  tail total (after data pass)     %10.2f" % ((s[5] - s[1]) / 1e3))
+
+sw = [v for v in s[64:192] if v]
+if len(sw) > 2:
+    d = [(sw[0] - t0) / 1e3] + [(b - a) / 1e3 for a, b in zip(sw, sw[1:])]
+    print("  sweeps of the last launch, service CTA passing grid barrier 1 (us since the previous one; first: since kernel start):")
+    print("    " + " ".join("%.1f" % v for v in d))
