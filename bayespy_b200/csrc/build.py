@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, "libbpk.so")
 SOURCES = ["runtime.cu", "ewise.cu", "reduce.cu", "linalg.cu", "nodes.cu", "pca.cu", "pca_vb.cu", "pca_masked.cu", "gmm_vb.cu", "gmm.cu", "gmc.cu"]
-HEADERS = ["common.cuh", "spd.cuh", "spd16.cuh", "warp_spd.cuh", "pca_common.cuh", "pca_vb_ops.cuh", os.path.join("..", "..", "include", "bpk.h")]
+HEADERS = ["common.cuh", "spd.cuh", "spd16.cuh", "warp_spd.cuh", "gmc_bcr3.cuh", "pca_common.cuh", "pca_vb_ops.cuh", os.path.join("..", "..", "include", "bpk.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

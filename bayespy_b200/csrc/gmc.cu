@@ -193,6 +193,8 @@ __device__ __forceinline__ void gmc_ld(double *dst, int ld, const double *src, i
     for (int e = threadIdx.x; e < D * D; e += blockDim.x) dst[(e / D) * ld + (e % D)] = src[e];
 }
 
+#include "gmc_bcr3.cuh"
+
 // eliminated node: invert the pivot, form G1, G2, v
 __global__ void __launch_bounds__(256) gmc_bcr_elim(BcrArgs a, int base_only) {
     extern __shared__ double sm[];
@@ -377,20 +379,47 @@ static int gmc_bcr_solve(const double *A, const double *B, const double *y, int6
     const int threads = 256;
     std::vector<int64_t> strides;
     int lvl = 0;
+    // version 3 (one warp per node, rows in registers: gmc_bcr3.cuh) for D <= 32; BPK_GMC_BCR_V2=1 keeps the CTA-per-node kernels
+    const bool v3 = D <= 32 && !getenv("BPK_GMC_BCR_V2");
+    const int DP = D <= 8 ? 8 : (D <= 16 ? 16 : 32);
+    const size_t w3 = (size_t)(2 * DP * (DP + 2) + 2 * DP) * sizeof(double), w3b = (size_t)(3 * DP * (DP + 2) + 2 * DP) * sizeof(double);
+    const size_t sm3_ek = BW_WARPS * w3, sm3_b = BW_WARPS * w3b;
+#define BCR3_DISPATCH(KERNEL, NODES, SMEM, ...)                                                                        \
+    do {                                                                                                             \
+        const unsigned g3 = (unsigned)(((NODES) + BW_WARPS - 1) / BW_WARPS);                                          \
+        if (DP == 8) {                                                                                               \
+            BPK_CUDA(cudaFuncSetAttribute(KERNEL<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM)));     \
+            BPK_LAUNCH(KERNEL<8>, g3, BW_WARPS * 32, SMEM, __VA_ARGS__);                                              \
+        } else if (DP == 16) {                                                                                       \
+            BPK_CUDA(cudaFuncSetAttribute(KERNEL<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM)));    \
+            BPK_LAUNCH(KERNEL<16>, g3, BW_WARPS * 32, SMEM, __VA_ARGS__);                                             \
+        } else {                                                                                                     \
+            BPK_CUDA(cudaFuncSetAttribute(KERNEL<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM)));    \
+            BPK_LAUNCH(KERNEL<32>, g3, BW_WARPS * 32, SMEM, __VA_ARGS__);                                             \
+        }                                                                                                            \
+    } while (0)
     for (int64_t s = 1; (T + s - 1) / s > 1; s *= 2, ++lvl) {
         const int64_t nact = (T + s - 1) / s, nel = nact / 2, nkeep = (nact + 1) / 2;
         a.s = s; a.off_this = off[lvl]; a.off_next = off[lvl + 1];
-        BPK_LAUNCH(gmc_bcr_elim, (unsigned)nel, threads, sm_elim, a, 0);
-        BPK_LAUNCH(gmc_bcr_keep, (unsigned)nkeep, threads, sm_keep, a);
+        if (v3) {
+            BCR3_DISPATCH(gmc_bcr3_elim, nel, sm3_ek, a, 0, nel);
+            BCR3_DISPATCH(gmc_bcr3_keep, nkeep, sm3_ek, a, nkeep);
+        } else {
+            BPK_LAUNCH(gmc_bcr_elim, (unsigned)nel, threads, sm_elim, a, 0);
+            BPK_LAUNCH(gmc_bcr_keep, (unsigned)nkeep, threads, sm_keep, a);
+        }
         strides.push_back(s);
     }
     a.s = 1; a.off_this = 0; a.off_next = 0;
-    BPK_LAUNCH(gmc_bcr_elim, 1, threads, sm_elim, a, 1);                 // the last node standing
+    if (v3) BCR3_DISPATCH(gmc_bcr3_elim, (int64_t)1, sm3_ek, a, 1, (int64_t)1);      // the last node standing
+    else BPK_LAUNCH(gmc_bcr_elim, 1, threads, sm_elim, a, 1);
     for (int q = (int)strides.size() - 1; q >= 0; --q) {
         const int64_t s = strides[q], nact = (T + s - 1) / s, nel = nact / 2;
         a.s = s; a.off_this = off[q]; a.off_next = off[q + 1];
-        BPK_LAUNCH(gmc_bcr_back, (unsigned)nel, threads, sm_back, a);
+        if (v3) BCR3_DISPATCH(gmc_bcr3_back, nel, sm3_b, a, nel);
+        else BPK_LAUNCH(gmc_bcr_back, (unsigned)nel, threads, sm_back, a);
     }
+#undef BCR3_DISPATCH
     BPK_LAUNCH(gmc_sum_kernel, 1, 1024, 0, a.ldnode, T, logdet);
     BPK_CUDA(cudaFreeAsync(ws, g_bpk.stream));
     return BPK_OK;

@@ -834,28 +834,7 @@ class FactorModelPlan:
             if self.kernel_timers is not None and self.kernel_timer_log and self.kernel_timer_log[-1][1] is None:
                 self.kernel_timer_log[-1] = (self.kernel_timer_log[-1][0], n_it)
             self._raise_ctrl_errors(err)
-            Lrows = Lh.numpy()[:n_it]
-            for r in range(n_it):
-                if vb.iter >= len(vb.L):
-                    vb._append_iterations(100)
-                for node in vb.model:
-                    vb.l[node][vb.iter] = Lrows[r, terms_of[node]] if node in terms_of else 0.0
-                L = float(Lrows[r, 5])
-                vb.L[vb.iter] = L
-                vb.cputime[vb.iter] = dt / max(n_it, 1)
-                if verbose:
-                    vb.print("Iteration %d: loglike=%e (%.3f seconds)" % (vb.iter + 1, L, dt / max(n_it, 1)))
-                vb.converged = False
-                if check and not vb.annealing_changed and vb.iter > 0:
-                    L0 = vb.L[vb.iter - 1]
-                    if L0 - L > 1e-6:
-                        warnings.warn("Lower bound decreased %e! Bug somewhere or numerical inaccuracy?" % (L0 - L))
-                    if r == n_it - 1 and stop:
-                        if verbose:
-                            vb.print("Converged at iteration %d." % (vb.iter + 1))
-                        vb.converged = True
-                vb.annealing_changed = False
-                vb.iter += 1
+            vb._record_resident_iterations(Lh.numpy()[:n_it], terms_of, dt, stop, check, verbose)
             done += n_it
             self.fused_calls += n_it
             converged = bool(stop)
@@ -1353,28 +1332,7 @@ class GaussianMixturePlan:
                 self._timer_pos += min(len(ids), max(n_it, 0))
                 be.gmm_vb_set_timers([])
             self._raise_ctrl_errors(err)
-            Lrows = Lh.numpy()[:n_it]
-            for r in range(n_it):
-                if vb.iter >= len(vb.L):
-                    vb._append_iterations(100)
-                for node in vb.model:
-                    vb.l[node][vb.iter] = Lrows[r, terms_of[node]] if node in terms_of else 0.0
-                L = float(Lrows[r, 5])
-                vb.L[vb.iter] = L
-                vb.cputime[vb.iter] = dt / max(n_it, 1)
-                if verbose:
-                    vb.print("Iteration %d: loglike=%e (%.3f seconds)" % (vb.iter + 1, L, dt / max(n_it, 1)))
-                vb.converged = False
-                if check and not vb.annealing_changed and vb.iter > 0:
-                    L0 = vb.L[vb.iter - 1]
-                    if L0 - L > 1e-6:
-                        warnings.warn("Lower bound decreased %e! Bug somewhere or numerical inaccuracy?" % (L0 - L))
-                    if r == n_it - 1 and stop:
-                        if verbose:
-                            vb.print("Converged at iteration %d." % (vb.iter + 1))
-                        vb.converged = True
-                vb.annealing_changed = False
-                vb.iter += 1
+            vb._record_resident_iterations(Lh.numpy()[:n_it], terms_of, dt, stop, check, verbose)
             done += n_it
             self.fused_calls += n_it
             converged = bool(stop)

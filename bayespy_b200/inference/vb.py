@@ -224,6 +224,49 @@ class VB:
         for node in self.l:
             self.l[node] = np.append(self.l[node], nans)
 
+    def _record_resident_iterations(self, rows, terms_of, dt, stop, check, verbose):
+        """Book-keeping of ``n`` iterations a device-resident loop has run (one row of bound terms each,
+        total in column 5): what _end_iteration_step does per iteration (vmp.py:693-764), for a whole chunk with
+        array assignments — the per-iteration Python loop is kept for verbose runs only."""
+        import warnings
+        n = len(rows)
+        if n == 0:
+            return
+        while self.iter + n > len(self.L):
+            self._append_iterations(100)
+        i0 = self.iter
+        Ls = rows[:, 5]
+        for node in self.model:
+            self.l[node][i0:i0 + n] = rows[:, terms_of[node]] if node in terms_of else 0.0
+        self.L[i0:i0 + n] = Ls
+        self.cputime[i0:i0 + n] = dt / n
+        compare = check and not self.annealing_changed
+        if verbose:
+            for r in range(n):
+                self.print("Iteration %d: loglike=%e (%.3f seconds)" % (i0 + r + 1, Ls[r], dt / n))
+        self.converged = False
+        if compare:
+            prev = np.concatenate(([self.L[i0 - 1]] if i0 > 0 else [np.nan], Ls[:-1]))
+            if i0 == 0:
+                prev[0] = np.nan
+            for d in (prev - Ls)[(prev - Ls) > 1e-6]:
+                warnings.warn("Lower bound decreased %e! Bug somewhere or numerical inaccuracy?" % d)
+            if stop and (i0 + n - 1) > 0:
+                if verbose:
+                    self.print("Converged at iteration %d." % (i0 + n))
+                self.converged = True
+        elif check and n > 1:
+            # the first iteration after an annealing change is not compared; the later ones of the chunk are
+            d = Ls[:-1] - Ls[1:]
+            for v in d[d > 1e-6]:
+                warnings.warn("Lower bound decreased %e! Bug somewhere or numerical inaccuracy?" % v)
+            if stop:
+                if verbose:
+                    self.print("Converged at iteration %d." % (i0 + n))
+                self.converged = True
+        self.annealing_changed = False
+        self.iter = i0 + n
+
     def _end_iteration_step(self, method, cputime, tol=None, verbose=True, bound_cpu_time=True):
         """vmp.py:693-764: callback, bound, print, decrease warning, convergence test."""
         if self.iter >= len(self.L):

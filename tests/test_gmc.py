@@ -120,7 +120,7 @@ def F_plates(Q):
     return tuple(Q["Y"].plates)
 
 
-@pytest.mark.parametrize("T,Dm", [(777, 6), (64, 32), (1025, 3), (9, 2)])
+@pytest.mark.parametrize("T,Dm", [(777, 6), (64, 32), (1025, 3), (9, 2), (300, 12), (130, 16), (50, 40), (2049, 32)])
 def test_block_banded_long_chain_vs_oracle(backend, T, Dm):
     """Chains long enough for the parallel-in-time (block cyclic reduction) path, any T (not only powers of two),
     against the oracle's sequential restatement of linalg.block_banded_solve."""

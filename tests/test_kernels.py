@@ -142,6 +142,31 @@ def test_gamma_moments_golden(backend):
     u, cgf = GammaDistribution().compute_moments_and_cgf([D.asarray(g["gam_phi0"]), D.asarray(g["gam_phi1"])])
     close(u[0].numpy(), g["gam_u0"]); close(u[1].numpy(), g["gam_u1"]); close(cgf.numpy(), g["gam_g"])
 
+@pytest.mark.parametrize("shape_a,shape_b", [((6, 8), (6, 8)), ((5, 4, 4), (1, 4, 4)), ((5, 4, 4), (5, 1, 1)), ((64,), ()),
+                                            ((7, 10), (10,)), ((7, 10), (7, 1)), ((3, 5, 6), (3, 1, 6)), ((9, 7), (9, 7)),
+                                            ((2, 3, 4, 6), (1, 3, 1, 6)), ((1000, 32, 32), (32, 32))])
+def test_ewise_fast_path_broadcasts(backend, shape_a, shape_b):
+    """Even inner extents with contiguous / broadcast operands take the 16-byte path of bpk_ewise (one outer axis at most
+    after collapsing); everything else the generic kernel.  Same results either way, bit for bit (pure elementwise)."""
+    from bayespy_b200 import darray as D
+    rng = np.random.RandomState(3)
+    a, b = rng.randn(*shape_a), rng.randn(*shape_b) + 3.0
+    A, B = D.asarray(a), D.asarray(b)
+    np.testing.assert_array_equal((A + B).numpy(), a + b)
+    np.testing.assert_array_equal((A * B).numpy(), a * b)
+    np.testing.assert_array_equal((B - A).numpy(), b - a)
+    np.testing.assert_array_equal((A / B).numpy(), a / b)
+    close(D.axpby(2.0, A, -3.0, B).numpy(), 2.0 * a + -3.0 * b, rtol=1e-15, atol=1e-15)      # fused multiply-add on device
+    close(D.affine(A, 1.5, 0.25).numpy(), 1.5 * a + 0.25, rtol=1e-15, atol=1e-15)
+    got = D.fma(0.5, A, B, 2.0, A).numpy()
+    close(got, 0.5 * a * b + 2.0 * a, rtol=1e-15, atol=1e-15)
+    # a view that starts 8 bytes into its buffer is not 16-byte aligned: generic kernel
+    if a.ndim == 1:
+        v = D.asarray(np.concatenate([[0.0], a]))
+        odd = v.slice_axis(0, 1, 1 + a.size)
+        np.testing.assert_array_equal((odd + B).numpy(), a + b)
+
+
 
 def test_gamma_domain_error(backend):
     from bayespy_b200 import darray as D
