@@ -361,9 +361,12 @@ static int gmc_bcr_solve(const double *A, const double *B, const double *y, int6
         int64_t nact = (T + s - 1) / s;
         tot += nact > 1 ? nact - 1 : 1;
     }
-    double *ws = nullptr;
+    // Workspace from the library's persistent stream-ordered scratch (2.4 GB at T = 1e5, D = 32): a cudaMallocAsync /
+    // cudaFreeAsync pair per call made the pool re-map physical memory whenever other allocations had split the block
+    // in between — stalls of 90-480 ms inside X.update() (round 2, session 11).
     size_t wsd = ((size_t)tot + 2 * (size_t)T) * blk + (size_t)T;
-    BPK_CUDA(cudaMallocAsync((void **)&ws, wsd * sizeof(double), g_bpk.stream));
+    double *ws = bpk_scratch(wsd * sizeof(double));
+    if (!ws) return bpk_set_error(BPK_ECUDA, "bpk_block_banded_solve: workspace of %zu bytes", wsd * sizeof(double));
     BcrArgs a;
     a.V = V; a.x = x; a.B = B; a.C = C; a.T = T; a.D = D; a.flag = g_bpk.d_flag;
     a.lev = ws; a.G1 = ws + (size_t)tot * blk; a.G2 = a.G1 + (size_t)T * blk; a.ldnode = a.G2 + (size_t)T * blk;
@@ -382,7 +385,7 @@ static int gmc_bcr_solve(const double *A, const double *B, const double *y, int6
     // version 3 (one warp per node, rows in registers: gmc_bcr3.cuh) for D <= 32; BPK_GMC_BCR_V2=1 keeps the CTA-per-node kernels
     const bool v3 = D <= 32 && !getenv("BPK_GMC_BCR_V2");
     const int DP = D <= 8 ? 8 : (D <= 16 ? 16 : 32);
-    const size_t w3 = (size_t)(2 * DP * (DP + 2) + 2 * DP) * sizeof(double), w3b = (size_t)(3 * DP * (DP + 2) + 2 * DP) * sizeof(double);
+    const size_t w3 = (size_t)(2 * DP * (DP + 4) + 2 * DP) * sizeof(double), w3b = (size_t)(3 * DP * (DP + 4) + 2 * DP) * sizeof(double);
     const size_t sm3_ek = BW_WARPS * w3, sm3_b = BW_WARPS * w3b;
 #define BCR3_DISPATCH(KERNEL, NODES, SMEM, ...)                                                                        \
     do {                                                                                                             \
@@ -421,7 +424,6 @@ static int gmc_bcr_solve(const double *A, const double *B, const double *y, int6
     }
 #undef BCR3_DISPATCH
     BPK_LAUNCH(gmc_sum_kernel, 1, 1024, 0, a.ldnode, T, logdet);
-    BPK_CUDA(cudaFreeAsync(ws, g_bpk.stream));
     return BPK_OK;
 }
 

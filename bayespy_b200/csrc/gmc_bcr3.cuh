@@ -4,20 +4,25 @@
 // linalg.py:468-575 restated as a parallel-in-time elimination with selected inversion).  Those spend their time in
 // block-wide barriers (a 32-step Gauss-Jordan with two __syncthreads per pivot, scalar shared-memory dot products):
 // 22 ms per smoother pass at T = 1e5, D = 32, for 85 GFLOP of work (2.3 ms on the fp64 pipe).  Here a warp owns a
-// node: lane r keeps row r of the matrix it works on in registers, the other operand of every D x D product is a
-// shared-memory tile read with 16-byte broadcast loads (one row of the tile per output column), and the only
-// synchronisation is __syncwarp.  D <= 32 (padded to DP = 8, 16 or 32 with an identity / zero border).
+// node and the only synchronisation is __syncwarp.  Every D x D product runs on the fp64 tensor pipe
+// (mma.sync.m8n8k4: A fragments from a row-major tile, B fragments from a tile holding B transposed, both
+// bank-conflict free at a pitch of DP + 4) — a first version with lane-owns-row FMA products and 16-byte broadcast
+// reads of the other operand was bound by shared-memory bandwidth (512 LDS.128 per product: 7.3 ms for level 0 at
+// T = 1e5 against 11.3 ms of the CTA-per-node kernels).  The pivot inverse keeps lane r = row r in registers
+// (symmetric sweep operator, pivot column exchanged through shared memory).  D <= 32, padded to DP = 8, 16 or 32
+// with an identity / zero border.
 #pragma once
 #include "common.cuh"
 
 #define BW_WARPS 4                 // warps (= nodes) per CTA
 
-template <int DP> struct BwTile { static constexpr int LD = DP + 2; };      // 16-byte aligned rows, even pitch
+template <int DP> struct BwTile { static constexpr int LD = DP + 4; };      // 16-byte aligned rows; fragment loads conflict free
 
 // global (row-major D x D) -> tile, optionally transposed; the border up to DP is zero
 template <int DP>
 __device__ __forceinline__ void bw_load(double *tile, const double *__restrict__ src, int D, int lane, bool transpose) {
     constexpr int LD = BwTile<DP>::LD;
+    __syncwarp();                             // every lane is done with the previous contents of the tile
     if (D == DP) {
 #pragma unroll 4
         for (int e = lane; e < DP * DP; e += 32) {
@@ -84,22 +89,72 @@ __device__ __forceinline__ void bw_row_put(double *tile, const double (&a)[DP], 
     }
     __syncwarp();
 }
-// out[c] (+)= sum_k a[k] * Bt[c][k]   — row r of (A B) with B given TRANSPOSED in the tile (Bt[c][k] = B[k][c])
-template <int DP, bool ACC>
-__device__ __forceinline__ void bw_mul(double (&out)[DP], const double (&a)[DP], const double *Bt) {
-    constexpr int LD = BwTile<DP>::LD;
+__device__ __forceinline__ void bw_dmma(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+// acc += A B with A a row-major tile ([m][k]) and B given TRANSPOSED (Bt[n][k] = B[k][n]); acc in the accumulator
+// layout of m8n8k4: tile (i, j), lane (gr, tg) holds C[i*8+gr][j*8+2tg], C[i*8+gr][j*8+2tg+1]
+template <int DP>
+__device__ __forceinline__ void bw_mma(double (&acc)[DP / 8][DP / 8][2], const double *A, const double *Bt, int lane) {
+    constexpr int LD = BwTile<DP>::LD, NB = DP / 8;
+    const int gr = lane >> 2, tg = lane & 3;
 #pragma unroll
-    for (int c = 0; c < DP; ++c) {
-        const double2 *row = reinterpret_cast<const double2 *>(Bt + c * LD);
-        double s0 = ACC ? out[c] : 0.0, s1 = 0.0;
+    for (int ks = 0; ks < DP / 4; ++ks) {
+        double af[NB], bf[NB];
 #pragma unroll
-        for (int k = 0; k < DP / 2; ++k) {
-            const double2 b = row[k];
-            s0 = fma(a[2 * k], b.x, s0);
-            s1 = fma(a[2 * k + 1], b.y, s1);
-        }
-        out[c] = s0 + s1;
+        for (int i = 0; i < NB; ++i) af[i] = A[(i * 8 + gr) * LD + ks * 4 + tg];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) bf[j] = Bt[(j * 8 + gr) * LD + ks * 4 + tg];
+#pragma unroll
+        for (int i = 0; i < NB; ++i)
+#pragma unroll
+            for (int j = 0; j < NB; ++j) bw_dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
     }
+}
+template <int DP>
+__device__ __forceinline__ void bw_acc_zero(double (&acc)[DP / 8][DP / 8][2]) {
+#pragma unroll
+    for (int i = 0; i < DP / 8; ++i)
+#pragma unroll
+        for (int j = 0; j < DP / 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+}
+// tile = scale * acc   /   tile -= acc
+template <int DP, bool SUB>
+__device__ __forceinline__ void bw_acc_put(double *tile, const double (&acc)[DP / 8][DP / 8][2], int lane, double scale) {
+    constexpr int LD = BwTile<DP>::LD;
+    const int gr = lane >> 2, tg = lane & 3;
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < DP / 8; ++i)
+#pragma unroll
+        for (int j = 0; j < DP / 8; ++j) {
+            double2 *p = reinterpret_cast<double2 *>(tile + (i * 8 + gr) * LD + j * 8 + 2 * tg);
+            if (SUB) { double2 v = *p; v.x -= acc[i][j][0]; v.y -= acc[i][j][1]; *p = v; }
+            else *p = make_double2(scale * acc[i][j][0], scale * acc[i][j][1]);
+        }
+    __syncwarp();
+}
+// lane r: sum_k tile[r][k] * v[k]  (v: shared-memory vector, zero padded to DP); lanes >= DP return 0
+template <int DP>
+__device__ __forceinline__ double bw_rowdot(const double *tile, const double *v, int lane) {
+    constexpr int LD = BwTile<DP>::LD;
+    const double2 *row = reinterpret_cast<const double2 *>(tile + (lane < DP ? lane : 0) * LD);
+    const double2 *p = reinterpret_cast<const double2 *>(v);
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < DP / 2; ++k) {
+        const double2 a = row[k], b = p[k];
+        s0 = fma(a.x, b.x, s0);
+        s1 = fma(a.y, b.y, s1);
+    }
+    return lane < DP ? s0 + s1 : 0.0;
+}
+template <int DP>
+__device__ __forceinline__ void bw_vec_load(double *vec, const double *__restrict__ src, int D, int lane) {
+    __syncwarp();
+    if (lane < DP) vec[lane] = lane < D ? src[lane] : 0.0;
+    __syncwarp();
 }
 // sum_k a[k] * v[k] with v a shared-memory vector (16-byte aligned, zero padded to DP)
 template <int DP>
@@ -160,35 +215,39 @@ __global__ void __launch_bounds__(BW_WARPS * 32, 2) gmc_bcr3_elim(BcrArgs a, int
     const int64_t j = base_only ? 0 : a.s * (2 * node + 1);
     double *Vj = a.V + j * D * D;
     bw_load<DP>(TA, Vj, D, lane, false);
-    double r[DP];
+    {
+        double r[DP];
 #pragma unroll
-    for (int k = 0; k < DP; ++k) {
-        // symmetrised pivot block; identity on the padded border
-        const double v = lane < DP ? 0.5 * (TA[lane * LD + k] + TA[k * LD + lane]) : 0.0;
-        r[k] = (lane < D && k < D) ? v : ((lane == k && lane < DP) ? 1.0 : 0.0);
+        for (int k = 0; k < DP; ++k) {
+            // symmetrised pivot block; identity on the padded border
+            const double v = lane < DP ? 0.5 * (TA[lane * LD + k] + TA[k * LD + lane]) : 0.0;
+            r[k] = (lane < D && k < D) ? v : ((lane == k && lane < DP) ? 1.0 : 0.0);
+        }
+        bw_vec_load<DP>(vec, a.x + j * D, D, lane);
+        int bad = 0;
+        const double ldet = bw_spd_inverse<DP>(r, col, lane, bad);
+        if (bad && lane == 0) atomicOr(a.flag, BPK_FLAG_NOTSPD);
+        if (lane == 0) a.ldnode[j] = ldet;
+        __syncwarp();
+        const double vj = bw_dot<DP>(r, vec);
+        if (lane < D) a.x[j * D + lane] = vj;
+        bw_row_put<DP>(TA, r, lane);                              // TA = Ainv_j (stays for the products)
     }
-    if (lane < DP) vec[lane] = lane < D ? a.x[j * D + lane] : 0.0;
-    int bad = 0;
-    const double ldet = bw_spd_inverse<DP>(r, col, lane, bad);
-    if (bad && lane == 0) atomicOr(a.flag, BPK_FLAG_NOTSPD);
-    if (lane == 0) a.ldnode[j] = ldet;
-    __syncwarp();
-    const double vj = bw_dot<DP>(r, vec);
-    if (lane < D) a.x[j * D + lane] = vj;
-    bw_row_put<DP>(TA, r, lane);
     bw_store<DP>(Vj, TA, D, lane, false, 1.0);
     if (base_only) return;
     const bool hasr = j + a.s < a.T;
-    double o[DP];
-    bw_load<DP>(TB, bcr_P(a, j - a.s), D, lane, false);          // Bt = P_ij  (B = P_ij^T)
-    bw_mul<DP, false>(o, r, TB);
-    bw_row_put<DP>(TA, o, lane);
-    bw_store<DP>(a.G1 + j * D * D, TA, D, lane, false, 1.0);
+    double acc[DP / 8][DP / 8][2];
+    bw_acc_zero<DP>(acc);
+    bw_load<DP>(TB, bcr_P(a, j - a.s), D, lane, false);           // Bt = P_ij  (B = P_ij^T)
+    bw_mma<DP>(acc, TA, TB, lane);
+    bw_acc_put<DP, false>(TB, acc, lane, 1.0);
+    bw_store<DP>(a.G1 + j * D * D, TB, D, lane, false, 1.0);
     if (hasr) {
-        bw_load<DP>(TB, bcr_P(a, j), D, lane, true);             // Bt = P_jk^T
-        bw_mul<DP, false>(o, r, TB);
-        bw_row_put<DP>(TA, o, lane);
-        bw_store<DP>(a.G2 + j * D * D, TA, D, lane, false, 1.0);
+        bw_acc_zero<DP>(acc);
+        bw_load<DP>(TB, bcr_P(a, j), D, lane, true);              // Bt = P_jk^T
+        bw_mma<DP>(acc, TA, TB, lane);
+        bw_acc_put<DP, false>(TB, acc, lane, 1.0);
+        bw_store<DP>(a.G2 + j * D * D, TB, D, lane, false, 1.0);
     } else {
         for (int e = lane; e < D * D; e += 32) a.G2[j * D * D + e] = 0.0;
     }
@@ -205,44 +264,35 @@ __global__ void __launch_bounds__(BW_WARPS * 32, 2) gmc_bcr3_keep(BcrArgs a, int
     double *TA = sm3 + (size_t)w * (2 * DP * LD + 2 * DP), *TB = TA + DP * LD, *vec = TB + DP * LD;
     const int64_t i = 2 * a.s * node, l = i - a.s, rn = i + a.s;
     const bool hasl = l >= 0, hasr = rn < a.T, hasn = rn + a.s < a.T;
-    double acc[DP], p[DP];
-#pragma unroll
-    for (int c = 0; c < DP; ++c) acc[c] = 0.0;
+    double acc[DP / 8][DP / 8][2];
+    bw_acc_zero<DP>(acc);
     double xs = 0.0;
     if (hasl) {
-        bw_load<DP>(TA, bcr_P(a, l), D, lane, true);             // rows of P_li^T
-        bw_row_get<DP>(p, TA, lane);
-        bw_load<DP>(TB, a.G2 + l * D * D, D, lane, true);        // Bt = G2_l^T
-        bw_mul<DP, true>(acc, p, TB);
-        __syncwarp();
-        if (lane < DP) vec[lane] = lane < D ? a.x[l * D + lane] : 0.0;
-        __syncwarp();
-        xs += bw_dot<DP>(p, vec);
+        bw_load<DP>(TA, bcr_P(a, l), D, lane, true);              // A = P_li^T
+        bw_vec_load<DP>(vec, a.x + l * D, D, lane);
+        xs += bw_rowdot<DP>(TA, vec, lane);
+        bw_load<DP>(TB, a.G2 + l * D * D, D, lane, true);         // Bt = G2_l^T
+        bw_mma<DP>(acc, TA, TB, lane);
     }
     if (hasr) {
-        bw_load<DP>(TA, bcr_P(a, i), D, lane, false);            // rows of P_ir
-        bw_row_get<DP>(p, TA, lane);
-        bw_load<DP>(TB, a.G1 + rn * D * D, D, lane, true);       // Bt = G1_r^T
-        bw_mul<DP, true>(acc, p, TB);
-        __syncwarp();
-        if (lane < DP) vec[lane] = lane < D ? a.x[rn * D + lane] : 0.0;
-        __syncwarp();
-        xs += bw_dot<DP>(p, vec);
+        bw_load<DP>(TA, bcr_P(a, i), D, lane, false);             // A = P_ir
+        bw_vec_load<DP>(vec, a.x + rn * D, D, lane);
+        xs += bw_rowdot<DP>(TA, vec, lane);
+        bw_load<DP>(TB, a.G1 + rn * D * D, D, lane, true);        // Bt = G1_r^T
+        bw_mma<DP>(acc, TA, TB, lane);
         if (hasn) {
-            double u[DP];
-            bw_load<DP>(TB, a.G2 + rn * D * D, D, lane, true);   // Bt = G2_r^T
-            bw_mul<DP, false>(u, p, TB);
-            bw_row_put<DP>(TA, u, lane);
-            bw_store<DP>(a.lev + (a.off_next + i / (2 * a.s)) * D * D, TA, D, lane, false, -1.0);
+            double u[DP / 8][DP / 8][2];
+            bw_acc_zero<DP>(u);
+            bw_load<DP>(TB, a.G2 + rn * D * D, D, lane, true);    // Bt = G2_r^T
+            bw_mma<DP>(u, TA, TB, lane);
+            bw_acc_put<DP, false>(TB, u, lane, -1.0);
+            bw_store<DP>(a.lev + (a.off_next + i / (2 * a.s)) * D * D, TB, D, lane, false, 1.0);
         }
     }
     if (lane < D) a.x[i * D + lane] -= xs;
     double *Vi = a.V + i * D * D;
     bw_load<DP>(TA, Vi, D, lane, false);
-    bw_row_get<DP>(p, TA, lane);
-#pragma unroll
-    for (int c = 0; c < DP; ++c) p[c] -= acc[c];
-    bw_row_put<DP>(TA, p, lane);
+    bw_acc_put<DP, true>(TA, acc, lane, 1.0);                     // A_i - (...)
     bw_store_sym<DP>(Vi, TA, D, lane);
 }
 
@@ -262,53 +312,41 @@ __global__ void __launch_bounds__(BW_WARPS * 32, 2) gmc_bcr3_back(BcrArgs a, int
     const double *Sik_g = a.lev + (a.off_next + i / (2 * a.s)) * D * D;       // S_{i,k} from the coarser level
     double *Cf_i = a.s == 1 ? a.C + i * D * D : a.lev + (a.off_this + i / a.s) * D * D;     // S_{i,j}
     double *Cf_j = a.s == 1 ? a.C + j * D * D : a.lev + (a.off_this + j / a.s) * D * D;     // S_{j,k}
-    double g[DP], s[DP], acc[DP];
+    double s[DP / 8][DP / 8][2], acc[DP / 8][DP / 8][2];
     double xs = 0.0;
     // ---- S_ji ----
-    bw_load<DP>(TA, a.G1 + j * D * D, D, lane, false);
-    bw_row_get<DP>(g, TA, lane);                                  // g = row of G1 (TA keeps G1 for the S_jj product)
-    bw_load<DP>(TB, a.V + i * D * D, D, lane, false);             // Bt = S_ii^T = S_ii
-    bw_mul<DP, false>(s, g, TB);
-    __syncwarp();
-    if (lane < DP) vec[lane] = lane < D ? a.x[i * D + lane] : 0.0;
-    __syncwarp();
-    xs += bw_dot<DP>(g, vec);
+    bw_acc_zero<DP>(s);
+    bw_load<DP>(TA, a.G1 + j * D * D, D, lane, false);            // TA = G1 (stays)
+    bw_vec_load<DP>(vec, a.x + i * D, D, lane);
+    xs += bw_rowdot<DP>(TA, vec, lane);
+    bw_load<DP>(TB, a.V + i * D * D, D, lane, false);             // Bt = S_ii (symmetric)
+    bw_mma<DP>(s, TA, TB, lane);
     if (hask) {
-        bw_load<DP>(TC, a.G2 + j * D * D, D, lane, false);        // TC keeps G2
-        bw_row_get<DP>(g, TC, lane);                              // g = row of G2
+        bw_load<DP>(TC, a.G2 + j * D * D, D, lane, false);        // TC = G2 (stays)
+        bw_vec_load<DP>(vec, a.x + k * D, D, lane);
+        xs += bw_rowdot<DP>(TC, vec, lane);
         bw_load<DP>(TB, Sik_g, D, lane, false);                   // Bt = S_ik  (B = S_ik^T)
-        bw_mul<DP, true>(s, g, TB);
-        __syncwarp();
-        if (lane < DP) vec[lane] = lane < D ? a.x[k * D + lane] : 0.0;
-        __syncwarp();
-        xs += bw_dot<DP>(g, vec);
+        bw_mma<DP>(s, TC, TB, lane);
     }
     if (lane < D) a.x[j * D + lane] -= xs;
-#pragma unroll
-    for (int c = 0; c < DP; ++c) s[c] = -s[c];                    // s = row of S_ji
-    bw_mul<DP, false>(acc, s, TA);                                // S_ji G1^T   (Bt = G1)
-    bw_row_put<DP>(TB, s, lane);
+    bw_acc_put<DP, false>(TB, s, lane, -1.0);                     // TB = S_ji
     bw_store<DP>(Cf_i, TB, D, lane, true, 1.0);                   // S_ij = S_ji^T
+    bw_acc_zero<DP>(acc);
+    bw_mma<DP>(acc, TB, TA, lane);                                // S_ji G1^T   (Bt = G1)
     // ---- S_jk ----
     if (hask) {
-        bw_row_get<DP>(g, TA, lane);                              // row of G1 again
+        bw_acc_zero<DP>(s);
         bw_load<DP>(TB, Sik_g, D, lane, true);                    // Bt = S_ik^T
-        bw_mul<DP, false>(s, g, TB);
-        bw_row_get<DP>(g, TC, lane);                              // row of G2
+        bw_mma<DP>(s, TA, TB, lane);
         bw_load<DP>(TB, a.V + k * D * D, D, lane, false);         // Bt = S_kk
-        bw_mul<DP, true>(s, g, TB);
-#pragma unroll
-        for (int c = 0; c < DP; ++c) s[c] = -s[c];                // s = row of S_jk
-        bw_mul<DP, true>(acc, s, TC);                             // + S_jk G2^T  (Bt = G2)
-        bw_row_put<DP>(TB, s, lane);
+        bw_mma<DP>(s, TC, TB, lane);
+        bw_acc_put<DP, false>(TB, s, lane, -1.0);                 // TB = S_jk
         bw_store<DP>(Cf_j, TB, D, lane, false, 1.0);
+        bw_mma<DP>(acc, TB, TC, lane);                            // + S_jk G2^T  (Bt = G2)
     }
     // ---- S_jj ----
     double *Vj = a.V + j * D * D;
     bw_load<DP>(TB, Vj, D, lane, false);                          // Ainv_j
-    bw_row_get<DP>(g, TB, lane);
-#pragma unroll
-    for (int c = 0; c < DP; ++c) g[c] -= acc[c];
-    bw_row_put<DP>(TB, g, lane);
+    bw_acc_put<DP, true>(TB, acc, lane, 1.0);
     bw_store_sym<DP>(Vj, TB, D, lane);
 }
