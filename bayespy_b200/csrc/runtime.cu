@@ -1,6 +1,7 @@
 // runtime.cu — context, memory, timers and the NCCL communicator of libbpk.
 // One process drives one GPU; every call is ordered on one compute stream.
 #include "common.cuh"
+#include <time.h>
 #include <stdarg.h>
 #include <string.h>
 #include <dlfcn.h>
@@ -124,6 +125,17 @@ extern "C" int bpk_malloc(void **dev, uint64_t bytes) {
     BPK_REQUIRE_INIT();
     if (!dev) return bpk_set_error(BPK_EINVAL, "bpk_malloc: null out pointer");
     if (bytes == 0) bytes = 8;
+    static const bool trace = getenv("BPK_TRACE_SLOW") != nullptr;       // diagnostics: allocations that reach the driver
+    if (trace) {
+        struct timespec t0, t1;
+        clock_gettime(CLOCK_MONOTONIC, &t0);
+        cudaError_t e = cudaMallocAsync(dev, bytes, g_bpk.stream);
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        const double ms = 1e3 * (t1.tv_sec - t0.tv_sec) + 1e-6 * (t1.tv_nsec - t0.tv_nsec);
+        if (ms > 2.0) fprintf(stderr, "[bpk] cudaMallocAsync(%.1f MB) took %.1f ms\n", bytes / 1048576.0, ms);
+        if (e != cudaSuccess) return bpk_set_error(BPK_ECUDA, "cudaMallocAsync: %s", cudaGetErrorString(e));
+        return BPK_OK;
+    }
     BPK_CUDA(cudaMallocAsync(dev, bytes, g_bpk.stream));
     return BPK_OK;
 }
