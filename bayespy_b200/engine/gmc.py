@@ -415,6 +415,31 @@ class GaussianMarkovChain(ExponentialFamily):
     def random(self):
         raise NotImplementedError("Sampling from a Gaussian Markov chain is not implemented")
 
+    def rotate(self, R, inv=None, logdet=None):
+        """q(x_1..x_N) -> q(R x_1..R x_N)  (gaussian_markov_chain.py:51-65, :167-184): moments by R, natural parameters
+        by R^-T, log-normaliser by -N log|det R|.  R is a host D x D matrix; the plated arrays rotate on the device."""
+        R = np.asarray(R, dtype=np.float64)
+        invR = np.linalg.inv(R) if inv is None else np.asarray(inv, dtype=np.float64)
+        logdetR = np.linalg.slogdet(R)[1] if logdet is None else float(logdet)
+        Dm = self.D
+        Rd, iRT = D.asarray(R), D.asarray(np.ascontiguousarray(invR.T))
+
+        def rot_vec(a, Mx):         # a[..., i] <- sum_k Mx[i, k] a[..., k]
+            a = D.asarray(a)
+            flat = a.reshape((-1, Dm))
+            return D.sum_product([Mx, flat], [["i", "k"], ["n", "k"]], ["n", "i"]).reshape(a.shape)
+
+        def rot_mat(a, Mx):         # a[..., i, j] <- sum_kl Mx[i, k] a[..., k, l] Mx[j, l]
+            a = D.asarray(a)
+            flat = a.reshape((-1, Dm, Dm))
+            t = D.sum_product([Mx, flat], [["i", "k"], ["n", "k", "l"]], ["n", "i", "l"])
+            return D.sum_product([t, Mx], [["n", "i", "l"], ["j", "l"]], ["n", "i", "j"]).reshape(a.shape)
+
+        self.u = [rot_vec(self.u[0], Rd), rot_mat(self.u[1], Rd), rot_mat(self.u[2], Rd)]
+        self.phi = [rot_vec(self.phi[0], iRT), rot_mat(self.phi[1], iRT), rot_mat(self.phi[2], iRT)]
+        self.g = D.affine(D.asarray(self.g), 1.0, -self.N * logdetR)
+        self._version += 1
+
 
 class _MarkovChainToGaussian(Deterministic):
     """The chain seen as N Gaussian vectors plated over time (gaussian_markov_chain.py:1988-2098): the

@@ -564,8 +564,77 @@ def gate_models(name="gate"):
     save(name, **out)
 
 
+def lssm_doc_rotated(name="lssm_doc_rotated"):
+    """doc/source/examples/lssm.rst in full: 10 plain iterations, then the rotation parameter expansion
+    (transformations.py:1112-1452 RotateGaussianMarkovChain with a plate-rotating RotateGaussianARD for the dynamics,
+    :376-1110) as callback until convergence.  Pins the cost functions and their gradients (R and Q) from a known
+    state as well."""
+    from bayespy.nodes import GaussianMarkovChain, Dot
+    from bayespy.inference.vmp import transformations
+    np.random.seed(1)
+    M, N, D = 30, 400, 10
+    alpha = Gamma(1e-5, 1e-5, plates=(D,), name="alpha")
+    A = GaussianARD(0, alpha, shape=(D,), plates=(D,), name="A")
+    X = GaussianMarkovChain(np.zeros(D), 1e-3 * np.identity(D), A, np.ones(D), n=N, name="X")
+    gamma = Gamma(1e-5, 1e-5, plates=(D,), name="gamma")
+    C = GaussianARD(0, gamma, shape=(D,), plates=(M, 1), name="C")
+    F = Dot(C, X, name="F")
+    C.initialize_from_random()
+    C_init = np.asarray(C.u[0]).copy()
+    tau = Gamma(1e-5, 1e-5, name="tau")
+    Y = GaussianARD(F, tau, name="Y")
+    Q = VB(X, C, gamma, A, alpha, tau, Y)
+    w = 0.3
+    a = np.array([[np.cos(w), -np.sin(w), 0, 0], [np.sin(w), np.cos(w), 0, 0], [0, 0, 1, 0], [0, 0, 0, 0]])
+    c = np.random.randn(M, 4)
+    x = np.empty((N, 4)); f = np.empty((M, N)); y = np.empty((M, N))
+    x[0] = 10 * np.random.randn(4)
+    f[:, 0] = np.dot(c, x[0])
+    y[:, 0] = f[:, 0] + 3 * np.random.randn(M)
+    for n in range(N - 1):
+        x[n + 1] = np.dot(a, x[n]) + [1, 1, 10, 10] * np.random.randn(4)
+        f[:, n + 1] = np.dot(c, x[n + 1])
+        y[:, n + 1] = f[:, n + 1] + 3 * np.random.randn(M)
+    mask = random.mask(M, N, p=0.2)
+    Y.observe(y, mask=mask)
+    Q.update(repeat=10, verbose=False)
+    rotC = transformations.RotateGaussianARD(C, gamma)
+    rotA = transformations.RotateGaussianARD(A, alpha)
+    rotX = transformations.RotateGaussianMarkovChain(X, rotA)
+    R = transformations.RotationOptimizer(rotX, rotC, D)
+    # cost functions and gradients from the state after 10 iterations, at a fixed test rotation
+    Rt = np.identity(D) + 0.1 * np.random.RandomState(3).randn(D, D)
+    inv, logdet = np.linalg.inv(Rt), np.linalg.slogdet(Rt)[1]
+    rotX.setup(); rotC.setup()
+    bX, dbX = rotX.bound(Rt, inv=inv, logdet=logdet)
+    bXonly, dbXonly = rotX._compute_bound(Rt, logdet=logdet, inv=inv, gradient=True)
+    bA, dRA, dQA = rotA.bound(inv.T, inv=Rt.T, logdet=-logdet, Q=Rt)
+    bC, dbC = rotC.bound(inv.T, inv=Rt.T, logdet=-logdet)
+    out = dict(y=y, mask=np.asarray(mask), C_init=C_init, Rt=Rt, bX=np.asarray(bX), dbX=dbX, bXonly=np.asarray(bXonly),
+               dbXonly=dbXonly, bA=np.asarray(bA), dRA=dRA, dQA=dQA, bC=np.asarray(bC), dbC=dbC, L10=Q.L[:10].copy())
+    # one explicit rotation by Rt: the rotated state
+    rotX.rotate(Rt, inv=inv, logdet=logdet)
+    rotC.rotate(inv.T, inv=Rt.T, logdet=-logdet)
+    for nm, node in (("X", X), ("A", A), ("alpha", alpha), ("C", C), ("gamma", gamma)):
+        tmp = {}
+        node_state(nm, node, tmp)
+        for k, v in tmp.items():
+            if nm == "X" and np.ndim(v) >= 2 and np.shape(v)[0] >= N - 1:
+                v = v[::37]                     # a sample of the time steps keeps the fixture small
+            out["rot1_" + k] = np.array(v, copy=True)      # the reference updates node.u in place later on
+    out["rot1_bound"] = Q.compute_lowerbound()
+    Q.callback = R.rotate
+    Q.update(repeat=1000, verbose=False)
+    out["L"] = Q.L[:Q.iter].copy()
+    out["iters"] = Q.iter
+    for nm, node in (("A", A), ("alpha", alpha), ("C", C), ("gamma", gamma), ("tau", tau)):
+        node_state(nm, node, out)
+    out["X_u0_sel"] = np.asarray(X.u[0])[::37]
+    save(name, **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["quickstart", "pca", "linalg", "summul", "dist", "gmm", "gmc", "rot", "dot", "mixard", "gmcplates", "gmcvarying", "pcabench", "pcamasked64", "take", "gate"]
+    which = sys.argv[1:] or ["quickstart", "pca", "linalg", "summul", "dist", "gmm", "gmc", "rot", "dot", "mixard", "gmcplates", "gmcvarying", "pcabench", "pcamasked64", "take", "gate", "lssmrot"]
     if "quickstart" in which:
         quickstart()
     if "pca" in which:
@@ -591,6 +660,8 @@ if __name__ == "__main__":
         lssm_plated()
     if "gate" in which:
         gate_models()
+    if "lssmrot" in which:
+        lssm_doc_rotated()
     if "take" in which:
         take_models()
     if "pcamasked64" in which:
