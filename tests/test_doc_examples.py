@@ -85,3 +85,50 @@ def test_pca_doc_example_with_rotations(backend, capsys):
     # earlier or later: per-node tier 650.0916 at iteration 31 (the doc's digits), fused-sweep tier 649.9677 at 24.
     np.testing.assert_allclose(L[-1], 650.09, rtol=5e-4)
     assert "Converged at iteration" in out
+
+
+def test_user_guide_inference_example(backend, capsys):
+    """doc/source/user_guide/inference.rst:5-28,40-46,60-63,96,154,185-233: the PCA model with four rows of the data
+    missing, a random initialisation of X, then Q.update() / Q.update(C, X) / Q.update(C, X, C, tau) /
+    Q.update(repeat=10) / Q.update(repeat=1000) / Q.update(repeat=10000, tol=1e-6) — every bound the guide prints
+    ('Iteration 1: loglike=-9.305259e+02' ... 'Iteration 13: loglike=-1.405139e+02') and both convergence points
+    ('Converged at iteration 488.', '... 847.')."""
+    from bayespy_b200.nodes import GaussianARD, Gamma, Dot
+    from bayespy_b200.inference import VB
+    np.random.seed(1)
+    D = 3
+    X = GaussianARD(0, 1, shape=(D,), plates=(1, 100), name="X")
+    alpha = Gamma(1e-3, 1e-3, plates=(D,), name="alpha")
+    C = GaussianARD(0, alpha, shape=(D,), plates=(10, 1), name="C")
+    F = Dot(C, X)
+    tau = Gamma(1e-3, 1e-3, name="tau")
+    Y = GaussianARD(F, tau)
+    c = np.random.randn(10, 2)
+    x = np.random.randn(2, 100)
+    data = np.dot(c, x) + 0.1 * np.random.randn(10, 100)
+    Y.observe(data)
+    Y.observe(data, mask=[[True], [False], [False], [True], [True], [False], [True], [True], [True], [False]])
+    Q = VB(Y, C, X, alpha, tau)
+    assert Q["X"] is X
+    X.initialize_from_parameters(np.random.randn(1, 100, D), 10)
+    Q.update()
+    Q.update(C, X)
+    Q.update(C, X, C, tau)
+    Q.update(repeat=10)
+    out = capsys.readouterr().out
+    printed = ["-9.305259e+02", "-8.818976e+02", "-8.071222e+02", "-7.167588e+02", "-6.827873e+02", "-6.259477e+02",
+               "-4.725400e+02", "-3.270816e+02", "-2.208865e+02", "-1.658761e+02", "-1.469468e+02", "-1.420311e+02",
+               "-1.405139e+02"]
+    for i, v in enumerate(printed):
+        assert "Iteration %d: loglike=%s" % (i + 1, v) in out
+    Q.update(repeat=1000)
+    out = capsys.readouterr().out
+    assert "Iteration 14: loglike=-1.396481e+02" in out
+    assert Q.converged and abs(Q.iter - 488) <= 2
+    assert "Converged at iteration %d." % Q.iter in out
+    np.testing.assert_allclose(Q.L[Q.iter - 1], -1.224106e+02, rtol=2e-6)
+    Q.update(repeat=10000, tol=1e-6)
+    out = capsys.readouterr().out
+    assert Q.converged and abs(Q.iter - 847) <= 5
+    assert "Converged at iteration %d." % Q.iter in out
+    np.testing.assert_allclose(Q.L[Q.iter - 1], -1.222506e+02, rtol=2e-6)

@@ -172,3 +172,49 @@ def test_lssm_doc_example_in_full_with_rotations(backend, capsys):
     np.testing.assert_allclose(Q.L[Q.iter - 1], g["L"][ref_iters - 1], rtol=5e-4)
     assert ("%.2e" % Q.L[Q.iter - 1]) == "-8.91e+03"            # lssm.rst prints -8.906...e+03
     np.testing.assert_allclose(np.asarray(n["tau"].u[0]), g["tau_u0"], rtol=5e-3)
+
+
+@pytest.mark.parametrize("Dm,N,M", [(3, 20, 6), (5, 12, 4)])
+def test_markov_chain_rotation_cost_equals_the_true_bound_change(backend, Dm, N, M):
+    """The reference's own consistency check (vmp/tests/test_transformations.py:728-806): for a random R, the change
+    of every rotated node's lower-bound term after ``rotate(R)`` equals the change the cost function predicted, and
+    the terms add up to ``bound(R)[0]``.  Holds for the dynamics node too: its approximate plate rotation is what
+    ``rotate_plates`` applies, and the cost function prices exactly that."""
+    from bayespy_b200.nodes import GaussianARD, GaussianMarkovChain, Gamma, Dot
+    from bayespy_b200.inference import VB
+    from bayespy_b200.inference.vmp.transformations import RotateGaussianARD, RotateGaussianMarkovChain
+    rs = np.random.RandomState(42 + Dm)
+    alpha = Gamma(1e-3, 1e-3, plates=(Dm,), name="alpha")
+    A = GaussianARD(0, alpha, shape=(Dm,), plates=(Dm,), name="A")
+    X = GaussianMarkovChain(0.3 * rs.randn(Dm), np.identity(Dm) + 0.1 * np.ones((Dm, Dm)), A, np.ones(Dm), n=N, name="X")
+    C = GaussianARD(0, 1, shape=(Dm,), plates=(M, 1), name="C")
+    F = Dot(C, X)
+    Y = GaussianARD(F, 2.0, name="Y")
+    C.initialize_from_value(rs.randn(M, 1, Dm))
+    Y.observe(rs.randn(M, N))
+    Q = VB(X, C, A, alpha, Y)
+    Q.update(repeat=3, verbose=False, tol=0)
+    for with_alpha in (True, False):
+        rotA = RotateGaussianARD(A, alpha) if with_alpha else RotateGaussianARD(A)
+        rotX = RotateGaussianMarkovChain(X, rotA)
+        nodes = [X, A] + ([alpha] if with_alpha else [])
+        true0 = {n: float(np.asarray(n.lower_bound_contribution())) for n in nodes}
+        rotX.setup()
+        I = np.identity(Dm)
+        R = I + 0.3 * rs.randn(Dm, Dm)
+        t0, t1 = rotX.get_bound_terms(I), rotX.get_bound_terms(R)
+        np.testing.assert_allclose(sum(t0.values()), rotX.bound(I)[0], rtol=1e-10)
+        np.testing.assert_allclose(sum(t1.values()), rotX.bound(R)[0], rtol=1e-10)
+        # analytic gradient of the whole block against central differences
+        b, db = rotX.bound(R)
+        for _ in range(4):
+            i, j = rs.randint(0, Dm, size=2)
+            E = np.zeros((Dm, Dm))
+            E[i, j] = 1e-6
+            num = (rotX.bound(R + E)[0] - rotX.bound(R - E)[0]) / 2e-6
+            np.testing.assert_allclose(db[i, j], num, rtol=2e-5, atol=1e-6)
+        rotX.rotate(R)
+        for n in nodes:
+            true1 = float(np.asarray(n.lower_bound_contribution()))
+            np.testing.assert_allclose(true1 - true0[n], t1[n] - t0[n], rtol=1e-7, atol=1e-7 * abs(true0[n]),
+                                       err_msg="rotation cost of %s (alpha rotated: %s)" % (n.name, with_alpha))

@@ -391,6 +391,13 @@ def run_lssm(args):
     y = lssm_data(T, M)                               # every rank runs the same replica (the path does not shard over T)
     Q, Y = build_lssm(y, Dm, (GaussianARD, GaussianMarkovChain, Gamma, Dot, VB))
     steps, warmup = args.steps, max(args.warmup, 3)
+    # The clock sampler (an nvidia-smi process) starts BEFORE the warm-up: its start-up holds driver locks for some
+    # hundred milliseconds, and an allocation that reaches the driver meanwhile (this path allocates from the
+    # stream-ordered pool all the time) was seen to take 850 ms inside the first timed iteration (session 13).
+    sampler = bench.ClockSampler(int(os.environ.get("LOCAL_RANK", "0")), args.clock_interval_ms)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.5)
     # Warm-up until the iteration time has settled: the per-node path allocates ~100 plate-sized arrays (0.8 GB each)
     # per iteration from the stream-ordered pool, and while the pool is still growing an allocation reaches the driver
     # (hundreds of ms each).  At least `warmup` iterations, at most 15; stop when an iteration is within 25 % of the best.
@@ -404,10 +411,6 @@ def run_lssm(args):
             break
     warmup = len(warm_ms)
     parallel.barrier()
-    sampler = bench.ClockSampler(int(os.environ.get("LOCAL_RANK", "0")), args.clock_interval_ms)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
     t_all = be.timer_create()
     l0 = be.launch_count()
     wall0 = time.perf_counter()
