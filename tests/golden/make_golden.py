@@ -429,6 +429,40 @@ def lssm_varying(name="lssm_varying", M=5, N=12, D=2, iters=4):
     save(name, **out)
 
 
+def lssm_mixing(name="lssm_mixing", M=5, N=14, D=2, K=3, iters=5):
+    """VaryingGaussianMarkovChain (gaussian_markov_chain.py:930-1452): A_n = sum_k s_nk B_k with B a GaussianARD of
+    shape (D, K), plates (D,) and the weights S plated over time; observed through Dot."""
+    from bayespy.nodes import VaryingGaussianMarkovChain, Dot
+    rs = np.random.RandomState(33)
+    y = rs.randn(M, N).cumsum(axis=-1) * 0.3 + rs.randn(M, N)
+    beta = Gamma(1e-3, 1e-3, plates=(K,), name="beta")
+    B = GaussianARD(0, beta, shape=(D, K), plates=(D,), name="B")
+    B_init = 0.5 * rs.randn(D, D, K)
+    B.initialize_from_value(B_init)
+    S = GaussianARD(0, 1, shape=(K,), plates=(N - 1,), name="S")
+    S_init = rs.randn(N - 1, K)
+    S.initialize_from_value(S_init)
+    nu = np.array([1.0, 2.5])[:D]            # the reference has no message to the innovation precision of this node
+    X = VaryingGaussianMarkovChain(np.zeros(D), 1e-3 * np.identity(D), B, S, nu, name="X")
+    assert X.plates == () and X.dims[0] == (N, D)
+    gamma = Gamma(1e-5, 1e-5, plates=(D,), name="gamma")
+    C = GaussianARD(0, gamma, shape=(D,), plates=(M, 1), name="C")
+    F = Dot(C, X, name="F")
+    C_init = rs.randn(M, 1, D)
+    C.initialize_from_value(C_init)
+    tau = Gamma(1e-5, 1e-5, name="tau")
+    Y = GaussianARD(F, tau, name="Y")
+    Y.observe(y)
+    Q = VB(X, C, gamma, B, beta, S, tau, Y)
+    Q.update(repeat=iters, verbose=False, tol=0)
+    out = dict(y=y, C_init=C_init, B_init=B_init, S_init=S_init, nu=nu, L=Q.L[:iters])
+    for nm, node in (("X", X), ("C", C), ("B", B), ("beta", beta), ("S", S), ("tau", tau)):
+        node_state(nm, node, out)
+    for node in Q.model:
+        out["l_" + node.name] = Q.l[node][:iters]
+    save(name, **out)
+
+
 def lssm_plated_dynamics(name="lssm_plated_dynamics", M=4, N=15, D=2, P=3, iters=4):
     """P independent chains, each with ITS OWN time-invariant dynamics: A with plates (P, 1, D)."""
     from bayespy.nodes import GaussianMarkovChain, Dot
@@ -634,7 +668,7 @@ def lssm_doc_rotated(name="lssm_doc_rotated"):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["quickstart", "pca", "linalg", "summul", "dist", "gmm", "gmc", "rot", "dot", "mixard", "gmcplates", "gmcvarying", "pcabench", "pcamasked64", "take", "gate", "lssmrot"]
+    which = sys.argv[1:] or ["quickstart", "pca", "linalg", "summul", "dist", "gmm", "gmc", "rot", "dot", "mixard", "gmcplates", "gmcvarying", "pcabench", "pcamasked64", "take", "gate", "lssmrot", "gmcmixing"]
     if "quickstart" in which:
         quickstart()
     if "pca" in which:
@@ -662,6 +696,8 @@ if __name__ == "__main__":
         gate_models()
     if "lssmrot" in which:
         lssm_doc_rotated()
+    if "gmcmixing" in which:
+        lssm_mixing()
     if "take" in which:
         take_models()
     if "pcamasked64" in which:
