@@ -441,6 +441,109 @@ class GaussianMarkovChain(ExponentialFamily):
         self._version += 1
 
 
+class _AddTrailingPlate(Deterministic):
+    """The parent seen with one more (unit) plate axis after its own plates: moments and messages are the parent's,
+    reshaped.  Lets a time-plated node broadcast against a node whose last plate is the state dimension."""
+
+    def __init__(self, node, name=""):
+        self.moment_kind = node.moment_kind
+        super().__init__(node, dims=node.dims, plates=tuple(node.plates) + (1,), name=name)
+
+    def _plates_from_parent(self, index):
+        return tuple(self.parents[0].plates) + (1,)
+
+    def _plates_to_parent(self, index):
+        return tuple(self.plates[:-1])
+
+    def _weights_to_parent(self, index, mask):
+        mask = np.asarray(mask)
+        return np.any(mask, axis=-1) if mask.ndim >= 1 else mask
+
+    def _compute_moments(self, u):
+        out = []
+        for ui, dims in zip(u, self.dims):
+            ui = D.asarray(dense(ui))
+            nd = len(dims)
+            out.append(ui.reshape(tuple(ui.shape[:ui.ndim - nd]) + (1,) + tuple(ui.shape[ui.ndim - nd:])))
+        return out
+
+    def message_to_parent(self, index):
+        # the children have summed their messages to this node's plates (..., 1): drop the unit axis
+        m = self.message_from_children()
+        out = []
+        for mi, dims in zip(m, self.dims):
+            if mi is None:
+                out.append(None)
+                continue
+            mi = D.asarray(mi)
+            nd = len(dims)
+            if mi.ndim - nd >= 1:
+                mi = mi.reshape(tuple(mi.shape[:mi.ndim - nd - 1]) + tuple(mi.shape[mi.ndim - nd:]))
+            out.append(mi)
+        return out
+
+
+class VaryingGaussianMarkovChain(GaussianMarkovChain):
+    """``VaryingGaussianMarkovChain(mu, Lambda, B, S, nu, n=None, name="")`` (gaussian_markov_chain.py:1200-1452): a
+    chain whose transition matrix mixes K matrices with time-varying weights, A_n = sum_k s_nk B_k, with B of shape
+    (D, K) and plates (..., D) and the weights S of shape (K,) and plates (..., N-1).
+
+    The reference has a dedicated distribution for it and notes that the same model is a ``GaussianMarkovChain`` over
+    ``SumMultiply`` (``:1296-1301``); that is how it is built here: the per-step dynamics moments <A_n>, <a_nd a_nd^T>
+    are one device contraction each, and the messages to B and S are the chain's messages to its dynamics carried
+    through the product node."""
+
+    def __init__(self, mu, Lambda, B, S, nu, n=None, plates=None, name="", initialize=True):
+        from .dot import SumMultiply
+        from .gaussian import ensure_gaussian as _eg
+        B = _eg(B, 2)
+        S = _eg(S, 1)
+        if len(B.dims[0]) != 2:
+            raise ValueError("Third parent has wrong dimensionality {0}.".format(B.dims[0]))
+        Dm, K = B.dims[0]
+        if len(B.plates) == 0 or B.plates[-1] != Dm:
+            raise ValueError("Third parent should have a last plate equal to the dimensionality of the system.")
+        if tuple(S.dims[0]) != (K,):
+            raise ValueError("Fourth parent has wrong dimensionality %s, should be %s" % (S.dims, ((K,), (K, K))))
+        nS = S.plates[-1] if len(S.plates) >= 1 else 1
+        if n is not None and nS != 1 and nS != int(n) - 1:
+            raise ValueError("The last plate of the fourth parent should have length equal to one or N-1, where N is "
+                             "the number of time instances.")
+        self._mixing = (B, S)
+        weights = _AddTrailingPlate(S) if len(S.plates) >= 1 else S
+        A = SumMultiply("jk,k->j", B, weights)
+        super().__init__(mu, Lambda, A, nu, n=n, plates=plates, name=name, initialize=initialize)
+
+
+class SwitchingGaussianMarkovChain(GaussianMarkovChain):
+    """``SwitchingGaussianMarkovChain(mu, Lambda, B, Z, nu, n=None, name="")`` (gaussian_markov_chain.py:1743-1985): at
+    every step one of K transition matrices is selected, A_n = B_{z_n}; B has plates (..., K, D) and D-dimensional rows,
+    Z is categorical with plates (..., N-1).  As the reference notes (``:1846-1851``) this is a ``GaussianMarkovChain``
+    over ``Gate``, which is how it is built here."""
+
+    def __init__(self, mu, Lambda, B, Z, nu, n=None, plates=None, name="", initialize=True):
+        from .gate import Gate
+        from .categorical import categorical_constant
+        B = ensure_gaussian(B, 1)
+        if len(B.plates) < 2:
+            raise ValueError("Third parent should have plates (..., K, D)")
+        K, Dm = int(B.plates[-2]), int(B.plates[-1])
+        if tuple(B.dims[0]) != (Dm,):
+            raise ValueError("Third parent should have a last plate equal to the dimensionality of the system.")
+        if not isinstance(Z, Node):
+            Z = categorical_constant(Z, K)
+        if Z.moment_kind != "categorical" or tuple(Z.dims) != ((K,),):
+            raise ValueError("Fourth parent has wrong dimensionality: %d categories expected" % K)
+        nZ = Z.plates[-1] if len(Z.plates) >= 1 else 1
+        if n is not None and nZ != 1 and nZ != int(n) - 1:
+            raise ValueError("The last plate of the fourth parent should have length equal to one or N-1, where N is "
+                             "the number of time instances.")
+        self._switching = (B, Z)
+        selector = _AddTrailingPlate(Z) if len(Z.plates) >= 1 else Z
+        A = Gate(selector, B, gated_plate=-2)
+        super().__init__(mu, Lambda, A, nu, n=n, plates=plates, name=name, initialize=initialize)
+
+
 class _MarkovChainToGaussian(Deterministic):
     """The chain seen as N Gaussian vectors plated over time (gaussian_markov_chain.py:1988-2098): the
     time axis of the parent's dims is the last plate here; the cross-time moment is not exposed."""

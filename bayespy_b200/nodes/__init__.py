@@ -9,6 +9,7 @@ from ..engine.wishart import Wishart                                          # 
 from ..engine.dirichlet import Dirichlet                                      # noqa: F401
 from ..engine.categorical import Categorical                                  # noqa: F401
 from ..engine.mixture import Mixture                                          # noqa: F401
-from ..engine.gmc import GaussianMarkovChain                                  # noqa: F401
+from ..engine.gmc import (GaussianMarkovChain, VaryingGaussianMarkovChain,   # noqa: F401
+                          SwitchingGaussianMarkovChain)
 from ..engine.take import Take                                                # noqa: F401
 from ..engine.gate import Gate                                                # noqa: F401

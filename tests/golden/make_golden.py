@@ -463,6 +463,41 @@ def lssm_mixing(name="lssm_mixing", M=5, N=14, D=2, K=3, iters=5):
     save(name, **out)
 
 
+def lssm_switching(name="lssm_switching", M=5, N=14, D=2, K=3, iters=5):
+    """SwitchingGaussianMarkovChain (gaussian_markov_chain.py:1454-1985): A_n = B_{z_n} with z_n categorical over K
+    transition matrices; B a GaussianARD of shape (D,), plates (K, D)."""
+    from bayespy.nodes import SwitchingGaussianMarkovChain, Dot
+    rs = np.random.RandomState(34)
+    y = rs.randn(M, N).cumsum(axis=-1) * 0.3 + rs.randn(M, N)
+    beta = Gamma(1e-3, 1e-3, plates=(K, 1, 1), name="beta")
+    B = GaussianARD(0, beta, shape=(D,), plates=(K, D), name="B")     # (..., K, D) plates, D-dimensional rows (:1878-1880)
+    B_init = 0.5 * rs.randn(K, D, D)
+    B.initialize_from_value(B_init)
+    pi = Dirichlet(np.ones(K), name="pi")
+    Z = Categorical(pi, plates=(N - 1,), name="Z")
+    Z_init = rs.randint(0, K, size=N - 1)
+    Z.initialize_from_value(Z_init)
+    nu = np.array([1.0, 2.5])[:D]
+    X = SwitchingGaussianMarkovChain(np.zeros(D), 1e-3 * np.identity(D), B, Z, nu, name="X")
+    assert X.plates == () and X.dims[0] == (N, D)
+    gamma = Gamma(1e-5, 1e-5, plates=(D,), name="gamma")
+    C = GaussianARD(0, gamma, shape=(D,), plates=(M, 1), name="C")
+    F = Dot(C, X, name="F")
+    C_init = rs.randn(M, 1, D)
+    C.initialize_from_value(C_init)
+    tau = Gamma(1e-5, 1e-5, name="tau")
+    Y = GaussianARD(F, tau, name="Y")
+    Y.observe(y)
+    Q = VB(X, C, gamma, B, beta, Z, pi, tau, Y)
+    Q.update(repeat=iters, verbose=False, tol=0)
+    out = dict(y=y, C_init=C_init, B_init=B_init, Z_init=Z_init, nu=nu, L=Q.L[:iters])
+    for nm, node in (("X", X), ("C", C), ("B", B), ("beta", beta), ("Z", Z), ("pi", pi), ("tau", tau)):
+        node_state(nm, node, out)
+    for node in Q.model:
+        out["l_" + node.name] = Q.l[node][:iters]
+    save(name, **out)
+
+
 def lssm_plated_dynamics(name="lssm_plated_dynamics", M=4, N=15, D=2, P=3, iters=4):
     """P independent chains, each with ITS OWN time-invariant dynamics: A with plates (P, 1, D)."""
     from bayespy.nodes import GaussianMarkovChain, Dot
@@ -698,6 +733,7 @@ if __name__ == "__main__":
         lssm_doc_rotated()
     if "gmcmixing" in which:
         lssm_mixing()
+        lssm_switching()
     if "take" in which:
         take_models()
     if "pcamasked64" in which:

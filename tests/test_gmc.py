@@ -267,3 +267,91 @@ def test_dynamics_plates_follow_the_reference_layout(oracle_backend):
     assert tuple(X3.plates) == (4,)
     with pytest.raises(ValueError):
         GaussianMarkovChain(np.zeros(Dm), np.identity(Dm), GaussianARD(0, 1, shape=(Dm,), plates=(Dm,)), np.ones(Dm))
+
+
+def test_varying_chain_mixing_matrices_matches_reference(backend):
+    """VaryingGaussianMarkovChain (gaussian_markov_chain.py:930-1452): A_n = sum_k s_nk B_k; the chain, the mixing
+    matrices B (shape (D, K), plates (D,)), their ARD prior, the weights S and the observation model against the
+    unmodified reference: bound trajectory, every bound term, every node's moments and natural parameters."""
+    from bayespy_b200.nodes import GaussianARD, VaryingGaussianMarkovChain, Gamma, Dot
+    from bayespy_b200.inference import VB
+    g = golden("lssm_mixing")
+    y = g["y"]
+    M, N = y.shape
+    Dm, K = g["B_init"].shape[1:]
+    beta = Gamma(1e-3, 1e-3, plates=(K,), name="beta")
+    B = GaussianARD(0, beta, shape=(Dm, K), plates=(Dm,), name="B")
+    B.initialize_from_value(g["B_init"])
+    S = GaussianARD(0, 1, shape=(K,), plates=(N - 1,), name="S")
+    S.initialize_from_value(g["S_init"])
+    X = VaryingGaussianMarkovChain(np.zeros(Dm), 1e-3 * np.identity(Dm), B, S, g["nu"], name="X")
+    assert tuple(X.plates) == () and tuple(X.dims[0]) == (N, Dm)
+    gamma = Gamma(1e-5, 1e-5, plates=(Dm,), name="gamma")
+    C = GaussianARD(0, gamma, shape=(Dm,), plates=(M, 1), name="C")
+    F = Dot(C, X, name="F")
+    C.initialize_from_value(g["C_init"])
+    tau = Gamma(1e-5, 1e-5, name="tau")
+    Y = GaussianARD(F, tau, name="Y")
+    Y.observe(y)
+    Q = VB(X, C, gamma, B, beta, S, tau, Y)
+    iters = len(g["L"])
+    Q.update(repeat=iters, verbose=False, tol=0)
+    np.testing.assert_allclose(Q.L[:iters], g["L"], rtol=1e-8)
+    for node in Q.model:
+        np.testing.assert_allclose(Q.l[node][:iters], g["l_" + node.name], rtol=1e-7, atol=1e-6, err_msg=node.name)
+    for nm, node in (("X", X), ("C", C), ("B", B), ("beta", beta), ("S", S), ("tau", tau)):
+        for i, u in enumerate(node.u):
+            ref = g["%s_u%d" % (nm, i)]
+            np.testing.assert_allclose(np.asarray(u).reshape(ref.shape), ref, rtol=1e-7, atol=1e-9 * np.max(np.abs(ref)),
+                                       err_msg="%s.u[%d]" % (nm, i))
+        for i, ph in enumerate(node.phi):
+            ref = g["%s_phi%d" % (nm, i)]
+            np.testing.assert_allclose(np.broadcast_to(np.asarray(ph), ref.shape), ref, rtol=1e-7,
+                                       atol=1e-9 * np.max(np.abs(ref)), err_msg="%s.phi[%d]" % (nm, i))
+    # wrong shapes are refused like in the reference
+    with pytest.raises(ValueError):
+        VaryingGaussianMarkovChain(np.zeros(Dm), np.identity(Dm), GaussianARD(0, 1, shape=(Dm, K), plates=(Dm + 1,)), S,
+                                   np.ones(Dm))
+    with pytest.raises(ValueError):
+        VaryingGaussianMarkovChain(np.zeros(Dm), np.identity(Dm), B, GaussianARD(0, 1, shape=(K + 1,), plates=(N - 1,)),
+                                   np.ones(Dm))
+
+
+def test_switching_chain_matches_reference(backend):
+    """SwitchingGaussianMarkovChain (gaussian_markov_chain.py:1454-1985): A_n = B_{z_n}, z_n ~ Categorical(pi); chain,
+    transition matrices, selector and its Dirichlet prior against the unmodified reference."""
+    from bayespy_b200.nodes import (GaussianARD, SwitchingGaussianMarkovChain, Gamma, Dot, Dirichlet, Categorical)
+    from bayespy_b200.inference import VB
+    g = golden("lssm_switching")
+    y = g["y"]
+    M, N = y.shape
+    K, Dm = g["B_init"].shape[:2]
+    beta = Gamma(1e-3, 1e-3, plates=(K, 1, 1), name="beta")
+    B = GaussianARD(0, beta, shape=(Dm,), plates=(K, Dm), name="B")
+    B.initialize_from_value(g["B_init"])
+    pi = Dirichlet(np.ones(K), name="pi")
+    Z = Categorical(pi, plates=(N - 1,), name="Z")
+    Z.initialize_from_value(g["Z_init"])
+    X = SwitchingGaussianMarkovChain(np.zeros(Dm), 1e-3 * np.identity(Dm), B, Z, g["nu"], name="X")
+    assert tuple(X.plates) == () and tuple(X.dims[0]) == (N, Dm)
+    gamma = Gamma(1e-5, 1e-5, plates=(Dm,), name="gamma")
+    C = GaussianARD(0, gamma, shape=(Dm,), plates=(M, 1), name="C")
+    F = Dot(C, X, name="F")
+    C.initialize_from_value(g["C_init"])
+    tau = Gamma(1e-5, 1e-5, name="tau")
+    Y = GaussianARD(F, tau, name="Y")
+    Y.observe(y)
+    Q = VB(X, C, gamma, B, beta, Z, pi, tau, Y)
+    iters = len(g["L"])
+    Q.update(repeat=iters, verbose=False, tol=0)
+    np.testing.assert_allclose(Q.L[:iters], g["L"], rtol=1e-8)
+    for node in Q.model:
+        np.testing.assert_allclose(Q.l[node][:iters], g["l_" + node.name], rtol=1e-7, atol=1e-6, err_msg=node.name)
+    for nm, node in (("X", X), ("C", C), ("B", B), ("beta", beta), ("Z", Z), ("pi", pi), ("tau", tau)):
+        for i, u in enumerate(node.u):
+            ref = g["%s_u%d" % (nm, i)]
+            np.testing.assert_allclose(np.asarray(u).reshape(ref.shape), ref, rtol=1e-7, atol=1e-9 * np.max(np.abs(ref)),
+                                       err_msg="%s.u[%d]" % (nm, i))
+    with pytest.raises(ValueError):
+        SwitchingGaussianMarkovChain(np.zeros(Dm), np.identity(Dm), B, Categorical(np.ones(K + 1) / (K + 1), plates=(N - 1,)),
+                                     np.ones(Dm))
