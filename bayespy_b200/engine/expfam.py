@@ -45,6 +45,11 @@ class Distribution:
     def compute_weights_to_parent(self, index, weights):
         return weights
 
+    def compute_gradient(self, g, u, phi):
+        """Euclidean gradient with respect to the natural parameters, given the Riemannian one (expfamily.py:64-70):
+        the Fisher information d<u>/dphi applied to ``g``."""
+        raise NotImplementedError("compute_gradient is not implemented for %s" % type(self).__name__)
+
     def plates_to_parent(self, index, plates):
         return plates
 
@@ -166,6 +171,40 @@ class ExponentialFamily(Node):
         u, g = self._distribution.compute_moments_and_cgf(self.phi)
         self._store(u, g, np.logical_not(self.observed))
 
+    # ---- parameters and gradients (expfamily.py:260-340): the natural parameters are the optimisation variables ------
+    def get_parameters(self):
+        from .gaussian import dense
+        return [D.asarray(dense(p)).contiguous().copy() for p in self.phi]
+
+    def set_parameters(self, x):
+        self._fused = None            # a fused sweep's shortcuts (shared covariance, virtual phi0 / g) no longer describe q
+        self.phi = self._canonical_phi([D.asarray(p) for p in x])
+        u, g = self._distribution.compute_moments_and_cgf(self.phi)
+        self._store(u, g, np.logical_not(self.observed))
+
+    def get_riemannian_gradient(self):
+        """Natural gradient of the bound: annealing * (<phi>_prior + sum of the children's messages) - phi."""
+        from .gaussian import dense
+        u_parents = self.moments_from_parents()
+        m_children = self.message_from_children()
+        phi_p = self._canonical_phi(self._distribution.compute_phi_from_parents(*u_parents))
+        out = []
+        for i, (p, m) in enumerate(zip(phi_p, m_children)):
+            t = D.add(p, m) if m is not None else p
+            t = D.axpby(self.annealing, t, -1.0, D.asarray(dense(self.phi[i])))
+            out.append(t.broadcast_to(self.get_shape(i)).contiguous())
+        return out
+
+    def get_gradient(self, rg):
+        """Gradient with respect to the natural parameters; takes the Riemannian gradient as input
+        (expfamily.py:283-297)."""
+        from .gaussian import dense
+        g = self._distribution.compute_gradient(rg, [D.asarray(dense(ui)) for ui in self.u],
+                                                [D.asarray(dense(p)) for p in self.phi])
+        if self.annealing != 1.0:
+            g = [D.mul(gi, 1.0 / self.annealing) for gi in g]
+        return g
+
     def observe(self, x, *args, mask=True):
         """Fix the moments on the observed plates and propagate the mask
         (expfamily.py:369-398)."""
@@ -204,8 +243,9 @@ class ExponentialFamily(Node):
         return m, mask
 
     # ---- lower bound (expfamily.py:400-480) ----------------------------------------------------------
-    def lower_bound_contribution(self):
-        """E[log p(X|parents)] - E[log q(X)] summed over the active plates -> 0-d DArray."""
+    def lower_bound_contribution(self, ignore_masked=True):
+        """E[log p(X|parents)] - E[log q(X)] summed over the active plates -> 0-d DArray.  ``ignore_masked=False`` sums
+        over ALL plates, also those no observation depends on (expfamily.py:470-480)."""
         u_parents = self.moments_from_parents()
         phi_p = self._canonical_phi(self._distribution.compute_phi_from_parents(*u_parents))
         L = D.asarray(self._distribution.compute_cgf_from_parents(*u_parents))
@@ -239,7 +279,7 @@ class ExponentialFamily(Node):
             b_keys = keys_p[nplate - (ui.ndim - nd):] + keys_d
             Z = D.sum_product([diff, ui], [a_keys, b_keys], keys_p)
             L = D.add(L, Z)
-        mdev = self.mask_device()
+        mdev = self.mask_device() if ignore_masked else None
         return D.reduce_to_shape(L, (), mask=mdev, from_shape=self.plates)
 
     _guard_zero_times_inf = False

@@ -249,6 +249,35 @@ class _GaussianNode(ExponentialFamily):
 # --------------------------------------------------------------------------------------------
 # GaussianARD
 # --------------------------------------------------------------------------------------------
+
+def gaussian_fisher_apply(g, u, K):
+    """Euclidean gradient of a Gaussian's bound with respect to its natural parameters from the Riemannian gradient
+    ``g`` = [g0 (.., K), g1 (.., K, K)] (gaussian.py:489-555, :824-890): the Fisher information d<u>/dphi applied to g.
+    With m = <x>, S = Cov(x), M2 = <x x^T>:
+        d0 = S g0 + 2 S g1 m
+        d1 = (S g0) m^T + m (S g0)^T + 2 M2 g1 M2 - 2 (m^T g1 m) m m^T
+    Device contractions over the flattened plates; K is the flattened variable size."""
+    x = D.asarray(u[0])
+    lead = tuple(x.shape[:x.ndim - 1]) if K > 1 or x.ndim >= 1 else ()
+    xf = x.reshape((-1, K))
+    n = xf.shape[0]
+    xx = D.asarray(dense(u[1])).reshape((-1, K, K)).broadcast_to((n, K, K))
+    g0 = D.asarray(g[0]).reshape((-1, K)).broadcast_to((n, K))
+    g1 = D.asarray(g[1]).reshape((-1, K, K)).broadcast_to((n, K, K))
+    xxT = D.mul(xf.reshape((n, K, 1)), xf.reshape((n, 1, K)))
+    cov = D.sub(xx, xxT)
+    cg0 = D.sum_product([cov, g0], [["n", "i", "j"], ["n", "j"]], ["n", "i"])
+    g1x = D.sum_product([g1, xf], [["n", "i", "j"], ["n", "j"]], ["n", "i"])
+    d0 = D.axpby(1.0, cg0, 2.0, D.sum_product([cov, g1x], [["n", "i", "j"], ["n", "j"]], ["n", "i"]))
+    cg0x = D.mul(cg0.reshape((n, K, 1)), xf.reshape((n, 1, K)))
+    xcg0 = D.mul(xf.reshape((n, K, 1)), cg0.reshape((n, 1, K)))
+    t = D.sum_product([xx, g1], [["n", "i", "k"], ["n", "k", "l"]], ["n", "i", "l"])
+    mid = D.sum_product([t, xx], [["n", "i", "l"], ["n", "l", "j"]], ["n", "i", "j"])
+    q = D.sum_product([g1x, xf], [["n", "i"], ["n", "i"]], ["n"])
+    d1 = D.add(D.add(cg0x, xcg0), D.axpby(2.0, mid, -2.0, D.mul(xxT, q.reshape((n, 1, 1)))))
+    return d0, d1
+
+
 class GaussianARDDistribution(Distribution):
     """x ~ N(mu, diag(alpha)^-1) over a variable block of shape ``shape``
     (gaussian.py:576-889).  Parents: mu (scalar-Gaussian moments plated over
@@ -258,6 +287,11 @@ class GaussianARDDistribution(Distribution):
         self.shape = tuple(shape)
         self.ndim = len(self.shape)
         self.K = _flat_count(self.shape)
+
+    def compute_gradient(self, g, u, phi):
+        """gaussian.py:824-890."""
+        d0, d1 = gaussian_fisher_apply(g, u, self.K)
+        return [d0.reshape(D.asarray(g[0]).shape), d1.reshape(D.asarray(g[1]).shape)]
 
     # -- plates: the variable axes are plate axes of both parents (gaussian.py:744-769)
     def plates_to_parent(self, index, plates):
@@ -545,6 +579,11 @@ class GaussianDistribution(Distribution):
         self.D = int(D_)
         self.shape = (self.D,)
         self.ndim = 1
+
+    def compute_gradient(self, g, u, phi):
+        """gaussian.py:489-555."""
+        d0, d1 = gaussian_fisher_apply(g, u, self.D)
+        return [d0.reshape(D.asarray(g[0]).shape), d1.reshape(D.asarray(g[1]).shape)]
 
     def compute_phi_from_parents(self, u_mu, u_Lambda, mask=True):
         """[<Lambda><mu>, -1/2 <Lambda>]  (gaussian.py:377-394 with :2438-2457)."""

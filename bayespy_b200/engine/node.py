@@ -206,7 +206,7 @@ class Node:
     def moments_from_parents(self, exclude=None):
         return [p.get_moments() if i != exclude else None for i, p in enumerate(self.parents)]
 
-    def lower_bound_contribution(self):
+    def lower_bound_contribution(self, ignore_masked=True):
         return 0.0
 
 
@@ -266,5 +266,5 @@ class Deterministic(Node):
         mask = self._weights_to_parent(index, self.mask)
         return m, mask
 
-    def lower_bound_contribution(self):
+    def lower_bound_contribution(self, ignore_masked=True):
         return 0.0

@@ -109,7 +109,10 @@ class FactorModelPlan:
                 return plan.update_Y_lazy()
             return o["Y.update"](annealing) if annealing != 1.0 else o["Y.update"]()
 
-        def col_lb(node):
+        def col_lb(node, ignore_masked=True):
+            if not ignore_masked:
+                plan._materialize_Y()
+                return o["col.lb"](ignore_masked=False)
             if plan.valid():
                 if plan.masked():
                     if plan._mstats_ready():
@@ -137,7 +140,10 @@ class FactorModelPlan:
             plan._materialize_Y()
             return o["Y.msg"](index)
 
-        def Y_lb(node):
+        def Y_lb(node, ignore_masked=True):
+            if not ignore_masked:
+                plan._materialize_Y()
+                return o["Y.lb"](ignore_masked=False)
             if plan.valid():
                 if not plan.masked():
                     return plan.bound_Y()
@@ -393,7 +399,7 @@ class FactorModelPlan:
         return D.add(D.add(D.add(t0, t1), D.affine(sumld, -0.5, 0.5 * N * K)), ncgf)
 
     def _col_is_fused(self):
-        return isinstance(self.col.u[1], FactoredSecondMoment) and \
+        return getattr(self.col, "_fused", None) is not None and isinstance(self.col.u[1], FactoredSecondMoment) and \
             all(n == 1 for n in self.col.u[1].cov.shape[:-2])
 
     # ---- small shared quantities ---------------------------------------------------------------------
@@ -966,7 +972,9 @@ class GaussianMixturePlan:
                 return plan.update_Z()
             return o["Z.update"](annealing) if annealing != 1.0 else o["Z.update"]()
 
-        def Z_lb(node):
+        def Z_lb(node, ignore_masked=True):
+            if not ignore_masked:
+                return o["Z.lb"](ignore_masked=False)
             return plan.bound_Z() if plan.valid() and getattr(plan.Z, "_fused", None) is not None else o["Z.lb"]()
 
         def Z_msg(node, index):
@@ -979,7 +987,9 @@ class GaussianMixturePlan:
                 return plan.message_to_mu() if index == 1 else plan.message_to_Lambda()
             return o["Y.msg"](index)
 
-        def Y_lb(node):
+        def Y_lb(node, ignore_masked=True):
+            if not ignore_masked:
+                return o["Y.lb"](ignore_masked=False)
             return plan.bound_Y() if plan.valid() else o["Y.lb"]()
 
         self.Z.update = types.MethodType(Z_update, self.Z)

@@ -183,9 +183,12 @@ class VB:
                 return
 
     # ---- lower bound (vmp.py:180-199) -----------------------------------------------------------
-    def _bound_terms(self):
+    def _bound_terms(self, ignore_masked=True):
         """One D2H of len(model) doubles: every node's term is produced on device."""
-        terms = [node.lower_bound_contribution() for node in self.model]
+        if ignore_masked:
+            terms = [node.lower_bound_contribution() for node in self.model]
+        else:
+            terms = [node.lower_bound_contribution(ignore_masked=False) for node in self.model]
         vec = DArray.empty((len(terms),))
         host_fill = {}
         for i, t in enumerate(terms):
@@ -199,7 +202,7 @@ class VB:
         return out
 
     def compute_lowerbound(self, ignore_masked=True):
-        return float(np.sum(self._bound_terms()))
+        return float(np.sum(self._bound_terms(ignore_masked)))
 
     def compute_lowerbound_terms(self, *nodes):
         vals = self._bound_terms()
@@ -313,6 +316,155 @@ class VB:
                 if verbose:
                     self.print("Auto-saved to %s" % self.autosave_filename)
         return self.converged
+
+    # ---- gradient-based learning (vmp.py:402-662): the nodes' natural parameters are the variables ----------------
+    def get_gradients(self, *nodes, euclidian=False):
+        """Riemannian gradients of the given nodes (and, on request, the Euclidean ones too)."""
+        rg = [self[node].get_riemannian_gradient() for node in nodes]
+        if euclidian:
+            g = [self[node].get_gradient(rg_x) for node, rg_x in zip(nodes, rg)]
+            return rg, g
+        return rg
+
+    def get_parameters(self, *nodes):
+        return [self[node].get_parameters() for node in nodes]
+
+    def set_parameters(self, x, *nodes):
+        for node, xi in zip(nodes, x):
+            self[node].set_parameters(xi)
+
+    def gradient_step(self, *nodes, scale=1.0):
+        """One step of natural-gradient ascent."""
+        p = self.add(self.get_parameters(*nodes), self.get_gradients(*nodes), scale=scale)
+        self.set_parameters(p, *nodes)
+
+    def dot(self, x1, x2):
+        """Inner product of two vectors in parameter format (one list of arrays per node)."""
+        v = 0.0
+        for y1, y2 in zip(x1, x2):
+            for z1, z2 in zip(y1, y2):
+                a, b = D.asarray(z1), D.asarray(z2)
+                keys = list(range(a.ndim))
+                v += float(D.sum_product([a, b.broadcast_to(a.shape)], [keys, keys], []).numpy())
+        return v
+
+    def add(self, x1, x2, scale=1):
+        return [[D.axpby(1.0, D.asarray(z1), float(scale), D.asarray(z2)) for z1, z2 in zip(y1, y2)]
+                for y1, y2 in zip(x1, x2)]
+
+    def optimize(self, *nodes, maxiter=10, verbose=True, method="fletcher-reeves", riemannian=True, collapsed=None,
+                 tol=None):
+        """Riemannian conjugate gradient over the natural parameters of ``nodes``; the ``collapsed`` nodes are
+        re-optimised in closed form after every trial step (vmp.py:470-605)."""
+        method = method.lower()
+        if method not in ("gradient", "fletcher-reeves"):
+            raise Exception("Unknown optimization method: %s" % (method))
+        collapsed = [] if collapsed is None else list(collapsed)
+        scale = 1.0
+        p = self.get_parameters(*nodes)
+        dd_prev = 0
+        s = None
+        for _ in range(maxiter):
+            t = time.time()
+            if riemannian and method == "gradient":
+                rg = self.get_gradients(*nodes, euclidian=False)
+                g1 = g2 = rg
+            else:
+                rg, g = self.get_gradients(*nodes, euclidian=True)
+                g1, g2 = (g, rg) if riemannian else (g, g)
+            if method == "gradient":
+                b = 0
+            else:
+                dd_curr = self.dot(g1, g2)
+                b = 0 if dd_prev == 0 else dd_curr / dd_prev
+                dd_prev = dd_curr
+            s = self.add(g2, s, scale=b) if b else g2
+            success = False
+            while not success:
+                p_new = self.add(p, s, scale=scale)
+                try:
+                    self.set_parameters(p_new, *nodes)
+                except Exception:
+                    if verbose:
+                        self.print("CG update was unsuccessful, using gradient and resetting CG")
+                    if s is g2:
+                        scale = scale / 2
+                    dd_prev = 0
+                    s = g2
+                    continue
+                collapsed_params = self.get_parameters(*collapsed)
+                try:
+                    for node in collapsed:
+                        self[node].update()
+                except Exception:
+                    self.set_parameters(collapsed_params, *collapsed)
+                    if verbose:
+                        self.print("Collapsed node update node failed, reset CG")
+                    if s is g2:
+                        scale = scale / 2
+                    dd_prev = 0
+                    s = g2
+                    continue
+                L = self.compute_lowerbound()
+                bound_decreased = (self.iter > 0 and L < self.L[self.iter - 1]
+                                   and not np.allclose(L, self.L[self.iter - 1], rtol=1e-8))
+                if np.isnan(L) or bound_decreased:
+                    self.set_parameters(collapsed_params, *collapsed)
+                    if s is g2:
+                        scale = scale / 2
+                        if verbose:
+                            self.print("Gradient ascent decreased lower bound from {0} to {1}, halfing step length"
+                                       .format(self.L[self.iter - 1], L))
+                    elif scale < 2 ** (-10):
+                        if verbose:
+                            self.print("CG decreased lower bound from {0} to {1}, reset CG."
+                                       .format(self.L[self.iter - 1], L))
+                        dd_prev = 0
+                        s = g2
+                    else:
+                        scale = scale / 2
+                        if verbose:
+                            self.print("CG decreased lower bound from {0} to {1}, halfing step length"
+                                       .format(self.L[self.iter - 1], L))
+                    continue
+                success = True
+            scale = scale * np.sqrt(2)
+            p = p_new
+            cputime = time.time() - t
+            if self._end_iteration_step("OPT", cputime, tol=tol, verbose=verbose):
+                break
+
+    def pattern_search(self, *nodes, collapsed=None, maxiter=3):
+        """Pattern search along the direction of one VB update of ``nodes`` (vmp.py:608-662)."""
+        import scipy.optimize
+        collapsed = [] if collapsed is None else list(collapsed)
+        t = time.time()
+        for x in nodes:
+            self[x].update()
+        for x in collapsed:
+            self[x].update()
+        p0 = self.get_parameters(*nodes)
+        for x in nodes:
+            self[x].update()
+        p1 = self.get_parameters(*nodes)
+        dp = self.add(p1, p0, scale=-1)
+
+        def cost(alpha):
+            p_new = self.add(p1, dp, scale=alpha)
+            try:
+                self.set_parameters(p_new, *nodes)
+            except Exception:
+                return np.inf
+            for x in collapsed:
+                self[x].update()
+            return -self.compute_lowerbound()
+
+        res = scipy.optimize.minimize_scalar(cost, bracket=[0, 3], options={"maxiter": maxiter})
+        self.set_parameters(self.add(p1, dp, scale=res.x), *nodes)
+        for x in collapsed:
+            self[x].update()
+        cputime = time.time() - t
+        self._end_iteration_step("PS", cputime)
 
     def set_annealing(self, annealing):
         """vmp.py:665-679."""

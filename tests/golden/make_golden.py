@@ -34,11 +34,12 @@ def save(name, **arrays):
 
 
 def node_state(prefix, node, out):
+    # copies: the reference updates node.u in place, a snapshot taken mid-script must not alias it
     for i, u in enumerate(node.u):
-        out["%s_u%d" % (prefix, i)] = np.asarray(u)
+        out["%s_u%d" % (prefix, i)] = np.array(u, copy=True)
     for i, p in enumerate(node.phi):
-        out["%s_phi%d" % (prefix, i)] = np.asarray(p)
-    out["%s_g" % prefix] = np.asarray(node.g)
+        out["%s_phi%d" % (prefix, i)] = np.array(p, copy=True)
+    out["%s_g" % prefix] = np.array(node.g, copy=True)
 
 
 def quickstart():
@@ -498,6 +499,48 @@ def lssm_switching(name="lssm_switching", M=5, N=14, D=2, K=3, iters=5):
     save(name, **out)
 
 
+def pca_gradients(name="pca_gradients", M=8, N=30, D=3):
+    """Gradient-based learning on the PCA model (vmp.py:402-662, expfamily.py:260-340, gaussian.py:824-890,
+    gamma.py:183-211): Riemannian and Euclidean gradients, a natural-gradient step, Riemannian conjugate gradient with
+    collapsed nodes, plain conjugate gradient, pattern search."""
+    rs = np.random.RandomState(11)
+    y = rs.randn(M, 2) @ rs.randn(2, N) + 0.1 * rs.randn(M, N)
+    X = GaussianARD(0, 1, shape=(D,), plates=(1, N), name="X")
+    alpha = Gamma(1e-3, 1e-3, plates=(D,), name="alpha")
+    C = GaussianARD(0, alpha, shape=(D,), plates=(M, 1), name="C")
+    F = SumMultiply("d,d->", X, C)
+    tau = Gamma(1e-3, 1e-3, name="tau")
+    Y = GaussianARD(F, tau, name="Y")
+    Y.observe(y)
+    C_init = rs.randn(M, 1, D)
+    C.initialize_from_value(C_init)
+    Q = VB(Y, X, C, alpha, tau)
+    Q.update(repeat=2, verbose=False, tol=0)
+    out = dict(y=y, C_init=C_init)
+    rg, g = Q.get_gradients(C, tau, X, euclidian=True)
+    for nm, r_, g_ in zip(("C", "tau", "X"), rg, g):
+        for i in range(2):
+            out["rg_%s_%d" % (nm, i)] = np.array(r_[i])
+            out["g_%s_%d" % (nm, i)] = np.array(g_[i])
+    out["dot"] = Q.dot(rg, g)
+    Q.gradient_step(C, tau, scale=0.4)
+    out["L_after_step"] = Q.compute_lowerbound()
+    node_state("step_C", C, out)
+    node_state("step_tau", tau, out)
+    Q.optimize(C, tau, maxiter=6, collapsed=[X, alpha], verbose=False, tol=0)
+    out["L_opt1"] = Q.L[:Q.iter].copy()
+    Q.optimize(C, X, maxiter=4, riemannian=False, verbose=False, tol=0)
+    out["L_opt2"] = Q.L[:Q.iter].copy()
+    Q.optimize(C, tau, maxiter=3, method="gradient", verbose=False, tol=0)
+    out["L_opt3"] = Q.L[:Q.iter].copy()
+    Q.pattern_search(C, tau, collapsed=[X, alpha])
+    Q.pattern_search(C, X)
+    out["L"] = Q.L[:Q.iter].copy()
+    for nm, node in (("X", X), ("C", C), ("alpha", alpha), ("tau", tau)):
+        node_state(nm, node, out)
+    save(name, **out)
+
+
 def lssm_plated_dynamics(name="lssm_plated_dynamics", M=4, N=15, D=2, P=3, iters=4):
     """P independent chains, each with ITS OWN time-invariant dynamics: A with plates (P, 1, D)."""
     from bayespy.nodes import GaussianMarkovChain, Dot
@@ -703,7 +746,7 @@ def lssm_doc_rotated(name="lssm_doc_rotated"):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["quickstart", "pca", "linalg", "summul", "dist", "gmm", "gmc", "rot", "dot", "mixard", "gmcplates", "gmcvarying", "pcabench", "pcamasked64", "take", "gate", "lssmrot", "gmcmixing"]
+    which = sys.argv[1:] or ["quickstart", "pca", "linalg", "summul", "dist", "gmm", "gmc", "rot", "dot", "mixard", "gmcplates", "gmcvarying", "pcabench", "pcamasked64", "take", "gate", "lssmrot", "gmcmixing", "gradients"]
     if "quickstart" in which:
         quickstart()
     if "pca" in which:
@@ -731,6 +774,8 @@ if __name__ == "__main__":
         gate_models()
     if "lssmrot" in which:
         lssm_doc_rotated()
+    if "gradients" in which:
+        pca_gradients()
     if "gmcmixing" in which:
         lssm_mixing()
         lssm_switching()
