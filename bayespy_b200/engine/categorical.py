@@ -86,7 +86,7 @@ class Categorical(ExponentialFamily):
     moment_kind = "categorical"
     _guard_zero_times_inf = True
 
-    def __init__(self, p, plates=None, name="", initialize=True):
+    def __init__(self, p, plates=None, name="", initialize=True, plates_multiplier=None):
         if isinstance(p, Node):
             if p.moment_kind != "dirichlet":
                 raise ValueError("Expected a Dirichlet-like node")
@@ -94,7 +94,7 @@ class Categorical(ExponentialFamily):
             p = dirichlet_constant(p)
         K = p.dims[0][0]
         super().__init__(p, dims=((K,),), distribution=CategoricalDistribution(K), plates=plates, name=name,
-                         initialize=initialize)
+                         initialize=initialize, plates_multiplier=plates_multiplier)
 
     def __str__(self):
         return "%s ~ Categorical(p)\n  p = \n%s\n" % (self.name, self.u[0].numpy())

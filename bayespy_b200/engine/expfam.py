@@ -60,11 +60,11 @@ class Distribution:
 class ExponentialFamily(Node):
     _distribution = None
 
-    def __init__(self, *parents, dims, distribution, plates=None, name="", initialize=True):
+    def __init__(self, *parents, dims, distribution, plates=None, name="", initialize=True, plates_multiplier=None):
         self._distribution = distribution
         self._id = Node._id_counter
         Node._id_counter += 1
-        super().__init__(*parents, dims=dims, plates=plates, name=name)
+        super().__init__(*parents, dims=dims, plates=plates, name=name, plates_multiplier=plates_multiplier)
         self._check_independent_parents()
         self.ndims = [len(d) for d in self.dims]
         self.observed = False            # False, True or a host bool array over plates
@@ -85,6 +85,9 @@ class ExponentialFamily(Node):
 
     def _plates_to_parent(self, index):
         return tuple(self._distribution.plates_to_parent(index, tuple(self.plates)))
+
+    def _map_parent_axes(self, index, values):
+        return tuple(self._distribution.plates_from_parent(index, tuple(values)))
 
     def _weights_to_parent(self, index, mask):
         return self._distribution.compute_weights_to_parent(index, mask)
@@ -280,7 +283,8 @@ class ExponentialFamily(Node):
             Z = D.sum_product([diff, ui], [a_keys, b_keys], keys_p)
             L = D.add(L, Z)
         mdev = self.mask_device() if ignore_masked else None
-        return D.reduce_to_shape(L, (), mask=mdev, from_shape=self.plates)
+        scale = float(np.prod(self.plates_multiplier)) if self.plates_multiplier else 1.0
+        return D.reduce_to_shape(L, (), mask=mdev, from_shape=self.plates, scale=scale)
 
     _guard_zero_times_inf = False
 

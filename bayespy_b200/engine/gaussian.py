@@ -421,7 +421,7 @@ class GaussianARD(_GaussianNode):
     """``GaussianARD(mu, alpha, ndim=None, shape=None, plates=None, name="")`` —
     same call signature and semantics as the reference node (gaussian.py:1559-1660)."""
 
-    def __init__(self, mu, alpha, ndim=None, shape=None, plates=None, name="", initialize=True):
+    def __init__(self, mu, alpha, ndim=None, shape=None, plates=None, name="", initialize=True, plates_multiplier=None):
         alpha = ensure_gamma(alpha)
         if isinstance(mu, Node):
             if mu.moment_kind != "gaussian":
@@ -451,7 +451,7 @@ class GaussianARD(_GaussianNode):
             mu = gaussian_constant(mu, 0)
         dist = GaussianARDDistribution(shape)
         super().__init__(mu, alpha, dims=(shape, shape + shape), distribution=dist, plates=plates,
-                         name=name, initialize=initialize)
+                         name=name, initialize=initialize, plates_multiplier=plates_multiplier)
 
     def rotate(self, R, inv=None, logdet=None, axis=-1, Q=None, subset=None):
         """Transform q(x) -> q(R x) along the variable axis (gaussian.py:1693-1745): natural parameters by
@@ -658,7 +658,7 @@ class GaussianDistribution(Distribution):
 class Gaussian(_GaussianNode):
     """``Gaussian(mu, Lambda, plates=None, name="")`` (gaussian.py:1346-1417)."""
 
-    def __init__(self, mu, Lambda, plates=None, name="", initialize=True):
+    def __init__(self, mu, Lambda, plates=None, name="", initialize=True, plates_multiplier=None):
         from .wishart import ensure_wishart
         Lambda = ensure_wishart(Lambda)
         Dm = Lambda.dims[0][-1]
@@ -672,4 +672,4 @@ class Gaussian(_GaussianNode):
                 raise ValueError("Mean and precision have inconsistent shapes: {0} and {1}".format(
                     mu.dims, Lambda.dims))
         super().__init__(mu, Lambda, dims=((Dm,), (Dm, Dm)), distribution=GaussianDistribution(Dm),
-                         plates=plates, name=name, initialize=initialize)
+                         plates=plates, name=name, initialize=initialize, plates_multiplier=plates_multiplier)

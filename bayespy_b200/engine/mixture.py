@@ -179,7 +179,8 @@ class MixtureDistribution(Distribution):
 class Mixture(ExponentialFamily):
     """``Mixture(z, NodeClass, *params, cluster_plate=-1, plates=None, name="")`` (mixture.py:359-488)."""
 
-    def __init__(self, z, node_class, *params, cluster_plate=-1, plates=None, name="", initialize=True):
+    def __init__(self, z, node_class, *params, cluster_plate=-1, plates=None, name="", initialize=True,
+                 plates_multiplier=None):
         if cluster_plate >= 0:
             raise ValueError("Cluster plate axis must be negative")
         # build (and discard) a template node of the mixed class to obtain its parents / distribution
@@ -206,7 +207,7 @@ class Mixture(ExponentialFamily):
         ndims_parents = [[len(d) for d in p.dims] for p in parents]
         dist = MixtureDistribution(raw, cluster_plate, K, ndims, ndims_parents)
         super().__init__(z, *parents, dims=tmpl.dims, distribution=dist, plates=plates, name=name,
-                         initialize=initialize)
+                         initialize=initialize, plates_multiplier=plates_multiplier)
 
     def get_moments(self):
         return [dense(ui) for ui in self.u]

@@ -49,13 +49,45 @@ def mask_is_full(mask):
     return mask is True or bool(np.all(mask))
 
 
+def combine_multipliers(*mults):
+    """Plate multipliers (tuples aligned with the trailing plates, 1 = not scaled) of a node and its parents combined
+    like plates are: right-aligned, a unit entry yields to the other (node.py:295-301 ``_total_plates``)."""
+    out = []
+    for m in mults:
+        if m is None:
+            continue
+        m = tuple(m)
+        n = max(len(out), len(m))
+        a = [1] * (n - len(out)) + list(out)
+        b = [1] * (n - len(m)) + list(m)
+        out = []
+        for x, y in zip(a, b):
+            if x != 1 and y != 1 and x != y:
+                raise ValueError("The plate multipliers are incompatible: %s and %s" % (tuple(a), tuple(b)))
+            out.append(y if x == 1 else x)
+    while out and out[0] == 1:
+        out.pop(0)
+    return tuple(out)
+
+
+def multiplier_to_parent(own, parent):
+    """Factor by which a message grows on its way to a parent: the product of this node's plate multipliers on the
+    axes where the parent (as seen from this node) has none (node.py:604-633)."""
+    own, parent = tuple(own), tuple(parent)
+    r = 1.0
+    for j in range(1, len(own) + 1):
+        if own[-j] != 1 and (j > len(parent) or parent[-j] == 1):
+            r *= own[-j]
+    return r
+
+
 class Node:
     """Base class: plates, parents/children, masks, message reduction."""
 
     moment_kind = None
     _id_counter = 0
 
-    def __init__(self, *parents, dims=None, plates=None, name="", notify_parents=True):
+    def __init__(self, *parents, dims=None, plates=None, name="", notify_parents=True, plates_multiplier=None):
         self.parents = list(parents)
         self.dims = tuple(tuple(d) for d in dims)
         self.name = name
@@ -70,6 +102,9 @@ class Node:
                     raise ValueError("The plates %s of the parents are not broadcastable to the given "
                                      "plates %s." % (p, plates))
             self.plates = plates
+        # stochastic VI: this node stands for `multiplier` times as many plates as it holds (node.py:257, :295-301)
+        self.plates_multiplier = combine_multipliers(
+            plates_multiplier, *[self._plates_multiplier_from_parent(i) for i in range(len(self.parents))])
         # which plates take part in inference at all (OR of the children's masks)
         self.mask = np.array(False)
         self._mask_dev = None
@@ -110,6 +145,25 @@ class Node:
     def _plates_to_parent(self, index):
         """This node's plates as seen from parent[index]."""
         return tuple(self.plates)
+
+    def _plates_multiplier_from_parent(self, index):
+        """Plate multiplier of parent[index] mapped to this node's plate axes (the same map as for the plates)."""
+        m = tuple(getattr(self.parents[index], "plates_multiplier", ()))
+        if not m or all(v == 1 for v in m):
+            return ()
+        pp = tuple(self.parents[index].plates)
+        full = (1,) * (len(pp) - len(m)) + m
+        # map the parent's plates once with the multiplier values in place of the extents
+        try:
+            mapped = self._map_parent_axes(index, full)
+        except Exception:
+            raise ValueError("The plate multiplier %s of parent %d cannot be mapped to the plates of this node" % (m, index))
+        return tuple(mapped)
+
+    def _map_parent_axes(self, index, values):
+        """Carry per-axis values of parent[index]'s plates over to this node's plate axes; the default is the identity
+        (sub-classes whose plates differ from their parents' override ``_plates_from_parent`` and this with it)."""
+        return tuple(values)
 
     def get_shape(self, i):
         return tuple(self.plates) + tuple(self.dims[i])
@@ -178,6 +232,8 @@ class Node:
         m, mask = self._message_and_mask_to_parent(index)
         parent = self.parents[index]
         plates_self = self._plates_to_parent(index)
+        scale = multiplier_to_parent(self.plates_multiplier, self._plates_multiplier_from_parent(index)) \
+            if self.plates_multiplier else 1.0
         mdev = self.mask_device() if mask is self.mask else self.mask_device(mask)
         out = []
         for i, mi in enumerate(m):
@@ -190,7 +246,7 @@ class Node:
             from_shape = tuple(plates_self) + dims
             to_shape = tuple(parent.plates) + dims
             mk = mdev.add_trailing(nd) if mdev is not None else None
-            out.append(D.reduce_to_shape(mi, to_shape, mask=mk, from_shape=from_shape))
+            out.append(D.reduce_to_shape(mi, to_shape, mask=mk, from_shape=from_shape, scale=scale))
         return out
 
     def message_from_children(self):

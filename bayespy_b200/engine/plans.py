@@ -204,6 +204,8 @@ class FactorModelPlan:
             return False
         if col.observed is not False or row.observed is not False:
             return False
+        if any(getattr(n, "plates_multiplier", ()) for n in (Y, self.F, col, row)):
+            return False                                   # mini-batch scaling: generic path
         return True
 
     # ---- missing values: per-column precision, fused (csrc/pca_masked.cu) -----------------------------------------
@@ -1001,7 +1003,8 @@ class GaussianMixturePlan:
     def valid(self):
         Y, Z = self.Y, self.Z
         ok = (Y.observed is True) and mask_is_full(Y.mask) and Z.observed is False \
-            and all(getattr(n, "annealing", 1.0) == 1.0 for n in (Y, Z, self.mu, self.Lam))
+            and all(getattr(n, "annealing", 1.0) == 1.0 for n in (Y, Z, self.mu, self.Lam)) \
+            and not any(getattr(n, "plates_multiplier", ()) for n in (Y, Z, self.mu, self.Lam))
         if not ok and self.world > 1:
             raise NotImplementedError("plate sharding is only supported on the fused path")
         return ok

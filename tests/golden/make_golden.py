@@ -541,6 +541,35 @@ def pca_gradients(name="pca_gradients", M=8, N=30, D=3):
     save(name, **out)
 
 
+def svi_mixture(name="svi_mixture", N=400, N_batch=40, K=4, D=2, steps=12):
+    """Stochastic variational inference (demos/stochastic_inference.py:93-141): a mini-batch Mixture whose Categorical
+    carries ``plates_multiplier=(N / N_batch,)``, local update of Z, then a natural-gradient step of the global nodes
+    with a decaying step length."""
+    rs = np.random.RandomState(8)
+    means = 4 * rs.randn(3, D)
+    data = means[rs.randint(0, 3, size=N)] + rs.randn(N, D)
+    mu = Gaussian(np.zeros(D), np.identity(D), plates=(K,), name="means")
+    alpha = Dirichlet(np.ones(K), name="class probabilities")
+    Z = Categorical(alpha, plates=(N_batch,), plates_multiplier=(N / N_batch,), name="classes")
+    Y = Mixture(Z, Gaussian, mu, np.identity(D), name="observations")
+    mu_init = rs.randn(K, D)
+    mu.initialize_from_value(mu_init)
+    Q = VB(Y, Z, mu, alpha)
+    Q.ignore_bound_checks = True
+    subsets = np.array([rs.choice(N, N_batch) for _ in range(steps)])
+    mus, alphas, Ls = [], [], []
+    for n in range(steps):
+        Y.observe(data[subsets[n], :])
+        Q.update(Z, verbose=False)
+        step = (n + 1) ** (-0.7)
+        Q.gradient_step(mu, alpha, scale=step)
+        mus.append(np.array(mu.u[0], copy=True))
+        alphas.append(np.array(alpha.u[0], copy=True))
+        Ls.append(Q.compute_lowerbound())
+    save(name, data=data, mu_init=mu_init, subsets=subsets, mus=np.array(mus), alphas=np.array(alphas), Ls=np.array(Ls),
+         L=Q.L[:Q.iter].copy())
+
+
 def lssm_plated_dynamics(name="lssm_plated_dynamics", M=4, N=15, D=2, P=3, iters=4):
     """P independent chains, each with ITS OWN time-invariant dynamics: A with plates (P, 1, D)."""
     from bayespy.nodes import GaussianMarkovChain, Dot
@@ -776,6 +805,7 @@ if __name__ == "__main__":
         lssm_doc_rotated()
     if "gradients" in which:
         pca_gradients()
+        svi_mixture()
     if "gmcmixing" in which:
         lssm_mixing()
         lssm_switching()

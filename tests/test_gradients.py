@@ -115,3 +115,36 @@ def test_gradient_is_the_derivative_of_the_bound_also_with_annealing(backend):
                             ana = ana + gr[i][..., c, r].reshape(-1)[j // (K * K)]
                     np.testing.assert_allclose(ana, num, rtol=2e-4, atol=1e-6,
                                                err_msg="%s phi[%d][%d], annealing %g" % (node.name, i, j, annealing))
+
+
+def test_stochastic_variational_inference_with_plate_multipliers(backend):
+    """demos/stochastic_inference.py:93-141 in small: the mini-batch model's Categorical stands for N / N_batch times its
+    plates (``plates_multiplier``); every step observes a seeded mini-batch, updates the local Z and takes a
+    natural-gradient step of the global nodes.  Means, class weights and bound after every step against the reference."""
+    from bayespy_b200.nodes import Gaussian, Dirichlet, Categorical, Mixture
+    from bayespy_b200.inference import VB
+    g = golden("svi_mixture")
+    data, subsets = g["data"], g["subsets"]
+    N, Dm = data.shape
+    N_batch, K = subsets.shape[1], g["mu_init"].shape[0]
+    mu = Gaussian(np.zeros(Dm), np.identity(Dm), plates=(K,), name="means")
+    alpha = Dirichlet(np.ones(K), name="class probabilities")
+    Z = Categorical(alpha, plates=(N_batch,), plates_multiplier=(N / N_batch,), name="classes")
+    Y = Mixture(Z, Gaussian, mu, np.identity(Dm), name="observations")
+    assert tuple(Y.plates_multiplier) == (N / N_batch,) and tuple(mu.plates_multiplier) == ()
+    mu.initialize_from_value(g["mu_init"])
+    Q = VB(Y, Z, mu, alpha)
+    Q.ignore_bound_checks = True
+    for n in range(len(subsets)):
+        Y.observe(data[subsets[n], :])
+        Q.update(Z, verbose=False)
+        Q.gradient_step(mu, alpha, scale=(n + 1) ** (-0.7))
+        np.testing.assert_allclose(np.asarray(mu.u[0]), g["mus"][n], rtol=1e-7, atol=1e-9, err_msg="means, step %d" % n)
+        np.testing.assert_allclose(np.asarray(alpha.u[0]), g["alphas"][n], rtol=1e-7, atol=1e-9,
+                                   err_msg="class weights, step %d" % n)
+        np.testing.assert_allclose(Q.compute_lowerbound(), g["Ls"][n], rtol=1e-8, err_msg="bound, step %d" % n)
+    np.testing.assert_allclose(Q.L[:Q.iter], g["L"], rtol=1e-8)
+    # incompatible multipliers are refused
+    with pytest.raises(ValueError):
+        Mixture(Categorical(alpha, plates=(N_batch,), plates_multiplier=(3.0,)), Gaussian,
+                Gaussian(np.zeros(Dm), np.identity(Dm), plates=(N_batch, K), plates_multiplier=(2.0, 1)), np.identity(Dm))
