@@ -818,19 +818,30 @@ class FactorModelPlan:
         terms_of = {self.Y: 0, self.col: 1, self.row: 2, alpha: 3, self.tau: 4}
         Yd = self._Yd()
         done, converged = 0, False
-        ctrl = DArray.zeros((2,))                 # 16 bytes = int[4]
+        t_enter = time.perf_counter()
+        host = dict(pre_us=0.0, call_us=0.0, wait_us=0.0, post_us=0.0, launches=0)
         while (repeat is None or done < repeat) and not converged:
             left = 50 if repeat is None else repeat - done
             chunk = 1 if (verbose or not fast) else min(left, 50)
-            Lh = DArray.empty((chunk, 6))
-            be.memset(ctrl.ptr, 0, 16)
+            # bound rows and the control words share one buffer: one read-back per chunk
+            buf = DArray.empty((chunk * 6 + 2,))
+            ctrl_ptr = buf.ptr + chunk * 48
+            be.memset(ctrl_ptr, 0, 16)            # int[4]: iterations done, stop, error bits
             if self.kernel_timers is not None:
                 ids = self.kernel_timers[self._timer_pos:self._timer_pos + chunk]
                 be.pca_vb_set_timers(ids)
             t0 = time.time()
+            tc0 = time.perf_counter()
             be.pca_vb_run(Yd.ptr, M, N, K, X.ptr, state.ptr, ops, chunk, has_alpha, has_tau, tol_dev,
-                          Lh.ptr, chunk, ctrl.ptr)
-            c = ctrl.numpy().view(np.int32)       # blocks until the chunk has run
+                          buf.ptr, chunk, ctrl_ptr)
+            tc1 = time.perf_counter()
+            hbuf = buf.numpy()                    # blocks until the chunk has run
+            tc2 = time.perf_counter()
+            c = hbuf[chunk * 6:].view(np.int32)
+            host["pre_us"] += 1e6 * (tc0 - t_enter)
+            host["call_us"] += 1e6 * (tc1 - tc0)
+            host["wait_us"] += 1e6 * (tc2 - tc1)
+            host["launches"] += 1
             if self.kernel_timers is not None:
                 used = be.pca_vb_timers_used()
                 # one timer may bracket several sweeps (the whole chunk is one launch when it can be)
@@ -842,13 +853,12 @@ class FactorModelPlan:
             if self.kernel_timers is not None and self.kernel_timer_log and self.kernel_timer_log[-1][1] is None:
                 self.kernel_timer_log[-1] = (self.kernel_timer_log[-1][0], n_it)
             self._raise_ctrl_errors(err)
-            vb._record_resident_iterations(Lh.numpy()[:n_it], terms_of, dt, stop, check, verbose)
+            vb._record_resident_iterations(hbuf[:chunk * 6].reshape(chunk, 6)[:n_it], terms_of, dt, stop, check, verbose)
             done += n_it
             self.fused_calls += n_it
             converged = bool(stop)
-            # later chunks compare against the last bound even if this one started without one
-            if check and n_it > 0 and not stop:
-                pass
+            t_enter = time.perf_counter()
+            host["post_us"] += 1e6 * (t_enter - tc2)
             if n_it == 0:
                 break
         if done > 0:
@@ -858,6 +868,8 @@ class FactorModelPlan:
                 self._resident_publish(state, lay, X, order)
             self._res_cache = dict(state=state, lay=lay, X=X, hsig=hsig, nodes=[id(n) for n in watched],
                                    versions=[n._version for n in watched])
+        host["post_us"] += 1e6 * (time.perf_counter() - t_enter)
+        self.host_timing = host                   # where the host spent its time around the launches (bench.py reports it)
         return converged
 
     def _resident_republish(self, X):

@@ -286,6 +286,7 @@ def run_gpu(args):
     wall = time.perf_counter() - wall0
     launches = be.launch_count() - l0
     ms_dev = be.timer_elapsed_ms(t_all)
+    host_timing = dict(getattr(plan, "host_timing", None) or {})      # host time around the launches of the timed region
     parallel.barrier()
     clocks = sampler.stop() if rank == 0 else None
     # the host drives the sweep synchronously (one bound read-back per sweep), so the slower of the
@@ -357,7 +358,9 @@ def run_gpu(args):
                                   "(data pass + grid reduction + node updates + bound per sweep, grid barriers in between); "
                                   "gpu_launches counts launches, roofline.sweeps_per_launch the sweeps inside each",
                    "lower_bound_last": L_last, "device_ms_per_step": ms_dev / steps,
-                   "host_wall_ms_per_step": 1e3 * wall / steps},
+                   "host_wall_ms_per_step": 1e3 * wall / steps,
+                   "host_us_around_launches": {k: (round(v, 1) if isinstance(v, float) else v)
+                                               for k, v in host_timing.items()}},
         "clocks": clocks,
         "e2e": {"value": 1.0 / e2e_s, "unit": "it/s", "h2d_bytes_per_step": int(nbytes),
                 "d2h_bytes_per_step": 8 * len(Q.model), "steps": e2e_steps, "statistic": "median over steps of the max over ranks",
