@@ -25,7 +25,7 @@ OK, ECUDA, EINVAL, ENOTSPD, EDOMAIN, ENCCL, ENOGPU = range(7)
 
 OPS = dict(COPY=0, ADD=1, SUB=2, MUL=3, DIV=4, AXPBY=5, AFFINE=6, FMA=7, WHERE=8,
            LOG=9, EXP=10, RECIP=11, SQUARE=12, SQRT=13, LGAMMA=14, DIGAMMA=15,
-           MVLGAMMA=16, MVDIGAMMA=17, NONZERO=18)
+           MVLGAMMA=16, MVDIGAMMA=17, NONZERO=18, TRIGAMMA=19)
 
 # name -> (restype, argtypes); the authoritative list of exported symbols
 # (tests/test_abi.py checks it against include/bpk.h and the built library)

@@ -42,6 +42,7 @@ __device__ __forceinline__ double ew_apply(int op, double a, double b, double c,
     case BPK_OP_MVLGAMMA: return bpk_mvlgamma(a, (int)alpha);
     case BPK_OP_MVDIGAMMA: return bpk_mvdigamma(a, (int)alpha);
     case BPK_OP_NONZERO: return a != 0.0 ? b : 0.0;
+    case BPK_OP_TRIGAMMA: return bpk_trigamma(a);
     }
     return nan("");
 }

@@ -380,6 +380,7 @@ def square(a): return _unary("SQUARE", a)
 def sqrt(a): return _unary("SQRT", a)
 def gammaln(a): return _unary("LGAMMA", a)
 def digamma(a): return _unary("DIGAMMA", a)
+def trigamma(a): return _unary("TRIGAMMA", a)
 def multigammaln(a, d): return _unary("MVLGAMMA", a, float(d))
 def multidigamma(a, d): return _unary("MVDIGAMMA", a, float(d))
 

@@ -27,14 +27,12 @@ class GammaDistribution(Distribution):
 
     def compute_gradient(self, g, u, phi):
         """gamma.py:183-211.  With b = -phi0, a = phi1: <u> = [a / b, psi(a) - log b], so the Fisher information is
-        [[a / b^2, 1 / b], [1 / b, psi'(a)]].  The trigamma function is evaluated on the host (scipy): gamma nodes are
-        plate-sized at most and this is not on the sweep path."""
-        import scipy.special as sp
+        [[a / b^2, 1 / b], [1 / b, psi'(a)]]."""
         b = D.mul(D.asarray(phi[0]), -1.0)
         a = D.asarray(phi[1])
         g0, g1 = D.asarray(g[0]), D.asarray(g[1])
         inv_b = D.div(1.0, b)
-        tri = D.asarray(sp.polygamma(1, a.numpy()))
+        tri = D.trigamma(a)
         d0 = D.add(D.mul(g0, D.mul(a, D.mul(inv_b, inv_b))), D.mul(g1, inv_b))
         d1 = D.add(D.mul(g1, tri), D.mul(g0, inv_b))
         return [d0, d1]

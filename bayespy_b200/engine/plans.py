@@ -823,8 +823,10 @@ class FactorModelPlan:
         while (repeat is None or done < repeat) and not converged:
             left = 50 if repeat is None else repeat - done
             chunk = 1 if (verbose or not fast) else min(left, 50)
-            # bound rows and the control words share one buffer: one read-back per chunk
-            buf = DArray.empty((chunk * 6 + 2,))
+            # bound rows and the control words share one buffer (kept across calls): one read-back per chunk
+            buf = getattr(self, "_ctl_buf", None)
+            if buf is None or buf.size != chunk * 6 + 2:
+                buf = self._ctl_buf = DArray.empty((chunk * 6 + 2,))
             ctrl_ptr = buf.ptr + chunk * 48
             be.memset(ctrl_ptr, 0, 16)            # int[4]: iterations done, stop, error bits
             if self.kernel_timers is not None:

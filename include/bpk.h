@@ -115,6 +115,7 @@ enum {
     BPK_OP_MVLGAMMA,    /* multigammaln(a, d=(int)alpha)        */
     BPK_OP_MVDIGAMMA,   /* sum_{i<d} psi(a - i/2), d=(int)alpha  misc.py:1146 */
     BPK_OP_NONZERO,     /* a != 0 ? b : 0   (expfamily.py:463 "0 * -inf") */
+    BPK_OP_TRIGAMMA,    /* psi'(a)        scipy.special.polygamma(1, a), gamma.py:210 */
     BPK_OP_COUNT_
 };
 int bpk_ewise(int op, int nd, const int64_t *shape,

@@ -165,6 +165,7 @@ class RefBackend:
                 np.vectorize(lambda v: sp.multigammaln(v, int(alpha)))(a)   # wishart.py:187
             elif op == 17: r = np.sum(sp.digamma(a[..., None] - 0.5 * np.arange(int(alpha))), axis=-1)  # misc.py:1146
             elif op == 18: r = np.where(a != 0, b, 0.0)            # expfamily.py:463
+            elif op == 19: r = sp.polygamma(1, a)                  # gamma.py:210
             else:
                 raise ValueError("bad op")
         o = _view(out, shape, out_stride)
