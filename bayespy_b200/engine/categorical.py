@@ -30,6 +30,25 @@ def categorical_constant(x, K):
     return Constant("categorical", [one_hot(x, K)], dims=((K,),), plates=x.shape, value=x)
 
 
+class CategoricalMoments:
+    """``CategoricalMoments(K)`` as the reference exposes it for ``Constant`` (categorical.py:20-90): integer class
+    labels become one-hot moments on the device (bit-exact)."""
+
+    def __init__(self, categories):
+        if not isinstance(categories, (int, np.integer)) or categories < 0:
+            raise ValueError("Number of categories must be a non-negative integer")
+        self.categories = int(categories)
+
+    def fixed_moments(self, x):
+        x = np.asarray(x)
+        if not issubclass(x.dtype.type, np.integer):
+            raise ValueError("Values must be integers")
+        if np.any(x < 0) or np.any(x >= self.categories):
+            raise ValueError("Invalid category index")
+        K = self.categories
+        return "categorical", [one_hot(x, K)], ((K,),), x.shape, x
+
+
 class CategoricalDistribution(Distribution):
 
     def __init__(self, categories):

@@ -66,7 +66,15 @@ class DirichletDistribution(Distribution):
         return [logp], f
 
     def random(self, *phi, plates=None):
-        return np.random.dirichlet(phi[0], size=plates)
+        # utils/random.py:329-347: normalised gamma draws (host RNG, so that seeded initialisations reproduce the
+        # reference draw for draw), also for plated concentration parameters
+        alpha = np.asarray(phi[0], dtype=np.float64)
+        size = tuple(plates) + alpha.shape[-1:] if plates is not None else alpha.shape
+        p = np.random.gamma(alpha, size=size)
+        total = np.sum(p, axis=-1, keepdims=True)
+        if np.any(total == 0):
+            raise RuntimeError("Numerically zero samples. Try using a larger Dirichlet concentration parameter value.")
+        return p / total
 
 
 class Dirichlet(ExponentialFamily):

@@ -270,11 +270,29 @@ class Node:
 class Constant(Node):
     """Fixed moments (nodes/constant.py).  ``u`` is a list of DArrays shaped plates+dims."""
 
-    def __init__(self, kind, u, dims, plates, name="const", value=None):
+    def __init__(self, kind, u=None, dims=None, plates=None, name="const", value=None):
+        if hasattr(kind, "fixed_moments"):
+            # the reference's public form ``Constant(moments, x, name=...)`` (nodes/constant.py:14-35)
+            moments, x = kind, u
+            self._moments_spec = moments
+            kind, u, dims, plates, value = moments.fixed_moments(x)
+        else:
+            self._moments_spec = None
         self.moment_kind = kind
         self.u = list(u)
         self.value = value
         super().__init__(dims=dims, plates=plates, name=name)
+
+    def set_value(self, x):
+        """Replace the fixed value (nodes/constant.py:46-57); the plates must not change."""
+        if self._moments_spec is None:
+            raise NotImplementedError("set_value needs a Constant created from a moments specification")
+        kind, u, dims, plates, value = self._moments_spec.fixed_moments(x)
+        if tuple(plates) != tuple(self.plates) or tuple(dims) != tuple(self.dims):
+            raise ValueError("Incorrect shape of the value: plates %s expected" % (tuple(self.plates),))
+        self.u = list(u)
+        self.value = value
+        self._version += 1
 
     def _ids(self):
         return []

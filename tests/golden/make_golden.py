@@ -570,6 +570,58 @@ def svi_mixture(name="svi_mixture", N=400, N_batch=40, K=4, D=2, steps=12):
          L=Q.L[:Q.iter].copy())
 
 
+def lda(name="lda_small", n_documents=5, n_words=600, n_vocabulary=20, n_topics=3, iters=6, svi_steps=6, subset_size=100):
+    """doc/source/examples/lda.rst:84-135 (batch VB) and :180-262 (stochastic VI with ``plates_multiplier``) scaled down:
+    Dirichlet / Categorical / Gate and a constant categorical index node."""
+    from bayespy import nodes
+    from bayespy.inference.vmp.nodes.categorical import CategoricalMoments
+    rs = np.random.RandomState(12)
+    word_documents = rs.randint(0, n_documents, size=n_words)
+    true_topic = rs.dirichlet(0.3 * np.ones(n_topics), size=n_documents)
+    true_word = rs.dirichlet(0.2 * np.ones(n_vocabulary), size=n_topics)
+    corpus = np.array([rs.choice(n_vocabulary, p=true_word[rs.choice(n_topics, p=true_topic[d])]) for d in word_documents])
+    out = dict(word_documents=word_documents, corpus=corpus)
+    p_topic = nodes.Dirichlet(np.ones(n_topics), plates=(n_documents,), name="p_topic")
+    p_word = nodes.Dirichlet(np.ones(n_vocabulary), plates=(n_topics,), name="p_word")
+    document_indices = nodes.Constant(CategoricalMoments(n_documents), word_documents, name="document_indices")
+    topics = nodes.Categorical(nodes.Gate(document_indices, p_topic), plates=(len(corpus),), name="topics")
+    words = nodes.Categorical(nodes.Gate(topics, p_word), name="words")
+    words.observe(corpus)
+    np.random.seed(5)
+    p_topic.initialize_from_random()
+    p_word.initialize_from_random()
+    out["p_topic_init"] = np.exp(np.array(p_topic.u[0], copy=True))
+    out["p_word_init"] = np.exp(np.array(p_word.u[0], copy=True))
+    Q = VB(words, topics, p_word, p_topic, document_indices)
+    Q.update(repeat=iters, verbose=False, tol=0)
+    out["L"] = Q.L[:iters].copy()
+    for nm, node in (("p_topic", p_topic), ("p_word", p_word), ("topics", topics)):
+        node_state(nm, node, out)
+    # stochastic variational inference
+    mult = n_words / subset_size
+    p_topic = nodes.Dirichlet(np.ones(n_topics), plates=(n_documents,), name="p_topic")
+    p_word = nodes.Dirichlet(np.ones(n_vocabulary), plates=(n_topics,), name="p_word")
+    document_indices = nodes.Constant(CategoricalMoments(n_documents), word_documents[:subset_size], name="document_indices")
+    topics = nodes.Categorical(nodes.Gate(document_indices, p_topic), plates=(subset_size,), plates_multiplier=(mult,),
+                               name="topics")
+    words = nodes.Categorical(nodes.Gate(topics, p_word), name="words")
+    p_topic.initialize_from_value(out["p_topic_init"])
+    p_word.initialize_from_value(out["p_word_init"])
+    Q = VB(words, topics, p_word, p_topic, document_indices)
+    Q.ignore_bound_checks = True
+    subsets = np.array([rs.choice(n_words, subset_size) for _ in range(svi_steps)])
+    pt, pw = [], []
+    for n in range(svi_steps):
+        Q["words"].observe(corpus[subsets[n]])
+        Q["document_indices"].set_value(word_documents[subsets[n]])
+        Q.update("topics", verbose=False)
+        Q.gradient_step("p_topic", "p_word", scale=(n + 1) ** (-0.7))
+        pt.append(np.array(p_topic.u[0], copy=True))
+        pw.append(np.array(p_word.u[0], copy=True))
+    out.update(subsets=subsets, svi_p_topic=np.array(pt), svi_p_word=np.array(pw), svi_L=Q.L[:Q.iter].copy())
+    save(name, **out)
+
+
 def lssm_plated_dynamics(name="lssm_plated_dynamics", M=4, N=15, D=2, P=3, iters=4):
     """P independent chains, each with ITS OWN time-invariant dynamics: A with plates (P, 1, D)."""
     from bayespy.nodes import GaussianMarkovChain, Dot
@@ -775,7 +827,7 @@ def lssm_doc_rotated(name="lssm_doc_rotated"):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["quickstart", "pca", "linalg", "summul", "dist", "gmm", "gmc", "rot", "dot", "mixard", "gmcplates", "gmcvarying", "pcabench", "pcamasked64", "take", "gate", "lssmrot", "gmcmixing", "gradients"]
+    which = sys.argv[1:] or ["quickstart", "pca", "linalg", "summul", "dist", "gmm", "gmc", "rot", "dot", "mixard", "gmcplates", "gmcvarying", "pcabench", "pcamasked64", "take", "gate", "lssmrot", "gmcmixing", "gradients", "lda"]
     if "quickstart" in which:
         quickstart()
     if "pca" in which:
@@ -803,6 +855,8 @@ if __name__ == "__main__":
         gate_models()
     if "lssmrot" in which:
         lssm_doc_rotated()
+    if "lda" in which:
+        lda()
     if "gradients" in which:
         pca_gradients()
         svi_mixture()
