@@ -622,6 +622,62 @@ def lda(name="lda_small", n_documents=5, n_words=600, n_vocabulary=20, n_topics=
     save(name, **out)
 
 
+def advanced_guide(name="advanced_guide"):
+    """doc/source/user_guide/advanced.rst on the user guide's PCA model: deterministic annealing (:219-224) and
+    stochastic variational inference with ``plates_multiplier=(1, 20)`` on X (:276-313)."""
+    from bayespy.nodes import Dot
+    rs = np.random.RandomState(17)
+    D = 3
+    c = rs.randn(10, 2)
+    x = rs.randn(2, 100)
+    data = np.dot(c, x) + 0.1 * rs.randn(10, 100)
+
+    def model(nx, mult=None):
+        kw = {} if mult is None else dict(plates_multiplier=mult)
+        X = GaussianARD(0, 1, shape=(D,), plates=(1, nx), name="X", **kw)
+        alpha = Gamma(1e-3, 1e-3, plates=(D,), name="alpha")
+        C = GaussianARD(0, alpha, shape=(D,), plates=(10, 1), name="C")
+        F = Dot(C, X)
+        tau = Gamma(1e-3, 1e-3, name="tau")
+        Y = GaussianARD(F, tau, name="Y")
+        return X, alpha, C, tau, Y
+    out = dict(data=data)
+    # deterministic annealing
+    X, alpha, C, tau, Y = model(100)
+    Y.observe(data)
+    Q = VB(Y, C, X, alpha, tau)
+    X_init = rs.randn(1, 100, D)
+    X.initialize_from_parameters(X_init, 10)
+    beta, betas = 0.1, []
+    while beta < 1.0:
+        beta = min(beta * 1.5, 1.0)
+        Q.set_annealing(beta)
+        Q.update(repeat=100, tol=1e-4, verbose=False)
+        betas.append((beta, Q.iter))
+    out.update(X_init=X_init, anneal_L=Q.L[:Q.iter].copy(), anneal_schedule=np.array(betas))
+    for nm, node in (("C", C), ("tau", tau), ("alpha", alpha)):
+        node_state("anneal_" + nm, node, out)
+    # stochastic variational inference
+    X, alpha, C, tau, Y = model(5, mult=(1, 20))
+    Q = VB(Y, C, X, alpha, tau)
+    C_init = rs.randn(10, 1, D)
+    C.initialize_from_value(C_init)
+    Q.ignore_bound_checks = True
+    steps = 15
+    subsets = np.array([rs.choice(100, 5) for _ in range(steps)])
+    Cs, taus, alphas = [], [], []
+    for n in range(steps):
+        Y.observe(data[:, subsets[n]])
+        Q.update(X, verbose=False)
+        Q.gradient_step(C, alpha, tau, scale=(n + 2.0) ** (-0.7))
+        Cs.append(np.array(C.u[0], copy=True))
+        taus.append(np.array(tau.u[0], copy=True))
+        alphas.append(np.array(alpha.u[0], copy=True))
+    out.update(C_init=C_init, subsets=subsets, svi_C=np.array(Cs), svi_tau=np.array(taus), svi_alpha=np.array(alphas),
+               svi_L=Q.L[:Q.iter].copy())
+    save(name, **out)
+
+
 def lssm_plated_dynamics(name="lssm_plated_dynamics", M=4, N=15, D=2, P=3, iters=4):
     """P independent chains, each with ITS OWN time-invariant dynamics: A with plates (P, 1, D)."""
     from bayespy.nodes import GaussianMarkovChain, Dot
@@ -857,6 +913,7 @@ if __name__ == "__main__":
         lssm_doc_rotated()
     if "lda" in which:
         lda()
+        advanced_guide()
     if "gradients" in which:
         pca_gradients()
         svi_mixture()

@@ -148,3 +148,55 @@ def test_stochastic_variational_inference_with_plate_multipliers(backend):
     with pytest.raises(ValueError):
         Mixture(Categorical(alpha, plates=(N_batch,), plates_multiplier=(3.0,)), Gaussian,
                 Gaussian(np.zeros(Dm), np.identity(Dm), plates=(N_batch, K), plates_multiplier=(2.0, 1)), np.identity(Dm))
+
+
+def _guide_pca(data, nx, mult=None):
+    from bayespy_b200.nodes import GaussianARD, Gamma, Dot
+    Dm = 3
+    kw = {} if mult is None else dict(plates_multiplier=mult)
+    X = GaussianARD(0, 1, shape=(Dm,), plates=(1, nx), name="X", **kw)
+    alpha = Gamma(1e-3, 1e-3, plates=(Dm,), name="alpha")
+    C = GaussianARD(0, alpha, shape=(Dm,), plates=(10, 1), name="C")
+    F = Dot(C, X)
+    tau = Gamma(1e-3, 1e-3, name="tau")
+    Y = GaussianARD(F, tau, name="Y")
+    return X, alpha, C, tau, Y
+
+
+def test_advanced_guide_annealing_and_stochastic_pca(backend):
+    """doc/source/user_guide/advanced.rst: deterministic annealing (:219-224: the annealing is raised by 1.5x after every
+    convergence at tol=1e-4; same stopping iterations and bounds as the reference) and stochastic VI on the PCA model
+    with ``plates_multiplier=(1, 20)`` on X, inherited by Dot and Y (:276-313: C, alpha, tau after every step)."""
+    from bayespy_b200.inference import VB
+    g = golden("advanced_guide")
+    data = g["data"]
+    X, alpha, C, tau, Y = _guide_pca(data, 100)
+    Y.observe(data)
+    Q = VB(Y, C, X, alpha, tau)
+    X.initialize_from_parameters(g["X_init"], 10)
+    beta, sched = 0.1, []
+    while beta < 1.0:
+        beta = min(beta * 1.5, 1.0)
+        Q.set_annealing(beta)
+        Q.update(repeat=100, tol=1e-4, verbose=False)
+        sched.append((beta, Q.iter))
+    np.testing.assert_allclose(np.array(sched), g["anneal_schedule"], rtol=1e-12)
+    np.testing.assert_allclose(Q.L[:Q.iter], g["anneal_L"], rtol=1e-7)
+    for nm, node in (("C", C), ("tau", tau), ("alpha", alpha)):
+        for i in range(2):
+            np.testing.assert_allclose(np.asarray(node.u[i]), g["anneal_%s_u%d" % (nm, i)], rtol=1e-6, atol=1e-9,
+                                       err_msg="%s.u[%d] after annealing" % (nm, i))
+    # stochastic variational inference
+    X, alpha, C, tau, Y = _guide_pca(data, 5, mult=(1, 20))
+    assert tuple(Y.plates_multiplier) == (20,) or tuple(Y.plates_multiplier) == (1, 20)
+    Q = VB(Y, C, X, alpha, tau)
+    C.initialize_from_value(g["C_init"])
+    Q.ignore_bound_checks = True
+    for n, subset in enumerate(g["subsets"]):
+        Y.observe(data[:, subset])
+        Q.update(X, verbose=False)
+        Q.gradient_step(C, alpha, tau, scale=(n + 2.0) ** (-0.7))
+        np.testing.assert_allclose(np.asarray(C.u[0]), g["svi_C"][n], rtol=1e-7, atol=1e-9, err_msg="C, step %d" % n)
+        np.testing.assert_allclose(np.asarray(tau.u[0]), g["svi_tau"][n], rtol=1e-7, err_msg="tau, step %d" % n)
+        np.testing.assert_allclose(np.asarray(alpha.u[0]), g["svi_alpha"][n], rtol=1e-7, err_msg="alpha, step %d" % n)
+    np.testing.assert_allclose(Q.L[:Q.iter], g["svi_L"], rtol=1e-8)
