@@ -222,6 +222,37 @@ class DArray:
         return DArray(self.owner, self.ptr + int(i) * self.strides[0] * esz, self.shape[1:], self.strides[1:],
                       self.dtype)
 
+    def basic_index(self, index):
+        """NumPy basic indexing (integers, slices with any non-zero step, None) as a view: pointer, shape and element
+        strides only.  ``index`` is a tuple with one entry per axis in order; missing trailing axes are taken whole."""
+        esz = np.dtype(_DT[self.dtype][0]).itemsize
+        ptr, shape, strides = self.ptr, [], []
+        ax = 0
+        for s in index:
+            if s is None:
+                shape.append(1)
+                strides.append(0)
+                continue
+            n, st = self.shape[ax], self.strides[ax]
+            if isinstance(s, (slice, range)):
+                # a range is an already normalised slice (its stop may be -1 for negative steps)
+                start, stop, step = (s.start, s.stop, s.step) if isinstance(s, range) else s.indices(n)
+                length = len(range(start, stop, step))
+                ptr += start * st * esz
+                shape.append(length)
+                strides.append(st * step)
+            else:
+                i = int(s)
+                if i < 0:
+                    i += n
+                if i < 0 or i >= n:
+                    raise IndexError("Index out of range")
+                ptr += i * st * esz
+            ax += 1
+        shape += list(self.shape[ax:])
+        strides += list(self.strides[ax:])
+        return DArray(self.owner, ptr, tuple(shape), tuple(strides), self.dtype)
+
     def slice_axis(self, axis, start, stop):
         esz = np.dtype(_DT[self.dtype][0]).itemsize
         if axis < 0:

@@ -168,6 +168,10 @@ class Node:
     def get_shape(self, i):
         return tuple(self.plates) + tuple(self.dims[i])
 
+    def __getitem__(self, index):
+        """Basic slicing of the plates (node.py:761-763)."""
+        return Slice(self, index, name=self.name + ".__getitem__")
+
     # ---- masks (host booleans; nodes.node.py:446-526) ------------------------------------------
     def get_mask(self):
         return self.mask
@@ -342,3 +346,123 @@ class Deterministic(Node):
 
     def lower_bound_contribution(self, ignore_masked=True):
         return 0.0
+
+
+# --------------------------------------------------------------------------------------------
+def _np_index(slices):
+    """Normalised slices (ranges) as NumPy index entries."""
+    out = []
+    for s in slices:
+        if isinstance(s, range):
+            out.append(slice(s.start, s.stop if s.stop >= 0 else None, s.step))
+        else:
+            out.append(s)
+    return tuple(out)
+
+
+class Slice(Deterministic):
+    """Basic slicing of a node's plates: integers, slices, ``None`` (new unit plate) and one ``Ellipsis``
+    (node.py:868-1160).  The moments are strided VIEWS of the parent's (no copy); the message to the parent is the
+    child's message placed into a zero array of the parent's plates through the same view."""
+
+    def __init__(self, X, slices, name=""):
+        self.moment_kind = X.moment_kind
+        slices = list(slices) if isinstance(slices, tuple) else [slices]
+        num_axis, ellipsis_index = 0, None
+        for k, s in enumerate(slices):
+            if isinstance(s, (int, np.integer)) and not isinstance(s, bool) or isinstance(s, slice):
+                num_axis += 1
+            elif s is None:
+                pass
+            elif s is Ellipsis:
+                if ellipsis_index is None:
+                    ellipsis_index = k
+                else:
+                    num_axis += 1
+                    slices[k] = slice(None)
+            else:
+                raise TypeError("Invalid argument type: {0}".format(s.__class__))
+        if num_axis > len(X.plates):
+            raise IndexError("Too many indices")
+        expand = len(X.plates) - num_axis
+        if ellipsis_index is not None:
+            k = ellipsis_index
+            slices = slices[:k] + [slice(None)] * expand + slices[k + 1:]
+        else:
+            slices = slices + [slice(None)] * expand
+        j = 0
+        for k, s in enumerate(slices):
+            if s is None:
+                continue
+            n = X.plates[j]
+            if isinstance(s, slice):
+                s = range(*s.indices(n))          # normalised: start, stop, step (negative steps included)
+                if len(s) <= 0:
+                    raise IndexError("Slicing leads to empty plates")
+            else:
+                s = int(s)
+                if s < 0:
+                    s += n
+                if s < 0 or s >= n:
+                    raise IndexError("Index out of range")
+            slices[k] = s
+            j += 1
+        self.slices = slices
+        super().__init__(X, dims=X.dims, name=name)
+
+    def _plates_to_parent(self, index):
+        return tuple(self.parents[index].plates)
+
+    def _plates_from_parent(self, index):
+        plates, k = list(self.parents[index].plates), 0
+        for s in self.slices:
+            if isinstance(s, range):
+                plates[k] = len(s)
+                k += 1
+            elif s is None:
+                plates = plates[:k] + [1] + plates[k:]
+                k += 1
+            else:
+                del plates[k]
+        return tuple(plates)
+
+    def _map_parent_axes(self, index, values):
+        out, j = [], 0
+        for s in self.slices:
+            if s is None:
+                out.append(1)
+            else:
+                if isinstance(s, range):
+                    out.append(values[j])
+                j += 1
+        return tuple(out)
+
+    def _compute_moments(self, u):
+        pp = tuple(self.parents[0].plates)
+        out = []
+        for ui, dims in zip(u, self.dims):
+            ui = D.asarray(ui.materialize() if hasattr(ui, "materialize") else ui)
+            out.append(ui.broadcast_to(pp + tuple(dims)).basic_index(tuple(self.slices)))
+        return out
+
+    def _place(self, child_value, dims, dtype_mask=False):
+        """Zero array over the parent's plates (+ dims) with ``child_value`` written through the slicing view."""
+        pp = tuple(self.parents[0].plates)
+        full = pp + tuple(dims)
+        out = DArray.zeros(full)
+        view = out.basic_index(tuple(self.slices))
+        src = D.asarray(child_value)
+        D.copy_into(view, src.broadcast_to(view.shape))
+        return out
+
+    def _weights_to_parent(self, index, mask):
+        pp = tuple(self.parents[0].plates)
+        w = np.zeros(pp, dtype=bool)
+        idx = _np_index(self.slices)
+        w[idx] = np.broadcast_to(np.asarray(mask, dtype=bool), w[idx].shape)
+        return w
+
+    def _compute_message_to_parent(self, index, m_children, u):
+        if index != 0:
+            raise ValueError("Invalid index")
+        return [None if mi is None else self._place(mi, dims) for mi, dims in zip(m_children, self.dims)]

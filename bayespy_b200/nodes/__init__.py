@@ -1,5 +1,5 @@
 """Node classes with the reference's public names (bayespy/nodes/__init__.py:105)."""
-from ..engine.node import Node, Constant, Deterministic                      # noqa: F401
+from ..engine.node import Node, Constant, Deterministic, Slice               # noqa: F401
 from ..engine.expfam import ExponentialFamily                                 # noqa: F401
 from ..engine.gaussian import GaussianARD                                     # noqa: F401
 from ..engine.gamma import Gamma                                              # noqa: F401

@@ -678,6 +678,36 @@ def advanced_guide(name="advanced_guide"):
     save(name, **out)
 
 
+def sliced_nodes(name="slice"):
+    """Basic slicing of plates (node.py:761-763, :868-1160): a plated latent mean observed through several slices —
+    ranges with steps, an integer, a new axis, an ellipsis, a negative step."""
+    rs = np.random.RandomState(23)
+    mu = GaussianARD(0.5, 1e-2, plates=(6, 4), name="mu")
+    vec = GaussianARD(0, 1e-1, shape=(2,), plates=(5,), name="vec")
+    obs = {}
+    # (negative steps are left out: the reference re-normalises its stored slices and ends up with empty plates there)
+    children = [("a", mu[1:4, ::2], 2.0), ("b", mu[0], 1.5), ("c", mu[None, 5, 1:3], 3.0), ("d", mu[..., -1], 1.0),
+                ("e", mu[::2, 1], 0.7)]
+    out, nodes = {}, []
+    for nm, parent, prec in children:
+        Y = GaussianARD(parent, prec, name="y_" + nm)
+        y = rs.randn(*Y.plates)
+        Y.observe(y)
+        out["y_" + nm] = y
+        out["plates_" + nm] = np.array(Y.plates)
+        nodes.append(Y)
+    Yv = GaussianARD(vec[1:4], [2.0, 0.5], shape=(2,), name="y_v")
+    yv = rs.randn(*(Yv.plates + (2,)))
+    Yv.observe(yv)
+    out["y_v"] = yv
+    Q = VB(mu, vec, Yv, *nodes)
+    Q.update(repeat=2, verbose=False, tol=0)
+    out["L"] = Q.L[:2].copy()
+    node_state("mu", mu, out)
+    node_state("vec", vec, out)
+    save(name, **out)
+
+
 def lssm_plated_dynamics(name="lssm_plated_dynamics", M=4, N=15, D=2, P=3, iters=4):
     """P independent chains, each with ITS OWN time-invariant dynamics: A with plates (P, 1, D)."""
     from bayespy.nodes import GaussianMarkovChain, Dot
@@ -883,7 +913,7 @@ def lssm_doc_rotated(name="lssm_doc_rotated"):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["quickstart", "pca", "linalg", "summul", "dist", "gmm", "gmc", "rot", "dot", "mixard", "gmcplates", "gmcvarying", "pcabench", "pcamasked64", "take", "gate", "lssmrot", "gmcmixing", "gradients", "lda"]
+    which = sys.argv[1:] or ["quickstart", "pca", "linalg", "summul", "dist", "gmm", "gmc", "rot", "dot", "mixard", "gmcplates", "gmcvarying", "pcabench", "pcamasked64", "take", "gate", "lssmrot", "gmcmixing", "gradients", "lda", "slice"]
     if "quickstart" in which:
         quickstart()
     if "pca" in which:
@@ -911,6 +941,8 @@ if __name__ == "__main__":
         gate_models()
     if "lssmrot" in which:
         lssm_doc_rotated()
+    if "slice" in which:
+        sliced_nodes()
     if "lda" in which:
         lda()
         advanced_guide()
