@@ -222,6 +222,30 @@ class DArray:
         return DArray(self.owner, self.ptr + int(i) * self.strides[0] * esz, self.shape[1:], self.strides[1:],
                       self.dtype)
 
+    def __getitem__(self, index):
+        """NumPy-style indexing.  Basic indexing (integers, slices, None, Ellipsis) returns a device view; anything else
+        (index arrays, boolean masks) is answered from a host copy, like ``numpy()[index]``."""
+        idx = index if isinstance(index, tuple) else (index,)
+        if all(isinstance(i, (int, np.integer, slice)) or i is None or i is Ellipsis for i in idx):
+            n_real = sum(1 for i in idx if i is not None and i is not Ellipsis)
+            if n_real > self.ndim:
+                raise IndexError("too many indices for array")
+            out, seen = [], False
+            for i in idx:
+                if i is Ellipsis:
+                    if seen:
+                        raise IndexError("an index can only have a single ellipsis ('...')")
+                    seen = True
+                    out += [slice(None)] * (self.ndim - n_real)
+                else:
+                    out.append(i)
+            return self.basic_index(tuple(out))
+        return self.numpy()[index]
+
+    @property
+    def T(self):
+        return DArray(self.owner, self.ptr, self.shape[::-1], self.strides[::-1], self.dtype)
+
     def basic_index(self, index):
         """NumPy basic indexing (integers, slices with any non-zero step, None) as a view: pointer, shape and element
         strides only.  ``index`` is a tuple with one entry per axis in order; missing trailing axes are taken whole."""

@@ -50,6 +50,7 @@ class CategoricalMoments:
 
 
 class CategoricalDistribution(Distribution):
+    zero_times_inf = True          # log-probabilities may be -inf where the one-hot moment is 0
 
     def __init__(self, categories):
         if not isinstance(categories, (int, np.integer)):
@@ -71,6 +72,7 @@ class CategoricalDistribution(Distribution):
 
     def compute_moments_and_cgf(self, phi, mask=True):
         """softmax with the reference's max-shift and second renormalisation; g = -logsumexp."""
+        phi = [D.asarray(v) for v in phi]         # the protocol also takes host arrays (seam 2, SURVEY 8b)
         p = phi[0].contiguous()
         K = p.shape[-1]
         P = tuple(p.shape[:-1])

@@ -51,6 +51,7 @@ class DirichletDistribution(Distribution):
 
     def compute_moments_and_cgf(self, phi, mask=True):
         """dirichlet.py:130-160; raises ValueError("Natural parameters should be positive")."""
+        phi = [D.asarray(v) for v in phi]
         p = phi[0].contiguous()
         K = p.shape[-1]
         P = tuple(p.shape[:-1])

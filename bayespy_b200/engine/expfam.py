@@ -76,6 +76,17 @@ class ExponentialFamily(Node):
         if initialize:
             self.initialize_from_prior()
 
+    # the moments: assigning the list (also from outside, as the reference's test utilities do) invalidates every
+    # cache keyed on this node's version
+    @property
+    def u(self):
+        return self._u
+
+    @u.setter
+    def u(self, value):
+        self._u = value
+        self._version = getattr(self, "_version", 0) + 1
+
     # ---- graph -------------------------------------------------------------------------------
     def _ids(self):
         return [self._id]
@@ -106,7 +117,7 @@ class ExponentialFamily(Node):
         """Write new moments on the plates selected by ``update_mask`` (host bool;
         stochastic.py:223-273 np.copyto(where=mask))."""
         if mask_is_full(update_mask) or self.u[0] is None:
-            self.u = [D.asarray(ui) for ui in u]
+            self.u = [self._trim_leading(D.asarray(ui), i) for i, ui in enumerate(u)]
             if g is not None:
                 self.g = g
         else:
@@ -116,6 +127,13 @@ class ExponentialFamily(Node):
             if g is not None and self.g is not None:
                 self.g = D.where(md, g, self.g)
         self._version += 1
+
+    def _trim_leading(self, a, i):
+        """Moments carry exactly len(plates) + ndim_i axes: unit axes a kernel produced in front of them are dropped."""
+        want = len(self.plates) + self.ndims[i]
+        if isinstance(a, DArray) and a.ndim > want and all(n == 1 for n in a.shape[:a.ndim - want]):
+            return a.squeeze_leading(want)
+        return a
 
     def _canonical_phi(self, phi):
         """Give every phi_i exactly len(plates)+ndim_i axes (expfamily.py:230-250)."""

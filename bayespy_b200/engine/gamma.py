@@ -56,6 +56,7 @@ class GammaDistribution(Distribution):
 
     def compute_moments_and_cgf(self, phi, mask=True):
         """gamma.py:124-148 as one kernel."""
+        phi = [D.asarray(v) for v in phi]
         be = _bpk.get()
         P = tuple(np.broadcast_shapes(phi[0].shape, phi[1].shape))
         n = int(np.prod(P, dtype=np.int64)) if P else 1

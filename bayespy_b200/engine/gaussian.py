@@ -343,6 +343,7 @@ class GaussianARDDistribution(Distribution):
 
     # -- moments (gaussian.py:672-706)
     def compute_moments_and_cgf(self, phi, mask=True):
+        phi = [D.asarray(dense(v)) for v in phi]
         if self.ndim == 0:
             # scalar closed form :673-678
             u0 = D.div(D.mul(phi[0], -0.5), phi[1])
@@ -607,6 +608,7 @@ class GaussianDistribution(Distribution):
 
     def compute_moments_and_cgf(self, phi, mask=True):
         """gaussian.py:397-446 (no truncation)."""
+        phi = [D.asarray(dense(v)) for v in phi]
         u0, cov, g, _ = gaussian_moments_device(phi[0], phi[1], self.D)
         return [u0, FactoredSecondMoment(u0, cov, self.shape)], g
 
@@ -662,6 +664,8 @@ class Gaussian(_GaussianNode):
         from .wishart import ensure_wishart
         Lambda = ensure_wishart(Lambda)
         Dm = Lambda.dims[0][-1]
+        if isinstance(mu, Node) and hasattr(mu, "_to_gaussian"):
+            mu = mu._to_gaussian()        # a Gaussian Markov chain as the mean: Gaussian vectors plated over time
         if isinstance(mu, Node):
             if mu.moment_kind != "gaussian" or tuple(mu.dims[0]) != (Dm,):
                 raise ValueError("Mean and precision have inconsistent shapes: {0} and {1}".format(

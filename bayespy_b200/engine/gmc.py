@@ -91,6 +91,7 @@ class _SingleChainDistribution(Distribution):
     def compute_moments_and_cgf(self, phi, mask=True):
         N, Dm = self.N, self.D
         be = _bpk.get()
+        phi = [D.asarray(v) for v in phi]
         y = phi[0].contiguous()
         A = D.mul(phi[1], -2.0)
         B = D.mul(phi[2], -1.0) if N > 1 else DArray.empty((1,))
@@ -281,6 +282,7 @@ class GaussianMarkovChainDistribution(Distribution):
     def compute_moments_and_cgf(self, phi, mask=True):
         if self._single is not None:
             return self._single.compute_moments_and_cgf(phi, mask=mask)
+        phi = [D.asarray(v) for v in phi]
         N, Dm, P = self.N, self.D, self.plates
         npl = len(P)
         batch = int(np.prod(P, dtype=np.int64)) if P else 1

@@ -110,8 +110,20 @@ class MixtureDistribution(Distribution):
                 ui = dense(ui)
                 if Phi_i.ndim - nd < -self.cluster_plate:
                     Phi_i = Phi_i.add_leading(-self.cluster_plate - (Phi_i.ndim - nd))
-                t = D.sum_product([Phi_i, ui], [self._cluster_keys(Phi_i, nd), self._plain_keys(ui, nd)], out,
-                                  sizes={"k": self.K})
+                if getattr(self.raw, "zero_times_inf", False):
+                    # expfamily.py:52-58: where the moment is zero the (possibly infinite) parameter does not count —
+                    # e.g. a class with probability exactly 0 that was not observed.  Only the discrete mixed
+                    # distributions need it; it materialises (plates, K, dims).
+                    npl_u = ui.ndim - nd
+                    need = -self.cluster_plate - 1
+                    ue = ui.add_leading(need - npl_u) if npl_u < need else ui
+                    ue = ue.expand_dims(ue.ndim - nd + self.cluster_plate + 1)
+                    sel = D.nonzero_select(ue, Phi_i)
+                    t = D.sum_product([sel, ue], [self._cluster_keys(sel, nd), self._cluster_keys(ue, nd)], out,
+                                      sizes={"k": self.K})
+                else:
+                    t = D.sum_product([Phi_i, ui], [self._cluster_keys(Phi_i, nd), self._plain_keys(ui, nd)], out,
+                                      sizes={"k": self.K})
                 L = D.add(L, t)
             return [L]
         # parameters of the mixed distribution

@@ -168,6 +168,22 @@ class Node:
     def get_shape(self, i):
         return tuple(self.plates) + tuple(self.dims[i])
 
+    # the names the reference's own unit tests call (node.py:429-441, :570, :657; deterministic.py:62-82)
+    def _message_to_child(self):
+        return self.get_moments()
+
+    def _message_to_parent(self, index, u_parent=None):
+        return self.message_to_parent(index)
+
+    def _message_from_children(self, *args, **kwargs):
+        return self.message_from_children()
+
+    def _message_from_parents(self, exclude=None):
+        return self.moments_from_parents(exclude=exclude)
+
+    def _compute_weights_to_parent(self, index, weights):
+        return self._weights_to_parent(index, np.asarray(weights))
+
     def __getitem__(self, index):
         """Basic slicing of the plates (node.py:761-763)."""
         return Slice(self, index, name=self.name + ".__getitem__")

@@ -71,7 +71,7 @@ class WishartDistribution(Distribution):
     def compute_moments_and_cgf(self, phi, mask=True):
         """wishart.py:165-188 as one kernel."""
         be = _bpk.get()
-        p0, p1 = phi
+        p0, p1 = [D.asarray(v) for v in phi]
         Dm = p0.shape[-1]
         P = tuple(np.broadcast_shapes(p0.shape[:-2], p1.shape))
         n = int(np.prod(P, dtype=np.int64)) if P else 1
