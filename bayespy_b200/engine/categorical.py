@@ -52,6 +52,15 @@ class CategoricalMoments:
 class CategoricalDistribution(Distribution):
     zero_times_inf = True          # log-probabilities may be -inf where the one-hot moment is 0
 
+    def compute_gradient(self, g, u, phi):
+        """multinomial.py:161-218 with one trial: the Fisher information of the softmax is diag(p) - p p^T, so
+        grad_i = g_i p_i - p_i sum_j g_j p_j."""
+        p, g0 = D.asarray(u[0]), D.asarray(g[0])
+        gp = D.mul(g0, p)
+        keys = list(range(gp.ndim))
+        tot = D.sum_product([gp], [keys], keys[:-1])
+        return [D.sub(gp, D.mul(p, tot.add_trailing(1)))]
+
     def __init__(self, categories):
         if not isinstance(categories, (int, np.integer)):
             raise ValueError("Number of categories must be integer")

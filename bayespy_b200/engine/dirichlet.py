@@ -40,6 +40,13 @@ def dirichlet_constant(p):
 
 class DirichletDistribution(Distribution):
 
+    def compute_gradient(self, g, u, phi):
+        """dirichlet.py:213-231, as the reference computes it: g * (psi'(phi) - psi'(sum_d phi_d)), elementwise."""
+        ph, g0 = D.asarray(phi[0]), D.asarray(g[0])
+        keys = list(range(ph.ndim))
+        tot = D.sum_product([ph], [keys], keys[:-1])
+        return [D.mul(g0, D.sub(D.trigamma(ph), D.trigamma(tot).add_trailing(1)))]
+
     def compute_message_to_parent(self, parent, index, u_self, u_alpha):
         return [u_self[0], D.asarray(1.0)]
 

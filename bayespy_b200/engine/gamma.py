@@ -100,6 +100,14 @@ class Gamma(ExponentialFamily):
         super().__init__(a, b, dims=((), ()), distribution=GammaDistribution(), plates=plates, name=name,
                          initialize=initialize)
 
+    def initialize_from_parameters(self, a, b):
+        """q <- Gamma(a, b)  (expfamily.py:166-180 with the fixed moments of the parents)."""
+        u_a = gamma_prior_constant(np.asarray(a, dtype=np.float64) * np.ones(np.shape(b))).get_moments()
+        u_b = ensure_gamma(np.asarray(b, dtype=np.float64) * np.ones(np.shape(a))).get_moments()
+        self.phi = self._canonical_phi(self._distribution.compute_phi_from_parents(u_a, u_b))
+        u, g = self._distribution.compute_moments_and_cgf(self.phi)
+        self._store(u, g, np.logical_not(self.observed))
+
     def __str__(self):
         a = self.phi[1].numpy()
         b = -self.phi[0].numpy()

@@ -677,3 +677,12 @@ class Gaussian(_GaussianNode):
                     mu.dims, Lambda.dims))
         super().__init__(mu, Lambda, dims=((Dm,), (Dm, Dm)), distribution=GaussianDistribution(Dm),
                          plates=plates, name=name, initialize=initialize, plates_multiplier=plates_multiplier)
+
+    def initialize_from_parameters(self, mu, Lambda):
+        """q <- N(mu, Lambda^-1)  (gaussian.py:1420-1423)."""
+        from .wishart import wishart_constant
+        u_mu = gaussian_constant(mu, 1).get_moments()
+        u_L = wishart_constant(Lambda).get_moments()
+        self.phi = self._canonical_phi(self._distribution.compute_phi_from_parents(u_mu, u_L))
+        u, g = self._distribution.compute_moments_and_cgf(self.phi)
+        self._store(u, g, np.logical_not(self.observed))
