@@ -127,7 +127,10 @@ class Node:
             c.delete()
 
     def _ids(self):
-        """IDs of the stochastic factors this node depends on (independence check)."""
+        """IDs of the stochastic factors this node depends on (independence check); ``_get_id_list`` is the
+        reference's name for it (node.py:443-444)."""
+        if hasattr(self, "_get_id_list"):
+            return self._get_id_list()
         raise NotImplementedError
 
     def _check_independent_parents(self):
@@ -238,6 +241,9 @@ class Node:
 
     # ---- messages -----------------------------------------------------------------------------
     def get_moments(self):
+        # a node written against the reference's base class provides `_message_to_child` instead
+        if type(self)._message_to_child is not Node._message_to_child:
+            return [D.asarray(ui) for ui in self._message_to_child()]
         raise NotImplementedError
 
     def _message_and_mask_to_parent(self, index):
@@ -273,7 +279,10 @@ class Node:
         """Sum of the children's messages, one entry per moment (None = no message)."""
         msg = [None] * len(self.dims)
         for child, index in self.children:
-            m = child.message_to_parent(index)
+            if type(child)._message_to_parent is not Node._message_to_parent:
+                m = [None if mi is None else D.asarray(mi) for mi in child._message_to_parent(index)]
+            else:
+                m = child.message_to_parent(index)
             for i in range(len(self.dims)):
                 if m[i] is not None:
                     msg[i] = m[i] if msg[i] is None else D.add(msg[i], m[i])
