@@ -170,12 +170,13 @@ class GaussianMarkovChainDistribution(Distribution):
     are summed over time here and carry a time axis of length 1 (so that no (N-1, D, D, D) array is ever formed);
     otherwise they keep the time axis and the generic plate reduction (node.py:570-655) does what is left."""
 
-    def __init__(self, N, Dm, plates=(), TA=1, Tn=1):
+    def __init__(self, N, Dm, plates=(), TA=1, Tn=1, plain=True):
         self.N, self.D = int(N), int(Dm)
         self.plates = tuple(int(p) for p in plates)
         self.TA, self.Tn = int(TA), int(Tn)
         self.static = self.TA == 1 and self.Tn == 1
-        self._single = _SingleChainDistribution(N, Dm) if (not self.plates and self.static) else None
+        # ``plain``: the dynamics parents have exactly the plates (D,) (no explicit time axis of length one either)
+        self._single = _SingleChainDistribution(N, Dm) if (not self.plates and self.static and plain) else None
 
     def _t_msg(self):
         return 1 if self.static else self.N - 1
@@ -405,7 +406,8 @@ class GaussianMarkovChain(ExponentialFamily):
             if chain_plates != plates:
                 raise ValueError("The plates %s of the parents are not broadcastable to the given plates %s."
                                  % (chain_plates, plates))
-        dist = GaussianMarkovChainDistribution(self.N, self.D, chain_plates, TA=TA, Tn=Tn)
+        dist = GaussianMarkovChainDistribution(self.N, self.D, chain_plates, TA=TA, Tn=Tn,
+                                               plain=len(A.plates) == 1 and len(nu.plates) <= 1)
         super().__init__(mu, Lambda, A, nu, dims=((self.N, Dm), (self.N, Dm, Dm), (self.N - 1, Dm, Dm)),
                          distribution=dist, plates=chain_plates, name=name, initialize=initialize)
 
