@@ -651,6 +651,16 @@ class FactorModelPlan:
             return None
         col, row, tau, Y = self.col, self.row, self.tau, self.Y
         alpha = row.parents[1]
+        # everything _resident_hyper() decides on: parent identities, observed state and fan-out of the hyper nodes
+        # (re-read on every call: a node may be observed, re-parented or given another child between two updates)
+        hk = tuple(id(pp) for n in (col, row, alpha, tau) for pp in getattr(n, "parents", ())) + (id(alpha), id(tau)) \
+            + tuple((o if (o is True or o is False or o is None) else "array", len(getattr(n, "children", ())))
+                    for n in (alpha, tau) for o in (getattr(n, "observed", None),))
+        key = (tuple(map(id, nodes)), tuple(map(id, vb.model)), hk)
+        cached = getattr(self, "_prog_cache", None)
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        self._prog_cache = None
         latent = {col, row}
         if isinstance(alpha, Gamma):
             latent.add(alpha)
@@ -663,10 +673,6 @@ class FactorModelPlan:
         order = [n for n in order if n is not Y and n is not self.F]
         if set(order) != latent or len(order) != len(latent):
             return None
-        # everything _resident_hyper() decides on: parent identities, observed state and fan-out of the hyper nodes
-        hk = tuple(id(pp) for n in (col, row, alpha, tau) for pp in getattr(n, "parents", ())) + (id(alpha), id(tau)) \
-            + tuple((repr(getattr(n, "observed", None)) if not isinstance(getattr(n, "observed", None), np.ndarray)
-                     else "array", len(getattr(n, "children", ()))) for n in (alpha, tau))
         if getattr(self, "_hyper_key", None) != hk:
             self._res_cache = None
             self._hyper = self._resident_hyper()
@@ -687,6 +693,7 @@ class FactorModelPlan:
             else:
                 ops.append(V["TAU"])
         ops.append(V["BOUND"])
+        self._prog_cache = (key, (ops, order))
         return ops, order
 
     def _resident_enter(self, order, lprev):
