@@ -50,7 +50,7 @@ for _ in range(3):
 ms = float(np.median(ts))
 print("pca_xsweep_masked_fused N=%d M=%d K=%d chunk_tiles=%s: %.3f ms (%d launches) | %.0f GB/s of 704 B/col | "
       "%.1f TFLOP/s on 76 DMMA/col executed (%.0f %% of the 36.9 TFLOP/s pipe; + ~3 kflop/col of DFMA) | %.2f us per 1000 columns"
-      % (N, M, K, os.environ.get("BPK_PMASK_CHUNK_TILES", "2"), ms, nl, 704 * N / ms / 1e6, 76 * 512 * N / ms / 1e9,
+      % (N, M, K, os.environ.get("BPK_PMASK_CHUNK_TILES", "8"), ms, nl, 704 * N / ms / 1e6, 76 * 512 * N / ms / 1e9,
          100 * 76 * 512 * N / ms / 1e9 / 36.9, ms * 1e3 / (N / 1000)))
 sv = st.numpy()
 print("  checksums: sum(stats) = %.12e, sum|stats| = %.12e, X[::100003] . 1 = %.12e"
