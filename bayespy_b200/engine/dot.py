@@ -138,16 +138,21 @@ class SumMultiply(Deterministic):
             for j in range(npl_par, 0, -1):
                 if parent.plates[npl_par - j] != 1:
                     pk.append(("p", j))
-            dk = self._keys(self.in_keys[index], ind)
+            dk_all = self._keys(self.in_keys[index], ind)
+            want = tuple(parent.dims[ind])
+            # a variable axis the parent holds with length 1 under a longer key is summed like a plate
+            bcast = [n == 1 and self.key_size[k[1]] != 1 for k, n in zip(dk_all, want)]
+            dk = [k for k, b in zip(dk_all, bcast) if not b]
             # plates of this node that are summed: axes no operand spans still count (multiplier)
             sizes = {("p", j): self.plates[npl_self - j] for j in range(1, npl_self + 1) if ("p", j) not in pk}
+            sizes.update({k: self.key_size[k[1]] for k, b in zip(dk_all, bcast) if b})
             r = D.sum_product(ops, ksets, pk + dk, sizes=sizes)
             # restore unit plate axes and force explicit variable dims
             pshape = tuple(r.shape[:len(pk)])
             it = iter(pshape)
             full_pl = tuple(next(it) if parent.plates[a] != 1 else 1 for a in range(npl_par))
-            r = r.reshape(full_pl + tuple(r.shape[len(pk):]))
-            want = tuple(parent.dims[ind])
+            itd = iter(tuple(r.shape[len(pk):]))
+            r = r.reshape(full_pl + tuple(1 if b else next(itd) for b in bcast))
             if tuple(r.shape[npl_par:]) != want:
                 r = r.broadcast_to(full_pl + want).contiguous()
             msg.append(r)

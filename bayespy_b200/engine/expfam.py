@@ -84,6 +84,9 @@ class ExponentialFamily(Node):
 
     @u.setter
     def u(self, value):
+        if isinstance(value, (list, tuple)):
+            # host arrays handed in from outside become device arrays here, once
+            value = [D.asarray(v) if isinstance(v, (np.ndarray, np.generic, float, int)) else v for v in value]
         self._u = value
         self._version = getattr(self, "_version", 0) + 1
 

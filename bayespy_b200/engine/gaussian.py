@@ -67,6 +67,20 @@ class FactoredSecondMoment:
     def __array__(self, dtype=None, copy=None):
         return self.numpy()
 
+    # array protocol of the dense form, for callers that treat the moment as an array
+    @property
+    def T(self): return self.materialize().T
+    @property
+    def ndim(self): return len(self.shape)
+    def __getitem__(self, index): return self.materialize()[index]
+    def __add__(self, o): return self.materialize() + dense(o)
+    def __radd__(self, o): return dense(o) + self.materialize()
+    def __sub__(self, o): return self.materialize() - dense(o)
+    def __rsub__(self, o): return dense(o) - self.materialize()
+    def __mul__(self, o): return self.materialize() * dense(o)
+    def __rmul__(self, o): return dense(o) * self.materialize()
+    def __neg__(self): return -self.materialize()
+
 
 def dense(x):
     return x.materialize() if hasattr(x, "materialize") else x
@@ -298,7 +312,7 @@ class GaussianARDDistribution(Distribution):
         return tuple(plates) + self.shape
 
     def plates_from_parent(self, index, plates):
-        return tuple(plates[:len(plates) - self.ndim]) if self.ndim else tuple(plates)
+        return tuple(plates[:max(len(plates) - self.ndim, 0)]) if self.ndim else tuple(plates)
 
     def compute_weights_to_parent(self, index, weights):
         w = np.asarray(weights)
