@@ -10,7 +10,7 @@ import numpy as np
 
 from .. import darray as D
 from .gaussian import dense, ensure_gaussian
-from .node import Deterministic, Node
+from .node import Constant, Deterministic, Node
 
 
 def _parse(args):
@@ -44,7 +44,17 @@ class SumMultiply(Deterministic):
         if iterator_axis is not None:
             raise NotImplementedError("Iterator axis not implemented yet")
         nodes, keysets, keys_out = _parse(args)
-        nodes = [ensure_gaussian(n, len(k)) for n, k in zip(nodes, keysets)]
+        # inputs and output are Gaussian unless at least one parent is Gaussian-gamma; then fixed arrays stay plain
+        # values (no scale of their own) and Gaussian parents count with tau = 1 (dot.py:177-222)
+        self.gaussian_gamma = any(isinstance(n, Node) and n.moment_kind == "gaussian_gamma" for n in nodes)
+        self.is_constant = [not isinstance(n, Node) or isinstance(n, Constant) for n in nodes]
+        if self.gaussian_gamma:
+            from .gaussian_gamma import ensure_gaussian_gamma
+            self.moment_kind = "gaussian_gamma"
+            nodes = [ensure_gaussian(n, len(k)) if c else ensure_gaussian_gamma(n, len(k))
+                     for n, k, c in zip(nodes, keysets, self.is_constant)]
+        else:
+            nodes = [ensure_gaussian(n, len(k)) for n, k in zip(nodes, keysets)]
         full = []
         for ks in keysets:
             for k in ks:
@@ -76,7 +86,8 @@ class SumMultiply(Deterministic):
         self.in_keys = keysets
         self.out_keys = keys_out
         shape = tuple(size[k] for k in keys_out)
-        super().__init__(*nodes, dims=(shape, shape + shape), plates=plates, name=name)
+        dims = (shape, shape + shape, (), ()) if self.gaussian_gamma else (shape, shape + shape)
+        super().__init__(*nodes, dims=dims, plates=plates, name=name)
 
     # -- label helpers: plate axis j (counted from the right, 1-based) -> ('p', j)
     @staticmethod
@@ -106,6 +117,13 @@ class SumMultiply(Deterministic):
                 npl = max(npl, a.ndim - (ind + 1) * len(ks))
             out_keys = self._plate_keys(npl) + self._keys(self.out_keys, ind)
             out.append(D.sum_product(ops, ksets, out_keys))
+        if self.gaussian_gamma:
+            # <tau> and <log tau> of the product: the scales multiply (dot.py:406-413)
+            tau, logtau = D.asarray(1.0), D.asarray(0.0)
+            for u, c in zip(u_parents, self.is_constant):
+                if not c:
+                    tau, logtau = D.mul(tau, u[2]), D.add(logtau, u[3])
+            out += [tau, logtau]
         return out
 
     def message_to_parent(self, index):
@@ -118,6 +136,24 @@ class SumMultiply(Deterministic):
         npl_self = len(self.plates)
         npl_par = len(parent.plates)
         msg = []
+        for ind in range(2, 4 if self.gaussian_gamma and not self.is_constant[index] else 2):
+            # the scale part: m2 times the other parents' <tau>, m3 as it is, summed to the parent's plates (dot.py:617-631)
+            if m[ind] is None:
+                msg.append(None)
+                continue
+            ops, ksets = [D.asarray(m[ind])], [self._plate_keys(D.asarray(m[ind]).ndim)]
+            if ind == 2:
+                for k, u in enumerate(u_parents):
+                    if k != index and not self.is_constant[k]:
+                        a = D.asarray(u[2])
+                        ops.append(a)
+                        ksets.append(self._plate_keys(a.ndim))
+            pk = [("p", j) for j in range(npl_par, 0, -1) if parent.plates[npl_par - j] != 1]
+            sizes = {("p", j): self.plates[npl_self - j] for j in range(1, npl_self + 1) if ("p", j) not in pk}
+            r = D.sum_product(ops, ksets, pk, sizes=sizes)
+            it = iter(tuple(r.shape))
+            msg.append(r.reshape(tuple(next(it) if parent.plates[a] != 1 else 1 for a in range(npl_par))))
+        scale_msgs, msg = msg, []
         for ind in range(2):
             if m[ind] is None:
                 msg.append(None)
@@ -156,7 +192,7 @@ class SumMultiply(Deterministic):
             if tuple(r.shape[npl_par:]) != want:
                 r = r.broadcast_to(full_pl + want).contiguous()
             msg.append(r)
-        return msg
+        return msg + scale_msgs
 
 
 def Dot(*args, **kwargs):

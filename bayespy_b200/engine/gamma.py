@@ -11,7 +11,7 @@ from .. import darray as D
 from ..darray import DArray
 from .expfam import Distribution, ExponentialFamily
 from .gaussian import ensure_gamma
-from .node import Constant, Node
+from .node import Constant, Deterministic, Node
 
 
 def gamma_prior_constant(a):
@@ -21,6 +21,44 @@ def gamma_prior_constant(a):
         raise ValueError("Shape parameter must be positive")
     ad = D.asarray(a)
     return Constant("gamma_prior", [ad, D.gammaln(ad)], dims=((), ()), plates=a.shape, value=a)
+
+
+class GammaToDiagonalWishart(Deterministic):
+    """Gamma scalars whose last plate axis becomes the diagonal of a Wishart-like matrix: [diag(x), sum log x]
+    (gamma.py:337-397)."""
+    moment_kind = "wishart"
+
+    def __init__(self, alpha, name=""):
+        alpha = ensure_gamma(alpha)
+        if len(alpha.plates) == 0:
+            raise Exception("Gamma variable needs to have plates in order to be used as a diagonal Wishart.")
+        self.Dm = int(alpha.plates[-1])
+        super().__init__(alpha, dims=((self.Dm, self.Dm), ()), name=name)
+
+    def _plates_to_parent(self, index):
+        return tuple(self.plates) + (self.Dm,)
+
+    def _plates_from_parent(self, index):
+        return tuple(self.parents[index].plates[:-1])
+
+    def _map_parent_axes(self, index, values):
+        return tuple(values[:-1])
+
+    def _weights_to_parent(self, index, mask):
+        return np.asarray(mask)[..., np.newaxis]
+
+    def _compute_moments(self, u):
+        x = D.asarray(u[0]).broadcast_to(tuple(D.asarray(u[0]).shape[:-1]) + (self.Dm,))
+        out = DArray.zeros(tuple(x.shape) + (self.Dm,))
+        D.copy_into(out.diag_view(1), x)
+        lx = D.asarray(u[1])
+        return [out, D.reduce_to_shape(lx, tuple(lx.shape[:-1]) + (1,),
+                                       from_shape=tuple(lx.shape[:-1]) + (self.Dm,)).reshape(lx.shape[:-1])]
+
+    def _compute_message_to_parent(self, index, m, u):
+        m0 = None if m[0] is None else D.asarray(m[0]).diag_view(1)
+        m1 = None if m[1] is None else D.asarray(m[1]).add_trailing(1)
+        return [m0, m1]
 
 
 class GammaDistribution(Distribution):
@@ -107,6 +145,18 @@ class Gamma(ExponentialFamily):
         self.phi = self._canonical_phi(self._distribution.compute_phi_from_parents(u_a, u_b))
         u, g = self._distribution.compute_moments_and_cgf(self.phi)
         self._store(u, g, np.logical_not(self.observed))
+
+    def as_wishart(self, ndim=0):
+        """[x, log x] are the moments of a 0-dimensional Wishart variable as they stand (gamma.py:258-261, :399-430)."""
+        if ndim != 0:
+            raise NotImplementedError()
+        return self
+
+    def as_diagonal_wishart(self):
+        return GammaToDiagonalWishart(self, name=self.name + " as Wishart")
+
+    def diag(self):
+        return self.as_diagonal_wishart()
 
     def __str__(self):
         a = self.phi[1].numpy()

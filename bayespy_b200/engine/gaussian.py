@@ -438,8 +438,12 @@ class GaussianARD(_GaussianNode):
 
     def __init__(self, mu, alpha, ndim=None, shape=None, plates=None, name="", initialize=True, plates_multiplier=None):
         alpha = ensure_gamma(alpha)
+        scaled_mean = isinstance(mu, Node) and mu.moment_kind == "gaussian_gamma"
+        if scaled_mean and len(mu.dims[0]) != 0:
+            # the reference's converter has no ndim change for Gaussian-gamma moments either (gaussian.py:218-225)
+            raise NotImplementedError("A Gaussian-gamma mean of GaussianARD must be scalar (ndim=0) over its plates")
         if isinstance(mu, Node):
-            if mu.moment_kind != "gaussian":
+            if mu.moment_kind not in ("gaussian", "gaussian_gamma"):
                 raise ValueError("mu must be a Gaussian-like node")
             mu_nd = len(mu.dims[0])
             mu_full = tuple(mu.plates) + tuple(mu.dims[0])
@@ -464,7 +468,11 @@ class GaussianARD(_GaussianNode):
             mu = GaussianDimsToPlates(mu) if mu_nd > 0 else mu
         else:
             mu = gaussian_constant(mu, 0)
-        dist = GaussianARDDistribution(shape)
+        if scaled_mean:
+            from .gaussian_gamma import GaussianARDScaledMeanDistribution
+            dist = GaussianARDScaledMeanDistribution(shape)
+        else:
+            dist = GaussianARDDistribution(shape)
         super().__init__(mu, alpha, dims=(shape, shape + shape), distribution=dist, plates=plates,
                          name=name, initialize=initialize, plates_multiplier=plates_multiplier)
 
@@ -680,16 +688,20 @@ class Gaussian(_GaussianNode):
         Dm = Lambda.dims[0][-1]
         if isinstance(mu, Node) and hasattr(mu, "_to_gaussian"):
             mu = mu._to_gaussian()        # a Gaussian Markov chain as the mean: Gaussian vectors plated over time
+        dist = GaussianDistribution(Dm)
         if isinstance(mu, Node):
-            if mu.moment_kind != "gaussian" or tuple(mu.dims[0]) != (Dm,):
+            if mu.moment_kind not in ("gaussian", "gaussian_gamma") or tuple(mu.dims[0]) != (Dm,):
                 raise ValueError("Mean and precision have inconsistent shapes: {0} and {1}".format(
                     mu.dims, Lambda.dims))
+            if mu.moment_kind == "gaussian_gamma":
+                from .gaussian_gamma import GaussianScaledMeanDistribution
+                dist = GaussianScaledMeanDistribution(Dm)
         else:
             mu = gaussian_constant(mu, 1)
             if tuple(mu.dims[0]) != (Dm,):
                 raise ValueError("Mean and precision have inconsistent shapes: {0} and {1}".format(
                     mu.dims, Lambda.dims))
-        super().__init__(mu, Lambda, dims=((Dm,), (Dm, Dm)), distribution=GaussianDistribution(Dm),
+        super().__init__(mu, Lambda, dims=((Dm,), (Dm, Dm)), distribution=dist,
                          plates=plates, name=name, initialize=initialize, plates_multiplier=plates_multiplier)
 
     def initialize_from_parameters(self, mu, Lambda):

@@ -113,6 +113,18 @@ class Node:
             for i, p in enumerate(self.parents):
                 p._add_child(self, i)
 
+    # what the reference calls ``node._moments``: a tag naming the moment kind (engine/moments.py)
+    @property
+    def _moments(self):
+        if "_moments_tag" in self.__dict__:
+            return self.__dict__["_moments_tag"]
+        from . import moments
+        return moments.of(self)
+
+    @_moments.setter
+    def _moments(self, value):
+        self.__dict__["_moments_tag"] = value
+
     # ---- graph ------------------------------------------------------------------------------
     def _add_child(self, child, index):
         self.children.append((child, index))

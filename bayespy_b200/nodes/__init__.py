@@ -5,6 +5,7 @@ from ..engine.gaussian import GaussianARD                                     # 
 from ..engine.gamma import Gamma                                              # noqa: F401
 from ..engine.dot import SumMultiply, Dot                                     # noqa: F401
 from ..engine.gaussian import Gaussian                                        # noqa: F401
+from ..engine.gaussian_gamma import GaussianGamma                            # noqa: F401
 from ..engine.wishart import Wishart                                          # noqa: F401
 from ..engine.dirichlet import Dirichlet                                      # noqa: F401
 from ..engine.categorical import Categorical                                  # noqa: F401

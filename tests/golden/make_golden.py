@@ -912,8 +912,92 @@ def lssm_doc_rotated(name="lssm_doc_rotated"):
     save(name, **out)
 
 
+def gaussian_gamma_models(name="gaussian_gamma"):
+    """nodes/gaussian.py GaussianGamma: (a) a factor model whose loadings carry a per-row gamma scale, through
+    SumMultiply (Gaussian-gamma output) into an observed GaussianARD; (b) a Gaussian-gamma mean with unknown
+    mean / precision / rate under a Gaussian likelihood; (c) scalar (ndim=0) Gaussian-gamma variables; (d) a diagonal
+    Wishart made of gamma scalars; (e) rotate / translate of q."""
+    from bayespy.nodes import GaussianGamma
+    rs = np.random.RandomState(11)
+    out = {}
+    # (a)
+    M, N, K = 5, 30, 3
+    y = rs.randn(M, K) @ rs.randn(K, N) + 0.2 * rs.randn(M, N)
+    mask = rs.rand(M, N) < 0.9
+    b = Gamma(2.0, 2.0, plates=(M, 1), name="b")
+    W = GaussianGamma(np.zeros(K), np.identity(K), 3.0, b, plates=(M, 1), name="W")
+    X = GaussianARD(0, 1, shape=(K,), plates=(1, N), name="X")
+    Xi = rs.randn(1, N, K)
+    X.initialize_from_value(Xi)
+    F = SumMultiply("k,k->", W, X, name="F")
+    assert F.dims == ((), (), (), ())
+    tau = Gamma(1e-3, 1e-3, name="tau")
+    Y = GaussianARD(F, tau, name="Y")
+    Y.observe(y, mask=mask)
+    Q = VB(Y, W, X, tau, b)
+    Q.update(repeat=6, verbose=False, tol=0)
+    out.update(a_y=y, a_mask=mask, a_Xinit=Xi, a_L=Q.L[:6].copy())
+    for nm, nd in (("a_W", W), ("a_X", X), ("a_tau", tau), ("a_b", b)):
+        node_state(nm, nd, out)
+    for i, u in enumerate(F.get_moments()):
+        out["a_F_u%d" % i] = np.array(u, copy=True)
+    for nm, nd in (("a_lW", W), ("a_lX", X), ("a_ltau", tau), ("a_lb", b), ("a_lY", Y)):
+        out[nm] = nd.lower_bound_contribution()
+    # (b)
+    Dm, Nb = 3, 25
+    z = rs.randn(Nb, Dm) + np.array([1.0, -2.0, 0.5])
+    mu0 = Gaussian(np.zeros(Dm), 1e-2 * np.identity(Dm), name="mu0")
+    L0 = Wishart(Dm + 1.0, np.identity(Dm), name="L0")
+    bb = Gamma(1.5, 1.0, name="bb")
+    m = GaussianGamma(mu0, L0, 2.5, bb, name="m")
+    L1 = Wishart(Dm + 2.0, np.identity(Dm), name="L1")
+    Z = Gaussian(m, L1, plates=(Nb,), name="Z")
+    Z.observe(z)
+    Q = VB(Z, m, L1, mu0, L0, bb)
+    Q.update(repeat=5, verbose=False, tol=0)
+    out.update(b_z=z, b_L=Q.L[:5].copy())
+    for nm, nd in (("b_m", m), ("b_L1", L1), ("b_mu0", mu0), ("b_L0", L0), ("b_bb", bb)):
+        node_state(nm, nd, out)
+    # (c) scalars: GaussianGamma(ndim=0) as the mean of a GaussianARD
+    P = 4
+    yc = rs.randn(6, P) * 0.5 + np.arange(P)
+    lam = Gamma(2.0, 1.0, plates=(P,), name="lam")
+    bc = Gamma(1.0, 1.0, plates=(P,), name="bc")
+    mc = GaussianGamma(np.zeros(P), lam.as_wishart(ndim=0), 1.5 * np.ones(P), bc, ndim=0, name="mc")
+    assert mc.plates == (P,) and mc.dims == ((), (), (), ())
+    al = Gamma(1e-2, 1e-2, plates=(6, 1), name="al")
+    Yc = GaussianARD(mc, al, name="Yc")
+    assert Yc.plates == (6, P)
+    Yc.observe(yc)
+    Q = VB(Yc, mc, lam, bc, al)
+    Q.update(repeat=5, verbose=False, tol=0)
+    out.update(c_y=yc, c_L=Q.L[:5].copy())
+    for nm, nd in (("c_mc", mc), ("c_lam", lam), ("c_bc", bc), ("c_al", al)):
+        node_state(nm, nd, out)
+    # (d) diagonal Wishart from gamma scalars as the precision of a Gaussian
+    g = Gamma(1e-2, 1e-2, plates=(Dm,), name="g")
+    Zd = Gaussian(np.zeros(Dm), g.diag(), plates=(Nb,), name="Zd")
+    Zd.observe(z)
+    Q = VB(Zd, g)
+    Q.update(repeat=2, verbose=False, tol=0)
+    out.update(d_L=Q.L[:2].copy())
+    node_state("d_g", g, out)
+    for i, u in enumerate(g.diag().get_moments()):
+        out["d_W_u%d" % i] = np.array(u, copy=True)
+    # (e) rotate and translate a Gaussian-gamma posterior
+    R = rs.randn(Dm, Dm)
+    bvec = rs.randn(Dm)
+    m.rotate(R)
+    node_state("e_rot", m, out)
+    m.translate(bvec)
+    node_state("e_tra", m, out)
+    out.update(e_R=R, e_b=bvec, e_loc=m.get_gaussian_location())
+    # (get_gaussian_mean_and_variance raises AttributeError in the reference: it reads self.ndim, which the node lacks)
+    save(name, **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["quickstart", "pca", "linalg", "summul", "dist", "gmm", "gmc", "rot", "dot", "mixard", "gmcplates", "gmcvarying", "pcabench", "pcamasked64", "take", "gate", "lssmrot", "gmcmixing", "gradients", "lda", "slice"]
+    which = sys.argv[1:] or ["quickstart", "pca", "linalg", "summul", "dist", "gmm", "gmc", "rot", "dot", "mixard", "gmcplates", "gmcvarying", "pcabench", "pcamasked64", "take", "gate", "lssmrot", "gmcmixing", "gradients", "lda", "slice", "gg"]
     if "quickstart" in which:
         quickstart()
     if "pca" in which:
@@ -954,6 +1038,8 @@ if __name__ == "__main__":
         lssm_switching()
     if "take" in which:
         take_models()
+    if "gg" in which:
+        gaussian_gamma_models()
     if "pcamasked64" in which:
         pca("pca_masked_64x16", 64, 300, 16, mask_p=0.8, iters=4)
     if "pcabench" in which:
