@@ -1,8 +1,10 @@
-"""Gaussian Markov chain node on device (nodes/gaussian_markov_chain.py:270-927 without input signals):
+"""Gaussian Markov chain node on device (nodes/gaussian_markov_chain.py:270-927):
 
-    x_0 ~ N(mu, Lambda^-1),   x_n ~ N(A_{n-1} x_{n-1}, diag(nu_{n-1})^-1),  n = 1..N-1
+    x_0 ~ N(mu, Lambda^-1),   x_n ~ N(A_{n-1} [x_{n-1}; z_{n-1}], diag(nu_{n-1})^-1),  n = 1..N-1
 
-with time-invariant (A plates (..., 1, D) or (D,)) or per-step (plates (..., N-1, D)) dynamics and independent
+with optional input signals z (a Gaussian-like parent with plates (..., N-1 | 1) and K-dimensional values; the rows of A
+then have length D + K), dynamics that may carry a gamma scale of their own (A a Gaussian-gamma node),
+time-invariant (A plates (..., 1, D) or (D,)) or per-step (plates (..., N-1, D)) dynamics and independent
 chains over leading plates, in the reference's plate layout.
 
 Moments u = [<x_n> (N,D), <x_n x_n^T> (N,D,D), <x_n x_{n+1}^T> (N-1,D,D)]; the time axis is part of the
@@ -170,13 +172,16 @@ class GaussianMarkovChainDistribution(Distribution):
     are summed over time here and carry a time axis of length 1 (so that no (N-1, D, D, D) array is ever formed);
     otherwise they keep the time axis and the generic plate reduction (node.py:570-655) does what is left."""
 
-    def __init__(self, N, Dm, plates=(), TA=1, Tn=1, plain=True):
+    def __init__(self, N, Dm, plates=(), TA=1, Tn=1, plain=True, K=0):
         self.N, self.D = int(N), int(Dm)
         self.plates = tuple(int(p) for p in plates)
         self.TA, self.Tn = int(TA), int(Tn)
         self.static = self.TA == 1 and self.Tn == 1
+        # input signals (:276, :485-540): x_n = A [x_{n-1}; z_{n-1}] + noise with rows of A of length E = D + K
+        self.K = int(K)
+        self.E = self.D + self.K
         # ``plain``: the dynamics parents have exactly the plates (D,) (no explicit time axis of length one either)
-        self._single = _SingleChainDistribution(N, Dm) if (not self.plates and self.static and plain) else None
+        self._single = _SingleChainDistribution(N, Dm) if (not self.plates and self.static and plain and not K) else None
 
     def _t_msg(self):
         return 1 if self.static else self.N - 1
@@ -185,17 +190,23 @@ class GaussianMarkovChainDistribution(Distribution):
     def plates_to_parent(self, index, plates):
         if self._single is not None:
             return self._single.plates_to_parent(index, plates)
+        if index == 4:
+            return tuple(plates) + (self.N - 1,)
         return tuple(plates) if index < 2 else tuple(plates) + (self._t_msg(), self.D)
 
     def plates_from_parent(self, index, plates):
         if index < 2:
             return tuple(plates)
+        if index == 4:
+            return tuple(plates[:-1])
         return tuple(plates[:-2])
 
     def compute_weights_to_parent(self, index, weights):
         if self._single is not None:
             return self._single.compute_weights_to_parent(index, weights)
         w = np.asarray(weights)
+        if index == 4:
+            return w.reshape(w.shape + (1,))
         return w if index < 2 else w.reshape(w.shape + (1, 1))
 
     def _parents(self, u_mu, u_Lambda, u_A, u_nu):
@@ -213,8 +224,8 @@ class GaussianMarkovChainDistribution(Distribution):
             if A.ndim == 1:
                 A, AA = A.add_leading(1), AA.add_leading(1)
             # the state plate may be stored compressed (a prior shared by all rows)
-            A = A.broadcast_to(tuple(A.shape[:-2]) + (Dm, Dm))
-            AA = AA.broadcast_to(tuple(AA.shape[:-3]) + (Dm, Dm, Dm))
+            A = A.broadcast_to(tuple(A.shape[:-2]) + (Dm, self.E))
+            AA = AA.broadcast_to(tuple(AA.shape[:-3]) + (Dm, self.E, self.E))
             if A.ndim == 2:                                                   # plates (D,): no time axis
                 A, AA = A.add_leading(1), AA.add_leading(1)
             if A.shape[-3] not in (1, self.N - 1):
@@ -233,13 +244,64 @@ class GaussianMarkovChainDistribution(Distribution):
                 raise ValueError("The second last plate of the innovation precision should have length one or N-1")
         return mu, mumu, Lam, logdetL, A, AA, nu, lognu
 
+    def _dynamics_scale(self, u_A):
+        """(<tau>, <log tau>) of a Gaussian-gamma dynamics parent, plates PA + (TA, D) like nu; None for a Gaussian one.
+        With it, u_A[0] = <tau a>, u_A[1] = <tau a a^T> and the innovation precision of row d is nu_d tau_d
+        (WrapToGaussianGamma, gaussian.py:2339-2348)."""
+        if u_A is None or len(u_A) < 4:
+            return None
+        t, lt = D.asarray(u_A[2]), D.asarray(u_A[3])
+        if t.ndim == 0:
+            t, lt = t.reshape((1, 1)), lt.reshape((1, 1))
+        elif t.ndim == 1:
+            t, lt = t.reshape((1, t.shape[0])), lt.reshape((1, lt.shape[0]))
+        return t, lt
+
+    def _inputs(self, u_inputs):
+        """z: Pz + (Tz, K), zz: Pz + (Tz, K, K) of the input-signal parent (None without inputs)."""
+        if not self.K:
+            return None, None
+        z, zz = D.asarray(u_inputs[0][0]), dense(u_inputs[0][1])
+        if z.ndim == 1:
+            z, zz = z.add_leading(1), zz.add_leading(1)
+        return z, zz
+
+    def _regressor_moments(self, u, z, zz):
+        """<c_n x_{n+1}^T> (P+(N-1, E, D)) and <c_n c_n^T> (P+(N-1, E, E)) of the regressor c_n = [x_n; z_n]: the chain's
+        own moments when there are no inputs, else the blocks of :485-500 placed side by side."""
+        N, Dm, P, E = self.N, self.D, self.plates, self.E
+        npl = len(P)
+        x, xx, xpxn = u
+        xx_head = xx.slice_axis(npl, 0, N - 1)
+        if not self.K:
+            return xpxn, xx_head
+        xh = x.slice_axis(npl, 0, N - 1)                                  # x_n,     P + (N-1, D)
+        xn = x.slice_axis(npl, 1, N)                                      # x_{n+1}
+        cxn = DArray.zeros(P + (N - 1, E, Dm))
+        D.copy_into(cxn.slice_axis(npl + 1, 0, Dm), xpxn)
+        D.copy_into(cxn.slice_axis(npl + 1, Dm, E), D.mul(z.add_trailing(1), xn.expand_dims(-2)))
+        cc = DArray.zeros(P + (N - 1, E, E))
+        top = cc.slice_axis(npl + 1, 0, Dm)
+        bot = cc.slice_axis(npl + 1, Dm, E)
+        xz = D.mul(xh.add_trailing(1), z.expand_dims(-2))                 # x_n z_n^T,  (.., N-1, D, K)
+        D.copy_into(top.slice_axis(npl + 2, 0, Dm), xx_head)
+        D.copy_into(top.slice_axis(npl + 2, Dm, E), xz)
+        D.copy_into(bot.slice_axis(npl + 2, 0, Dm), xz.swap_last2())
+        D.copy_into(bot.slice_axis(npl + 2, Dm, E), zz)
+        return cxn, cc
+
     # -- natural parameters (gaussian_markov_chain.py:542-627)
-    def compute_phi_from_parents(self, u_mu, u_Lambda, u_A, u_nu, mask=True):
-        if self._single is not None:
+    def compute_phi_from_parents(self, u_mu, u_Lambda, u_A, u_nu, *u_inputs, mask=True):
+        if self._single is not None and len(u_A) < 4:
             return self._single.compute_phi_from_parents(u_mu, u_Lambda, u_A, u_nu, mask=mask)
         N, Dm, P = self.N, self.D, self.plates
         npl = len(P)
-        mu, _, Lam, _, A, AA, nu, _ = self._parents(u_mu, u_Lambda, u_A, u_nu)
+        mu, _, Lam, _, A_full, AA_full, nu, _ = self._parents(u_mu, u_Lambda, u_A, u_nu)
+        # the state block of the dynamics
+        A = A_full.slice_axis(A_full.ndim - 1, 0, Dm)
+        AA = AA_full.slice_axis(AA_full.ndim - 2, 0, Dm).slice_axis(AA_full.ndim - 1, 0, Dm)
+        scale = self._dynamics_scale(u_A)
+        nu_diag = nu if scale is None else D.mul(nu, scale[0])
         pk = _pk(npl)
         # x_0: phi0[..., 0, :] = <Lambda> <mu>,  phi1[..., 0, :, :] = -1/2 <Lambda>
         Lmu = D.sum_product([Lam, mu], [pk[npl - (Lam.ndim - 2):] + ["i", "j"], pk[npl - (mu.ndim - 1):] + ["j"]], pk + ["i"])
@@ -252,7 +314,7 @@ class GaussianMarkovChainDistribution(Distribution):
         if N > 1:
             # blocks n >= 1: -1/2 diag(nu_{n-1});  blocks n <= N-2: -1/2 sum_d nu_{n,d} <a_{n,d} a_{n,d}^T>
             tail = phi1.slice_axis(npl, 1, N)
-            D._ew("AFFINE", tail.diag_view(1).shape, tail.diag_view(1), [nu], alpha=-0.5, beta=0.0)
+            D._ew("AFFINE", tail.diag_view(1).shape, tail.diag_view(1), [nu_diag], alpha=-0.5, beta=0.0)
             nk, ak = nu.ndim - 2, AA.ndim - 4
             S = D.sum_product([nu, AA], [pk[npl - nk:] + ["n", "d"], pk[npl - ak:] + ["n", "d", "i", "j"]],
                               pk + ["n", "i", "j"], scale=-0.5)
@@ -261,14 +323,30 @@ class GaussianMarkovChainDistribution(Distribution):
             # super-diagonal blocks (sum of super and sub): phi2[..., n, i, j] = nu_{n,j} <A_n>[j, i]
             nuA_T = D.mul(A, nu.add_trailing(1)).swap_last2()
             D.copy_into(phi2, nuA_T)
+            if self.K:
+                # effect of the input signals (:608-616): phi0[n+1] += nu B z_n,  phi0[n] -= sum_d nu_d <a_d b_d^T> z_n
+                z, _ = self._inputs(u_inputs)
+                E = self.E
+                B = A_full.slice_axis(A_full.ndim - 1, Dm, E)
+                AB = AA_full.slice_axis(AA_full.ndim - 2, 0, Dm).slice_axis(AA_full.ndim - 1, Dm, E)
+                kn, ka, kz = pk[npl - nk:], pk[npl - ak:], pk[npl - (z.ndim - 2):]
+                t1 = D.sum_product([nu, B, z], [kn + ["n", "d"], ka + ["n", "d", "k"], kz + ["n", "k"]], pk + ["n", "d"])
+                t2 = D.sum_product([nu, AB, z], [kn + ["n", "d"], ka + ["n", "d", "i", "k"], kz + ["n", "k"]],
+                                   pk + ["n", "i"], scale=-1.0)
+                nxt, cur = phi0.slice_axis(npl, 1, N), phi0.slice_axis(npl, 0, N - 1)
+                D._ew("ADD", nxt.shape, nxt, [nxt, t1])
+                D._ew("ADD", cur.shape, cur, [cur, t2])
         return [phi0, phi1, phi2]
 
     # -- E[log normaliser of the prior] (:251-267, :629-657)
-    def compute_cgf_from_parents(self, u_mu, u_Lambda, u_A, u_nu):
-        if self._single is not None:
+    def compute_cgf_from_parents(self, u_mu, u_Lambda, u_A, u_nu, *u_inputs):
+        if self._single is not None and len(u_A) < 4:
             return self._single.compute_cgf_from_parents(u_mu, u_Lambda, u_A, u_nu)
         npl = len(self.plates)
-        _, mumu, Lam, logdetL, _, _, _, lognu = self._parents(u_mu, u_Lambda, u_A, u_nu)
+        _, mumu, Lam, logdetL, _, AA_full, nu, lognu = self._parents(u_mu, u_Lambda, u_A, u_nu)
+        scale = self._dynamics_scale(u_A)
+        if scale is not None:
+            lognu = D.add(lognu, scale[1])
         pk = _pk(npl)
         kL, km = pk[npl - (Lam.ndim - 2):], pk[npl - (mumu.ndim - 2):]
         out_pl = pk[npl - max(Lam.ndim - 2, mumu.ndim - 2):]
@@ -277,7 +355,18 @@ class GaussianMarkovChainDistribution(Distribution):
         kn = pk[npl - (lognu.ndim - 2):]
         per_step = 0.5 * ((self.N - 1) if lognu.shape[-2] == 1 else 1.0)      # a time-invariant nu counts N-1 times
         s = D.sum_product([lognu], [kn + ["n", "d"]], kn, scale=per_step)
-        return D.add(g, s)
+        g = D.add(g, s)
+        if self.K:
+            # -1/2 sum_n sum_d nu_d tr(<b_d b_d^T> <z_n z_n^T>)  (:638-655); time-invariant factors count N-1 times
+            _, zz = self._inputs(u_inputs)
+            Dm, E = self.D, self.E
+            BB = AA_full.slice_axis(AA_full.ndim - 2, Dm, E).slice_axis(AA_full.ndim - 1, Dm, E)
+            kn, ka, kz = pk[npl - (nu.ndim - 2):], pk[npl - (BB.ndim - 4):], pk[npl - (zz.ndim - 3):]
+            out_pl = max((kn, ka, kz), key=len)
+            gi = D.sum_product([nu, BB, zz], [kn + ["n", "d"], ka + ["n", "d", "k", "l"], kz + ["n", "k", "l"]],
+                               out_pl, scale=-0.5, sizes={"n": self.N - 1})
+            g = D.add(g, gi)
+        return g
 
     # -- smoother (:89-123)
     def compute_moments_and_cgf(self, phi, mask=True):
@@ -315,14 +404,17 @@ class GaussianMarkovChainDistribution(Distribution):
         return [D.asarray(x), D.asarray(u1), D.asarray(u2)], -0.5 * self.N * self.D * LOG2PI
 
     # -- messages (:443-527 combined with gaussian.py:2351-2371 / :2496-2522)
-    def compute_message_to_parent(self, parent, index, u, u_mu, u_Lambda, u_A, u_nu):
-        if self._single is not None:
+    def compute_message_to_parent(self, parent, index, u, u_mu, u_Lambda, u_A, u_nu, *u_inputs):
+        gg_dynamics = getattr(parent, "moment_kind", None) == "gaussian_gamma" if index == 2 else \
+            (u_A is not None and len(u_A) >= 4)
+        if self._single is not None and not gg_dynamics:
             return self._single.compute_message_to_parent(parent, index, u, u_mu, u_Lambda, u_A, u_nu)
         N, Dm, P = self.N, self.D, self.plates
         npl = len(P)
         pk = _pk(npl)
         x, xx, xpxn = u
         mu, mumu, Lam, _, A, AA, nu, _ = self._parents(u_mu, u_Lambda, u_A, u_nu)
+        scale = self._dynamics_scale(u_A)
         if index in (0, 1):
             x0 = x.slice_axis(npl, 0, 1).reshape(P + (Dm,))
             x0x0 = xx.slice_axis(npl, 0, 1).reshape(P + (Dm, Dm))
@@ -335,7 +427,23 @@ class GaussianMarkovChainDistribution(Distribution):
             return [D.mul(t, -0.5), D.asarray(0.5)]
         if N < 2:
             return [None, None]
-        xx_head = xx.slice_axis(npl, 0, N - 1)                          # <x_n x_n^T>, n <= N-2
+        z, zz = self._inputs(u_inputs) if index != 4 else (None, None)
+        if index == 4:
+            # to the input signals (:504-527): [sum_d nu_d b_d x_{n+1,d} - sum_d nu_d <b_d a_d^T> x_n, -1/2 sum_d nu_d <b_d b_d^T>]
+            E = self.E
+            B = A.slice_axis(A.ndim - 1, Dm, E)
+            AB = AA.slice_axis(AA.ndim - 2, 0, Dm).slice_axis(AA.ndim - 1, Dm, E)
+            BB = AA.slice_axis(AA.ndim - 2, Dm, E).slice_axis(AA.ndim - 1, Dm, E)
+            kn, ka = pk[npl - (nu.ndim - 2):], pk[npl - (A.ndim - 3):]
+            xn, xh = x.slice_axis(npl, 1, N), x.slice_axis(npl, 0, N - 1)
+            a = D.sum_product([nu, B, xn], [kn + ["n", "d"], ka + ["n", "d", "k"], pk + ["n", "d"]], pk + ["n", "k"])
+            b = D.sum_product([nu, AB, xh], [kn + ["n", "d"], ka + ["n", "d", "i", "k"], pk + ["n", "i"]], pk + ["n", "k"])
+            out_pl = max((kn, ka), key=len)
+            m1 = D.sum_product([nu, BB], [kn + ["n", "d"], ka + ["n", "d", "k", "l"]], out_pl + ["n", "k", "l"], scale=-0.5)
+            return [D.sub(a, b), m1]
+        # moments of the regressor c_n = [x_n; z_n] in place of the chain's own (identical without inputs)
+        xpxn, xx_head = self._regressor_moments(u, z, zz)
+        tau_A = None if scale is None else scale[0]
         if self.static:
             # time sums first (plates kept, time axis of length 1): nothing of size (N-1, D, D, D) is formed
             t1 = ["t"]
@@ -345,10 +453,16 @@ class GaussianMarkovChainDistribution(Distribution):
                 # to a_d: [nu_d sum_n <x_{n+1,d} x_n>, -1/2 nu_d sum_n <x_n x_n^T>]   plates P + (1, D)
                 m0 = D.mul(Sxpxn.swap_last2(), nu.add_trailing(1))
                 m1 = D.mul(D.mul(Sxx_head.expand_dims(-3), nu.add_trailing(2)), -0.5)
+                if gg_dynamics:
+                    # the scale part of the message to Gaussian-gamma dynamics: [-1/2 nu_d sum_n <x_{n+1,d}^2>, (N-1)/2]
+                    dxx = D.sum_product([xx.slice_axis(npl, 1, N).diag_view(1)], [pk + ["n", "d"]], pk + t1 + ["d"], scale=-0.5)
+                    return [m0, m1, D.mul(dxx, nu), DArray.full(P + (1, Dm), 0.5 * (N - 1))]
                 return [m0, m1]
             if index == 3:
                 ka = pk[npl - (A.ndim - 3):]
                 dxx = D.sum_product([xx.slice_axis(npl, 1, N).diag_view(1)], [pk + ["n", "d"]], pk + t1 + ["d"], scale=-0.5)
+                if tau_A is not None:
+                    dxx = D.mul(dxx, tau_A)
                 a = D.sum_product([Sxpxn, A], [pk + t1 + ["i", "d"], ka + t1 + ["d", "i"]], pk + t1 + ["d"])
                 b = D.sum_product([Sxx_head, AA], [pk + t1 + ["i", "j"], ka + t1 + ["d", "i", "j"]], pk + t1 + ["d"], scale=-0.5)
                 return [D.add(D.add(dxx, a), b), DArray.full(P + (1, Dm), 0.5 * (N - 1))]
@@ -357,10 +471,15 @@ class GaussianMarkovChainDistribution(Distribution):
         if index == 2:
             m0 = D.mul(xpxn.swap_last2(), nu.add_trailing(1))                                   # nu_{n,d} <x_{n+1,d} x_n>
             m1 = D.mul(D.mul(xx_head.expand_dims(-3), nu.add_trailing(2)), -0.5)                # -1/2 nu_{n,d} <x_n x_n^T>
+            if gg_dynamics:
+                dxx = D.mul(xx.slice_axis(npl, 1, N).diag_view(1), -0.5)
+                return [m0, m1, D.mul(dxx, nu), DArray.full(P + (N - 1, Dm), 0.5)]
             return [m0, m1]
         if index == 3:
             ka = pk[npl - (A.ndim - 3):]
             dxx = D.mul(xx.slice_axis(npl, 1, N).diag_view(1), -0.5)
+            if tau_A is not None:
+                dxx = D.mul(dxx, tau_A)
             a = D.sum_product([xpxn, A], [pk + ["n", "i", "d"], ka + ["n", "d", "i"]], pk + ["n", "d"])
             b = D.sum_product([xx_head, AA], [pk + ["n", "i", "j"], ka + ["n", "d", "i", "j"]], pk + ["n", "d"], scale=-0.5)
             return [D.add(D.add(dxx, a), b), DArray.full(P + (N - 1, Dm), 0.5)]
@@ -372,21 +491,30 @@ class GaussianMarkovChain(ExponentialFamily):
     moment_kind = "gaussian_markov_chain"
 
     def __init__(self, mu, Lambda, A, nu, n=None, inputs=None, plates=None, name="", initialize=True):
-        if inputs is not None:
-            raise NotImplementedError("Input signals are not supported yet")
         Lambda = ensure_wishart(Lambda)
         Dm = Lambda.dims[0][-1]
         mu = ensure_gaussian(mu, 1)
-        A = ensure_gaussian(A, 1)
+        # the dynamics may carry a gamma scale of their own (a Gaussian-gamma node, gaussian_markov_chain.py:817)
+        if not (isinstance(A, Node) and A.moment_kind == "gaussian_gamma"):
+            A = ensure_gaussian(A, 1)
         nu = ensure_gamma(nu)
-        if tuple(A.dims[0]) != (Dm,) or tuple(A.plates[-1:]) != (Dm,):
+        K = 0
+        if inputs is not None:
+            inputs = ensure_gaussian(inputs, 1)
+            if len(inputs.dims[0]) != 1:
+                raise ValueError("Input signals have wrong dimensionality")
+            K = int(inputs.dims[0][0])
+        if tuple(A.dims[0]) != (Dm + K,):
+            raise ValueError("Dynamics matrix has wrong dimensionality: rows of length %d expected" % (Dm + K))
+        if tuple(A.plates[-1:]) != (Dm,):
             raise ValueError("Dynamics matrix should have a last plate equal to the dimensionality of the system: "
                              "plates (..., N-1 or 1, D), shape (D,)")
         # time extents of the dynamics (gaussian_markov_chain.py:840-880): the second-last plate of A / nu
         TA = int(A.plates[-2]) if len(A.plates) >= 2 else 1
         Tn = int(nu.plates[-2]) if len(nu.plates) >= 2 else 1
-        n_parents = max(TA, Tn)
-        if TA != 1 and Tn != 1 and TA != Tn:
+        Tz = int(inputs.plates[-1]) if inputs is not None and len(inputs.plates) >= 1 else 1
+        n_parents = max(TA, Tn, Tz)
+        if len({t for t in (TA, Tn, Tz) if t != 1}) > 1:
             raise ValueError("Plates of parents are giving different number of time instances")
         if n is None:
             if n_parents == 1:
@@ -399,7 +527,7 @@ class GaussianMarkovChain(ExponentialFamily):
         self.N, self.D = int(n), int(Dm)
         from .node import broadcast_plates
         chain_plates = broadcast_plates(tuple(mu.plates), tuple(Lambda.plates), tuple(A.plates[:-2]),
-                                        tuple(nu.plates[:-2]))
+                                        tuple(nu.plates[:-2]), tuple(inputs.plates[:-1]) if inputs is not None else ())
         if plates is not None:
             plates = tuple(int(p) for p in plates)
             chain_plates = broadcast_plates(chain_plates, plates)
@@ -407,8 +535,10 @@ class GaussianMarkovChain(ExponentialFamily):
                 raise ValueError("The plates %s of the parents are not broadcastable to the given plates %s."
                                  % (chain_plates, plates))
         dist = GaussianMarkovChainDistribution(self.N, self.D, chain_plates, TA=TA, Tn=Tn,
-                                               plain=len(A.plates) == 1 and len(nu.plates) <= 1)
-        super().__init__(mu, Lambda, A, nu, dims=((self.N, Dm), (self.N, Dm, Dm), (self.N - 1, Dm, Dm)),
+                                               plain=len(A.plates) == 1 and len(nu.plates) <= 1 and
+                                               A.moment_kind == "gaussian", K=K)
+        parents = (mu, Lambda, A, nu) if inputs is None else (mu, Lambda, A, nu, inputs)
+        super().__init__(*parents, dims=((self.N, Dm), (self.N, Dm, Dm), (self.N - 1, Dm, Dm)),
                          distribution=dist, plates=chain_plates, name=name, initialize=initialize)
 
     def _to_gaussian(self):

@@ -996,8 +996,72 @@ def gaussian_gamma_models(name="gaussian_gamma"):
     save(name, **out)
 
 
+def lssm_inputs(name="lssm_inputs", M=4, N=25, D=2, K=2, P=3, iters=5):
+    """gaussian_markov_chain.py:485-540, :608-616, :638-655: a state-space model driven by input signals.  (a) known
+    inputs (an array), dynamics [A B] learned; (b) uncertain inputs (a Gaussian node that receives messages), per-chain
+    plates, a masked observation; (c) dynamics with a gamma scale of their own (a GaussianGamma node as A)."""
+    from bayespy.nodes import GaussianMarkovChain, GaussianGamma
+    rs = np.random.RandomState(17)
+    out = {}
+    # (a)
+    z = np.stack([np.sin(0.4 * np.arange(N - 1)), np.ones(N - 1)], axis=-1)           # (N-1, K)
+    x = np.zeros((N, D))
+    a_true = np.array([[0.8, -0.3], [0.3, 0.8]])
+    b_true = np.array([[1.0, 0.2], [0.0, -0.5]])
+    for n in range(N - 1):
+        x[n + 1] = a_true @ x[n] + b_true @ z[n] + 0.1 * rs.randn(D)
+    c = rs.randn(M, D)
+    y = c @ x.T + 0.2 * rs.randn(M, N)
+    alpha = Gamma(1e-3, 1e-3, plates=(D + K,), name="alpha")
+    A = GaussianARD(0, alpha, shape=(D + K,), plates=(D,), name="A")
+    X = GaussianMarkovChain(np.zeros(D), 1e-2 * np.identity(D), A, np.ones(D), inputs=z, n=N, name="X")
+    C = GaussianARD(0, 1e-2, shape=(D,), plates=(M, 1), name="C")
+    C_init = rs.randn(M, 1, D)
+    C.initialize_from_value(C_init)
+    F = SumMultiply("i,i", C, X, name="F")
+    tau = Gamma(1e-3, 1e-3, name="tau")
+    Y = GaussianARD(F, tau, name="Y")
+    Y.observe(y)
+    Q = VB(X, C, A, alpha, tau, Y)
+    Q.update(repeat=iters, verbose=False, tol=0)
+    out.update(a_z=z, a_y=y, a_Cinit=C_init, a_L=Q.L[:iters].copy())
+    for nm, nd in (("a_X", X), ("a_C", C), ("a_A", A), ("a_alpha", alpha), ("a_tau", tau)):
+        node_state(nm, nd, out)
+    # (b) uncertain inputs, chain plates
+    U_mean = rs.randn(P, N - 1, K)
+    U = GaussianARD(U_mean, 4.0, shape=(K,), plates=(P, N - 1), name="U")
+    A2 = GaussianARD(0, 1.0, shape=(D + K,), plates=(P, 1, D), name="A2")
+    A2_init = 0.3 * rs.randn(P, 1, D, D + K)
+    A2.initialize_from_value(A2_init)
+    nu2 = Gamma(2.0, 2.0, plates=(P, 1, D), name="nu2")
+    X2 = GaussianMarkovChain(np.zeros(D), np.identity(D), A2, nu2, inputs=U, name="X2")
+    assert X2.plates == (P,)
+    y2 = rs.randn(P, N, D)
+    mask2 = rs.rand(P, N) < 0.8
+    Y2 = Gaussian(X2, 5.0 * np.identity(D), name="Y2")
+    Y2.observe(y2, mask=mask2)
+    Q = VB(X2, A2, nu2, U, Y2)
+    Q.update(repeat=iters, verbose=False, tol=0)
+    out.update(b_Umean=U_mean, b_y=y2, b_mask=mask2, b_A2init=A2_init, b_L=Q.L[:iters].copy())
+    for nm, nd in (("b_X2", X2), ("b_A2", A2), ("b_nu2", nu2), ("b_U", U)):
+        node_state(nm, nd, out)
+    # (c) Gaussian-gamma dynamics
+    b3 = Gamma(2.0, 1.0, plates=(D,), name="b3")
+    A3 = GaussianGamma(np.zeros(D + K), np.identity(D + K), 2.0, b3, plates=(D,), name="A3")
+    X3 = GaussianMarkovChain(np.zeros(D), np.identity(D), A3, np.ones(D), inputs=z, n=N, name="X3")
+    Y3 = Gaussian(X3, 10.0 * np.identity(D), name="Y3")
+    y3 = x + 0.3 * rs.randn(N, D)
+    Y3.observe(y3)
+    Q = VB(X3, A3, b3, Y3)
+    Q.update(repeat=iters, verbose=False, tol=0)
+    out.update(c_y=y3, c_L=Q.L[:iters].copy())
+    for nm, nd in (("c_X3", X3), ("c_A3", A3), ("c_b3", b3)):
+        node_state(nm, nd, out)
+    save(name, **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["quickstart", "pca", "linalg", "summul", "dist", "gmm", "gmc", "rot", "dot", "mixard", "gmcplates", "gmcvarying", "pcabench", "pcamasked64", "take", "gate", "lssmrot", "gmcmixing", "gradients", "lda", "slice", "gg"]
+    which = sys.argv[1:] or ["quickstart", "pca", "linalg", "summul", "dist", "gmm", "gmc", "rot", "dot", "mixard", "gmcplates", "gmcvarying", "pcabench", "pcamasked64", "take", "gate", "lssmrot", "gmcmixing", "gradients", "lda", "slice", "gg", "gmcinputs"]
     if "quickstart" in which:
         quickstart()
     if "pca" in which:
@@ -1040,6 +1104,8 @@ if __name__ == "__main__":
         take_models()
     if "gg" in which:
         gaussian_gamma_models()
+    if "gmcinputs" in which:
+        lssm_inputs()
     if "pcamasked64" in which:
         pca("pca_masked_64x16", 64, 300, 16, mask_p=0.8, iters=4)
     if "pcabench" in which:

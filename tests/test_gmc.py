@@ -355,3 +355,81 @@ def test_switching_chain_matches_reference(backend):
     with pytest.raises(ValueError):
         SwitchingGaussianMarkovChain(np.zeros(Dm), np.identity(Dm), B, Categorical(np.ones(K + 1) / (K + 1), plates=(N - 1,)),
                                      np.ones(Dm))
+
+
+def _check_nodes(g, pairs, rtol=1e-7):
+    def same(a, ref, msg):
+        a, ref = np.broadcast_arrays(np.asarray(a), ref)       # either side may hold an axis in broadcast (unit) form
+        np.testing.assert_allclose(a, ref, rtol=rtol, atol=1e-8, err_msg=msg)
+    for nm, node in pairs:
+        for i in range(len(node.u)):
+            same(node.u[i], g["%s_u%d" % (nm, i)], "%s.u[%d]" % (nm, i))
+        for i in range(len(node.phi)):
+            same(node.phi[i], g["%s_phi%d" % (nm, i)], "%s.phi[%d]" % (nm, i))
+        same(node.g, g[nm + "_g"], nm + ".g")
+
+
+def test_chain_driven_by_known_input_signals_matches_reference(backend):
+    """gaussian_markov_chain.py:485-540, :608-616, :638-655: x_n = [A B] [x_{n-1}; z_{n-1}] + noise, z an array."""
+    from bayespy_b200.nodes import GaussianMarkovChain, GaussianARD, Gamma, SumMultiply
+    from bayespy_b200.inference import VB
+    g = golden("lssm_inputs")
+    M, N, Dm, K = 4, 25, 2, 2
+    alpha = Gamma(1e-3, 1e-3, plates=(Dm + K,), name="alpha")
+    A = GaussianARD(0, alpha, shape=(Dm + K,), plates=(Dm,), name="A")
+    X = GaussianMarkovChain(np.zeros(Dm), 1e-2 * np.identity(Dm), A, np.ones(Dm), inputs=g["a_z"], n=N, name="X")
+    C = GaussianARD(0, 1e-2, shape=(Dm,), plates=(M, 1), name="C")
+    C.initialize_from_value(g["a_Cinit"])
+    F = SumMultiply("i,i", C, X, name="F")
+    tau = Gamma(1e-3, 1e-3, name="tau")
+    Y = GaussianARD(F, tau, name="Y")
+    Y.observe(g["a_y"])
+    Q = VB(X, C, A, alpha, tau, Y)
+    iters = len(g["a_L"])
+    Q.update(repeat=iters, verbose=False, tol=0)
+    np.testing.assert_allclose(Q.L[:iters], g["a_L"], rtol=1e-8)
+    _check_nodes(g, (("a_X", X), ("a_C", C), ("a_A", A), ("a_alpha", alpha), ("a_tau", tau)))
+    with pytest.raises(ValueError):
+        GaussianMarkovChain(np.zeros(Dm), np.identity(Dm), GaussianARD(0, 1, shape=(Dm,), plates=(Dm,)), np.ones(Dm),
+                            inputs=g["a_z"], n=N)                      # rows of A must have length D + K
+    with pytest.raises(ValueError):
+        GaussianMarkovChain(np.zeros(Dm), np.identity(Dm), A, np.ones(Dm), inputs=g["a_z"], n=N + 3)
+
+
+def test_plated_chains_with_uncertain_inputs_match_reference(backend):
+    """Inputs as a Gaussian node (it receives the chain's message, :504-527), chain plates, a masked observation."""
+    from bayespy_b200.nodes import GaussianMarkovChain, GaussianARD, Gaussian, Gamma
+    from bayespy_b200.inference import VB
+    g = golden("lssm_inputs")
+    N, Dm, K, P = 25, 2, 2, 3
+    U = GaussianARD(g["b_Umean"], 4.0, shape=(K,), plates=(P, N - 1), name="U")
+    A2 = GaussianARD(0, 1.0, shape=(Dm + K,), plates=(P, 1, Dm), name="A2")
+    A2.initialize_from_value(g["b_A2init"])
+    nu2 = Gamma(2.0, 2.0, plates=(P, 1, Dm), name="nu2")
+    X2 = GaussianMarkovChain(np.zeros(Dm), np.identity(Dm), A2, nu2, inputs=U, name="X2")
+    assert X2.plates == (P,) and X2.N == N
+    Y2 = Gaussian(X2, 5.0 * np.identity(Dm), name="Y2")
+    Y2.observe(g["b_y"], mask=g["b_mask"])
+    Q = VB(X2, A2, nu2, U, Y2)
+    iters = len(g["b_L"])
+    Q.update(repeat=iters, verbose=False, tol=0)
+    np.testing.assert_allclose(Q.L[:iters], g["b_L"], rtol=1e-8)
+    _check_nodes(g, (("b_X2", X2), ("b_A2", A2), ("b_nu2", nu2), ("b_U", U)))
+
+
+def test_chain_with_gaussian_gamma_dynamics_matches_reference(backend):
+    """A GaussianGamma node as the dynamics (gaussian_markov_chain.py:817 joins its scale with nu)."""
+    from bayespy_b200.nodes import GaussianMarkovChain, GaussianGamma, Gaussian, Gamma
+    from bayespy_b200.inference import VB
+    g = golden("lssm_inputs")
+    N, Dm, K = 25, 2, 2
+    b3 = Gamma(2.0, 1.0, plates=(Dm,), name="b3")
+    A3 = GaussianGamma(np.zeros(Dm + K), np.identity(Dm + K), 2.0, b3, plates=(Dm,), name="A3")
+    X3 = GaussianMarkovChain(np.zeros(Dm), np.identity(Dm), A3, np.ones(Dm), inputs=g["a_z"], n=N, name="X3")
+    Y3 = Gaussian(X3, 10.0 * np.identity(Dm), name="Y3")
+    Y3.observe(g["c_y"])
+    Q = VB(X3, A3, b3, Y3)
+    iters = len(g["c_L"])
+    Q.update(repeat=iters, verbose=False, tol=0)
+    np.testing.assert_allclose(Q.L[:iters], g["c_L"], rtol=1e-8)
+    _check_nodes(g, (("c_X3", X3), ("c_A3", A3), ("c_b3", b3)))

@@ -4,7 +4,7 @@ The test modules are imported from the staged, unmodified reference (oracle/_ref
 this package provides (GaussianARD, Gaussian, Gamma, Wishart, Dirichlet, Categorical, Mixture, SumMultiply, Take, Gate,
 GaussianMarkovChain, VaryingGaussianMarkovChain, GaussianGamma, ...) is swapped for ours inside the module, then single reference test
 methods are run as they are: their shapes, random inputs, assertions and finite-difference utilities
-(``assert_message_to_parent``, ``assert_moments``).  61 of the 78 methods of those modules run green; the others are
+(``assert_message_to_parent``, ``assert_moments``).  62 of the 78 methods of those modules run green; the others are
 listed with the reason in NOT_APPLICABLE (they need classes or internals outside the path).  Oracle backend on CPU,
 libbpk under -m gpu."""
 import importlib
@@ -68,6 +68,7 @@ PASSING = [
     ("test_gaussian_markov_chain", "TestGaussianMarkovChain.test_message_to_mu0"),
     ("test_gaussian_markov_chain", "TestGaussianMarkovChain.test_message_to_parents"),
     ("test_gaussian_markov_chain", "TestGaussianMarkovChain.test_message_to_v"),
+    ("test_gaussian_markov_chain", "TestGaussianMarkovChain.test_message_to_parents_with_inputs"),
     ("test_gaussian_markov_chain", "TestGaussianMarkovChain.test_plates"),
     ("test_gaussian_markov_chain", "TestGaussianMarkovChain.test_smoothing"),
     ("test_gaussian_markov_chain", "TestVaryingGaussianMarkovChain.test_message_to_B"),
@@ -92,7 +93,6 @@ NOT_APPLICABLE = {
     ("test_gaussian", "TestConcatGaussian.test_moments"): "node class outside the path (GaussianGamma / ConcatGaussian)",
     ("test_gaussian", "TestGaussianARD.test_rotate"): "rotation of a multi-axis GaussianARD / axis != -1",
     ("test_gaussian_markov_chain", "TestGaussianMarkovChain.test_message_to_child"): "uses the reference's Moments classes / converters directly",
-    ("test_gaussian_markov_chain", "TestGaussianMarkovChain.test_message_to_parents_with_inputs"): "input signals of the Markov chain are not implemented",
     ("test_gaussian_markov_chain", "TestVaryingGaussianMarkovChain.test_message_to_child"): "API detail: IndexError: list index out of range",
     ("test_gaussian_markov_chain", "TestVaryingGaussianMarkovChain.test_plates_from_parents"): "plated Varying chains (chain plates in front of the time axis of S)",
 }
