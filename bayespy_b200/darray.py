@@ -506,7 +506,26 @@ def sum_product(arrays, keysets, out_keys, scale=1.0, out=None, accumulate=False
         return out
     shp, sts = _collapse_groups(shape, [ostr] + in_strides, len(out_keys))
     if len(shp) > _bpk.MAXD:
-        raise ValueError("sum_product rank %d exceeds %d" % (len(shp), _bpk.MAXD))
+        if len(arrays) < 3:
+            raise ValueError("sum_product rank %d exceeds %d" % (len(shp), _bpk.MAXD))
+        # too many distinct axes for one launch: contract the two operands that leave the smallest intermediate first
+        # (keys needed later - by another operand, the output or a multiplicity in ``sizes`` - are kept)
+        best = None
+        for i in range(len(arrays)):
+            for j in range(i + 1, len(arrays)):
+                later = set(out_keys) | set(sizes or ())
+                for m, ks in enumerate(keysets):
+                    if m != i and m != j:
+                        later |= set(ks)
+                keep = [k for k in dict.fromkeys(list(keysets[i]) + list(keysets[j])) if k in later]
+                cost = int(np.prod([ext[k] for k in keep], dtype=np.int64)) if keep else 1
+                if best is None or cost < best[0]:
+                    best = (cost, i, j, keep)
+        _, i, j, keep = best
+        t = sum_product([arrays[i], arrays[j]], [keysets[i], keysets[j]], keep)
+        rest = [m for m in range(len(arrays)) if m != i and m != j]
+        return sum_product([t] + [arrays[m] for m in rest], [keep] + [keysets[m] for m in rest], out_keys, scale, out,
+                           accumulate, sizes)
     dts = [_DT[a.dtype][1] for a in arrays]
     be.sum_multiply(shp, [a.ptr for a in arrays], dts, sts[1:], out.ptr, sts[0], scale, accumulate)
     return out

@@ -480,8 +480,12 @@ class GaussianARD(_GaussianNode):
         """Transform q(x) -> q(R x) along the variable axis (gaussian.py:1693-1745): natural parameters by
         R^-T, moments by R, log-normaliser by -log|det R|.  R is a host K x K matrix; the plated arrays are
         transformed on the device (one pass over u0; the covariance stays factored when it is shared)."""
-        if Q is not None or subset is not None or axis not in (-1, 0) or len(self.dims[0]) != 1:
-            raise NotImplementedError("rotate: only axis=-1 of a one-axis GaussianARD, without Q / subset")
+        if Q is not None or subset is not None:
+            raise NotImplementedError()
+        if len(self.dims[0]) != 1:
+            return self._rotate_axis(R, inv, logdet, axis)
+        if axis not in (-1, 0):
+            raise ValueError("Axis out of bounds")
         from .plans import LazyArray
         R = np.asarray(R, dtype=np.float64)
         invR = np.linalg.inv(R) if inv is None else np.asarray(inv, dtype=np.float64)
@@ -538,6 +542,45 @@ class GaussianARD(_GaussianNode):
         self._version += 1
         for hook in getattr(self, "_rotate_hooks", ()):
             hook(Rd, old_version)          # e.g. a plan's cached plate sums rotate with the node
+
+    def _rotate_axis(self, R, inv, logdet, axis):
+        """Rotation along one axis of a variable block with several axes (gaussian.py:1693-1730 with rotate_mean /
+        rotate_covariance :2612-2666): every array is viewed as (rest, K, rest[, K, rest]) and contracted with R on the
+        device; the log-normaliser moves by -log|det R| times the number of rotated fibres."""
+        nd = len(self.dims[0])
+        if nd == 0 or not -nd <= axis < nd:
+            raise ValueError("Axis out of bounds")
+        axis = axis % nd - nd                                         # counted from the end
+        R = np.asarray(R, dtype=np.float64)
+        invR = np.linalg.inv(R) if inv is None else np.asarray(inv, dtype=np.float64)
+        logdetR = np.linalg.slogdet(R)[1] if logdet is None else float(logdet)
+        K = self.dims[0][axis]
+        if R.shape != (K, K):
+            raise ValueError("The rotation matrix must be %d x %d" % (K, K))
+
+        def n_(shape):
+            return int(np.prod(shape, dtype=np.int64)) if len(shape) else 1
+
+        def rot_mean(a, Mx):
+            a = D.asarray(dense(a)).contiguous()
+            p = a.ndim + axis
+            v = a.reshape((n_(a.shape[:p]), K, n_(a.shape[p + 1:])))
+            return D.sum_product([Mx, v], [["i", "k"], ["n", "k", "m"]], ["n", "i", "m"]).reshape(a.shape)
+
+        def rot_cov(a, Mx):
+            a = D.asarray(dense(a)).contiguous()
+            p2 = a.ndim + axis
+            p1 = p2 - nd
+            v = a.reshape((n_(a.shape[:p1]), K, n_(a.shape[p1 + 1:p2]), K, n_(a.shape[p2 + 1:])))
+            return D.sum_product([Mx, v, Mx], [["i", "k"], ["n", "k", "m", "l", "q"], ["j", "l"]],
+                                 ["n", "i", "m", "j", "q"]).reshape(a.shape)
+        Rd, iRT = D.asarray(R), D.asarray(np.ascontiguousarray(invR.T))
+        g_old = self.g.materialize() if hasattr(self.g, "materialize") else self.g
+        self._fused = None
+        self.phi = [rot_mean(self.phi[0], iRT), rot_cov(self.phi[1], iRT)]
+        self.u = [rot_mean(self.u[0], Rd), rot_cov(self.u[1], Rd)]
+        fibres = n_(self.dims[0]) // K
+        self.g = D.affine(D.asarray(g_old), 1.0, -logdetR * fibres)
 
     def rotate_plates(self, Q, plate_axis=-1):
         """Approximate rotation of a plate axis (gaussian.py:1743-1774): the means mix exactly, <x_i> <- sum_k Q_ik <x_k>;

@@ -576,33 +576,48 @@ class GaussianMarkovChain(ExponentialFamily):
 
 
 class _AddTrailingPlate(Deterministic):
-    """The parent seen with one more (unit) plate axis after its own plates: moments and messages are the parent's,
-    reshaped.  Lets a time-plated node broadcast against a node whose last plate is the state dimension."""
+    """The parent seen with one more (unit) plate axis: after its own plates (``position`` 0) or in front of its last
+    ``position`` plates.  Moments and messages are the parent's, reshaped.  Lets a time-plated node broadcast against a
+    node whose last plate is the state dimension, and plated mixing matrices (..., D) against the time axis."""
 
-    def __init__(self, node, name=""):
+    def __init__(self, node, name="", position=0):
         self.moment_kind = node.moment_kind
-        super().__init__(node, dims=node.dims, plates=tuple(node.plates) + (1,), name=name)
+        self.position = int(position)
+        if self.position > len(node.plates):
+            raise ValueError("The node has fewer than %d plates" % self.position)
+        super().__init__(node, dims=node.dims, plates=self._insert(tuple(node.plates)), name=name)
+
+    def _insert(self, plates, value=1):
+        k = len(plates) - self.position
+        return tuple(plates[:k]) + (value,) + tuple(plates[k:])
 
     def _plates_from_parent(self, index):
-        return tuple(self.parents[0].plates) + (1,)
+        return self._insert(tuple(self.parents[0].plates))
+
+    def _map_parent_axes(self, index, values):
+        return self._insert(tuple(values))
 
     def _plates_to_parent(self, index):
-        return tuple(self.plates[:-1])
+        k = len(self.plates) - 1 - self.position
+        return tuple(self.plates[:k]) + tuple(self.plates[k + 1:])
 
     def _weights_to_parent(self, index, mask):
         mask = np.asarray(mask)
-        return np.any(mask, axis=-1) if mask.ndim >= 1 else mask
+        return np.any(mask, axis=-1 - self.position) if mask.ndim >= 1 + self.position else mask
 
     def _compute_moments(self, u):
         out = []
         for ui, dims in zip(u, self.dims):
             ui = D.asarray(dense(ui))
-            nd = len(dims)
-            out.append(ui.reshape(tuple(ui.shape[:ui.ndim - nd]) + (1,) + tuple(ui.shape[ui.ndim - nd:])))
+            npl = ui.ndim - len(dims)
+            if npl >= self.position:
+                k = npl - self.position
+                ui = ui.reshape(tuple(ui.shape[:k]) + (1,) + tuple(ui.shape[k:]))
+            out.append(ui)
         return out
 
     def message_to_parent(self, index):
-        # the children have summed their messages to this node's plates (..., 1): drop the unit axis
+        # the children have summed their messages to this node's plates: drop the unit axis
         m = self.message_from_children()
         out = []
         for mi, dims in zip(m, self.dims):
@@ -610,9 +625,10 @@ class _AddTrailingPlate(Deterministic):
                 out.append(None)
                 continue
             mi = D.asarray(mi)
-            nd = len(dims)
-            if mi.ndim - nd >= 1:
-                mi = mi.reshape(tuple(mi.shape[:mi.ndim - nd - 1]) + tuple(mi.shape[mi.ndim - nd:]))
+            npl = mi.ndim - len(dims)
+            if npl >= 1 + self.position:
+                k = npl - 1 - self.position
+                mi = mi.reshape(tuple(mi.shape[:k]) + tuple(mi.shape[k + 1:]))
             out.append(mi)
         return out
 
@@ -645,7 +661,9 @@ class VaryingGaussianMarkovChain(GaussianMarkovChain):
                              "the number of time instances.")
         self._mixing = (B, S)
         weights = _AddTrailingPlate(S) if len(S.plates) >= 1 else S
-        A = SumMultiply("jk,k->j", B, weights)
+        # chains over plates: the mixing matrices (..., D) meet the time axis of the weights (..., N-1, 1) as (..., 1, D)
+        mixing = _AddTrailingPlate(B, position=1) if len(B.plates) >= 2 else B
+        A = SumMultiply("jk,k->j", mixing, weights)
         super().__init__(mu, Lambda, A, nu, n=n, plates=plates, name=name, initialize=initialize)
 
 

