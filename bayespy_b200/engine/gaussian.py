@@ -586,8 +586,6 @@ class GaussianARD(_GaussianNode):
         """Approximate rotation of a plate axis (gaussian.py:1743-1774): the means mix exactly, <x_i> <- sum_k Q_ik <x_k>;
         the precision of plate p is scaled by (sum_i Q_ip)^-2 instead of being mixed; then the moments and the
         log-normaliser are recomputed from the natural parameters."""
-        if len(self.dims[0]) != 1:
-            raise NotImplementedError("rotate_plates is implemented for GaussianARD nodes with one variable axis")
         if not isinstance(plate_axis, int):
             raise ValueError("Plate axis must be integer")
         if plate_axis >= 0:
@@ -595,21 +593,23 @@ class GaussianARD(_GaussianNode):
         if plate_axis < -len(self.plates) or plate_axis >= 0:
             raise ValueError("Axis out of bounds")
         Q = np.asarray(Q, dtype=np.float64)
-        P, K = self.plates[plate_axis], self.dims[0][0]
+        shape = tuple(self.dims[0])
+        P, K = self.plates[plate_axis], _flat_count(shape)        # the variable block counts as one flattened axis
         if Q.shape != (P, P):
             raise ValueError("Q must be a square matrix over the rotated plate axis")
         npl = len(self.plates)
         ax = npl + plate_axis                                   # position of the rotated axis among the plates
         pk = [("p", j) for j in range(npl)]
-        u0 = D.asarray(self.u[0]).broadcast_to(tuple(self.plates) + (K,))
+        u0 = D.asarray(self.u[0]).broadcast_to(tuple(self.plates) + shape).contiguous().reshape(tuple(self.plates) + (K,))
         keys_in = pk[:ax] + ["k"] + pk[ax + 1:] + ["d"]
         keys_out = pk[:ax] + ["i"] + pk[ax + 1:] + ["d"]
         u0 = D.sum_product([D.asarray(Q), u0], [["i", "k"], keys_in], keys_out)
         s = np.sum(Q, axis=0)
         scale = D.asarray((s ** -2.0).reshape((P,) + (1,) * (npl - ax - 1) + (1, 1)))
-        phi1 = D.mul(D.asarray(dense(self.phi[1])).broadcast_to(tuple(self.plates) + (K, K)), scale)
+        phi1 = D.asarray(dense(self.phi[1])).broadcast_to(tuple(self.plates) + shape + shape).contiguous()
+        phi1 = D.mul(phi1.reshape(tuple(self.plates) + (K, K)), scale)
         phi0 = D.sum_product([phi1, u0], [pk + ["a", "b"], pk + ["b"]], pk + ["a"], scale=-2.0)
-        self.phi = [phi0, phi1]
+        self.phi = [phi0.reshape(tuple(self.plates) + shape), phi1.reshape(tuple(self.plates) + shape + shape)]
         u, g = self._distribution.compute_moments_and_cgf(self.phi)
         self._fused = None
         self._store(u, g, np.logical_not(self.observed))

@@ -1,12 +1,15 @@
-"""Rotation parameter expansion: ``RotationOptimizer`` and ``RotateGaussianARD`` of
-bayespy/inference/vmp/transformations.py:23-222 and :376-1110, for the case every documented PCA / factor-model
-example uses: rotation of the variable axis of a ``GaussianARD`` block (``axis=-1``, no plate rotation, no subset),
-with its ARD precision either updated (``RotateGaussianARD(C, alpha)``) or fixed (``RotateGaussianARD(X)``).
+"""Rotation parameter expansion: ``RotationOptimizer`` and the rotators of
+bayespy/inference/vmp/transformations.py — ``RotateGaussianARD`` (:376-1110, any variable axis of an array with any
+plates, with or without a joint rotation of one plate axis, ARD precision with any broadcastable plates, updated or
+fixed), ``RotateGaussianMarkovChain`` (:1112-1452, chains over plates, time-varying / per-chain dynamics),
+``RotateVaryingMarkovChain`` (:1454-1541), ``RotateSwitchingMarkovChain`` (:1544-1632) and ``RotateMultiple`` (:1635-1677).
 
-Split of work: the plate-summed second moments the cost function needs (sum <x x^T>, sum <x> mu^T — K x K each) are
-reduced on the device by the same plate-sum kernels the VB sweep uses and read back once per ``rotate()``; the
-optimisation over the K x K matrix R (SciPy CG, exactly the reference's call) runs on the host; applying R to the
-plated moments (u0 <- u0 R^T over all N columns, Cov <- R Cov R^T) is again device work.
+Split of work: the plate sums the cost functions need (a handful of D x D [x C x C] arrays per rotated block) are
+contracted on the device by the same kernels the VB sweep uses (``bpk_sum_multiply`` on strided views of the moments)
+and read back once per ``setup()``; the optimisation over the D x D matrix R (SciPy CG, exactly the reference's call)
+runs on the host; applying R to the plated moments is again device work.  The factor-model case of every documented
+example (one variable axis, ARD precision over that axis) keeps a two-plate-sum fast path that never materialises the
+per-plate covariances of a long node.
 """
 import warnings
 
@@ -28,19 +31,27 @@ class RotateGaussianARD:
     """``RotateGaussianARD(X)`` / ``RotateGaussianARD(C, alpha)`` (transformations.py:376-1110)."""
 
     def __init__(self, X, *alpha, axis=-1, precompute=False, subset=None):
-        if not isinstance(X, GaussianARD) or len(X.dims[0]) != 1:
-            raise NotImplementedError("Rotation is implemented for GaussianARD nodes with one variable axis")
-        if axis not in (-1, 0) or subset is not None or precompute:
-            raise NotImplementedError("Only axis=-1 without subset / precompute is implemented")
+        if not isinstance(X, GaussianARD) or len(X.dims[0]) < 1:
+            raise ValueError("RotateGaussianARD rotates a GaussianARD node with at least one variable axis")
+        if subset is not None:
+            raise NotImplementedError("Rotation of a subset of the axis is not implemented")
         if len(alpha) > 1:
             raise ValueError("Too many arguments")
+        nd = len(X.dims[0])
+        if not isinstance(axis, int) or not -nd <= axis < nd:
+            raise ValueError("Axis out of bounds")
         self.node_X = X
         self.node_alpha = alpha[0] if alpha else None
         self.update_alpha = bool(alpha)
-        if self.update_alpha and not (isinstance(self.node_alpha, Gamma) and tuple(self.node_alpha.plates) == tuple(X.dims[0])):
-            raise NotImplementedError("The ARD node must be a Gamma node with plates equal to the rotated axis")
-        self.D = X.dims[0][0]
+        if self.update_alpha and not isinstance(self.node_alpha, Gamma):
+            raise ValueError("The ARD node must be a Gamma node")
+        self.axis = axis % nd - nd                       # counted from the end of the variable axes
+        self.D = X.dims[0][self.axis]
         self.plate_axis = None
+        # the case every documented factor model has - one variable axis, an ARD precision over exactly that axis (or a
+        # fixed one), no plate mixing - keeps its own statistics: two K x K plate sums of the (possibly very long) node
+        self._simple = nd == 1 and (not self.update_alpha or tuple(self.node_alpha.plates) == tuple(X.dims[0]))
+        self._general = None
 
     def nodes(self):
         return [self.node_X, self.node_alpha] if self.update_alpha else [self.node_X]
@@ -48,9 +59,14 @@ class RotateGaussianARD:
     # ---- statistics (transformations.py:482-640, the branch without plate rotation) -------------------------
     def setup(self, plate_axis=None):
         self.plate_axis = plate_axis
-        if plate_axis is not None:
-            return self._setup_with_plate_rotation(plate_axis)
         X, K = self.node_X, self.D
+        self._general = None
+        if plate_axis is not None and self._simple and len(X.plates) == 1 and plate_axis in (-1, 0):
+            return self._setup_with_plate_rotation(plate_axis)
+        if plate_axis is not None or not self._simple or not self._simple_parents():
+            self._general = _ArrayRotationStatistics(X, self.node_alpha if self.update_alpha else None, self.axis,
+                                                     plate_axis)
+            return
         Np = int(np.prod(X.plates, dtype=np.int64)) if X.plates else 1
         u_mu, u_al = X.parents[0].get_moments(), X.parents[1].get_moments()
         x = X.u[0].reshape((-1, K))
@@ -88,6 +104,17 @@ class RotateGaussianARD:
             if a.size not in (1, K) or (a.ndim > 1 and any(n != 1 for n in a.shape[:-1])):
                 raise NotImplementedError("A fixed precision that varies over plates is not supported by the rotation")
             self.alpha = np.broadcast_to(a.reshape(-1)[-K:] if a.size >= K else a.reshape(()), (K,)).copy()
+
+    def _simple_parents(self):
+        """True when the prior mean and a fixed precision do not vary over the plates (what the two-plate-sum
+        statistics of ``setup`` can express)."""
+        X, K = self.node_X, self.D
+        u_mu, u_al = X.parents[0].get_moments(), X.parents[1].get_moments()
+        if not self.update_alpha:
+            a = D.asarray(u_al[0])
+            if a.size not in (1, K) or (a.ndim > 1 and any(n != 1 for n in a.shape[:-1])):
+                return False
+        return True
 
     def _setup_with_plate_rotation(self, plate_axis):
         """Statistics for a joint rotation of the variable axis (by R) and of ONE plate axis (by Q), the case the
@@ -139,6 +166,9 @@ class RotateGaussianARD:
         ARD precision Gamma(a0, b0) with posterior shape `a`:  b_i = b0_i + e_i / 2, <alpha_i> = a_i / b_i and
             bound = -1/2 sum_i <alpha_i> e_i - n/2 sum_i log b_i - sum_i (a0_i log b_i + b0_i <alpha_i>) + n log|det R|.
         """
+        if self._general is not None:
+            return self._general.bound(R, Q, self.node_X, self.node_alpha if self.update_alpha else None,
+                                       logdet=logdet, inv=inv, gradient=gradient, terms=terms)
         plate_entropy = 0.0
         if self.plate_axis is not None:
             if Q is None:
@@ -203,11 +233,182 @@ class RotateGaussianARD:
 
     # ---- apply (transformations.py:454-468 -> gaussian.py:1693-1774) -----------------------------------------------
     def rotate(self, R, inv=None, logdet=None, Q=None):
-        self.node_X.rotate(R, inv=inv, logdet=logdet)
+        self.node_X.rotate(R, inv=inv, logdet=logdet, axis=self.axis)
         if self.plate_axis is not None:
             self.node_X.rotate_plates(Q, plate_axis=self.plate_axis)
         if self.update_alpha:
             self.node_alpha.update()
+
+
+class _ArrayRotationStatistics:
+    """Rotation of one variable axis (length D, by R) and optionally one plate axis (length C, by Q) of a GaussianARD
+    array with plates P and variable shape S, for a prior mean and an ARD precision with any plates that broadcast to
+    F = P + S (transformations.py:475-1095 is the reference's treatment of the same problem).
+
+    Index space: F = O x c x v, with v the rotated variable axis, c the rotated plate axis (a dummy axis of length one
+    when no plate is rotated) and O every other axis, plate or variable alike.  The precision varies over a sub-grid
+    G of O (axes along which it has extent one are summed out) and possibly over c and v.  Plate sums, reduced on the
+    device once per ``setup``:
+
+        CovS[g,q,k,l]   = sum_o Cov(x_oqk, x_oql)              MM[g,q,r,k,l] = sum_o <x_oqk> <x_orl>
+        Mmu[g,q,p,k,i]  = sum_o <x_oqk> <mu_opi>               mumu[g,p,i]   = sum_o <mu_opi^2>
+
+    After x -> Q x R^T (means mixed exactly over the plate axis, covariances scaled by the squared column sums s_p of Q,
+    the approximation GaussianARD.rotate_plates applies) the expected squared deviation from the prior mean is
+
+        e[g,p,i] = s_p^2 (R CovS[g,p] R^T)_ii + sum_qr Q_pq Q_pr (R MM[g,q,r] R^T)_ii - 2 sum_q Q_pq (R Mmu[g,q,p])_ii
+                   + mumu[g,p,i]
+
+    summed further over p / i where the precision does not vary.  With a fixed precision the bound changes by
+    -1/2 sum <alpha> e; with a Gamma(a0, b0) precision re-optimised after the rotation, b = b0 + e/2 and the bound
+    terms are  X: -1/2 (a/b) e - n/2 log b,  alpha: -a0 log b - b0 a/b.  The entropy of q(X) grows by
+    |F|/D log|det R| + |F|/C sum_p log|s_p|."""
+
+    def __init__(self, X, alpha, axis, plate_axis):
+        P, S = tuple(X.plates), tuple(X.dims[0])
+        F = P + S
+        nF, nS = len(F), len(S)
+        v = nF + axis                                              # position of the rotated variable axis in F
+        if plate_axis is None:
+            c = None
+        else:
+            if not isinstance(plate_axis, int):
+                raise ValueError("Plate axis must be integer")
+            if not -len(P) <= plate_axis < len(P):
+                raise ValueError("Plate axis out of bounds")
+            c = plate_axis % len(P)
+        self.D, self.C = F[v], (F[c] if c is not None else 1)
+        self.has_Q = c is not None
+        O = [j for j in range(nF) if j != v and j != c]
+        self.nF_elems = float(np.prod(F, dtype=np.float64)) if F else 1.0
+        # --- moments as device arrays with one key per axis of F
+        u_mu, u_al = X.parents[0].get_moments(), X.parents[1].get_moments()
+        m = D.asarray(X.u[0]).broadcast_to(F)
+        u1 = D.asarray(dense(X.u[1])).broadcast_to(P + S + S).contiguous()
+        # second moments between positions that differ along v only: the diagonal over every other variable axis
+        st, sh = list(u1.strides), list(u1.shape)
+        np_, first, second = len(P), len(P), len(P) + nS
+        d_shape = list(F) + [self.D]
+        d_strides = list(st[:np_])
+        for j in range(nS):
+            d_strides.append(st[first + j] if np_ + j == v else st[first + j] + st[second + j])
+        d_strides.append(st[second + (v - np_)])
+        xxd = DArray(u1.owner, u1.ptr, d_shape, d_strides, u1.dtype)
+
+        def aligned(a):
+            a = D.asarray(a)
+            if a.ndim > nF:
+                a = a.squeeze_leading(nF)
+            return a.add_leading(nF - a.ndim)
+        mu, mu2 = aligned(u_mu[0]), aligned(u_mu[1])
+        if alpha is not None:
+            ashape = (1,) * (nF - len(alpha.plates)) + tuple(alpha.plates)
+        else:
+            ashape = tuple(aligned(u_al[0]).shape)
+        for j in range(nF):
+            if ashape[j] not in (1, F[j]):
+                raise ValueError("The plates of the ARD precision do not broadcast to the rotated array")
+        self.av, self.ac = ashape[v], (ashape[c] if c is not None else 1)
+        G_axes = [j for j in O if ashape[j] != 1]
+        self.G = tuple(F[j] for j in G_axes)
+        gk = [("f", j) for j in G_axes]
+
+        def keys(vkey, ckey):
+            return [vkey if j == v else (ckey if j == c else ("f", j)) for j in range(nF)]
+        sizes = {("f", j): F[j] for j in O}
+        cq, cr, cp = (["q"], ["r"], ["p"]) if c is not None else ([], [], [])
+        XXS = D.sum_product([xxd], [keys("k", "q") + ["l"]], gk + cq + ["k", "l"], sizes=sizes)
+        MMd = D.sum_product([m, m], [keys("k", "q"), keys("l", "q")], gk + cq + ["k", "l"], sizes=sizes)
+        MM = D.sum_product([m, m], [keys("k", "q"), keys("l", "r")], gk + cq + cr + ["k", "l"], sizes=sizes)
+        szm = dict(sizes)
+        szm.update({"i": self.D, "p": self.C})
+        Mmu = D.sum_product([m, mu], [keys("k", "q"), keys("i", "p")], gk + cq + cp + ["k", "i"], sizes=szm)
+        mumu = D.sum_product([mu2], [keys("i", "p")], gk + cp + ["i"], sizes=szm)
+        g = int(np.prod(self.G, dtype=np.int64)) if self.G else 1
+        Dn, Cn = self.D, self.C
+        self.CovS = (_np(XXS) - _np(MMd)).reshape(g, Cn, Dn, Dn)
+        self.MM = _np(MM).reshape(g, Cn, Cn, Dn, Dn)
+        self.Mmu = _np(Mmu).reshape(g, Cn, Cn, Dn, Dn)
+        self.mumu = _np(mumu).reshape(g, Cn, Dn)
+        self.n_o = float(np.prod([F[j] for j in O if j not in G_axes], dtype=np.float64)) if O else 1.0
+        # elements of X per element of the precision
+        self.n = self.n_o * (Cn if self.ac == 1 else 1) * (Dn if self.av == 1 else 1)
+        ash = (g, self.ac, self.av)
+        if alpha is not None:
+            def to_alpha(a):
+                a = np.asarray(a, dtype=np.float64)
+                a = a.reshape((1,) * (nF - a.ndim) + a.shape) if a.ndim <= nF else a.reshape(a.shape[a.ndim - nF:])
+                full = np.broadcast_to(a, ashape)
+                order = G_axes + ([c] if c is not None else []) + [v]
+                rest = [j for j in range(nF) if j not in order]
+                return np.transpose(full, rest + order).reshape(ash)
+            self.a = to_alpha(_np(alpha.phi[1]))
+            self.a0 = to_alpha(_np(alpha.parents[0].get_moments()[0]))
+            self.b0 = to_alpha(_np(alpha.parents[1].get_moments()[0]))
+            self.prec = None
+        else:
+            a = _np(u_al[0])
+            a = a.reshape((1,) * (nF - a.ndim) + a.shape) if a.ndim <= nF else a.reshape(a.shape[a.ndim - nF:])
+            order = G_axes + ([c] if c is not None else []) + [v]
+            rest = [j for j in range(nF) if j not in order]
+            self.prec = np.transpose(a, rest + order).reshape(ash)
+
+    def bound(self, R, Q, node_X, node_alpha, logdet=None, inv=None, gradient=False, terms=False):
+        Dn, Cn = self.D, self.C
+        if self.has_Q:
+            if Q is None:
+                raise ValueError("Plates should be rotated but no Q given")
+            Q = np.asarray(Q, dtype=np.float64)
+        else:
+            Q = np.ones((1, 1))
+        if logdet is None:
+            logdet = np.linalg.slogdet(R)[1]
+        if inv is None and gradient:
+            inv = np.linalg.inv(R)
+        s = np.sum(Q, axis=0)
+        cdiag = np.einsum("ik,gpkl,il->gpi", R, self.CovS, R)
+        RMR = np.einsum("ik,gqrkl,il->gqri", R, self.MM, R)
+        bdiag = np.einsum("pq,pr,gqri->gpi", Q, Q, RMR)
+        tdiag = np.einsum("pq,ik,gqpki->gpi", Q, R, self.Mmu)
+        e_full = (s * s)[None, :, None] * cdiag + bdiag - 2.0 * tdiag + self.mumu
+        e = e_full
+        if self.ac == 1:
+            e = e.sum(axis=1, keepdims=True)
+        if self.av == 1:
+            e = e.sum(axis=2, keepdims=True)
+        n = self.n
+        if node_alpha is not None:
+            rate = self.b0 + 0.5 * e
+            prec = self.a / rate
+            logprec = -np.log(rate)
+            hyper = np.sum(self.a0 * logprec) - np.sum(self.b0 * prec)
+        else:
+            prec, logprec, hyper = self.prec, 0.0, 0.0
+        entropy_gain = self.nF_elems / Dn * logdet + self.nF_elems / Cn * np.sum(np.log(np.abs(s)))
+        fit = -0.5 * np.sum(prec * e) + 0.5 * n * np.sum(logprec)
+        if terms:
+            out = {node_X: fit + entropy_gain}
+            if node_alpha is not None:
+                out[node_alpha] = hyper
+            return out
+        value = fit + hyper + entropy_gain
+        if not gradient:
+            return value
+        if node_alpha is not None:
+            w = -0.5 * prec + 0.5 * (0.5 * e * prec - 0.5 * n - self.a0 + self.b0 * prec) / rate
+        else:
+            w = -0.5 * prec
+        W = np.broadcast_to(w, e_full.shape)
+        B = np.einsum("pq,pr,gqrkl->gpkl", Q, Q, self.MM)
+        T = np.einsum("pq,gqpki->gpki", Q, self.Mmu)
+        dR = 2.0 * np.einsum("gpi,p,ik,gpkl->il", W, s * s, R, self.CovS) \
+            + np.einsum("gpi,ik,gpkl->il", W, R, B + np.swapaxes(B, -1, -2)) \
+            - 2.0 * np.einsum("gpi,gpli->il", W, T) + self.nF_elems / Dn * inv.T
+        if not self.has_Q:
+            return value, dR
+        dQ = 2.0 * np.einsum("gpi,pr,gqri->pq", W, Q, RMR) - 2.0 * np.einsum("gpi,ik,gqpki->pq", W, R, self.Mmu)
+        col = 2.0 * s * np.einsum("gpi,gpi->p", W, cdiag) + self.nF_elems / Cn / s
+        return value, dR, dQ + col[None, :]
 
 
 class RotateGaussianMarkovChain:
@@ -228,12 +429,12 @@ class RotateGaussianMarkovChain:
         from ...engine.gmc import GaussianMarkovChain
         if not isinstance(X, GaussianMarkovChain):
             raise ValueError("RotateGaussianMarkovChain rotates a GaussianMarkovChain node")
-        if len(X.plates) != 0:
-            raise NotImplementedError("Rotation of plated chains is not implemented")
         if len(args) == 0:
             raise NotImplementedError()
         if len(args) > 1:
             raise ValueError("Wrong number of arguments")
+        if len(X.parents) > 4:
+            raise NotImplementedError("Rotation of a chain with input signals is not implemented")
         self.X_node = X
         self.A_node = X.parents[2]
         self.A_rotator = args[0]
@@ -253,28 +454,50 @@ class RotateGaussianMarkovChain:
         self.X_node.rotate(R, inv=inv, logdet=logdet)
         self.A_rotator.rotate(inv.T, inv=R.T, logdet=-logdet, Q=R)
 
+    def _dynamics_statistics(self, xx_head, xpxn, pk, sizes):
+        """Sums over chains and time steps that couple the dynamics with the chain's second moments:
+        sum A_n <x_{n-1} x_n^T>,  sum A_n <x_{n-1} x_{n-1}^T> A_n^T  and, per state d, sum tr(Cov(a_nd) <x_{n-1} x_{n-1}^T>).
+        The dynamics may have a time axis of length N-1 or 1 and fewer plates than the chain."""
+        X = self.X_node
+        dist = X._distribution
+        u_par = X.moments_from_parents()
+        _, _, _, _, A, AA, _, _ = dist._parents(u_par[0], u_par[1], u_par[2], u_par[3])
+        npl = len(pk)
+        ka = pk[npl - (A.ndim - 3):]
+        A_XpXn = D.sum_product([A, xpxn], [ka + ["n", "i", "k"], pk + ["n", "k", "j"]], ["i", "j"], sizes=sizes)
+        A_XpXp_A = D.sum_product([A, xx_head, A], [ka + ["n", "i", "k"], pk + ["n", "k", "l"], ka + ["n", "j", "l"]],
+                                 ["i", "j"], sizes=sizes)
+        aa = D.sum_product([AA, xx_head], [ka + ["n", "d", "k", "l"], pk + ["n", "k", "l"]], ["d"], sizes=sizes)
+        mm = D.sum_product([A, xx_head, A], [ka + ["n", "d", "k"], pk + ["n", "k", "l"], ka + ["n", "d", "l"]], ["d"],
+                           sizes=sizes)
+        return _np(A_XpXn), _np(A_XpXp_A), _np(aa) - _np(mm)
+
     def setup(self):
-        X, Dm = self.X_node, self.X_node.D
-        x, xx, xpxn = X.u
-        x0 = D.asarray(x).slice_axis(0, 0, 1)
-        self.X0 = _np(x0).reshape(Dm)
-        self.X0X0 = _np(D.asarray(xx).slice_axis(0, 0, 1)).reshape(Dm, Dm)
-        total = _np(D.sum_product([D.asarray(xx)], [["n", "i", "j"]], ["i", "j"]))
-        last = _np(D.asarray(xx).slice_axis(0, self.N - 1, self.N)).reshape(Dm, Dm)
-        self.XnXn = total - self.X0X0                               # sum_{n>=1} <x_n x_n^T>
-        XpXp = total - last                                        # sum_{n>=1} <x_{n-1} x_{n-1}^T>
-        XpXn = _np(D.sum_product([D.asarray(xpxn)], [["n", "i", "j"]], ["i", "j"]))
+        X, Dm, N = self.X_node, self.X_node.D, self.N
+        P = tuple(X.plates)
+        npl = len(P)
+        pk = [("p", j) for j in range(npl, 0, -1)]
+        psizes = {k: n for k, n in zip(pk, P)}          # extents of the chain plates (parents may lack some of them)
+        sizes = dict(psizes)
+        sizes["n"] = N - 1
+        x, xx, xpxn = [D.asarray(v) for v in X.u]
+        x = x.broadcast_to(P + (N, Dm))
+        xx = xx.broadcast_to(P + (N, Dm, Dm))
+        xpxn = xpxn.broadcast_to(P + (N - 1, Dm, Dm))
+        x0 = x.slice_axis(npl, 0, 1).reshape(P + (Dm,))
+        x0x0 = xx.slice_axis(npl, 0, 1).reshape(P + (Dm, Dm))
+        xx_tail = xx.slice_axis(npl, 1, N)
+        xx_head = xx.slice_axis(npl, 0, N - 1)
+        self.XnXn = _np(D.sum_product([xx_tail], [pk + ["n", "i", "j"]], ["i", "j"]))     # sum_{n>=1} <x_n x_n^T>
         u_mu, u_Lam = X.parents[0].get_moments(), X.parents[1].get_moments()
-        self.Lambda = np.broadcast_to(_np(u_Lam[0]), (Dm, Dm)).copy()
-        self.Lambda_mu_X0 = np.outer(self.Lambda @ np.broadcast_to(_np(u_mu[0]), (Dm,)), self.X0)
-        A = np.broadcast_to(_np(self.A_node.u[0]), (Dm, Dm))
-        AA = np.broadcast_to(_np(dense(self.A_node.u[1])), (Dm, Dm, Dm))
-        if len(self.A_node.plates) != 1:
-            raise NotImplementedError("Rotation with time-varying or plated dynamics is not implemented")
-        CovA = AA - A[:, :, None] * A[:, None, :]
-        self.A_XpXn = A @ XpXn
-        self.A_XpXp_A = A @ XpXp @ A.T
-        self.CovA_XpXp = np.einsum("dij,ij->d", CovA, XpXp)
+        Lam, mu = D.asarray(u_Lam[0]), D.asarray(u_mu[0])
+        kL, km = pk[npl - (Lam.ndim - 2):], pk[npl - (mu.ndim - 1):]
+        # sum over chains of Lambda (x) <x_0 x_0^T> and of (Lambda mu) <x_0>^T
+        self.L_X0X0 = _np(D.sum_product([Lam, x0x0], [kL + ["i", "j"], pk + ["k", "l"]], ["i", "j", "k", "l"], sizes=psizes))
+        self.Lambda_mu_X0 = _np(D.sum_product([Lam, mu, x0], [kL + ["i", "k"], km + ["k"], pk + ["j"]], ["i", "j"],
+                                              sizes=psizes))
+        self.A_XpXn, self.A_XpXp_A, self.CovA_XpXp = self._dynamics_statistics(xx_head, xpxn, pk, sizes)
+        self.n_chains = float(np.prod(P, dtype=np.float64)) if P else 1.0
         self.A_rotator.setup(plate_axis=-1)
 
     def _compute_bound(self, R, logdet=None, inv=None, gradient=False, terms=False):
@@ -282,21 +505,24 @@ class RotateGaussianMarkovChain:
         logdetR = np.linalg.slogdet(R)[1] if logdet is None else logdet
         r = np.sum(R, axis=0)
         R_Sn = R @ self.XnXn
-        L_R_S0 = self.Lambda @ R @ self.X0X0
         R_ASA = R @ self.A_XpXp_A
         rc = r * self.CovA_XpXp
-        yy = np.sum(R_Sn * R) + np.sum(L_R_S0 * R)
+        T4 = self.L_X0X0                                             # T4[i,j,k,l] = sum_b Lambda_b[i,j] <x_0 x_0^T>_b[k,l]
+        init = np.einsum("ijkl,jk,il->", T4, R, R)                   # sum_b tr(Lambda_b R <x_0 x_0^T>_b R^T)
+        yy = np.sum(R_Sn * R) + init
         yz = np.sum((R @ self.A_XpXn) * R) + np.sum(self.Lambda_mu_X0 * R)
         zz = np.sum(R_ASA * R) + np.dot(rc, r)
-        value = -0.5 * yy + yz - 0.5 * zz + self.N * logdetR
+        entropy = self.N * self.n_chains
+        value = -0.5 * yy + yz - 0.5 * zz + entropy * logdetR
         if terms:
             value = {self.X_node: value}
         if not gradient:
             return value
-        dyy = 2.0 * (R_Sn + L_R_S0)
+        dinit = np.einsum("iabl,il->ab", T4, R) + np.einsum("ajkb,jk->ab", T4, R)
+        dyy = 2.0 * R_Sn + dinit
         dyz = R @ (self.A_XpXn + self.A_XpXn.T) + self.Lambda_mu_X0
         dzz = 2.0 * (R_ASA + rc[None, :])
-        return value, -0.5 * dyy + dyz - 0.5 * dzz + self.N * invR.T
+        return value, -0.5 * dyy + dyz - 0.5 * dzz + entropy * invR.T
 
     def bound(self, R, logdet=None, inv=None):
         if inv is None:
@@ -316,6 +542,131 @@ class RotateGaussianMarkovChain:
             logdet = np.linalg.slogdet(R)[1]
         out = dict(self.A_rotator.get_bound_terms(inv.T, inv=R.T, logdet=-logdet, Q=R))
         out.update(self._compute_bound(R, logdet=logdet, inv=inv, gradient=False, terms=True))
+        return out
+
+
+class RotateVaryingMarkovChain(RotateGaussianMarkovChain):
+    """``RotateVaryingMarkovChain(X, B, S, B_rotator)`` (transformations.py:1454-1541): the chain's dynamics are
+    A_n = sum_k s_nk B_k (``SumMultiply('dk,k->d', B, S)`` under a ``GaussianMarkovChain``, which is also what
+    ``VaryingGaussianMarkovChain`` builds).  q(x_n) -> q(R x_n) goes with B_k -> R B_k R^-1 through ``B_rotator`` (a
+    ``RotateGaussianARD`` of B on its first variable axis, rotated by R^-T, and on its last plate axis, by R); the
+    weights S are left alone.
+
+    Only the statistics that couple the dynamics with the chain differ from the parent class: with
+    <s s^T>_n the second moment of the weights and Sp_n = <x_{n-1} x_{n-1}^T>,
+        G[e,f] = sum_n sum_kk' <s_k s_k'>_n  mean(b_ek)^T Sp_n mean(b_fk')       (transforms exactly, as R G R^T)
+        c[e]   = sum_n sum_kk' <s_k s_k'>_n  tr(Cov(b_ek, b_ek') Sp_n)            (scaled by the squared column sums of R)"""
+
+    def __init__(self, X, B, S, B_rotator):
+        super().__init__(X, B_rotator)
+        from ...engine.dot import SumMultiply
+        A = self.A_node
+        ok = isinstance(A, SumMultiply) and len(A.parents) == 2 and len(A.in_keys[0]) == 2 and \
+            list(A.in_keys[1]) == [A.in_keys[0][1]] and list(A.out_keys) == [A.in_keys[0][0]]
+        if not ok:
+            raise ValueError("The dynamics of the chain must be SumMultiply('dk,k->d', B, S)")
+        self.B_node, self.S_node = B, S
+
+    def _dynamics_statistics(self, xx_head, xpxn, pk, sizes):
+        X, A = self.X_node, self.A_node
+        u_par = X.moments_from_parents()
+        _, _, _, _, Abar, _, _, _ = X._distribution._parents(u_par[0], u_par[1], u_par[2], u_par[3])
+        npl = len(pk)
+        ka = pk[npl - (Abar.ndim - 3):]
+        A_XpXn = D.sum_product([Abar, xpxn], [ka + ["n", "i", "k"], pk + ["n", "k", "j"]], ["i", "j"], sizes=sizes)
+        u_B, u_S = A.parents[0].get_moments(), A.parents[1].get_moments()
+        b, bb = D.asarray(u_B[0]), D.asarray(dense(u_B[1]))          # plates (.., T|1, D) + (D, K) [+ (D, K)]
+        sv, ss = D.asarray(u_S[0]), D.asarray(dense(u_S[1]))         # plates (.., T|1, 1) + (K,) [+ (K,)]
+        plate_keys = pk + ["n", "e"]
+
+        def pl(a, nd, row="e"):
+            ks = list(plate_keys[len(plate_keys) - (a.ndim - nd):]) if a.ndim > nd else []
+            return [row if k == "e" else k for k in ks]
+        kb, kb2 = pl(b, 2), pl(b, 2, row="f")
+        kS = pl(ss, 2, row="z")
+        Sp = [pk + ["n", "i", "j"]]
+        G = D.sum_product([b, ss, xx_head, b], [kb + ["i", "k"], kS + ["k", "m"]] + Sp + [kb2 + ["j", "m"]], ["e", "f"],
+                          sizes=sizes)
+        tot = D.sum_product([bb, ss, xx_head], [pl(bb, 4) + ["i", "k", "j", "m"], kS + ["k", "m"]] + Sp, ["e"], sizes=sizes)
+        G = _np(G)
+        Dm = X.D
+        G = np.broadcast_to(G, (Dm, Dm)) if G.shape != (Dm, Dm) else G
+        return _np(A_XpXn), G, np.broadcast_to(_np(tot), (Dm,)) - np.diag(G)
+
+
+class RotateSwitchingMarkovChain(RotateGaussianMarkovChain):
+    """``RotateSwitchingMarkovChain(X, B, Z, B_rotator)`` (transformations.py:1544-1632): at every step the dynamics are
+    one of K matrices, A_n = B_{z_n} (``Gate(Z, B, gated_plate=-2)`` under a ``GaussianMarkovChain``, which is what
+    ``SwitchingGaussianMarkovChain`` builds); B has plates (..., K, D).  q(x_n) -> q(R x_n) goes with B_k -> R B_k R^-1
+    through ``B_rotator`` (``RotateGaussianARD(B)``: variable axis by R^-T, last plate axis by R).  With the selection
+    probabilities p_nk = <z_nk>:
+        G[e,f] = sum_n sum_k p_nk mean(b_ke)^T Sp_n mean(b_kf),      c[e] = sum_n sum_k p_nk tr(Cov(b_ke) Sp_n)."""
+
+    def __init__(self, X, B, Z, B_rotator):
+        super().__init__(X, B_rotator)
+        from ...engine.gate import Gate
+        A = self.A_node
+        if not (isinstance(A, Gate) and A.gated_plate == -2):
+            raise ValueError("The dynamics of the chain must be Gate(Z, B, gated_plate=-2)")
+        K, Dm = A.K, X.D
+        if tuple(B.plates[-2:]) != (K, Dm):
+            raise ValueError("Incorrect plates in B")
+        if len(B.dims[0]) != 1:
+            raise ValueError("B should have exactly one variable axis")
+        self.B_node, self.Z_node = B, Z
+
+    def _dynamics_statistics(self, xx_head, xpxn, pk, sizes):
+        X, A = self.X_node, self.A_node
+        u_par = X.moments_from_parents()
+        _, _, _, _, Abar, _, _, _ = X._distribution._parents(u_par[0], u_par[1], u_par[2], u_par[3])
+        npl = len(pk)
+        ka = pk[npl - (Abar.ndim - 3):]
+        A_XpXn = D.sum_product([Abar, xpxn], [ka + ["n", "i", "k"], pk + ["n", "k", "j"]], ["i", "j"], sizes=sizes)
+        pz = D.asarray(A.parents[0].get_moments()[0])                 # plates (.., N-1 | 1, 1) + (K,)
+        u_B = A.parents[1].get_moments()
+        b, bb = D.asarray(u_B[0]), D.asarray(dense(u_B[1]))           # plates (.., K, D) + (D,) [+ (D,)]
+        zkeys = (pk + ["n", "z"])
+        kz = list(zkeys[len(zkeys) - (pz.ndim - 1):]) + ["c"]
+
+        def kB(a, nd, row):
+            ks = pk + ["c", row]
+            return list(ks[len(ks) - (a.ndim - nd):])
+        Sp = [pk + ["n", "i", "j"]]
+        G = D.sum_product([pz, b, xx_head, b], [kz, kB(b, 1, "e") + ["i"]] + Sp + [kB(b, 1, "f") + ["j"]], ["e", "f"],
+                          sizes=sizes)
+        tot = D.sum_product([pz, bb, xx_head], [kz, kB(bb, 2, "e") + ["i", "j"]] + Sp, ["e"], sizes=sizes)
+        G = _np(G)
+        return _np(A_XpXn), G, _np(tot) - np.diag(G)
+
+
+class RotateMultiple:
+    """The same rotation applied to several blocks at once; their cost functions add (transformations.py:1635-1677)."""
+
+    def __init__(self, *rotators):
+        self.rotators = rotators
+
+    def nodes(self):
+        return [n for r in self.rotators for n in r.nodes()]
+
+    def rotate(self, R, inv=None, logdet=None):
+        for r in self.rotators:
+            r.rotate(R, inv=inv, logdet=logdet)
+
+    def setup(self):
+        for r in self.rotators:
+            r.setup()
+
+    def bound(self, R, logdet=None, inv=None):
+        value, grad = 0.0, 0.0
+        for r in self.rotators:
+            b, db = r.bound(R, logdet=logdet, inv=inv)
+            value, grad = value + b, grad + db
+        return value, grad
+
+    def get_bound_terms(self, *args, **kwargs):
+        out = {}
+        for r in self.rotators:
+            out.update(r.get_bound_terms(*args, **kwargs))
         return out
 
 

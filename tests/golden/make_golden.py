@@ -1086,8 +1086,80 @@ def lssm_mixing_plated(name="lssm_mixing_plated", P=3, N=10, D=2, K=2, iters=4):
     save(name, **out)
 
 
+def lssm_varying_rotated(name="lssm_varying_rotated", M=4, N=16, D=2, K=2, P=2, iters=4):
+    """transformations.py:1454-1541 with the array form of RotateGaussianARD (:376-1110): (a) a chain with mixed dynamics
+    A_n = sum_k s_nk B_k rotated together with its loadings after every VB iteration (RotateVaryingMarkovChain, the
+    mixing matrices rotated on variable axis -2 and plate axis -1 with an ARD precision over both variable axes);
+    (b) plated chains with per-chain time-varying dynamics (RotateGaussianMarkovChain)."""
+    from bayespy.nodes import GaussianMarkovChain
+    from bayespy.inference.vmp.transformations import (RotateGaussianARD, RotateVaryingMarkovChain,
+                                                       RotateGaussianMarkovChain, RotationOptimizer)
+    rs = np.random.RandomState(55)
+    out = {}
+    y = rs.randn(M, N).cumsum(axis=-1) * 0.4 + 0.3 * rs.randn(M, N)
+    beta = Gamma(1e-3, 1e-3, plates=(D, K), name="beta")
+    B = GaussianARD(0, beta, shape=(D, K), plates=(1, D), name="B")
+    B_init = 0.5 * rs.randn(1, D, D, K)
+    B.initialize_from_value(B_init)
+    S = GaussianARD(0, 1, shape=(K,), plates=(N - 1, 1), name="S")
+    S_init = rs.randn(N - 1, 1, K)
+    S.initialize_from_value(S_init)
+    A = SumMultiply("dk,k->d", B, S, name="A")
+    X = GaussianMarkovChain(np.zeros(D), 1e-3 * np.identity(D), A, np.ones(D), n=N, name="X")
+    gamma = Gamma(1e-3, 1e-3, plates=(D,), name="gamma")
+    C = GaussianARD(0, gamma, shape=(D,), plates=(M, 1), name="C")
+    C_init = rs.randn(M, 1, D)
+    C.initialize_from_value(C_init)
+    F = SumMultiply("d,d", C, X, name="F")
+    tau = Gamma(1e-3, 1e-3, name="tau")
+    Y = GaussianARD(F, tau, name="Y")
+    Y.observe(y)
+    Q = VB(Y, X, C, gamma, B, beta, S, tau)
+    rotB = RotateGaussianARD(B, beta, axis=-2)
+    rotX = RotateVaryingMarkovChain(X, B, S, rotB)
+    rotC = RotateGaussianARD(C, gamma)
+    Rot = RotationOptimizer(rotX, rotC, D)
+    Ls = []
+    for it in range(iters):
+        Q.update(verbose=False)
+        Rot.rotate(maxiter=10)
+        Ls.append(Q.compute_lowerbound())
+    out.update(a_y=y, a_Binit=B_init, a_Sinit=S_init, a_Cinit=C_init, a_L=Q.L[:iters].copy(), a_Lrot=np.array(Ls))
+    for nm, nd in (("a_X", X), ("a_C", C), ("a_B", B), ("a_beta", beta), ("a_gamma", gamma), ("a_tau", tau)):
+        node_state(nm, nd, out)
+    # (b) plated chains, per-chain time-varying dynamics; an observation per chain
+    alpha = Gamma(1e-3, 1e-3, plates=(D,), name="alpha")
+    A2 = GaussianARD(0, alpha, shape=(D,), plates=(P, N - 1, D), name="A2")
+    A2_init = 0.4 * rs.randn(P, N - 1, D, D)
+    A2.initialize_from_value(A2_init)
+    X2 = GaussianMarkovChain(np.zeros(D), 1e-2 * np.identity(D), A2, np.ones(D), name="X2")
+    assert X2.plates == (P,)
+    gamma2 = Gamma(1e-3, 1e-3, plates=(D,), name="gamma2")
+    C2 = GaussianARD(0, gamma2, shape=(D,), plates=(M, 1, 1), name="C2")
+    C2_init = rs.randn(M, 1, 1, D)
+    C2.initialize_from_value(C2_init)
+    F2 = SumMultiply("d,d", C2, X2, name="F2")
+    y2 = rs.randn(M, P, N)
+    Y2 = GaussianARD(F2, 3.0, name="Y2")
+    Y2.observe(y2)
+    Q2 = VB(Y2, X2, C2, gamma2, A2, alpha)
+    rotA2 = RotateGaussianARD(A2, alpha)
+    rotX2 = RotateGaussianMarkovChain(X2, rotA2)
+    rotC2 = RotateGaussianARD(C2, gamma2)
+    Rot2 = RotationOptimizer(rotX2, rotC2, D)
+    Ls2 = []
+    for it in range(iters):
+        Q2.update(verbose=False)
+        Rot2.rotate(maxiter=10)
+        Ls2.append(Q2.compute_lowerbound())
+    out.update(b_y=y2, b_A2init=A2_init, b_C2init=C2_init, b_L=Q2.L[:iters].copy(), b_Lrot=np.array(Ls2))
+    for nm, nd in (("b_X2", X2), ("b_C2", C2), ("b_A2", A2), ("b_alpha", alpha), ("b_gamma2", gamma2)):
+        node_state(nm, nd, out)
+    save(name, **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["quickstart", "pca", "linalg", "summul", "dist", "gmm", "gmc", "rot", "dot", "mixard", "gmcplates", "gmcvarying", "pcabench", "pcamasked64", "take", "gate", "lssmrot", "gmcmixing", "gradients", "lda", "slice", "gg", "gmcinputs"]
+    which = sys.argv[1:] or ["quickstart", "pca", "linalg", "summul", "dist", "gmm", "gmc", "rot", "dot", "mixard", "gmcplates", "gmcvarying", "pcabench", "pcamasked64", "take", "gate", "lssmrot", "gmcmixing", "gradients", "lda", "slice", "gg", "gmcinputs", "rotgeneral"]
     if "quickstart" in which:
         quickstart()
     if "pca" in which:
@@ -1133,6 +1205,8 @@ if __name__ == "__main__":
         gaussian_gamma_models()
     if "gmcinputs" in which:
         lssm_inputs()
+    if "rotgeneral" in which:
+        lssm_varying_rotated()
     if "pcamasked64" in which:
         pca("pca_masked_64x16", 64, 300, 16, mask_p=0.8, iters=4)
     if "pcabench" in which:

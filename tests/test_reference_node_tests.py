@@ -1,10 +1,11 @@
-"""The reference's OWN node unit tests (bayespy/inference/vmp/nodes/tests/) run against this package's node classes.
+"""The reference's OWN unit tests (bayespy/inference/vmp/nodes/tests/ and bayespy/inference/vmp/tests/) run against this
+package's classes.
 
 The test modules are imported from the staged, unmodified reference (oracle/_ref); every node class they import that
 this package provides (GaussianARD, Gaussian, Gamma, Wishart, Dirichlet, Categorical, Mixture, SumMultiply, Take, Gate,
 GaussianMarkovChain, VaryingGaussianMarkovChain, GaussianGamma, ...) is swapped for ours inside the module, then single reference test
 methods are run as they are: their shapes, random inputs, assertions and finite-difference utilities
-(``assert_message_to_parent``, ``assert_moments``).  65 of the 78 methods of those modules run green; the others are
+(``assert_message_to_parent``, ``assert_moments``).  65 of the 78 node test methods and all 7 methods of vmp/tests (rotations, annealing) run green; the others are
 listed with the reason in NOT_APPLICABLE (they need classes or internals outside the path).  Oracle backend on CPU,
 libbpk under -m gpu."""
 import importlib
@@ -14,6 +15,15 @@ import numpy as np
 import pytest
 
 PASSING = [
+    # bayespy/inference/vmp/tests: the rotation cost functions against true bound differences and numerical gradients
+    # over the reference's whole grid of shapes / plates / axes / precisions, and deterministic annealing
+    ("vmp.test_transformations", "TestRotateGaussianARD.test_cost_function"),
+    ("vmp.test_transformations", "TestRotateGaussianARD.test_cost_gradient"),
+    ("vmp.test_transformations", "TestRotateGaussianMarkovChain.test_cost_function"),
+    ("vmp.test_transformations", "TestRotateGaussianMarkovChain.test_cost_gradient"),
+    ("vmp.test_transformations", "TestRotateVaryingMarkovChain.test_cost_function"),
+    ("vmp.test_transformations", "TestRotateVaryingMarkovChain.test_cost_gradient"),
+    ("vmp.test_annealing", "TestVB.test_annealing"),
     ("test_take", "TestTake.test_message_to_parent"),
     ("test_take", "TestTake.test_moments"),
     ("test_take", "TestTake.test_parent_validity"),
@@ -105,13 +115,19 @@ def _module(name):
         pytest.skip("oracle/_ref is not staged and /root/reference is absent")
     make_ref.import_reference()
     import bayespy_b200.nodes as ours
-    tm = importlib.import_module("bayespy.inference.vmp.nodes.tests." + name)
+    import bayespy_b200.inference.vmp.transformations as our_rotations
+    if name.startswith("vmp."):
+        tm = importlib.import_module("bayespy.inference.vmp.tests." + name[4:])
+    else:
+        tm = importlib.import_module("bayespy.inference.vmp.nodes.tests." + name)
     import bayespy_b200.engine.moments as our_moments
     for attr in dir(tm):
         if not isinstance(getattr(tm, attr), type):
             continue
         if hasattr(ours, attr):
             setattr(tm, attr, getattr(ours, attr))
+        elif attr.startswith("Rotat") and hasattr(our_rotations, attr):
+            setattr(tm, attr, getattr(our_rotations, attr))
         elif attr.endswith("Moments") and attr != "Moments" and hasattr(our_moments, attr):
             setattr(tm, attr, getattr(our_moments, attr))
     if hasattr(tm, "VB"):

@@ -218,3 +218,128 @@ def test_markov_chain_rotation_cost_equals_the_true_bound_change(backend, Dm, N,
             true1 = float(np.asarray(n.lower_bound_contribution()))
             np.testing.assert_allclose(true1 - true0[n], t1[n] - t0[n], rtol=1e-7, atol=1e-7 * abs(true0[n]),
                                        err_msg="rotation cost of %s (alpha rotated: %s)" % (n.name, with_alpha))
+
+
+def _same_state(g, pairs, rtol=1e-6):
+    for nm, node in pairs:
+        for i in range(len(node.u)):
+            ref = g["%s_u%d" % (nm, i)]
+            a, ref = np.broadcast_arrays(np.asarray(node.u[i]), ref)
+            np.testing.assert_allclose(a, ref, rtol=rtol, atol=1e-7 * max(1.0, np.max(np.abs(ref))), err_msg="%s.u[%d]" % (nm, i))
+
+
+def test_mixed_dynamics_rotated_with_loadings_matches_reference(backend):
+    """RotateVaryingMarkovChain + the array form of RotateGaussianARD (variable axis -2, plate axis -1, an ARD precision
+    over both variable axes) + RotationOptimizer after every iteration: bound before and after each rotation and the
+    posterior against the reference (lssm_varying_rotated.npz, part a)."""
+    from bayespy_b200.nodes import GaussianARD, Gamma, SumMultiply, GaussianMarkovChain
+    from bayespy_b200.inference import VB
+    from bayespy_b200.inference.vmp.transformations import (RotateGaussianARD, RotateVaryingMarkovChain,
+                                                            RotationOptimizer)
+    g = golden("lssm_varying_rotated")
+    y = g["a_y"]
+    M, N = y.shape
+    Dm, K = g["a_Binit"].shape[-2:]
+    beta = Gamma(1e-3, 1e-3, plates=(Dm, K), name="beta")
+    B = GaussianARD(0, beta, shape=(Dm, K), plates=(1, Dm), name="B")
+    B.initialize_from_value(g["a_Binit"])
+    S = GaussianARD(0, 1, shape=(K,), plates=(N - 1, 1), name="S")
+    S.initialize_from_value(g["a_Sinit"])
+    A = SumMultiply("dk,k->d", B, S, name="A")
+    X = GaussianMarkovChain(np.zeros(Dm), 1e-3 * np.identity(Dm), A, np.ones(Dm), n=N, name="X")
+    gamma = Gamma(1e-3, 1e-3, plates=(Dm,), name="gamma")
+    C = GaussianARD(0, gamma, shape=(Dm,), plates=(M, 1), name="C")
+    C.initialize_from_value(g["a_Cinit"])
+    F = SumMultiply("d,d", C, X, name="F")
+    tau = Gamma(1e-3, 1e-3, name="tau")
+    Y = GaussianARD(F, tau, name="Y")
+    Y.observe(y)
+    Q = VB(Y, X, C, gamma, B, beta, S, tau)
+    rotB = RotateGaussianARD(B, beta, axis=-2)
+    rotX = RotateVaryingMarkovChain(X, B, S, rotB)
+    rotC = RotateGaussianARD(C, gamma)
+    Rot = RotationOptimizer(rotX, rotC, Dm)
+    iters = len(g["a_L"])
+    Ls = []
+    for _ in range(iters):
+        Q.update(verbose=False)
+        Rot.rotate(maxiter=10)
+        Ls.append(Q.compute_lowerbound())
+    np.testing.assert_allclose(Q.L[:iters], g["a_L"], rtol=1e-6)
+    np.testing.assert_allclose(Ls, g["a_Lrot"], rtol=1e-6)
+    assert np.all(np.array(Ls) >= Q.L[:iters] - 1e-6 * np.abs(Q.L[:iters]))          # a rotation never lowers the bound
+    _same_state(g, (("a_X", X), ("a_C", C), ("a_B", B), ("a_beta", beta), ("a_gamma", gamma), ("a_tau", tau)), rtol=1e-5)
+
+
+def test_plated_chains_with_time_varying_dynamics_rotated_match_reference(backend):
+    """RotateGaussianMarkovChain over chain plates with one transition matrix per chain and step (part b)."""
+    from bayespy_b200.nodes import GaussianARD, Gamma, SumMultiply, GaussianMarkovChain
+    from bayespy_b200.inference import VB
+    from bayespy_b200.inference.vmp.transformations import (RotateGaussianARD, RotateGaussianMarkovChain,
+                                                            RotationOptimizer)
+    g = golden("lssm_varying_rotated")
+    y2 = g["b_y"]
+    M, P, N = y2.shape
+    Dm = g["b_A2init"].shape[-1]
+    alpha = Gamma(1e-3, 1e-3, plates=(Dm,), name="alpha")
+    A2 = GaussianARD(0, alpha, shape=(Dm,), plates=(P, N - 1, Dm), name="A2")
+    A2.initialize_from_value(g["b_A2init"])
+    X2 = GaussianMarkovChain(np.zeros(Dm), 1e-2 * np.identity(Dm), A2, np.ones(Dm), name="X2")
+    assert tuple(X2.plates) == (P,)
+    gamma2 = Gamma(1e-3, 1e-3, plates=(Dm,), name="gamma2")
+    C2 = GaussianARD(0, gamma2, shape=(Dm,), plates=(M, 1, 1), name="C2")
+    C2.initialize_from_value(g["b_C2init"])
+    F2 = SumMultiply("d,d", C2, X2, name="F2")
+    Y2 = GaussianARD(F2, 3.0, name="Y2")
+    Y2.observe(y2)
+    Q2 = VB(Y2, X2, C2, gamma2, A2, alpha)
+    rotA2 = RotateGaussianARD(A2, alpha)
+    rotX2 = RotateGaussianMarkovChain(X2, rotA2)
+    rotC2 = RotateGaussianARD(C2, gamma2)
+    Rot2 = RotationOptimizer(rotX2, rotC2, Dm)
+    iters = len(g["b_L"])
+    Ls = []
+    for _ in range(iters):
+        Q2.update(verbose=False)
+        Rot2.rotate(maxiter=10)
+        Ls.append(Q2.compute_lowerbound())
+    np.testing.assert_allclose(Q2.L[:iters], g["b_L"], rtol=1e-6)
+    np.testing.assert_allclose(Ls, g["b_Lrot"], rtol=1e-6)
+    _same_state(g, (("b_X2", X2), ("b_C2", C2), ("b_A2", A2), ("b_alpha", alpha), ("b_gamma2", gamma2)), rtol=1e-5)
+
+
+def test_switching_chain_rotation_cost_is_the_true_bound_change(backend):
+    """RotateSwitchingMarkovChain (transformations.py:1544-1632) checked the way the reference checks its rotators
+    (tests/test_transformations.py): the cost terms reproduce the true change of every node's bound term under a
+    random rotation, and the gradient agrees with finite differences.  RotateMultiple adds cost functions."""
+    from scipy.optimize import approx_fprime
+    from bayespy_b200.nodes import (GaussianARD, Gaussian, Categorical, SwitchingGaussianMarkovChain)
+    from bayespy_b200.inference.vmp.transformations import (RotateGaussianARD, RotateSwitchingMarkovChain,
+                                                            RotateMultiple)
+    rs = np.random.RandomState(3)
+    Dm, N, K = 2, 6, 3
+    B = GaussianARD(0.5, 4, shape=(Dm,), plates=(K, Dm), name="B")
+    B.initialize_from_value(0.5 * rs.randn(K, Dm, Dm))
+    Z = Categorical(np.ones(K) / K, plates=(N - 1,), name="Z")
+    X = SwitchingGaussianMarkovChain(np.zeros(Dm), np.identity(Dm), B, Z, np.ones(Dm), n=N, name="X")
+    Y = Gaussian(X, np.identity(Dm) + np.ones((Dm, Dm)), name="Y")
+    Y.observe(rs.randn(N, Dm))
+    for _ in range(2):
+        X.update(); B.update(); Z.update()
+    rotX = RotateSwitchingMarkovChain(X, B, Z, RotateGaussianARD(B, axis=-1))
+    before = {n: float(n.lower_bound_contribution()) for n in (X, B)}
+    rotX.setup()
+    R = rs.randn(Dm, Dm)
+    c0, c1 = rotX.get_bound_terms(np.identity(Dm)), rotX.get_bound_terms(R)
+    value, grad = rotX.bound(R)
+    np.testing.assert_allclose(sum(c1.values()), value, rtol=1e-10)
+    num = approx_fprime(R.ravel(), lambda r: rotX.bound(r.reshape(Dm, Dm))[0], 1e-7).reshape(Dm, Dm)
+    np.testing.assert_allclose(grad, num, rtol=1e-4, atol=1e-5)
+    both = RotateMultiple(rotX, rotX)
+    np.testing.assert_allclose(both.bound(R)[0], 2 * value, rtol=1e-12)
+    np.testing.assert_allclose(both.bound(R)[1], 2 * grad, rtol=1e-12)
+    rotX.rotate(R)
+    for n in (X, B):
+        np.testing.assert_allclose(float(n.lower_bound_contribution()) - before[n], c1[n] - c0[n], rtol=1e-6, atol=1e-8)
+    with pytest.raises(ValueError):
+        RotateSwitchingMarkovChain(X, GaussianARD(0, 1, shape=(Dm,), plates=(K + 1, Dm)), Z, RotateGaussianARD(B))
