@@ -116,12 +116,19 @@ class Categorical(ExponentialFamily):
     moment_kind = "categorical"
     _guard_zero_times_inf = True
 
-    def __init__(self, p, plates=None, name="", initialize=True, plates_multiplier=None):
+    def __init__(self, p, plates=None, name="", initialize=True, plates_multiplier=None, **kwargs):
         if isinstance(p, Node):
             if p.moment_kind != "dirichlet":
                 raise ValueError("Expected a Dirichlet-like node")
         else:
-            p = dirichlet_constant(p)
+            p = dirichlet_constant(p)               # invalid probabilities are refused before anything else
+        if plates is not None:
+            from .node import is_subshape
+            if not is_subshape(tuple(p.plates), tuple(plates)):
+                raise ValueError("The plates %s of the parents are not broadcastable to the given plates %s."
+                                 % (tuple(p.plates), tuple(plates)))
+        if kwargs:
+            raise TypeError("Categorical got unexpected keyword arguments: %s" % ", ".join(sorted(kwargs)))
         K = p.dims[0][0]
         super().__init__(p, dims=((K,),), distribution=CategoricalDistribution(K), plates=plates, name=name,
                          initialize=initialize, plates_multiplier=plates_multiplier)

@@ -33,6 +33,12 @@ class MixtureDistribution(Distribution):
 
     def __init__(self, distribution, cluster_plate, n_clusters, ndims, ndims_parents):
         self.raw = distribution
+        # the mixture itself has no cluster axis: a distribution that carries per-plate constants (the number of trials
+        # of a multinomial) gives them up along that axis (mixture.py:37-46)
+        try:
+            self.squeezed = distribution.squeeze(cluster_plate) if hasattr(distribution, "squeeze") else distribution
+        except ValueError as err:
+            raise ValueError("Cannot mix over plate axis {0}: {1}".format(cluster_plate, str(err))) from err
         self.cluster_plate = cluster_plate
         self.K = n_clusters
         self.ndims = ndims
@@ -80,7 +86,20 @@ class MixtureDistribution(Distribution):
         out = []
         for Phi_i, nd in zip(Phi, self.ndims):
             Phi_i = D.asarray(Phi_i)
-            # 0 * inf guard of mixture.py:228-230 is not needed for finite cluster parameters
+            if getattr(self.raw, "zero_times_inf", False):
+                # mixture.py:228-230: a cluster with assignment probability exactly 0 does not count even when its
+                # parameter is -inf (log of a zero probability).  Only the discrete mixed distributions can have that.
+                pd = D.asarray(p)
+                if Phi_i.ndim - nd < -self.cluster_plate:
+                    Phi_i = Phi_i.add_leading(-self.cluster_plate - (Phi_i.ndim - nd))
+                # p (plates.., K) seen with K at the cluster position and unit axes for the variable dims
+                npl = pd.ndim - 1
+                pos = npl + self.cluster_plate + 1                # where the cluster axis goes among the plates
+                if pos < 0:
+                    pd, npl, pos = pd.add_leading(-pos), npl - pos, 0
+                order = list(range(pos)) + [npl] + list(range(pos, npl))
+                pv = DArray(pd.owner, pd.ptr, [pd.shape[i] for i in order], [pd.strides[i] for i in order], pd.dtype)
+                Phi_i = D.nonzero_select(pv.add_trailing(nd), Phi_i)
             out.append(self._weighted_average(Phi_i, nd, p))
         return out
 
@@ -89,10 +108,10 @@ class MixtureDistribution(Distribution):
         return self._weighted_average(g, 0, u_z[0])
 
     def compute_moments_and_cgf(self, phi, mask=True):
-        return self.raw.compute_moments_and_cgf(phi, mask=mask)
+        return self.squeezed.compute_moments_and_cgf(phi, mask=mask)
 
     def compute_fixed_moments_and_f(self, x, mask=True):
-        return self.raw.compute_fixed_moments_and_f(x, mask=True)
+        return self.squeezed.compute_fixed_moments_and_f(x, mask=True)
 
     def compute_message_to_parent(self, parent, index, u, u_z, *u_params):
         if index == 0:
@@ -185,7 +204,10 @@ class MixtureDistribution(Distribution):
         return tuple(plates)
 
     def random(self, *phi, plates=None):
-        return self.raw.random(*phi, plates=plates)
+        return self.squeezed.random(*phi, plates=plates)
+
+    def compute_gradient(self, g, u, phi):
+        return self.squeezed.compute_gradient(g, u, phi)
 
 
 class Mixture(ExponentialFamily):

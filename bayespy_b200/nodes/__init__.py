@@ -9,6 +9,7 @@ from ..engine.gaussian_gamma import GaussianGamma                            # n
 from ..engine.wishart import Wishart                                          # noqa: F401
 from ..engine.dirichlet import Dirichlet                                      # noqa: F401
 from ..engine.categorical import Categorical                                  # noqa: F401
+from ..engine.multinomial import Multinomial                                # noqa: F401
 from ..engine.mixture import Mixture                                          # noqa: F401
 from ..engine.gmc import (GaussianMarkovChain, VaryingGaussianMarkovChain,   # noqa: F401
                           SwitchingGaussianMarkovChain)

@@ -1158,8 +1158,47 @@ def lssm_varying_rotated(name="lssm_varying_rotated", M=4, N=16, D=2, K=2, P=2, 
     save(name, **out)
 
 
+def multinomial_models(name="multinomial"):
+    """nodes/multinomial.py: (a) counts with a Dirichlet prior (posterior in closed form), (b) a mixture of multinomials
+    with a different number of trials per item (the trials array has a unit axis where the cluster axis is)."""
+    from bayespy.nodes import Multinomial
+    rs = np.random.RandomState(9)
+    K, C, N = 4, 3, 40
+    out = {}
+    p = Dirichlet(np.array([1.0, 2.0, 0.5, 1.5]), name="p")
+    x = rs.multinomial(12, [0.1, 0.4, 0.2, 0.3], size=6)
+    X = Multinomial(12, p, plates=(6,), name="X")
+    X.observe(x)
+    Q = VB(X, p)
+    Q.update(repeat=2, verbose=False, tol=0)
+    out.update(a_x=x, a_L=Q.L[:2].copy())
+    node_state("a_p", p, out)
+    # (b)
+    ptrue = rs.dirichlet(np.ones(K), size=C)
+    lab = rs.randint(0, C, size=N)
+    n = rs.randint(5, 30, size=(N, 1))
+    counts = np.array([rs.multinomial(n[i, 0], ptrue[lab[i]]) for i in range(N)])
+    alpha = Dirichlet(np.ones(C), name="alpha")
+    Z = Categorical(alpha, plates=(N,), name="Z")
+    z_init = rs.randint(0, C, size=N)
+    Z.initialize_from_value(z_init)
+    P = Dirichlet(np.ones(K), plates=(C,), name="P")
+    Xm = Mixture(Z, Multinomial, n, P, name="Xm")
+    Xm.observe(counts)
+    Q = VB(Xm, P, Z, alpha)
+    Q.update(repeat=6, verbose=False, tol=0)
+    out.update(b_n=n, b_counts=counts, b_zinit=z_init, b_L=Q.L[:6].copy())
+    for nm, nd in (("b_P", P), ("b_Z", Z), ("b_alpha", alpha)):
+        node_state(nm, nd, out)
+    # an unobserved multinomial: moments and log-normaliser
+    Xf = Multinomial(np.array([[3], [7]]), np.array([[0.2, 0.8], [0.5, 0.5], [0.9, 0.1]]), name="Xf")
+    assert Xf.plates == (2, 3)
+    node_state("c_Xf", Xf, out)
+    save(name, **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["quickstart", "pca", "linalg", "summul", "dist", "gmm", "gmc", "rot", "dot", "mixard", "gmcplates", "gmcvarying", "pcabench", "pcamasked64", "take", "gate", "lssmrot", "gmcmixing", "gradients", "lda", "slice", "gg", "gmcinputs", "rotgeneral"]
+    which = sys.argv[1:] or ["quickstart", "pca", "linalg", "summul", "dist", "gmm", "gmc", "rot", "dot", "mixard", "gmcplates", "gmcvarying", "pcabench", "pcamasked64", "take", "gate", "lssmrot", "gmcmixing", "gradients", "lda", "slice", "gg", "gmcinputs", "rotgeneral", "multinomial"]
     if "quickstart" in which:
         quickstart()
     if "pca" in which:
@@ -1207,6 +1246,8 @@ if __name__ == "__main__":
         lssm_inputs()
     if "rotgeneral" in which:
         lssm_varying_rotated()
+    if "multinomial" in which:
+        multinomial_models()
     if "pcamasked64" in which:
         pca("pca_masked_64x16", 64, 300, 16, mask_p=0.8, iters=4)
     if "pcabench" in which:

@@ -5,7 +5,7 @@ The test modules are imported from the staged, unmodified reference (oracle/_ref
 this package provides (GaussianARD, Gaussian, Gamma, Wishart, Dirichlet, Categorical, Mixture, SumMultiply, Take, Gate,
 GaussianMarkovChain, VaryingGaussianMarkovChain, GaussianGamma, ...) is swapped for ours inside the module, then single reference test
 methods are run as they are: their shapes, random inputs, assertions and finite-difference utilities
-(``assert_message_to_parent``, ``assert_moments``).  65 of the 78 node test methods and all 7 methods of vmp/tests (rotations, annealing) run green; the others are
+(``assert_message_to_parent``, ``assert_moments``).  72 of the 83 node test methods and all 7 methods of vmp/tests (rotations, annealing) run green; the others are
 listed with the reason in NOT_APPLICABLE (they need classes or internals outside the path).  Oracle backend on CPU,
 libbpk under -m gpu."""
 import importlib
@@ -43,9 +43,15 @@ PASSING = [
     ("test_deterministic", "TestTile.test_message_to_parent"),
     ("test_categorical", "TestCategorical.test_constant"),
     ("test_categorical", "TestCategorical.test_gradient"),
+    ("test_categorical", "TestCategorical.test_init"),
     ("test_categorical", "TestCategorical.test_initialization"),
     ("test_categorical", "TestCategorical.test_moments"),
     ("test_categorical", "TestCategorical.test_observed"),
+    ("test_multinomial", "TestMultinomial.test_init"),
+    ("test_multinomial", "TestMultinomial.test_moments"),
+    ("test_multinomial", "TestMultinomial.test_lower_bound"),
+    ("test_multinomial", "TestMultinomial.test_mixture"),
+    ("test_multinomial", "TestMultinomial.test_mixture_with_count_array"),
     ("test_dirichlet", "TestDirichlet.test_constant"),
     ("test_dirichlet", "TestDirichlet.test_init"),
     ("test_dirichlet", "TestDirichlet.test_moments"),
@@ -60,6 +66,7 @@ PASSING = [
     ("test_mixture", "TestMixture.test_mask_to_parent"),
     ("test_mixture", "TestMixture.test_message_to_child"),
     ("test_mixture", "TestMixture.test_message_to_parent"),
+    ("test_mixture", "TestMixture.test_nans"),
     ("test_mixture", "TestMixture.test_random"),
     ("test_gaussian", "TestGaussianARD.test_init"),
     ("test_gaussian", "TestGaussianARD.test_initialization"),
@@ -99,8 +106,6 @@ NOT_APPLICABLE = {
     ("test_node", "TestNode.test_message_to_parent"): "exercises the reference's Node base-class internals (subclasses it inside the test)",
     ("test_node", "TestSlice.test_message_to_child"): "exercises the reference's Node base-class internals (subclasses it inside the test)",
     ("test_node", "TestSlice.test_message_to_parent"): "exercises the reference's Node base-class internals (subclasses it inside the test)",
-    ("test_categorical", "TestCategorical.test_init"): "Multinomial-style constructor argument",
-    ("test_mixture", "TestMixture.test_nans"): "uses the reference's Moments classes / converters directly",
     ("test_gaussian", "TestConcatGaussian.test_message_to_parents"): "node class outside the path (GaussianGamma / ConcatGaussian)",
     ("test_gaussian", "TestConcatGaussian.test_moments"): "node class outside the path (GaussianGamma / ConcatGaussian)",
     ("test_gaussian_markov_chain", "TestGaussianMarkovChain.test_message_to_child"): "uses the reference's Moments classes / converters directly",
