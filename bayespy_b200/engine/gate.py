@@ -28,6 +28,8 @@ class Gate(Deterministic):
         if len(X.plates) < abs(gated_plate):
             raise ValueError("The gated node does not have a plate axis is gated")
         self.K = K = int(X.plates[gated_plate])
+        if isinstance(Z, Node) and hasattr(Z, "_to_categorical"):
+            Z = Z._to_categorical()
         if not isinstance(Z, Node):
             Z = categorical_constant(Z, K)
         if Z.moment_kind != "categorical" or tuple(Z.dims) != ((K,),):

@@ -682,6 +682,8 @@ class SwitchingGaussianMarkovChain(GaussianMarkovChain):
         K, Dm = int(B.plates[-2]), int(B.plates[-1])
         if tuple(B.dims[0]) != (Dm,):
             raise ValueError("Third parent should have a last plate equal to the dimensionality of the system.")
+        if isinstance(Z, Node) and hasattr(Z, "_to_categorical"):
+            Z = Z._to_categorical()
         if not isinstance(Z, Node):
             Z = categorical_constant(Z, K)
         if Z.moment_kind != "categorical" or tuple(Z.dims) != ((K,),):

@@ -227,6 +227,8 @@ class Mixture(ExponentialFamily):
         if len(mix_plates) < -cluster_plate:
             raise ValueError("The mixed distribution does not have a plates axis for the cluster plate axis")
         K = mix_plates.pop(cluster_plate)
+        if isinstance(z, Node) and hasattr(z, "_to_categorical"):
+            z = z._to_categorical()         # e.g. a categorical Markov chain seen as categorical variables over time
         if isinstance(z, Node):
             if z.moment_kind != "categorical":
                 raise ValueError("z must be a categorical-like node")

@@ -10,6 +10,7 @@ from ..engine.wishart import Wishart                                          # 
 from ..engine.dirichlet import Dirichlet                                      # noqa: F401
 from ..engine.categorical import Categorical                                  # noqa: F401
 from ..engine.multinomial import Multinomial                                # noqa: F401
+from ..engine.categorical_markov_chain import CategoricalMarkovChain      # noqa: F401
 from ..engine.mixture import Mixture                                          # noqa: F401
 from ..engine.gmc import (GaussianMarkovChain, VaryingGaussianMarkovChain,   # noqa: F401
                           SwitchingGaussianMarkovChain)

@@ -132,3 +132,58 @@ def test_user_guide_inference_example(backend, capsys):
     assert Q.converged and abs(Q.iter - 847) <= 5
     assert "Converged at iteration %d." % Q.iter in out
     np.testing.assert_allclose(Q.L[Q.iter - 1], -1.222506e+02, rtol=2e-6)
+
+
+def test_hmm_doc_example_known_and_unknown_parameters(backend, capsys):
+    """hmm.rst:8-11,35-96 ('Iteration 1: loglike=-1.095883e+02', the exact posterior of the weather chain) and
+    :150-290 ('Iteration 1: loglike=-9.963054e+02 ... Iteration 8: loglike=-9.235053e+02, Converged at iteration 8'):
+    a categorical Markov chain under a categorical and then a Gaussian mixture, with seeded draws from the chain and
+    from the mixture (host RNG in the reference's order)."""
+    from bayespy_b200.nodes import CategoricalMarkovChain, Categorical, Mixture, Dirichlet, Gaussian
+    from bayespy_b200.inference import VB
+    np.random.seed(1)
+    a0 = [0.6, 0.4]
+    A = [[0.7, 0.3], [0.4, 0.6]]
+    N = 100
+    Z = CategoricalMarkovChain(a0, A, states=N)
+    P = [[0.1, 0.4, 0.5], [0.6, 0.3, 0.1]]
+    Y = Mixture(Z, Categorical, P)
+    weather = Z.random()
+    activity = Mixture(weather, Categorical, P).random()
+    Y.observe(activity)
+    Q = VB(Y, Z)
+    Q.update()
+    L = _loglikes(capsys.readouterr().out)
+    np.testing.assert_allclose(L, [-1.095883e+02], rtol=5e-7)
+    pz = np.asarray(Z._to_categorical().get_moments()[0])
+    assert pz.shape == (N, 2) and np.allclose(pz.sum(axis=-1), 1.0)
+    # unknown parameters, Gaussian emissions
+    mu = np.array([[0, 0], [3, 4], [6, 0]])
+    std, K, N = 2.0, 3, 200
+    p0 = np.ones(K) / K
+    q = 0.9
+    r = (1 - q) / (K - 1)
+    P = q * np.identity(K) + r * (np.ones((3, 3)) - np.identity(3))
+    y = np.zeros((N, 2))
+    z = np.zeros(N)
+    state = np.random.choice(K, p=p0)
+    for n in range(N):
+        z[n] = state
+        y[n, :] = std * np.random.randn(2) + mu[state]
+        state = np.random.choice(K, p=P[state])
+    a0 = Dirichlet(1e-3 * np.ones(K))
+    A = Dirichlet(1e-3 * np.ones((K, K)))
+    Z = CategoricalMarkovChain(a0, A, states=N)
+    Lambda = std ** (-2) * np.identity(2)
+    Y = Mixture(Z, Gaussian, mu, Lambda)
+    Y.observe(y)
+    Q = VB(Y, Z, A, a0)
+    Q.update(repeat=1000)
+    out = capsys.readouterr().out
+    L = _loglikes(out)
+    assert len(L) == 8 and "Converged at iteration 8." in out
+    np.testing.assert_allclose(L[0], -9.963054e+02, rtol=5e-7)
+    np.testing.assert_allclose(L[7], -9.235053e+02, rtol=5e-7)
+    # the chain recovers most of the simulated states
+    zhat = np.argmax(np.asarray(Z._to_categorical().get_moments()[0]), axis=-1)
+    assert np.mean(zhat == z) > 0.9
