@@ -81,10 +81,36 @@ def multiplier_to_parent(own, parent):
     return r
 
 
-class Node:
+class _NodeType(type):
+    """Every node class takes the reference's ``plotter=`` keyword (node.py:241-246, :860-866); it is kept for
+    ``plot()`` and never reaches the class's own constructor."""
+
+    def __call__(cls, *args, plotter=None, **kwargs):
+        obj = super().__call__(*args, **kwargs)
+        obj._plotter = plotter
+        return obj
+
+
+class Node(metaclass=_NodeType):
     """Base class: plates, parents/children, masks, message reduction."""
 
     moment_kind = None
+    _plotter = None
+
+    def set_plotter(self, plotter):
+        self._plotter = plotter
+
+    def plot(self, fig=None, **kwargs):
+        """Plot with the node's plotter, if one was given (node.py:850-866)."""
+        if self._plotter is None:
+            raise Exception("No plotter defined, can not plot")
+        return self._plotter(self, fig=fig, **kwargs)
+
+    def show(self):
+        print(str(self))
+
+    def has_plotter(self):
+        return self._plotter is not None
     _id_counter = 0
 
     def __init__(self, *parents, dims=None, plates=None, name="", notify_parents=True, plates_multiplier=None):

@@ -50,6 +50,15 @@ class VB:
         self.cputime = np.array(())
         self.l = {node: np.array([]) for node in self.model}
         self.autosave_iterations = autosave_iterations
+        if not autosave_filename:
+            # like the reference (vmp.py:86-97): a dated file name in the temporary directory, so that save() / load()
+            # without a name work; no file is created before the first save
+            import datetime
+            import tempfile
+            date = datetime.datetime.today().strftime("%Y%m%d%H%M%S")
+            fd = tempfile.NamedTemporaryFile(prefix="vb_autosave_%s_" % date, suffix=".hdf5", delete=True)
+            autosave_filename = fd.name
+            fd.close()
         self.autosave_filename = autosave_filename
         names = [node.name for node in self.model]
         if len(names) != len(self.model):
@@ -71,6 +80,13 @@ class VB:
             if node.name == name:
                 return node
         raise ValueError("Node %s not found" % (name,))
+
+    def plot(self, *nodes, **kwargs):
+        """Plot the given nodes (default: every node that has a plotter), vmp.py:767-790."""
+        nodes = self.model if len(nodes) == 0 else [self[n] for n in nodes if n is not None]
+        for node in nodes:
+            if node.has_plotter():
+                node.plot(**kwargs)
 
     # ---- checkpoints (vmp.py:237-356; container and hierarchy: inference/checkpoint.py) ------------------------
     def save(self, *nodes, filename=None):

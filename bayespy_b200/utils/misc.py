@@ -101,3 +101,28 @@ def sum_multiply_to_plates(*arrays, to_plates=(), from_plates=None, ndim=0):
     elif y.ndim < want:
         y = y.add_leading(want - y.ndim)
     return _ret(y, on_device)
+
+
+# ---- small host helpers model scripts use (bookkeeping on NumPy arrays, nothing of the device path) ----------------
+def trues(shape):
+    return np.ones(shape, dtype=bool)
+
+
+def atleast_nd(X, d):
+    X = np.asarray(X)
+    return X.reshape((1,) * (d - X.ndim) + X.shape) if X.ndim < d else X
+
+
+def rmse(y1, y2, axis=None):
+    return np.sqrt(np.mean((np.asarray(y1) - np.asarray(y2)) ** 2, axis=axis))
+
+
+def grid(x1, x2):
+    """All pairs (x1_i, x2_j) as an (M*N, 2) array, x1 varying fastest (misc.py:588-591)."""
+    X1, X2 = np.meshgrid(x1, x2)
+    return np.column_stack((X1.ravel(), X2.ravel()))
+
+
+def identity(*shape):
+    n = int(np.prod(shape)) if shape else 1
+    return np.identity(n).reshape(tuple(shape) + tuple(shape))

@@ -1,0 +1,14 @@
+"""The calls with which the reference's demo scripts (bayespy/demos/*.py) are run — small sizes, plotting off — both
+when make_golden.py records the reference's printed bounds and when tests/test_reference_demos.py replays the
+unmodified scripts through this package."""
+
+CALLS = {
+    "pca": lambda m: m.run(M=8, N=40, D_y=2, D=4, rotate=True, maxiter=12, plot=False),
+    "lssm": lambda m: m.demo(M=4, N=40, D=3, maxiter=8, rotate=True, plot=False, monitor=False),
+    "hmm": lambda m: m.run(N=60, maxiter=5, plot=False),
+    "annealing": lambda m: m.run(N=100, maxiter=15, plot=False),
+    "pattern_search": lambda m: m.run(M=8, N=30, D_y=2, D=4, maxiter=15, plot=False),
+    "stochastic_inference": lambda m: m.run(N=2000, N_batch=50, maxiter=8, plot=False),
+    "lda": lambda m: m.run(n_documents=5, n_topics=3, n_vocabulary=8, n_words=300, maxiter=5, seed=1),
+    "lssm_sd": lambda m: m.demo(N=60, maxiter=5, D=2, K=2, plot=False, monitor=False),
+}
