@@ -33,6 +33,7 @@ def categorical_constant(x, K):
 class CategoricalMoments:
     """``CategoricalMoments(K)`` as the reference exposes it for ``Constant`` (categorical.py:20-90): integer class
     labels become one-hot moments on the device (bit-exact)."""
+    kind = "categorical"
 
     def __init__(self, categories):
         if not isinstance(categories, (int, np.integer)) or categories < 0:

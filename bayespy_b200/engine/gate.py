@@ -23,6 +23,9 @@ class Gate(Deterministic):
         if gated_plate >= 0:
             raise ValueError("Cluster plate must be negative integer")
         self.gated_plate = int(gated_plate)
+        if moments is not None:
+            from . import moments as _moments
+            X = _moments.ensure(X, moments)              # e.g. an array with ``moments=GaussianMoments(())`` (gate.py:56-62)
         if not isinstance(X, Node):
             raise ValueError("X must be a node or moments should be provided")
         if len(X.plates) < abs(gated_plate):

@@ -151,6 +151,12 @@ class Node(metaclass=_NodeType):
     def _moments(self, value):
         self.__dict__["_moments_tag"] = value
 
+    @staticmethod
+    def _ensure_moments(node, moments_class, **kwargs):
+        """node.py:330-372: ``node`` (a node or an array) as a node with the wanted kind of moments."""
+        from . import moments
+        return moments.ensure(node, moments_class, **kwargs)
+
     # ---- graph ------------------------------------------------------------------------------
     def _add_child(self, child, index):
         self.children.append((child, index))

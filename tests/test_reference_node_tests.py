@@ -5,7 +5,7 @@ The test modules are imported from the staged, unmodified reference (oracle/_ref
 this package provides (GaussianARD, Gaussian, Gamma, Wishart, Dirichlet, Categorical, Mixture, SumMultiply, Take, Gate,
 GaussianMarkovChain, VaryingGaussianMarkovChain, GaussianGamma, ...) is swapped for ours inside the module, then single reference test
 methods are run as they are: their shapes, random inputs, assertions and finite-difference utilities
-(``assert_message_to_parent``, ``assert_moments``).  75 of the 86 node test methods and all 7 methods of vmp/tests (rotations, annealing) run green; the others are
+(``assert_message_to_parent``, ``assert_moments``).  79 of the 86 node test methods and all 7 methods of vmp/tests (rotations, annealing) run green; the others are
 listed with the reason in NOT_APPLICABLE (they need classes or internals outside the path).  Oracle backend on CPU,
 libbpk under -m gpu."""
 import importlib
@@ -28,6 +28,9 @@ PASSING = [
     ("test_take", "TestTake.test_moments"),
     ("test_take", "TestTake.test_parent_validity"),
     ("test_take", "TestTake.test_plates_multiplier_from_parent"),
+    ("test_gate", "TestGate.test_init"),
+    ("test_gate", "TestGate.test_message_to_child"),
+    ("test_gate", "TestGate.test_message_to_parent"),
     ("test_gate", "TestGate.test_mask_to_parent"),
     ("test_dot", "TestSumMultiply.test_compute_moments"),
     ("test_dot", "TestSumMultiply.test_message_to_parent"),
@@ -91,6 +94,7 @@ PASSING = [
     ("test_gaussian_markov_chain", "TestGaussianMarkovChain.test_message_to_parents"),
     ("test_gaussian_markov_chain", "TestGaussianMarkovChain.test_message_to_v"),
     ("test_gaussian_markov_chain", "TestGaussianMarkovChain.test_message_to_parents_with_inputs"),
+    ("test_gaussian_markov_chain", "TestGaussianMarkovChain.test_message_to_child"),
     ("test_gaussian_markov_chain", "TestGaussianMarkovChain.test_plates"),
     ("test_gaussian_markov_chain", "TestGaussianMarkovChain.test_smoothing"),
     ("test_gaussian_markov_chain", "TestVaryingGaussianMarkovChain.test_plates_from_parents"),
@@ -102,16 +106,12 @@ PASSING = [
 ]
 
 NOT_APPLICABLE = {
-    ("test_gate", "TestGate.test_init"): "uses the reference's Moments classes / converters directly",
-    ("test_gate", "TestGate.test_message_to_child"): "uses the reference's Moments classes / converters directly",
-    ("test_gate", "TestGate.test_message_to_parent"): "uses the reference's Moments classes / converters directly",
     ("test_node", "TestNode.test_compute_message"): "exercises the reference's Node base-class internals (subclasses it inside the test)",
     ("test_node", "TestNode.test_message_to_parent"): "exercises the reference's Node base-class internals (subclasses it inside the test)",
     ("test_node", "TestSlice.test_message_to_child"): "exercises the reference's Node base-class internals (subclasses it inside the test)",
     ("test_node", "TestSlice.test_message_to_parent"): "exercises the reference's Node base-class internals (subclasses it inside the test)",
     ("test_gaussian", "TestConcatGaussian.test_message_to_parents"): "node class outside the path (GaussianGamma / ConcatGaussian)",
     ("test_gaussian", "TestConcatGaussian.test_moments"): "node class outside the path (GaussianGamma / ConcatGaussian)",
-    ("test_gaussian_markov_chain", "TestGaussianMarkovChain.test_message_to_child"): "uses the reference's Moments classes / converters directly",
     ("test_gaussian_markov_chain", "TestVaryingGaussianMarkovChain.test_message_to_child"): "API detail: IndexError: list index out of range",
 }
 
