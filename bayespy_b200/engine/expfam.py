@@ -229,6 +229,26 @@ class ExponentialFamily(Node):
             g = [D.mul(gi, 1.0 / self.annealing) for gi in g]
         return g
 
+    def logpdf(self, X, mask=True):
+        """log q(X) of this node's current distribution (expfamily.py:483-497); a host array over the plates."""
+        if mask is not True:
+            raise NotImplementedError("Mask not yet implemented")
+        from .gaussian import dense
+        u, f = self._distribution.compute_fixed_moments_and_f(X, mask=mask)
+        Z = D.add(D.asarray(self.g.materialize() if hasattr(self.g, "materialize") else self.g), D.asarray(f))
+        for phi_d, u_d, nd in zip(self.phi, u, self.ndims):
+            phi_d = D.asarray(dense(phi_d))
+            u_d = D.asarray(dense(u_d))
+            npl = max(phi_d.ndim, u_d.ndim) - nd
+            keys_p = list(range(npl))
+            keys_d = list(range(100, 100 + nd))
+            Z = D.add(Z, D.sum_product([phi_d, u_d], [keys_p[npl - (phi_d.ndim - nd):] + keys_d,
+                                                       keys_p[npl - (u_d.ndim - nd):] + keys_d], keys_p))
+        return np.asarray(Z)
+
+    def pdf(self, X, mask=True):
+        return np.exp(self.logpdf(X, mask=mask))
+
     def observe(self, x, *args, mask=True):
         """Fix the moments on the observed plates and propagate the mask
         (expfamily.py:369-398)."""

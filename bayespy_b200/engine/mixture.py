@@ -247,3 +247,23 @@ class Mixture(ExponentialFamily):
 
     def get_moments(self):
         return [dense(ui) for ui in self.u]
+
+    def integrated_logpdf_from_parents(self, x, index):
+        """log of the predictive density of ``x`` with the cluster assignment integrated out and the cluster parameters
+        averaged in log scale, log sum_k p_k exp(<log p(x | theta_k)>) (mixture.py:491-545).  A query for plots and
+        model checks: the result comes back as a host array with the plates of ``x``."""
+        if index != 0:
+            raise NotImplementedError()
+        dist = self._distribution
+        u, f = dist.squeezed.compute_fixed_moments_and_f(x)
+        u_parents = self.moments_from_parents()
+        L = dist.compute_message_to_parent(self.parents[0], 0, [dense(ui) for ui in u], *u_parents)[0]   # (.., K)
+        with np.errstate(divide="ignore"):
+            w = D.add(L, D.log(D.asarray(u_parents[0][0])))
+        w = D.asarray(w).contiguous()
+        K = w.shape[-1]
+        P = tuple(w.shape[:-1])
+        from .. import _bpk
+        soft, g = DArray.empty(P + (K,)), DArray.empty(P)
+        _bpk.get().softmax_moments(w.ptr, int(np.prod(P, dtype=np.int64)) if P else 1, K, soft.ptr, g.ptr)
+        return np.asarray(D.sub(D.asarray(f), g))            # g = -logsumexp

@@ -1221,7 +1221,7 @@ def reference_demos(name="demos"):
         except RuntimeError as err:           # Q.save() in a container without HDF5: no reference output for this demo
             print(demo, "not recorded:", err)
             continue
-        L = [float(v) for v in re.findall(r"loglike=([-+]?(?:[0-9.]+e[-+][0-9]+|inf|nan))", buf.getvalue())]
+        L = [float(v) for v in re.findall(r"(?:loglike=|integrated pdf: )([-+]?(?:[0-9.]+(?:e[-+][0-9]+)?|inf|nan))", buf.getvalue())]
         print(demo, len(L), L[:2], L[-1:])
         out[demo] = np.array(L)
     save(name, **out)

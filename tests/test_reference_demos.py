@@ -53,7 +53,7 @@ def test_reference_demo_runs_unchanged(backend, as_bayespy, demo, capsys):
     m = _load(as_bayespy, demo)
     np.random.seed(1)
     CALLS[demo](m)
-    L = np.array([float(v) for v in re.findall(r"loglike=([-+]?(?:[0-9.]+e[-+][0-9]+|inf|nan))", capsys.readouterr().out)])
+    L = np.array([float(v) for v in re.findall(r"(?:loglike=|integrated pdf: )([-+]?(?:[0-9.]+(?:e[-+][0-9]+)?|inf|nan))", capsys.readouterr().out)])
     assert len(L) > 0
     g = golden("demos")
     if demo in g.files:
