@@ -1,0 +1,178 @@
+"""Differential tests: the same model script is built twice — with the unmodified reference (oracle/_ref) and with this
+package — from the same seeds, updated for a few iterations, and every bound is compared.  The models sit at the edges
+of the node set: chains driven by inputs (time-varying dynamics, masks, constant inputs), Gaussian-gamma variables
+under SumMultiply / Take / Gate / Mixture / scalar plates, a categorical Markov chain with per-step transitions over
+plates and as the selector of a switching state-space model, multinomial counts over plates.
+
+Host-logic tests (plates, broadcasting, message routing): they run on the oracle backend; the kernels underneath are
+the ones the ``-m gpu`` parity tests exercise."""
+import numpy as np
+import pytest
+
+
+@pytest.fixture
+def both(oracle_backend):
+    from oracle import make_ref
+    make_ref.build()
+    if not make_ref.available():
+        pytest.skip("oracle/_ref is not staged and /root/reference is absent")
+    make_ref.import_reference()
+    import bayespy.inference as ref_inference
+    import bayespy.nodes as ref_nodes
+    import bayespy_b200.inference as our_inference
+    import bayespy_b200.nodes as our_nodes
+    return (ref_nodes, ref_inference), (our_nodes, our_inference)
+
+
+def chain_inputs_time_varying(N, rs):
+    D_, K, T = 2, 2, 6
+    U = rs.randn(T - 1, K)
+    A = N.GaussianARD(0, 1.0, shape=(D_ + K,), plates=(T - 1, D_), name="A")
+    A.initialize_from_value(0.3 * rs.randn(T - 1, D_, D_ + K))
+    nu = N.Gamma(2.0, 2.0, plates=(T - 1, D_), name="nu")
+    X = N.GaussianMarkovChain(np.zeros(D_), np.identity(D_), A, nu, inputs=U, name="X")
+    Y = N.Gaussian(X, 3.0 * np.identity(D_), name="Y")
+    Y.observe(rs.randn(T, D_), mask=rs.rand(T) < 0.8)
+    return [X, A, nu, Y]
+
+
+def gaussian_gamma_product(N, rs):
+    Kd, P, M = 3, 4, 5
+    b1 = N.Gamma(2.0, 2.0, plates=(P, 1), name="b1")
+    W = N.GaussianGamma(np.zeros(Kd), np.identity(Kd), 3.0, b1, plates=(P, 1), name="W")
+    b2 = N.Gamma(1.5, 1.0, plates=(1, M), name="b2")
+    Z = N.GaussianGamma(np.ones(Kd), 2 * np.identity(Kd), 2.0, b2, plates=(1, M), name="Z")
+    F = N.SumMultiply("k,k->", W, Z, name="F")
+    Y = N.GaussianARD(F, 1.0, name="Y")
+    Y.observe(rs.randn(P, M))
+    return [Y, W, Z, b1, b2]
+
+
+def gaussian_gamma_times_constant_and_gaussian(N, rs):
+    Kd, P = 3, 6
+    b1 = N.Gamma(2.0, 2.0, plates=(P,), name="b1")
+    W = N.GaussianGamma(np.zeros(Kd), np.identity(Kd), 3.0, b1, plates=(P,), name="W")
+    X = N.GaussianARD(0, 1, shape=(Kd,), plates=(P,), name="X")
+    X.initialize_from_value(rs.randn(P, Kd))
+    F = N.SumMultiply("k,k,k->", W, X, rs.randn(P, Kd), name="F")
+    tau = N.Gamma(1e-2, 1e-2, name="tau")
+    Y = N.GaussianARD(F, tau, name="Y")
+    Y.observe(rs.randn(P))
+    return [Y, W, X, b1, tau]
+
+
+def gaussian_gamma_taken_by_index(N, rs):
+    G, Nn, Dm = 3, 12, 2
+    b = N.Gamma(2.0, 2.0, plates=(G,), name="b")
+    W = N.GaussianGamma(np.zeros(Dm), np.identity(Dm), 3.0, b, plates=(G,), name="W")
+    m = N.Take(W, rs.randint(0, G, size=Nn), name="m")
+    Y = N.Gaussian(m, 2.0 * np.identity(Dm), name="Y")
+    Y.observe(rs.randn(Nn, Dm))
+    return [Y, W, b]
+
+
+def gaussian_gamma_gated(N, rs):
+    K, Nn, Dm = 3, 10, 2
+    b = N.Gamma(2.0, 2.0, plates=(K,), name="b")
+    W = N.GaussianGamma(np.zeros(Dm), np.identity(Dm), 3.0, b, plates=(K,), name="W")
+    Z = N.Categorical(np.ones(K) / K, plates=(Nn,), name="Z")
+    Y = N.Gaussian(N.Gate(Z, W, name="m"), 2.0 * np.identity(Dm), name="Y")
+    Y.observe(rs.randn(Nn, Dm))
+    return [Y, W, b, Z]
+
+
+def mixture_with_gaussian_gamma_means(N, rs):
+    K, Nn, Dm = 3, 15, 2
+    mu = N.GaussianGamma(np.zeros(Dm), 0.1 * np.identity(Dm), 2.0, 2.0, plates=(K,), name="mu")
+    L = N.Wishart(Dm + 1.0, np.identity(Dm), plates=(K,), name="L")
+    Z = N.Categorical(N.Dirichlet(np.ones(K), name="al"), plates=(Nn,), name="Z")
+    Z.initialize_from_value(rs.randint(0, K, size=Nn))
+    Y = N.Mixture(Z, N.Gaussian, mu, L, name="Y")
+    Y.observe(rs.randn(Nn, Dm))
+    return [Y, mu, L, Z]
+
+
+def scalar_gaussian_gamma_over_plates(N, rs):
+    P, M = 3, 4
+    lam = N.Gamma(2.0, 1.0, plates=(P, 1), name="lam")
+    b = N.Gamma(1.0, 1.0, plates=(1, M), name="b")
+    mc = N.GaussianGamma(rs.randn(P, M), lam.as_wishart(ndim=0), 1.5, b, ndim=0, name="mc")
+    Y = N.GaussianARD(mc, 2.0, plates=(5, P, M), name="Y")
+    Y.observe(rs.randn(5, P, M), mask=rs.rand(5, P, M) < 0.8)
+    return [Y, mc, lam, b]
+
+
+def hidden_markov_chains_with_per_step_transitions(N, rs):
+    Kc, T, P = 3, 9, 2
+    a0 = N.Dirichlet(np.ones(Kc), plates=(P,), name="a0")
+    A = N.Dirichlet(np.ones(Kc), plates=(P, T - 1, Kc), name="A")
+    Zc = N.CategoricalMarkovChain(a0, A, name="Zc")
+    mu = N.GaussianARD(0, 1e-1, shape=(2,), plates=(Kc,), name="mu")
+    mu.initialize_from_value(rs.randn(Kc, 2))
+    Y = N.Mixture(Zc, N.Gaussian, mu, np.identity(2), name="Y")
+    Y.observe(rs.randn(P, T, 2))
+    return [Y, Zc, mu, A, a0]
+
+
+def switching_state_space_model_selected_by_a_markov_chain(N, rs):
+    Dm, T, K = 2, 10, 2
+    a0 = N.Dirichlet(np.ones(K), name="a0")
+    A = N.Dirichlet(np.ones(K), plates=(K,), name="A")
+    Zc = N.CategoricalMarkovChain(a0, A, states=T - 1, name="Zc")
+    B = N.GaussianARD(0, 1.0, shape=(Dm,), plates=(K, Dm), name="B")
+    B.initialize_from_value(0.4 * rs.randn(K, Dm, Dm))
+    X = N.SwitchingGaussianMarkovChain(np.zeros(Dm), np.identity(Dm), B, Zc, np.ones(Dm), n=T, name="X")
+    Y = N.Gaussian(X, 4.0 * np.identity(Dm), name="Y")
+    Y.observe(rs.randn(T, Dm))
+    return [X, B, Zc, A, a0, Y]
+
+
+def multinomial_counts_over_plates(N, rs):
+    Kc, P = 4, 5
+    p = N.Dirichlet(np.ones(Kc), plates=(P,), name="p")
+    n = rs.randint(3, 9, size=(6, P))
+    X = N.Multinomial(n, p, name="Xm")
+    X.observe(np.array([[rs.multinomial(n[i, j], np.ones(Kc) / Kc) for j in range(P)] for i in range(6)]))
+    return [X, p]
+
+
+MODELS = [chain_inputs_time_varying, gaussian_gamma_product, gaussian_gamma_times_constant_and_gaussian,
+          gaussian_gamma_taken_by_index, gaussian_gamma_gated, mixture_with_gaussian_gamma_means,
+          scalar_gaussian_gamma_over_plates, hidden_markov_chains_with_per_step_transitions,
+          switching_state_space_model_selected_by_a_markov_chain, multinomial_counts_over_plates]
+
+
+@pytest.mark.parametrize("model", MODELS, ids=[m.__name__ for m in MODELS])
+def test_same_script_same_bounds(both, model):
+    bounds = []
+    for nodes, inference in both:
+        np.random.seed(7)
+        Q = inference.VB(*model(nodes, np.random.RandomState(11)))
+        Q.update(repeat=4, verbose=False, tol=0)
+        bounds.append(np.array(Q.L[:4]))
+    assert np.all(np.isfinite(bounds[0]))
+    np.testing.assert_allclose(bounds[1], bounds[0], rtol=1e-9)
+
+
+def test_constant_inputs_equal_inputs_repeated_over_time(both):
+    """An input signal with a unit time plate drives every step (the reference's own message code does not take that
+    form): same bounds as the reference gets with the rows written out over chains and time."""
+    def model(N, tiled):
+        rs = np.random.RandomState(5)
+        D_, K, T, P = 2, 2, 8, 3
+        z = rs.randn(1, K)
+        if tiled:
+            z = np.broadcast_to(np.repeat(z, T - 1, axis=0), (P, T - 1, K)).copy()
+        A = N.GaussianARD(0, 1.0, shape=(D_ + K,), plates=(P, 1, D_), name="A")
+        A.initialize_from_value(0.3 * rs.randn(P, 1, D_, D_ + K))
+        nu = N.Gamma(2.0, 2.0, plates=(P, 1, D_), name="nu")
+        X = N.GaussianMarkovChain(np.zeros(D_), np.identity(D_), A, nu, inputs=z, n=T, name="X")
+        Y = N.Gaussian(X, 3.0 * np.identity(D_), name="Y")
+        Y.observe(rs.randn(P, T, D_))
+        return [X, A, nu, Y]
+    (ref_nodes, ref_inf), (our_nodes, our_inf) = both
+    Qr = ref_inf.VB(*model(ref_nodes, True))
+    Qr.update(repeat=4, verbose=False, tol=0)
+    Qo = our_inf.VB(*model(our_nodes, False))
+    Qo.update(repeat=4, verbose=False, tol=0)
+    np.testing.assert_allclose(Qo.L[:4], Qr.L[:4], rtol=1e-9)
