@@ -747,6 +747,29 @@ class Gaussian(_GaussianNode):
         super().__init__(mu, Lambda, dims=((Dm,), (Dm, Dm)), distribution=dist,
                          plates=plates, name=name, initialize=initialize, plates_multiplier=plates_multiplier)
 
+    def rotate(self, R, inv=None, logdet=None, Q=None):
+        """q(x) -> q(R x) (gaussian.py:1451-1520 without the plate mixing Q): natural parameters by R^-T, moments by R,
+        log-normaliser by -log|det R|; the plated arrays are transformed on the device."""
+        if Q is not None:
+            raise NotImplementedError("Plate mixing of a Gaussian node is not implemented")
+        R = np.asarray(R, dtype=np.float64)
+        invR = np.linalg.inv(R) if inv is None else np.asarray(inv, dtype=np.float64)
+        logdetR = np.linalg.slogdet(R)[1] if logdet is None else float(logdet)
+        K = self.dims[0][0]
+        Rd, iRT = D.asarray(R), D.asarray(np.ascontiguousarray(invR.T))
+
+        def rot_vec(a, Mx):
+            a = D.asarray(dense(a))
+            return D.sum_product([Mx, a.reshape((-1, K))], [["i", "k"], ["n", "k"]], ["n", "i"]).reshape(a.shape)
+
+        def rot_mat(a, Mx):
+            a = D.asarray(dense(a))
+            return D.sum_product([Mx, a.reshape((-1, K, K)), Mx], [["i", "k"], ["n", "k", "l"], ["j", "l"]],
+                                 ["n", "i", "j"]).reshape(a.shape)
+        self.phi = [rot_vec(self.phi[0], iRT), rot_mat(self.phi[1], iRT)]
+        self.u = [rot_vec(self.u[0], Rd), rot_mat(self.u[1], Rd)]
+        self.g = D.affine(D.asarray(self.g), 1.0, -logdetR)
+
     def initialize_from_parameters(self, mu, Lambda):
         """q <- N(mu, Lambda^-1)  (gaussian.py:1420-1423)."""
         from .wishart import wishart_constant

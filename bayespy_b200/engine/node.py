@@ -111,6 +111,10 @@ class Node(metaclass=_NodeType):
 
     def has_plotter(self):
         return self._plotter is not None
+
+    def lowerbound(self):
+        """This node's term of the lower bound as a float (node.py:844-848)."""
+        return float(self.lower_bound_contribution())
     _id_counter = 0
 
     def __init__(self, *parents, dims=None, plates=None, name="", notify_parents=True, plates_multiplier=None):

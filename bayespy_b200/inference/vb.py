@@ -81,6 +81,22 @@ class VB:
                 return node
         raise ValueError("Node %s not found" % (name,))
 
+    def use_logging(self, use):
+        """Send the iteration lines to the ``logging`` module instead of printing them (vmp.py:111-118)."""
+        if use:
+            import logging
+            self.print = logging.getLogger(__name__).info
+        else:
+            self.print = print
+
+    def set_autosave(self, filename, iterations=None, nodes=None):
+        """vmp.py:121-126."""
+        self.autosave_filename = filename
+        self.filename = filename
+        self.autosave_nodes = nodes
+        if iterations is not None:
+            self.autosave_iterations = iterations
+
     def plot(self, *nodes, **kwargs):
         """Plot the given nodes (default: every node that has a plotter), vmp.py:767-790."""
         nodes = self.model if len(nodes) == 0 else [self[n] for n in nodes if n is not None]

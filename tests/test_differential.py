@@ -176,3 +176,37 @@ def test_constant_inputs_equal_inputs_repeated_over_time(both):
     Qo = our_inf.VB(*model(our_nodes, False))
     Qo.update(repeat=4, verbose=False, tol=0)
     np.testing.assert_allclose(Qo.L[:4], Qr.L[:4], rtol=1e-9)
+
+
+def test_gaussian_rotate_and_vb_conveniences(both, tmp_path, caplog):
+    """``Gaussian.rotate`` leaves a consistent q (moments and log-normaliser recomputed from the rotated natural
+    parameters agree) and matches the reference's; ``VB.set_autosave`` / ``use_logging`` / ``node.lowerbound``."""
+    import logging
+    (ref_nodes, ref_inf), (our_nodes, our_inf) = both
+    rs = np.random.RandomState(2)
+    data, R = rs.randn(7, 3), rs.randn(3, 3)
+    states = []
+    for N in (ref_nodes, our_nodes):
+        X = N.Gaussian(np.ones(3), 2.0 * np.identity(3), plates=(7,), name="X")
+        Y = N.Gaussian(X, np.identity(3), name="Y")
+        Y.observe(data)
+        X.update()
+        X.rotate(R)
+        states.append(([np.asarray(v) for v in X.u], [np.asarray(v) for v in X.phi], np.asarray(X.g)))
+        last = X
+    for a, b in zip(states[0][0] + states[0][1], states[1][0] + states[1][1]):
+        np.testing.assert_allclose(b, a, rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(states[1][2], states[0][2], rtol=1e-10)
+    u, g = last._distribution.compute_moments_and_cgf(last.phi)
+    np.testing.assert_allclose(np.asarray(u[0]), states[1][0][0], rtol=1e-9)
+    np.testing.assert_allclose(np.asarray(g), states[1][2], rtol=1e-9)
+    assert last.lowerbound() == float(last.lower_bound_contribution())
+    Q = our_inf.VB(Y, last)
+    fn = str(tmp_path / "auto.ckpt")
+    Q.set_autosave(fn, iterations=1)
+    Q.use_logging(True)
+    with caplog.at_level(logging.INFO):
+        Q.update(repeat=2, tol=0)
+    assert any("loglike" in r.getMessage() for r in caplog.records) and any("Auto-saved" in r.getMessage() for r in caplog.records)
+    import os
+    assert os.path.exists(fn) or os.path.exists(fn + ".npz")
