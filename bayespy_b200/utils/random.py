@@ -41,3 +41,12 @@ def covariance(D, size=(), nu=None):
         size = (size,)
     W = np.random.randn(*(size + (D, nu)))
     return np.linalg.inv(W @ np.swapaxes(W, -1, -2) / nu)
+
+
+def bernoulli(p, size=None):
+    """Boolean draws with success probabilities ``p`` (utils/random.py:236-244)."""
+    if isinstance(size, int):
+        size = (size,)
+    if size is None:
+        size = np.shape(p)
+    return np.random.rand(*size) < p

@@ -187,3 +187,33 @@ def test_hmm_doc_example_known_and_unknown_parameters(backend, capsys):
     # the chain recovers most of the simulated states
     zhat = np.argmax(np.asarray(Z._to_categorical().get_moments()[0]), axis=-1)
     assert np.mean(zhat == z) > 0.9
+
+
+def test_bmm_doc_example(oracle_backend, capsys):
+    """bmm.rst:8-11,28-125: a Bernoulli mixture with Beta-distributed success probabilities —
+    'Iteration 1: loglike=-6.872145e+02 ... Iteration 17: loglike=-5.236921e+02, Converged at iteration 17'.
+    (Host-logic test: the Beta / Bernoulli nodes are the two-category case of the Dirichlet / Multinomial kernels.)"""
+    from bayespy_b200.nodes import Categorical, Dirichlet, Beta, Mixture, Bernoulli
+    from bayespy_b200.inference import VB
+    from bayespy_b200.utils import random
+    np.random.seed(1)
+    p0 = [0.1, 0.9, 0.1, 0.9, 0.1, 0.9, 0.1, 0.9, 0.1, 0.9]
+    p1 = [0.1, 0.1, 0.1, 0.1, 0.1, 0.9, 0.9, 0.9, 0.9, 0.9]
+    p2 = [0.9, 0.9, 0.9, 0.9, 0.9, 0.1, 0.1, 0.1, 0.1, 0.1]
+    p = np.array([p0, p1, p2])
+    z = random.categorical([1 / 3, 1 / 3, 1 / 3], size=100)
+    x = random.bernoulli(p[z])
+    N, D, K = 100, 10, 10
+    R = Dirichlet(K * [1e-5], name="R")
+    Z = Categorical(R, plates=(N, 1), name="Z")
+    P = Beta([0.5, 0.5], plates=(D, K), name="P")
+    X = Mixture(Z, Bernoulli, P)
+    Q = VB(Z, R, X, P)
+    P.initialize_from_random()
+    X.observe(x)
+    Q.update(repeat=1000)
+    out = capsys.readouterr().out
+    L = _loglikes(out)
+    assert len(L) == 17 and "Converged at iteration 17." in out
+    np.testing.assert_allclose(L[0], -6.872145e+02, rtol=5e-7)
+    np.testing.assert_allclose(L[16], -5.236921e+02, rtol=5e-7)

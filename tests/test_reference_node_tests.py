@@ -5,7 +5,7 @@ The test modules are imported from the staged, unmodified reference (oracle/_ref
 this package provides (GaussianARD, Gaussian, Gamma, Wishart, Dirichlet, Categorical, Mixture, SumMultiply, Take, Gate,
 GaussianMarkovChain, VaryingGaussianMarkovChain, GaussianGamma, ...) is swapped for ours inside the module, then single reference test
 methods are run as they are: their shapes, random inputs, assertions and finite-difference utilities
-(``assert_message_to_parent``, ``assert_moments``).  79 of the 86 node test methods and all 7 methods of vmp/tests (rotations, annealing) run green; the others are
+(``assert_message_to_parent``, ``assert_moments``).  79 of the 86 node test methods (plus the 14 of test_{bernoulli,binomial,beta}.py on the oracle backend) and all 7 methods of vmp/tests (rotations, annealing) run green; the others are
 listed with the reason in NOT_APPLICABLE (they need classes or internals outside the path).  Oracle backend on CPU,
 libbpk under -m gpu."""
 import importlib
@@ -175,12 +175,35 @@ def test_reference_node_test(backend, module, test):
     assert not problems, problems[0][1]
 
 
+# Nodes added after the last GPU session of the round: the two-category cases of the Dirichlet / Multinomial nodes, on the
+# same kernels.  Their reference tests run on the oracle backend.
+PASSING_HOST_ONLY = [(m, "%s.%s" % (c, t)) for m, c, ts in (
+    ("test_bernoulli", "TestBernoulli", ("test_init", "test_mixture", "test_moments", "test_observed", "test_random")),
+    ("test_binomial", "TestBinomial", ("test_init", "test_mixture", "test_mixture_with_count_array", "test_moments",
+                                       "test_observed", "test_random")),
+    ("test_beta", "TestBeta", ("test_init", "test_moments", "test_random")),
+) for t in ts]
+
+
+@pytest.mark.parametrize("module,test", PASSING_HOST_ONLY, ids=["%s::%s" % mt for mt in PASSING_HOST_ONLY])
+def test_reference_node_test_on_the_oracle_backend(oracle_backend, module, test):
+    tm = _module(module)
+    cls, method = test.split(".")
+    case = getattr(tm, cls)(method)
+    np.random.seed(0)
+    result = unittest.TestResult()
+    case.run(result)
+    problems = result.errors + result.failures
+    assert not problems, problems[0][1]
+
+
 def test_the_two_lists_cover_the_reference_modules():
     """Every test method of the twelve modules is either run above or listed with its reason."""
     seen = set()
-    for name in sorted({m for m, _ in PASSING} | {m for m, _ in NOT_APPLICABLE}):
+    for name in sorted({m for m, _ in PASSING} | {m for m, _ in NOT_APPLICABLE} | {m for m, _ in PASSING_HOST_ONLY}):
         tm = _module(name)
         for c in _cases(unittest.defaultTestLoader.loadTestsFromModule(tm)):
             parts = c.id().split(".")
             seen.add((name, parts[-2] + "." + parts[-1]))
+    seen -= set(PASSING_HOST_ONLY)
     assert seen == set(PASSING) | set(NOT_APPLICABLE)
