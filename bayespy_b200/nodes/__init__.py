@@ -12,6 +12,7 @@ from ..engine.categorical import Categorical                                  # 
 from ..engine.multinomial import Multinomial                                # noqa: F401
 from ..engine.categorical_markov_chain import CategoricalMarkovChain      # noqa: F401
 from ..engine.binomial import Beta, Bernoulli, Binomial                         # noqa: F401
+from ..engine.poisson import Poisson, Exponential                              # noqa: F401
 from ..engine.mixture import Mixture                                          # noqa: F401
 from ..engine.gmc import (GaussianMarkovChain, VaryingGaussianMarkovChain,   # noqa: F401
                           SwitchingGaussianMarkovChain)

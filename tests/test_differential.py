@@ -136,10 +136,36 @@ def multinomial_counts_over_plates(N, rs):
     return [X, p]
 
 
+def poisson_counts_with_gamma_rates(N, rs):
+    lam = N.Gamma(2.0, 1.0, plates=(4,), name="lam")
+    X = N.Poisson(lam, plates=(10, 4), name="X")
+    X.observe(rs.poisson(3.0, size=(10, 4)), mask=rs.rand(10, 4) < 0.9)
+    return [X, lam]
+
+
+def bernoulli_mixture(N, rs):
+    K, Nn, Dd = 3, 20, 4
+    Z = N.Categorical(N.Dirichlet(np.ones(K), name="R"), plates=(Nn, 1), name="Z")
+    Z.initialize_from_value(rs.randint(0, K, size=(Nn, 1)))
+    P = N.Beta([0.5, 0.5], plates=(Dd, K), name="P")
+    X = N.Mixture(Z, N.Bernoulli, P, name="X")
+    X.observe(rs.rand(Nn, Dd) < 0.4)
+    return [X, P, Z]
+
+
+def binomial_counts_over_plates(N, rs):
+    p = N.Beta([1.0, 2.0], plates=(3,), name="p")
+    n = rs.randint(2, 9, size=(5, 3))
+    X = N.Binomial(n, p, name="X")
+    X.observe(rs.binomial(n, 0.3))
+    return [X, p]
+
+
 MODELS = [chain_inputs_time_varying, gaussian_gamma_product, gaussian_gamma_times_constant_and_gaussian,
           gaussian_gamma_taken_by_index, gaussian_gamma_gated, mixture_with_gaussian_gamma_means,
           scalar_gaussian_gamma_over_plates, hidden_markov_chains_with_per_step_transitions,
-          switching_state_space_model_selected_by_a_markov_chain, multinomial_counts_over_plates]
+          switching_state_space_model_selected_by_a_markov_chain, multinomial_counts_over_plates,
+          poisson_counts_with_gamma_rates, bernoulli_mixture, binomial_counts_over_plates]
 
 
 @pytest.mark.parametrize("model", MODELS, ids=[m.__name__ for m in MODELS])
@@ -210,3 +236,19 @@ def test_gaussian_rotate_and_vb_conveniences(both, tmp_path, caplog):
     assert any("loglike" in r.getMessage() for r in caplog.records) and any("Auto-saved" in r.getMessage() for r in caplog.records)
     import os
     assert os.path.exists(fn) or os.path.exists(fn + ".npz")
+
+
+def test_exponential_is_gamma_with_unit_shape(both):
+    """``Exponential(l)`` (a stub that raises in the reference, exponential.py:61) is ``Gamma(1, l)``."""
+    _, (N, I) = both
+    Ls = []
+    for make in (lambda b: N.Exponential(b, plates=(6,), name="E"), lambda b: N.Gamma(1, b, plates=(6,), name="E")):
+        rs = np.random.RandomState(4)
+        b = N.Gamma(2.0, 1.0, name="b")
+        E = make(b)
+        Y = N.GaussianARD(0, E, plates=(5, 6), name="Y")
+        Y.observe(rs.randn(5, 6))
+        Q = I.VB(Y, E, b)
+        Q.update(repeat=3, verbose=False, tol=0)
+        Ls.append(Q.L[:3].copy())
+    np.testing.assert_array_equal(Ls[0], Ls[1])
