@@ -13,6 +13,7 @@ from ..engine.multinomial import Multinomial                                # no
 from ..engine.categorical_markov_chain import CategoricalMarkovChain      # noqa: F401
 from ..engine.binomial import Beta, Bernoulli, Binomial                         # noqa: F401
 from ..engine.poisson import Poisson, Exponential                              # noqa: F401
+from ..engine.add import Add                                                   # noqa: F401
 from ..engine.mixture import Mixture                                          # noqa: F401
 from ..engine.gmc import (GaussianMarkovChain, VaryingGaussianMarkovChain,   # noqa: F401
                           SwitchingGaussianMarkovChain)

@@ -161,11 +161,21 @@ def binomial_counts_over_plates(N, rs):
     return [X, p]
 
 
+def sum_of_independent_gaussians(N, rs):
+    X = N.Gaussian(np.zeros(2), np.identity(2), plates=(3,), name="X")
+    Y = N.GaussianARD(1.0, 2.0, shape=(2,), name="Y2")
+    Z = N.Add(X, Y, rs.randn(3, 2), name="Z")
+    tau = N.Gamma(1e-2, 1e-2, name="tau")
+    W = N.GaussianARD(Z, tau, ndim=1, plates=(4, 3), name="W")
+    W.observe(rs.randn(4, 3, 2), mask=rs.rand(4, 3) < 0.8)
+    return [W, X, Y, tau]
+
+
 MODELS = [chain_inputs_time_varying, gaussian_gamma_product, gaussian_gamma_times_constant_and_gaussian,
           gaussian_gamma_taken_by_index, gaussian_gamma_gated, mixture_with_gaussian_gamma_means,
           scalar_gaussian_gamma_over_plates, hidden_markov_chains_with_per_step_transitions,
           switching_state_space_model_selected_by_a_markov_chain, multinomial_counts_over_plates,
-          poisson_counts_with_gamma_rates, bernoulli_mixture, binomial_counts_over_plates]
+          poisson_counts_with_gamma_rates, sum_of_independent_gaussians, bernoulli_mixture, binomial_counts_over_plates]
 
 
 @pytest.mark.parametrize("model", MODELS, ids=[m.__name__ for m in MODELS])
