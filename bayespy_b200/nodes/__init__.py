@@ -14,6 +14,7 @@ from ..engine.categorical_markov_chain import CategoricalMarkovChain      # noqa
 from ..engine.binomial import Beta, Bernoulli, Binomial                         # noqa: F401
 from ..engine.poisson import Poisson, Exponential                              # noqa: F401
 from ..engine.add import Add                                                   # noqa: F401
+from ..engine.concatenate import Concatenate                                  # noqa: F401
 from ..engine.mixture import Mixture                                          # noqa: F401
 from ..engine.gmc import (GaussianMarkovChain, VaryingGaussianMarkovChain,   # noqa: F401
                           SwitchingGaussianMarkovChain)

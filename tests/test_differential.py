@@ -171,11 +171,21 @@ def sum_of_independent_gaussians(N, rs):
     return [W, X, Y, tau]
 
 
+def concatenated_groups(N, rs):
+    a = N.GaussianARD(0, 1.0, shape=(2,), plates=(3,), name="a")
+    b = N.GaussianARD(1, 2.0, shape=(2,), plates=(4,), name="b")
+    Z = N.Concatenate(a, b, name="Z")
+    tau = N.Gamma(1e-2, 1e-2, name="tau")
+    Y = N.GaussianARD(Z, tau, ndim=1, plates=(5, 7), name="Y")
+    Y.observe(rs.randn(5, 7, 2))          # (a mask through Concatenate raises in the reference: its mask split is off)
+    return [Y, a, b, tau]
+
+
 MODELS = [chain_inputs_time_varying, gaussian_gamma_product, gaussian_gamma_times_constant_and_gaussian,
           gaussian_gamma_taken_by_index, gaussian_gamma_gated, mixture_with_gaussian_gamma_means,
           scalar_gaussian_gamma_over_plates, hidden_markov_chains_with_per_step_transitions,
           switching_state_space_model_selected_by_a_markov_chain, multinomial_counts_over_plates,
-          poisson_counts_with_gamma_rates, sum_of_independent_gaussians, bernoulli_mixture, binomial_counts_over_plates]
+          poisson_counts_with_gamma_rates, sum_of_independent_gaussians, concatenated_groups, bernoulli_mixture, binomial_counts_over_plates]
 
 
 @pytest.mark.parametrize("model", MODELS, ids=[m.__name__ for m in MODELS])

@@ -5,7 +5,7 @@ The test modules are imported from the staged, unmodified reference (oracle/_ref
 this package provides (GaussianARD, Gaussian, Gamma, Wishart, Dirichlet, Categorical, Mixture, SumMultiply, Take, Gate,
 GaussianMarkovChain, VaryingGaussianMarkovChain, GaussianGamma, ...) is swapped for ours inside the module, then single reference test
 methods are run as they are: their shapes, random inputs, assertions and finite-difference utilities
-(``assert_message_to_parent``, ``assert_moments``).  79 of the 86 node test methods (plus the 16 of test_{bernoulli,binomial,beta,poisson}.py on the oracle backend) and all 7 methods of vmp/tests (rotations, annealing) run green; the others are
+(``assert_message_to_parent``, ``assert_moments``).  79 of the 86 node test methods (plus the 20 of test_{bernoulli,binomial,beta,poisson,concatenate}.py on the oracle backend) and all 7 methods of vmp/tests (rotations, annealing) run green; the others are
 listed with the reason in NOT_APPLICABLE (they need classes or internals outside the path).  Oracle backend on CPU,
 libbpk under -m gpu."""
 import importlib
@@ -183,6 +183,8 @@ PASSING_HOST_ONLY = [(m, "%s.%s" % (c, t)) for m, c, ts in (
                                        "test_observed", "test_random")),
     ("test_beta", "TestBeta", ("test_init", "test_moments", "test_random")),
     ("test_poisson", "TestPoisson", ("test_init", "test_moments")),
+    ("test_concatenate", "TestConcatenate", ("test_init", "test_mask_to_parent", "test_message_to_child",
+                                             "test_message_to_parent")),
 ) for t in ts]
 
 
