@@ -15,6 +15,7 @@ from ..engine.binomial import Beta, Bernoulli, Binomial                         
 from ..engine.poisson import Poisson, Exponential                              # noqa: F401
 from ..engine.add import Add                                                   # noqa: F401
 from ..engine.concatenate import Concatenate                                  # noqa: F401
+from ..engine.concat_gaussian import ConcatGaussian                           # noqa: F401
 from ..engine.mixture import Mixture                                          # noqa: F401
 from ..engine.gmc import (GaussianMarkovChain, VaryingGaussianMarkovChain,   # noqa: F401
                           SwitchingGaussianMarkovChain)

@@ -5,7 +5,7 @@ The test modules are imported from the staged, unmodified reference (oracle/_ref
 this package provides (GaussianARD, Gaussian, Gamma, Wishart, Dirichlet, Categorical, Mixture, SumMultiply, Take, Gate,
 GaussianMarkovChain, VaryingGaussianMarkovChain, GaussianGamma, ...) is swapped for ours inside the module, then single reference test
 methods are run as they are: their shapes, random inputs, assertions and finite-difference utilities
-(``assert_message_to_parent``, ``assert_moments``).  79 of the 86 node test methods (plus the 20 of test_{bernoulli,binomial,beta,poisson,concatenate}.py on the oracle backend) and all 7 methods of vmp/tests (rotations, annealing) run green; the others are
+(``assert_message_to_parent``, ``assert_moments``).  79 of the 86 node test methods (plus 22 on the oracle backend: test_{bernoulli,binomial,beta,poisson,concatenate}.py and TestConcatGaussian) and all 7 methods of vmp/tests (rotations, annealing) run green; the others are
 listed with the reason in NOT_APPLICABLE (they need classes or internals outside the path).  Oracle backend on CPU,
 libbpk under -m gpu."""
 import importlib
@@ -110,8 +110,6 @@ NOT_APPLICABLE = {
     ("test_node", "TestNode.test_message_to_parent"): "exercises the reference's Node base-class internals (subclasses it inside the test)",
     ("test_node", "TestSlice.test_message_to_child"): "exercises the reference's Node base-class internals (subclasses it inside the test)",
     ("test_node", "TestSlice.test_message_to_parent"): "exercises the reference's Node base-class internals (subclasses it inside the test)",
-    ("test_gaussian", "TestConcatGaussian.test_message_to_parents"): "node class outside the path (GaussianGamma / ConcatGaussian)",
-    ("test_gaussian", "TestConcatGaussian.test_moments"): "node class outside the path (GaussianGamma / ConcatGaussian)",
     ("test_gaussian_markov_chain", "TestVaryingGaussianMarkovChain.test_message_to_child"): "API detail: IndexError: list index out of range",
 }
 
@@ -183,6 +181,7 @@ PASSING_HOST_ONLY = [(m, "%s.%s" % (c, t)) for m, c, ts in (
                                        "test_observed", "test_random")),
     ("test_beta", "TestBeta", ("test_init", "test_moments", "test_random")),
     ("test_poisson", "TestPoisson", ("test_init", "test_moments")),
+    ("test_gaussian", "TestConcatGaussian", ("test_message_to_parents", "test_moments")),
     ("test_concatenate", "TestConcatenate", ("test_init", "test_mask_to_parent", "test_message_to_child",
                                              "test_message_to_parent")),
 ) for t in ts]
