@@ -11,7 +11,7 @@ from .. import darray as D
 from ..darray import DArray
 from .dirichlet import Dirichlet, DirichletDistribution
 from .expfam import Distribution, ExponentialFamily
-from .node import Constant, Node, broadcast_plates
+from .node import Constant, Deterministic, Node, broadcast_plates
 
 
 def beta_constant(p):
@@ -54,9 +54,37 @@ class Beta(Dirichlet):
         if initialize:
             self.initialize_from_prior()
 
+    def complement(self):
+        return Complement(self)
+
     def __str__(self):
         a = self.phi[0].numpy()
         return "%s ~ Beta(a, b)\n  a = \n%s\n  b = \n%s\n" % (self.name, a[..., 0], a[..., 1])
+
+
+class Complement(Deterministic):
+    """1 - p of a beta-like node: the two moments [log p, log(1-p)] swap places, and so does a message (beta.py:178-203)."""
+    moment_kind = "dirichlet"
+
+    def __init__(self, p, name=""):
+        p = ensure_beta(p)
+        super().__init__(p, dims=p.dims, name=name)
+
+    @staticmethod
+    def _swap(a):
+        a = D.asarray(a)
+        st = list(a.strides)
+        esz = 8
+        st[-1] = -st[-1]
+        return DArray(a.owner, a.ptr + (a.shape[-1] - 1) * a.strides[-1] * esz, a.shape, st, a.dtype)
+
+    def _compute_moments(self, u_p):
+        return [self._swap(u_p[0]).contiguous()]
+
+    def _compute_message_to_parent(self, index, m, u_p):
+        if index != 0:
+            raise IndexError()
+        return [None if m[0] is None else self._swap(m[0]).contiguous()]
 
 
 class BinomialDistribution(Distribution):

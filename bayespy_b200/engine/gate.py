@@ -117,3 +117,14 @@ class Gate(Deterministic):
                                          sizes=self._sizes(i)))
             return out
         raise ValueError("Invalid parent index")
+
+
+def Choose(z, *nodes):
+    """Plate elements picked from several nodes by a categorical variable (gate.py:219-250): a ``Gate`` over the
+    ``Concatenate`` of the nodes along a new last plate axis.
+
+        z = [0, 0, 2, 1];  Choose(z, x0, x1, x2).get_moments()[0]  ->  [<x0>, <x0>, <x2>, <x1>]"""
+    from .concatenate import Concatenate
+    from . import moments
+    z = moments.ensure(z, moments._categorical_moments()(len(nodes)))
+    return Gate(z, Concatenate(*[n[..., None] for n in nodes]))

@@ -267,3 +267,15 @@ class Mixture(ExponentialFamily):
         soft, g = DArray.empty(P + (K,)), DArray.empty(P)
         _bpk.get().softmax_moments(w.ptr, int(np.prod(P, dtype=np.int64)) if P else 1, K, soft.ptr, g.ptr)
         return np.asarray(D.sub(D.asarray(f), g))            # g = -logsumexp
+
+
+def MultiMixture(thetas, *mixture_args, **kwargs):
+    """A mixture over several cluster axes with as many categorical variables (mixture.py:548-566): nested ``Mixture``
+    nodes, the i-th assignment given i trailing unit plates so that the mixed axes stay separate."""
+    thetas = [t if isinstance(t, Node) else np.asarray(t) for t in thetas]
+    N = len(thetas)
+    thetas = [t[(Ellipsis,) + i * (None,)] for i, t in enumerate(thetas)]
+    args = thetas[:1]
+    for t in thetas[1:]:
+        args += [Mixture, t]
+    return Mixture(*(args + list(mixture_args)), **kwargs)

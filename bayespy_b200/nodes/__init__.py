@@ -11,13 +11,13 @@ from ..engine.dirichlet import Dirichlet                                      # 
 from ..engine.categorical import Categorical                                  # noqa: F401
 from ..engine.multinomial import Multinomial                                # noqa: F401
 from ..engine.categorical_markov_chain import CategoricalMarkovChain      # noqa: F401
-from ..engine.binomial import Beta, Bernoulli, Binomial                         # noqa: F401
+from ..engine.binomial import Beta, Bernoulli, Binomial, Complement                         # noqa: F401
 from ..engine.poisson import Poisson, Exponential                              # noqa: F401
 from ..engine.add import Add                                                   # noqa: F401
 from ..engine.concatenate import Concatenate                                  # noqa: F401
 from ..engine.concat_gaussian import ConcatGaussian                           # noqa: F401
-from ..engine.mixture import Mixture                                          # noqa: F401
+from ..engine.mixture import Mixture, MultiMixture                                          # noqa: F401
 from ..engine.gmc import (GaussianMarkovChain, VaryingGaussianMarkovChain,   # noqa: F401
                           SwitchingGaussianMarkovChain)
 from ..engine.take import Take                                                # noqa: F401
-from ..engine.gate import Gate                                                # noqa: F401
+from ..engine.gate import Gate, Choose                                                # noqa: F401

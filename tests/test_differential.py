@@ -181,11 +181,36 @@ def concatenated_groups(N, rs):
     return [Y, a, b, tau]
 
 
+def mixture_over_two_cluster_axes(N, rs):
+    K1, K2, Nn = 2, 3, 12
+    z1 = N.Categorical(N.Dirichlet(np.ones(K1), name="r1"), plates=(Nn,), name="z1")
+    z2 = N.Categorical(N.Dirichlet(np.ones(K2), name="r2"), plates=(Nn,), name="z2")
+    z1.initialize_from_value(rs.randint(0, K1, size=Nn))
+    z2.initialize_from_value(rs.randint(0, K2, size=Nn))
+    mu = N.GaussianARD(0, 1e-1, plates=(K1, K2), name="mu")
+    mu.initialize_from_value(rs.randn(K1, K2))
+    X = N.MultiMixture([z1, z2], N.GaussianARD, mu, 2.0, name="X")
+    X.observe(rs.randn(Nn))
+    return [X, mu, z1, z2]
+
+
+def chosen_and_complemented(N, rs):
+    x0, x1, x2 = (N.GaussianARD(m, 1.0, name="x%d" % i) for i, m in enumerate((0.0, 10.0, 20.0)))
+    z = N.Categorical(np.ones(3) / 3, plates=(6,), name="z")
+    Y = N.GaussianARD(N.Choose(z, x0, x1, x2), 2.0, name="Y")
+    Y.observe(rs.randn(6) * 5 + 10)
+    p = N.Beta([2.0, 3.0], name="p")
+    B = N.Bernoulli(p.complement(), plates=(8,), name="B")
+    B.observe(rs.rand(8) < 0.3)
+    return [Y, z, x0, x1, x2, B, p]
+
+
 MODELS = [chain_inputs_time_varying, gaussian_gamma_product, gaussian_gamma_times_constant_and_gaussian,
           gaussian_gamma_taken_by_index, gaussian_gamma_gated, mixture_with_gaussian_gamma_means,
           scalar_gaussian_gamma_over_plates, hidden_markov_chains_with_per_step_transitions,
           switching_state_space_model_selected_by_a_markov_chain, multinomial_counts_over_plates,
-          poisson_counts_with_gamma_rates, sum_of_independent_gaussians, concatenated_groups, bernoulli_mixture, binomial_counts_over_plates]
+          poisson_counts_with_gamma_rates, sum_of_independent_gaussians, concatenated_groups, mixture_over_two_cluster_axes,
+          chosen_and_complemented, bernoulli_mixture, binomial_counts_over_plates]
 
 
 @pytest.mark.parametrize("model", MODELS, ids=[m.__name__ for m in MODELS])
