@@ -78,8 +78,8 @@ class GammaDistribution(Distribution):
     def compute_message_to_parent(self, parent, index, u_self, u_a, u_b):
         """gamma.py:96-113."""
         if index == 0:
-            raise NotImplementedError("Message to the shape parameter of Gamma is not supported "
-                                      "(the reference needs a GammaShape node for it)")
+            # to the shape a, whose moments are [a, lgamma(a)]: [<log x> + <log b>, -1]  (gamma.py:96-106)
+            return [D.add(u_self[1], u_b[1]), D.asarray(-1.0)]
         elif index == 1:
             return [D.mul(u_self[0], -1.0), u_a[0]]
         raise ValueError("Index out of bounds")
@@ -162,3 +162,55 @@ class Gamma(ExponentialFamily):
         a = self.phi[1].numpy()
         b = -self.phi[0].numpy()
         return "%s ~ Gamma(a, b)\n  a =\n%s\n  b =\n%s\n" % (self.name, a, b)
+
+
+def invpsi(x):
+    """Inverse digamma function on host arrays: Minka's initial guess and five Newton steps (misc.py:1404-1429,
+    the same recipe so that estimates agree digit for digit)."""
+    import scipy.special as sp
+    x = np.asarray(x, dtype=np.float64)
+    with np.errstate(over="ignore", divide="ignore"):
+        y = np.where(x >= -2.22, np.exp(x) + 0.5, -1.0 / (x - sp.psi(1)))
+    for _ in range(5):
+        y = y - (sp.psi(y) - x) / sp.polygamma(1, y)
+    return y
+
+
+class GammaShape(Node):
+    """Maximum-likelihood point estimate of the shape parameter of gamma variables (gamma.py:273-335).  The children's
+    messages enter the bound as m0 a + m1 lgamma(a), so a = psi^-1(-m0 / m1): a root of the size of the hyper-parameter
+    plates, found on the host with the reference's Newton recipe; the moments [a, lgamma(a)] live on the device."""
+    moment_kind = "gamma_prior"
+
+    def __init__(self, m0=0, m1=0, plates=None, name=""):
+        super().__init__(dims=((), ()), plates=plates if plates is not None else (), name=name)
+        self._id = Node._id_counter
+        Node._id_counter += 1
+        self._m0, self._m1 = m0, m1
+        self.observed = False
+        self.initialize_from_value(1.0)
+
+    def _ids(self):
+        return [self._id]
+
+    def initialize_from_value(self, x):
+        self.u = list(gamma_prior_constant(np.asarray(x, dtype=np.float64) * np.ones(self.plates)).u)
+        self._version += 1
+
+    def get_moments(self):
+        return list(self.u)
+
+    def update(self, annealing=1.0):
+        m = self.message_from_children()
+        m0 = self._m0 + np.asarray(m[0])
+        m1 = self._m1 + np.asarray(m[1])
+        self.initialize_from_value(invpsi(-m0 / m1))
+
+    def lower_bound_contribution(self, ignore_masked=True):
+        return 0.0
+
+    def _update_mask(self):
+        mask = np.array(False)
+        for child, index in self.children:
+            mask = np.logical_or(mask, child._mask_to_parent(index))
+        self._set_mask(mask)

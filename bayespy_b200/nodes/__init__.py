@@ -2,7 +2,7 @@
 from ..engine.node import Node, Constant, Deterministic, Slice               # noqa: F401
 from ..engine.expfam import ExponentialFamily                                 # noqa: F401
 from ..engine.gaussian import GaussianARD                                     # noqa: F401
-from ..engine.gamma import Gamma                                              # noqa: F401
+from ..engine.gamma import Gamma, GammaShape                                              # noqa: F401
 from ..engine.dot import SumMultiply, Dot                                     # noqa: F401
 from ..engine.gaussian import Gaussian                                        # noqa: F401
 from ..engine.gaussian_gamma import GaussianGamma                            # noqa: F401

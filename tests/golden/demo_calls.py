@@ -7,6 +7,7 @@ CALLS = {
     "lssm": lambda m: m.demo(M=4, N=40, D=3, maxiter=8, rotate=True, plot=False, monitor=False),
     "mog": lambda m: m.run(N=40, K=4, D=2),          # also prints the integral of the predictive density over a grid
     "categorical": lambda m: m.run(M=10, D=3),
+    "gamma_shape": lambda m: m.run(),
     "hmm": lambda m: m.run(N=60, maxiter=5, plot=False),
     "annealing": lambda m: m.run(N=100, maxiter=15, plot=False),
     "pattern_search": lambda m: m.run(M=8, N=30, D_y=2, D=4, maxiter=15, plot=False),

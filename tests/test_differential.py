@@ -205,12 +205,20 @@ def chosen_and_complemented(N, rs):
     return [Y, z, x0, x1, x2, B, p]
 
 
+def gamma_shape_point_estimate(N, rs):
+    a = N.GammaShape(name="a")
+    b = N.Gamma(1e-5, 1e-5, name="b")
+    tau = N.Gamma(a, b, plates=(200,), name="tau")
+    tau.observe(rs.gamma(10.0, 1 / 20.0, size=200))
+    return [tau, a, b]
+
+
 MODELS = [chain_inputs_time_varying, gaussian_gamma_product, gaussian_gamma_times_constant_and_gaussian,
           gaussian_gamma_taken_by_index, gaussian_gamma_gated, mixture_with_gaussian_gamma_means,
           scalar_gaussian_gamma_over_plates, hidden_markov_chains_with_per_step_transitions,
           switching_state_space_model_selected_by_a_markov_chain, multinomial_counts_over_plates,
           poisson_counts_with_gamma_rates, sum_of_independent_gaussians, concatenated_groups, mixture_over_two_cluster_axes,
-          chosen_and_complemented, bernoulli_mixture, binomial_counts_over_plates]
+          chosen_and_complemented, gamma_shape_point_estimate, bernoulli_mixture, binomial_counts_over_plates]
 
 
 @pytest.mark.parametrize("model", MODELS, ids=[m.__name__ for m in MODELS])

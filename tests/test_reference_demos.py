@@ -48,8 +48,21 @@ def _load(path, name):
     return m
 
 
-@pytest.mark.parametrize("demo", sorted(CALLS))
+# demos whose nodes were added after the round's last GPU session: oracle backend only
+HOST_ONLY = {"gamma_shape"}
+
+
+@pytest.mark.parametrize("demo", sorted(HOST_ONLY))
+def test_reference_demo_runs_unchanged_on_the_oracle_backend(oracle_backend, as_bayespy, demo, capsys):
+    _run_and_compare(as_bayespy, demo, capsys)
+
+
+@pytest.mark.parametrize("demo", sorted(set(CALLS) - HOST_ONLY))
 def test_reference_demo_runs_unchanged(backend, as_bayespy, demo, capsys):
+    _run_and_compare(as_bayespy, demo, capsys)
+
+
+def _run_and_compare(as_bayespy, demo, capsys):
     m = _load(as_bayespy, demo)
     np.random.seed(1)
     CALLS[demo](m)
