@@ -1,6 +1,6 @@
 """The reference's documentation (doc/source/user_guide/*.rst, doc/source/examples/*.rst) as doctests, run twice: with
 the unmodified reference and with this package answering ``import bayespy`` (tests/doc_runner.py, one clean interpreter
-each).  Every example that passes with the reference must pass here; where a printed VB trajectory does not match the
+each, side by side).  Every example that passes with the reference must pass here; where a printed VB trajectory does not match the
 documentation text (the rotation optimiser inside the loop amplifies round-off, so the iteration at which the
 convergence test fires can move by one or two — it also does between the reference's own documentation and the
 reference run in this environment), the bounds printed here are compared with the bounds the reference prints.
@@ -17,7 +17,8 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 DOCS = "/root/reference/doc/source"
-FILES = sorted(f[len(DOCS) + 1:] for f in glob.glob(DOCS + "/user_guide/*.rst") + glob.glob(DOCS + "/examples/*.rst"))
+FILES = sorted(f[len(DOCS) + 1:] for f in glob.glob(DOCS + "/user_guide/*.rst") + glob.glob(DOCS + "/examples/*.rst")
+               if ">>>" in open(f).read())                       # the files that hold doctest examples
 
 # Examples whose expected text cannot match here for a reason that is not arithmetic.
 NOT_COMPARABLE = {
@@ -25,11 +26,15 @@ NOT_COMPARABLE = {
 }
 
 
-def _run(mode, rel):
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "doc_runner.py"), mode, os.path.join(DOCS, rel)],
-                         capture_output=True, text=True, timeout=900, cwd=ROOT)
-    lines = [l for l in out.stdout.splitlines() if l.startswith("DOCRESULT ")]
-    assert lines, out.stderr[-2000:]
+def _start(mode, rel):
+    return subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "doc_runner.py"), mode, os.path.join(DOCS, rel)],
+                            stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT)
+
+
+def _result(proc):
+    out, err = proc.communicate(timeout=900)
+    lines = [l for l in out.splitlines() if l.startswith("DOCRESULT ")]
+    assert lines, err[-2000:]
     return json.loads(lines[-1][len("DOCRESULT "):])
 
 
@@ -38,7 +43,8 @@ def _run(mode, rel):
 def test_documentation_examples_run_like_with_the_reference(rel):
     from oracle import make_ref
     make_ref.build()
-    ours, ref = _run("ours", rel), _run("reference", rel)
+    procs = _start("ours", rel), _start("reference", rel)          # the two interpreters run side by side
+    ours, ref = _result(procs[0]), _result(procs[1])
     assert ours["tries"] == ref["tries"]
     ref_failed = {l for l, _, _ in ref["failed"]}
     for lineno, source, got in ours["failed"]:
