@@ -305,3 +305,29 @@ def test_exponential_is_gamma_with_unit_shape(both):
         Q.update(repeat=3, verbose=False, tol=0)
         Ls.append(Q.L[:3].copy())
     np.testing.assert_array_equal(Ls[0], Ls[1])
+
+
+def test_density_queries_match_the_reference(both):
+    """``node.logpdf`` / ``pdf`` (expfamily.py:483-504) and ``Mixture.integrated_logpdf_from_parents`` (mixture.py:491-545)."""
+    rs = np.random.RandomState(8)
+    data, grid = rs.randn(30, 2), rs.randn(11, 2)
+    got = []
+    for N, I in both:
+        np.random.seed(5)
+        K = 3
+        al = N.Dirichlet(np.ones(K), name="al")
+        Z = N.Categorical(al, plates=(30,), name="Z")
+        Z.initialize_from_value(np.arange(30) % K)
+        mu = N.Gaussian(np.zeros(2), 1e-2 * np.identity(2), plates=(K,), name="mu")
+        L = N.Wishart(3.0, np.identity(2), plates=(K,), name="L")
+        Y = N.Mixture(Z, N.Gaussian, mu, L, name="Y")
+        Y.observe(data)
+        Q = I.VB(Y, mu, L, Z, al)
+        Q.update(repeat=3, verbose=False, tol=0)
+        zh = N.Categorical(al, name="zh")
+        Yh = N.Mixture(zh, N.Gaussian, mu, L, name="Yh")
+        got.append((np.asarray(Yh.integrated_logpdf_from_parents(grid, 0)),
+                    np.asarray(mu.logpdf(np.ones((K, 2)))),
+                    np.asarray(mu.pdf(np.zeros((K, 2))))))
+    for a, b in zip(got[0], got[1]):
+        np.testing.assert_allclose(b, a, rtol=1e-9)
