@@ -102,3 +102,73 @@ class Dirichlet(ExponentialFamily):
 
     def __str__(self):
         return "%s ~ Dirichlet(alpha)\n  alpha =\n%s" % (self.name, self.phi[0].numpy())
+
+
+class Concentration(Node):
+    """Maximum-likelihood point estimate of the concentration parameters of Dirichlet variables (dirichlet.py:234-330).
+    The children's messages are [sum <log p>, count]; with the optional regularisation ("prior" log-probability and
+    sample number) the estimate solves psi(a_k) = psi(sum a) + mean <log p_k> by the reference's fixed-point iteration —
+    a root over the hyper-parameter plates found on the host; the moments [a, lgamma(sum a) - sum lgamma(a)] live on
+    the device."""
+    moment_kind = "dirichlet_prior"
+
+    def __init__(self, D_, regularization=True, plates=None, name=""):
+        self.D = int(D_)
+        super().__init__(dims=((self.D,), ()), plates=plates if plates is not None else (), name=name)
+        self._id = Node._id_counter
+        Node._id_counter += 1
+        self.observed = False
+        if regularization is None or regularization is False:
+            regularization = [0, 0]
+        elif regularization is True:
+            regularization = [np.log(1 / self.D), 1]
+        if len(regularization) != 2:
+            raise ValueError("Regularization must 2-tuple")
+        self.regularization = regularization
+        self.initialize_from_value(np.ones(self.D))
+
+    def _ids(self):
+        return [self._id]
+
+    def initialize_from_value(self, x):
+        x = np.asarray(x, dtype=np.float64) * np.ones(tuple(self.plates) + (self.D,))
+        self.u = list(concentration_constant(x).u)
+        self._version += 1
+
+    def get_moments(self):
+        return list(self.u)
+
+    def update(self, annealing=1.0):
+        import scipy.special as sp
+        from .gamma import invpsi
+        m = self.message_from_children()
+        logp = np.asarray(m[0]) + self.regularization[0]
+        n = np.asarray(m[1]) + self.regularization[1]
+        mean_logp = logp / np.asarray(n)[..., None]
+        if np.any(np.isinf(mean_logp)):
+            raise ValueError("Cannot estimate DirichletConcentration because of infs. This means that there are "
+                             "numerically zero probabilities in the child Dirichlet node.")
+        a = np.ones(self.D)
+        da = np.inf
+        while np.any(np.abs(da / a) > 1e-5):
+            a_new = invpsi(sp.psi(np.sum(a, axis=-1, keepdims=True)) + mean_logp)
+            da = a_new - a
+            a = a_new
+        self.initialize_from_value(a)
+
+    def lower_bound_contribution(self, ignore_masked=True):
+        u0, u1 = np.asarray(self.u[0]), np.asarray(self.u[1])
+        return float(np.sum(np.sum(u0 * self.regularization[0], axis=-1) + u1 * self.regularization[1]))
+
+    def _update_mask(self):
+        mask = np.array(False)
+        for child, index in self.children:
+            mask = np.logical_or(mask, child._mask_to_parent(index))
+        self._set_mask(mask)
+
+
+DirichletConcentration = Concentration
+
+
+def BetaConcentration(**kwargs):
+    return Concentration(2, **kwargs)

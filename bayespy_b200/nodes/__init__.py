@@ -7,7 +7,7 @@ from ..engine.dot import SumMultiply, Dot                                     # 
 from ..engine.gaussian import Gaussian                                        # noqa: F401
 from ..engine.gaussian_gamma import GaussianGamma                            # noqa: F401
 from ..engine.wishart import Wishart                                          # noqa: F401
-from ..engine.dirichlet import Dirichlet                                      # noqa: F401
+from ..engine.dirichlet import Dirichlet, Concentration, DirichletConcentration, BetaConcentration                                      # noqa: F401
 from ..engine.categorical import Categorical                                  # noqa: F401
 from ..engine.multinomial import Multinomial                                # noqa: F401
 from ..engine.categorical_markov_chain import CategoricalMarkovChain      # noqa: F401

@@ -213,12 +213,21 @@ def gamma_shape_point_estimate(N, rs):
     return [tau, a, b]
 
 
+def dirichlet_concentration_point_estimate(N, rs):
+    conc = N.DirichletConcentration(4, name="conc")
+    p = N.Dirichlet(conc, plates=(25,), name="p")
+    X = N.Multinomial(40, p, name="X")
+    X.observe(np.array([rs.multinomial(40, pk) for pk in rs.dirichlet([2.0, 5.0, 1.0, 3.0], size=25)]))
+    return [X, p, conc]
+
+
 MODELS = [chain_inputs_time_varying, gaussian_gamma_product, gaussian_gamma_times_constant_and_gaussian,
           gaussian_gamma_taken_by_index, gaussian_gamma_gated, mixture_with_gaussian_gamma_means,
           scalar_gaussian_gamma_over_plates, hidden_markov_chains_with_per_step_transitions,
           switching_state_space_model_selected_by_a_markov_chain, multinomial_counts_over_plates,
           poisson_counts_with_gamma_rates, sum_of_independent_gaussians, concatenated_groups, mixture_over_two_cluster_axes,
-          chosen_and_complemented, gamma_shape_point_estimate, bernoulli_mixture, binomial_counts_over_plates]
+          chosen_and_complemented, gamma_shape_point_estimate, dirichlet_concentration_point_estimate,
+          bernoulli_mixture, binomial_counts_over_plates]
 
 
 @pytest.mark.parametrize("model", MODELS, ids=[m.__name__ for m in MODELS])
