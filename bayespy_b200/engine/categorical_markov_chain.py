@@ -191,10 +191,6 @@ class CategoricalMarkovChain(ExponentialFamily):
             self._as_categorical = CategoricalMarkovChainToCategorical(self, name=self.name)
         return self._as_categorical
 
-    def __getitem__(self, index):
-        # slicing addresses the time axis of the states seen as categorical variables (as the reference's converter does)
-        return self._to_categorical()[index]
-
 
 class CategoricalMarkovChainToCategorical(Deterministic):
     """The chain seen as N categorical variables plated over time (categorical_markov_chain.py:333-410): the state

@@ -221,13 +221,36 @@ def dirichlet_concentration_point_estimate(N, rs):
     return [X, p, conc]
 
 
+def masked_hidden_markov_chains_over_plates(N, rs):
+    Kc, T, P = 3, 8, 4
+    a0 = N.Dirichlet(np.ones(Kc), name="a0")
+    A = N.Dirichlet(np.ones(Kc), plates=(Kc,), name="A")
+    Zc = N.CategoricalMarkovChain(a0, A, states=T, plates=(P,), name="Zc")
+    mu = N.GaussianARD(0, 1e-1, plates=(Kc,), name="mu")
+    mu.initialize_from_value(rs.randn(Kc))
+    tau = N.Gamma(1e-2, 1e-2, plates=(Kc,), name="tau")
+    Y = N.Mixture(Zc, N.GaussianARD, mu, tau, name="Y")
+    Y.observe(rs.randn(P, T), mask=rs.rand(P, T) < 0.7)
+    return [Y, Zc, mu, tau, A, a0]
+
+
+def gaussians_gated_by_a_markov_chain(N, rs):
+    Kc, T = 3, 7
+    Zc = N.CategoricalMarkovChain([0.2, 0.3, 0.5], N.Dirichlet(np.ones(Kc), plates=(Kc,), name="A"), states=T, name="Zc")
+    B = N.GaussianARD(0, 1.0, shape=(2,), plates=(Kc,), name="B")
+    B.initialize_from_value(rs.randn(Kc, 2))
+    Y = N.GaussianARD(N.Gate(Zc, B, name="G"), 2.0, ndim=1, name="Y")
+    Y.observe(rs.randn(T, 2))
+    return [Y, Zc, B]
+
+
 MODELS = [chain_inputs_time_varying, gaussian_gamma_product, gaussian_gamma_times_constant_and_gaussian,
           gaussian_gamma_taken_by_index, gaussian_gamma_gated, mixture_with_gaussian_gamma_means,
           scalar_gaussian_gamma_over_plates, hidden_markov_chains_with_per_step_transitions,
           switching_state_space_model_selected_by_a_markov_chain, multinomial_counts_over_plates,
           poisson_counts_with_gamma_rates, sum_of_independent_gaussians, concatenated_groups, mixture_over_two_cluster_axes,
           chosen_and_complemented, gamma_shape_point_estimate, dirichlet_concentration_point_estimate,
-          bernoulli_mixture, binomial_counts_over_plates]
+          masked_hidden_markov_chains_over_plates, gaussians_gated_by_a_markov_chain, bernoulli_mixture, binomial_counts_over_plates]
 
 
 @pytest.mark.parametrize("model", MODELS, ids=[m.__name__ for m in MODELS])
