@@ -5,7 +5,7 @@ The test modules are imported from the staged, unmodified reference (oracle/_ref
 this package provides (GaussianARD, Gaussian, Gamma, Wishart, Dirichlet, Categorical, Mixture, SumMultiply, Take, Gate,
 GaussianMarkovChain, VaryingGaussianMarkovChain, GaussianGamma, ...) is swapped for ours inside the module, then single reference test
 methods are run as they are: their shapes, random inputs, assertions and finite-difference utilities
-(``assert_message_to_parent``, ``assert_moments``).  79 of the 86 node test methods (plus 22 on the oracle backend: test_{bernoulli,binomial,beta,poisson,concatenate}.py and TestConcatGaussian) and all 7 methods of vmp/tests (rotations, annealing) run green; the others are
+(``assert_message_to_parent``, ``assert_moments``).  101 of the 106 methods of the 19 node test modules (79 on both backends, 22 on the oracle backend) and all 7 methods of vmp/tests (rotations, annealing) run green; the others are
 listed with the reason in NOT_APPLICABLE (they need classes or internals outside the path).  Oracle backend on CPU,
 libbpk under -m gpu."""
 import importlib
